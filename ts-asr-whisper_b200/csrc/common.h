@@ -1,0 +1,44 @@
+// common.h -- host-side context, error plumbing and TMA tensor-map encoding shared by all kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dicow_b200.h"
+
+struct dicow_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  char err[512] = {0};
+  // cuTensorMapEncodeTiled fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
+  void* encode_tiled = nullptr;
+};
+
+namespace dicow {
+
+int set_error(dicow_ctx* ctx, int code, const char* fmt, ...);
+
+#define DICOW_CUDA_OK(ctx, expr)                                                                            \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return dicow::set_error((ctx), DICOW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                                          \
+  } while (0)
+
+#define DICOW_REQUIRE(ctx, cond, ...)                                              \
+  do {                                                                             \
+    if (!(cond)) return dicow::set_error((ctx), DICOW_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+// Encode a bf16 tiled tensor map with 128-byte swizzle and zero OOB fill.
+//   rank 2 or 3; dims[] innermost first (elements); strides_bytes[] for dims 1..rank-1; box[] elements.
+int make_tmap_bf16(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace dicow

@@ -1,0 +1,234 @@
+// elementwise.cu -- HBM-bound kernels of the encoder: fused FDDT + LayerNorm (warp-shuffle reductions),
+// mel-feature re-layout for the implicit-GEMM conv stem.
+//
+// FDDT (Frame-level Diarization-Dependent Transformation), reference src/models/dicow/FDDT.py:41-63:
+//     x'[b,t,:] = sum_{c in S,T,N,O} stno[b,c,t] * (w_c (.) x[b,t,:] + b_c)
+// In the reference this is ~15 eager element-wise launches per layer, each a full read+write of the residual
+// stream (encoder.py:205-206), followed by nn.LayerNorm (HF:modeling_whisper.py:393).  Here one kernel reads the
+// fp32 residual row once, applies FDDT, writes it back, and emits LayerNorm(x') in bf16 for the QKV GEMM.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dicow {
+namespace {
+
+struct FddtLnParams {
+  float* x;  // [rows, d] fp32 residual stream (updated in place when FDDT is applied)
+  int rows, d, T;
+  // FDDT (nullable => skipped)
+  const float* stno;  // [B, 4, T]
+  long long stno_bs;
+  const float* fddt_w;  // [4, d] (S,T,N,O) or NULL for bias-only FDDT
+  const float* fddt_b;  // [4, d]
+  // LayerNorm (nullable gamma => no LN outputs)
+  const float* gamma;
+  const float* beta;
+  float eps;
+  __nv_bfloat16* ln_bf16;  // [rows, d] or NULL
+  float* ln_f32;           // [rows, d] or NULL
+  __nv_bfloat16* x_bf16;   // [rows, d] bf16 copy of x' or NULL
+};
+
+// one warp per row; VPL float4 per lane (d <= 128 * VPL)
+template <int VPL>
+__global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= p.rows) return;
+  const int nvec = p.d >> 2;
+  float4 v[VPL];
+  float4* xrow = reinterpret_cast<float4*>(p.x + (long long)row * p.d);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < nvec) ? xrow[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (p.stno != nullptr) {
+    const int b = row / p.T, t = row - b * p.T;
+    float m[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) m[c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.T + t);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nvec) {
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.fddt_w != nullptr) w = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (p.fddt_w != nullptr) {
+            const float4 wc = __ldg(reinterpret_cast<const float4*>(p.fddt_w + (long long)c * p.d) + c4);
+            w.x = fmaf(m[c], wc.x, w.x), w.y = fmaf(m[c], wc.y, w.y), w.z = fmaf(m[c], wc.z, w.z),
+            w.w = fmaf(m[c], wc.w, w.w);
+          }
+          const float4 bc = __ldg(reinterpret_cast<const float4*>(p.fddt_b + (long long)c * p.d) + c4);
+          bb.x = fmaf(m[c], bc.x, bb.x), bb.y = fmaf(m[c], bc.y, bb.y), bb.z = fmaf(m[c], bc.z, bb.z),
+          bb.w = fmaf(m[c], bc.w, bb.w);
+        }
+        v[i].x = fmaf(v[i].x, w.x, bb.x), v[i].y = fmaf(v[i].y, w.y, bb.y);
+        v[i].z = fmaf(v[i].z, w.z, bb.z), v[i].w = fmaf(v[i].w, w.w, bb.w);
+        xrow[c4] = v[i];
+      }
+    }
+  }
+  if (p.x_bf16 != nullptr) {
+    uint2* o = reinterpret_cast<uint2*>(p.x_bf16 + (long long)row * p.d);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nvec) o[c4] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    }
+  }
+  if (p.gamma == nullptr) return;
+  // LayerNorm over d: two-pass (mean, then centred variance) in fp32, eps inside the sqrt (nn.LayerNorm)
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);  // padded lanes hold zeros
+  const float mean = warp_sum(s) / (float)p.d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nvec) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b2 * b2) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)p.d + p.eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+      float4 y;
+      y.x = fmaf((v[i].x - mean) * rstd, g.x, be.x);
+      y.y = fmaf((v[i].y - mean) * rstd, g.y, be.y);
+      y.z = fmaf((v[i].z - mean) * rstd, g.z, be.z);
+      y.w = fmaf((v[i].w - mean) * rstd, g.w, be.w);
+      if (p.ln_bf16 != nullptr)
+        reinterpret_cast<uint2*>(p.ln_bf16 + (long long)row * p.d)[c4] =
+            make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (p.ln_f32 != nullptr) reinterpret_cast<float4*>(p.ln_f32 + (long long)row * p.d)[c4] = y;
+    }
+  }
+}
+
+// input_features fp32 [B, C, F] -> channels-last bf16 [B, F + 2, C] with zero rows 0 and F+1
+// (the zero-padded buffer conv1's implicit GEMM reads; reference: encoder.py:167 nn.Conv1d(padding=1))
+__global__ void __launch_bounds__(256) features_to_cl_kernel(const float* __restrict__ in,
+                                                             __nv_bfloat16* __restrict__ out, int C, int F) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* src = in + (long long)b * C * F;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j, f = f0 + tx;
+    tile[ty + j][tx] = (c < C && f < F) ? src[(long long)c * F + f] : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + (long long)b * (F + 2) * C;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int f = f0 + ty + j, c = c0 + tx;
+    if (f < F && c < C) dst[(long long)(f + 1) * C + c] = __float2bfloat16_rn(tile[tx][ty + j]);
+  }
+  // zero pad rows (done by the blocks of the first f-tile)
+  if (blockIdx.x == 0) {
+    const int c = c0 + tx;
+    if (ty == 0 && c < C) {
+      dst[c] = __float2bfloat16_rn(0.f);
+      dst[(long long)(F + 1) * C + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// zero the two pad rows of a channels-last [B, T + 2, C] bf16 buffer (conv1 writes rows 1..T)
+__global__ void zero_pad_rows_kernel(__nv_bfloat16* buf, int T, int C) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  __nv_bfloat16* base = buf + (long long)b * (T + 2) * C;
+  base[c] = __float2bfloat16_rn(0.f);
+  base[(long long)(T + 1) * C + c] = __float2bfloat16_rn(0.f);
+}
+
+// fp32 -> bf16 cast (weights preparation, small tensors)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+}  // namespace
+}  // namespace dicow
+
+using namespace dicow;
+
+extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_fddt_ln_args_t), "dicow_fddt_layernorm: bad args struct");
+  DICOW_REQUIRE(ctx, a->x != nullptr && a->rows >= 1 && a->d >= 4 && (a->d % 4) == 0 && a->d <= 1280,
+                "dicow_fddt_layernorm: need x, rows>=1, d%%4==0, d<=1280 (got rows=%d d=%d)", a->rows, a->d);
+  DICOW_REQUIRE(ctx, a->stno == nullptr || (a->fddt_b != nullptr && a->T >= 1 && (a->rows % a->T) == 0),
+                "dicow_fddt_layernorm: FDDT needs fddt_b and rows %% T == 0");
+  DICOW_REQUIRE(ctx, a->gamma == nullptr || a->beta != nullptr, "dicow_fddt_layernorm: gamma without beta");
+  FddtLnParams p{};
+  p.x = a->x, p.rows = a->rows, p.d = a->d, p.T = a->T > 0 ? a->T : a->rows;
+  p.stno = a->stno, p.stno_bs = a->stno_batch_stride, p.fddt_w = a->fddt_w, p.fddt_b = a->fddt_b;
+  p.gamma = a->gamma, p.beta = a->beta, p.eps = a->eps;
+  p.ln_bf16 = reinterpret_cast<__nv_bfloat16*>(a->ln_out_bf16), p.ln_f32 = a->ln_out_f32;
+  p.x_bf16 = reinterpret_cast<__nv_bfloat16*>(a->x_out_bf16);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int rows_per_block = 8;
+  const int grid = ceil_div(a->rows, rows_per_block);
+  const int vpl = ceil_div(a->d, 128);
+  switch (vpl) {
+#define DICOW_CASE(V) \
+  case V: fddt_ln_kernel<V><<<grid, rows_per_block * 32, 0, stream>>>(p); break;
+    DICOW_CASE(1) DICOW_CASE(2) DICOW_CASE(3) DICOW_CASE(4) DICOW_CASE(5) DICOW_CASE(6) DICOW_CASE(7) DICOW_CASE(8)
+    DICOW_CASE(9) DICOW_CASE(10)
+#undef DICOW_CASE
+    default: return set_error(ctx, DICOW_ERR_UNSUPPORTED, "dicow_fddt_layernorm: d=%d unsupported", a->d);
+  }
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_features_to_channels_last(dicow_handle_t h, const float* in, void* out_bf16, int B, int C, int F,
+                                               void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, in && out_bf16 && B >= 1 && C >= 1 && F >= 1, "dicow_features_to_channels_last: bad args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid(ceil_div(F, 32), ceil_div(C, 32), B);
+  features_to_cl_kernel<<<grid, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), C, F);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_zero_pad_rows(dicow_handle_t h, void* buf_bf16, int B, int T, int C, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, buf_bf16 && B >= 1 && T >= 1 && C >= 1, "dicow_zero_pad_rows: bad args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid(ceil_div(C, 256), B);
+  zero_pad_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(buf_bf16), T, C);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_cast_f32_bf16(dicow_handle_t h, const float* in, void* out_bf16, int64_t n, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, in && out_bf16 && n >= 0, "dicow_cast_f32_bf16: bad args");
+  if (n == 0) return DICOW_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}

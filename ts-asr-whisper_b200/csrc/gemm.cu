@@ -1,0 +1,401 @@
+// gemm.cu -- persistent warp-specialised bf16 GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[b, m, n] = epilogue( sum_k A[b, m, k] * W[n, k] )      A, W bf16 K-major; fp32 accumulate in TMEM
+//
+// Roles (384 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule, N fastest so the
+// CTAs running concurrently share A rows through L2):
+//   warp 0 lane 0 : TMA producer  -- A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle, mbarrier tx
+//   warp 1 lane 0 : MMA issuer    -- 4 x tcgen05.mma (M128 x N(BN) x K16) per stage, tcgen05.commit frees the stage
+//   warp 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns -> epilogue overlaps next mainloop)
+//   warps 4..11   : epilogue      -- tcgen05.ld (thread == accumulator row), fused bias / GELU / residual / FDDT
+//
+// Replaces nn.Linear / nn.Conv1d calls of the reference (see include/dicow_b200.h for the call-site list).
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dicow {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int kNonEpiWarps = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = (kNonEpiWarps + kEpiWarps) * 32;
+
+struct GemmParams {
+  int nb, Mb, N, K, K1;
+  int tiles_m, tiles_n, total_tiles, kblocks;
+  const float* bias;
+  void* out;
+  long long ldo, out_bs;
+  int out_vec_ok;  // rows of `out` (and resid) are 16-byte aligned at every 32-column chunk
+  const float* resid;
+  long long ldr, resid_bs;
+  const float* gate;
+  const float* stno;
+  long long stno_bs;
+  const float* fddt_w;
+  const float* fddt_b;
+  const float* pos;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: both powers of two
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- epilogue on one 32-column chunk held in registers -------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int b, int m, int n, int ncols,
+                                               const float (&mask)[4]) {
+  // bias
+  if (p.bias != nullptr) {
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += __ldg(p.bias + n + j);
+    }
+  }
+  if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+
+  if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+    if (ncols == 32 && p.out_vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16(v[j], v[j + 1]);
+        q.y = pack_bf16(v[j + 2], v[j + 3]);
+        q.z = pack_bf16(v[j + 4], v[j + 5]);
+        q.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(o + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+    if constexpr (EPI == DICOW_EPI_RESIDUAL_F32) {
+      const float alpha = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.0f;
+      const float* r = p.resid + (long long)b * p.resid_bs + (long long)m * p.ldr + n;
+      if (ncols == 32 && p.out_vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 rv = *reinterpret_cast<const float4*>(r + j);
+          v[j] = fmaf(alpha, v[j], rv.x), v[j + 1] = fmaf(alpha, v[j + 1], rv.y);
+          v[j + 2] = fmaf(alpha, v[j + 2], rv.z), v[j + 3] = fmaf(alpha, v[j + 3], rv.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) v[j] = fmaf(alpha, v[j], r[j]);
+      }
+    }
+    if constexpr (EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
+      // FDDT.forward (src/models/dicow/FDDT.py:52-62): sum_c (w_c * x + b_c) * m_c, classes S,T,N,O
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < ncols) {
+          float w = 0.f, bb = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            w = fmaf(mask[c], __ldg(p.fddt_w + (long long)c * p.N + n + j), w);
+            bb = fmaf(mask[c], __ldg(p.fddt_b + (long long)c * p.N + n + j), bb);
+          }
+          float x = fmaf(v[j], w, bb);
+          if (p.pos != nullptr) x += __ldg(p.pos + (long long)m * p.N + n + j);
+          v[j] = x;
+        }
+      }
+    }
+    if (ncols == 32 && p.out_vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = v[j];
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    if (p.K1 > 0) tma_prefetch_desc(&tmA2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int b = mt / p.tiles_m;
+      const int m0 = (mt % p.tiles_m) * BM;
+      const int n0 = nt * BN;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int k0 = kb * BK;
+        if (p.K1 > 0 && k0 >= p.K1)
+          tma_load_3d(&tmA2, &full_bar[stage], sA, k0 - p.K1, m0, b);
+        else
+          tma_load_3d(&tmA, &full_bar[stage], sA, k0, m0, b);
+        tma_load_2d(&tmW, &full_bar[stage], sB, k0, n0, kEvictLast);
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = make_sdesc_sw128(a_addr + k * 32, 1024, 0);
+          const uint64_t db = make_sdesc_sw128(b_addr + k * 32, 1024, 0);
+          umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == p.kblocks - 1) umma_commit(&tfull_bar[acc]);
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp >= kNonEpiWarps) {
+    // ===================== epilogue =====================
+    const int e = warp - kNonEpiWarps;
+    const int quad = e & 3;  // == warp % 4: the TMEM lane quadrant this warp may access
+    const int half = e >> 2; // which half of the BN columns
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int b = mt / p.tiles_m;
+      const int m = (mt % p.tiles_m) * BM + quad * 32 + lane;
+      const int n_base = nt * BN + half * (BN / 2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const bool row_ok = m < p.Mb;
+
+      float mask[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mask[c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.Mb + m);
+        }
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int n = n_base + c;
+        const int ncols = min(32, p.N - n);
+        if (ncols <= 0) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk<EPI>(p, v, b, m, n, ncols, mask);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
+                const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kfn = gemm_bf16_kernel<BN, EPI>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = p.total_tiles < ctx->num_sms ? p.total_tiles : ctx->num_sms;
+  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+template <int BN>
+int dispatch_epi(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
+                 const GemmParams& p, cudaStream_t stream) {
+  switch (epi) {
+    case DICOW_EPI_BIAS_BF16: return launch_gemm<BN, DICOW_EPI_BIAS_BF16>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_BIAS_GELU_BF16: return launch_gemm<BN, DICOW_EPI_BIAS_GELU_BF16>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_RESIDUAL_F32: return launch_gemm<BN, DICOW_EPI_RESIDUAL_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_BIAS_F32: return launch_gemm<BN, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_GELU_FDDT_POS_F32:
+      return launch_gemm<BN, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: unknown epilogue %d", epi);
+  }
+}
+
+}  // namespace
+
+}  // namespace dicow
+
+using namespace dicow;
+
+extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_gemm_args_t),
+                "dicow_gemm_bf16: bad args struct (size %zu, expected %zu)", a ? a->struct_size : 0,
+                sizeof(dicow_gemm_args_t));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DICOW_REQUIRE(ctx, a->nb >= 1 && a->Mb >= 1 && a->N >= 1 && a->K >= 8, "dicow_gemm_bf16: bad shape nb=%d Mb=%d N=%d K=%d",
+                a->nb, a->Mb, a->N, a->K);
+  DICOW_REQUIRE(ctx, a->A && a->W && a->out, "dicow_gemm_bf16: null operand");
+  DICOW_REQUIRE(ctx, (a->lda % 8) == 0 && (a->ldw % 8) == 0 && (a->K % 8) == 0 && (a->a_batch_stride % 8) == 0,
+                "dicow_gemm_bf16: lda/ldw/K/a_batch_stride must be multiples of 8 elements (16-byte TMA strides)");
+  DICOW_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->W) % 16) == 0,
+                "dicow_gemm_bf16: A/W must be 16-byte aligned");
+  const bool split = a->A2 != nullptr;
+  if (split) {
+    DICOW_REQUIRE(ctx, a->K1 > 0 && a->K1 < a->K && (a->K1 % BK) == 0 && (a->lda2 % 8) == 0 &&
+                           (a->a2_batch_stride % 8) == 0 && (reinterpret_cast<uintptr_t>(a->A2) % 16) == 0,
+                  "dicow_gemm_bf16: bad split-K source (K1=%d)", a->K1);
+  }
+  if (a->epilogue == DICOW_EPI_RESIDUAL_F32) DICOW_REQUIRE(ctx, a->resid != nullptr, "dicow_gemm_bf16: resid is NULL");
+  if (a->epilogue == DICOW_EPI_GELU_FDDT_POS_F32)
+    DICOW_REQUIRE(ctx, a->stno && a->fddt_w && a->fddt_b, "dicow_gemm_bf16: FDDT epilogue needs stno/fddt_w/fddt_b");
+
+  const int BN = a->N >= 256 ? 256 : 128;
+  GemmParams p{};
+  p.nb = a->nb, p.Mb = a->Mb, p.N = a->N, p.K = a->K, p.K1 = split ? a->K1 : 0;
+  p.tiles_m = ceil_div(a->Mb, BM);
+  p.tiles_n = ceil_div(a->N, BN);
+  p.total_tiles = a->nb * p.tiles_m * p.tiles_n;
+  p.kblocks = ceil_div(a->K, BK);
+  p.bias = a->bias;
+  p.out = a->out, p.ldo = a->ldo, p.out_bs = a->out_batch_stride;
+  p.resid = a->resid, p.ldr = a->ldr, p.resid_bs = a->resid_batch_stride, p.gate = a->gate;
+  p.stno = a->stno, p.stno_bs = a->stno_batch_stride, p.fddt_w = a->fddt_w, p.fddt_b = a->fddt_b, p.pos = a->pos;
+  const bool out_is_bf16 = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16;
+  const int vec = out_is_bf16 ? 8 : 4;
+  bool vec_ok = (a->ldo % vec) == 0 && (a->out_batch_stride % vec) == 0 &&
+                (reinterpret_cast<uintptr_t>(a->out) % 16) == 0;
+  if (a->bias) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(a->bias) % 16) == 0;
+  if (a->epilogue == DICOW_EPI_RESIDUAL_F32)
+    vec_ok = vec_ok && (a->ldr % 4) == 0 && (a->resid_batch_stride % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(a->resid) % 16) == 0;
+  p.out_vec_ok = vec_ok ? 1 : 0;
+
+  CUtensorMap tmA, tmA2, tmW;
+  const int Ka = split ? a->K1 : a->K;
+  {
+    uint64_t dims[3] = {(uint64_t)Ka, (uint64_t)a->Mb, (uint64_t)a->nb};
+    uint64_t bs = a->nb > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * (uint64_t)a->Mb;
+    uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(ctx, &tmA, a->A, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (split) {
+    uint64_t dims[3] = {(uint64_t)(a->K - a->K1), (uint64_t)a->Mb, (uint64_t)a->nb};
+    uint64_t bs = a->nb > 1 ? (uint64_t)a->a2_batch_stride : (uint64_t)a->lda2 * (uint64_t)a->Mb;
+    uint64_t strides[2] = {(uint64_t)a->lda2 * 2, bs * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(ctx, &tmA2, a->A2, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)BN};
+    int rc = make_tmap_bf16(ctx, &tmW, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (BN == 256) return dispatch_epi<256>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
+  return dispatch_epi<128>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
+}

@@ -1,0 +1,114 @@
+"""ctypes binding of libdicow_b200.so (see include/dicow_b200.h).
+
+The library is the only compute backend: if it is missing or the device is not sm_100 every op raises --
+there is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdicow_b200.so")
+
+# dicow_epilogue_t
+EPI_BIAS_BF16 = 0
+EPI_BIAS_GELU_BF16 = 1
+EPI_RESIDUAL_F32 = 2
+EPI_BIAS_F32 = 3
+EPI_GELU_FDDT_POS_F32 = 4
+
+
+class DicowError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_batch_stride", C.c_int64),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("a2_batch_stride", C.c_int64),
+        ("K1", C.c_int32),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("nb", C.c_int32), ("Mb", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_batch_stride", C.c_int64),
+        ("epilogue", C.c_int32),
+        ("resid", C.c_void_p), ("ldr", C.c_int64), ("resid_batch_stride", C.c_int64),
+        ("gate", C.c_void_p),
+        ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64),
+        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+_handles: dict[int, C.c_void_p] = {}
+
+
+def load_library() -> C.CDLL:
+    """dlopen the shared library and declare prototypes (no GPU needed)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DicowError(
+                f"{LIB_PATH} is not built. Run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                "There is no fallback path.")
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
+        _lib = lib
+        return lib
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp = C.c_void_p
+    lib.dicow_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.dicow_create.restype = C.c_int
+    lib.dicow_destroy.argtypes = [vp]
+    lib.dicow_destroy.restype = C.c_int
+    lib.dicow_last_error.argtypes = [vp]
+    lib.dicow_last_error.restype = C.c_char_p
+    lib.dicow_check.argtypes = [vp]
+    lib.dicow_check.restype = C.c_int
+    lib.dicow_abi_version.argtypes = []
+    lib.dicow_abi_version.restype = C.c_int
+    lib.dicow_gemm_bf16.argtypes = [vp, C.POINTER(GemmArgs), vp]
+    lib.dicow_gemm_bf16.restype = C.c_int
+    for name, argtypes in _EXTRA_PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+# name -> argtypes for the remaining int-returning entry points; filled by ops modules' needs
+_EXTRA_PROTOS: dict[str, list] = {}
+
+EXPORTED_SYMBOLS = [
+    "dicow_create", "dicow_destroy", "dicow_last_error", "dicow_check", "dicow_abi_version",
+    "dicow_gemm_bf16",
+]
+
+
+def handle(device: int) -> C.c_void_p:
+    """Per-device library handle (created lazily)."""
+    lib = load_library()
+    h = _handles.get(device)
+    if h is None:
+        out = C.c_void_p()
+        rc = lib.dicow_create(int(device), C.byref(out))
+        if rc != 0:
+            raise DicowError(
+                f"dicow_create(device={device}) failed with status {rc} "
+                "(2 = CUDA error / no device, 4 = not an sm_100 GPU). No fallback path exists.")
+        _handles[device] = out
+        h = out
+    return h
+
+
+def check(rc: int, h: C.c_void_p, what: str) -> None:
+    if rc != 0:
+        msg = load_library().dicow_last_error(h)
+        raise DicowError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
