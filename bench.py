@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- encoder-forward utterances/s (30 s @ 16 kHz windows), whisper-large-v3-turbo + FDDT (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one DiCoWEncoder forward over one batch of B=32 synthetic utterances per GPU (BASELINE configs[1]):
+log-mel-shaped input_features [B, 128, 3000] fp32 + soft STNO masks [B, 4, 1500], random-init weights of the
+large-v3-turbo architecture with FDDT parameters perturbed off their identity init.  Utterances are independent, so
+N GPUs run N replicas with no data-path collective ("weak" scaling: B per GPU fixed).
+
+  value  : utt/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e    : utt/s through the public API with pinned HOST buffers: H2D of features + masks and D2H of
+           last_hidden_state inside the timed region, every step
+  roofline: the tcgen05 GEMM kernel family (dominant: ~60 % of the step), algorithmic FLOPs / CUDA-event time per
+           launch measured live in the timed steps, against the measured cuBLAS bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the reference's algorithm (oracle/dicow_oracle.py -- the reference itself is Python
+           over HF transformers and /root/reference does not exist on the GPU box) in fp32 on all host cores, on a
+           bounded sample (B=1 forwards) of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encoder-fwd utterances/sec (30s@16kHz) large-v3-turbo+FDDT"
+GFLOP_PER_UTT = 2273.8  # conv stem 17.7 + 32 x (QKVO 19.661 + QK^T/PV 11.520 + MLP 39.322)
+
+
+def turbo_config():
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    return DiCoWConfig(vocab_size=51866, num_mel_bins=128, d_model=1280, encoder_layers=32, encoder_attention_heads=20,
+                       decoder_layers=4, decoder_attention_heads=20, encoder_ffn_dim=5120, decoder_ffn_dim=5120,
+                       max_source_positions=1500, max_target_positions=448, use_fddt=True, use_pre_pos_fddt=True,
+                       fddt_is_diagonal=True, non_target_fddt_value=0.5, fddt_init="suppressive", ctc_weight=0.0,
+                       activation_function="gelu")
+
+
+def perturb_(enc, gen_device):
+    """Move FDDT / LayerNorm parameters off their identity init -- seeded."""
+    g = torch.Generator(device=gen_device).manual_seed(1234)
+    with torch.no_grad():
+        for name, p in enc.named_parameters():
+            if "fddt" in name:
+                if name.endswith("weight"):
+                    p.copy_(torch.rand(p.shape, generator=g, device=gen_device) + 0.5)
+                else:
+                    p.copy_(torch.randn(p.shape, generator=g, device=gen_device) * 0.1)
+            elif "layer_norm.weight" in name:
+                p.copy_(torch.rand(p.shape, generator=g, device=gen_device) * 0.4 + 0.8)
+            elif "embed_positions" in name:
+                p.copy_(torch.randn(p.shape, generator=g, device=gen_device) * 0.1)
+
+
+def make_inputs(B, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    feats = (torch.randn(B, 128, 3000, generator=g) * 0.4 - 0.3).clamp_(-1.0, 1.5)
+    stno = torch.softmax(3.0 * torch.randn(B, 4, 1500, generator=g), dim=1)
+    if pin:
+        feats, stno = feats.pin_memory(), stno.pin_memory()
+    return feats.to(device), stno.to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_reference(steps, warmup, B=1, threads=None):
+    """The reference's CPU implementation of the path (oracle port, fp32, SDPA, all host threads)."""
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    dm = synth.LARGE_V3_TURBO
+    g = torch.Generator().manual_seed(7)
+    p = {}
+    for k, shp in synth.param_shapes(dm, decoder=False).items():
+        if "lm_head" in k or "subsample" in k or "additional" in k:
+            continue
+        if k.endswith("weight") and len(shp) >= 2:
+            p[k] = torch.randn(shp, generator=g) * (1.0 / (shp[1] * (shp[2] if len(shp) > 2 else 1)) ** 0.5)
+        elif "fddt" in k and k.endswith("weight"):
+            p[k] = torch.rand(shp, generator=g) + 0.5
+        elif "layer_norm.weight" in k:
+            p[k] = torch.rand(shp, generator=g) * 0.4 + 0.8
+        else:
+            p[k] = torch.randn(shp, generator=g) * 0.1
+    feats, stno = make_inputs(B, 100)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.encoder_forward(p, dm, feats, stno)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return {"utt_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads,
+            "sample": f"{len(times)} forward(s) of B={B} utterance(s), fp32, torch {torch.__version__} SDPA, "
+                      f"{warmup} warm-up"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step (BASELINE configs[1]: 32)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "whisper-large-v3-turbo + FDDT encoder forward, batch=32 synthetic 30s, 1xB200 "
+                          "(BASELINE configs[1])", "batch_per_gpu": args.batch, "mel_bins": 128, "frames": 3000,
+              "layers": 32, "d_model": 1280, "parallelism": f"replicas x{world}, no data-path collective",
+              "l2": "per-step working set (2.5 GB weights+activations per layer pass) >> 126 MB L2; 3 input batches rotate"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        W = max(1, min(args.warmup, 1))
+        K = max(1, min(args.steps, 3))
+        r = time_reference(K, W, B=1)
+        line = {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": "utt/s", "n_gpus": args.gpus,
+                "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["utt_per_s"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch.distributed as dist
+    from ts_asr_whisper_b200 import ops
+    from ts_asr_whisper_b200.modeling import DiCoWEncoder
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU: the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    with torch.device(dev):
+        enc = DiCoWEncoder(turbo_config())
+    perturb_(enc, dev)
+    enc.eval()
+    B = args.batch
+    host = [make_inputs(B, 10 + i, pin=True) for i in range(3)]
+    resident = [(f.to(dev), s.to(dev)) for f, s in host]
+    out_host = torch.empty(B, 1500, 1280, dtype=torch.float32).pin_memory()
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    d2h = out_host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        enc(resident[i % 3][0], stno_mask=resident[i % 3][1])
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.timing_log = []
+    l0 = ops.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        enc(resident[i % 3][0], stno_mask=resident[i % 3][1])
+    e1.record()
+    barrier()
+    launches = ops.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    log, ops.timing_log = ops.timing_log, None
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed: end to end through the public API with host buffers ----
+    for i in range(2):
+        enc(host[i][0].to(dev, non_blocking=True), stno_mask=host[i][1].to(dev, non_blocking=True))
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        f, s = host[i % 3]
+        o = enc(f.to(dev, non_blocking=True), stno_mask=s.to(dev, non_blocking=True)).last_hidden_state
+        out_host.copy_(o, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+        "fallback B200_PROFILING.md sustained"
+    by_kind = {}
+    for kind, fl, a, b in log:
+        d = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    kern = {k: {"launches": v[2], "ms_per_step": v[1] / args.steps,
+                "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[0] else None} for k, v in by_kind.items()}
+    gemm = by_kind.get("gemm", [0.0, 1.0, 1])
+    achieved = gemm[0] / (gemm[1] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,*> (tcgen05 GEMM family: QKV/out/fc1/fc2/conv)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": gemm[2] // max(1, args.steps),
+                "gflop_per_launch_avg": gemm[0] / max(1, gemm[2]) / 1e9,
+                "us_per_launch_avg": 1e3 * gemm[1] / max(1, gemm[2]),
+                "share_of_step": gemm[1] / ms if ms else None}
+    utts = world * B * args.steps
+    value = utts / (ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
+            "whole_step": {"tflops_per_gpu": value / world * GFLOP_PER_UTT / 1e3,
+                           "frac_of_sustained_peak": value / world * GFLOP_PER_UTT / 1e3 / peak_tf}}
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_reference(2, 1, B=1)
+        line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,70 @@ typedef struct {
 
 DICOW_API int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused FDDT + LayerNorm over the fp32 residual stream (HBM-bound, one warp per row, warp-shuffle reductions).
+ *   x'[b,t,:] = sum_c stno[b,c,t] * (w_c (.) x[b,t,:] + b_c)          src/models/dicow/FDDT.py:52-62
+ *   ln        = LayerNorm(x') * gamma + beta  (eps inside the sqrt)     HF:modeling_whisper.py:393,403; encoder.py:228
+ * Replaces the ~15 eager element-wise launches of src/models/dicow/encoder.py:205-206 plus nn.LayerNorm.
+ * x is updated in place when stno != NULL.  Any of the outputs may be NULL.  fddt_w == NULL selects the bias-only
+ * FDDT variant (FDDT.py:43-51).  rows = B*T; row r uses mask column (r / T, :, r % T).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  float* x; /* [rows, d] fp32 */
+  int32_t rows, d, T;
+  const float* stno; /* [B, 4, T] fp32 or NULL (no FDDT) */
+  int64_t stno_batch_stride;
+  const float* fddt_w; /* [4, d] fp32 rows S,T,N,O, or NULL */
+  const float* fddt_b; /* [4, d] */
+  const float* gamma;  /* [d] or NULL (no LayerNorm) */
+  const float* beta;
+  float eps;
+  void* ln_out_bf16; /* [rows, d] bf16 or NULL */
+  float* ln_out_f32; /* [rows, d] fp32 or NULL */
+  void* x_out_bf16;  /* [rows, d] bf16 copy of x' or NULL */
+} dicow_fddt_ln_args_t;
+
+DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* args, void* stream);
+
+/* input_features fp32 [B, C, F] -> zero-padded channels-last bf16 [B, F + 2, C] (the buffer conv1's implicit GEMM
+ * reads; src/models/dicow/encoder.py:167 nn.Conv1d(padding=1)). */
+DICOW_API int dicow_features_to_channels_last(dicow_handle_t h, const float* in, void* out_bf16, int B, int C, int F,
+                                              void* stream);
+/* zero rows 0 and T+1 of a channels-last [B, T + 2, C] bf16 buffer */
+DICOW_API int dicow_zero_pad_rows(dicow_handle_t h, void* buf_bf16, int B, int T, int C, void* stream);
+/* fp32 -> bf16 cast (weight preparation) */
+DICOW_API int dicow_cast_f32_bf16(dicow_handle_t h, const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-head attention, head_dim 64, flash-style on tcgen05: S = Q K^T into TMEM, online softmax (one thread per
+ * query row), P (bf16) V accumulated in TMEM.  softmax(Q K^T) V with NO extra scaling (the reference scales q by
+ * hd^-0.5 before the product, HF:modeling_whisper.py:305-310 -- folded into the q projection weights) and no padding
+ * mask; causal = 1 applies the decoder's lower-triangular mask (key <= query + Tk - Tq).
+ * Replaces HF WhisperAttention's SDPA call (HF:modeling_whisper.py:342-352) for the encoder self-attention, the
+ * SE-DiCoW enrollment cross-attention (src/models/dicow/layers.py:156-160) and decoder prefill.
+ *
+ * Element (b, t, h, e) of Q lives at Q + b*q_batch_stride + t*q_row_stride + h*64 + e (elements, bf16); likewise
+ * K, V (kv strides) and the output.  All strides must be multiples of 8 elements, bases 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  const void* Q;
+  const void* K;
+  const void* V;
+  void* out; /* bf16 */
+  int32_t B, H, Tq, Tk;
+  int64_t q_row_stride, q_batch_stride;
+  int64_t kv_row_stride, kv_batch_stride;
+  int64_t o_row_stride, o_batch_stride;
+  int32_t causal;
+  int32_t variant; /* 0 = default; 1 = stage P through shared memory instead of TMEM (debug / comparison) */
+} dicow_attention_args_t;
+
+DICOW_API int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args_t* args, void* stream);
+/* debug aid: clock64 stamps of one CTA's KV loop are written to buf ([steps][8] int64); NULL disables */
+DICOW_API int dicow_debug_set_attention_profile(dicow_handle_t h, void* buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,91 @@
+"""GPU parity of the B200 DiCoWEncoder (C-ABI kernels) against the CPU oracle on identical synthetic weights/inputs.
+Tolerance: north_star's bf16 bar -- max |err| <= 2e-2 x max |ref| (GEMM/attention operands are bf16, fp32 accumulate,
+fp32 residual stream; the oracle is fp32 throughout)."""
+import dataclasses
+
+import pytest
+import torch
+
+from oracle import dicow_oracle as orc
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+def build_encoder(dm: synth.Dims, dev):
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling import DiCoWEncoder
+    cfg = DiCoWConfig(**dm.hf_kwargs())
+    enc = DiCoWEncoder(cfg)
+    params = synth.make_params(dm, decoder=False)
+    sd = {k[len("model.encoder."):]: torch.from_numpy(v) for k, v in params.items()}
+    enc.load_state_dict(sd, strict=True)
+    return enc.to(dev).eval(), orc.to_torch(params)
+
+
+def rel_err(out, ref):
+    return ((out.float().cpu() - ref).abs().max() / ref.abs().max()).item()
+
+
+CASES = {
+    # whisper-tiny + FDDT (BASELINE configs[0]) with the CTC head
+    "tiny": (synth.WHISPER_TINY, 2, False),
+    # large-v3-turbo dims, 2 layers (full-depth runs are covered by bench.py / smoke at B200 sizes)
+    "turbo2": (dataclasses.replace(synth.LARGE_V3_TURBO, enc_layers=2, vocab=2047), 1, False),
+    # SE-DiCoW: enrollment stream + 2 SCB layers, tiny dims
+    "tiny_se": (dataclasses.replace(synth.WHISPER_TINY, use_enrollments=True, scb_layers=2, vocab=1000), 2, True),
+    # the golden miniature (odd T, every feature on)
+    "mini": (synth.GOLDEN_MINI, 2, True),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_encoder_matches_oracle(name):
+    dm, B, use_enr = CASES[name]
+    dev = torch.device("cuda:0")
+    enc, p = build_encoder(dm, dev)
+    feats = torch.from_numpy(synth.make_features(name, B, dm.n_mels, 2 * dm.T))
+    stno = torch.from_numpy(synth.make_stno(name, B, dm.T, "soft", pad_tail=11))
+    enr = None
+    if use_enr:
+        enr = {"input_features": torch.from_numpy(synth.make_features(name + "e", B, dm.n_mels, 2 * dm.T)),
+               "stno_mask": torch.from_numpy(synth.make_stno(name + "e", B, dm.T, "hard"))}
+    with torch.no_grad():
+        ref = orc.encoder_forward(p, dm, feats, stno, enr)
+        ref_logits = orc.ctc_logits(p, dm, ref)
+    enr_d = {k: v.to(dev) for k, v in enr.items()} if enr else None
+    out = enc(feats.to(dev), stno_mask=stno.to(dev), enrollments=enr_d)
+    e1 = rel_err(out.last_hidden_state, ref)
+    lo = enc(feats.to(dev), stno_mask=stno.to(dev), enrollments=enr_d, return_logits=True)
+    e2 = rel_err(lo.logits, ref_logits)
+    torch.cuda.synchronize()
+    print(f"{name}: hidden rel err {e1:.3e}, ctc logits rel err {e2:.3e}")
+    assert out.last_hidden_state.shape == ref.shape and lo.logits.shape == ref_logits.shape
+    assert e1 < BF16_TOL and e2 < BF16_TOL
+
+
+def test_golden_fixture_on_gpu():
+    """CUDA path vs the committed reference outputs (tests/golden/mini_model.npz) directly."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mini_model.npz"))
+    dm = synth.GOLDEN_MINI
+    dev = torch.device("cuda:0")
+    enc, _ = build_encoder(dm, dev)
+    feats = torch.from_numpy(synth.make_features("g0", 2, dm.n_mels, 2 * dm.T)).to(dev)
+    stno = torch.from_numpy(synth.make_stno("g0", 2, dm.T, "soft", pad_tail=7)).to(dev)
+    enr = {"input_features": torch.from_numpy(synth.make_features("g0e", 2, dm.n_mels, 2 * dm.T)).to(dev),
+           "stno_mask": torch.from_numpy(synth.make_stno("g0e", 2, dm.T, "hard")).to(dev)}
+    out = enc(feats, stno_mask=stno, enrollments=enr).last_hidden_state
+    assert rel_err(out, torch.from_numpy(g["enc_se"])) < BF16_TOL
+    lg = enc(feats, stno_mask=stno, enrollments=enr, return_logits=True).logits
+    assert rel_err(lg, torch.from_numpy(g["ctc_logits_se"])) < BF16_TOL
+
+
+def test_no_cpu_fallback():
+    from ts_asr_whisper_b200 import ops
+    dm = synth.GOLDEN_MINI
+    enc, _ = build_encoder(dm, torch.device("cuda:0"))
+    with pytest.raises(ops.DicowError):
+        enc.cpu()(torch.zeros(1, dm.n_mels, 2 * dm.T), stno_mask=torch.zeros(1, 4, dm.T))

@@ -1,0 +1,104 @@
+"""GPU parity of the individual C-ABI kernels against plain torch fp32 on the same bf16-rounded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ts_asr_whisper_b200 import ops as _ops
+    return _ops
+
+
+def _rel_err(out, ref):
+    return ((out.float() - ref.float()).abs().max() / ref.float().abs().max().clamp(min=1e-6)).item()
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 256, 64, 0), (1500, 1280, 1280, 0), (3000, 5120, 1280, 1),
+                                       (3000, 1280, 5120, 2), (777, 1003, 320, 3), (100, 384, 384, 0)])
+def test_gemm(ops, M, N, K, epi):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev, generator=g)
+    ref = A.float() @ W.float().t() + b
+    if epi == ops.EPI_BIAS_BF16:
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.gemm(A, W, out, epilogue=epi, bias=b)
+    elif epi == ops.EPI_BIAS_GELU_BF16:
+        ref = torch.nn.functional.gelu(ref)
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.gemm(A, W, out, epilogue=epi, bias=b)
+    elif epi == ops.EPI_BIAS_F32:
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+        ops.gemm(A, W, out, epilogue=epi, bias=b)
+    else:
+        res = torch.randn(M, N, device=dev, generator=g)
+        gate = torch.tensor([0.7], device=dev)
+        ref = res + torch.tanh(gate) * ref
+        out = res.clone()
+        ops.gemm(A, W, out, epilogue=epi, bias=b, resid=out, gate=gate)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    assert _rel_err(out, ref) < (1e-2 if out.dtype == torch.bfloat16 else 1e-4)
+
+
+@pytest.mark.parametrize("d,T,B", [(384, 1500, 2), (1280, 1500, 2), (128, 50, 3)])
+def test_fddt_layernorm(ops, d, T, B):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(d)
+    x = torch.randn(B, T, d, device=dev, generator=g)
+    stno = torch.softmax(3 * torch.randn(B, 4, T, device=dev, generator=g), dim=1)
+    fw = torch.rand(4, d, device=dev, generator=g) + 0.5
+    fb = torch.randn(4, d, device=dev, generator=g) * 0.1
+    gam = torch.rand(d, device=dev, generator=g) + 0.5
+    bet = torch.randn(d, device=dev, generator=g) * 0.1
+    xr = sum((x * fw[c] + fb[c]) * stno[:, c, :, None] for c in range(4))
+    lnr = torch.nn.functional.layer_norm(xr, (d,), gam, bet, 1e-5)
+    xx = x.clone()
+    ln_b = torch.empty(B, T, d, device=dev, dtype=torch.bfloat16)
+    ln_f = torch.empty(B, T, d, device=dev)
+    xb = torch.empty(B, T, d, device=dev, dtype=torch.bfloat16)
+    ops.fddt_layernorm(xx, T=T, stno=stno, fddt_w=fw, fddt_b=fb, gamma=gam, beta=bet, ln_out_bf16=ln_b,
+                       ln_out_f32=ln_f, x_out_bf16=xb)
+    torch.cuda.synchronize()
+    assert (xx - xr).abs().max().item() < 1e-5
+    assert (ln_f - lnr).abs().max().item() < 1e-4
+    assert _rel_err(ln_b, lnr) < 1e-2
+    assert _rel_err(xb, xr) < 1e-2
+    # LayerNorm only
+    x2 = x.clone()
+    ops.fddt_layernorm(x2, gamma=gam, beta=bet, ln_out_f32=ln_f)
+    torch.cuda.synchronize()
+    assert torch.equal(x2, x)
+    assert (ln_f - torch.nn.functional.layer_norm(x, (d,), gam, bet, 1e-5)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("variant", [0, 1, 6, 8])
+@pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 6, 1500, 1500, False), (1, 20, 1500, 1500, False),
+                                              (3, 2, 50, 50, False), (2, 4, 100, 100, True), (2, 3, 37, 1500, False),
+                                              (1, 2, 448, 448, True), (2, 2, 128, 256, False)])
+def test_attention(ops, variant, B, H, Tq, Tk, causal):
+    dev = torch.device("cuda:0")
+    d = H * 64
+    g = torch.Generator(device=dev).manual_seed(Tq * 7 + Tk + H)
+    # fused layout [B, T, 3d] as written by the QKV projection
+    q = (torch.randn(B, Tq, d, device=dev, generator=g) * 0.4).bfloat16()
+    kv = (torch.randn(B, Tk, 2 * d, device=dev, generator=g) * 1.2).bfloat16()
+    out = torch.full((B, Tq, d), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.attention(q, kv, kv[:, :, d:], out, B=B, H=H, Tq=Tq, Tk=Tk, q_row_stride=d, q_batch_stride=Tq * d,
+                  kv_row_stride=2 * d, kv_batch_stride=Tk * 2 * d, o_row_stride=d, o_batch_stride=Tq * d,
+                  causal=causal, variant=variant)
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Tq, H, 64).transpose(1, 2)
+    kf = kv[:, :, :d].float().view(B, Tk, H, 64).transpose(1, 2)
+    vf = kv[:, :, d:].float().view(B, Tk, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2)
+    if causal:
+        mask = torch.ones(Tq, Tk, device=dev, dtype=torch.bool).tril(Tk - Tq)
+        s = s.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B, Tq, d)
+    assert not torch.isnan(out.float()).any()
+    assert _rel_err(out, ref) < 2e-2

@@ -15,6 +15,7 @@ struct dicow_ctx {
   char err[512] = {0};
   // cuTensorMapEncodeTiled fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
   void* encode_tiled = nullptr;
+  void* attn_prof = nullptr;  // debug: see dicow_debug_set_attention_profile
 };
 
 namespace dicow {

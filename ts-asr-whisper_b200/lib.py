@@ -42,6 +42,31 @@ class GemmArgs(C.Structure):
     ]
 
 
+class FddtLnArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("x", C.c_void_p),
+        ("rows", C.c_int32), ("d", C.c_int32), ("T", C.c_int32),
+        ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64),
+        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("eps", C.c_float),
+        ("ln_out_bf16", C.c_void_p), ("ln_out_f32", C.c_void_p), ("x_out_bf16", C.c_void_p),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("Q", C.c_void_p), ("K", C.c_void_p), ("V", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32),
+        ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("causal", C.c_int32), ("variant", C.c_int32),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 _handles: dict[int, C.c_void_p] = {}
@@ -77,18 +102,23 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_abi_version.restype = C.c_int
     lib.dicow_gemm_bf16.argtypes = [vp, C.POINTER(GemmArgs), vp]
     lib.dicow_gemm_bf16.restype = C.c_int
-    for name, argtypes in _EXTRA_PROTOS.items():
-        fn = getattr(lib, name)
-        fn.argtypes = argtypes
-        fn.restype = C.c_int
+    lib.dicow_fddt_layernorm.argtypes = [vp, C.POINTER(FddtLnArgs), vp]
+    lib.dicow_attention_bf16.argtypes = [vp, C.POINTER(AttentionArgs), vp]
+    lib.dicow_features_to_channels_last.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.dicow_zero_pad_rows.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.dicow_cast_f32_bf16.argtypes = [vp, vp, vp, C.c_int64, vp]
+    lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)  # raises AttributeError if the library does not export a declared symbol
+        if name != "dicow_last_error":
+            fn.restype = C.c_int
 
 
-# name -> argtypes for the remaining int-returning entry points; filled by ops modules' needs
-_EXTRA_PROTOS: dict[str, list] = {}
-
+# every entry point include/dicow_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTED_SYMBOLS = [
     "dicow_create", "dicow_destroy", "dicow_last_error", "dicow_check", "dicow_abi_version",
-    "dicow_gemm_bf16",
+    "dicow_gemm_bf16", "dicow_fddt_layernorm", "dicow_attention_bf16", "dicow_features_to_channels_last",
+    "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile",
 ]
 
 

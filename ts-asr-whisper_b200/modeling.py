@@ -1,0 +1,468 @@
+"""Host-side mirror of the reference's model classes for the hot path (encoder side).
+
+Same class names, constructor arguments, ``forward`` signatures and state_dict parameter names as
+  src/models/dicow/encoder.py  (DiCoWEncoder)           src/models/dicow/FDDT.py   (FDDT)
+  src/models/dicow/layers.py   (CustomDiagonalLinear, Gate, CrossAttentionEnrollBlock, SpeakerCommunicationBlock)
+so checkpoints, name-keyword freezing (src/models/containers.py:80-97) and HF ``generate()``'s signature
+inspection keep working -- but the modules are parameter containers only: every FLOP of ``forward`` is a call into
+libdicow_b200.so (ops.py).  There is no eager / CPU fallback: without the library or an sm_100 GPU, forward raises.
+
+Inference (no-grad) path; the residual stream is fp32, GEMM / attention operands bf16 with fp32 accumulation, which
+is the reference's own bf16-autocast numerics (SURVEY.md Appendix A "Training numerics", section 7 "Mixed-precision").
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+from transformers.modeling_outputs import BaseModelOutput, CausalLMOutput
+
+from . import ops
+from .configuration import DiCoWConfig
+
+_FDDT_ORDER = ("silence", "target", "non_target", "overlap")  # STNO channel order (FDDT.py:56-62)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers (names == reference state_dict)
+# ----------------------------------------------------------------------------------------------------------------
+class CustomDiagonalLinear(nn.Module):
+    """weight/bias [d]; inits follow src/models/dicow/layers.py:49-71."""
+
+    def __init__(self, d_model: int, bias: bool = True, init_eye_val: float = 0.0, fddt_init: Optional[str] = None):
+        super().__init__()
+        self.init_eye_val = init_eye_val
+        self.fddt_init = fddt_init
+        self.weight = nn.Parameter(torch.empty(d_model))
+        self.bias = nn.Parameter(torch.zeros(d_model)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        with torch.no_grad():
+            bound = math.sqrt(3.0 / self.weight.numel())
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.zero_()
+            if self.fddt_init == "non-disturbing":
+                self.weight.fill_(1.0)
+            elif self.fddt_init == "suppressive":
+                self.weight.fill_(self.init_eye_val)
+
+
+class FDDT(nn.Module):
+    """Diagonal Frame-level Diarization-Dependent Transformation parameters (src/models/dicow/FDDT.py:6-40)."""
+
+    def __init__(self, d_model: int, non_target_rate: float = 0.01, fddt_init: Optional[str] = None,
+                 use_silence: bool = True, use_target: bool = True, use_overlap: bool = True,
+                 use_non_target: bool = True):
+        super().__init__()
+        self.d_model = d_model
+        if use_target:
+            self.target_linear = CustomDiagonalLinear(d_model, True, 1.0, fddt_init)
+        if use_non_target:
+            self.non_target_linear = CustomDiagonalLinear(d_model, True, non_target_rate, fddt_init)
+        if use_overlap:
+            self.overlap_linear = CustomDiagonalLinear(d_model, True, 1.0, fddt_init)
+        if use_silence:
+            self.silence_linear = CustomDiagonalLinear(d_model, True, non_target_rate, fddt_init)
+
+    def tables(self):
+        """([4, d] weights, [4, d] biases) in STNO order; a disabled class is the identity (FDDT.py:54-62)."""
+        ref = next(self.parameters())
+        ws, bs = [], []
+        for c in _FDDT_ORDER:
+            lin = getattr(self, c + "_linear", None)
+            ws.append(lin.weight if lin is not None else torch.ones(self.d_model, device=ref.device))
+            bs.append(lin.bias if lin is not None else torch.zeros(self.d_model, device=ref.device))
+        return torch.stack(ws).float().contiguous(), torch.stack(bs).float().contiguous()
+
+
+class Gate(nn.Module):
+    def __init__(self, items: int, init_val: float = 0.0):
+        super().__init__()
+        self.init_val = init_val
+        self.gate = nn.Parameter(torch.full((items,), init_val))
+
+    def reset_parameters(self) -> None:
+        with torch.no_grad():
+            self.gate.fill_(self.init_val)
+
+
+class AttentionParams(nn.Module):
+    """q/k/v/out projections named like HF WhisperAttention (k_proj has no bias, HF:modeling_whisper.py:281-284)."""
+
+    def __init__(self, d: int):
+        super().__init__()
+        self.k_proj = nn.Linear(d, d, bias=False)
+        self.v_proj = nn.Linear(d, d, bias=True)
+        self.q_proj = nn.Linear(d, d, bias=True)
+        self.out_proj = nn.Linear(d, d, bias=True)
+
+
+class EncoderLayerParams(nn.Module):
+    def __init__(self, d: int, ffn: int):
+        super().__init__()
+        self.self_attn = AttentionParams(d)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, ffn)
+        self.fc2 = nn.Linear(ffn, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+
+
+class CrossAttentionEnrollBlock(nn.Module):
+    """Parameters of src/models/dicow/layers.py:113-143 (ffn is a Sequential so the names are ffn.0 / ffn.3)."""
+
+    def __init__(self, config: DiCoWConfig):
+        super().__init__()
+        d, ffn = config.d_model, config.encoder_ffn_dim
+        self.cross_attn = AttentionParams(d)
+        self.cross_gate = Gate(1, init_val=0.0)
+        self.ffn = nn.Sequential(nn.Linear(2 * d, ffn), nn.Identity(), nn.Identity(), nn.Linear(ffn, d), nn.Identity())
+        with torch.no_grad():  # layers.py:95-110: start as "copy the first half through"
+            nn.init.xavier_uniform_(self.ffn[0].weight, gain=1e-1)
+            self.ffn[0].weight[:d, :d] += torch.eye(d)
+            self.ffn[0].bias.zero_()
+            nn.init.xavier_uniform_(self.ffn[3].weight, gain=1e-1)
+            self.ffn[3].weight[:, :d] += torch.eye(d)
+            self.ffn[3].bias.zero_()
+
+
+class SpeakerCommunicationBlock(nn.Module):
+    def __init__(self, config: DiCoWConfig):
+        super().__init__()
+        self.streams = 2
+        self.cae = CrossAttentionEnrollBlock(config)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# prepared (bf16 / fused) weights
+# ----------------------------------------------------------------------------------------------------------------
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return ops.cast_bf16(t.detach().float())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _prep_attention(att: AttentionParams, fuse_qkv: bool = True) -> Dict[str, torch.Tensor]:
+    """bf16 projection weights; hd^-0.5 = 0.125 (exact in bf16 for head_dim 64) is folded into Wq / bq, which is the
+    reference's ``q_proj(x) * scaling`` (HF:modeling_whisper.py:310) bit for bit in exact arithmetic."""
+    d = att.q_proj.weight.shape[0]
+    sc = 64 ** -0.5
+    wq, bq = att.q_proj.weight.detach().float() * sc, att.q_proj.bias.detach().float() * sc
+    wk = att.k_proj.weight.detach().float()
+    wv, bv = att.v_proj.weight.detach().float(), att.v_proj.bias.detach().float()
+    out = {"wo": _bf16(att.out_proj.weight), "bo": _f32(att.out_proj.bias)}
+    if fuse_qkv:
+        out["wqkv"] = _bf16(torch.cat([wq, wk, wv], 0))
+        out["bqkv"] = torch.cat([bq, torch.zeros(d, device=bq.device), bv]).contiguous()
+    else:
+        out["wq"], out["bq"] = _bf16(wq), bq.contiguous()
+        out["wkv"] = _bf16(torch.cat([wk, wv], 0))
+        out["bkv"] = torch.cat([torch.zeros(d, device=bq.device), bv]).contiguous()
+    return out
+
+
+def _conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight [Cout, Cin, 3] -> GEMM weight [Cout, 3*Cin] with k-major taps (matches the overlapping-row view
+    of the zero-padded channels-last activation buffer)."""
+    return _bf16(w.detach().float().permute(0, 2, 1).reshape(w.shape[0], -1))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# DiCoWEncoder
+# ----------------------------------------------------------------------------------------------------------------
+class DiCoWEncoder(nn.Module):
+    """B200 implementation of src/models/dicow/encoder.py:10-246 (same attributes, forward signature, outputs)."""
+
+    config_class = DiCoWConfig
+    main_input_name = "input_features"
+
+    def __init__(self, config: DiCoWConfig):
+        super().__init__()
+        config.check_supported()
+        self.config = config
+        d = config.d_model
+        self.ctc_weight = config.ctc_weight
+        self.conv1 = nn.Conv1d(config.num_mel_bins, d, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv1d(d, d, kernel_size=3, stride=2, padding=1)
+        self.embed_positions = nn.Embedding(config.max_source_positions, d)
+        self.embed_positions.requires_grad_(False)
+        self.layers = nn.ModuleList([EncoderLayerParams(d, config.encoder_ffn_dim)
+                                     for _ in range(config.encoder_layers)])
+        self.layer_norm = nn.LayerNorm(d)
+        if config.additional_self_attention_layer and self.ctc_weight > 0.0:
+            self.additional_self_attention_layer = AttentionParams(d)
+        if config.pre_ctc_sub_sample and self.ctc_weight > 0.0:
+            self.subsample_conv1 = nn.Conv1d(d, d, kernel_size=3, stride=2, padding=1, bias=False)
+            self.subsample_conv2 = nn.Conv1d(d, d, kernel_size=3, stride=2, padding=1, bias=False)
+        if self.ctc_weight > 0.0:
+            self.lm_head = nn.Linear(d, config.vocab_size + 1, bias=False)
+        if config.use_fddt:
+            n = config.apply_fddt_to_n_layers if config.apply_fddt_to_n_layers != -1 else len(self.layers)
+            kw = dict(fddt_init=config.fddt_init, use_silence=config.fddt_use_silence,
+                      use_target=config.fddt_use_target, use_overlap=config.fddt_use_overlap,
+                      use_non_target=config.fddt_use_non_target)
+            self.fddts = nn.ModuleList([FDDT(d, non_target_rate=1.0, **kw) for _ in range(n)])
+            if config.use_pre_pos_fddt:
+                self.initial_fddt = FDDT(d, non_target_rate=config.non_target_fddt_value, **kw)
+        if config.use_enrollments and config.scb_layers is not None:
+            self.ca_enrolls = nn.ModuleList([SpeakerCommunicationBlock(config) for _ in range(config.scb_layers)])
+        self.first_task_token = config.vocab_size - 30 * 50 - 1 - 6
+        self._prepared: Optional[dict] = None
+        self._prepared_key = None
+        self.attention_variant = 0
+
+    # ---- reference API surface -----------------------------------------------------------------------------
+    def get_max_len(self) -> int:  # encoder.py:137-138
+        return self.config.max_source_positions * self.conv1.stride[0] * self.conv2.stride[0]
+
+    def get_output_embeddings(self):
+        return None
+
+    def get_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """CTC loss exactly as encoder.py:108-135 (library op; the fused CUDA CTC kernel is SURVEY K13, not built yet)."""
+        if labels.max() >= self.config.vocab_size:
+            raise ValueError(f"Label values must be <= vocab_size: {self.config.vocab_size}")
+        if self.config.remove_timestamps_from_ctc:
+            labels = torch.nn.utils.rnn.pad_sequence([lab[lab < self.first_task_token] for lab in labels],
+                                                     padding_value=-100).T
+        input_lengths = torch.full((logits.shape[0],), logits.shape[1], device=logits.device)
+        target_lengths = (labels >= 0).sum(-1)
+        log_probs = nn.functional.log_softmax(logits, dim=-1, dtype=torch.float32).transpose(0, 1)
+        return nn.functional.ctc_loss(log_probs, labels, input_lengths, target_lengths, blank=logits.shape[-1] - 1,
+                                      reduction=self.config.ctc_loss_reduction, zero_infinity=True)
+
+    # ---- weight preparation ----------------------------------------------------------------------------------
+    def _cache_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_cache(self) -> None:
+        self._prepared = None
+
+    def prepare(self) -> dict:
+        """bf16 / fused copies of the weights for the kernels; rebuilt when a parameter tensor changed."""
+        key = self._cache_key()
+        if self._prepared is not None and key == self._prepared_key:
+            return self._prepared
+        cfg = self.config
+        dev = self.conv1.weight.device
+        d = cfg.d_model
+        w: dict = {}
+        w["conv1_w"], w["conv1_b"] = _conv_weight(self.conv1.weight), _f32(self.conv1.bias)
+        w["conv2_w"], w["conv2_b"] = _conv_weight(self.conv2.weight), _f32(self.conv2.bias)
+        w["pos"] = _f32(self.embed_positions.weight)
+        if cfg.use_fddt and cfg.use_pre_pos_fddt:
+            w["fddt0"] = self.initial_fddt.tables()
+        else:  # identity FDDT for the conv2 epilogue
+            w["fddt0"] = (torch.ones(4, d, device=dev), torch.zeros(4, d, device=dev))
+        w["fddt"] = [f.tables() for f in self.fddts] if cfg.use_fddt else []
+        layers = []
+        for lyr in self.layers:
+            e = _prep_attention(lyr.self_attn)
+            e["ln1_g"], e["ln1_b"] = _f32(lyr.self_attn_layer_norm.weight), _f32(lyr.self_attn_layer_norm.bias)
+            e["ln2_g"], e["ln2_b"] = _f32(lyr.final_layer_norm.weight), _f32(lyr.final_layer_norm.bias)
+            e["w1"], e["b1"] = _bf16(lyr.fc1.weight), _f32(lyr.fc1.bias)
+            e["w2"], e["b2"] = _bf16(lyr.fc2.weight), _f32(lyr.fc2.bias)
+            layers.append(e)
+        w["layers"] = layers
+        w["lnf_g"], w["lnf_b"] = _f32(self.layer_norm.weight), _f32(self.layer_norm.bias)
+        if hasattr(self, "ca_enrolls"):
+            scbs = []
+            for blk in self.ca_enrolls:
+                e = _prep_attention(blk.cae.cross_attn, fuse_qkv=False)
+                e["w1"], e["b1"] = _bf16(blk.cae.ffn[0].weight), _f32(blk.cae.ffn[0].bias)
+                e["w2"], e["b2"] = _bf16(blk.cae.ffn[3].weight), _f32(blk.cae.ffn[3].bias)
+                e["gate"] = _f32(blk.cae.cross_gate.gate)
+                scbs.append(e)
+            w["scb"] = scbs
+        if hasattr(self, "additional_self_attention_layer"):
+            w["ctc_attn"] = _prep_attention(self.additional_self_attention_layer)
+        if hasattr(self, "subsample_conv1"):
+            w["sub1"] = _conv_weight(self.subsample_conv1.weight)
+            w["sub2"] = _conv_weight(self.subsample_conv2.weight)
+        if hasattr(self, "lm_head"):
+            w["lm_head"] = _bf16(self.lm_head.weight)
+        self._prepared, self._prepared_key = w, key
+        return w
+
+    # ---- kernels sequences -----------------------------------------------------------------------------------
+    def _self_attention(self, e: dict, xin_bf16: torch.Tensor, Bx: int, T: int, out: torch.Tensor,
+                        o_row_stride: int, o_batch_stride: int) -> None:
+        """fused QKV projection + attention; writes bf16 context into ``out`` (pointer/strides given)."""
+        d, H = self.config.d_model, self.config.encoder_attention_heads
+        qkv = torch.empty(Bx * T, 3 * d, dtype=torch.bfloat16, device=xin_bf16.device)
+        ops.gemm(xin_bf16, e["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=e["bqkv"])
+        ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], out, B=Bx, H=H, Tq=T, Tk=T, q_row_stride=3 * d,
+                      q_batch_stride=T * 3 * d, kv_row_stride=3 * d, kv_batch_stride=T * 3 * d,
+                      o_row_stride=o_row_stride, o_batch_stride=o_batch_stride, variant=self.attention_variant)
+
+    def _scb(self, e: dict, x: torch.Tensor, xb: torch.Tensor, B: int, T: int) -> None:
+        """SE-DiCoW speaker communication block (layers.py:145-170) on the interleaved [2B, T, d] streams:
+        x (fp32 residual, target rows updated in place), xb = bf16 copy of x."""
+        d, H = self.config.d_model, self.config.encoder_attention_heads
+        dev = x.device
+        q = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+        kv = torch.empty(B, T, 2 * d, dtype=torch.bfloat16, device=dev)
+        # q from the target rows (even), k/v from the enrollment rows (odd) -- no LayerNorm
+        ops.gemm(xb, e["wq"], q, epilogue=ops.EPI_BIAS_BF16, bias=e["bq"], nb=B, Mb=T, lda=d,
+                 a_batch_stride=2 * T * d, ldo=d, out_batch_stride=T * d)
+        ops.gemm(xb[1], e["wkv"], kv, epilogue=ops.EPI_BIAS_BF16, bias=e["bkv"], nb=B, Mb=T, lda=d,
+                 a_batch_stride=2 * T * d, ldo=2 * d, out_batch_stride=T * 2 * d)
+        ctx = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+        ops.attention(q, kv, kv[:, :, d:], ctx, B=B, H=H, Tq=T, Tk=T, q_row_stride=d, q_batch_stride=T * d,
+                      kv_row_stride=2 * d, kv_batch_stride=T * 2 * d, o_row_stride=d, o_batch_stride=T * d,
+                      variant=self.attention_variant)
+        ao = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(ctx, e["wo"], ao, epilogue=ops.EPI_BIAS_BF16, bias=e["bo"])
+        # ffn.0 over cat([attn_out, q_stream]) without materialising the concat: split-K over two sources
+        hdn = torch.empty(B, T, e["w1"].shape[0], dtype=torch.bfloat16, device=dev)
+        ops.gemm(ao, e["w1"], hdn, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"], nb=B, Mb=T, K=2 * d, lda=d,
+                 a_batch_stride=T * d, A2=xb, lda2=d, a2_batch_stride=2 * T * d, K1=d, ldo=hdn.shape[-1],
+                 out_batch_stride=T * hdn.shape[-1])
+        # target rows: x += tanh(gate) * (ffn.3(hdn))
+        ops.gemm(hdn, e["w2"], x, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], nb=B, Mb=T, lda=hdn.shape[-1],
+                 a_batch_stride=T * hdn.shape[-1], ldo=d, out_batch_stride=2 * T * d, resid=x, ldr=d,
+                 resid_batch_stride=2 * T * d, gate=e["gate"])
+
+    def possibly_update_last_hidden_states(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        """encoder.py:87-106: extra self-attention (replaces the hidden state), two stride-2 convs.  fp32 in/out."""
+        B, T, _ = hidden_states.shape
+        return self._ctc_neck(self.prepare(), ops.cast_bf16(hidden_states), B, T).float()
+
+    def _ctc_neck(self, w: dict, hb: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """bf16 [B, T, d] -> bf16 [B, T', d] (T' = T/4 with sub-sampling)."""
+        cfg = self.config
+        d = cfg.d_model
+        dev = hb.device
+        sub = "sub1" in w
+        if "ctc_attn" in w:
+            e = w["ctc_attn"]
+            ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=dev)
+            self._self_attention(e, hb.view(B * T, d), B, T, ctx, d, T * d)
+            if sub:  # out_proj writes straight into the zero-padded channels-last buffer of the first conv
+                buf = torch.empty(B, T + 2, d, dtype=torch.bfloat16, device=dev)
+                ops.zero_pad_rows(buf)
+                ops.gemm(ctx, e["wo"], buf[:, 1:], epilogue=ops.EPI_BIAS_BF16, bias=e["bo"], nb=B, Mb=T, lda=d,
+                         a_batch_stride=T * d, ldo=d, out_batch_stride=(T + 2) * d)
+            else:
+                buf = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+                ops.gemm(ctx, e["wo"], buf, epilogue=ops.EPI_BIAS_BF16, bias=e["bo"])
+                return buf
+        elif sub:
+            buf = torch.zeros(B, T + 2, d, dtype=torch.bfloat16, device=dev)
+            buf[:, 1:T + 1] = hb.view(B, T, d)
+        else:
+            return hb.view(B, T, d)
+        T1 = (T + 2 - 3) // 2 + 1
+        buf1 = torch.empty(B, T1 + 2, d, dtype=torch.bfloat16, device=dev)
+        ops.zero_pad_rows(buf1)
+        ops.gemm(buf, w["sub1"], buf1[:, 1:], epilogue=ops.EPI_BIAS_BF16, nb=B, Mb=T1, K=3 * d, lda=2 * d,
+                 a_batch_stride=(T + 2) * d, ldo=d, out_batch_stride=(T1 + 2) * d)
+        T2 = (T1 + 2 - 3) // 2 + 1
+        out = torch.empty(B, T2, d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(buf1, w["sub2"], out, epilogue=ops.EPI_BIAS_BF16, nb=B, Mb=T2, K=3 * d, lda=2 * d,
+                 a_batch_stride=(T1 + 2) * d, ldo=d, out_batch_stride=T2 * d)
+        return out
+
+    def ctc_logits_from_hidden(self, hidden_bf16: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        w = self.prepare()
+        neck = self._ctc_neck(w, hidden_bf16, B, T)
+        Tp = neck.shape[1]
+        V1 = w["lm_head"].shape[0]
+        logits = torch.empty(B, Tp, V1, dtype=torch.float32, device=neck.device)
+        ops.gemm(neck.view(B * Tp, -1), w["lm_head"], logits.view(B * Tp, V1), epilogue=ops.EPI_BIAS_F32)
+        return logits
+
+    @torch.no_grad()
+    def forward(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False, enrollments=None):
+        cfg = self.config
+        if output_attentions or output_hidden_states or head_mask is not None:
+            raise NotImplementedError("output_attentions / output_hidden_states / head_mask are not produced by the "
+                                      "fused B200 path")
+        if enrollments is not None:  # encoder.py:152-154
+            input_features = torch.stack((input_features, enrollments["input_features"]), dim=1).flatten(0, 1)
+            stno_mask = torch.stack((stno_mask, enrollments["stno_mask"]), dim=1).flatten(0, 1)
+        expected = self.get_max_len()
+        if input_features.shape[-1] != expected:  # encoder.py:156-160
+            raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
+                             f"{input_features.shape[-1]}. Make sure to pad the input mel features to {expected}.")
+        if not input_features.is_cuda:
+            raise ops.DicowError("DiCoWEncoder.forward needs CUDA tensors on an sm_100 device (no CPU fallback)")
+        w = self.prepare()
+        dev = input_features.device
+        d, F = cfg.d_model, input_features.shape[-1]
+        Bx, T = input_features.shape[0], F // 2
+        feats = input_features.float().contiguous()
+        if cfg.use_fddt:
+            if stno_mask is None:
+                raise ValueError("stno_mask is required when use_fddt is set")
+            stno = stno_mask.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            stno = None
+        # ---- stem: conv1+GELU, conv2+GELU, initial FDDT, + positions (encoder.py:167-179) ----
+        a0 = torch.empty(Bx, F + 2, cfg.num_mel_bins, dtype=torch.bfloat16, device=dev)
+        ops.features_to_channels_last(feats, a0)
+        a1 = torch.empty(Bx, F + 2, d, dtype=torch.bfloat16, device=dev)
+        ops.zero_pad_rows(a1)
+        C = cfg.num_mel_bins
+        ops.gemm(a0, w["conv1_w"], a1[:, 1:], epilogue=ops.EPI_BIAS_GELU_BF16, bias=w["conv1_b"], nb=Bx, Mb=F,
+                 K=3 * C, lda=C, a_batch_stride=(F + 2) * C, ldo=d, out_batch_stride=(F + 2) * d)
+        x = torch.empty(Bx, T, d, dtype=torch.float32, device=dev)
+        if stno is not None and cfg.use_pre_pos_fddt:
+            stno0 = stno
+        else:  # identity transform: class 0 weight 1
+            stno0 = torch.zeros(Bx, 4, T, dtype=torch.float32, device=dev)
+            stno0[:, 0] = 1.0
+        fw0, fb0 = w["fddt0"]
+        ops.gemm(a1, w["conv2_w"], x, epilogue=ops.EPI_GELU_FDDT_POS_F32, bias=w["conv2_b"], nb=Bx, Mb=T, K=3 * d,
+                 lda=2 * d, a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, stno=stno0,
+                 stno_batch_stride=4 * T, fddt_w=fw0, fddt_b=fb0, pos=w["pos"])
+        del a0, a1
+        # ---- layers (encoder.py:191-223) ----
+        n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers) else 0
+        if n_scb and (Bx % 2):
+            raise ValueError("use_enrollments expects interleaved target/enrollment streams (even batch)")
+        ffn = cfg.encoder_ffn_dim
+        for i, e in enumerate(w["layers"]):
+            rows = Bx * T
+            ln = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            fd = w["fddt"][i] if (cfg.use_fddt and i < len(w["fddt"])) else None
+            if i < n_scb:
+                xb = torch.empty(Bx, T, d, dtype=torch.bfloat16, device=dev)
+                ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+                                   fddt_b=fd[1] if fd else None, x_out_bf16=xb)
+                self._scb(w["scb"][i], x, xb, Bx // 2, T)
+                if i == n_scb - 1:  # encoder.py:210-213: the enrollment stream is no longer needed
+                    x = x.view(Bx // 2, 2, T, d)[:, 0].contiguous()
+                    stno = stno.view(Bx // 2, 2, 4, T)[:, 0].contiguous() if stno is not None else None
+                    Bx //= 2
+                    rows = Bx * T
+                    ln = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+                ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln)
+            else:
+                ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+                                   fddt_b=fd[1] if fd else None, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln)
+            ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            self._self_attention(e, ln, Bx, T, ctx, d, T * d)
+            xf = x.view(rows, d)
+            ops.gemm(ctx, e["wo"], xf, epilogue=ops.EPI_RESIDUAL_F32, bias=e["bo"], resid=xf)
+            ops.fddt_layernorm(x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=ln)
+            hdn = torch.empty(rows, ffn, dtype=torch.bfloat16, device=dev)
+            ops.gemm(ln, e["w1"], hdn, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
+            ops.gemm(hdn, e["w2"], xf, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=xf)
+            del hdn, ctx, ln
+        # ---- final LayerNorm (encoder.py:228) ----
+        out = torch.empty(Bx, T, d, dtype=torch.float32, device=dev)
+        out_bf16 = torch.empty(Bx, T, d, dtype=torch.bfloat16, device=dev) if return_logits else None
+        ops.fddt_layernorm(x, gamma=w["lnf_g"], beta=w["lnf_b"], ln_out_f32=out, ln_out_bf16=out_bf16)
+        if return_logits:  # encoder.py:233-240
+            logits = self.ctc_logits_from_hidden(out_bf16, Bx, T)
+            return CausalLMOutput(loss=None, logits=logits, hidden_states=out)
+        if return_dict is False:
+            return (out,)
+        return BaseModelOutput(last_hidden_state=out)
