@@ -160,12 +160,38 @@ typedef struct {
   int64_t kv_row_stride, kv_batch_stride;
   int64_t o_row_stride, o_batch_stride;
   int32_t causal;
-  int32_t variant; /* 0 = default; 1 = stage P through shared memory instead of TMEM (debug / comparison) */
+  int32_t variant; /* 0 = default (two query tiles per CTA in ping-pong, 2 of every 8 exponentials evaluated as a
+                      polynomial on the FMA pipe); 1, 2, 3 = same with 0, 4, 6 of 8; 16+ = single-tile comparison kernels */
 } dicow_attention_args_t;
 
 DICOW_API int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args_t* args, void* stream);
 /* debug aid: clock64 stamps of one CTA's KV loop are written to buf ([steps][8] int64); NULL disables */
 DICOW_API int dicow_debug_set_attention_profile(dicow_handle_t h, void* buf);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Whisper log-mel front-end (n_fft 400, hop 160, periodic Hann, centred reflect-padded STFT, last frame dropped, power,
+ * mel filterbank, log10(max(., 1e-10)), floor at (max over the whole recording - 8), (x + 4) / 4).
+ * Replaces WhisperFeatureExtractor._torch_extract_fbank_features (HF:models/whisper/feature_extraction_whisper.py:135-164)
+ * as called at src/data/local_datasets.py:208-214; one batch row = one (possibly multi-window) recording, zero-padded
+ * by the caller to n_pad samples (a multiple of 480000 in the reference; any multiple of 160 here).
+ * out[b, m, t], t < n_pad / 160.  attention_mask[b, t] = (t * 160 < lengths[b])  (feature_extraction_whisper.py:328-337).
+ * workspace: B * 4 bytes of device scratch (per-recording running max).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  const float* audio; /* [B, n_pad] fp32 */
+  int64_t audio_batch_stride;
+  int32_t B;
+  int64_t n_pad;
+  const int64_t* lengths;   /* [B] valid samples per recording (device) or NULL */
+  const float* mel_filters; /* [201, n_mels] fp32 (WhisperFeatureExtractor.mel_filters) */
+  int32_t n_mels;
+  float* out;              /* [B, n_mels, n_pad / 160] fp32 */
+  int32_t* attention_mask; /* [B, n_pad / 160] or NULL */
+  void* workspace;
+} dicow_logmel_args_t;
+
+DICOW_API int dicow_logmel(dicow_handle_t h, const dicow_logmel_args_t* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -79,11 +79,16 @@ extern "C" int dicow_create(int device, dicow_handle_t* out) {
     return DICOW_ERR_CUDA;
   }
   ctx->encode_tiled = fn;
+  if (mel_tables_create(ctx) != DICOW_OK) {
+    delete ctx;
+    return DICOW_ERR_CUDA;
+  }
   *out = ctx;
   return DICOW_OK;
 }
 
 extern "C" int dicow_destroy(dicow_handle_t h) {
+  if (h != nullptr && h->mel_tables != nullptr) cudaFree(h->mel_tables);
   delete h;
   return DICOW_OK;
 }

@@ -19,6 +19,7 @@
 // and the decoder's teacher-forced attention.
 #include <math.h>
 
+#include "attention_common.h"
 #include "common.h"
 #include "ptx.cuh"
 
@@ -37,13 +38,6 @@ constexpr uint32_t S_COL = 0;    // 128 fp32 columns
 constexpr uint32_t O_COL = 128;  // 64 fp32 columns
 constexpr uint32_t P_COL = 192;  // 64 columns = 128 bf16 (P through TMEM)
 constexpr uint32_t TMEM_COLS = 256;
-
-struct AttnParams {
-  int B, H, Tq, Tk, causal;
-  __nv_bfloat16* out;
-  long long o_rs, o_bs;
-  long long* prof;  // debug: per-step clock64 stamps of one CTA (dicow_debug_set_attention_profile), else NULL
-};
 
 template <bool P_SMEM>
 struct AttnSmem {
@@ -405,14 +399,13 @@ extern "C" int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args
   p.o_rs = a->o_row_stride, p.o_bs = a->o_batch_stride;
   p.prof = reinterpret_cast<long long*>(ctx->attn_prof);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  // variant bits: [0] P through shared memory; [1..2] poly-exp2 share: 0 -> default(2/8), 1 -> 0/8, 2 -> 3/8, 3 -> 4/8;
-  // [3] single pass (hold the S row in registers)
-  switch (a->variant & 15) {
+  // variant 0..3: ping-pong kernel (attention_fa.cu) with {2, 0, 4, 6} of every 8 exponentials on the FMA pipe.
+  // variant 16 + v: the single-tile kernel of this file, kept for comparison -- v bits: [0] P through shared memory;
+  // [1..2] poly-exp2 share: 0 -> 2/8, 1 -> 0/8, 2 -> 3/8, 3 -> 4/8; [3] single pass (hold the S row in registers)
+  if (a->variant >= 0 && a->variant <= 3) return launch_attention_fa(ctx, tmQ, tmK, tmV, p, a->variant, stream);
+  switch (a->variant - 16) {
     case 0: return launch_attention<false, 2, true>(ctx, tmQ, tmK, tmV, p, stream);
     case 1: return launch_attention<true, 2, true>(ctx, tmQ, tmK, tmV, p, stream);
-    case 2: return launch_attention<false, 0, true>(ctx, tmQ, tmK, tmV, p, stream);
-    case 4: return launch_attention<false, 3, true>(ctx, tmQ, tmK, tmV, p, stream);
-    case 6: return launch_attention<false, 4, true>(ctx, tmQ, tmK, tmV, p, stream);
     case 8: return launch_attention<false, 2, false>(ctx, tmQ, tmK, tmV, p, stream);
     case 10: return launch_attention<false, 0, false>(ctx, tmQ, tmK, tmV, p, stream);
     default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_attention_bf16: unknown variant %d", a->variant);

@@ -1,0 +1,24 @@
+// attention_common.h -- parameters shared by the attention kernels (attention_fa.cu: ping-pong kernel; attention.cu:
+// C-ABI entry + the single-tile kernel kept for comparison).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+struct dicow_ctx;
+
+namespace dicow {
+
+struct AttnParams {
+  int B, H, Tq, Tk, causal;
+  __nv_bfloat16* out;
+  long long o_rs, o_bs;
+  long long* prof;  // debug: per-step clock64 stamps of one CTA (dicow_debug_set_attention_profile), else NULL
+};
+
+// two 128-row query tiles per CTA, ping-pong softmax (attention_fa.cu); emu selects how many of every 8 exponentials run
+// as a polynomial on the FMA pipe
+int launch_attention_fa(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                        const AttnParams& p, int emu, cudaStream_t stream);
+
+}  // namespace dicow

@@ -16,6 +16,7 @@ struct dicow_ctx {
   // cuTensorMapEncodeTiled fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)
   void* encode_tiled = nullptr;
   void* attn_prof = nullptr;  // debug: see dicow_debug_set_attention_profile
+  float* mel_tables = nullptr;  // Hann window + DFT basis (mel.cu), owned by the handle
 };
 
 namespace dicow {
@@ -39,6 +40,8 @@ int set_error(dicow_ctx* ctx, int code, const char* fmt, ...);
 //   rank 2 or 3; dims[] innermost first (elements); strides_bytes[] for dims 1..rank-1; box[] elements.
 int make_tmap_bf16(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+
+int mel_tables_create(dicow_ctx* ctx);  // mel.cu
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
   }
   if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
   }
 
   if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16) {
@@ -152,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -178,10 +178,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -192,20 +192,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = nt * BN;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sB = sA + Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        const int k0 = kb * BK;
-        if (p.K1 > 0 && k0 >= p.K1)
-          tma_load_3d(&tmA2, &full_bar[stage], sA, k0 - p.K1, m0, b);
-        else
-          tma_load_3d(&tmA, &full_bar[stage], sA, k0, m0, b);
-        tma_load_2d(&tmW, &full_bar[stage], sB, k0, n0, kEvictLast);
+        if (elect_one()) {
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (p.K1 > 0 && k0 >= p.K1)
+            tma_load_3d(&tmA2, &full_bar[stage], sA, k0 - p.K1, m0, b);
+          else
+            tma_load_3d(&tmA, &full_bar[stage], sA, k0, m0, b);
+          tma_load_2d(&tmW, &full_bar[stage], sB, k0, n0, kEvictLast);
+        }
+        __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -220,15 +223,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint64_t da = make_sdesc_sw128(a_addr, 1024, 0);
+        const uint64_t db = make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = make_sdesc_sw128(a_addr + k * 32, 1024, 0);
-          const uint64_t db = make_sdesc_sw128(b_addr + k * 32, 1024, 0);
-          umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)  // +32 B along K per step: +2 in the descriptor's (addr >> 4) field
+            umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.kblocks - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == p.kblocks - 1) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
     }

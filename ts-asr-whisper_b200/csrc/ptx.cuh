@@ -18,6 +18,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// Warp index / values broadcast from lane 0: the compiler treats the result as warp-uniform, so role branches on it
+// are uniform branches and the TMA / MMA issue code inside them compiles to straight uniform-datapath sequences
+// (without this, every tcgen05.mma issued under `if (lane == 0)` is wrapped in an ELECT / BRA.U.ANY retry loop).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -40,6 +58,36 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Blackwell packed fp32 arithmetic (two lanes per instruction on the FMA pipe): halves the issue slots of the
+// softmax scale/offset and row-sum
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = j + f, f in [-0.5, 0.5], degree-4 polynomial for 2^f
 // (max rel. error ~4e-6 -- far below the bf16 rounding of its consumer), exponent added into the float bits.
 // Valid for x in [-126, 126]; callers clamp.  Used to off-load a fraction of the softmax exponentials from the
@@ -59,6 +107,47 @@ __device__ __forceinline__ float poly_exp2(float x) {
 // exact (erf) GELU, as torch.nn.functional.gelu default / HF ACT2FN["gelu"]
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The same erf GELU in ~14 branch-free instructions (libdevice erff costs ~45 in a GEMM epilogue, which made the
+// fc1 epilogue issue-bound): gelu(x) = max(x, 0) - |x|/2 * erfc(|x|/sqrt2), erfc(z) = poly5(t) exp(-z^2),
+// t = 1/(1 + p z) (Abramowitz-Stegun 7.1.26, |erfc error| <= 1.5e-7).  Max abs deviation from the erf form over
+// [-12, 12]: 3.3e-7 (tests/test_gpu_kernels.py::test_gelu_epilogue), far below the bf16 rounding of its consumer.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = fast_rcp(fmaf(ax, 0.23164189f /* 0.3275911 / sqrt2 */, 1.0f));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q *= t;
+  const float e = fast_exp2(x * x * -0.72134752044448170368f /* -log2(e) / 2 */);
+  return fmaf(-0.5f * ax, q * e, fmaxf(x, 0.0f));
+}
+
+// two exp2 at once on the FMA/ALU pipes with packed f32x2 arithmetic (11 instructions per pair, no MUFU)
+__device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 t = add_f32x2(x, magic);
+  const float2 r = add_f32x2(t, nmagic);                            // rint(x)
+  const float2 f = fma_f32x2(r, make_float2(-1.0f, -1.0f), x);      // x - rint(x) in [-0.5, 0.5]
+  float2 q = fma_f32x2(f, make_float2(0.0096181291f, 0.0096181291f), make_float2(0.0555041087f, 0.0555041087f));
+  q = fma_f32x2(q, f, make_float2(0.2402265070f, 0.2402265070f));
+  q = fma_f32x2(q, f, make_float2(0.6931471806f, 0.6931471806f));
+  q = fma_f32x2(q, f, make_float2(1.0f, 1.0f));
+  float2 e;
+  e.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23));
+  e.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23));
+  return e;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -106,8 +195,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > DICOW_WAIT_TIMEOUT_CYCLES) {
+#ifdef DICOW_DEBUG_WAIT
       printf("[dicow] mbarrier wait timeout: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
@@ -286,6 +377,16 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// register re-distribution between warp groups (all 4 warps of a warp group must execute the same one)
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -67,6 +67,16 @@ class AttentionArgs(C.Structure):
     ]
 
 
+class LogmelArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("audio", C.c_void_p), ("audio_batch_stride", C.c_int64),
+        ("B", C.c_int32), ("n_pad", C.c_int64),
+        ("lengths", C.c_void_p), ("mel_filters", C.c_void_p), ("n_mels", C.c_int32),
+        ("out", C.c_void_p), ("attention_mask", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 _handles: dict[int, C.c_void_p] = {}
@@ -108,6 +118,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_zero_pad_rows.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_cast_f32_bf16.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
+    lib.dicow_logmel.argtypes = [vp, C.POINTER(LogmelArgs), vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the library does not export a declared symbol
         if name != "dicow_last_error":
@@ -118,7 +129,7 @@ def _declare(lib: C.CDLL) -> None:
 EXPORTED_SYMBOLS = [
     "dicow_create", "dicow_destroy", "dicow_last_error", "dicow_check", "dicow_abi_version",
     "dicow_gemm_bf16", "dicow_fddt_layernorm", "dicow_attention_bf16", "dicow_features_to_channels_last",
-    "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile",
+    "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile", "dicow_logmel",
 ]
 
 

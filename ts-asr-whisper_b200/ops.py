@@ -216,3 +216,30 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     _lib.check(rc, h, "dicow_cast_f32_bf16")
     launch_count += 1
     return out
+
+
+def logmel(audio: torch.Tensor, mel_filters: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+           return_attention_mask: bool = False):
+    """Whisper log-mel of a batch of zero-padded recordings (dicow_logmel): audio fp32 [B, n_pad] (n_pad % 160 == 0),
+    mel_filters fp32 [201, M], lengths int64 [B].  Returns input_features [B, M, n_pad // 160] fp32 (and the int32
+    attention mask [B, n_pad // 160])."""
+    dev = _require_cuda(audio, mel_filters, lengths)
+    assert audio.dtype == torch.float32 and audio.dim() == 2 and audio.stride(1) == 1
+    assert mel_filters.dtype == torch.float32 and mel_filters.is_contiguous() and mel_filters.shape[0] == 201
+    B, n_pad = audio.shape
+    M = mel_filters.shape[1]
+    frames = n_pad // 160
+    out = torch.empty(B, M, frames, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, frames, dtype=torch.int32, device=dev) if return_attention_mask else None
+    if return_attention_mask and lengths is None:
+        lengths = torch.full((B,), n_pad, dtype=torch.int64, device=dev)
+    if lengths is not None:
+        assert lengths.dtype == torch.int64 and lengths.is_contiguous()
+    ws = torch.empty(B, dtype=torch.int32, device=dev)
+    a = _lib.LogmelArgs()
+    a.struct_size = C.sizeof(_lib.LogmelArgs)
+    a.audio, a.audio_batch_stride, a.B, a.n_pad = _ptr(audio), audio.stride(0), B, n_pad
+    a.lengths, a.mel_filters, a.n_mels = _ptr(lengths), _ptr(mel_filters), M
+    a.out, a.attention_mask, a.workspace = _ptr(out), _ptr(mask), _ptr(ws)
+    _call("dicow_logmel", dev, a, "logmel")
+    return (out, mask) if return_attention_mask else out
