@@ -193,6 +193,114 @@ typedef struct {
 
 DICOW_API int dicow_logmel(dicow_handle_t h, const dicow_logmel_args_t* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Token-by-token decoder step (greedy generate()).  Replaces, per generated token, HF WhisperDecoder.forward with a KV
+ * cache (HF:modeling_whisper.py:449-506, 691-796), proj_out (src/models/dicow/modeling_dicow.py:302) and the greedy
+ * branch of DiCoWGenerationMixin._sample (src/models/dicow/generation.py:707-782).  Every entry point optionally reads
+ * the current position from a device scalar `pos` so that one step is a fixed launch sequence (CUDA-graph replayable).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* out[m, :] = epilogue(A[m, :] W^T + bias) for M <= 64 rows: weights streamed once from HBM (mma.sync m16n8k16).
+ * epilogue: DICOW_EPI_BIAS_BF16 | DICOW_EPI_BIAS_GELU_BF16 | DICOW_EPI_RESIDUAL_F32 (out = resid + acc + bias) |
+ * DICOW_EPI_BIAS_F32.  If pos != NULL the output base is advanced by (*pos) * pos_stride elements (KV-cache append). */
+typedef struct {
+  size_t struct_size;
+  const void* A; /* bf16 [M, K] */
+  int64_t lda;
+  const void* W; /* bf16 [N, K] */
+  int64_t ldw;
+  int32_t M, N, K;
+  const float* bias;
+  void* out;
+  int64_t ldo;
+  int32_t epilogue;
+  const float* resid;
+  int64_t ldr;
+  const int32_t* pos;
+  int64_t pos_stride;
+} dicow_gemm_skinny_args_t;
+DICOW_API int dicow_gemm_skinny_bf16(dicow_handle_t h, const dicow_gemm_skinny_args_t* args, void* stream);
+
+/* one query row per (batch, head), head_dim 64: out[b, h*64:] = softmax(q . K^T) V over Tk keys (Tk = *pos + 1 if pos).
+ * Q/out bf16 [B, H*64]; K/V bf16 rows at K + b*kv_batch_stride + k*kv_row_stride + h*64. */
+typedef struct {
+  size_t struct_size;
+  const void* Q;
+  int64_t q_batch_stride;
+  const void* K;
+  const void* V;
+  int64_t kv_row_stride, kv_batch_stride;
+  void* out;
+  int64_t o_batch_stride;
+  int32_t B, H, Tk;
+  const int32_t* pos;
+} dicow_decode_attention_args_t;
+DICOW_API int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_attention_args_t* args, void* stream);
+
+/* x[b, s, :] = embed_tokens[ids[b, p + s]] + embed_positions[p + s], p = pos ? *pos : past   (fp32 tables, fp32 out)
+ * HF:modeling_whisper.py:741-760 */
+DICOW_API int dicow_embed_tokens(dicow_handle_t h, const int64_t* ids, int64_t ids_row_stride, const float* embed_tokens,
+                                 const float* embed_positions, float* x, int B, int S, int d, int vocab, int past,
+                                 const int32_t* pos, void* stream);
+/* *pos += by (device scalar) */
+DICOW_API int dicow_advance(dicow_handle_t h, int32_t* pos, int by, void* stream);
+
+/* SuppressTokensLogitsProcessor + WhisperTimeStampLogitsProcessor (HF:generation/logits_process.py:1905-2043) + the DiCoW
+ * EOS-at-begin exception (src/models/dicow/utils.py:5-14) + argmax + finished-row bookkeeping
+ * (src/models/dicow/generation.py:728-779) in one pass over logits [B, V]; writes the new token to ids[b, len] where
+ * len = pos ? *pos + 1 : cur_len, and clears unfinished[b] on EOS.  No host synchronisation. */
+typedef struct {
+  size_t struct_size;
+  const float* logits;
+  int64_t ld;
+  int32_t B, V;
+  int64_t* ids; /* [B, >= len + 1] */
+  int64_t ids_row_stride;
+  const int32_t* pos;
+  int32_t cur_len;
+  int32_t begin_index; /* prompt length (forced_decoder_ids) */
+  int32_t eos, pad, no_timestamps, ts_begin;
+  int32_t max_initial_timestamp_index; /* -1 = None */
+  int32_t timestamp_rules;             /* 1 = return_timestamps (timestamp processor on); 0 = suppress list + argmax only */
+  const uint32_t* suppress_bitmap;     /* ceil(V / 32) words, bit v set = suppressed; or NULL */
+  int32_t* unfinished;                 /* [B] */
+  float* processed_scores;             /* optional [B, V]: the scores after all processors (tests) */
+} dicow_logits_rules_args_t;
+DICOW_API int dicow_logits_rules_argmax(dicow_handle_t h, const dicow_logits_rules_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses.  soft-label CE: src/models/dicow/modeling_dicow.py:95-144 (soft_mode = 1: Gaussian-smoothed timestamp targets,
+ * lower/upper-case streams, per-token min, mean over labels != -100) or :312-323 (soft_mode = 0: hard labels, mean over
+ * all rows).  workspace: 2 * rows floats.  CTC: src/models/dicow/encoder.py:108-135 (blank = V1 - 1, every frame valid,
+ * zero_infinity, reduction mean|sum); workspace: B * T + 2 * B floats.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  const float* logits; /* [rows, V] fp32 */
+  int64_t ld;
+  int32_t rows, V;
+  const int64_t* labels;     /* [rows], -100 = padding */
+  const int64_t* upp_labels; /* [rows] or NULL */
+  int32_t ts_begin, n_ts;    /* n_ts = 0: no timestamp smoothing */
+  const float* smoothing;    /* [n_ts, n_ts] row-normalised */
+  int32_t soft_mode;
+  float* workspace;
+  float* loss; /* [1] */
+} dicow_softlabel_ce_args_t;
+DICOW_API int dicow_softlabel_ce(dicow_handle_t h, const dicow_softlabel_ce_args_t* args, void* stream);
+
+typedef struct {
+  size_t struct_size;
+  const float* logits; /* [B, T, V1] fp32 contiguous */
+  int32_t B, T, V1;
+  const int64_t* labels; /* [B, Lmax], negative = padding */
+  int32_t Lmax;
+  int32_t reduction_mean; /* 1 = "mean" (per-utterance loss / target length, batch mean), 0 = "sum" */
+  float* workspace;
+  float* loss; /* [1] */
+} dicow_ctc_loss_args_t;
+DICOW_API int dicow_ctc_loss(dicow_handle_t h, const dicow_ctc_loss_args_t* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

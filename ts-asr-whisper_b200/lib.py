@@ -77,6 +77,55 @@ class LogmelArgs(C.Structure):
     ]
 
 
+class GemmSkinnyArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64), ("epilogue", C.c_int32),
+        ("resid", C.c_void_p), ("ldr", C.c_int64), ("pos", C.c_void_p), ("pos_stride", C.c_int64),
+    ]
+
+
+class DecodeAttentionArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("Q", C.c_void_p), ("q_batch_stride", C.c_int64), ("K", C.c_void_p), ("V", C.c_void_p),
+        ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
+        ("out", C.c_void_p), ("o_batch_stride", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tk", C.c_int32), ("pos", C.c_void_p),
+    ]
+
+
+class LogitsRulesArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("B", C.c_int32), ("V", C.c_int32),
+        ("ids", C.c_void_p), ("ids_row_stride", C.c_int64), ("pos", C.c_void_p), ("cur_len", C.c_int32),
+        ("begin_index", C.c_int32), ("eos", C.c_int32), ("pad", C.c_int32), ("no_timestamps", C.c_int32),
+        ("ts_begin", C.c_int32), ("max_initial_timestamp_index", C.c_int32), ("timestamp_rules", C.c_int32),
+        ("suppress_bitmap", C.c_void_p), ("unfinished", C.c_void_p), ("processed_scores", C.c_void_p),
+    ]
+
+
+class SoftlabelCeArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int32), ("V", C.c_int32),
+        ("labels", C.c_void_p), ("upp_labels", C.c_void_p), ("ts_begin", C.c_int32), ("n_ts", C.c_int32),
+        ("smoothing", C.c_void_p), ("soft_mode", C.c_int32), ("workspace", C.c_void_p), ("loss", C.c_void_p),
+    ]
+
+
+class CtcLossArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("logits", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32),
+        ("labels", C.c_void_p), ("Lmax", C.c_int32), ("reduction_mean", C.c_int32),
+        ("workspace", C.c_void_p), ("loss", C.c_void_p),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 _handles: dict[int, C.c_void_p] = {}
@@ -119,6 +168,13 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_cast_f32_bf16.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
     lib.dicow_logmel.argtypes = [vp, C.POINTER(LogmelArgs), vp]
+    lib.dicow_gemm_skinny_bf16.argtypes = [vp, C.POINTER(GemmSkinnyArgs), vp]
+    lib.dicow_decode_attention_bf16.argtypes = [vp, C.POINTER(DecodeAttentionArgs), vp]
+    lib.dicow_embed_tokens.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.dicow_advance.argtypes = [vp, vp, C.c_int, vp]
+    lib.dicow_logits_rules_argmax.argtypes = [vp, C.POINTER(LogitsRulesArgs), vp]
+    lib.dicow_softlabel_ce.argtypes = [vp, C.POINTER(SoftlabelCeArgs), vp]
+    lib.dicow_ctc_loss.argtypes = [vp, C.POINTER(CtcLossArgs), vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the library does not export a declared symbol
         if name != "dicow_last_error":
@@ -130,6 +186,8 @@ EXPORTED_SYMBOLS = [
     "dicow_create", "dicow_destroy", "dicow_last_error", "dicow_check", "dicow_abi_version",
     "dicow_gemm_bf16", "dicow_fddt_layernorm", "dicow_attention_bf16", "dicow_features_to_channels_last",
     "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile", "dicow_logmel",
+    "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
+    "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss",
 ]
 
 

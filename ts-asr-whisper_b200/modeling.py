@@ -120,6 +120,7 @@ class CrossAttentionEnrollBlock(nn.Module):
         self.cross_attn = AttentionParams(d)
         self.cross_gate = Gate(1, init_val=0.0)
         self.ffn = nn.Sequential(nn.Linear(2 * d, ffn), nn.Identity(), nn.Identity(), nn.Linear(ffn, d), nn.Identity())
+        self.ffn[0]._dicow_custom_init = self.ffn[3]._dicow_custom_init = True  # keep through HF post_init()
         with torch.no_grad():  # layers.py:95-110: start as "copy the first half through"
             nn.init.xavier_uniform_(self.ffn[0].weight, gain=1e-1)
             self.ffn[0].weight[:d, :d] += torch.eye(d)
@@ -224,17 +225,15 @@ class DiCoWEncoder(nn.Module):
         return None
 
     def get_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        """CTC loss exactly as encoder.py:108-135 (library op; the fused CUDA CTC kernel is SURVEY K13, not built yet)."""
+        """CTC loss as encoder.py:108-135 (fp32 log-softmax, blank = last class, every frame valid, zero_infinity) in
+        the fused kernel (ops.ctc_loss); the label filtering is index bookkeeping on the int64 labels."""
         if labels.max() >= self.config.vocab_size:
             raise ValueError(f"Label values must be <= vocab_size: {self.config.vocab_size}")
         if self.config.remove_timestamps_from_ctc:
             labels = torch.nn.utils.rnn.pad_sequence([lab[lab < self.first_task_token] for lab in labels],
                                                      padding_value=-100).T
-        input_lengths = torch.full((logits.shape[0],), logits.shape[1], device=logits.device)
-        target_lengths = (labels >= 0).sum(-1)
-        log_probs = nn.functional.log_softmax(logits, dim=-1, dtype=torch.float32).transpose(0, 1)
-        return nn.functional.ctc_loss(log_probs, labels, input_lengths, target_lengths, blank=logits.shape[-1] - 1,
-                                      reduction=self.config.ctc_loss_reduction, zero_infinity=True)
+        return ops.ctc_loss(logits.float().contiguous(), labels.to(logits.device).contiguous(),
+                            reduction=self.config.ctc_loss_reduction)
 
     # ---- weight preparation ----------------------------------------------------------------------------------
     def _cache_key(self):

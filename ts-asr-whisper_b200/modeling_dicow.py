@@ -1,0 +1,748 @@
+"""Host-side mirror of the reference's top-level model for the hot path:
+
+    DiCoW                           src/models/dicow/modeling_dicow.py:146-221  (WhisperModel with a DiCoWEncoder)
+    DiCoWForConditionalGeneration   src/models/dicow/modeling_dicow.py:224-357  (+ DiCoWGenerationMixin, generation.py)
+    SoftLabelCreator                src/models/dicow/modeling_dicow.py:23-144
+
+Same class names, ``forward`` / ``generate`` signatures, ``state_dict`` keys (``model.encoder.*``, ``model.decoder.*``,
+``proj_out.weight`` tied to ``model.decoder.embed_tokens.weight``) and outputs.  The modules are parameter containers:
+the arithmetic of the decoder (HF WhisperDecoder, HF:models/whisper/modeling_whisper.py:449-796), proj_out, both losses
+and the greedy token loop with its logits processors runs in libdicow_b200.so (ops.py).  ``generate()`` owns its
+long-form loop instead of overriding private HF hooks (the reference targets transformers 4.55 internals that no longer
+exist) and mirrors HF WhisperGenerationMixin.generate (HF:models/whisper/generation_whisper.py:
+383-968) + the reference's overrides (generation.py:73-118 STNO slicing, :121-149 forced init tokens, :415-534
+_retrieve_segment) for the supported mode: greedy, forced language/task prompt, timestamps on, no temperature fallback,
+no conditioning on previous text (the recipes' configs/decode/*_greedy.yaml).  No eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import re
+from decimal import ROUND_HALF_UP, Decimal
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+from transformers import GenerationConfig, PreTrainedModel
+from transformers.modeling_outputs import BaseModelOutput, Seq2SeqLMOutput, Seq2SeqModelOutput
+
+from . import ops
+from .configuration import DiCoWConfig
+from .modeling import AttentionParams, DiCoWEncoder, _bf16, _f32
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers (names == HF WhisperDecoder state_dict)
+# ----------------------------------------------------------------------------------------------------------------
+class DecoderLayerParams(nn.Module):
+    def __init__(self, d: int, ffn: int):
+        super().__init__()
+        self.self_attn = AttentionParams(d)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.encoder_attn = AttentionParams(d)
+        self.encoder_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, ffn)
+        self.fc2 = nn.Linear(ffn, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+
+
+class DiCoWDecoder(nn.Module):
+    """Parameters of HF WhisperDecoder (HF:modeling_whisper.py:650-689)."""
+
+    def __init__(self, config: DiCoWConfig):
+        super().__init__()
+        d = config.d_model
+        self.config = config
+        self.embed_tokens = nn.Embedding(config.vocab_size, d, padding_idx=config.pad_token_id)
+        self.embed_positions = nn.Embedding(config.max_target_positions, d)
+        self.layers = nn.ModuleList([DecoderLayerParams(d, config.decoder_ffn_dim) for _ in range(config.decoder_layers)])
+        self.layer_norm = nn.LayerNorm(d)
+
+
+def shift_tokens_right(labels: torch.Tensor, pad_token_id: int, decoder_start_token_id: int) -> torch.Tensor:
+    """HF:modeling_whisper.py shift_tokens_right (index bookkeeping on int64 labels; call site modeling_dicow.py:275-279)."""
+    shifted = labels.new_zeros(labels.shape)
+    shifted[:, 1:] = labels[:, :-1].clone()
+    shifted[:, 0] = decoder_start_token_id
+    shifted.masked_fill_(shifted == -100, pad_token_id)
+    return shifted
+
+
+class SoftLabelCreator(nn.Module):
+    """Timestamp-smoothing table of src/models/dicow/modeling_dicow.py:23-70.  The reference stores a dense
+    [num_ts, vocab] matrix and builds dense one-hot targets; the timestamp ids of a Whisper tokenizer are one contiguous
+    block, so the kernel only needs ``ts_begin`` and the [num_ts, num_ts] Gaussian weights."""
+
+    def __init__(self, tokenizer, timestamp_sigma: float = 0.08):
+        super().__init__()
+        self.tokenizer = tokenizer
+        self.timestamp_sigma = timestamp_sigma
+        pat = re.compile(r"<\|(\d+\.\d+)\|>")
+        id_to_time = {}
+        for tok, idx in tokenizer.get_vocab().items():
+            m = pat.match(tok)
+            if m:
+                id_to_time[idx] = float(m.group(1))
+        self.ts_begin, self.smoothing = 0, None
+        if id_to_time:
+            ids = sorted(id_to_time)
+            if ids != list(range(ids[0], ids[0] + len(ids))):
+                raise NotImplementedError("timestamp token ids are expected to be one contiguous block")
+            times = torch.tensor([id_to_time[i] for i in ids])
+            w = torch.exp(-((times[:, None] - times[None, :]) ** 2) / (2 * timestamp_sigma ** 2))
+            self.ts_begin = ids[0]
+            self.register_buffer("ts_smoothing_weights", (w / w.sum(dim=1, keepdim=True)).contiguous(), persistent=False)
+            self.smoothing = True
+
+    def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optional[torch.Tensor]) -> torch.Tensor:
+        V = logits.shape[-1]
+        sm = self.ts_smoothing_weights.to(logits.device) if self.smoothing else None
+        return ops.softlabel_ce(logits.reshape(-1, V), labels.to(logits.device),
+                                upp_labels.to(logits.device) if upp_labels is not None else None,
+                                ts_begin=self.ts_begin, smoothing=sm, soft_mode=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# base model
+# ----------------------------------------------------------------------------------------------------------------
+class DiCoW(nn.Module):
+    """encoder + decoder (src/models/dicow/modeling_dicow.py:146-221)."""
+
+    def __init__(self, config: DiCoWConfig):
+        super().__init__()
+        self.config = config
+        self.encoder = DiCoWEncoder(config)
+        self.decoder = DiCoWDecoder(config)
+        self._prepared: Optional[dict] = None
+        self._prepared_key = None
+
+    def get_encoder(self):
+        return self.encoder
+
+    def get_decoder(self):
+        return self.decoder
+
+    # ---- bf16 / fused decoder weights ------------------------------------------------------------------------
+    def prepare_decoder(self) -> dict:
+        key = tuple((p.data_ptr(), p._version) for p in self.decoder.parameters())
+        if self._prepared is not None and key == self._prepared_key:
+            return self._prepared
+        dec = self.decoder
+        sc = 64 ** -0.5  # folded q scale (HF:modeling_whisper.py:310), exact in bf16
+
+        def att(a: AttentionParams) -> dict:
+            d = a.q_proj.weight.shape[0]
+            zeros = torch.zeros(d, device=a.q_proj.weight.device)
+            return {"wq": _bf16(a.q_proj.weight.detach().float() * sc), "bq": (a.q_proj.bias.detach().float() * sc).contiguous(),
+                    "wkv": _bf16(torch.cat([a.k_proj.weight.detach().float(), a.v_proj.weight.detach().float()], 0)),
+                    "bkv": torch.cat([zeros, a.v_proj.bias.detach().float()]).contiguous(),
+                    "wo": _bf16(a.out_proj.weight), "bo": _f32(a.out_proj.bias)}
+
+        w: dict = {"tok": _f32(dec.embed_tokens.weight), "pos": _f32(dec.embed_positions.weight),
+                   "proj": _bf16(dec.embed_tokens.weight),  # proj_out is tied to embed_tokens (train.py:109-113)
+                   "lnf_g": _f32(dec.layer_norm.weight), "lnf_b": _f32(dec.layer_norm.bias), "layers": []}
+        for lyr in dec.layers:
+            e = {"self": att(lyr.self_attn), "cross": att(lyr.encoder_attn)}
+            s = e["self"]
+            s["wqkv"] = torch.cat([s["wq"], s["wkv"]], 0).contiguous()
+            s["bqkv"] = torch.cat([s["bq"], s["bkv"]]).contiguous()
+            for nm, ln in (("ln1", lyr.self_attn_layer_norm), ("ln2", lyr.encoder_attn_layer_norm),
+                           ("ln3", lyr.final_layer_norm)):
+                e[nm + "_g"], e[nm + "_b"] = _f32(ln.weight), _f32(ln.bias)
+            e["w1"], e["b1"] = _bf16(lyr.fc1.weight), _f32(lyr.fc1.bias)
+            e["w2"], e["b2"] = _bf16(lyr.fc2.weight), _f32(lyr.fc2.bias)
+            w["layers"].append(e)
+        self._prepared, self._prepared_key = w, key
+        return w
+
+    # ---- teacher-forced decoder (training / evaluation forward) -------------------------------------------------
+    @torch.no_grad()
+    def decode_teacher_forced(self, decoder_input_ids: torch.Tensor, enc_bf16: torch.Tensor):
+        """[B, S] ids + encoder states bf16 [B, T, d] -> (hidden fp32 [B, S, d], hidden bf16 [B*S, d]).
+        HF WhisperDecoder.forward without cache (HF:modeling_whisper.py:691-796): embed + learned positions,
+        layers x [causal self-attn, cross-attn, MLP] (pre-LN), final LN."""
+        cfg = self.config
+        w = self.prepare_decoder()
+        dev = enc_bf16.device
+        B, S = decoder_input_ids.shape
+        T, d, H = enc_bf16.shape[1], cfg.d_model, cfg.decoder_attention_heads
+        if S > cfg.max_target_positions:
+            raise ValueError(f"decoder sequence length {S} exceeds max_target_positions {cfg.max_target_positions}")
+        ids = decoder_input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        x = torch.empty(B, S, d, dtype=torch.float32, device=dev)
+        ops.embed_tokens(ids, w["tok"], w["pos"], x, S=S, past=0)
+        rows = B * S
+        xf = x.view(rows, d)
+        ln = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        qkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
+        q = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        kv = torch.empty(B * T, 2 * d, dtype=torch.bfloat16, device=dev)
+        hdn = torch.empty(rows, cfg.decoder_ffn_dim, dtype=torch.bfloat16, device=dev)
+        encf = enc_bf16.reshape(B * T, d)
+        for e in w["layers"]:
+            s, c = e["self"], e["cross"]
+            ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln)
+            ops.gemm(ln, s["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=s["bqkv"])
+            ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], ctx, B=B, H=H, Tq=S, Tk=S, q_row_stride=3 * d,
+                          q_batch_stride=S * 3 * d, kv_row_stride=3 * d, kv_batch_stride=S * 3 * d, o_row_stride=d,
+                          o_batch_stride=S * d, causal=True)
+            ops.gemm(ctx, s["wo"], xf, epilogue=ops.EPI_RESIDUAL_F32, bias=s["bo"], resid=xf)
+            ops.fddt_layernorm(x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=ln)
+            ops.gemm(ln, c["wq"], q, epilogue=ops.EPI_BIAS_BF16, bias=c["bq"])
+            ops.gemm(encf, c["wkv"], kv, epilogue=ops.EPI_BIAS_BF16, bias=c["bkv"])
+            ops.attention(q, kv, kv[:, d:], ctx, B=B, H=H, Tq=S, Tk=T, q_row_stride=d, q_batch_stride=S * d,
+                          kv_row_stride=2 * d, kv_batch_stride=T * 2 * d, o_row_stride=d, o_batch_stride=S * d)
+            ops.gemm(ctx, c["wo"], xf, epilogue=ops.EPI_RESIDUAL_F32, bias=c["bo"], resid=xf)
+            ops.fddt_layernorm(x, gamma=e["ln3_g"], beta=e["ln3_b"], ln_out_bf16=ln)
+            ops.gemm(ln, e["w1"], hdn, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
+            ops.gemm(hdn, e["w2"], xf, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=xf)
+        hid = torch.empty(B, S, d, dtype=torch.float32, device=dev)
+        ops.fddt_layernorm(x, gamma=w["lnf_g"], beta=w["lnf_b"], ln_out_f32=hid, ln_out_bf16=ln)
+        return hid, ln
+
+    @torch.no_grad()
+    def forward(self, input_features=None, attention_mask=None, stno_mask=None, decoder_input_ids=None,
+                decoder_attention_mask=None, head_mask=None, decoder_head_mask=None, cross_attn_head_mask=None,
+                encoder_outputs=None, past_key_values=None, decoder_inputs_embeds=None, decoder_position_ids=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                cache_position=None, enrollments=None):
+        if past_key_values is not None or decoder_inputs_embeds is not None or decoder_position_ids is not None:
+            raise NotImplementedError("the B200 path decodes through generate(); HF cache objects / input embeddings "
+                                      "are not accepted by forward()")
+        if encoder_outputs is None:
+            encoder_outputs = self.encoder(input_features, stno_mask=stno_mask, enrollments=enrollments)
+        enc = encoder_outputs[0] if not isinstance(encoder_outputs, torch.Tensor) else encoder_outputs
+        hid, _ = self.decode_teacher_forced(decoder_input_ids, ops.cast_bf16(enc.float()))
+        return Seq2SeqModelOutput(last_hidden_state=hid, encoder_last_hidden_state=enc)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# greedy token loop
+# ----------------------------------------------------------------------------------------------------------------
+class _GreedyState:
+    """Per-(device, batch size) buffers and the two captured CUDA graphs of one decoder step."""
+
+    def __init__(self, model: "DiCoWForConditionalGeneration", B: int, T: int, dev: torch.device):
+        cfg = model.config
+        d, L = cfg.d_model, cfg.decoder_layers
+        self.B, self.T = B, T
+        self.S_max = cfg.max_target_positions
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.ids = torch.zeros(B, self.S_max + 1, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.unfinished = torch.ones(B, dtype=torch.int32, device=dev)
+        self.x = torch.empty(B, d, dtype=torch.float32, device=dev)
+        self.ln = torch.empty(B, d, **bf)
+        self.q = torch.empty(B, d, **bf)
+        self.ctx = torch.empty(B, d, **bf)
+        self.h = torch.empty(B, cfg.decoder_ffn_dim, **bf)
+        self.self_kv = torch.zeros(L, B, self.S_max, 2 * d, **bf)
+        self.cross_kv = torch.empty(L, B, T, 2 * d, **bf)
+        self.logits = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
+        self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.weights_id = None  # id() of the prepared-weight dict the graphs were captured with
+
+
+class DiCoWForConditionalGeneration(PreTrainedModel):
+    config_class = DiCoWConfig
+    base_model_prefix = "model"
+    main_input_name = "input_features"
+    _tied_weights_keys = {"proj_out.weight": "model.decoder.embed_tokens.weight"}
+    _no_split_modules = ["EncoderLayerParams", "DecoderLayerParams"]
+    # step graphs are captured once per batch size; set False to launch the step kernels eagerly (debugging)
+    use_cuda_graphs = True
+
+    def __init__(self, config: DiCoWConfig):
+        super().__init__(config)
+        self.model = DiCoW(config)
+        self.proj_out = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        self.max_target_positions = config.max_target_positions
+        self.encoder_logits = None
+        self.tokenizer = None
+        self.stno_mask = None
+        self.stno_mask_seek = None
+        self.soft_label_creator = None
+        self._greedy: Dict[tuple, _GreedyState] = {}
+        self.post_init()
+        self.tie_weights()
+        if getattr(self, "generation_config", None) is None:
+            self.generation_config = GenerationConfig.from_model_config(config)
+
+    # ---- HF plumbing ---------------------------------------------------------------------------------------
+    def _init_weights(self, module):
+        """HF WhisperPreTrainedModel._init_weights semantics for the container modules; FDDT / Gate / SCB modules
+        initialise themselves (src/models/dicow/encoder.py:79-82)."""
+        std = getattr(self.config, "init_std", 0.02)
+        from .modeling import CustomDiagonalLinear, Gate
+        if isinstance(module, (CustomDiagonalLinear, Gate)):
+            module.reset_parameters()
+        elif isinstance(module, (nn.Linear, nn.Conv1d)):
+            if getattr(module, "_dicow_custom_init", False):
+                return
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.weight.data.fill_(1.0)
+            module.bias.data.zero_()
+
+    def tie_weights(self, *args, **kwargs):
+        self.proj_out.weight = self.model.decoder.embed_tokens.weight
+
+    def get_encoder(self):
+        return self.model.get_encoder()
+
+    def get_decoder(self):
+        return self.model.get_decoder()
+
+    def get_output_embeddings(self):
+        return self.proj_out
+
+    def set_output_embeddings(self, new_embeddings):
+        self.proj_out = new_embeddings
+
+    def get_input_embeddings(self):
+        return self.model.decoder.embed_tokens
+
+    def can_generate(self) -> bool:
+        return True
+
+    def freeze_encoder(self):
+        for p in self.model.encoder.parameters():
+            p.requires_grad_(False)
+
+    # ---- reference API -------------------------------------------------------------------------------------
+    def set_tokenizer(self, tokenizer):  # modeling_dicow.py:237-240
+        self.tokenizer = tokenizer
+        self.soft_label_creator = SoftLabelCreator(tokenizer)
+
+    def get_enc_logits(self, hidden_states: torch.Tensor) -> torch.Tensor:  # modeling_dicow.py:242-246
+        enc = self.model.get_encoder()
+        B, T, _ = hidden_states.shape
+        return enc.ctc_logits_from_hidden(ops.cast_bf16(hidden_states.float()), B, T)
+
+    @torch.no_grad()
+    def forward(self, input_features=None, attention_mask=None, stno_mask=None, decoder_input_ids=None,
+                decoder_attention_mask=None, head_mask=None, decoder_head_mask=None, cross_attn_head_mask=None,
+                encoder_outputs=None, past_key_values=None, decoder_inputs_embeds=None, decoder_position_ids=None,
+                labels=None, upp_labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, cache_position=None, forced_decoder_ids=None, enrollments=None):
+        """src/models/dicow/modeling_dicow.py:248-354.  Forward values only (the training backward is not built yet:
+        DESIGN.md section 8)."""
+        cfg = self.config
+        if labels is not None and decoder_input_ids is None and decoder_inputs_embeds is None:
+            decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
+        if past_key_values is not None or decoder_inputs_embeds is not None:
+            raise NotImplementedError("forward() is the teacher-forced path; token-by-token decoding is generate()")
+        enc_model = self.model.get_encoder()
+        if encoder_outputs is None:
+            encoder_outputs = enc_model(input_features, stno_mask=stno_mask, enrollments=enrollments)
+        enc = encoder_outputs[0] if not isinstance(encoder_outputs, torch.Tensor) else encoder_outputs
+        B, T, d = enc.shape
+        enc_bf16 = ops.cast_bf16(enc.float())
+        hid, hid_bf16 = self.model.decode_teacher_forced(decoder_input_ids, enc_bf16)
+        S = decoder_input_ids.shape[1]
+        w = self.model.prepare_decoder()
+        logits = torch.empty(B, S, cfg.vocab_size, dtype=torch.float32, device=enc.device)
+        ops.gemm(hid_bf16, w["proj"], logits.view(B * S, cfg.vocab_size), epilogue=ops.EPI_BIAS_F32)
+        loss = None
+        if labels is not None:
+            labels = labels.to(enc.device)
+            flat = logits.view(B * S, cfg.vocab_size)
+            if self.soft_label_creator is not None:
+                dec_loss = self.soft_label_creator.compute_loss(flat, labels, upp_labels)
+            else:  # hard-label fallback, mean over ALL positions (modeling_dicow.py:312-323)
+                dec_loss = ops.softlabel_ce(flat, labels, upp_labels.to(enc.device) if upp_labels is not None else None,
+                                            soft_mode=False)
+            if cfg.ctc_weight > 0.0:
+                enc_logits = enc_model.ctc_logits_from_hidden(enc_bf16, B, T)
+                enc_labels = labels.clone()
+                prefix = getattr(self.tokenizer, "prefix_tokens", None) if self.tokenizer is not None else None
+                if prefix is None:
+                    prefix = getattr(self, "ctc_prefix_tokens", ())
+                for tok in prefix:  # modeling_dicow.py:330-332
+                    if enc_labels.shape[1] and bool((enc_labels[:, 0] == tok).all()):
+                        enc_labels = enc_labels[:, 1:]
+                enc_labels[enc_labels == cfg.eos_token_id] = -100
+                ctc = enc_model.get_loss(enc_logits, enc_labels)
+                loss = (1 - cfg.ctc_weight) * dec_loss + cfg.ctc_weight * ctc
+            else:
+                loss = dec_loss
+        if return_dict is False:
+            out = (logits, enc)
+            return ((loss,) + out) if loss is not None else out
+        return Seq2SeqLMOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc)
+
+    # ---- greedy decoding of one 30 s window batch ----------------------------------------------------------------
+    def _decode_step(self, st: _GreedyState, w: dict, sample: bool, gen: dict) -> None:
+        """One token for every row: fixed launch sequence, position read from the device scalar ``st.pos``."""
+        cfg = self.config
+        d, H, B, T = cfg.d_model, cfg.decoder_attention_heads, st.B, st.T
+        ops.embed_tokens(st.ids, w["tok"], w["pos"], st.x, S=1, pos=st.pos)
+        for li, e in enumerate(w["layers"]):
+            s, c = e["self"], e["cross"]
+            kvc = st.self_kv[li]
+            ops.fddt_layernorm(st.x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=st.ln)
+            ops.gemm_skinny(st.ln, s["wq"], st.q, epilogue=ops.EPI_BIAS_BF16, bias=s["bq"])
+            ops.gemm_skinny(st.ln, s["wkv"], kvc, epilogue=ops.EPI_BIAS_BF16, bias=s["bkv"], ldo=st.S_max * 2 * d,
+                            pos=st.pos, pos_stride=2 * d)
+            ops.decode_attention(st.q, kvc, kvc[:, :, d:], st.ctx, B=B, H=H, Tk=0, kv_row_stride=2 * d,
+                                 kv_batch_stride=st.S_max * 2 * d, pos=st.pos)
+            ops.gemm_skinny(st.ctx, s["wo"], st.x, epilogue=ops.EPI_RESIDUAL_F32, bias=s["bo"], resid=st.x)
+            ops.fddt_layernorm(st.x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=st.ln)
+            ops.gemm_skinny(st.ln, c["wq"], st.q, epilogue=ops.EPI_BIAS_BF16, bias=c["bq"])
+            ckv = st.cross_kv[li]
+            ops.decode_attention(st.q, ckv, ckv[:, :, d:], st.ctx, B=B, H=H, Tk=T, kv_row_stride=2 * d,
+                                 kv_batch_stride=T * 2 * d)
+            ops.gemm_skinny(st.ctx, c["wo"], st.x, epilogue=ops.EPI_RESIDUAL_F32, bias=c["bo"], resid=st.x)
+            ops.fddt_layernorm(st.x, gamma=e["ln3_g"], beta=e["ln3_b"], ln_out_bf16=st.ln)
+            ops.gemm_skinny(st.ln, e["w1"], st.h, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
+            ops.gemm_skinny(st.h, e["w2"], st.x, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=st.x)
+        if sample:
+            ops.fddt_layernorm(st.x, gamma=w["lnf_g"], beta=w["lnf_b"], ln_out_bf16=st.ln)
+            ops.gemm_skinny(st.ln, w["proj"], st.logits, epilogue=ops.EPI_BIAS_F32)
+            ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **gen)
+        ops.advance(st.pos, 1)
+
+    @torch.no_grad()
+    def greedy_decode_window(self, enc_hidden: torch.Tensor, prompt: torch.Tensor, max_total_len: int, gen: dict,
+                             return_first_logits: bool = False):
+        """Greedy branch of DiCoWGenerationMixin._sample (generation.py:707-782) for one batch of 30 s windows.
+        enc_hidden [B, T, d] (fp32 or bf16), prompt int64 [B, P] (forced init tokens).  Returns int64 ids [B, n] on
+        the device (prompt + generated, finished rows padded)."""
+        cfg = self.config
+        dev = enc_hidden.device
+        B, T, d = enc_hidden.shape
+        P = prompt.shape[1]
+        max_total_len = min(max_total_len, cfg.max_target_positions)
+        w = self.model.prepare_decoder()
+        if B > 64:
+            raise NotImplementedError("decode batch above 64 windows: split the batch")
+        key = (dev.index, B, T)
+        st = self._greedy.get(key)
+        if st is None:
+            st = self._greedy[key] = _GreedyState(self, B, T, dev)
+        enc_bf16 = enc_hidden if enc_hidden.dtype == torch.bfloat16 else ops.cast_bf16(enc_hidden.float())
+        encf = enc_bf16.reshape(B * T, d)
+        for li, e in enumerate(w["layers"]):  # cross-attention K/V once per window (HF caches them after step 0)
+            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv[li].view(B * T, 2 * d), epilogue=ops.EPI_BIAS_BF16,
+                     bias=e["cross"]["bkv"])
+        if st.weights_id != id(w):  # parameters changed since capture: the graphs hold stale weight pointers
+            st.graphs.clear()
+            st.weights_id = id(w)
+        st.ids.zero_()
+        st.ids[:, :P] = prompt.to(device=dev, dtype=torch.int64)
+        st.pos.zero_()
+        st.unfinished.fill_(1)
+        gen = dict(gen, begin_index=P)
+
+        def run(sample: bool):
+            if not self.use_cuda_graphs:
+                self._decode_step(st, w, sample, gen)
+                return
+            gkey = (sample, P, tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+                                            for k, v in gen.items())))
+            g = st.graphs.get(gkey)
+            if g is None:
+                # warm-up launch outside capture (kernel attributes, lazy module load), then restore the state it touched
+                ids0, pos0, unf0 = st.ids.clone(), st.pos.clone(), st.unfinished.clone()
+                self._decode_step(st, w, sample, gen)
+                torch.cuda.synchronize(dev)
+                st.ids.copy_(ids0), st.pos.copy_(pos0), st.unfinished.copy_(unf0)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode_step(st, w, sample, gen)
+                st.graphs[gkey] = g
+                st.ids.copy_(ids0), st.pos.copy_(pos0), st.unfinished.copy_(unf0)
+            g.replay()
+
+        for _ in range(P - 1):  # prompt tokens: fill the self-attention cache only
+            run(False)
+        first_logits = None
+        n_new = max_total_len - P
+        for step in range(n_new):
+            run(True)
+            if step == 0 and return_first_logits:
+                first_logits = st.logits.clone()
+            if (step & 7) == 7 and not bool(st.unfinished.any().item()):  # host check every 8 tokens only
+                n_new = step + 1
+                break
+        ids = st.ids[:, :P + n_new].clone()
+        # rows that finished early were padded by the kernel; trim columns that are padding for every row
+        return (ids, first_logits) if return_first_logits else ids
+
+    def _suppress_bitmap(self, tokens, dev) -> Optional[torch.Tensor]:
+        """device bitmap of SuppressTokensLogitsProcessor's ids, cached so captured graphs keep a valid pointer"""
+        if not tokens:
+            return None
+        key = (dev.index, tuple(int(t) for t in tokens))
+        cache = self.__dict__.setdefault("_suppress_cache", {})
+        if key not in cache:
+            cache[key] = ops.suppress_bitmap(key[1], self.config.vocab_size, dev)
+        return cache[key]
+
+    # ---- generate() -----------------------------------------------------------------------------------------
+    def _generation_settings(self, generation_config, kwargs) -> dict:
+        gc = generation_config if generation_config is not None else self.generation_config
+        def get(name, default=None):
+            if name in kwargs and kwargs[name] is not None:
+                return kwargs[name]
+            v = getattr(gc, name, None)
+            return default if v is None else v
+        num_beams = get("num_beams", 1)
+        if num_beams != 1:
+            raise NotImplementedError("beam search is a SURVEY section 8f 'next' row; the B200 path decodes greedily")
+        if (get("ctc_weight", 0) or 0) > 0:
+            raise NotImplementedError("joint CTC/attention decoding is a SURVEY section 8f 'next' row")
+        if get("do_sample", False):
+            raise ValueError("Provided generation mode is not supported (greedy only)")
+        ts_begin = get("no_timestamps_token_id")
+        if ts_begin is None:
+            raise ValueError("generation_config.no_timestamps_token_id is required (Whisper generation config)")
+        eos = get("eos_token_id", self.config.eos_token_id)
+        eos = eos[0] if isinstance(eos, (list, tuple)) else eos
+        pad = get("pad_token_id", self.config.pad_token_id)
+        return {"eos": int(eos), "pad": int(pad if pad is not None else eos), "no_timestamps": int(ts_begin),
+                "ts_begin": int(ts_begin) + 1, "suppress_tokens": get("suppress_tokens"),
+                "return_timestamps": bool(get("return_timestamps", True)),
+                "max_initial_timestamp_index": get("max_initial_timestamp_index"),
+                "max_new_tokens": get("max_new_tokens"), "max_length": get("max_length", self.config.max_target_positions),
+                "forced_decoder_ids": get("forced_decoder_ids")}
+
+    @torch.no_grad()
+    def generate(self, input_features: Optional[torch.Tensor] = None, generation_config=None,
+                 condition_on_prev_tokens: Optional[bool] = None, assistant_model=None,
+                 attention_mask: Optional[torch.Tensor] = None, stno_mask: Optional[torch.Tensor] = None,
+                 forced_decoder_ids=None, enrollments: Optional[dict] = None, return_segments: bool = False,
+                 **kwargs):
+        """src/models/dicow/generation.py:536-564 over HF WhisperGenerationMixin.generate (long-form seek loop)."""
+        if condition_on_prev_tokens:
+            raise NotImplementedError("Current version does not support conditioning")  # generation.py:543-544
+        if assistant_model is not None:
+            raise NotImplementedError("assisted generation is not supported")
+        cfg = self.config
+        if forced_decoder_ids is not None:
+            kwargs["forced_decoder_ids"] = forced_decoder_ids
+        gs = self._generation_settings(generation_config, kwargs)
+        fdi = gs["forced_decoder_ids"]
+        if fdi is None:
+            fdi = getattr(cfg, "forced_decoder_ids", None)
+        if fdi is None:
+            raise NotImplementedError("language detection (no forced_decoder_ids) is a SURVEY section 8f 'next' row; "
+                                      "the recipes always pass the language/task prompt (provide_gt_lang)")
+        dev = input_features.device
+        init_tokens = torch.as_tensor(fdi, dtype=torch.int64, device=dev)
+        if init_tokens.dim() == 1:
+            init_tokens = init_tokens[None].expand(input_features.shape[0], -1)
+        B0 = input_features.shape[0]
+        P = init_tokens.shape[1]
+        if gs["max_new_tokens"] is not None:
+            if gs["max_new_tokens"] + P > cfg.max_target_positions:
+                raise ValueError(f"The length of `decoder_input_ids`, including special start tokens, prompt tokens, and "
+                                 f"previous tokens, is {P},  and `max_new_tokens` is {gs['max_new_tokens']}. Thus, the "
+                                 f"combined length of `decoder_input_ids` and `max_new_tokens` is: "
+                                 f"{gs['max_new_tokens'] + P}. This exceeds the `max_target_positions` of the Whisper "
+                                 f"model: {cfg.max_target_positions}.")
+            max_total = P + int(gs["max_new_tokens"])
+        else:
+            max_total = int(gs["max_length"])
+        self.stno_mask = stno_mask
+        enc = self.model.get_encoder()
+        input_stride = 2
+        num_segment_frames = input_stride * cfg.max_source_positions
+        time_precision = 0.02
+        total_frames = input_features.shape[-1]
+        if attention_mask is not None:
+            max_frames = attention_mask.sum(-1).cpu().to(torch.long)
+        else:
+            max_frames = torch.full((B0,), total_frames, dtype=torch.long)
+        seek = torch.zeros(B0, dtype=torch.long)
+        rules = dict(eos=gs["eos"], pad=gs["pad"], no_timestamps=gs["no_timestamps"], ts_begin=gs["ts_begin"],
+                     max_initial_timestamp_index=gs["max_initial_timestamp_index"],
+                     timestamp_rules=gs["return_timestamps"],
+                     suppress_bitmap=self._suppress_bitmap(gs["suppress_tokens"], dev))
+        segments: List[List[dict]] = [[] for _ in range(B0)]
+        batch_idx_map = list(range(B0))
+        feats = input_features
+        while bool((seek < max_frames).any()):
+            # drop finished recordings from the batch (HF:_maybe_reduce_batch)
+            keep = [i for i, prev in enumerate(batch_idx_map) if seek[prev] < max_frames[prev]]
+            if len(keep) != len(batch_idx_map):
+                feats = feats[keep]
+                batch_idx_map = [batch_idx_map[i] for i in keep]
+            cur = len(batch_idx_map)
+            time_offset = seek.to(torch.float64) * time_precision / input_stride
+            seek_num_frames = (max_frames - seek).clamp(max=num_segment_frames)
+            seg_in, seg_stno = [], []
+            for i, prev in enumerate(batch_idx_map):
+                s0, n = int(seek[prev]), int(seek_num_frames[prev])
+                f = feats[i:i + 1, :, s0:s0 + n]
+                if f.shape[-1] < num_segment_frames:  # HF:_get_input_segment pads the mel with zeros
+                    f = torch.nn.functional.pad(f, (0, num_segment_frames - f.shape[-1]))
+                seg_in.append(f)
+                if stno_mask is not None:  # generation.py:73-118: STNO index = mel frame // 2, silence-padded
+                    v0 = s0 // 2
+                    nv = int((max_frames[prev] // 2 - v0).clamp(max=num_segment_frames // 2))
+                    m = stno_mask[prev:prev + 1, :, v0:v0 + nv]
+                    if m.shape[-1] < num_segment_frames // 2:
+                        orig = m.shape[-1]
+                        m = torch.nn.functional.pad(m, (0, num_segment_frames // 2 - orig))
+                        m[0, 0, orig:] = 1.0
+                    seg_stno.append(m)
+            seg_in = torch.cat(seg_in, 0)
+            seg_stno = torch.cat(seg_stno, 0) if seg_stno else None
+            self.stno_mask_seek = seg_stno
+            enr = None
+            if cfg.use_enrollments and enrollments is not None:
+                idx = torch.as_tensor(batch_idx_map, device=dev)
+                enr = {k: v[idx] for k, v in enrollments.items()}
+            hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr).last_hidden_state
+            ids = self.greedy_decode_window(hidden, init_tokens[torch.as_tensor(batch_idx_map, device=dev)], max_total,
+                                            rules)
+            self.stno_mask_seek = None
+            ids_host = ids.cpu()
+            for i, prev in enumerate(batch_idx_map):
+                seq = ids_host[i, P:]
+                # strip padding but keep one eos, then drop the eos (HF:generate_with_fallback post-processing)
+                if seq.numel() and int(seq[-1]) == gs["pad"]:
+                    npad = int((seq == gs["pad"]).sum())
+                    if gs["pad"] == gs["eos"]:
+                        npad -= 1
+                    if npad:
+                        seq = seq[:-npad]
+                if seq.numel() and int(seq[-1]) == gs["eos"]:
+                    seq = seq[:-1]
+                segs, offset = self._retrieve_segment(seq, float(time_offset[prev]), gs["ts_begin"],
+                                                      int(seek_num_frames[prev]), time_precision, input_stride)
+                seek[prev] += offset
+                segments[prev] += segs
+        # pad the concatenated segment tokens on the right (HF:_pad_to_max_length)
+        seqs = [torch.cat([s["tokens"] for s in sl]) if sl else torch.zeros(0, dtype=torch.int64) for sl in segments]
+        n = max([int(s.numel()) for s in seqs] + [0])
+        out = torch.full((B0, n), gs["pad"], dtype=torch.int64)
+        for i, s in enumerate(seqs):
+            out[i, :s.numel()] = s
+        outputs = {"sequences": out.to(dev), "segments": segments}
+        self.encoder_logits = None
+        if return_segments:
+            return outputs
+        if self.tokenizer is not None:
+            return self._fix_timestamps_from_segmentation(outputs)
+        return outputs["sequences"]
+
+    @staticmethod
+    def _retrieve_segment(seq: torch.Tensor, time_offset: float, timestamp_begin: int, seek_num_frames: int,
+                          time_precision: float, input_stride: int):
+        """Split one window's tokens on consecutive timestamp pairs and compute the seek advance
+        (src/models/dicow/generation.py:415-534).  ``seq`` is a CPU int64 tensor without prompt / eos."""
+        toks = seq.tolist()
+        is_ts = [t >= timestamp_begin for t in toks]
+        single_ts_ending = is_ts[-2:] == [False, True]
+        pair_ends = [i + 1 for i in range(len(toks) - 1) if is_ts[i] and is_ts[i + 1]]
+        segments = []
+        if pair_ends:
+            slices = list(pair_ends)
+            if single_ts_ending:
+                slices.append(len(toks))
+            else:
+                slices[-1] += 1  # keep the closing timestamp in the last segment
+            last = 0
+            for k, cur in enumerate(slices):
+                part = seq[last:cur]
+                is_last = k == len(slices) - 1
+                start_pos = int(part[0]) - timestamp_begin
+                end_pos = int(part[-1 if (not is_last or single_ts_ending) else -2]) - timestamp_begin
+                segments.append({"start": torch.tensor(time_offset + start_pos * time_precision, dtype=torch.float64),
+                                 "end": torch.tensor(time_offset + end_pos * time_precision, dtype=torch.float64),
+                                 "tokens": part})
+                last = cur
+            if single_ts_ending:
+                offset = seek_num_frames  # no speech after the last timestamp
+            else:
+                offset = (toks[last - 2] - timestamp_begin) * input_stride  # seek to the last closed segment
+        else:
+            ts = [t for t in toks if t >= timestamp_begin]
+            start_pos, last_pos = 0.0, seek_num_frames // 2
+            skip = False
+            offset = seek_num_frames
+            if len(ts) > 1:
+                start_pos, last_pos = ts[-2] - timestamp_begin, ts[-1] - timestamp_begin
+            elif len(ts) == 1:
+                start_pos = ts[-1] - timestamp_begin
+                if start_pos > 200:  # the segment does not fit the window: roll back (generation.py:501-507)
+                    offset = start_pos * input_stride - 100
+                    skip = True
+            elif len(toks) > 1:
+                pass  # decoding without timestamps: keep the window as one segment
+            else:
+                skip = True
+            if not skip:
+                segments = [{"start": torch.tensor(time_offset + start_pos * time_precision, dtype=torch.float64),
+                             "end": torch.tensor(time_offset + last_pos * time_precision, dtype=torch.float64),
+                             "tokens": seq}]
+                offset = seek_num_frames
+        if offset <= 0:
+            raise ValueError(f"Segment offset: {offset} <= 0. This should not happen!")
+        return segments, int(offset)
+
+    # ---- re-tokenisation of global timestamps (needs the tokenizer) -----------------------------------------------
+    @staticmethod
+    def round_to_nearest_0_02(x) -> Decimal:
+        return (Decimal(str(x)) / Decimal("0.02")).to_integral_value(rounding=ROUND_HALF_UP) * Decimal("0.02")
+
+    def _fix_timestamps_from_segmentation(self, sequences: dict) -> torch.Tensor:
+        """Fold recording-global segment times back into Whisper's 0-30 s timestamp tokens, inserting block markers
+        between 30 s blocks (src/models/dicow/generation.py:322-413).  Text/tokenizer logic on the host."""
+        vocab = self.tokenizer.get_vocab()
+        first_ts, empty_tok = vocab["<|0.00|>"], vocab["Ġ"]
+        thirty, zero = Decimal(30), Decimal(0)
+        results = []
+        for segs in sequences["segments"]:
+            segs = [s for s in segs if len(s["tokens"]) > 0 and not (len(s["tokens"]) == 1 and int(s["tokens"][0]) == first_ts)]
+            pieces = []
+            prev_end = None
+            corr = Decimal(0.0)
+            for s in segs:
+                start = self.round_to_nearest_0_02(s["start"].item())
+                end = self.round_to_nearest_0_02(s["end"].item())
+                toks = s["tokens"]
+                block = (start + corr) // 30
+                if prev_end is not None:
+                    prev_block = (prev_end - Decimal("0.001")) // 30
+                    if block > prev_block:
+                        pieces.append((30, [empty_tok], 30))
+                    for _ in range(int(block - prev_block - 1)):
+                        pieces.append((0, [empty_tok], 30))
+                else:
+                    for _ in range(int(start // 30)):
+                        pieces.append((0, [empty_tok], 30))
+                if (start + corr) // 30 == (end + corr) // 30:
+                    pieces.append(((start + corr) % 30, toks, (end + corr) % 30))
+                elif (end + corr) % 30 == 0:
+                    pieces.append(((start + corr) % 30, toks, 30))
+                    corr = zero
+                else:
+                    new_start = (corr + start) % 30
+                    new_end = (end + corr) % 30
+                    if end - start == thirty:
+                        if float(new_start) % 30.0 == 0.0:
+                            new_end, corr = thirty, zero
+                        else:
+                            corr = Decimal(-0.02)
+                            new_end += Decimal(corr)
+                    else:
+                        corr = zero
+                    pieces.append((new_start, toks, new_end))
+                prev_end = end + corr
+            text = "".join(f"<|{a:.2f}|>{self.tokenizer.decode(t)}<|{b:.2f}|>" for a, t, b in pieces)
+            results.append(self.tokenizer(text)["input_ids"])
+        dev = sequences["sequences"].device
+        n = max([len(r) for r in results] + [0])
+        out = torch.full((len(results), n), self.tokenizer.pad_token_id, dtype=torch.int64)
+        for i, r in enumerate(results):
+            out[i, :len(r)] = torch.tensor(r, dtype=torch.int64)
+        return out.to(dev)

@@ -243,3 +243,155 @@ def logmel(audio: torch.Tensor, mel_filters: torch.Tensor, lengths: Optional[tor
     a.out, a.attention_mask, a.workspace = _ptr(out), _ptr(mask), _ptr(ws)
     _call("dicow_logmel", dev, a, "logmel")
     return (out, mask) if return_attention_mask else out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# decoder step / losses
+# ----------------------------------------------------------------------------------------------------------------
+def gemm_skinny(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int,
+                bias: Optional[torch.Tensor] = None, M: Optional[int] = None, ldo: Optional[int] = None,
+                resid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, pos_stride: int = 0
+                ) -> torch.Tensor:
+    """out[m, :] = epilogue(A[m, :] W^T + bias) for M <= 64 rows (dicow_gemm_skinny_bf16).  ``out`` may be a view
+    into a larger buffer: its data_ptr(), ``ldo`` (row stride, elements) and ``pos`` (device int32 scalar: base
+    advanced by pos * pos_stride elements) address the rows."""
+    dev = _require_cuda(A, W, out, bias, resid, pos)
+    a = _lib.GemmSkinnyArgs()
+    a.struct_size = C.sizeof(_lib.GemmSkinnyArgs)
+    a.A, a.lda = _ptr(A), A.stride(-2) if A.dim() > 1 else A.shape[-1]
+    a.W, a.ldw = _ptr(W), W.stride(0)
+    a.M = M if M is not None else A.numel() // A.shape[-1]
+    a.N, a.K = W.shape
+    a.bias = _ptr(bias)
+    a.out = _ptr(out)
+    a.ldo = ldo if ldo is not None else out.stride(-2)
+    a.epilogue = epilogue
+    a.resid = _ptr(resid)
+    a.ldr = resid.stride(-2) if resid is not None else 0
+    a.pos = _ptr(pos)
+    a.pos_stride = pos_stride
+    _call("dicow_gemm_skinny_bf16", dev, a, "gemm_skinny", 2.0 * a.M * a.N * a.K)
+    return out
+
+
+def decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tk: int,
+                     kv_row_stride: int, kv_batch_stride: int, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """one query row per (batch, head) against a K/V cache (dicow_decode_attention_bf16); q/out bf16 [B, H*64]."""
+    dev = _require_cuda(q, k, v, out, pos)
+    a = _lib.DecodeAttentionArgs()
+    a.struct_size = C.sizeof(_lib.DecodeAttentionArgs)
+    a.Q, a.q_batch_stride = _ptr(q), q.stride(0)
+    a.K, a.V = _ptr(k), _ptr(v)
+    a.kv_row_stride, a.kv_batch_stride = kv_row_stride, kv_batch_stride
+    a.out, a.o_batch_stride = _ptr(out), out.stride(0)
+    a.B, a.H, a.Tk = B, H, Tk
+    a.pos = _ptr(pos)
+    _call("dicow_decode_attention_bf16", dev, a, "decode_attention")
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, posw: torch.Tensor, x: torch.Tensor, *, S: int, past: int = 0,
+                 pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[b, s] = tok[ids[b, p + s]] + posw[p + s] with p = *pos or ``past`` (dicow_embed_tokens); fp32."""
+    global launch_count
+    dev = _require_cuda(ids, tok, posw, x, pos)
+    assert ids.dtype == torch.int64 and tok.dtype == torch.float32 and posw.dtype == torch.float32
+    assert tok.is_contiguous() and posw.is_contiguous() and x.is_contiguous() and x.dtype == torch.float32
+    B = ids.shape[0]
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_embed_tokens(h, _ptr(ids), ids.stride(0), _ptr(tok), _ptr(posw), _ptr(x), B, S,
+                                                    tok.shape[1], tok.shape[0], past, _ptr(pos), _stream(dev))
+    _lib.check(rc, h, "dicow_embed_tokens")
+    launch_count += 1
+    return x
+
+
+def advance(pos: torch.Tensor, by: int = 1) -> None:
+    global launch_count
+    dev = _require_cuda(pos)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_advance(h, _ptr(pos), by, _stream(dev))
+    _lib.check(rc, h, "dicow_advance")
+    launch_count += 1
+
+
+def logits_rules_argmax(logits: torch.Tensor, ids: torch.Tensor, unfinished: torch.Tensor, *, begin_index: int, eos: int,
+                        pad: int, no_timestamps: int, ts_begin: int, cur_len: int = 0,
+                        pos: Optional[torch.Tensor] = None, max_initial_timestamp_index: Optional[int] = None,
+                        suppress_bitmap: Optional[torch.Tensor] = None,
+                        processed_scores: Optional[torch.Tensor] = None, timestamp_rules: bool = True) -> None:
+    """suppress + Whisper timestamp rules + DiCoW EOS exception + argmax; appends the token to ``ids`` in place
+    (dicow_logits_rules_argmax)."""
+    dev = _require_cuda(logits, ids, unfinished, pos, suppress_bitmap, processed_scores)
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and ids.dtype == torch.int64
+    assert unfinished.dtype == torch.int32
+    a = _lib.LogitsRulesArgs()
+    a.struct_size = C.sizeof(_lib.LogitsRulesArgs)
+    a.logits, a.ld = _ptr(logits), logits.stride(0)
+    a.B, a.V = logits.shape
+    a.ids, a.ids_row_stride = _ptr(ids), ids.stride(0)
+    a.pos, a.cur_len = _ptr(pos), cur_len
+    a.begin_index, a.eos, a.pad, a.no_timestamps, a.ts_begin = begin_index, eos, pad, no_timestamps, ts_begin
+    a.max_initial_timestamp_index = -1 if max_initial_timestamp_index is None else max_initial_timestamp_index
+    a.timestamp_rules = 1 if timestamp_rules else 0
+    a.suppress_bitmap = _ptr(suppress_bitmap)
+    a.unfinished = _ptr(unfinished)
+    a.processed_scores = _ptr(processed_scores)
+    _call("dicow_logits_rules_argmax", dev, a, "logits_rules")
+
+
+def suppress_bitmap(token_ids, vocab: int, device) -> torch.Tensor:
+    """int32 bitmap (bit v of word v // 32 set = token v suppressed) for logits_rules_argmax."""
+    words = [0] * ((vocab + 31) // 32)
+    for t in token_ids or ():
+        if 0 <= int(t) < vocab:
+            words[int(t) >> 5] |= 1 << (int(t) & 31)
+    words = [w - (1 << 32) if w >= (1 << 31) else w for w in words]
+    return torch.tensor(words, dtype=torch.int32, device=device)
+
+
+def softlabel_ce(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optional[torch.Tensor] = None, *,
+                 ts_begin: int = 0, smoothing: Optional[torch.Tensor] = None, soft_mode: bool = True) -> torch.Tensor:
+    """Decoder loss (dicow_softlabel_ce): logits fp32 [rows, V]; labels int64 [rows].  Returns a 0-dim fp32 tensor."""
+    dev = _require_cuda(logits, labels, upp_labels, smoothing)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    labels = labels.reshape(-1).contiguous()
+    upp = upp_labels.reshape(-1).contiguous() if upp_labels is not None else None
+    rows, V = logits.shape
+    assert labels.numel() == rows and labels.dtype == torch.int64
+    ws = torch.empty(2 * rows, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    a = _lib.SoftlabelCeArgs()
+    a.struct_size = C.sizeof(_lib.SoftlabelCeArgs)
+    a.logits, a.ld, a.rows, a.V = _ptr(logits), logits.stride(0), rows, V
+    a.labels, a.upp_labels = _ptr(labels), _ptr(upp)
+    a.ts_begin = ts_begin
+    a.n_ts = smoothing.shape[0] if smoothing is not None else 0
+    a.smoothing = _ptr(smoothing)
+    a.soft_mode = 1 if soft_mode else 0
+    a.workspace, a.loss = _ptr(ws), _ptr(loss)
+    _call("dicow_softlabel_ce", dev, a, "softlabel_ce")
+    return loss
+
+
+def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
+    """CTC loss with blank = last class, all frames valid, zero_infinity (dicow_ctc_loss).  logits fp32 [B, T, V+1]
+    contiguous, labels int64 [B, Lmax] (negative = padding)."""
+    dev = _require_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int64
+    if reduction not in ("mean", "sum"):
+        raise NotImplementedError(f"ctc_loss_reduction={reduction}")
+    labels = labels.contiguous()
+    B, T, V1 = logits.shape
+    ws = torch.empty(B * T + 2 * B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    a = _lib.CtcLossArgs()
+    a.struct_size = C.sizeof(_lib.CtcLossArgs)
+    a.logits, a.B, a.T, a.V1 = _ptr(logits), B, T, V1
+    a.labels, a.Lmax = _ptr(labels), labels.shape[1]
+    a.reduction_mean = 1 if reduction == "mean" else 0
+    a.workspace, a.loss = _ptr(ws), _ptr(loss)
+    _call("dicow_ctc_loss", dev, a, "ctc_loss")
+    return loss
