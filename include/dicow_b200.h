@@ -99,6 +99,7 @@ typedef struct {
   const float* fddt_w; /* [4, N] fp32, rows in S,T,N,O order */
   const float* fddt_b; /* [4, N] */
   const float* pos;    /* [Mb, N] fp32 (embed_positions.weight) or NULL */
+  int32_t flags;       /* 0 = auto; bit 0: force the single-CTA kernel; bit 1: force the CTA-pair (cta_group::2) kernel */
 } dicow_gemm_args_t;
 
 DICOW_API int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* args, void* stream);

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU and exports every entry point include/dicow_b200.h declares; the ctypes struct
+mirrors agree with the header field by field (names, order); no compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dicow_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ts_asr_whisper_b200 import build, lib as _lib
+    build.build()
+    return _lib
+
+
+def _header_text():
+    with open(HEADER) as f:
+        return re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+
+
+def test_exports_match_header(lib):
+    declared = re.findall(r"DICOW_API\s+[\w\s\*]+?\b(dicow_\w+)\s*\(", _header_text())
+    assert declared, "no declarations parsed"
+    assert sorted(declared) == sorted(lib.EXPORTED_SYMBOLS)
+    so = lib.load_library()
+    for name in declared:
+        assert hasattr(so, name), f"{name} not exported by libdicow_b200.so"
+    assert so.dicow_abi_version() >= 1
+
+
+@pytest.mark.parametrize("cname,pyname", [("dicow_gemm_args_t", "GemmArgs"), ("dicow_fddt_ln_args_t", "FddtLnArgs"),
+                                          ("dicow_attention_args_t", "AttentionArgs"), ("dicow_logmel_args_t", "LogmelArgs"),
+                                          ("dicow_gemm_skinny_args_t", "GemmSkinnyArgs"),
+                                          ("dicow_decode_attention_args_t", "DecodeAttentionArgs"),
+                                          ("dicow_logits_rules_args_t", "LogitsRulesArgs"),
+                                          ("dicow_softlabel_ce_args_t", "SoftlabelCeArgs"),
+                                          ("dicow_ctc_loss_args_t", "CtcLossArgs")])
+def test_struct_mirrors(lib, cname, pyname):
+    m = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", _header_text(), flags=re.S)
+    assert m, cname
+    fields = []
+    for decl in m.group(1).split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(",")
+        first = names[0].split()[-1]
+        fields.append(first.lstrip("*"))
+        fields += [n.strip().lstrip("*") for n in names[1:]]
+    py = [f[0] for f in getattr(lib, pyname)._fields_]
+    assert py == fields, f"{cname}: header {fields} vs ctypes {py}"
+
+
+def test_no_device_fails_loudly(lib):
+    """without an sm_100 GPU the handle cannot be created and ops raise -- there is no CPU fallback"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ts_asr_whisper_b200 import ops
+    with pytest.raises(lib.DicowError):
+        lib.handle(0)
+    with pytest.raises(ops.DicowError):
+        ops.cast_bf16(torch.zeros(4))

@@ -1,0 +1,72 @@
+"""Host-side generate() logic vs outputs of the reference's own functions (tests/golden/generate_logic.json, made by
+tests/golden/make_golden_generate.py from /root/reference/src/models/dicow/generation.py).  CPU only: these functions are
+token/seek bookkeeping around the CUDA decode loop."""
+import json
+import os
+import types
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "generate_logic.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def cls():
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    return DiCoWForConditionalGeneration
+
+
+def test_retrieve_segment_matches_reference(gold, cls):
+    ts = gold["timestamp_begin"]
+    for name, case in gold["retrieve_segment"].items():
+        seq = torch.tensor(case["tokens"], dtype=torch.int64)
+        segs, offset = cls._retrieve_segment(seq, case["time_offset"], ts, case["seek_num_frames"], 0.02, 2)
+        assert "error" not in case
+        assert offset == case["offset"], name
+        assert len(segs) == len(case["segments"]), name
+        for s, r in zip(segs, case["segments"]):
+            assert s["tokens"].tolist() == r["tokens"], name
+            assert abs(float(s["start"]) - r["start"]) < 1e-9 and abs(float(s["end"]) - r["end"]) < 1e-9, name
+
+
+class RecordingTokenizer:
+    pad_token_id = 50257
+
+    def __init__(self, ts):
+        self.ts, self.texts = ts, []
+
+    def get_vocab(self):
+        return {"<|0.00|>": self.ts, "Ġ": 220}
+
+    def decode(self, toks):
+        return "".join(f" w{int(x)}" for x in toks)
+
+    def __call__(self, text):
+        self.texts.append(text)
+        return {"input_ids": list(text.encode())}
+
+
+def test_fix_timestamps_matches_reference(gold, cls):
+    ts = gold["timestamp_begin"]
+    for name, case in gold["fix_timestamps"].items():
+        tok = RecordingTokenizer(ts)
+        me = types.SimpleNamespace(tokenizer=tok, round_to_nearest_0_02=cls.round_to_nearest_0_02)
+        seq = {"sequences": torch.zeros(1, 1, dtype=torch.int64),
+               "segments": [[{"start": torch.tensor(a, dtype=torch.float64), "end": torch.tensor(b, dtype=torch.float64),
+                              "tokens": torch.tensor(tk, dtype=torch.int64)} for a, b, tk in case["segments"]]]}
+        out = cls._fix_timestamps_from_segmentation(me, seq)
+        assert tok.texts[0] == case["text"], name
+        assert out[0].tolist() == case["ids"], name
+
+
+def test_shift_tokens_right():
+    from ts_asr_whisper_b200.modeling_dicow import shift_tokens_right
+    lab = torch.tensor([[5, 6, -100, -100], [7, 8, 9, 10]])
+    assert shift_tokens_right(lab, 1, 2).tolist() == [[2, 5, 6, 1], [2, 7, 8, 9]]

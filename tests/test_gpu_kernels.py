@@ -15,9 +15,11 @@ def _rel_err(out, ref):
     return ((out.float() - ref.float()).abs().max() / ref.float().abs().max().clamp(min=1e-6)).item()
 
 
+@pytest.mark.parametrize("flags", [1, 2])  # 1 = single-CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles)
 @pytest.mark.parametrize("M,N,K,epi", [(128, 256, 64, 0), (1500, 1280, 1280, 0), (3000, 5120, 1280, 1),
-                                       (3000, 1280, 5120, 2), (777, 1003, 320, 3), (100, 384, 384, 0)])
-def test_gemm(ops, M, N, K, epi):
+                                       (3000, 1280, 5120, 2), (777, 1003, 320, 3), (100, 384, 384, 0),
+                                       (48000, 1280, 1280, 0)])
+def test_gemm(ops, M, N, K, epi, flags):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(M + N + K)
     A = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
@@ -26,20 +28,20 @@ def test_gemm(ops, M, N, K, epi):
     ref = A.float() @ W.float().t() + b
     if epi == ops.EPI_BIAS_BF16:
         out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
-        ops.gemm(A, W, out, epilogue=epi, bias=b)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, flags=flags)
     elif epi == ops.EPI_BIAS_GELU_BF16:
         ref = torch.nn.functional.gelu(ref)
         out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
-        ops.gemm(A, W, out, epilogue=epi, bias=b)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, flags=flags)
     elif epi == ops.EPI_BIAS_F32:
         out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
-        ops.gemm(A, W, out, epilogue=epi, bias=b)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, flags=flags)
     else:
         res = torch.randn(M, N, device=dev, generator=g)
         gate = torch.tensor([0.7], device=dev)
         ref = res + torch.tanh(gate) * ref
         out = res.clone()
-        ops.gemm(A, W, out, epilogue=epi, bias=b, resid=out, gate=gate)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, resid=out, gate=gate, flags=flags)
     torch.cuda.synchronize()
     assert not torch.isnan(out.float()).any()
     assert _rel_err(out, ref) < (1e-2 if out.dtype == torch.bfloat16 else 1e-4)

@@ -123,7 +123,7 @@ def case_fddt(B, T, Cin, Cout, seed=3):
     return describe_err(out, ref, f"conv2+fddt+pos B={B} T={T} Cin={Cin} Cout={Cout}")
 
 
-def timing(M, N, K, epi=ops.EPI_BIAS_BF16, iters=20):
+def timing(M, N, K, epi=ops.EPI_BIAS_BF16, iters=20, flags=0):
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev)
@@ -134,12 +134,12 @@ def timing(M, N, K, epi=ops.EPI_BIAS_BF16, iters=20):
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         kw = {}
     for _ in range(3):
-        ops.gemm(A, W, out, epilogue=epi, bias=b, **kw)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, flags=flags, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.gemm(A, W, out, epilogue=epi, bias=b, **kw)
+        ops.gemm(A, W, out, epilogue=epi, bias=b, flags=flags, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -154,7 +154,7 @@ def timing(M, N, K, epi=ops.EPI_BIAS_BF16, iters=20):
     e1.record()
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / iters
-    print(f"  [timing M={M} N={N} K={K} epi={epi}] {ms:.3f} ms  {tf:.1f} TFLOP/s   (cuBLAS {ms2:.3f} ms "
+    print(f"  [timing M={M} N={N} K={K} epi={epi} flags={flags}] {ms:.3f} ms  {tf:.1f} TFLOP/s   (cuBLAS {ms2:.3f} ms "
           f"{2.0 * M * N * K / ms2 / 1e9:.1f} TFLOP/s)")
     return True
 
@@ -179,6 +179,12 @@ CASES = [
     lambda: timing(48000, 5120, 1280, epi=ops.EPI_BIAS_GELU_BF16),
     lambda: timing(48000, 1280, 5120, epi=ops.EPI_RESIDUAL_F32),
     lambda: timing(48000, 1280, 1280),
+    lambda: timing(48000, 3840, 1280, flags=2),
+    lambda: timing(48000, 5120, 1280, epi=ops.EPI_BIAS_GELU_BF16, flags=2),
+    lambda: timing(48000, 1280, 5120, epi=ops.EPI_RESIDUAL_F32, flags=2),
+    lambda: timing(48000, 1280, 1280, flags=2),
+    lambda: timing(48000, 3840, 1280, flags=1),
+    lambda: timing(48000, 5120, 1280, epi=ops.EPI_BIAS_GELU_BF16, flags=1),
 ]
 
 if __name__ == "__main__":

@@ -292,6 +292,186 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: a cluster of two CTAs (two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2
+// (M = 256).  CTA r stages rows [128 r, 128 r + 128) of the A tile and rows [BN/2 r, BN/2 r + BN/2) of the W tile, so
+// each SM pulls 32 KB instead of 48 KB per 64-deep k block from L2 (the single-CTA kernel sits at the L2 -> SM
+// throughput limit: ncu r01 shows 72-74 % tensor-pipe activity with every stage wait on the TMA side).  The leader CTA
+// (rank 0) issues all MMAs; TMA transaction bytes of both CTAs are signalled on the leader's full barrier; commits are
+// multicast to the empty / accumulator-full barriers of both CTAs; both CTAs' epilogue warps drain their own 128
+// accumulator rows and release the accumulator on the leader's barrier.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmCfg2 {
+  static constexpr int STAGES = 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using Cfg = GemmCfg2<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready (both CTAs, multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained (leader's copy counts both CTAs' epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster = (int)cluster_id_x();
+  const int nclusters = (int)cluster_nctaid_x();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    if (p.K1 > 0) tma_prefetch_desc(&tmA2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / MMA
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA loads its half of the pair's stage) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster; tile < p.total_tiles; tile += nclusters) {
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int b = mt / p.tiles_m;
+      const int m0 = (mt % p.tiles_m) * (2 * BM) + (int)rank * BM;
+      const int n0 = nt * BN + (int)rank * (BN / 2);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (p.K1 > 0 && k0 >= p.K1)
+            tma_load_3d_2cta(&tmA2, bar, sA, k0 - p.K1, m0, b);
+          else
+            tma_load_3d_2cta(&tmA, bar, sA, k0, m0, b);
+          tma_load_2d_2cta(&tmW, bar, sB, k0, n0, kEvictLast);
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster; tile < p.total_tiles; tile += nclusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = make_sdesc_sw128(a_addr, 1024, 0);
+          const uint64_t db = make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);
+            if (kb == p.kblocks - 1) umma_commit_2cta(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kNonEpiWarps) {
+    // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
+    const int e = warp - kNonEpiWarps;
+    const int quad = e & 3;
+    const int half = e >> 2;
+    int it = 0;
+    for (int tile = cluster; tile < p.total_tiles; tile += nclusters, ++it) {
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int b = mt / p.tiles_m;
+      const int m = (mt % p.tiles_m) * (2 * BM) + (int)rank * BM + quad * 32 + lane;
+      const int n_base = nt * BN + half * (BN / 2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const bool row_ok = m < p.Mb;
+
+      float mask[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mask[c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.Mb + m);
+        }
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int n = n_base + c;
+        const int ncols = min(32, p.N - n);
+        if (ncols <= 0) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk<EPI>(p, v, b, m, n, ncols, mask);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still address this CTA's barriers or TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 template <int BN, int EPI>
 int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
                 const GemmParams& p, cudaStream_t stream) {
@@ -306,6 +486,35 @@ int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2,
   kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
+}
+
+template <int BN, int EPI>
+int launch_gemm_2cta(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
+                     const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg2<BN>;
+  auto kfn = gemm_bf16_2cta_kernel<BN, EPI>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  int grid = 2 * (p.total_tiles < ctx->num_sms / 2 ? p.total_tiles : ctx->num_sms / 2);
+  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+int dispatch_epi_2cta(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
+                      const GemmParams& p, cudaStream_t stream) {
+  switch (epi) {
+    case DICOW_EPI_BIAS_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_BF16>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_BIAS_GELU_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_GELU_BF16>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_RESIDUAL_F32: return launch_gemm_2cta<256, DICOW_EPI_RESIDUAL_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_BIAS_F32: return launch_gemm_2cta<256, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_GELU_FDDT_POS_F32:
+      return launch_gemm_2cta<256, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: unknown epilogue %d", epi);
+  }
 }
 
 template <int BN>
@@ -353,9 +562,15 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
     DICOW_REQUIRE(ctx, a->stno && a->fddt_w && a->fddt_b, "dicow_gemm_bf16: FDDT epilogue needs stno/fddt_w/fddt_b");
 
   const int BN = a->N >= 256 ? 256 : 128;
+  // CTA pairs (256-row tiles) when every pair gets at least ~2 tiles; `flags & 1` forces the single-CTA kernel,
+  // `flags & 2` forces pairs (tests / comparison)
+  const long long tiles128 = (long long)a->nb * ceil_div(a->Mb, BM) * ceil_div(a->N, BN);
+  bool two_cta = BN == 256 && tiles128 >= 2 * (long long)ctx->num_sms;
+  if (a->flags & 1) two_cta = false;
+  if ((a->flags & 2) && BN == 256) two_cta = true;
   GemmParams p{};
   p.nb = a->nb, p.Mb = a->Mb, p.N = a->N, p.K = a->K, p.K1 = split ? a->K1 : 0;
-  p.tiles_m = ceil_div(a->Mb, BM);
+  p.tiles_m = ceil_div(a->Mb, two_cta ? 2 * BM : BM);
   p.tiles_n = ceil_div(a->N, BN);
   p.total_tiles = a->nb * p.tiles_m * p.tiles_n;
   p.kblocks = ceil_div(a->K, BK);
@@ -396,10 +611,11 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)BN};
+    uint32_t box[2] = {BK, (uint32_t)(two_cta ? BN / 2 : BN)};
     int rc = make_tmap_bf16(ctx, &tmW, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
+  if (two_cta) return dispatch_epi_2cta(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
   if (BN == 256) return dispatch_epi<256>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
   return dispatch_epi<128>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
 }

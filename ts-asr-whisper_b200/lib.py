@@ -38,7 +38,7 @@ class GemmArgs(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_int64), ("resid_batch_stride", C.c_int64),
         ("gate", C.c_void_p),
         ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64),
-        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p),
+        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p), ("flags", C.c_int32),
     ]
 
 

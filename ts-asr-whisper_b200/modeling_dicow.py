@@ -681,8 +681,11 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             else:
                 skip = True
             if not skip:
+                dur = last_pos * time_precision
+                if len(ts) <= 1:  # the reference multiplies an int64 tensor here, i.e. rounds this product to fp32
+                    dur = float(torch.tensor(last_pos, dtype=torch.int64) * time_precision)
                 segments = [{"start": torch.tensor(time_offset + start_pos * time_precision, dtype=torch.float64),
-                             "end": torch.tensor(time_offset + last_pos * time_precision, dtype=torch.float64),
+                             "end": torch.tensor(time_offset + dur, dtype=torch.float64),
                              "tokens": seq}]
                 offset = seek_num_frames
         if offset <= 0:

@@ -70,7 +70,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
          resid: Optional[torch.Tensor] = None, ldr: int = 0, resid_batch_stride: int = 0,
          gate: Optional[torch.Tensor] = None, stno: Optional[torch.Tensor] = None, stno_batch_stride: int = 0,
          fddt_w: Optional[torch.Tensor] = None, fddt_b: Optional[torch.Tensor] = None,
-         pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+         pos: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """out[b, m, :] = epilogue(sum_k A[b, m, k] W[:, k]) -- see dicow_gemm_bf16 in include/dicow_b200.h.
 
     A: bf16, rows addressed as A + b*a_batch_stride + m*lda.  W: bf16 [N, K].  Defaults describe a plain
@@ -109,6 +109,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     a.fddt_w = _ptr(fddt_w)
     a.fddt_b = _ptr(fddt_b)
     a.pos = _ptr(pos)
+    a.flags = flags
     h = _lib.handle(dev.index or 0)
     with torch.cuda.device(dev), _Timed("gemm", 2.0 * nb * Mb * N * K, dev):
         rc = _lib.load_library().dicow_gemm_bf16(h, C.byref(a), _stream(dev))
