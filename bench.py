@@ -182,14 +182,13 @@ def main():
         return
 
     import torch.distributed as dist
-    from ts_asr_whisper_b200 import ops
+    from ts_asr_whisper_b200 import ops, parallel
     from ts_asr_whisper_b200.modeling import DiCoWEncoder
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200 GPU: the product path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init_process_group("nccl", dev)  # no-op for a single process
 
     with torch.device(dev):
         enc = DiCoWEncoder(turbo_config())
@@ -203,8 +202,7 @@ def main():
     d2h = out_host.numel() * 4
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
@@ -238,10 +236,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], dev)  # multi-GPU numbers are the slowest rank's
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -109,8 +109,10 @@ DICOW_API int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* args, v
  *   x'[b,t,:] = sum_c stno[b,c,t] * (w_c (.) x[b,t,:] + b_c)          src/models/dicow/FDDT.py:52-62
  *   ln        = LayerNorm(x') * gamma + beta  (eps inside the sqrt)     HF:modeling_whisper.py:393,403; encoder.py:228
  * Replaces the ~15 eager element-wise launches of src/models/dicow/encoder.py:205-206 plus nn.LayerNorm.
- * x is updated in place when stno != NULL.  Any of the outputs may be NULL.  fddt_w == NULL selects the bias-only
- * FDDT variant (FDDT.py:43-51).  rows = B*T; row r uses mask column (r / T, :, r % T).
+ * Optional pending residual updates delta1 / delta2 (the bf16 outputs of out_proj and fc2: under the reference's bf16
+ * autocast the Linear output is bf16 and the residual sum fp32, HF:modeling_whisper.py:400,411) are added first:
+ *   x' = FDDT(x + delta1 + delta2).  x' is written back to x when store_x != 0.  Any of the outputs may be NULL.
+ * fddt_w == NULL selects the bias-only FDDT variant (FDDT.py:43-51).  rows = B*T; row r uses mask column (r / T, :, r % T).
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct {
   size_t struct_size;
@@ -126,6 +128,9 @@ typedef struct {
   void* ln_out_bf16; /* [rows, d] bf16 or NULL */
   float* ln_out_f32; /* [rows, d] fp32 or NULL */
   void* x_out_bf16;  /* [rows, d] bf16 copy of x' or NULL */
+  const void* delta1_bf16; /* [rows, d] bf16 or NULL */
+  const void* delta2_bf16; /* [rows, d] bf16 or NULL */
+  int32_t store_x;         /* write x' back into x */
 } dicow_fddt_ln_args_t;
 
 DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* args, void* stream);

@@ -104,3 +104,32 @@ def test_attention(ops, variant, B, H, Tq, Tk, causal):
     ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B, Tq, d)
     assert not torch.isnan(out.float()).any()
     assert _rel_err(out, ref) < 2e-2
+
+
+def test_fddt_layernorm_pending_deltas(ops):
+    """x' = FDDT(x + d1 + d2) with bf16 deltas; store_x=False leaves x untouched"""
+    dev = torch.device("cuda:0")
+    B, T, d = 2, 300, 1280
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(B, T, d, device=dev, generator=g)
+    d1 = (torch.randn(B * T, d, device=dev, generator=g) * 0.3).bfloat16()
+    d2 = (torch.randn(B * T, d, device=dev, generator=g) * 0.3).bfloat16()
+    stno = torch.softmax(3 * torch.randn(B, 4, T, device=dev, generator=g), dim=1)
+    fw = torch.rand(4, d, device=dev, generator=g) + 0.5
+    fb = torch.randn(4, d, device=dev, generator=g) * 0.1
+    gam = torch.rand(d, device=dev, generator=g) + 0.5
+    bet = torch.randn(d, device=dev, generator=g) * 0.1
+    xs = (x + d1.float().view(B, T, d)) + d2.float().view(B, T, d)
+    xr = sum((xs * fw[c] + fb[c]) * stno[:, c, :, None] for c in range(4))
+    lnr = torch.nn.functional.layer_norm(xr, (d,), gam, bet, 1e-5)
+    xx = x.clone()
+    ln_f = torch.empty(B, T, d, device=dev)
+    ops.fddt_layernorm(xx, T=T, stno=stno, fddt_w=fw, fddt_b=fb, gamma=gam, beta=bet, ln_out_f32=ln_f, delta1=d1, delta2=d2)
+    torch.cuda.synchronize()
+    assert (xx - xr).abs().max().item() < 1e-5 and (ln_f - lnr).abs().max().item() < 1e-4
+    x2 = x.clone()
+    ops.fddt_layernorm(x2, gamma=gam, beta=bet, ln_out_f32=ln_f, delta1=d1, store_x=False)
+    torch.cuda.synchronize()
+    assert torch.equal(x2, x)
+    ref2 = torch.nn.functional.layer_norm(x + d1.float().view(B, T, d), (d,), gam, bet, 1e-5)
+    assert (ln_f - ref2).abs().max().item() < 1e-4

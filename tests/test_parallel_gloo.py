@@ -1,0 +1,67 @@
+"""N > 1 host-side logic on CPU: world_size-2 gloo process group (rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from ts_asr_whisper_b200 import parallel
+    parallel.init_process_group("gloo")
+    assert dist.get_world_size() == world
+    # utterance sharding: the shards partition the batch
+    mine = list(parallel.shard_range(11, rank, world))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    # timing reduction = slowest rank
+    mx = parallel.max_over_ranks([10.0 + rank, 5.0 - rank])
+    sm = parallel.sum_over_ranks([float(len(mine))])
+    # gradient exchange: mean over ranks, several buckets
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(7, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[2].requires_grad_(False)
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = parallel.allreduce_gradients(params, bucket_bytes=32)
+    parallel.barrier()
+    q.put((rank, gathered, mx, sm, [p.grad.clone() for p in params], n))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, gathered, mx, sm, grads, n in res:
+        assert sorted(sum(gathered, [])) == list(range(11)) and abs(len(gathered[0]) - len(gathered[1])) <= 1
+        assert mx == [11.0, 5.0] and sm == [11.0]
+        assert n >= 2  # 84-byte and 20-byte gradients with a 32-byte bucket: two collectives
+        assert torch.allclose(grads[0], torch.full((7, 3), 1.5)) and torch.allclose(grads[1], torch.full((5,), 3.0))
+        assert torch.allclose(grads[2], torch.full((2, 2), 3.0 * (rank + 1)))  # frozen parameter: left alone
+
+
+def test_shard_range_partitions():
+    from ts_asr_whisper_b200.parallel import shard_range
+    for n in (0, 1, 7, 32, 33):
+        for world in (1, 2, 3, 8):
+            parts = [list(shard_range(n, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1

@@ -27,6 +27,10 @@ struct FddtLnParams {
   __nv_bfloat16* ln_bf16;  // [rows, d] or NULL
   float* ln_f32;           // [rows, d] or NULL
   __nv_bfloat16* x_bf16;   // [rows, d] bf16 copy of x' or NULL
+  // pending residual updates (bf16 GEMM outputs: out_proj / fc2), added before FDDT: x' = FDDT(x + delta1 + delta2)
+  const __nv_bfloat16* delta1;
+  const __nv_bfloat16* delta2;
+  int store_x;  // write x' back to x
 };
 
 // one warp per row; VPL float4 per lane (d <= 128 * VPL)
@@ -42,6 +46,22 @@ __global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     v[i] = (c < nvec) ? xrow[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int dd = 0; dd < 2; ++dd) {
+    const __nv_bfloat16* dl = dd == 0 ? p.delta1 : p.delta2;
+    if (dl == nullptr) continue;
+    const uint2* drow = reinterpret_cast<const uint2*>(dl + (long long)row * p.d);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const uint2 u = __ldg(drow + c);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        v[i].x += a.x, v[i].y += a.y, v[i].z += b2.x, v[i].w += b2.y;
+      }
+    }
   }
   if (p.stno != nullptr) {
     const int b = row / p.T, t = row - b * p.T;
@@ -67,8 +87,14 @@ __global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
         }
         v[i].x = fmaf(v[i].x, w.x, bb.x), v[i].y = fmaf(v[i].y, w.y, bb.y);
         v[i].z = fmaf(v[i].z, w.z, bb.z), v[i].w = fmaf(v[i].w, w.w, bb.w);
-        xrow[c4] = v[i];
       }
+    }
+  }
+  if (p.store_x) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nvec) xrow[c4] = v[i];
     }
   }
   if (p.x_bf16 != nullptr) {
@@ -181,6 +207,9 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   p.gamma = a->gamma, p.beta = a->beta, p.eps = a->eps;
   p.ln_bf16 = reinterpret_cast<__nv_bfloat16*>(a->ln_out_bf16), p.ln_f32 = a->ln_out_f32;
   p.x_bf16 = reinterpret_cast<__nv_bfloat16*>(a->x_out_bf16);
+  p.delta1 = reinterpret_cast<const __nv_bfloat16*>(a->delta1_bf16);
+  p.delta2 = reinterpret_cast<const __nv_bfloat16*>(a->delta2_bf16);
+  p.store_x = a->store_x;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int rows_per_block = 8;
   const int grid = ceil_div(a->rows, rows_per_block);

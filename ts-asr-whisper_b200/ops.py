@@ -131,10 +131,16 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
                    fddt_w: Optional[torch.Tensor] = None, fddt_b: Optional[torch.Tensor] = None,
                    gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-5,
                    ln_out_bf16: Optional[torch.Tensor] = None, ln_out_f32: Optional[torch.Tensor] = None,
-                   x_out_bf16: Optional[torch.Tensor] = None) -> None:
-    """In-place FDDT on the fp32 residual rows of ``x`` ([..., d], contiguous) + LayerNorm outputs
-    (dicow_fddt_layernorm).  ``stno`` is [B, 4, T] fp32 with ``B*T == rows``."""
-    dev = _require_cuda(x, stno, fddt_w, fddt_b, gamma, beta, ln_out_bf16, ln_out_f32, x_out_bf16)
+                   x_out_bf16: Optional[torch.Tensor] = None, delta1: Optional[torch.Tensor] = None,
+                   delta2: Optional[torch.Tensor] = None, store_x: Optional[bool] = None) -> None:
+    """x' = FDDT(x + delta1 + delta2) on the fp32 residual rows of ``x`` ([..., d], contiguous), written back when
+    ``store_x`` (default: whenever x' differs from x), + LayerNorm outputs (dicow_fddt_layernorm).  ``stno`` is
+    [B, 4, T] fp32 with ``B*T == rows``; the deltas are bf16 [rows, d] (pending out_proj / fc2 outputs)."""
+    dev = _require_cuda(x, stno, fddt_w, fddt_b, gamma, beta, ln_out_bf16, ln_out_f32, x_out_bf16, delta1, delta2)
+    for dl in (delta1, delta2):
+        assert dl is None or (dl.dtype == torch.bfloat16 and dl.is_contiguous() and dl.numel() == x.numel())
+    if store_x is None:
+        store_x = stno is not None or delta1 is not None or delta2 is not None
     assert x.dtype == torch.float32 and x.is_contiguous()
     a = _lib.FddtLnArgs()
     a.struct_size = C.sizeof(_lib.FddtLnArgs)
@@ -154,6 +160,8 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
     a.ln_out_bf16 = _ptr(ln_out_bf16)
     a.ln_out_f32 = _ptr(ln_out_f32)
     a.x_out_bf16 = _ptr(x_out_bf16)
+    a.delta1_bf16, a.delta2_bf16 = _ptr(delta1), _ptr(delta2)
+    a.store_x = 1 if store_x else 0
     _call("dicow_fddt_layernorm", dev, a, "fddt_ln")
 
 

@@ -1,0 +1,90 @@
+"""Data-parallel plumbing over torch.distributed (one process per GPU, NCCL on the GPU box, gloo in CPU tests).
+
+The hot path shards over utterances (30 s windows are independent through mel, encoder, decoder and loss: SURVEY.md
+section 8e): forward / decode run N replicas with NO data-path collective; training has one exchange step, the gradient
+all-reduce (reference: torch DDP via accelerate, scripts/submit_slurm.sh:34, configs/base.yaml:73)."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world() -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment (1 process = 1 GPU)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_process_group(backend: str | None = None, device: torch.device | None = None) -> None:
+    """Join the job's process group when launched under torchrun (WORLD_SIZE > 1); no-op otherwise."""
+    _, world, _ = rank_world()
+    if world <= 1 or dist.is_initialized():
+        return
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+    dist.init_process_group(backend, **kw)
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous, balanced shard of ``n_items`` utterances for ``rank`` (sizes differ by at most one; the shards
+    partition range(n_items)).  Matches what a DistributedSampler-style split gives without padding duplicates."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def max_over_ranks(values: Sequence[float], device: torch.device | str = "cpu") -> List[float]:
+    """Element-wise MAX of per-rank timings (ms): multi-GPU numbers are the slowest rank's."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def sum_over_ranks(values: Sequence[float], device: torch.device | str = "cpu") -> List[float]:
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+def barrier() -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20) -> int:
+    """Average the gradients of ``params`` over the data-parallel group (the one exchange step of training).
+    Gradients are packed into flat buckets of about ``bucket_bytes`` (sized for launch latency over NVLink/NVSwitch, not
+    link count) and all-reduced with SUM then divided by the world size, like torch DDP.  Every parameter with
+    requires_grad takes part -- the reference's "unfreeze after DDP wrap" hazard is not
+    reproduced.  Returns the number of collectives issued."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.requires_grad and p.grad is not None]
+    n_coll, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal n_coll, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        n_coll += 1
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return n_coll
