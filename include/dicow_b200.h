@@ -131,6 +131,7 @@ typedef struct {
   const void* delta1_bf16; /* [rows, d] bf16 or NULL */
   const void* delta2_bf16; /* [rows, d] bf16 or NULL */
   int32_t store_x;         /* write x' back into x */
+  int32_t flags;           /* 0 = default (TMA-pipelined rows); bit 0: warp-per-row kernel, bit 1: column-owner kernel (comparison) */
 } dicow_fddt_ln_args_t;
 
 DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* args, void* stream);

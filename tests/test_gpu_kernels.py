@@ -47,8 +47,9 @@ def test_gemm(ops, M, N, K, epi, flags):
     assert _rel_err(out, ref) < (1e-2 if out.dtype == torch.bfloat16 else 1e-4)
 
 
-@pytest.mark.parametrize("d,T,B", [(384, 1500, 2), (1280, 1500, 2), (128, 50, 3)])
-def test_fddt_layernorm(ops, d, T, B):
+@pytest.mark.parametrize("flags", [0, 1, 2])  # 0 = TMA-pipelined kernel, 1 = warp-per-row, 2 = column-owner
+@pytest.mark.parametrize("d,T,B", [(384, 1500, 2), (1280, 1500, 2), (128, 50, 3), (1280, 1501, 1)])
+def test_fddt_layernorm(ops, d, T, B, flags):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(d)
     x = torch.randn(B, T, d, device=dev, generator=g)
@@ -64,7 +65,7 @@ def test_fddt_layernorm(ops, d, T, B):
     ln_f = torch.empty(B, T, d, device=dev)
     xb = torch.empty(B, T, d, device=dev, dtype=torch.bfloat16)
     ops.fddt_layernorm(xx, T=T, stno=stno, fddt_w=fw, fddt_b=fb, gamma=gam, beta=bet, ln_out_bf16=ln_b,
-                       ln_out_f32=ln_f, x_out_bf16=xb)
+                       ln_out_f32=ln_f, x_out_bf16=xb, flags=flags)
     torch.cuda.synchronize()
     assert (xx - xr).abs().max().item() < 1e-5
     assert (ln_f - lnr).abs().max().item() < 1e-4
@@ -72,7 +73,7 @@ def test_fddt_layernorm(ops, d, T, B):
     assert _rel_err(xb, xr) < 1e-2
     # LayerNorm only
     x2 = x.clone()
-    ops.fddt_layernorm(x2, gamma=gam, beta=bet, ln_out_f32=ln_f)
+    ops.fddt_layernorm(x2, gamma=gam, beta=bet, ln_out_f32=ln_f, flags=flags)
     torch.cuda.synchronize()
     assert torch.equal(x2, x)
     assert (ln_f - torch.nn.functional.layer_norm(x, (d,), gam, bet, 1e-5)).abs().max().item() < 1e-4

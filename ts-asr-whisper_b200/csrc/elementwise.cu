@@ -139,6 +139,321 @@ __global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
   }
 }
 
+// TMA-pipelined variant (default): one producer warp streams rows (x fp32 + up to two bf16 deltas) into a 16-stage
+// shared-memory ring with cp.async.bulk + mbarrier transaction counts; 16 consumer warps each take a row from the ring,
+// so the HBM latency is hidden by the ring depth (160 KB in flight per SM) instead of by occupancy -- the register-
+// resident warp-per-row kernel runs at 16 warps / SM and 40-60 % of the HBM roofline (ncu r01).  The FDDT tables sit in
+// shared memory (read 8 values per element from there instead of through L1 tags).
+constexpr int LT_NW = 16;   // consumer warps
+constexpr int LT_NST = 16;  // ring stages (one row each), a multiple of LT_NW so a stage always belongs to one warp
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int VPL>
+__global__ void __launch_bounds__((LT_NW + 1) * 32, 1) fddt_ln_tma_kernel(const FddtLnParams p) {
+  extern __shared__ __align__(128) uint8_t lsm[];
+  const int d = p.d;
+  const uint32_t xb = d * 4, db = d * 2, stage_bytes = xb + 2 * db;
+  uint8_t* ring = lsm;                                                   // [LT_NST][x | d1 | d2]
+  float* tab = reinterpret_cast<float*>(lsm + LT_NST * stage_bytes);     // [8][d]: w S,T,N,O then b S,T,N,O
+  uint64_t* full = reinterpret_cast<uint64_t*>(tab + (p.stno != nullptr ? 8 * d : 0));
+  uint64_t* empty = full + LT_NST;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int nvec = d >> 2;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LT_NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (p.stno != nullptr) {
+    for (int i = threadIdx.x; i < 4 * nvec; i += blockDim.x) {
+      reinterpret_cast<float4*>(tab)[i] =
+          p.fddt_w != nullptr ? __ldg(reinterpret_cast<const float4*>(p.fddt_w) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      reinterpret_cast<float4*>(tab)[4 * nvec + i] = __ldg(reinterpret_cast<const float4*>(p.fddt_b) + i);
+    }
+  }
+  __syncthreads();
+  // rows of this CTA: row = i * gridDim.x + blockIdx.x
+  const int n_local = (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t tx = xb + (p.delta1 != nullptr ? db : 0) + (p.delta2 != nullptr ? db : 0);
+
+  if (warp == LT_NW) {
+    // ===================== producer =====================
+    for (int i = 0; i < n_local; ++i) {
+      const int st = i % LT_NST;
+      mbar_wait(&empty[st], ((i / LT_NST) & 1) ^ 1);
+      if (elect_one()) {
+        const long long row = (long long)i * gridDim.x + blockIdx.x;
+        uint8_t* dst = ring + st * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], tx);
+        bulk_load(dst, p.x + row * d, xb, &full[st]);
+        if (p.delta1 != nullptr) bulk_load(dst + xb, p.delta1 + row * d, db, &full[st]);
+        if (p.delta2 != nullptr) bulk_load(dst + xb + db, p.delta2 + row * d, db, &full[st]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // ===================== consumers: one row per warp per turn =====================
+  for (int i = warp; i < n_local; i += LT_NW) {
+    const int st = i % LT_NST;
+    const int row = i * (int)gridDim.x + (int)blockIdx.x;
+    mbar_wait(&full[st], (i / LT_NST) & 1);
+    const uint8_t* src = ring + st * stage_bytes;
+    float4 v[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = (c < nvec) ? reinterpret_cast<const float4*>(src)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+      if ((dd == 0 ? p.delta1 : p.delta2) == nullptr) continue;
+      const uint2* dr = reinterpret_cast<const uint2*>(src + xb + dd * db);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nvec) {
+          const uint2 u = dr[c];
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+          const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          v[k].x += a.x, v[k].y += a.y, v[k].z += b2.x, v[k].w += b2.y;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // the row is in registers: the stage may be refilled
+    if (p.stno != nullptr) {
+      const int b = row / p.T, t = row - b * p.T;
+      float m[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m[c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.T + t);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < nvec) {
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f), bb = w;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 wc = reinterpret_cast<const float4*>(tab + c * d)[c4];
+            const float4 bc = reinterpret_cast<const float4*>(tab + (4 + c) * d)[c4];
+            w.x = fmaf(m[c], wc.x, w.x), w.y = fmaf(m[c], wc.y, w.y), w.z = fmaf(m[c], wc.z, w.z), w.w = fmaf(m[c], wc.w, w.w);
+            bb.x = fmaf(m[c], bc.x, bb.x), bb.y = fmaf(m[c], bc.y, bb.y), bb.z = fmaf(m[c], bc.z, bb.z),
+            bb.w = fmaf(m[c], bc.w, bb.w);
+          }
+          v[k].x = fmaf(v[k].x, w.x, bb.x), v[k].y = fmaf(v[k].y, w.y, bb.y);
+          v[k].z = fmaf(v[k].z, w.z, bb.z), v[k].w = fmaf(v[k].w, w.w, bb.w);
+        }
+      }
+    }
+    if (p.store_x) {
+      float4* xrow = reinterpret_cast<float4*>(p.x + (long long)row * d);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < nvec) xrow[c4] = v[k];
+      }
+    }
+    if (p.x_bf16 != nullptr) {
+      uint2* o = reinterpret_cast<uint2*>(p.x_bf16 + (long long)row * d);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c4 = lane + 32 * k;
+        if (c4 < nvec) o[c4] = make_uint2(pack_bf16(v[k].x, v[k].y), pack_bf16(v[k].z, v[k].w));
+      }
+    }
+    if (p.gamma == nullptr) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);  // padded lanes hold zeros
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + 32 * k < nvec) {
+        const float a = v[k].x - mean, b2 = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+        q += (a * a + b2 * b2) + (c * c + e * e);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + p.eps);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c4 = lane + 32 * k;
+      if (c4 < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+        float4 y;
+        y.x = fmaf((v[k].x - mean) * rstd, g.x, be.x);
+        y.y = fmaf((v[k].y - mean) * rstd, g.y, be.y);
+        y.z = fmaf((v[k].z - mean) * rstd, g.z, be.z);
+        y.w = fmaf((v[k].w - mean) * rstd, g.w, be.w);
+        if (p.ln_bf16 != nullptr)
+          reinterpret_cast<uint2*>(p.ln_bf16 + (long long)row * d)[c4] =
+              make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+        if (p.ln_f32 != nullptr) reinterpret_cast<float4*>(p.ln_f32 + (long long)row * d)[c4] = y;
+      }
+    }
+  }
+}
+
+template <int VPL>
+int launch_fddt_ln_tma(dicow_ctx* ctx, const FddtLnParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)LT_NST * 8 * p.d + (p.stno != nullptr ? (size_t)32 * p.d : 0) + 2 * LT_NST * 8 + 128;
+  auto kfn = fddt_ln_tma_kernel<VPL>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int grid = p.rows < ctx->num_sms ? p.rows : ctx->num_sms;
+  kfn<<<grid, (LT_NW + 1) * 32, smem, stream>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+// Column-owner variant (default): thread t owns the float4 column t of every row its CTA processes, so the FDDT tables
+// (4 classes x {w, b}) and the LayerNorm affine parameters of that column live in registers for the whole kernel --
+// the warp-per-row kernel above re-reads 8 table values per element through L1 (40 KB per row against 10 KB of HBM
+// data; ncu r01: l1tex 60 %, DRAM 40 %).  A CTA handles ROWS rows per iteration; the two LayerNorm reductions go through
+// shared memory once per iteration for all ROWS rows together.
+constexpr int LN_ROWS = 4;
+
+__global__ void __launch_bounds__(512) fddt_ln_cols_kernel(const FddtLnParams p, const int row_groups) {
+  __shared__ float red[2][32][LN_ROWS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int nvec = p.d >> 2;
+  const bool own = tid < nvec;  // threads past d/4 only take part in the reductions
+  float4 tw[4], tb[4], g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+  const bool has_fddt = p.stno != nullptr;
+  if (own) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tw[c] = make_float4(1.f, 1.f, 1.f, 1.f);
+      tb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_fddt) {
+        if (p.fddt_w != nullptr) tw[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_w + (long long)c * p.d) + tid);
+        tb[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_b + (long long)c * p.d) + tid);
+      }
+    }
+    if (p.gamma != nullptr) {
+      g4 = __ldg(reinterpret_cast<const float4*>(p.gamma) + tid);
+      b4 = __ldg(reinterpret_cast<const float4*>(p.beta) + tid);
+    }
+  }
+  const float inv_d = 1.0f / (float)p.d;
+  for (int grp = blockIdx.x; grp < row_groups; grp += gridDim.x) {
+    const int row0 = grp * LN_ROWS;
+    float4 v[LN_ROWS];
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) {
+      const int row = row0 + r;
+      v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (own && row < p.rows) v[r] = reinterpret_cast<const float4*>(p.x + (long long)row * p.d)[tid];
+    }
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+      const __nv_bfloat16* dl = dd == 0 ? p.delta1 : p.delta2;
+      if (dl == nullptr) continue;
+#pragma unroll
+      for (int r = 0; r < LN_ROWS; ++r) {
+        const int row = row0 + r;
+        if (own && row < p.rows) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(dl + (long long)row * p.d) + tid);
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          v[r].x += a.x, v[r].y += a.y, v[r].z += c.x, v[r].w += c.y;
+        }
+      }
+    }
+    if (has_fddt) {
+#pragma unroll
+      for (int r = 0; r < LN_ROWS; ++r) {
+        const int row = row0 + r;
+        if (own && row < p.rows) {
+          const int b = row / p.T, t = row - b * p.T;
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f), bb = w;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float m = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.T + t);
+            w.x = fmaf(m, tw[c].x, w.x), w.y = fmaf(m, tw[c].y, w.y), w.z = fmaf(m, tw[c].z, w.z), w.w = fmaf(m, tw[c].w, w.w);
+            bb.x = fmaf(m, tb[c].x, bb.x), bb.y = fmaf(m, tb[c].y, bb.y), bb.z = fmaf(m, tb[c].z, bb.z),
+            bb.w = fmaf(m, tb[c].w, bb.w);
+          }
+          v[r].x = fmaf(v[r].x, w.x, bb.x), v[r].y = fmaf(v[r].y, w.y, bb.y);
+          v[r].z = fmaf(v[r].z, w.z, bb.z), v[r].w = fmaf(v[r].w, w.w, bb.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) {
+      const int row = row0 + r;
+      if (own && row < p.rows) {
+        if (p.store_x) reinterpret_cast<float4*>(p.x + (long long)row * p.d)[tid] = v[r];
+        if (p.x_bf16 != nullptr)
+          reinterpret_cast<uint2*>(p.x_bf16 + (long long)row * p.d)[tid] =
+              make_uint2(pack_bf16(v[r].x, v[r].y), pack_bf16(v[r].z, v[r].w));
+      }
+    }
+    if (p.gamma == nullptr) continue;  // uniform
+    // LayerNorm over d: mean, then centred variance (two-pass in fp32, eps inside the sqrt like nn.LayerNorm)
+    float s[LN_ROWS];
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) s[r] = warp_sum((v[r].x + v[r].y) + (v[r].z + v[r].w));
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < LN_ROWS; ++r) red[0][warp][r] = s[r];
+    }
+    __syncthreads();
+    float mean[LN_ROWS], q[LN_ROWS];
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[0][w][r];
+      mean[r] = t * inv_d;
+      float a = 0.f;
+      if (own) {
+        const float e0 = v[r].x - mean[r], e1 = v[r].y - mean[r], e2 = v[r].z - mean[r], e3 = v[r].w - mean[r];
+        a = (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+      }
+      q[r] = warp_sum(a);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < LN_ROWS; ++r) red[1][warp][r] = q[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) {
+      const int row = row0 + r;
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[1][w][r];
+      const float rstd = rsqrtf(t * inv_d + p.eps);
+      if (own && row < p.rows) {
+        float4 y;
+        y.x = fmaf((v[r].x - mean[r]) * rstd, g4.x, b4.x);
+        y.y = fmaf((v[r].y - mean[r]) * rstd, g4.y, b4.y);
+        y.z = fmaf((v[r].z - mean[r]) * rstd, g4.z, b4.z);
+        y.w = fmaf((v[r].w - mean[r]) * rstd, g4.w, b4.w);
+        if (p.ln_bf16 != nullptr)
+          reinterpret_cast<uint2*>(p.ln_bf16 + (long long)row * p.d)[tid] =
+              make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+        if (p.ln_f32 != nullptr) reinterpret_cast<float4*>(p.ln_f32 + (long long)row * p.d)[tid] = y;
+      }
+    }
+    // red[0] is rewritten only after the next iteration's loads and a full pass of arithmetic, but a fast warp could
+    // still race a slow one reading red[1]: the first __syncthreads of the next iteration orders red[0] writes after
+    // these reads only for red[0]; keep the two buffers disjoint and re-synchronise before reuse
+    __syncthreads();
+  }
+}
+
 // input_features fp32 [B, C, F] -> channels-last bf16 [B, F + 2, C] with zero rows 0 and F+1
 // (the zero-padded buffer conv1's implicit GEMM reads; reference: encoder.py:167 nn.Conv1d(padding=1))
 __global__ void __launch_bounds__(256) features_to_cl_kernel(const float* __restrict__ in,
@@ -196,8 +511,8 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;
   dicow_ctx* ctx = h;
   DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_fddt_ln_args_t), "dicow_fddt_layernorm: bad args struct");
-  DICOW_REQUIRE(ctx, a->x != nullptr && a->rows >= 1 && a->d >= 4 && (a->d % 4) == 0 && a->d <= 1280,
-                "dicow_fddt_layernorm: need x, rows>=1, d%%4==0, d<=1280 (got rows=%d d=%d)", a->rows, a->d);
+  DICOW_REQUIRE(ctx, a->x != nullptr && a->rows >= 1 && a->d >= 4 && (a->d % 4) == 0 && a->d <= 2048 && (a->d <= 1280 || a->d >= 128),
+                "dicow_fddt_layernorm: need x, rows>=1, d%%4==0, d<=2048 (got rows=%d d=%d)", a->rows, a->d);
   DICOW_REQUIRE(ctx, a->stno == nullptr || (a->fddt_b != nullptr && a->T >= 1 && (a->rows % a->T) == 0),
                 "dicow_fddt_layernorm: FDDT needs fddt_b and rows %% T == 0");
   DICOW_REQUIRE(ctx, a->gamma == nullptr || a->beta != nullptr, "dicow_fddt_layernorm: gamma without beta");
@@ -211,6 +526,27 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   p.delta2 = reinterpret_cast<const __nv_bfloat16*>(a->delta2_bf16);
   p.store_x = a->store_x;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // default: TMA-pipelined kernel (needs 16-byte rows: d % 8 == 0); flags bit 0 -> warp-per-row, bit 1 -> column-owner
+  if ((a->d % 8) == 0 && a->d <= 1280 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(a->delta1_bf16) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->delta2_bf16) % 16) == 0) {
+    switch (ceil_div(a->d, 128)) {
+#define DICOW_CASE(V) \
+  case V: return launch_fddt_ln_tma<V>(ctx, p, stream);
+      DICOW_CASE(1) DICOW_CASE(2) DICOW_CASE(3) DICOW_CASE(4) DICOW_CASE(5) DICOW_CASE(6) DICOW_CASE(7) DICOW_CASE(8)
+      DICOW_CASE(9) DICOW_CASE(10)
+#undef DICOW_CASE
+      default: break;
+    }
+  }
+  if (a->d >= 128 && a->d <= 2048 && (a->flags & 2)) {  // column-owner kernel (comparison)
+    const int threads = ceil_div(a->d / 4, 32) * 32;
+    const int groups = ceil_div(a->rows, LN_ROWS);
+    const int per_sm = threads >= 512 ? 2 : (2048 / threads > 6 ? 6 : 2048 / threads);
+    const int grid2 = groups < ctx->num_sms * per_sm ? groups : ctx->num_sms * per_sm;
+    fddt_ln_cols_kernel<<<grid2, threads, 0, stream>>>(p, groups);
+    DICOW_CUDA_OK(ctx, cudaGetLastError());
+    return DICOW_OK;
+  }
   const int rows_per_block = 8;
   const int grid = ceil_div(a->rows, rows_per_block);
   const int vpl = ceil_div(a->d, 128);

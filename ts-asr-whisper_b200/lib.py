@@ -52,7 +52,7 @@ class FddtLnArgs(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("eps", C.c_float),
         ("ln_out_bf16", C.c_void_p), ("ln_out_f32", C.c_void_p), ("x_out_bf16", C.c_void_p),
-        ("delta1_bf16", C.c_void_p), ("delta2_bf16", C.c_void_p), ("store_x", C.c_int32),
+        ("delta1_bf16", C.c_void_p), ("delta2_bf16", C.c_void_p), ("store_x", C.c_int32), ("flags", C.c_int32),
     ]
 
 

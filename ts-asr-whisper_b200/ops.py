@@ -132,7 +132,7 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
                    gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-5,
                    ln_out_bf16: Optional[torch.Tensor] = None, ln_out_f32: Optional[torch.Tensor] = None,
                    x_out_bf16: Optional[torch.Tensor] = None, delta1: Optional[torch.Tensor] = None,
-                   delta2: Optional[torch.Tensor] = None, store_x: Optional[bool] = None) -> None:
+                   delta2: Optional[torch.Tensor] = None, store_x: Optional[bool] = None, flags: int = 0) -> None:
     """x' = FDDT(x + delta1 + delta2) on the fp32 residual rows of ``x`` ([..., d], contiguous), written back when
     ``store_x`` (default: whenever x' differs from x), + LayerNorm outputs (dicow_fddt_layernorm).  ``stno`` is
     [B, 4, T] fp32 with ``B*T == rows``; the deltas are bf16 [rows, d] (pending out_proj / fc2 outputs)."""
@@ -162,6 +162,7 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
     a.x_out_bf16 = _ptr(x_out_bf16)
     a.delta1_bf16, a.delta2_bf16 = _ptr(delta1), _ptr(delta2)
     a.store_x = 1 if store_x else 0
+    a.flags = flags
     _call("dicow_fddt_layernorm", dev, a, "fddt_ln")
 
 
