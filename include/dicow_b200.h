@@ -64,8 +64,10 @@ typedef enum {
   DICOW_EPI_BIAS_GELU_BF16 = 1, /* out_bf16 = gelu_erf(acc + bias)                                              */
   DICOW_EPI_RESIDUAL_F32 = 2,   /* out_f32  = resid + alpha * (acc + bias); alpha = tanh(*gate) or 1 if gate NULL */
   DICOW_EPI_BIAS_F32 = 3,       /* out_f32  = acc + bias                                                        */
-  DICOW_EPI_GELU_FDDT_POS_F32 = 4 /* out_f32 = FDDT(gelu_erf(acc + bias), stno) + pos[m, :]   (conv2 epilogue:
-                                     src/models/dicow/encoder.py:168-179)                                        */
+  DICOW_EPI_GELU_FDDT_POS_F32 = 4, /* out_f32 = FDDT(gelu_erf(acc + bias), stno) + pos[m, :]   (conv2 epilogue:
+                                      src/models/dicow/encoder.py:168-179)                                       */
+  DICOW_EPI_ACCUM_F32 = 5          /* out_f32 += alpha * acc  (atomic fp32 adds; alpha = *gate or 1): weight-gradient
+                                      accumulation, contraction split over CTAs (splits)                          */
 } dicow_epilogue_t;
 
 typedef struct {
@@ -99,7 +101,12 @@ typedef struct {
   const float* fddt_w; /* [4, N] fp32, rows in S,T,N,O order */
   const float* fddt_b; /* [4, N] */
   const float* pos;    /* [Mb, N] fp32 (embed_positions.weight) or NULL */
-  int32_t flags;       /* 0 = auto; bit 0: force the single-CTA kernel; bit 1: force the CTA-pair (cta_group::2) kernel */
+  int32_t flags;       /* 0 = auto; bit 0: force the single-CTA kernel; bit 1: force the CTA-pair (cta_group::2) kernel;
+                          bit 2: A is given transposed, At[k][m] with row stride lda (contraction index on the rows);
+                          bit 3: W is given transposed, Wt[k][n] with row stride ldw.  Transposed operands are consumed
+                          MN-major by the tensor core -- no transposed copies: dgrad dX = dY W uses bit 3 with the
+                          forward weight, wgrad dW = dY^T X uses bits 2 | 3 with the activations                      */
+  int32_t splits;      /* DICOW_EPI_ACCUM_F32: 0 = choose, n > 1 = split the contraction n ways, 1 = no split        */
 } dicow_gemm_args_t;
 
 DICOW_API int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* args, void* stream);

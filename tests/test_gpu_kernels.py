@@ -134,3 +134,34 @@ def test_fddt_layernorm_pending_deltas(ops):
     assert torch.equal(x2, x)
     ref2 = torch.nn.functional.layer_norm(x + d1.float().view(B, T, d), (d,), gam, bet, 1e-5)
     assert (ln_f - ref2).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(1500, 1280, 1280), (777, 384, 1536), (128, 256, 64), (3000, 5120, 1280)])
+def test_gemm_backward_variants(ops, M, N, K):
+    """dgrad dX = dY W (W consumed MN-major from its forward layout) and wgrad dW += dY^T X (both operands MN-major,
+    contraction split over CTAs, atomic fp32 accumulation) -- no transposed copies anywhere"""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    X = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    dY = (torch.randn(M, N, device=dev, generator=g) * 0.3).bfloat16()
+    # dgrad
+    dX = torch.full((M, K), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.gemm(dY, W, dX, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T)
+    ref = dY.float() @ W.float()
+    torch.cuda.synchronize()
+    assert not torch.isnan(dX.float()).any()
+    assert _rel_err(dX, ref) < 1e-2
+    # wgrad with accumulation into an existing gradient
+    dW0 = torch.randn(N, K, device=dev, generator=g)
+    dW = dW0.clone()
+    ops.gemm(dY, X, dW, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T)
+    ref = dW0 + dY.float().t() @ X.float()
+    torch.cuda.synchronize()
+    assert _rel_err(dW, ref) < 2e-3
+    # explicit single split and alpha scaling
+    dW2 = torch.zeros(N, K, device=dev)
+    alpha = torch.tensor([0.125], device=dev)
+    ops.gemm(dY, X, dW2, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, splits=1, gate=alpha)
+    torch.cuda.synchronize()
+    assert _rel_err(dW2, 0.125 * (dY.float().t() @ X.float())) < 2e-3

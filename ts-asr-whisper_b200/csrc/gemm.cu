@@ -28,6 +28,7 @@ constexpr int kGemmThreads = (kNonEpiWarps + kEpiWarps) * 32;
 struct GemmParams {
   int nb, Mb, N, K, K1;
   int tiles_m, tiles_n, total_tiles, kblocks;
+  int splits, kb_per_split;  // split-K (DICOW_EPI_ACCUM_F32 only): work item = (tile, split)
   const float* bias;
   void* out;
   long long ldo, out_bs;
@@ -110,6 +111,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
           if (j < ncols) v[j] = fmaf(alpha, v[j], r[j]);
       }
     }
+    if constexpr (EPI == DICOW_EPI_ACCUM_F32) {
+      // out += alpha * acc (gradient accumulation / split-K partial sums): fp32 reductions at L2, no read-back
+      const float alpha = (p.gate != nullptr) ? __ldg(p.gate) : 1.0f;
+      if (ncols == 32 && p.out_vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(alpha * v[j]),
+                       "f"(alpha * v[j + 1]), "f"(alpha * v[j + 2]), "f"(alpha * v[j + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) atomicAdd(o + j, alpha * v[j]);
+      }
+      return;
+    }
     if constexpr (EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
       // FDDT.forward (src/models/dicow/FDDT.py:52-62): sum_c (w_c * x + b_c) * m_c, classes S,T,N,O
 #pragma unroll
@@ -138,7 +155,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
   }
 }
 
-template <int BN, int EPI>
+// A_MN / B_MN: the operand is given transposed in memory (At[k][m] / Wt[k][n], contraction index on the rows) and is
+// consumed MN-major: the stage holds 64 x 64 atoms ([64 contraction rows] x [64 output elements = 128 B], 8 KB each, one
+// TMA box per atom), descriptors use SBO = 1024 (8 contraction rows), LBO = 8192 (next 64-element atom).  This is what
+// the backward GEMMs need without any transposed copies: dgrad dX = dY W (W row-major [N, K] is the MN-major B operand),
+// wgrad dW = dY^T X (both operands MN-major, contraction over the rows).
+template <int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
@@ -184,24 +206,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x) {
+      const int tile = work % p.total_tiles, split = work / p.total_tiles;
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;
       const int b = mt / p.tiles_m;
       const int m0 = (mt % p.tiles_m) * BM;
       const int n0 = nt * BN;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (p.K1 > 0 && k0 >= p.K1)
-            tma_load_3d(&tmA2, &full_bar[stage], sA, k0 - p.K1, m0, b);
-          else
-            tma_load_3d(&tmA, &full_bar[stage], sA, k0, m0, b);
-          tma_load_2d(&tmW, &full_bar[stage], sB, k0, n0, kEvictLast);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a) tma_load_3d(&tmA, &full_bar[stage], sA + a * 8192, m0 + 64 * a, k0, b);
+          } else {
+            if (p.K1 > 0 && k0 >= p.K1)
+              tma_load_3d(&tmA2, &full_bar[stage], sA, k0 - p.K1, m0, b);
+            else
+              tma_load_3d(&tmA, &full_bar[stage], sA, k0, m0, b);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_2d(&tmW, &full_bar[stage], sB + a * 8192, n0 + 64 * a, k0, kEvictLast);
+          } else {
+            tma_load_2d(&tmW, &full_bar[stage], sB, k0, n0, kEvictLast);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -209,28 +244,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint64_t a_step = A_MN ? 128 : 2;  // per 16-deep MMA: 16 contraction rows (2048 B) or 32 B along K
+    constexpr uint64_t b_step = B_MN ? 128 : 2;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x, ++it) {
+      const int split = work / p.total_tiles;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint64_t da = make_sdesc_sw128(a_addr, 1024, 0);
-        const uint64_t db = make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
+        const uint64_t da = A_MN ? make_sdesc_sw128(a_addr, 1024, 8192) : make_sdesc_sw128(a_addr, 1024, 0);
+        const uint64_t db = B_MN ? make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 8192)
+                                 : make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B along K per step: +2 in the descriptor's (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc,
+                         (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (kb == p.kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -242,7 +283,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = e & 3;  // == warp % 4: the TMEM lane quadrant this warp may access
     const int half = e >> 2; // which half of the BN columns
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x, ++it) {
+      const int tile = work % p.total_tiles;
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;
       const int b = mt / p.tiles_m;
@@ -472,17 +514,18 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool A_MN = false, bool B_MN = false>
 int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
                 const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kfn = gemm_bf16_kernel<BN, EPI>;
+  auto kfn = gemm_bf16_kernel<BN, EPI, A_MN, B_MN>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = p.total_tiles < ctx->num_sms ? p.total_tiles : ctx->num_sms;
+  const int work = p.total_tiles * p.splits;
+  const int grid = work < ctx->num_sms ? work : ctx->num_sms;
   kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
@@ -531,6 +574,34 @@ int dispatch_epi(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensor
   }
 }
 
+// backward-pass variants (MN-major operands): dgrad (W transposed) writes bf16 / fp32, wgrad (both transposed) accumulates
+template <int BN>
+int dispatch_transposed(dicow_ctx* ctx, int epi, bool a_t, bool w_t, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                        const GemmParams& p, cudaStream_t stream) {
+  if (!a_t && w_t) {
+    switch (epi) {
+      case DICOW_EPI_BIAS_BF16: return launch_gemm<BN, DICOW_EPI_BIAS_BF16, false, true>(ctx, tmA, tmA, tmW, p, stream);
+      case DICOW_EPI_BIAS_F32: return launch_gemm<BN, DICOW_EPI_BIAS_F32, false, true>(ctx, tmA, tmA, tmW, p, stream);
+      case DICOW_EPI_ACCUM_F32: return launch_gemm<BN, DICOW_EPI_ACCUM_F32, false, true>(ctx, tmA, tmA, tmW, p, stream);
+      default: break;
+    }
+  } else if (a_t && w_t) {
+    switch (epi) {
+      case DICOW_EPI_ACCUM_F32: return launch_gemm<BN, DICOW_EPI_ACCUM_F32, true, true>(ctx, tmA, tmA, tmW, p, stream);
+      case DICOW_EPI_BIAS_F32: return launch_gemm<BN, DICOW_EPI_BIAS_F32, true, true>(ctx, tmA, tmA, tmW, p, stream);
+      default: break;
+    }
+  } else if (a_t && !w_t) {
+    switch (epi) {
+      case DICOW_EPI_ACCUM_F32: return launch_gemm<BN, DICOW_EPI_ACCUM_F32, true, false>(ctx, tmA, tmA, tmW, p, stream);
+      case DICOW_EPI_BIAS_BF16: return launch_gemm<BN, DICOW_EPI_BIAS_BF16, true, false>(ctx, tmA, tmA, tmW, p, stream);
+      default: break;
+    }
+  }
+  return set_error(ctx, DICOW_ERR_UNSUPPORTED, "dicow_gemm_bf16: epilogue %d is not built for transposed operands (%d, %d)", epi,
+                   (int)a_t, (int)w_t);
+}
+
 }  // namespace
 
 }  // namespace dicow
@@ -547,8 +618,8 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   DICOW_REQUIRE(ctx, a->nb >= 1 && a->Mb >= 1 && a->N >= 1 && a->K >= 8, "dicow_gemm_bf16: bad shape nb=%d Mb=%d N=%d K=%d",
                 a->nb, a->Mb, a->N, a->K);
   DICOW_REQUIRE(ctx, a->A && a->W && a->out, "dicow_gemm_bf16: null operand");
-  DICOW_REQUIRE(ctx, (a->lda % 8) == 0 && (a->ldw % 8) == 0 && (a->K % 8) == 0 && (a->a_batch_stride % 8) == 0,
-                "dicow_gemm_bf16: lda/ldw/K/a_batch_stride must be multiples of 8 elements (16-byte TMA strides)");
+  DICOW_REQUIRE(ctx, (a->lda % 8) == 0 && (a->ldw % 8) == 0 && (a->a_batch_stride % 8) == 0,
+                "dicow_gemm_bf16: lda/ldw/a_batch_stride must be multiples of 8 elements (16-byte TMA strides)");
   DICOW_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->W) % 16) == 0,
                 "dicow_gemm_bf16: A/W must be 16-byte aligned");
   const bool split = a->A2 != nullptr;
@@ -561,12 +632,17 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   if (a->epilogue == DICOW_EPI_GELU_FDDT_POS_F32)
     DICOW_REQUIRE(ctx, a->stno && a->fddt_w && a->fddt_b, "dicow_gemm_bf16: FDDT epilogue needs stno/fddt_w/fddt_b");
 
+  const bool a_t = (a->flags & 4) != 0;  // A given as At[k][m] (row stride lda)
+  const bool w_t = (a->flags & 8) != 0;  // W given as Wt[k][n] (row stride ldw)
+  DICOW_REQUIRE(ctx, !(a_t && split), "dicow_gemm_bf16: a transposed A cannot be split over two sources");
+  DICOW_REQUIRE(ctx, (!a_t || (a->Mb % 8) == 0) && (!w_t || (a->N % 8) == 0),
+                "dicow_gemm_bf16: transposed operands need Mb / N multiples of 8");
   const int BN = a->N >= 256 ? 256 : 128;
   // CTA pairs (256-row tiles) when every pair gets at least ~2 tiles; `flags & 1` forces the single-CTA kernel,
   // `flags & 2` forces pairs (tests / comparison)
   const long long tiles128 = (long long)a->nb * ceil_div(a->Mb, BM) * ceil_div(a->N, BN);
   bool two_cta = BN == 256 && tiles128 >= 2 * (long long)ctx->num_sms;
-  if (a->flags & 1) two_cta = false;
+  if ((a->flags & 1) || a_t || w_t || a->epilogue == DICOW_EPI_ACCUM_F32) two_cta = false;
   if ((a->flags & 2) && BN == 256) two_cta = true;
   GemmParams p{};
   p.nb = a->nb, p.Mb = a->Mb, p.N = a->N, p.K = a->K, p.K1 = split ? a->K1 : 0;
@@ -574,6 +650,15 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   p.tiles_n = ceil_div(a->N, BN);
   p.total_tiles = a->nb * p.tiles_m * p.tiles_n;
   p.kblocks = ceil_div(a->K, BK);
+  p.splits = 1;
+  if (a->epilogue == DICOW_EPI_ACCUM_F32 && a->splits != 1) {
+    // split the contraction so that about two waves of CTAs are busy (explicit a->splits > 1 overrides)
+    int want = a->splits > 1 ? a->splits : ceil_div(2 * ctx->num_sms, p.total_tiles);
+    want = want < 1 ? 1 : (want > p.kblocks ? p.kblocks : want);
+    p.splits = want;
+  }
+  p.kb_per_split = ceil_div(p.kblocks, p.splits);
+  p.splits = ceil_div(p.kblocks, p.kb_per_split);
   p.bias = a->bias;
   p.out = a->out, p.ldo = a->ldo, p.out_bs = a->out_batch_stride;
   p.resid = a->resid, p.ldr = a->ldr, p.resid_bs = a->resid_batch_stride, p.gate = a->gate;
@@ -590,7 +675,14 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
 
   CUtensorMap tmA, tmA2, tmW;
   const int Ka = split ? a->K1 : a->K;
-  {
+  if (a_t) {  // At[k][m]: inner dimension = output rows, boxes of 64 x 64
+    uint64_t dims[3] = {(uint64_t)a->Mb, (uint64_t)a->K, (uint64_t)a->nb};
+    uint64_t bs = a->nb > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * (uint64_t)a->K;
+    uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
+    uint32_t box[3] = {64, BK, 1};
+    int rc = make_tmap_bf16(ctx, &tmA, a->A, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
     uint64_t dims[3] = {(uint64_t)Ka, (uint64_t)a->Mb, (uint64_t)a->nb};
     uint64_t bs = a->nb > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * (uint64_t)a->Mb;
     uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
@@ -608,12 +700,22 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   } else {
     tmA2 = tmA;
   }
-  {
+  if (w_t) {  // Wt[k][n]
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->K};
+    uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {64, BK};
+    int rc = make_tmap_bf16(ctx, &tmW, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)(two_cta ? BN / 2 : BN)};
     int rc = make_tmap_bf16(ctx, &tmW, a->W, 2, dims, strides, box);
     if (rc) return rc;
+  }
+  if (a_t || w_t) {
+    if (BN == 256) return dispatch_transposed<256>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
+    return dispatch_transposed<128>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
   }
   if (two_cta) return dispatch_epi_2cta(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
   if (BN == 256) return dispatch_epi<256>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);

@@ -18,6 +18,9 @@ EPI_BIAS_GELU_BF16 = 1
 EPI_RESIDUAL_F32 = 2
 EPI_BIAS_F32 = 3
 EPI_GELU_FDDT_POS_F32 = 4
+EPI_ACCUM_F32 = 5
+GEMM_A_T = 4  # dicow_gemm_args_t.flags: A given transposed (At[k][m])
+GEMM_W_T = 8  # W given transposed (Wt[k][n])
 
 
 class DicowError(RuntimeError):
@@ -38,7 +41,7 @@ class GemmArgs(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_int64), ("resid_batch_stride", C.c_int64),
         ("gate", C.c_void_p),
         ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64),
-        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p), ("flags", C.c_int32),
+        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p), ("flags", C.c_int32), ("splits", C.c_int32),
     ]
 
 

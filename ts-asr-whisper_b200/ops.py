@@ -10,8 +10,8 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GELU_FDDT_POS_F32, EPI_RESIDUAL_F32,
-                  DicowError)
+from .lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GELU_FDDT_POS_F32,
+                  EPI_RESIDUAL_F32, GEMM_A_T, GEMM_W_T, DicowError)
 
 # number of kernels this module has launched (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -70,7 +70,8 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
          resid: Optional[torch.Tensor] = None, ldr: int = 0, resid_batch_stride: int = 0,
          gate: Optional[torch.Tensor] = None, stno: Optional[torch.Tensor] = None, stno_batch_stride: int = 0,
          fddt_w: Optional[torch.Tensor] = None, fddt_b: Optional[torch.Tensor] = None,
-         pos: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+         pos: Optional[torch.Tensor] = None, flags: int = 0, splits: int = 0, N: Optional[int] = None
+         ) -> torch.Tensor:
     """out[b, m, :] = epilogue(sum_k A[b, m, k] W[:, k]) -- see dicow_gemm_bf16 in include/dicow_b200.h.
 
     A: bf16, rows addressed as A + b*a_batch_stride + m*lda.  W: bf16 [N, K].  Defaults describe a plain
@@ -79,10 +80,17 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     global launch_count
     dev = _require_cuda(A, W, out, bias, A2, resid, gate, stno, fddt_w, fddt_b, pos)
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
-    N, Kw = W.shape
+    if flags & GEMM_W_T:  # W holds Wt[k][n]
+        Kw, Nw = W.shape
+    else:
+        Nw, Kw = W.shape
+    N = Nw if N is None else N
     K = Kw if K is None else K
     if Mb is None:
-        Mb = A.numel() // A.shape[-1] if nb == 1 else A.shape[-2]
+        if flags & GEMM_A_T:  # A holds At[k][m]
+            Mb = A.shape[-1]
+        else:
+            Mb = A.numel() // A.shape[-1] if nb == 1 else A.shape[-2]
     a = _lib.GemmArgs()
     a.struct_size = C.sizeof(_lib.GemmArgs)
     a.A = _ptr(A)
@@ -110,6 +118,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     a.fddt_b = _ptr(fddt_b)
     a.pos = _ptr(pos)
     a.flags = flags
+    a.splits = splits
     h = _lib.handle(dev.index or 0)
     with torch.cuda.device(dev), _Timed("gemm", 2.0 * nb * Mb * N * K, dev):
         rc = _lib.load_library().dicow_gemm_bf16(h, C.byref(a), _stream(dev))
