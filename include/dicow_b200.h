@@ -176,9 +176,38 @@ typedef struct {
   int32_t causal;
   int32_t variant; /* 0 = default (two query tiles per CTA in ping-pong, 2 of every 8 exponentials evaluated as a
                       polynomial on the FMA pipe); 1, 2, 3 = same with 0, 4, 6 of 8; 16+ = single-tile comparison kernels */
+  float* lse;      /* optional [B, H, Tq] fp32: log2(sum_k 2^(s_k log2 e)) per query row, saved for dicow_attention_bwd_bf16 */
 } dicow_attention_args_t;
 
 DICOW_API int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args_t* args, void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention backward (training): dQ, dK, dV from dO, the forward's Q / K / V / O and its saved lse.  Two tcgen05 passes
+ * (dQ; dK + dV) that recompute the probabilities; no atomics.  dO shares O's strides; dK / dV share one stride pair.
+ * workspace: B * H * Tq floats.  Replaces autograd through the SDPA call of HF WhisperAttention
+ * (HF:modeling_whisper.py:342-352) in the fine-tuning step.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  const void* Q;
+  const void* K;
+  const void* V;
+  const void* O;
+  const void* dO;
+  const float* lse; /* [B, H, Tq] from dicow_attention_bf16 */
+  void* dQ;
+  void* dK;
+  void* dV;
+  int32_t B, H, Tq, Tk;
+  int64_t q_row_stride, q_batch_stride;
+  int64_t kv_row_stride, kv_batch_stride;
+  int64_t o_row_stride, o_batch_stride;
+  int64_t dq_row_stride, dq_batch_stride;
+  int64_t dkv_row_stride, dkv_batch_stride;
+  int32_t causal;
+  float* workspace;
+} dicow_attention_bwd_args_t;
+DICOW_API int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_bwd_args_t* args, void* stream);
+
 /* debug aid: clock64 stamps of one CTA's KV loop are written to buf ([steps][8] int64); NULL disables */
 DICOW_API int dicow_debug_set_attention_profile(dicow_handle_t h, void* buf);
 

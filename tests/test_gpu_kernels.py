@@ -165,3 +165,45 @@ def test_gemm_backward_variants(ops, M, N, K):
     ops.gemm(dY, X, dW2, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, splits=1, gate=alpha)
     torch.cuda.synchronize()
     assert _rel_err(dW2, 0.125 * (dY.float().t() @ X.float())) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 3, 1500, 1500, False), (1, 2, 200, 200, True), (2, 2, 37, 300, False),
+                                              (1, 4, 448, 448, True), (3, 2, 64, 64, False)])
+def test_attention_backward(ops, B, H, Tq, Tk, causal):
+    """dQ / dK / dV of the tcgen05 backward passes vs torch autograd through fp32 softmax attention"""
+    dev = torch.device("cuda:0")
+    d = H * 64
+    g = torch.Generator(device=dev).manual_seed(Tq + Tk + H)
+    q = (torch.randn(B, Tq, d, device=dev, generator=g) * 0.35).bfloat16()
+    kv = (torch.randn(B, Tk, 2 * d, device=dev, generator=g) * 1.0).bfloat16()
+    do = (torch.randn(B, Tq, d, device=dev, generator=g) * 0.5).bfloat16()
+    out = torch.empty(B, Tq, d, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Tq, device=dev)
+    ops.attention(q, kv, kv[:, :, d:], out, B=B, H=H, Tq=Tq, Tk=Tk, q_row_stride=d, q_batch_stride=Tq * d,
+                  kv_row_stride=2 * d, kv_batch_stride=Tk * 2 * d, o_row_stride=d, o_batch_stride=Tq * d, causal=causal,
+                  lse=lse)
+    dq = torch.full((B, Tq, d), float("nan"), device=dev, dtype=torch.bfloat16)
+    dkv = torch.full((B, Tk, 2 * d), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.attention_bwd(q, kv, kv[:, :, d:], out, do, lse, dq, dkv, dkv[:, :, d:], B=B, H=H, Tq=Tq, Tk=Tk, q_row_stride=d,
+                      q_batch_stride=Tq * d, kv_row_stride=2 * d, kv_batch_stride=Tk * 2 * d, o_row_stride=d,
+                      o_batch_stride=Tq * d, dq_row_stride=d, dq_batch_stride=Tq * d, dkv_row_stride=2 * d,
+                      dkv_batch_stride=Tk * 2 * d, causal=causal)
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Tq, H, 64).transpose(1, 2).requires_grad_(True)
+    kf = kv[:, :, :d].float().view(B, Tk, H, 64).transpose(1, 2).requires_grad_(True)
+    vf = kv[:, :, d:].float().view(B, Tk, H, 64).transpose(1, 2).requires_grad_(True)
+    s = qf @ kf.transpose(-1, -2)
+    if causal:
+        mask = torch.ones(Tq, Tk, device=dev, dtype=torch.bool).tril(Tk - Tq)
+        s = s.masked_fill(~mask, float("-inf"))
+    ref = torch.softmax(s, -1) @ vf
+    ref.backward(do.float().view(B, Tq, H, 64).transpose(1, 2))
+    # lse saved by the forward: log2 units
+    ref_lse = torch.logsumexp(s, -1) * 1.4426950408889634
+    assert (lse - ref_lse).abs().max().item() < 2e-2
+    rdq = qf.grad.transpose(1, 2).reshape(B, Tq, d)
+    rdk = kf.grad.transpose(1, 2).reshape(B, Tk, d)
+    rdv = vf.grad.transpose(1, 2).reshape(B, Tk, d)
+    assert not torch.isnan(dq.float()).any() and not torch.isnan(dkv.float()).any()
+    print(f"attention bwd rel err dq {_rel_err(dq, rdq):.3e} dk {_rel_err(dkv[:, :, :d], rdk):.3e} dv {_rel_err(dkv[:, :, d:], rdv):.3e}")
+    assert _rel_err(dq, rdq) < 2e-2 and _rel_err(dkv[:, :, :d], rdk) < 2e-2 and _rel_err(dkv[:, :, d:], rdv) < 2e-2

@@ -1,0 +1,376 @@
+// attention_bwd.cu -- flash-attention backward (head_dim 64) on tcgen05, two passes without atomics:
+//
+//   pass dQ  (DKV = false): one CTA owns 128 query rows and streams key blocks of 64:
+//       S = Q K_j^T, dP = dO V_j^T  (SS MMAs, M128 N64 K64)  ->  P = 2^(S log2e - lse), dS = P (dP - D)
+//       dQ += dS K_j                 (A = dS from TMEM, K_j consumed MN-major)
+//   pass dKV (DKV = true): one CTA owns 128 keys and streams query blocks of 64, everything transposed so that the
+//       TMEM lanes are the owned keys:
+//       S^T = K Q_i^T, dP^T = V dO_i^T  ->  P^T, dS^T (the per-query lse / D are per-COLUMN vectors here)
+//       dV += P^T dO_i, dK += dS^T Q_i  (A from TMEM, Q_i / dO_i consumed MN-major)
+//   D[b, h, t] = sum_e dO[b, t, h, e] O[b, t, h, e] comes from a small pre-pass; lse is saved by the forward kernel.
+//
+// Thread == TMEM lane == owned row, P / dS are written back over S / dP in TMEM as bf16 A operands (the forward
+// kernel's trick), TMEM use is 256 columns so two CTAs share an SM and overlap each other's softmax and MMA phases.
+// Both passes recompute S and P, i.e. 2 x the forward's exponentials; no fp32 atomics, results are deterministic.
+//
+// Replaces the autograd backward of the SDPA call inside HF WhisperAttention (HF:modeling_whisper.py:342-352) for the
+// fine-tuning step (src/train.py -> HF Trainer.training_step -> loss.backward()).
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dicow {
+namespace {
+
+constexpr int HD = 64;
+constexpr int OWN = 128;  // owned rows per CTA (TMEM lanes)
+constexpr int BLK = 64;   // streamed rows per block
+constexpr int XSTAGES = 2;
+constexpr int kBwdThreads = 192;
+constexpr uint32_t OWN_BYTES = OWN * HD * 2;  // 16 KB
+constexpr uint32_t BLK_BYTES = BLK * HD * 2;  // 8 KB
+
+// TMEM columns
+constexpr uint32_t SP_COL = 0;     // S (64 fp32) then P (bf16 in the first 32 columns)
+constexpr uint32_t DP_COL = 64;    // dP then dS
+constexpr uint32_t ACC1_COL = 128;  // dQ | dV
+constexpr uint32_t ACC2_COL = 192;  // dK
+constexpr uint32_t TMEM_COLS = 256;
+
+constexpr uint32_t R1_OFF = 0;
+constexpr uint32_t R2_OFF = OWN_BYTES;
+constexpr uint32_t X1_OFF = 2 * OWN_BYTES;
+constexpr uint32_t X2_OFF = X1_OFF + XSTAGES * BLK_BYTES;
+constexpr uint32_t BAR_OFF = X2_OFF + XSTAGES * BLK_BYTES;
+constexpr uint32_t SMEM_BYTES = BAR_OFF + 128 + 1024;
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdParams {
+  int B, H, Tq, Tk, causal;
+  const float* lse;  // [B, H, Tq] log2 units
+  const float* D;    // [B, H, Tq]
+  __nv_bfloat16* out1;  // dQ | dV
+  __nv_bfloat16* out2;  // dK
+  long long o1_rs, o1_bs, o2_rs, o2_bs;
+};
+
+// tmR1 / tmR2: owner tiles (box 64 x 128), tmX1 / tmX2: streamed blocks (box 64 x 64)
+//   DKV = false: R1 = Q, R2 = dO, X1 = K, X2 = V
+//   DKV = true : R1 = K, R2 = V,  X1 = Q, X2 = dO
+template <bool DKV>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
+                     const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                     const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* r_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* x_full = r_full + 1;            // [XSTAGES]
+  uint64_t* x_empty = x_full + XSTAGES;     // [XSTAGES]
+  uint64_t* sdp_full = x_empty + XSTAGES;   // S / dP of the block in TMEM
+  uint64_t* pds_full = sdp_full + 1;        // P / dS written back
+  uint64_t* acc_done = pds_full + 1;        // all accumulating MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * OWN;  // first owned row (query for dQ, key for dKV)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int off = p.Tk - p.Tq;  // causal: key k visible to query t iff k <= t + off
+  // streamed block range [blk0, blk1)
+  int blk0 = 0, blk1;
+  if (!DKV) {
+    int kv_end = p.causal ? min(p.Tk, r0 + OWN + off) : p.Tk;
+    blk1 = (max(kv_end, 1) + BLK - 1) / BLK;
+  } else {
+    blk1 = (p.Tq + BLK - 1) / BLK;
+    if (p.causal) blk0 = min(blk1, max(0, r0 - off) / BLK);  // first query block that can see key r0
+  }
+  const int nblk = blk1 - blk0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmR1);
+    tma_prefetch_desc(&tmR2);
+    tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmX2);
+    mbar_init(r_full, 1);
+    for (int s = 0; s < XSTAGES; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(r_full, 2 * OWN_BYTES);
+      tma_load_4d(&tmR1, r_full, smem + R1_OFF, 0, r0, h, b, kEvictFirst);
+      tma_load_4d(&tmR2, r_full, smem + R2_OFF, 0, r0, h, b, kEvictFirst);
+    }
+    __syncwarp();
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i % XSTAGES;
+      mbar_wait(&x_empty[st], ((i / XSTAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&x_full[st], 2 * BLK_BYTES);
+        tma_load_4d(&tmX1, &x_full[st], smem + X1_OFF + st * BLK_BYTES, 0, (blk0 + i) * BLK, h, b, kEvictLast);
+        tma_load_4d(&tmX2, &x_full[st], smem + X2_OFF + st * BLK_BYTES, 0, (blk0 + i) * BLK, h, b, kEvictLast);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_ss = make_idesc_bf16(OWN, BLK, 0, 0);  // owner tile x streamed block, both K-major
+    constexpr uint32_t idesc_ts = make_idesc_bf16(OWN, HD, 0, 1);   // A from TMEM, streamed block MN-major
+    const uint64_t r1desc = make_sdesc_sw128(smem_u32(smem + R1_OFF), 1024, 0);
+    const uint64_t r2desc = make_sdesc_sw128(smem_u32(smem + R2_OFF), 1024, 0);
+    mbar_wait(r_full, 0);
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i % XSTAGES;
+      mbar_wait(&x_full[st], (i / XSTAGES) & 1);
+      tc_fence_after();
+      const uint32_t x1 = smem_u32(smem + X1_OFF + st * BLK_BYTES), x2 = smem_u32(smem + X2_OFF + st * BLK_BYTES);
+      const uint64_t x1k = make_sdesc_sw128(x1, 1024, 0), x2k = make_sdesc_sw128(x2, 1024, 0);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + SP_COL, r1desc + (uint64_t)(k * 2), x1k + (uint64_t)(k * 2), idesc_ss, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + DP_COL, r2desc + (uint64_t)(k * 2), x2k + (uint64_t)(k * 2), idesc_ss, k != 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      const uint64_t x1m = make_sdesc_sw128(x1, 1024, 1024), x2m = make_sdesc_sw128(x2, 1024, 1024);
+      if (elect_one()) {
+        if (!DKV) {  // dQ += dS K_j
+#pragma unroll
+          for (int k = 0; k < BLK / 16; ++k)
+            umma_bf16_ts(tmem_base + ACC1_COL, tmem_base + DP_COL + k * 8, x1m + (uint64_t)(k * 128), idesc_ts,
+                         (i | k) != 0 ? 1u : 0u);
+        } else {  // dV += P^T dO_i ; dK += dS^T Q_i
+#pragma unroll
+          for (int k = 0; k < BLK / 16; ++k)
+            umma_bf16_ts(tmem_base + ACC1_COL, tmem_base + SP_COL + k * 8, x2m + (uint64_t)(k * 128), idesc_ts,
+                         (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BLK / 16; ++k)
+            umma_bf16_ts(tmem_base + ACC2_COL, tmem_base + DP_COL + k * 8, x1m + (uint64_t)(k * 128), idesc_ts,
+                         (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&x_empty[st]);
+        if (i == nblk - 1) umma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== P / dS (warps 0..3): thread == owned row == TMEM lane =====================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+    const int own_idx = r0 + row;
+    const long long stat_base = ((long long)b * p.H + h) * p.Tq;
+    float my_lse = 0.f, my_D = 0.f;
+    if (!DKV && own_idx < p.Tq) {
+      my_lse = __ldg(p.lse + stat_base + own_idx);
+      my_D = __ldg(p.D + stat_base + own_idx);
+    }
+    for (int i = 0; i < nblk; ++i) {
+      const int c0 = (blk0 + i) * BLK;  // first streamed row of the block (key for dQ, query for dKV)
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {  // 32 streamed rows at a time (register budget: 2 CTAs / SM)
+        uint32_t sr[32], dr[32];
+        tmem_ld_x32(lane_addr + SP_COL + hc * 32, sr);
+        tmem_ld_x32(lane_addr + DP_COL + hc * 32, dr);
+        tmem_ld_wait();
+        uint32_t pp[16], ds[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c0 + hc * 32 + c + u;
+            float lse_c, D_c;
+            bool vis;
+            if (!DKV) {  // row = query own_idx, column = key col
+              lse_c = my_lse, D_c = my_D;
+              vis = own_idx < p.Tq && col < p.Tk && (!p.causal || col <= own_idx + off);
+            } else {  // row = key own_idx, column = query col
+              vis = col < p.Tq && own_idx < p.Tk && (!p.causal || own_idx <= col + off);
+              const int cc = min(col, p.Tq - 1);
+              lse_c = __ldg(p.lse + stat_base + cc);
+              D_c = __ldg(p.D + stat_base + cc);
+            }
+            const float sv = __uint_as_float(sr[c + u]);
+            const float dp = __uint_as_float(dr[c + u]);
+            const float pr = vis ? fast_exp2(fmaf(sv, kLog2e, -lse_c)) : 0.f;
+            pv[u] = pr;
+            dv[u] = pr * (dp - D_c);
+          }
+          pp[c >> 1] = pack_bf16(pv[0], pv[1]);
+          ds[c >> 1] = pack_bf16(dv[0], dv[1]);
+        }
+        // P / dS (bf16) go over the first 32 columns of S / dP: columns [16 hc, 16 hc + 16) were read in half 0 already
+        tmem_st_x16(lane_addr + SP_COL + hc * 16, pp);
+        tmem_st_x16(lane_addr + DP_COL + hc * 16, ds);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // ---- epilogue: accumulators -> bf16 -> global ----
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int limit = DKV ? p.Tk : p.Tq;
+#pragma unroll
+    for (int which = 0; which < (DKV ? 2 : 1); ++which) {
+      __nv_bfloat16* base = which == 0 ? p.out1 : p.out2;
+      const long long rs = which == 0 ? p.o1_rs : p.o2_rs, bs = which == 0 ? p.o1_bs : p.o2_bs;
+      __nv_bfloat16* orow = base + (long long)b * bs + (long long)own_idx * rs + h * HD;
+      uint32_t o[32];
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        tmem_ld_x32(lane_addr + (which == 0 ? ACC1_COL : ACC2_COL) + c, o);
+        tmem_ld_wait();
+        if (own_idx < limit) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 8) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[k]), __uint_as_float(o[k + 1]));
+            v.y = pack_bf16(__uint_as_float(o[k + 2]), __uint_as_float(o[k + 3]));
+            v.z = pack_bf16(__uint_as_float(o[k + 4]), __uint_as_float(o[k + 5]));
+            v.w = pack_bf16(__uint_as_float(o[k + 6]), __uint_as_float(o[k + 7]));
+            *reinterpret_cast<uint4*>(orow + c + k) = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// D[b, h, t] = sum_e dO[b, t, h, e] * O[b, t, h, e]; 8 lanes per (b, t, h) row of 64
+__global__ void __launch_bounds__(256) attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO,
+                                                                 const __nv_bfloat16* __restrict__ O, float* __restrict__ D,
+                                                                 int B, int H, int Tq, long long do_rs, long long do_bs,
+                                                                 long long o_rs, long long o_bs) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long item = gid >> 3;  // (b, t, h)
+  const int sub = (int)(gid & 7);
+  const long long total = (long long)B * Tq * H;
+  float acc = 0.f;
+  int b = 0, t = 0, hh = 0;
+  if (item < total) {
+    hh = (int)(item % H);
+    t = (int)((item / H) % Tq);
+    b = (int)(item / ((long long)H * Tq));
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(dO + b * do_bs + t * do_rs + hh * HD + sub * 8));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(O + b * o_bs + t * o_rs + hh * HD + sub * 8));
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pc[i]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (item < total && sub == 0) D[((long long)b * H + hh) * Tq + t] = acc;
+}
+
+int make_map(dicow_ctx* ctx, CUtensorMap* m, const void* base, int T, int H, int B, long long rs, long long bs, int rows) {
+  uint64_t dims[4] = {(uint64_t)HD, (uint64_t)T, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)rs * 2, (uint64_t)HD * 2, (uint64_t)bs * 2};
+  uint32_t box[4] = {HD, (uint32_t)rows, 1, 1};
+  return make_tmap_bf16(ctx, m, base, 4, dims, strides, box);
+}
+
+}  // namespace
+}  // namespace dicow
+
+using namespace dicow;
+
+extern "C" int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_bwd_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_attention_bwd_args_t),
+                "dicow_attention_bwd_bf16: bad args struct");
+  DICOW_REQUIRE(ctx, a->Q && a->K && a->V && a->O && a->dO && a->lse && a->workspace && a->dQ && a->dK && a->dV,
+                "dicow_attention_bwd_bf16: null operand");
+  DICOW_REQUIRE(ctx, a->B >= 1 && a->H >= 1 && a->Tq >= 1 && a->Tk >= 1 && a->B <= 65535 && a->H <= 65535,
+                "dicow_attention_bwd_bf16: bad shape");
+  DICOW_REQUIRE(ctx, !a->causal || a->Tk >= a->Tq, "dicow_attention_bwd_bf16: causal needs Tk >= Tq");
+  const long long st[] = {a->q_row_stride, a->q_batch_stride, a->kv_row_stride, a->kv_batch_stride, a->o_row_stride,
+                          a->o_batch_stride, a->dq_row_stride, a->dq_batch_stride, a->dkv_row_stride, a->dkv_batch_stride};
+  for (long long s : st) DICOW_REQUIRE(ctx, s >= 0 && (s % 8) == 0, "dicow_attention_bwd_bf16: strides must be multiples of 8");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long qbs = a->B > 1 ? a->q_batch_stride : (long long)a->Tq * a->q_row_stride;
+  const long long kbs = a->B > 1 ? a->kv_batch_stride : (long long)a->Tk * a->kv_row_stride;
+  const long long obs = a->B > 1 ? a->o_batch_stride : (long long)a->Tq * a->o_row_stride;
+  float* D = a->workspace;
+  {
+    const long long threads = (long long)a->B * a->Tq * a->H * 8;
+    attention_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->dO), reinterpret_cast<const __nv_bfloat16*>(a->O), D, a->B, a->H, a->Tq,
+        a->o_row_stride, obs, a->o_row_stride, obs);
+    DICOW_CUDA_OK(ctx, cudaGetLastError());
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  BwdParams p{};
+  p.B = a->B, p.H = a->H, p.Tq = a->Tq, p.Tk = a->Tk, p.causal = a->causal ? 1 : 0;
+  p.lse = a->lse, p.D = D;
+  CUtensorMap mQo, mdOo, mKs, mVs, mKo, mVo, mQs, mdOs;
+  int rc = 0;
+  rc |= make_map(ctx, &mQo, a->Q, a->Tq, a->H, a->B, a->q_row_stride, qbs, OWN);
+  rc |= make_map(ctx, &mdOo, a->dO, a->Tq, a->H, a->B, a->o_row_stride, obs, OWN);
+  rc |= make_map(ctx, &mKs, a->K, a->Tk, a->H, a->B, a->kv_row_stride, kbs, BLK);
+  rc |= make_map(ctx, &mVs, a->V, a->Tk, a->H, a->B, a->kv_row_stride, kbs, BLK);
+  rc |= make_map(ctx, &mKo, a->K, a->Tk, a->H, a->B, a->kv_row_stride, kbs, OWN);
+  rc |= make_map(ctx, &mVo, a->V, a->Tk, a->H, a->B, a->kv_row_stride, kbs, OWN);
+  rc |= make_map(ctx, &mQs, a->Q, a->Tq, a->H, a->B, a->q_row_stride, qbs, BLK);
+  rc |= make_map(ctx, &mdOs, a->dO, a->Tq, a->H, a->B, a->o_row_stride, obs, BLK);
+  if (rc) return DICOW_ERR_CUDA;
+  // pass dQ
+  p.out1 = reinterpret_cast<__nv_bfloat16*>(a->dQ), p.o1_rs = a->dq_row_stride, p.o1_bs = a->dq_batch_stride;
+  p.out2 = nullptr, p.o2_rs = p.o2_bs = 0;
+  attention_bwd_kernel<false><<<dim3(ceil_div(a->Tq, OWN), a->H, a->B), kBwdThreads, SMEM_BYTES, stream>>>(mQo, mdOo, mKs, mVs, p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  // pass dK / dV
+  p.out1 = reinterpret_cast<__nv_bfloat16*>(a->dV), p.o1_rs = a->dkv_row_stride, p.o1_bs = a->dkv_batch_stride;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a->dK), p.o2_rs = a->dkv_row_stride, p.o2_bs = a->dkv_batch_stride;
+  attention_bwd_kernel<true><<<dim3(ceil_div(a->Tk, OWN), a->H, a->B), kBwdThreads, SMEM_BYTES, stream>>>(mKo, mVo, mQs, mdOs, p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}

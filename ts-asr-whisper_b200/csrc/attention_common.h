@@ -14,6 +14,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long o_rs, o_bs;
   long long* prof;  // debug: per-step clock64 stamps of one CTA (dicow_debug_set_attention_profile), else NULL
+  float* lse;       // optional [B, H, Tq]: log2-sum-exp of every score row (training: attention backward), else NULL
 };
 
 // two 128-row query tiles per CTA, ping-pong softmax (attention_fa.cu); emu selects how many of every 8 exponentials run

@@ -327,6 +327,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&pv_done[t], (nkv - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l;
+      if (p.lse != nullptr && q_idx < p.Tq)
+        p.lse[((long long)b * p.H + h) * p.Tq + q_idx] = fmaf(m_used, kLog2e, log2f(l));
       uint32_t o[32];
       __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)q_idx * p.o_rs + h * HD;
 #pragma unroll

@@ -67,7 +67,22 @@ class AttentionArgs(C.Structure):
         ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
         ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
-        ("causal", C.c_int32), ("variant", C.c_int32),
+        ("causal", C.c_int32), ("variant", C.c_int32), ("lse", C.c_void_p),
+    ]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("Q", C.c_void_p), ("K", C.c_void_p), ("V", C.c_void_p), ("O", C.c_void_p), ("dO", C.c_void_p),
+        ("lse", C.c_void_p), ("dQ", C.c_void_p), ("dK", C.c_void_p), ("dV", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32),
+        ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("dq_row_stride", C.c_int64), ("dq_batch_stride", C.c_int64),
+        ("dkv_row_stride", C.c_int64), ("dkv_batch_stride", C.c_int64),
+        ("causal", C.c_int32), ("workspace", C.c_void_p),
     ]
 
 
@@ -172,6 +187,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_cast_f32_bf16.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
     lib.dicow_logmel.argtypes = [vp, C.POINTER(LogmelArgs), vp]
+    lib.dicow_attention_bwd_bf16.argtypes = [vp, C.POINTER(AttentionBwdArgs), vp]
     lib.dicow_gemm_skinny_bf16.argtypes = [vp, C.POINTER(GemmSkinnyArgs), vp]
     lib.dicow_decode_attention_bf16.argtypes = [vp, C.POINTER(DecodeAttentionArgs), vp]
     lib.dicow_embed_tokens.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -191,7 +207,7 @@ EXPORTED_SYMBOLS = [
     "dicow_gemm_bf16", "dicow_fddt_layernorm", "dicow_attention_bf16", "dicow_features_to_channels_last",
     "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile", "dicow_logmel",
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
-    "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss",
+    "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
 ]
 
 

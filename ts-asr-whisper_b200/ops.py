@@ -177,7 +177,8 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tq: int,
               Tk: int, q_row_stride: int, q_batch_stride: int, kv_row_stride: int, kv_batch_stride: int,
-              o_row_stride: int, o_batch_stride: int, causal: bool = False, variant: int = 0) -> torch.Tensor:
+              o_row_stride: int, o_batch_stride: int, causal: bool = False, variant: int = 0,
+              lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(Q K^T) V per (batch, head), head_dim 64 (dicow_attention_bf16).  q/k/v/out may be views into fused
     buffers: only their data_ptr() and the explicit strides (elements) are used."""
     dev = _require_cuda(q, k, v, out)
@@ -190,6 +191,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.o_row_stride, a.o_batch_stride = o_row_stride, o_batch_stride
     a.causal = 1 if causal else 0
     a.variant = variant
+    a.lse = _ptr(lse)
     # algorithmic FLOPs: QK^T + PV = 4 * Tq * Tk * 64 per (batch, head); causal counts the visible half
     fl = 4.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)
     _call("dicow_attention_bf16", dev, a, "attention", fl)
@@ -414,3 +416,30 @@ def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean"
     a.workspace, a.loss = _ptr(ws), _ptr(loss)
     _call("dicow_ctc_loss", dev, a, "ctc_loss")
     return loss
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# backward (training)
+# ----------------------------------------------------------------------------------------------------------------
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, *, B: int, H: int, Tq: int, Tk: int, q_row_stride: int,
+                  q_batch_stride: int, kv_row_stride: int, kv_batch_stride: int, o_row_stride: int, o_batch_stride: int,
+                  dq_row_stride: int, dq_batch_stride: int, dkv_row_stride: int, dkv_batch_stride: int,
+                  causal: bool = False) -> None:
+    """dQ / dK / dV of softmax(Q K^T) V (dicow_attention_bwd_bf16); all tensors bf16 views addressed by explicit
+    strides (elements), ``lse`` fp32 [B, H, Tq] as saved by attention(..., lse=...); ``do`` shares ``o``'s strides."""
+    dev = _require_cuda(q, k, v, o, do, lse, dq, dk, dv)
+    ws = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
+    a = _lib.AttentionBwdArgs()
+    a.struct_size = C.sizeof(_lib.AttentionBwdArgs)
+    a.Q, a.K, a.V, a.O, a.dO, a.lse = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(do), _ptr(lse)
+    a.dQ, a.dK, a.dV = _ptr(dq), _ptr(dk), _ptr(dv)
+    a.B, a.H, a.Tq, a.Tk = B, H, Tq, Tk
+    a.q_row_stride, a.q_batch_stride = q_row_stride, q_batch_stride
+    a.kv_row_stride, a.kv_batch_stride = kv_row_stride, kv_batch_stride
+    a.o_row_stride, a.o_batch_stride = o_row_stride, o_batch_stride
+    a.dq_row_stride, a.dq_batch_stride = dq_row_stride, dq_batch_stride
+    a.dkv_row_stride, a.dkv_batch_stride = dkv_row_stride, dkv_batch_stride
+    a.causal = 1 if causal else 0
+    a.workspace = _ptr(ws)
+    fl = 10.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)  # 5 GEMMs; S and dP are recomputed in the 2nd pass
+    _call("dicow_attention_bwd_bf16", dev, a, "attention_bwd", fl)
