@@ -66,8 +66,10 @@ typedef enum {
   DICOW_EPI_BIAS_F32 = 3,       /* out_f32  = acc + bias                                                        */
   DICOW_EPI_GELU_FDDT_POS_F32 = 4, /* out_f32 = FDDT(gelu_erf(acc + bias), stno) + pos[m, :]   (conv2 epilogue:
                                       src/models/dicow/encoder.py:168-179)                                       */
-  DICOW_EPI_ACCUM_F32 = 5          /* out_f32 += alpha * acc  (atomic fp32 adds; alpha = *gate or 1): weight-gradient
+  DICOW_EPI_ACCUM_F32 = 5,         /* out_f32 += alpha * acc  (atomic fp32 adds; alpha = *gate or 1): weight-gradient
                                       accumulation, contraction split over CTAs (splits)                          */
+  DICOW_EPI_GELU_SAVE_BF16 = 6,    /* training forward: aux_bf16 = acc + bias (pre-activation), out_bf16 = gelu_erf(.)  */
+  DICOW_EPI_DGELU_BF16 = 7         /* backward: out_bf16 = acc * gelu_erf'(aux_bf16)   (aux has out's leading dimension) */
 } dicow_epilogue_t;
 
 typedef struct {
@@ -107,6 +109,7 @@ typedef struct {
                           MN-major by the tensor core -- no transposed copies: dgrad dX = dY W uses bit 3 with the
                           forward weight, wgrad dW = dY^T X uses bits 2 | 3 with the activations                      */
   int32_t splits;      /* DICOW_EPI_ACCUM_F32: 0 = choose, n > 1 = split the contraction n ways, 1 = no split        */
+  void* aux_bf16;      /* DICOW_EPI_GELU_SAVE_BF16 (written) / DICOW_EPI_DGELU_BF16 (read): pre-activation, ld = ldo   */
 } dicow_gemm_args_t;
 
 DICOW_API int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* args, void* stream);
@@ -207,6 +210,80 @@ typedef struct {
   float* workspace;
 } dicow_attention_bwd_args_t;
 DICOW_API int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_bwd_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward of dicow_fddt_layernorm: given dy = dL/d(LayerNorm output) (bf16) and g_in = dL/dx' arriving through the
+ * residual stream (fp32, or NULL), recompute x' = FDDT(x + delta1 + delta2) and write g_out = dL/d(x + delta1 + delta2)
+ * (fp32, + optional bf16 copy for the next dgrad / wgrad GEMM); accumulate (+=) dgamma, dbeta [d] and the FDDT table
+ * gradients dfddt_w, dfddt_b [4, d].  gamma == NULL: no LayerNorm on the path (FDDT backward of g_in only).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  const float* x;
+  const void* delta1_bf16;
+  const void* delta2_bf16;
+  int32_t rows, d, T;
+  const float* stno;
+  int64_t stno_batch_stride;
+  const float* fddt_w;
+  const float* fddt_b;
+  const float* gamma;
+  float eps;
+  const void* dy_bf16;
+  const float* g_in;
+  float* g_out;
+  void* g_out_bf16;
+  float* dgamma;
+  float* dbeta;
+  float* dfddt_w;
+  float* dfddt_b;
+} dicow_ln_bwd_args_t;
+DICOW_API int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_args_t* args, void* stream);
+
+/* out[n] += alpha * sum_rows x[row, n]  (bias gradients); x bf16 (is_bf16 = 1) or fp32, leading dimension ld */
+DICOW_API int dicow_colsum(dicow_handle_t h, const void* x, int is_bf16, int64_t ld, int rows, int N, float* out, float alpha,
+                           void* stream);
+/* col2im of Conv1d(k = 3, padding = 1, stride): dcol bf16 [B, T_out, 3 C] (the dgrad GEMM's output in im2col layout)
+ * -> dx bf16 [B, T, C] addressed by dx_batch_stride / dx_row_stride (elements) */
+DICOW_API int dicow_conv1d_col2im(dicow_handle_t h, const void* dcol_bf16, void* dx_bf16, int B, int T, int T_out, int C,
+                                  int stride, int64_t dx_batch_stride, int64_t dx_row_stride, void* stream);
+
+/* CTC backward (src/models/dicow/encoder.py:123-134 through autograd): dlogits_bf16[b, t, :V1] = loss_scale * dL/dlogits,
+ * columns [V1, ldd) zeroed (ldd: leading dimension, a multiple of 8 so the buffer feeds the wgrad GEMM).
+ * lse: per-row natural-log sum exp (B * T floats, e.g. the first B * T floats of dicow_ctc_loss's workspace).
+ * workspace: (2 * B * T * (2 Lmax + 1) + B) floats. */
+typedef struct {
+  size_t struct_size;
+  const float* logits;
+  const float* lse;
+  int32_t B, T, V1;
+  const int64_t* labels;
+  int32_t Lmax;
+  int32_t reduction_mean;
+  float loss_scale;
+  float* workspace;
+  void* dlogits_bf16;
+  int64_t ldd;
+} dicow_ctc_bwd_args_t;
+DICOW_API int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* args, void* stream);
+
+/* backward of dicow_softlabel_ce: dlogits_bf16[r, :V] = scale * (softmax(logits[r]) - target of the winning case stream),
+ * 0 for masked rows; scale = upstream gradient / (number of unmasked rows | rows) supplied by the caller. */
+typedef struct {
+  size_t struct_size;
+  const float* logits;
+  int64_t ld;
+  int32_t rows, V;
+  const int64_t* labels;
+  const int64_t* upp_labels;
+  int32_t ts_begin, n_ts;
+  const float* smoothing;
+  int32_t soft_mode;
+  float scale;
+  void* dlogits_bf16;
+  int64_t ldd;
+} dicow_softlabel_ce_bwd_args_t;
+DICOW_API int dicow_softlabel_ce_bwd(dicow_handle_t h, const dicow_softlabel_ce_bwd_args_t* args, void* stream);
 
 /* debug aid: clock64 stamps of one CTA's KV loop are written to buf ([steps][8] int64); NULL disables */
 DICOW_API int dicow_debug_set_attention_profile(dicow_handle_t h, void* buf);

@@ -34,7 +34,9 @@ def test_exports_match_header(lib):
 
 @pytest.mark.parametrize("cname,pyname", [("dicow_gemm_args_t", "GemmArgs"), ("dicow_fddt_ln_args_t", "FddtLnArgs"),
                                           ("dicow_attention_args_t", "AttentionArgs"), ("dicow_logmel_args_t", "LogmelArgs"),
-                                          ("dicow_attention_bwd_args_t", "AttentionBwdArgs"),
+                                          ("dicow_attention_bwd_args_t", "AttentionBwdArgs"), ("dicow_ln_bwd_args_t", "LnBwdArgs"),
+                                          ("dicow_ctc_bwd_args_t", "CtcBwdArgs"),
+                                          ("dicow_softlabel_ce_bwd_args_t", "SoftlabelCeBwdArgs"),
                                           ("dicow_gemm_skinny_args_t", "GemmSkinnyArgs"),
                                           ("dicow_decode_attention_args_t", "DecodeAttentionArgs"),
                                           ("dicow_logits_rules_args_t", "LogitsRulesArgs"),

@@ -1,0 +1,596 @@
+// backward.cu -- HBM-bound backward kernels of the fine-tuning step (the GEMM / attention backward live in gemm.cu and
+// attention_bwd.cu):
+//   * LayerNorm backward fused with the FDDT backward, the residual-stream gradient add and the bf16 copy that the
+//     next dgrad / wgrad GEMM consumes; parameter gradients (gamma, beta, the 4 x {w, b} FDDT tables) are column
+//     reductions kept in registers by column-owner threads and flushed with one atomic per column per CTA;
+//   * column sums (bias gradients);
+//   * col2im of the stride-2 subsampling convolutions (dgrad of the implicit-GEMM conv);
+//   * CTC backward (alpha / beta in log space -> d logits) and the decoder cross-entropy backward (softmax - target).
+// Reference semantics: autograd through nn.LayerNorm (HF:modeling_whisper.py:393,403), FDDT.forward
+// (src/models/dicow/FDDT.py:52-62), nn.functional.ctc_loss (src/models/dicow/encoder.py:123-134) and
+// SoftLabelCreator.compute_loss (src/models/dicow/modeling_dicow.py:95-144).
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dicow {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm (+ FDDT) backward
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LB_ROWS = 2;
+
+struct LnBwdParams {
+  const float* x;  // [rows, d] value the forward kernel read (before pending deltas / FDDT)
+  const __nv_bfloat16* delta1;
+  const __nv_bfloat16* delta2;
+  int rows, d, T;
+  const float* stno;
+  long long stno_bs;
+  const float* fddt_w;
+  const float* fddt_b;
+  const float* gamma;          // NULL: no LayerNorm on this path (dy unused)
+  float eps;
+  const __nv_bfloat16* dy;     // [rows, d] gradient w.r.t. the LayerNorm output
+  const float* g_in;           // [rows, d] gradient arriving through the residual stream (or NULL)
+  float* g_out;                // [rows, d] gradient w.r.t. x (== w.r.t. delta1 and delta2)
+  __nv_bfloat16* g_out_bf16;   // optional bf16 copy
+  float* dgamma;               // [d] +=
+  float* dbeta;                // [d] +=
+  float* dfddt_w;              // [4, d] += (or NULL)
+  float* dfddt_b;              // [4, d] +=
+};
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float f4_sum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float4 bf16x4(const uint2 u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void atomic_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// thread t owns float4 column t; a CTA walks over its row pairs; two block reductions per pair
+__global__ void __launch_bounds__(512) ln_fddt_bwd_kernel(const LnBwdParams p, const int row_groups) {
+  __shared__ float red[2][16][LB_ROWS][2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int nvec = p.d >> 2;
+  const bool own = tid < nvec;
+  const bool has_fddt = p.stno != nullptr;
+  const bool has_ln = p.gamma != nullptr;
+  float4 tw[4], tb[4], g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc_dg = g4, acc_db = g4, acc_w[4], acc_b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tw[c] = make_float4(1.f, 1.f, 1.f, 1.f), tb[c] = g4, acc_w[c] = g4, acc_b[c] = g4;
+    if (own && has_fddt) {
+      if (p.fddt_w != nullptr) tw[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_w + (long long)c * p.d) + tid);
+      tb[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_b + (long long)c * p.d) + tid);
+    }
+  }
+  if (own && has_ln) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma) + tid);
+  const float inv_d = 1.0f / (float)p.d;
+  for (int grp = blockIdx.x; grp < row_groups; grp += gridDim.x) {
+    const int row0 = grp * LB_ROWS;
+    float4 xs[LB_ROWS], xp[LB_ROWS], weff[LB_ROWS], dyg[LB_ROWS];
+    float m[LB_ROWS][4];
+#pragma unroll
+    for (int r = 0; r < LB_ROWS; ++r) {
+      const int row = row0 + r;
+      const bool ok = own && row < p.rows;
+      xs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dyg[r] = xs[r];
+      weff[r] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (ok) {
+        xs[r] = reinterpret_cast<const float4*>(p.x + (long long)row * p.d)[tid];
+        if (p.delta1 != nullptr) xs[r] = f4_add(xs[r], bf16x4(__ldg(reinterpret_cast<const uint2*>(p.delta1 + (long long)row * p.d) + tid)));
+        if (p.delta2 != nullptr) xs[r] = f4_add(xs[r], bf16x4(__ldg(reinterpret_cast<const uint2*>(p.delta2 + (long long)row * p.d) + tid)));
+        if (has_ln) dyg[r] = f4_mul(bf16x4(__ldg(reinterpret_cast<const uint2*>(p.dy + (long long)row * p.d) + tid)), g4);
+      }
+      xp[r] = xs[r];
+      if (has_fddt && row < p.rows) {
+        const int b = row / p.T, t = row - b * p.T;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f), bb = w;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          m[r][c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.T + t);
+          w = f4_add(w, f4_scale(tw[c], m[r][c]));
+          bb = f4_add(bb, f4_scale(tb[c], m[r][c]));
+        }
+        weff[r] = w;
+        if (ok) xp[r] = f4_add(f4_mul(xs[r], w), bb);
+      }
+    }
+    float4 dxp[LB_ROWS];  // gradient w.r.t. x' (the LayerNorm input)
+    if (has_ln) {
+      // reduction 1: sum x', sum dy*gamma
+      float s1[LB_ROWS], s2[LB_ROWS];
+#pragma unroll
+      for (int r = 0; r < LB_ROWS; ++r) {
+        s1[r] = warp_sum(own ? f4_sum(xp[r]) : 0.f);
+        s2[r] = warp_sum(f4_sum(dyg[r]));
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < LB_ROWS; ++r) red[0][warp][r][0] = s1[r], red[0][warp][r][1] = s2[r];
+      }
+      __syncthreads();
+      float mean[LB_ROWS], c1[LB_ROWS];
+      float4 xc[LB_ROWS];
+#pragma unroll
+      for (int r = 0; r < LB_ROWS; ++r) {
+        float a = 0.f, b2 = 0.f;
+        for (int w = 0; w < nwarps; ++w) a += red[0][w][r][0], b2 += red[0][w][r][1];
+        mean[r] = a * inv_d, c1[r] = b2 * inv_d;
+        xc[r] = own ? make_float4(xp[r].x - mean[r], xp[r].y - mean[r], xp[r].z - mean[r], xp[r].w - mean[r])
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        s1[r] = warp_sum(f4_sum(f4_mul(xc[r], xc[r])));
+        s2[r] = warp_sum(f4_sum(f4_mul(dyg[r], xc[r])));
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < LB_ROWS; ++r) red[1][warp][r][0] = s1[r], red[1][warp][r][1] = s2[r];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < LB_ROWS; ++r) {
+        const int row = row0 + r;
+        float a = 0.f, b2 = 0.f;
+        for (int w = 0; w < nwarps; ++w) a += red[1][w][r][0], b2 += red[1][w][r][1];
+        const float rstd = rsqrtf(a * inv_d + p.eps);
+        const float c2 = b2 * inv_d * rstd * rstd;  // mean(dy*gamma * xhat) * rstd, with xhat = xc * rstd
+        // dx' = rstd * (dyg - c1 - xhat * mean(dyg * xhat))
+        dxp[r] = make_float4(rstd * (dyg[r].x - c1[r] - xc[r].x * c2), rstd * (dyg[r].y - c1[r] - xc[r].y * c2),
+                             rstd * (dyg[r].z - c1[r] - xc[r].z * c2), rstd * (dyg[r].w - c1[r] - xc[r].w * c2));
+        if (own && row < p.rows) {
+          // dgamma += dy * xhat ; dbeta += dy   (dy = dyg / gamma is avoided: reload dy)
+          const float4 dy = bf16x4(__ldg(reinterpret_cast<const uint2*>(p.dy + (long long)row * p.d) + tid));
+          acc_dg = f4_add(acc_dg, f4_mul(dy, f4_scale(xc[r], rstd)));
+          acc_db = f4_add(acc_db, dy);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < LB_ROWS; ++r) dxp[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < LB_ROWS; ++r) {
+      const int row = row0 + r;
+      if (!(own && row < p.rows)) continue;
+      if (p.g_in != nullptr) dxp[r] = f4_add(dxp[r], reinterpret_cast<const float4*>(p.g_in + (long long)row * p.d)[tid]);
+      float4 g = dxp[r];
+      if (has_fddt) {
+        const float4 dweff = f4_mul(dxp[r], xs[r]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc_w[c] = f4_add(acc_w[c], f4_scale(dweff, m[r][c]));
+          acc_b[c] = f4_add(acc_b[c], f4_scale(dxp[r], m[r][c]));
+        }
+        g = f4_mul(dxp[r], weff[r]);
+      }
+      reinterpret_cast<float4*>(p.g_out + (long long)row * p.d)[tid] = g;
+      if (p.g_out_bf16 != nullptr)
+        reinterpret_cast<uint2*>(p.g_out_bf16 + (long long)row * p.d)[tid] =
+            make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+    }
+    __syncthreads();  // red[] reuse
+  }
+  if (own) {
+    if (has_ln && p.dgamma != nullptr) {
+      atomic_add4(p.dgamma + 4 * tid, acc_dg);
+      atomic_add4(p.dbeta + 4 * tid, acc_db);
+    }
+    if (has_fddt && p.dfddt_b != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (p.dfddt_w != nullptr) atomic_add4(p.dfddt_w + (long long)c * p.d + 4 * tid, acc_w[c]);
+        atomic_add4(p.dfddt_b + (long long)c * p.d + 4 * tid, acc_b[c]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out[n] += sum_rows X[row, n]     (bias gradients);  X bf16 or fp32
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ld, int rows, int N,
+                                                     float* __restrict__ out, float alpha, int rows_per_block) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += (float)X[(long long)r * ld + n];
+  atomicAdd(out + n, alpha * acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// col2im of Conv1d(k = 3, padding 1, stride s):  dX[b, t, c] = sum_k dcol[b, (t + 1 - k) / s, k C + c]
+//   (t + 1 - k) % s == 0 and 0 <= (t + 1 - k) / s < T_out
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx,
+                                                     int B, int T, int T_out, int C, int stride, long long dx_bs,
+                                                     long long dx_rs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * T * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % T);
+  const int b = (int)(i / ((long long)C * T));
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int u = t + 1 - k;
+    if (u >= 0 && (u % stride) == 0 && u / stride < T_out)
+      acc += __bfloat162float(dcol[((long long)b * T_out + u / stride) * (3LL * C) + (long long)k * C + c]);
+  }
+  dx[(long long)b * dx_bs + (long long)t * dx_rs + c] = __float2bfloat16_rn(acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTC backward
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float log_add(float a, float b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  const float mx = fmaxf(a, b);
+  return mx + log1pf(__expf(-fabsf(a - b)));
+}
+
+struct CtcBwdParams {
+  const float* logits;  // [B, T, V1]
+  const float* lse;     // [B * T] natural-log sum exp of every row
+  int T, V1, Lmax;
+  const long long* labels;
+  float* alpha;  // [B, T, S] workspace, S = 2 Lmax + 1
+  float* beta;   // [B, T, S]
+  float* nll;    // [B]
+  int mean, B;
+  __nv_bfloat16* dlogits;  // [B, T, ldd]
+  long long ldd;
+  float loss_scale;  // upstream gradient * (ctc weight)
+};
+
+// alpha and beta lattices: one CTA per (utterance, direction); thread == extended-label state
+__global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p) {
+  extern __shared__ float buf[];  // [2][S]
+  const int b = blockIdx.x, dir = blockIdx.y, s = threadIdx.x;
+  const long long* lab = p.labels + (long long)b * p.Lmax;
+  __shared__ int s_len;
+  if (s == 0) {
+    int n = 0;
+    for (int i = 0; i < p.Lmax; ++i) n += lab[i] >= 0 ? 1 : 0;
+    s_len = n;
+  }
+  __syncthreads();
+  const int L = s_len, S = 2 * L + 1, Sm = 2 * p.Lmax + 1, blank = p.V1 - 1;
+  const bool active = s < S;
+  int cls = blank;
+  bool skip_prev = false, skip_next = false;  // may jump from s-2 (alpha) / to s+2 (beta)
+  if (active && (s & 1)) {
+    cls = (int)lab[s >> 1];
+    skip_prev = s >= 3 && lab[(s >> 1) - 1] != cls;
+    skip_next = s + 2 < S && lab[(s >> 1) + 1] != cls;
+  }
+  const float* lg = p.logits + (long long)b * p.T * p.V1;
+  const float* ls = p.lse + (long long)b * p.T;
+  float* lat = (dir == 0 ? p.alpha : p.beta) + (long long)b * p.T * Sm;
+  float* cur = buf;
+  float* nxt = buf + Sm;
+  if (dir == 0) {
+    if (active) {
+      const float v = (s <= 1) ? lg[cls] - ls[0] : -INFINITY;
+      cur[s] = v, lat[s] = v;
+    }
+    __syncthreads();
+    for (int t = 1; t < p.T; ++t) {
+      if (active) {
+        float a = cur[s];
+        if (s >= 1) a = log_add(a, cur[s - 1]);
+        if (skip_prev) a = log_add(a, cur[s - 2]);
+        a += lg[(long long)t * p.V1 + cls] - ls[t];
+        nxt[s] = a, lat[(long long)t * Sm + s] = a;
+      }
+      __syncthreads();
+      float* tmp = cur;
+      cur = nxt, nxt = tmp;
+    }
+    if (s == 0) {
+      float ll = cur[S - 1];
+      if (S >= 2) ll = log_add(ll, cur[S - 2]);
+      p.nll[b] = -ll;
+    }
+  } else {
+    const int tl = p.T - 1;
+    if (active) {
+      const float v = (s >= S - 2) ? lg[(long long)tl * p.V1 + cls] - ls[tl] : -INFINITY;
+      cur[s] = v, lat[(long long)tl * Sm + s] = v;
+    }
+    __syncthreads();
+    for (int t = p.T - 2; t >= 0; --t) {
+      if (active) {
+        float a = cur[s];
+        if (s + 1 < S) a = log_add(a, cur[s + 1]);
+        if (skip_next) a = log_add(a, cur[s + 2]);
+        a += lg[(long long)t * p.V1 + cls] - ls[t];
+        nxt[s] = a, lat[(long long)t * Sm + s] = a;
+      }
+      __syncthreads();
+      float* tmp = cur;
+      cur = nxt, nxt = tmp;
+    }
+  }
+}
+
+// d logits[b, t, v] = scale_b * (softmax(logits)[v] - occupancy[b, t, v]); one CTA per (b, t) row.
+//   occupancy[v] = sum_{s: ext[s] = v} exp(alpha_t(s) + beta_t(s) - lp[t, v] + nll)
+// scale_b = loss_scale / (B * max(L_b, 1)) for "mean", loss_scale for "sum"; 0 when the loss is infinite (zero_infinity).
+__global__ void __launch_bounds__(512) ctc_grad_kernel(const CtcBwdParams p) {
+  extern __shared__ float occ[];  // [S]: occupancy of the class of state s, accumulated at its first occurrence
+  const int bt = blockIdx.x, b = bt / p.T, t = bt - b * p.T;
+  const int tid = threadIdx.x;
+  const long long* lab = p.labels + (long long)b * p.Lmax;
+  __shared__ int s_len;
+  __shared__ float s_blank;
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < p.Lmax; ++i) n += lab[i] >= 0 ? 1 : 0;
+    s_len = n;
+    s_blank = 0.f;
+  }
+  __syncthreads();
+  const int L = s_len, S = 2 * L + 1, Sm = 2 * p.Lmax + 1, blank = p.V1 - 1;
+  const float nll = p.nll[b];
+  const bool finite = nll < INFINITY;  // also false for NaN
+  const float scale = !finite ? 0.f : (p.mean ? p.loss_scale / ((float)p.B * (float)max(L, 1)) : p.loss_scale);
+  const float* lg = p.logits + (long long)bt * p.V1;
+  const float lse = p.lse[bt];
+  __nv_bfloat16* out = p.dlogits + (long long)bt * p.ldd;
+  // dense part: scale * softmax
+  for (int v = tid; v < p.ldd; v += blockDim.x) out[v] = __float2bfloat16_rn(v < p.V1 ? scale * __expf(lg[v] - lse) : 0.f);
+  if (!finite) return;  // uniform
+  for (int s = tid; s < S; s += blockDim.x) occ[s] = 0.f;
+  __syncthreads();
+  const float* al = p.alpha + (long long)bt * Sm;
+  const float* be = p.beta + (long long)bt * Sm;
+  float blank_acc = 0.f;
+  for (int s = tid; s < S; s += blockDim.x) {
+    const int cls = (s & 1) ? (int)lab[s >> 1] : blank;
+    const float lp = lg[cls] - lse;
+    const float w = __expf(al[s] + be[s] - lp + nll);  // alpha and beta both contain the emission at t
+    if (!(s & 1)) {
+      blank_acc += w;
+    } else {
+      int first = s;  // first state with the same class (repeated labels share one logit)
+      for (int u = 1; u < s; u += 2)
+        if (lab[u >> 1] == cls) {
+          first = u;
+          break;
+        }
+      atomicAdd(&occ[first], w);
+    }
+  }
+  blank_acc = warp_sum(blank_acc);
+  if ((tid & 31) == 0 && blank_acc != 0.f) atomicAdd(&s_blank, blank_acc);
+  __syncthreads();
+  // sparse part: subtract the occupancy at the label classes (each class exactly once) and at the blank
+  for (int s = 1 + 2 * tid; s < S; s += 2 * blockDim.x) {
+    const float o = occ[s];
+    if (o != 0.f) {
+      const int cls = (int)lab[s >> 1];
+      out[cls] = __float2bfloat16_rn(scale * (__expf(lg[cls] - lse) - o));
+    }
+  }
+  if (tid == 0) out[blank] = __float2bfloat16_rn(scale * (__expf(lg[blank] - lse) - s_blank));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decoder cross-entropy backward: d logits = scale * (softmax - target_of_the_winning_stream), rows with label -100 -> 0
+// ------------------------------------------------------------------------------------------------------------------
+struct CeBwdParams {
+  const float* logits;
+  long long ld;
+  int R, V;
+  const long long* labels;
+  const long long* upp;
+  int ts_begin, n_ts;
+  const float* smooth;
+  int soft_mode;
+  const float* row_lower;  // optional per-row losses of both streams from the forward (to pick the min); NULL: recompute
+  float scale;             // upstream gradient / normaliser
+  __nv_bfloat16* dlogits;
+  long long ldd;
+};
+
+__device__ __forceinline__ float ce_target_dot(const CeBwdParams& p, const float* row, long long lab, float* sm) {
+  if (lab < 0) lab = 0;
+  if (lab >= p.V) lab = p.V - 1;
+  if (p.n_ts > 0 && lab >= p.ts_begin && lab < p.ts_begin + p.n_ts) {
+    const float* w = p.smooth + (lab - p.ts_begin) * p.n_ts;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < p.n_ts; k += blockDim.x) acc = fmaf(__ldg(w + k), row[p.ts_begin + k], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float t = 0.f;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += sm[w2];
+    __syncthreads();
+    return t;
+  }
+  return row[lab];
+}
+
+__global__ void __launch_bounds__(512) ce_bwd_kernel(const CeBwdParams p) {
+  __shared__ float sa[16], sb[16];
+  const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const float* row = p.logits + (long long)r * p.ld;
+  __nv_bfloat16* out = p.dlogits + (long long)r * p.ldd;
+  const long long lab = p.labels[r];
+  const long long ulab = p.upp != nullptr ? p.upp[r] : lab;
+  // which stream wins the per-token min (ties -> the lower-case stream, like torch.min on equal values)
+  bool use_upper = false;
+  if (p.upp != nullptr && ulab != lab) {
+    // loss = lse - <target, logits>: smaller loss == larger target dot
+    const float dl = ce_target_dot(p, row, lab, sa), du = ce_target_dot(p, row, ulab, sa);
+    const bool lo_ign = !p.soft_mode && lab == -100, up_ign = !p.soft_mode && ulab == -100;
+    if (lo_ign || up_ign) {
+      // hard fallback: an ignored stream has loss 0, the other a positive loss -> the ignored one is the min (no gradient)
+      for (int v = tid; v < p.ldd; v += blockDim.x) out[v] = __float2bfloat16_rn(0.f);
+      return;
+    }
+    use_upper = du > dl;
+  }
+  const long long tl = use_upper ? ulab : lab;
+  const bool masked = p.soft_mode ? (lab == -100) : (tl == -100);
+  if (masked) {
+    for (int v = tid; v < p.ldd; v += blockDim.x) out[v] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  // logsumexp of the row
+  float m = -INFINITY, s = 0.f;
+  for (int v = tid; v < p.V; v += blockDim.x) {
+    const float x = row[v];
+    if (x > m) {
+      s = s * __expf(m - x) + 1.0f;
+      m = x;
+    } else if (x > -INFINITY) {
+      s += __expf(x - m);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    m = mn;
+  }
+  if (lane == 0) sa[warp] = m, sb[warp] = s;
+  __syncthreads();
+  float mt = -INFINITY;
+  for (int w = 0; w < nw; ++w) mt = fmaxf(mt, sa[w]);
+  float st = 0.f;
+  for (int w = 0; w < nw; ++w) st += sa[w] == -INFINITY ? 0.f : sb[w] * __expf(sa[w] - mt);
+  const float lse = mt + logf(st);
+  long long t = tl < 0 ? 0 : (tl >= p.V ? p.V - 1 : tl);
+  const bool is_ts = p.n_ts > 0 && t >= p.ts_begin && t < p.ts_begin + p.n_ts;
+  const float* w = is_ts ? p.smooth + (t - p.ts_begin) * p.n_ts : nullptr;
+  for (int v = tid; v < p.ldd; v += blockDim.x) {
+    float g = 0.f;
+    if (v < p.V) {
+      float tgt = 0.f;
+      if (is_ts) {
+        if (v >= p.ts_begin && v < p.ts_begin + p.n_ts) tgt = __ldg(w + (v - p.ts_begin));
+      } else if (v == t) {
+        tgt = 1.f;
+      }
+      g = p.scale * (__expf(row[v] - lse) - tgt);
+    }
+    out[v] = __float2bfloat16_rn(g);
+  }
+}
+
+}  // namespace
+}  // namespace dicow
+
+using namespace dicow;
+
+extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_ln_bwd_args_t), "dicow_layernorm_fddt_bwd: bad args struct");
+  DICOW_REQUIRE(ctx, a->x && a->g_out && a->rows >= 1 && a->d >= 4 && (a->d % 4) == 0 && a->d <= 2048,
+                "dicow_layernorm_fddt_bwd: need x, g_out, d %% 4 == 0, d <= 2048");
+  DICOW_REQUIRE(ctx, a->gamma == nullptr || a->dy_bf16 != nullptr, "dicow_layernorm_fddt_bwd: gamma without dy");
+  DICOW_REQUIRE(ctx, a->stno == nullptr || (a->fddt_b != nullptr && a->T >= 1 && (a->rows % a->T) == 0),
+                "dicow_layernorm_fddt_bwd: FDDT needs fddt_b and rows %% T == 0");
+  LnBwdParams p{};
+  p.x = a->x, p.delta1 = reinterpret_cast<const __nv_bfloat16*>(a->delta1_bf16);
+  p.delta2 = reinterpret_cast<const __nv_bfloat16*>(a->delta2_bf16);
+  p.rows = a->rows, p.d = a->d, p.T = a->T > 0 ? a->T : a->rows;
+  p.stno = a->stno, p.stno_bs = a->stno_batch_stride, p.fddt_w = a->fddt_w, p.fddt_b = a->fddt_b;
+  p.gamma = a->gamma, p.eps = a->eps, p.dy = reinterpret_cast<const __nv_bfloat16*>(a->dy_bf16), p.g_in = a->g_in;
+  p.g_out = a->g_out, p.g_out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->g_out_bf16);
+  p.dgamma = a->dgamma, p.dbeta = a->dbeta, p.dfddt_w = a->dfddt_w, p.dfddt_b = a->dfddt_b;
+  const int threads = ceil_div(a->d / 4, 32) * 32;
+  const int groups = ceil_div(a->rows, LB_ROWS);
+  const int grid = groups < 2 * ctx->num_sms ? groups : 2 * ctx->num_sms;
+  ln_fddt_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p, groups);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_colsum(dicow_handle_t h, const void* x, int is_bf16, int64_t ld, int rows, int N, float* out,
+                            float alpha, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, x && out && rows >= 1 && N >= 1, "dicow_colsum: bad args");
+  const int rpb = 128;
+  dim3 grid(ceil_div(N, 256), ceil_div(rows, rpb));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, N, out, alpha, rpb);
+  else
+    colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ld, rows, N, out, alpha, rpb);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_conv1d_col2im(dicow_handle_t h, const void* dcol_bf16, void* dx_bf16, int B, int T, int T_out, int C,
+                                   int stride, int64_t dx_batch_stride, int64_t dx_row_stride, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, dcol_bf16 && dx_bf16 && B >= 1 && T >= 1 && T_out >= 1 && C >= 1 && stride >= 1, "dicow_conv1d_col2im: bad args");
+  const long long total = (long long)B * T * C;
+  col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dcol_bf16), reinterpret_cast<__nv_bfloat16*>(dx_bf16), B, T, T_out, C, stride,
+      dx_batch_stride, dx_row_stride);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_ctc_bwd_args_t), "dicow_ctc_loss_bwd: bad args struct");
+  DICOW_REQUIRE(ctx, a->logits && a->lse && a->labels && a->workspace && a->dlogits_bf16 && a->B >= 1 && a->T >= 1 && a->V1 >= 2,
+                "dicow_ctc_loss_bwd: bad args");
+  DICOW_REQUIRE(ctx, a->Lmax >= 0 && 2 * a->Lmax + 1 <= 1024 && a->ldd >= a->V1, "dicow_ctc_loss_bwd: bad Lmax / ldd");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int S = 2 * a->Lmax + 1;
+  CtcBwdParams p{};
+  p.logits = a->logits, p.lse = a->lse, p.T = a->T, p.V1 = a->V1, p.Lmax = a->Lmax, p.B = a->B;
+  p.labels = reinterpret_cast<const long long*>(a->labels);
+  p.alpha = a->workspace;
+  p.beta = p.alpha + (long long)a->B * a->T * S;
+  p.nll = p.beta + (long long)a->B * a->T * S;
+  p.mean = a->reduction_mean, p.dlogits = reinterpret_cast<__nv_bfloat16*>(a->dlogits_bf16), p.ldd = a->ldd;
+  p.loss_scale = a->loss_scale;
+  const int threads = ((S + 31) / 32) * 32;
+  ctc_lattice_kernel<<<dim3(a->B, 2), threads, 2 * S * sizeof(float), stream>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  ctc_grad_kernel<<<a->B * a->T, 512, S * sizeof(float), stream>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_softlabel_ce_bwd(dicow_handle_t h, const dicow_softlabel_ce_bwd_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_softlabel_ce_bwd_args_t), "dicow_softlabel_ce_bwd: bad args struct");
+  DICOW_REQUIRE(ctx, a->logits && a->labels && a->dlogits_bf16 && a->rows >= 1 && a->V >= 1 && a->ldd >= a->V,
+                "dicow_softlabel_ce_bwd: bad args");
+  CeBwdParams p{};
+  p.logits = a->logits, p.ld = a->ld, p.R = a->rows, p.V = a->V;
+  p.labels = reinterpret_cast<const long long*>(a->labels), p.upp = reinterpret_cast<const long long*>(a->upp_labels);
+  p.ts_begin = a->ts_begin, p.n_ts = a->n_ts, p.smooth = a->smoothing, p.soft_mode = a->soft_mode;
+  p.scale = a->scale, p.dlogits = reinterpret_cast<__nv_bfloat16*>(a->dlogits_bf16), p.ldd = a->ldd;
+  ce_bwd_kernel<<<a->rows, 512, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}

@@ -41,6 +41,7 @@ struct GemmParams {
   const float* fddt_w;
   const float* fddt_b;
   const float* pos;
+  __nv_bfloat16* aux;  // [.., N] bf16, leading dimension ldo: pre-activation saved by GELU_SAVE / read by DGELU
 };
 
 template <int BN>
@@ -71,12 +72,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
         if (j < ncols) v[j] += __ldg(p.bias + n + j);
     }
   }
-  if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_FDDT_POS_F32) {
+  if constexpr (EPI == DICOW_EPI_GELU_SAVE_BF16) {  // training forward: keep the pre-activation for the backward pass
+    __nv_bfloat16* a = p.aux + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+    if (ncols == 32 && p.out_vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16(v[j], v[j + 1]), q.y = pack_bf16(v[j + 2], v[j + 3]);
+        q.z = pack_bf16(v[j + 4], v[j + 5]), q.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(a + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) a[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if constexpr (EPI == DICOW_EPI_DGELU_BF16) {  // backward: out = acc * gelu'(pre)
+    const __nv_bfloat16* a = p.aux + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] *= dgelu_erf_fast(__bfloat162float(a[j]));
+  }
+  if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_FDDT_POS_F32 || EPI == DICOW_EPI_GELU_SAVE_BF16) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
   }
 
-  if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16) {
+  if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_SAVE_BF16 ||
+                EPI == DICOW_EPI_DGELU_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bs + (long long)m * p.ldo + n;
     if (ncols == 32 && p.out_vec_ok) {
 #pragma unroll
@@ -570,6 +594,8 @@ int dispatch_epi(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensor
     case DICOW_EPI_BIAS_F32: return launch_gemm<BN, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, p, stream);
     case DICOW_EPI_GELU_FDDT_POS_F32:
       return launch_gemm<BN, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_ACCUM_F32: return launch_gemm<BN, DICOW_EPI_ACCUM_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_GELU_SAVE_BF16: return launch_gemm<BN, DICOW_EPI_GELU_SAVE_BF16>(ctx, tmA, tmA2, tmW, p, stream);
     default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: unknown epilogue %d", epi);
   }
 }
@@ -583,6 +609,7 @@ int dispatch_transposed(dicow_ctx* ctx, int epi, bool a_t, bool w_t, const CUten
       case DICOW_EPI_BIAS_BF16: return launch_gemm<BN, DICOW_EPI_BIAS_BF16, false, true>(ctx, tmA, tmA, tmW, p, stream);
       case DICOW_EPI_BIAS_F32: return launch_gemm<BN, DICOW_EPI_BIAS_F32, false, true>(ctx, tmA, tmA, tmW, p, stream);
       case DICOW_EPI_ACCUM_F32: return launch_gemm<BN, DICOW_EPI_ACCUM_F32, false, true>(ctx, tmA, tmA, tmW, p, stream);
+      case DICOW_EPI_DGELU_BF16: return launch_gemm<BN, DICOW_EPI_DGELU_BF16, false, true>(ctx, tmA, tmA, tmW, p, stream);
       default: break;
     }
   } else if (a_t && w_t) {
@@ -642,7 +669,7 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   // `flags & 2` forces pairs (tests / comparison)
   const long long tiles128 = (long long)a->nb * ceil_div(a->Mb, BM) * ceil_div(a->N, BN);
   bool two_cta = BN == 256 && tiles128 >= 2 * (long long)ctx->num_sms;
-  if ((a->flags & 1) || a_t || w_t || a->epilogue == DICOW_EPI_ACCUM_F32) two_cta = false;
+  if ((a->flags & 1) || a_t || w_t || a->epilogue >= DICOW_EPI_ACCUM_F32) two_cta = false;
   if ((a->flags & 2) && BN == 256) two_cta = true;
   GemmParams p{};
   p.nb = a->nb, p.Mb = a->Mb, p.N = a->N, p.K = a->K, p.K1 = split ? a->K1 : 0;
@@ -663,7 +690,12 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   p.out = a->out, p.ldo = a->ldo, p.out_bs = a->out_batch_stride;
   p.resid = a->resid, p.ldr = a->ldr, p.resid_bs = a->resid_batch_stride, p.gate = a->gate;
   p.stno = a->stno, p.stno_bs = a->stno_batch_stride, p.fddt_w = a->fddt_w, p.fddt_b = a->fddt_b, p.pos = a->pos;
-  const bool out_is_bf16 = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16;
+  p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux_bf16);
+  const bool out_is_bf16 = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16 ||
+                           a->epilogue == DICOW_EPI_GELU_SAVE_BF16 || a->epilogue == DICOW_EPI_DGELU_BF16;
+  if (a->epilogue == DICOW_EPI_GELU_SAVE_BF16 || a->epilogue == DICOW_EPI_DGELU_BF16)
+    DICOW_REQUIRE(ctx, a->aux_bf16 != nullptr && (reinterpret_cast<uintptr_t>(a->aux_bf16) % 16) == 0,
+                  "dicow_gemm_bf16: this epilogue needs aux_bf16 (same leading dimension as out)");
   const int vec = out_is_bf16 ? 8 : 4;
   bool vec_ok = (a->ldo % vec) == 0 && (a->out_batch_stride % vec) == 0 &&
                 (reinterpret_cast<uintptr_t>(a->out) % 16) == 0;

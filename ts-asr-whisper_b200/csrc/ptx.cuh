@@ -150,6 +150,21 @@ __device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
   return e;
 }
 
+// d/dx of the erf GELU: Phi(x) + x phi(x), with the same erfc approximation (|error| < 1e-6)
+__device__ __forceinline__ float dgelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = fast_rcp(fmaf(ax, 0.23164189f, 1.0f));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q *= t;
+  const float e = fast_exp2(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
+  const float half_erfc = 0.5f * q * e;                         // 0.5 erfc(|x| / sqrt2)
+  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -19,6 +19,8 @@ EPI_RESIDUAL_F32 = 2
 EPI_BIAS_F32 = 3
 EPI_GELU_FDDT_POS_F32 = 4
 EPI_ACCUM_F32 = 5
+EPI_GELU_SAVE_BF16 = 6
+EPI_DGELU_BF16 = 7
 GEMM_A_T = 4  # dicow_gemm_args_t.flags: A given transposed (At[k][m])
 GEMM_W_T = 8  # W given transposed (Wt[k][n])
 
@@ -41,7 +43,7 @@ class GemmArgs(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_int64), ("resid_batch_stride", C.c_int64),
         ("gate", C.c_void_p),
         ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64),
-        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p), ("flags", C.c_int32), ("splits", C.c_int32),
+        ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p), ("pos", C.c_void_p), ("flags", C.c_int32), ("splits", C.c_int32), ("aux_bf16", C.c_void_p),
     ]
 
 
@@ -83,6 +85,37 @@ class AttentionBwdArgs(C.Structure):
         ("dq_row_stride", C.c_int64), ("dq_batch_stride", C.c_int64),
         ("dkv_row_stride", C.c_int64), ("dkv_batch_stride", C.c_int64),
         ("causal", C.c_int32), ("workspace", C.c_void_p),
+    ]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("x", C.c_void_p), ("delta1_bf16", C.c_void_p), ("delta2_bf16", C.c_void_p),
+        ("rows", C.c_int32), ("d", C.c_int32), ("T", C.c_int32),
+        ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64), ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p),
+        ("gamma", C.c_void_p), ("eps", C.c_float), ("dy_bf16", C.c_void_p), ("g_in", C.c_void_p),
+        ("g_out", C.c_void_p), ("g_out_bf16", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("dfddt_w", C.c_void_p), ("dfddt_b", C.c_void_p),
+    ]
+
+
+class CtcBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("logits", C.c_void_p), ("lse", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32),
+        ("labels", C.c_void_p), ("Lmax", C.c_int32), ("reduction_mean", C.c_int32), ("loss_scale", C.c_float),
+        ("workspace", C.c_void_p), ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64),
+    ]
+
+
+class SoftlabelCeBwdArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int32), ("V", C.c_int32),
+        ("labels", C.c_void_p), ("upp_labels", C.c_void_p), ("ts_begin", C.c_int32), ("n_ts", C.c_int32),
+        ("smoothing", C.c_void_p), ("soft_mode", C.c_int32), ("scale", C.c_float),
+        ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64),
     ]
 
 
@@ -188,6 +221,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
     lib.dicow_logmel.argtypes = [vp, C.POINTER(LogmelArgs), vp]
     lib.dicow_attention_bwd_bf16.argtypes = [vp, C.POINTER(AttentionBwdArgs), vp]
+    lib.dicow_layernorm_fddt_bwd.argtypes = [vp, C.POINTER(LnBwdArgs), vp]
+    lib.dicow_colsum.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, C.c_float, vp]
+    lib.dicow_conv1d_col2im.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, vp]
+    lib.dicow_ctc_loss_bwd.argtypes = [vp, C.POINTER(CtcBwdArgs), vp]
+    lib.dicow_softlabel_ce_bwd.argtypes = [vp, C.POINTER(SoftlabelCeBwdArgs), vp]
     lib.dicow_gemm_skinny_bf16.argtypes = [vp, C.POINTER(GemmSkinnyArgs), vp]
     lib.dicow_decode_attention_bf16.argtypes = [vp, C.POINTER(DecodeAttentionArgs), vp]
     lib.dicow_embed_tokens.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -208,6 +246,7 @@ EXPORTED_SYMBOLS = [
     "dicow_zero_pad_rows", "dicow_cast_f32_bf16", "dicow_debug_set_attention_profile", "dicow_logmel",
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
+    "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
 ]
 
 

@@ -10,8 +10,8 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_GELU_FDDT_POS_F32,
-                  EPI_RESIDUAL_F32, GEMM_A_T, GEMM_W_T, DicowError)
+from .lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_DGELU_BF16, EPI_GELU_FDDT_POS_F32,
+                  EPI_GELU_SAVE_BF16, EPI_RESIDUAL_F32, GEMM_A_T, GEMM_W_T, DicowError)
 
 # number of kernels this module has launched (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -70,8 +70,8 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
          resid: Optional[torch.Tensor] = None, ldr: int = 0, resid_batch_stride: int = 0,
          gate: Optional[torch.Tensor] = None, stno: Optional[torch.Tensor] = None, stno_batch_stride: int = 0,
          fddt_w: Optional[torch.Tensor] = None, fddt_b: Optional[torch.Tensor] = None,
-         pos: Optional[torch.Tensor] = None, flags: int = 0, splits: int = 0, N: Optional[int] = None
-         ) -> torch.Tensor:
+         pos: Optional[torch.Tensor] = None, flags: int = 0, splits: int = 0, N: Optional[int] = None,
+         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b, m, :] = epilogue(sum_k A[b, m, k] W[:, k]) -- see dicow_gemm_bf16 in include/dicow_b200.h.
 
     A: bf16, rows addressed as A + b*a_batch_stride + m*lda.  W: bf16 [N, K].  Defaults describe a plain
@@ -119,6 +119,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     a.pos = _ptr(pos)
     a.flags = flags
     a.splits = splits
+    a.aux_bf16 = _ptr(aux)
     h = _lib.handle(dev.index or 0)
     with torch.cuda.device(dev), _Timed("gemm", 2.0 * nb * Mb * N * K, dev):
         rc = _lib.load_library().dicow_gemm_bf16(h, C.byref(a), _stream(dev))
@@ -443,3 +444,106 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, *, B: int, H: int, Tq: int, T
     a.workspace = _ptr(ws)
     fl = 10.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)  # 5 GEMMs; S and dP are recomputed in the 2nd pass
     _call("dicow_attention_bwd_bf16", dev, a, "attention_bwd", fl)
+
+
+def layernorm_fddt_bwd(x: torch.Tensor, g_out: torch.Tensor, *, dy: Optional[torch.Tensor] = None,
+                       g_in: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                       delta1: Optional[torch.Tensor] = None, delta2: Optional[torch.Tensor] = None, T: int = 0,
+                       stno: Optional[torch.Tensor] = None, fddt_w: Optional[torch.Tensor] = None,
+                       fddt_b: Optional[torch.Tensor] = None, g_out_bf16: Optional[torch.Tensor] = None,
+                       dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
+                       dfddt_w: Optional[torch.Tensor] = None, dfddt_b: Optional[torch.Tensor] = None) -> None:
+    """backward of fddt_layernorm (dicow_layernorm_fddt_bwd); parameter gradients are accumulated (+=)."""
+    dev = _require_cuda(x, g_out, dy, g_in, gamma, delta1, delta2, stno, fddt_w, fddt_b, g_out_bf16, dgamma, dbeta,
+                        dfddt_w, dfddt_b)
+    a = _lib.LnBwdArgs()
+    a.struct_size = C.sizeof(_lib.LnBwdArgs)
+    a.x, a.delta1_bf16, a.delta2_bf16 = _ptr(x), _ptr(delta1), _ptr(delta2)
+    a.d = x.shape[-1]
+    a.rows = x.numel() // x.shape[-1]
+    a.T = T if T else a.rows
+    a.stno = _ptr(stno)
+    a.stno_batch_stride = stno.stride(0) if stno is not None else 0
+    a.fddt_w, a.fddt_b = _ptr(fddt_w), _ptr(fddt_b)
+    a.gamma, a.eps = _ptr(gamma), eps
+    a.dy_bf16, a.g_in, a.g_out, a.g_out_bf16 = _ptr(dy), _ptr(g_in), _ptr(g_out), _ptr(g_out_bf16)
+    a.dgamma, a.dbeta, a.dfddt_w, a.dfddt_b = _ptr(dgamma), _ptr(dbeta), _ptr(dfddt_w), _ptr(dfddt_b)
+    _call("dicow_layernorm_fddt_bwd", dev, a, "ln_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, alpha: float = 1.0) -> None:
+    """out[n] += alpha * sum_rows x[row, n] (dicow_colsum); x bf16 / fp32 [rows, N] with unit column stride."""
+    global launch_count
+    dev = _require_cuda(x, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32 and x.dtype in (torch.bfloat16, torch.float32)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_colsum(h, _ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), x.shape[0],
+                                              out.numel(), _ptr(out), alpha, _stream(dev))
+    _lib.check(rc, h, "dicow_colsum")
+    launch_count += 1
+
+
+def conv1d_col2im(dcol: torch.Tensor, dx: torch.Tensor, *, B: int, T: int, T_out: int, C_in: int, stride: int,
+                  dx_batch_stride: int, dx_row_stride: int) -> None:
+    global launch_count
+    dev = _require_cuda(dcol, dx)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_conv1d_col2im(h, _ptr(dcol), _ptr(dx), B, T, T_out, C_in, stride, dx_batch_stride,
+                                                     dx_row_stride, _stream(dev))
+    _lib.check(rc, h, "dicow_conv1d_col2im")
+    launch_count += 1
+
+
+def ctc_loss_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean", loss_scale: float = 1.0):
+    """CTC loss value and loss_scale * dL/dlogits (bf16, rows padded to a multiple of 8 columns for the wgrad GEMM)."""
+    dev = _require_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    labels = labels.contiguous()
+    B, T, V1 = logits.shape
+    Lmax = labels.shape[1]
+    ws_f = torch.empty(B * T + 2 * B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    a = _lib.CtcLossArgs()
+    a.struct_size = C.sizeof(_lib.CtcLossArgs)
+    a.logits, a.B, a.T, a.V1 = _ptr(logits), B, T, V1
+    a.labels, a.Lmax = _ptr(labels), Lmax
+    a.reduction_mean = 1 if reduction == "mean" else 0
+    a.workspace, a.loss = _ptr(ws_f), _ptr(loss)
+    _call("dicow_ctc_loss", dev, a, "ctc_loss")
+    S = 2 * Lmax + 1
+    ldd = -(-V1 // 8) * 8
+    ws_b = torch.empty(2 * B * T * S + B, dtype=torch.float32, device=dev)
+    dlogits = torch.empty(B, T, ldd, dtype=torch.bfloat16, device=dev)
+    b = _lib.CtcBwdArgs()
+    b.struct_size = C.sizeof(_lib.CtcBwdArgs)
+    b.logits, b.lse, b.B, b.T, b.V1 = _ptr(logits), _ptr(ws_f), B, T, V1
+    b.labels, b.Lmax, b.reduction_mean, b.loss_scale = _ptr(labels), Lmax, a.reduction_mean, loss_scale
+    b.workspace, b.dlogits_bf16, b.ldd = _ptr(ws_b), _ptr(dlogits), ldd
+    _call("dicow_ctc_loss_bwd", dev, b, "ctc_bwd")
+    return loss, dlogits
+
+
+def softlabel_ce_bwd(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optional[torch.Tensor] = None, *,
+                     ts_begin: int = 0, smoothing: Optional[torch.Tensor] = None, soft_mode: bool = True,
+                     scale: float = 1.0) -> torch.Tensor:
+    """scale * d(sum of per-token losses)/dlogits as bf16 [rows, ceil8(V)] (dicow_softlabel_ce_bwd)."""
+    dev = _require_cuda(logits, labels, upp_labels, smoothing)
+    labels = labels.reshape(-1).contiguous()
+    upp = upp_labels.reshape(-1).contiguous() if upp_labels is not None else None
+    rows, V = logits.shape
+    ldd = -(-V // 8) * 8
+    out = torch.empty(rows, ldd, dtype=torch.bfloat16, device=dev)
+    a = _lib.SoftlabelCeBwdArgs()
+    a.struct_size = C.sizeof(_lib.SoftlabelCeBwdArgs)
+    a.logits, a.ld, a.rows, a.V = _ptr(logits), logits.stride(0), rows, V
+    a.labels, a.upp_labels = _ptr(labels), _ptr(upp)
+    a.ts_begin = ts_begin
+    a.n_ts = smoothing.shape[0] if smoothing is not None else 0
+    a.smoothing = _ptr(smoothing)
+    a.soft_mode = 1 if soft_mode else 0
+    a.scale = scale
+    a.dlogits_bf16, a.ldd = _ptr(out), ldd
+    _call("dicow_softlabel_ce_bwd", dev, a, "ce_bwd")
+    return out
