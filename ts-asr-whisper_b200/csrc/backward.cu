@@ -234,6 +234,51 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// out_bf16[i] = g[i] * gelu'(pre[i])     (conv stem backward: the GELU sits between an fp32 gradient and the conv dgrad)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dgelu_mul_kernel(const T* __restrict__ g, long long ldg,
+                                                        const __nv_bfloat16* __restrict__ pre, long long ldp,
+                                                        __nv_bfloat16* __restrict__ out, long long ldo, int rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int c = (int)(i % cols);
+  const long long r = i / cols;
+  const float gv = (float)g[r * ldg + c];
+  out[r * ldo + c] = __float2bfloat16_rn(gv * dgelu_erf_fast(__bfloat162float(pre[r * ldp + c])));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decoder embedding backward: d_tok[ids[r], :] += g[r, :], d_pos[past + r % S, :] += g[r, :]   (fp32 atomics)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const float* __restrict__ g, const long long* __restrict__ ids,
+                                                            int rows, int S, int d, int past, int vocab,
+                                                            float* __restrict__ d_tok, float* __restrict__ d_pos) {
+  const int r = blockIdx.x;
+  const long long id = ids[r];
+  const int s = past + r % S;
+  const bool tok_ok = d_tok != nullptr && id >= 0 && id < vocab;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = g[(long long)r * d + c];
+    if (tok_ok) atomicAdd(d_tok + id * d + c, v);
+    if (d_pos != nullptr) atomicAdd(d_pos + (long long)s * d + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out_bf16[r, c] = c < cols ? in_f32[r, c] : 0, c < cols_out  (fp32 gradient -> padded bf16 GEMM operand)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_2d_kernel(const float* __restrict__ in, long long ldi,
+                                                      __nv_bfloat16* __restrict__ out, long long ldo, int rows, int cols,
+                                                      int cols_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols_out) return;
+  const int c = (int)(i % cols_out);
+  const long long r = i / cols_out;
+  out[r * ldo + c] = __float2bfloat16_rn(c < cols ? in[r * ldi + c] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // CTC backward
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float log_add(float a, float b) {
@@ -252,10 +297,19 @@ struct CtcBwdParams {
   float* beta;   // [B, T, S]
   float* nll;    // [B]
   int mean, B;
-  __nv_bfloat16* dlogits;  // [B, T, ldd]
+  __nv_bfloat16* dlogits;  // [B, T, ldd]  (fp32 when out_f32)
   long long ldd;
-  float loss_scale;  // upstream gradient * (ctc weight)
+  float loss_scale;         // upstream gradient * (ctc weight)
+  const float* scale_dev;   // optional device-resident multiplier of loss_scale (the upstream gradient)
+  int out_f32;
 };
+
+__device__ __forceinline__ void store_grad(void* base, bool f32, long long i, float v) {
+  if (f32)
+    reinterpret_cast<float*>(base)[i] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+}
 
 // alpha and beta lattices: one CTA per (utterance, direction); thread == extended-label state
 __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p) {
@@ -348,12 +402,15 @@ __global__ void __launch_bounds__(512) ctc_grad_kernel(const CtcBwdParams p) {
   const int L = s_len, S = 2 * L + 1, Sm = 2 * p.Lmax + 1, blank = p.V1 - 1;
   const float nll = p.nll[b];
   const bool finite = nll < INFINITY;  // also false for NaN
-  const float scale = !finite ? 0.f : (p.mean ? p.loss_scale / ((float)p.B * (float)max(L, 1)) : p.loss_scale);
+  const float ls = p.loss_scale * (p.scale_dev != nullptr ? __ldg(p.scale_dev) : 1.f);
+  const float scale = !finite ? 0.f : (p.mean ? ls / ((float)p.B * (float)max(L, 1)) : ls);
   const float* lg = p.logits + (long long)bt * p.V1;
   const float lse = p.lse[bt];
-  __nv_bfloat16* out = p.dlogits + (long long)bt * p.ldd;
+  const bool f32 = p.out_f32 != 0;
+  void* out = f32 ? static_cast<void*>(reinterpret_cast<float*>(p.dlogits) + (long long)bt * p.ldd)
+                  : static_cast<void*>(p.dlogits + (long long)bt * p.ldd);
   // dense part: scale * softmax
-  for (int v = tid; v < p.ldd; v += blockDim.x) out[v] = __float2bfloat16_rn(v < p.V1 ? scale * __expf(lg[v] - lse) : 0.f);
+  for (int v = tid; v < p.ldd; v += blockDim.x) store_grad(out, f32, v, v < p.V1 ? scale * __expf(lg[v] - lse) : 0.f);
   if (!finite) return;  // uniform
   for (int s = tid; s < S; s += blockDim.x) occ[s] = 0.f;
   __syncthreads();
@@ -384,10 +441,10 @@ __global__ void __launch_bounds__(512) ctc_grad_kernel(const CtcBwdParams p) {
     const float o = occ[s];
     if (o != 0.f) {
       const int cls = (int)lab[s >> 1];
-      out[cls] = __float2bfloat16_rn(scale * (__expf(lg[cls] - lse) - o));
+      store_grad(out, f32, cls, scale * (__expf(lg[cls] - lse) - o));
     }
   }
-  if (tid == 0) out[blank] = __float2bfloat16_rn(scale * (__expf(lg[blank] - lse) - s_blank));
+  if (tid == 0) store_grad(out, f32, blank, scale * (__expf(lg[blank] - lse) - s_blank));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -404,6 +461,7 @@ struct CeBwdParams {
   int soft_mode;
   const float* row_lower;  // optional per-row losses of both streams from the forward (to pick the min); NULL: recompute
   float scale;             // upstream gradient / normaliser
+  const float* scale_dev;  // optional device-resident multiplier of scale
   __nv_bfloat16* dlogits;
   long long ldd;
 };
@@ -480,6 +538,7 @@ __global__ void __launch_bounds__(512) ce_bwd_kernel(const CeBwdParams p) {
   long long t = tl < 0 ? 0 : (tl >= p.V ? p.V - 1 : tl);
   const bool is_ts = p.n_ts > 0 && t >= p.ts_begin && t < p.ts_begin + p.n_ts;
   const float* w = is_ts ? p.smooth + (t - p.ts_begin) * p.n_ts : nullptr;
+  const float scale = p.scale * (p.scale_dev != nullptr ? __ldg(p.scale_dev) : 1.f);
   for (int v = tid; v < p.ldd; v += blockDim.x) {
     float g = 0.f;
     if (v < p.V) {
@@ -489,7 +548,7 @@ __global__ void __launch_bounds__(512) ce_bwd_kernel(const CeBwdParams p) {
       } else if (v == t) {
         tgt = 1.f;
       }
-      g = p.scale * (__expf(row[v] - lse) - tgt);
+      g = scale * (__expf(row[v] - lse) - tgt);
     }
     out[v] = __float2bfloat16_rn(g);
   }
@@ -570,7 +629,7 @@ extern "C" int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* 
   p.beta = p.alpha + (long long)a->B * a->T * S;
   p.nll = p.beta + (long long)a->B * a->T * S;
   p.mean = a->reduction_mean, p.dlogits = reinterpret_cast<__nv_bfloat16*>(a->dlogits_bf16), p.ldd = a->ldd;
-  p.loss_scale = a->loss_scale;
+  p.loss_scale = a->loss_scale, p.scale_dev = a->scale_dev, p.out_f32 = a->out_f32;
   const int threads = ((S + 31) / 32) * 32;
   ctc_lattice_kernel<<<dim3(a->B, 2), threads, 2 * S * sizeof(float), stream>>>(p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
@@ -589,8 +648,53 @@ extern "C" int dicow_softlabel_ce_bwd(dicow_handle_t h, const dicow_softlabel_ce
   p.logits = a->logits, p.ld = a->ld, p.R = a->rows, p.V = a->V;
   p.labels = reinterpret_cast<const long long*>(a->labels), p.upp = reinterpret_cast<const long long*>(a->upp_labels);
   p.ts_begin = a->ts_begin, p.n_ts = a->n_ts, p.smooth = a->smoothing, p.soft_mode = a->soft_mode;
-  p.scale = a->scale, p.dlogits = reinterpret_cast<__nv_bfloat16*>(a->dlogits_bf16), p.ldd = a->ldd;
+  p.scale = a->scale, p.scale_dev = a->scale_dev;
+  p.dlogits = reinterpret_cast<__nv_bfloat16*>(a->dlogits_bf16), p.ldd = a->ldd;
   ce_bwd_kernel<<<a->rows, 512, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_dgelu_mul(dicow_handle_t h, const void* g, int g_is_bf16, int64_t ldg, const void* pre_bf16, int64_t ldp,
+                               void* out_bf16, int64_t ldo, int rows, int cols, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, g && pre_bf16 && out_bf16 && rows >= 1 && cols >= 1, "dicow_dgelu_mul: bad args");
+  const long long total = (long long)rows * cols;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (g_is_bf16)
+    dgelu_mul_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ldg,
+                                                              reinterpret_cast<const __nv_bfloat16*>(pre_bf16), ldp,
+                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, rows, cols);
+  else
+    dgelu_mul_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g), ldg,
+                                                      reinterpret_cast<const __nv_bfloat16*>(pre_bf16), ldp,
+                                                      reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, rows, cols);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_embedding_bwd(dicow_handle_t h, const float* g, const int64_t* ids, int rows, int S, int d, int past,
+                                   int vocab, float* d_embed_tokens, float* d_embed_positions, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, g && ids && rows >= 1 && S >= 1 && d >= 1 && past >= 0, "dicow_embedding_bwd: bad args");
+  embedding_bwd_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      g, reinterpret_cast<const long long*>(ids), rows, S, d, past, vocab, d_embed_tokens, d_embed_positions);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_cast_f32_bf16_2d(dicow_handle_t h, const float* in, int64_t ldi, void* out_bf16, int64_t ldo, int rows,
+                                      int cols, int cols_out, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, in && out_bf16 && rows >= 1 && cols >= 1 && cols_out >= cols && ldo >= cols_out && ldi >= cols,
+                "dicow_cast_f32_bf16_2d: bad args");
+  const long long total = (long long)rows * cols_out;
+  cast_2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      in, ldi, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, rows, cols, cols_out);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

@@ -106,6 +106,7 @@ class CtcBwdArgs(C.Structure):
         ("logits", C.c_void_p), ("lse", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32),
         ("labels", C.c_void_p), ("Lmax", C.c_int32), ("reduction_mean", C.c_int32), ("loss_scale", C.c_float),
         ("workspace", C.c_void_p), ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64),
+        ("scale_dev", C.c_void_p), ("out_f32", C.c_int32),
     ]
 
 
@@ -115,7 +116,7 @@ class SoftlabelCeBwdArgs(C.Structure):
         ("logits", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int32), ("V", C.c_int32),
         ("labels", C.c_void_p), ("upp_labels", C.c_void_p), ("ts_begin", C.c_int32), ("n_ts", C.c_int32),
         ("smoothing", C.c_void_p), ("soft_mode", C.c_int32), ("scale", C.c_float),
-        ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64),
+        ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64), ("scale_dev", C.c_void_p),
     ]
 
 
@@ -225,6 +226,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_colsum.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, C.c_float, vp]
     lib.dicow_conv1d_col2im.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, vp]
     lib.dicow_ctc_loss_bwd.argtypes = [vp, C.POINTER(CtcBwdArgs), vp]
+    lib.dicow_dgelu_mul.argtypes = [vp, vp, C.c_int, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, vp]
+    lib.dicow_cast_f32_bf16_2d.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
+    lib.dicow_embedding_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.dicow_softlabel_ce_bwd.argtypes = [vp, C.POINTER(SoftlabelCeBwdArgs), vp]
     lib.dicow_gemm_skinny_bf16.argtypes = [vp, C.POINTER(GemmSkinnyArgs), vp]
     lib.dicow_decode_attention_bf16.argtypes = [vp, C.POINTER(DecodeAttentionArgs), vp]
@@ -247,6 +251,7 @@ EXPORTED_SYMBOLS = [
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
+    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d",
 ]
 
 

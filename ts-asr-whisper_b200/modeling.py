@@ -226,14 +226,22 @@ class DiCoWEncoder(nn.Module):
 
     def get_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """CTC loss as encoder.py:108-135 (fp32 log-softmax, blank = last class, every frame valid, zero_infinity) in
-        the fused kernel (ops.ctc_loss); the label filtering is index bookkeeping on the int64 labels."""
+        the fused kernel (ops.ctc_loss); the label filtering is index bookkeeping on the int64 labels.  Logits that
+        carry a grad_fn (training forward with return_logits=True) get the CTC backward kernels through autograd."""
         if labels.max() >= self.config.vocab_size:
             raise ValueError(f"Label values must be <= vocab_size: {self.config.vocab_size}")
+        labels = self.ctc_label_filter(labels).to(logits.device).contiguous()
+        if torch.is_grad_enabled() and logits.requires_grad:
+            from .training import CtcLossFn
+            return CtcLossFn.apply(logits, labels, self.config.ctc_loss_reduction)
+        return ops.ctc_loss(logits.float().contiguous(), labels, reduction=self.config.ctc_loss_reduction)
+
+    def ctc_label_filter(self, labels: torch.Tensor) -> torch.Tensor:
+        """encoder.py:111-113: drop timestamp / task tokens from the CTC targets when configured"""
         if self.config.remove_timestamps_from_ctc:
             labels = torch.nn.utils.rnn.pad_sequence([lab[lab < self.first_task_token] for lab in labels],
                                                      padding_value=-100).T
-        return ops.ctc_loss(logits.float().contiguous(), labels.to(logits.device).contiguous(),
-                            reduction=self.config.ctc_loss_reduction)
+        return labels
 
     # ---- weight preparation ----------------------------------------------------------------------------------
     def _cache_key(self):
@@ -376,9 +384,27 @@ class DiCoWEncoder(nn.Module):
         ops.gemm(neck.view(B * Tp, -1), w["lm_head"], logits.view(B * Tp, V1), epilogue=ops.EPI_BIAS_F32)
         return logits
 
-    @torch.no_grad()
     def forward(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False, enrollments=None):
+        """encoder.py:140-246.  With autograd recording, trainable parameters and ``return_logits`` (the CTC pre-training
+        call, src/utils/trainers.py:76-103) the logits carry a grad_fn (training.EncoderLogitsFn); every other call is
+        the inference path.  Fine-tuning goes through DiCoWForConditionalGeneration.forward, which owns the encoder's
+        backward."""
+        if return_logits and input_features.is_cuda:
+            from . import training
+            if training.trainable(self):
+                if enrollments is not None or output_attentions or output_hidden_states or head_mask is not None:
+                    raise NotImplementedError("training forward: enrollments / attention outputs are not built yet")
+                params = [p for p in self.parameters() if p.requires_grad]
+                logits, hidden = training.EncoderLogitsFn.apply(self, input_features, stno_mask, *params)
+                return CausalLMOutput(loss=None, logits=logits, hidden_states=hidden)
+        with torch.no_grad():
+            return self._forward_inference(input_features, attention_mask, head_mask, output_attentions,
+                                           output_hidden_states, return_dict, stno_mask, return_logits, enrollments)
+
+    def _forward_inference(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
+                           output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False,
+                           enrollments=None):
         cfg = self.config
         if output_attentions or output_hidden_states or head_mask is not None:
             raise NotImplementedError("output_attentions / output_hidden_states / head_mask are not produced by the "

@@ -325,19 +325,58 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         B, T, _ = hidden_states.shape
         return enc.ctc_logits_from_hidden(ops.cast_bf16(hidden_states.float()), B, T)
 
-    @torch.no_grad()
+    def _ctc_labels(self, labels: torch.Tensor) -> torch.Tensor:
+        """CTC targets of the joint loss (modeling_dicow.py:326-333): the decoder labels minus the common prompt tokens,
+        eos -> -100; int64 index bookkeeping."""
+        cfg = self.config
+        enc_labels = labels.clone()
+        prefix = getattr(self.tokenizer, "prefix_tokens", None) if self.tokenizer is not None else None
+        if prefix is None:
+            prefix = getattr(self, "ctc_prefix_tokens", ())
+        for tok in prefix:  # modeling_dicow.py:330-332
+            if enc_labels.shape[1] and bool((enc_labels[:, 0] == tok).all()):
+                enc_labels = enc_labels[:, 1:]
+        enc_labels[enc_labels == cfg.eos_token_id] = -100
+        return enc_labels
+
     def forward(self, input_features=None, attention_mask=None, stno_mask=None, decoder_input_ids=None,
                 decoder_attention_mask=None, head_mask=None, decoder_head_mask=None, cross_attn_head_mask=None,
                 encoder_outputs=None, past_key_values=None, decoder_inputs_embeds=None, decoder_position_ids=None,
                 labels=None, upp_labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
                 return_dict=None, cache_position=None, forced_decoder_ids=None, enrollments=None):
-        """src/models/dicow/modeling_dicow.py:248-354.  Forward values only (the training backward is not built yet:
-        DESIGN.md section 8)."""
+        """src/models/dicow/modeling_dicow.py:248-354.  With labels, autograd recording and trainable parameters the loss
+        carries a grad_fn whose backward is the hand-scheduled kernel sequence of training.DiCoWTrainStepFn (what HF
+        Trainer.training_step -> loss.backward() runs); otherwise forward values only."""
         cfg = self.config
         if labels is not None and decoder_input_ids is None and decoder_inputs_embeds is None:
             decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         if past_key_values is not None or decoder_inputs_embeds is not None:
             raise NotImplementedError("forward() is the teacher-forced path; token-by-token decoding is generate()")
+        if labels is not None and encoder_outputs is None and input_features is not None and input_features.is_cuda:
+            from . import training
+            if training.trainable(self):
+                if enrollments is not None:
+                    raise NotImplementedError("training with SE-DiCoW enrollment streams is not built yet (DESIGN.md)")
+                enc_model = self.model.get_encoder()
+                enc_labels = None
+                if cfg.ctc_weight > 0.0:
+                    enc_labels = self._ctc_labels(labels)
+                    if enc_labels.max() >= cfg.vocab_size:  # encoder.py:109-110
+                        raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
+                    enc_labels = enc_model.ctc_label_filter(enc_labels)
+                params = [p for p in self.parameters() if p.requires_grad]
+                loss, logits, enc = training.DiCoWTrainStepFn.apply(self, input_features, stno_mask, decoder_input_ids, labels,
+                                                                    upp_labels, enc_labels, *params)
+                if return_dict is False:
+                    return (loss, logits, enc)
+                return Seq2SeqLMOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc)
+        with torch.no_grad():
+            return self._forward_inference(input_features, stno_mask, decoder_input_ids, encoder_outputs, labels, upp_labels,
+                                           return_dict, enrollments)
+
+    def _forward_inference(self, input_features, stno_mask, decoder_input_ids, encoder_outputs, labels, upp_labels,
+                           return_dict, enrollments):
+        cfg = self.config
         enc_model = self.model.get_encoder()
         if encoder_outputs is None:
             encoder_outputs = enc_model(input_features, stno_mask=stno_mask, enrollments=enrollments)
@@ -360,15 +399,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                                             soft_mode=False)
             if cfg.ctc_weight > 0.0:
                 enc_logits = enc_model.ctc_logits_from_hidden(enc_bf16, B, T)
-                enc_labels = labels.clone()
-                prefix = getattr(self.tokenizer, "prefix_tokens", None) if self.tokenizer is not None else None
-                if prefix is None:
-                    prefix = getattr(self, "ctc_prefix_tokens", ())
-                for tok in prefix:  # modeling_dicow.py:330-332
-                    if enc_labels.shape[1] and bool((enc_labels[:, 0] == tok).all()):
-                        enc_labels = enc_labels[:, 1:]
-                enc_labels[enc_labels == cfg.eos_token_id] = -100
-                ctc = enc_model.get_loss(enc_logits, enc_labels)
+                ctc = enc_model.get_loss(enc_logits, self._ctc_labels(labels))
                 loss = (1 - cfg.ctc_weight) * dec_loss + cfg.ctc_weight * ctc
             else:
                 loss = dec_loss

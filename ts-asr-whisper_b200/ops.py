@@ -71,7 +71,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
          gate: Optional[torch.Tensor] = None, stno: Optional[torch.Tensor] = None, stno_batch_stride: int = 0,
          fddt_w: Optional[torch.Tensor] = None, fddt_b: Optional[torch.Tensor] = None,
          pos: Optional[torch.Tensor] = None, flags: int = 0, splits: int = 0, N: Optional[int] = None,
-         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+         aux: Optional[torch.Tensor] = None, ldw: Optional[int] = None) -> torch.Tensor:
     """out[b, m, :] = epilogue(sum_k A[b, m, k] W[:, k]) -- see dicow_gemm_bf16 in include/dicow_b200.h.
 
     A: bf16, rows addressed as A + b*a_batch_stride + m*lda.  W: bf16 [N, K].  Defaults describe a plain
@@ -101,7 +101,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     a.a2_batch_stride = a2_batch_stride
     a.K1 = K1
     a.W = _ptr(W)
-    a.ldw = W.stride(0)
+    a.ldw = W.stride(0) if ldw is None else ldw
     a.nb, a.Mb, a.N, a.K = nb, Mb, N, K
     a.bias = _ptr(bias)
     a.out = _ptr(out)
@@ -496,40 +496,59 @@ def conv1d_col2im(dcol: torch.Tensor, dx: torch.Tensor, *, B: int, T: int, T_out
     launch_count += 1
 
 
-def ctc_loss_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean", loss_scale: float = 1.0):
-    """CTC loss value and loss_scale * dL/dlogits (bf16, rows padded to a multiple of 8 columns for the wgrad GEMM)."""
+def ctc_loss_with_lse(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean"):
+    """CTC loss value plus the per-row log-sum-exp workspace the backward consumes (dicow_ctc_loss)."""
     dev = _require_cuda(logits, labels)
-    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int64
+    if reduction not in ("mean", "sum"):
+        raise NotImplementedError(f"ctc_loss_reduction={reduction}")
     labels = labels.contiguous()
     B, T, V1 = logits.shape
-    Lmax = labels.shape[1]
     ws_f = torch.empty(B * T + 2 * B, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     a = _lib.CtcLossArgs()
     a.struct_size = C.sizeof(_lib.CtcLossArgs)
     a.logits, a.B, a.T, a.V1 = _ptr(logits), B, T, V1
-    a.labels, a.Lmax = _ptr(labels), Lmax
+    a.labels, a.Lmax = _ptr(labels), labels.shape[1]
     a.reduction_mean = 1 if reduction == "mean" else 0
     a.workspace, a.loss = _ptr(ws_f), _ptr(loss)
     _call("dicow_ctc_loss", dev, a, "ctc_loss")
+    return loss, ws_f
+
+
+def ctc_loss_bwd(logits: torch.Tensor, labels: torch.Tensor, lse_ws: torch.Tensor, reduction: str = "mean",
+                 loss_scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    """loss_scale * (*scale_dev) * dL/dlogits (dicow_ctc_loss_bwd): bf16 [B, T, ceil8(V1)] with zeroed padding columns
+    (the wgrad GEMM's operand), or fp32 [B, T, V1] when ``out_f32`` (what autograd hands to a visible logits tensor)."""
+    dev = _require_cuda(logits, labels, lse_ws, scale_dev)
+    labels = labels.contiguous()
+    B, T, V1 = logits.shape
+    Lmax = labels.shape[1]
     S = 2 * Lmax + 1
-    ldd = -(-V1 // 8) * 8
+    ldd = V1 if out_f32 else -(-V1 // 8) * 8
     ws_b = torch.empty(2 * B * T * S + B, dtype=torch.float32, device=dev)
-    dlogits = torch.empty(B, T, ldd, dtype=torch.bfloat16, device=dev)
+    dlogits = torch.empty(B, T, ldd, dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
     b = _lib.CtcBwdArgs()
     b.struct_size = C.sizeof(_lib.CtcBwdArgs)
-    b.logits, b.lse, b.B, b.T, b.V1 = _ptr(logits), _ptr(ws_f), B, T, V1
-    b.labels, b.Lmax, b.reduction_mean, b.loss_scale = _ptr(labels), Lmax, a.reduction_mean, loss_scale
+    b.logits, b.lse, b.B, b.T, b.V1 = _ptr(logits), _ptr(lse_ws), B, T, V1
+    b.labels, b.Lmax, b.reduction_mean, b.loss_scale = _ptr(labels), Lmax, 1 if reduction == "mean" else 0, loss_scale
     b.workspace, b.dlogits_bf16, b.ldd = _ptr(ws_b), _ptr(dlogits), ldd
+    b.scale_dev, b.out_f32 = _ptr(scale_dev), 1 if out_f32 else 0
     _call("dicow_ctc_loss_bwd", dev, b, "ctc_bwd")
-    return loss, dlogits
+    return dlogits
+
+
+def ctc_loss_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean", loss_scale: float = 1.0):
+    """CTC loss value and loss_scale * dL/dlogits (bf16, rows padded to a multiple of 8 columns for the wgrad GEMM)."""
+    loss, ws_f = ctc_loss_with_lse(logits, labels, reduction)
+    return loss, ctc_loss_bwd(logits, labels, ws_f, reduction, loss_scale)
 
 
 def softlabel_ce_bwd(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optional[torch.Tensor] = None, *,
                      ts_begin: int = 0, smoothing: Optional[torch.Tensor] = None, soft_mode: bool = True,
-                     scale: float = 1.0) -> torch.Tensor:
-    """scale * d(sum of per-token losses)/dlogits as bf16 [rows, ceil8(V)] (dicow_softlabel_ce_bwd)."""
-    dev = _require_cuda(logits, labels, upp_labels, smoothing)
+                     scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scale * (*scale_dev) * d(sum of per-token losses)/dlogits as bf16 [rows, ceil8(V)] (dicow_softlabel_ce_bwd)."""
+    dev = _require_cuda(logits, labels, upp_labels, smoothing, scale_dev)
     labels = labels.reshape(-1).contiguous()
     upp = upp_labels.reshape(-1).contiguous() if upp_labels is not None else None
     rows, V = logits.shape
@@ -544,6 +563,54 @@ def softlabel_ce_bwd(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Opt
     a.smoothing = _ptr(smoothing)
     a.soft_mode = 1 if soft_mode else 0
     a.scale = scale
+    a.scale_dev = _ptr(scale_dev)
     a.dlogits_bf16, a.ldd = _ptr(out), ldd
     _call("dicow_softlabel_ce_bwd", dev, a, "ce_bwd")
+    return out
+
+
+def dgelu_mul(g: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, cols] = g * gelu'(pre) (dicow_dgelu_mul); g fp32 / bf16 and pre bf16, 2-D with unit column stride."""
+    global launch_count
+    dev = _require_cuda(g, pre)
+    assert g.dim() == 2 and pre.shape == g.shape and g.stride(1) == 1 and pre.stride(1) == 1
+    assert pre.dtype == torch.bfloat16 and g.dtype in (torch.bfloat16, torch.float32)
+    out = torch.empty(g.shape, dtype=torch.bfloat16, device=dev)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_dgelu_mul(h, _ptr(g), 1 if g.dtype == torch.bfloat16 else 0, g.stride(0), _ptr(pre),
+                                                 pre.stride(0), _ptr(out), out.stride(0), g.shape[0], g.shape[1], _stream(dev))
+    _lib.check(rc, h, "dicow_dgelu_mul")
+    launch_count += 1
+    return out
+
+
+def embedding_bwd(g: torch.Tensor, ids: torch.Tensor, *, S: int, d_tok: Optional[torch.Tensor],
+                  d_pos: Optional[torch.Tensor], past: int = 0) -> None:
+    """d_tok[ids[r]] += g[r], d_pos[past + r % S] += g[r] (dicow_embedding_bwd); g fp32 [B * S, d] contiguous."""
+    global launch_count
+    dev = _require_cuda(g, ids, d_tok, d_pos)
+    assert g.dtype == torch.float32 and g.is_contiguous() and ids.dtype == torch.int64 and ids.is_contiguous()
+    rows, d = g.shape
+    vocab = d_tok.shape[0] if d_tok is not None else 0
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_embedding_bwd(h, _ptr(g), _ptr(ids), rows, S, d, past, vocab, _ptr(d_tok), _ptr(d_pos),
+                                                     _stream(dev))
+    _lib.check(rc, h, "dicow_embedding_bwd")
+    launch_count += 1
+
+
+def cast_bf16_padded(src: torch.Tensor, cols_out: int) -> torch.Tensor:
+    """fp32 [rows, cols] (row stride arbitrary) -> bf16 [rows, cols_out] with zero padding (dicow_cast_f32_bf16_2d)."""
+    global launch_count
+    dev = _require_cuda(src)
+    assert src.dim() == 2 and src.dtype == torch.float32 and src.stride(1) == 1 and cols_out >= src.shape[1]
+    out = torch.empty(src.shape[0], cols_out, dtype=torch.bfloat16, device=dev)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_cast_f32_bf16_2d(h, _ptr(src), src.stride(0), _ptr(out), cols_out, src.shape[0],
+                                                        src.shape[1], cols_out, _stream(dev))
+    _lib.check(rc, h, "dicow_cast_f32_bf16_2d")
+    launch_count += 1
     return out
