@@ -34,6 +34,15 @@ def _worker(rank: int, world: int, port: int, q):
     for i, p in enumerate(params):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     n = parallel.allreduce_gradients(params, bucket_bytes=32)
+    # overlapped exchange: per-layer flat buckets reported while "the backward" is still running, waited for at the end
+    ex = parallel.GradientExchange()
+    flats = [torch.full((40,), float(rank + 1) * (k + 1)) for k in range(3)]
+    for fl in flats:
+        ex.bucket_ready(fl)
+    ex.finish()
+    assert ex.active and ex.n_collectives == 3 and ex.bytes == 3 * 40 * 4
+    for k, fl in enumerate(flats):
+        assert torch.allclose(fl, torch.full((40,), 1.5 * (k + 1)))
     parallel.barrier()
     q.put((rank, gathered, mx, sm, [p.grad.clone() for p in params], n))
     dist.destroy_process_group()

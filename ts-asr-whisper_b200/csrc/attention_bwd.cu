@@ -43,7 +43,8 @@ constexpr uint32_t R2_OFF = OWN_BYTES;
 constexpr uint32_t X1_OFF = 2 * OWN_BYTES;
 constexpr uint32_t X2_OFF = X1_OFF + XSTAGES * BLK_BYTES;
 constexpr uint32_t BAR_OFF = X2_OFF + XSTAGES * BLK_BYTES;
-constexpr uint32_t SMEM_BYTES = BAR_OFF + 128 + 1024;
+constexpr uint32_t STAT_OFF = BAR_OFF + 128;
+constexpr uint32_t SMEM_BYTES = STAT_OFF + 4 * BLK * 4 + 1024;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -73,6 +74,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_cons
   uint64_t* pds_full = sdp_full + 1;        // P / dS written back
   uint64_t* acc_done = pds_full + 1;        // all accumulating MMAs retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  float* s_stat = reinterpret_cast<float*>(smem + STAT_OFF);  // [2][-lse | -D][BLK] (dKV pass)
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -185,13 +187,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_cons
     const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
     const int own_idx = r0 + row;
     const long long stat_base = ((long long)b * p.H + h) * p.Tq;
-    float my_lse = 0.f, my_D = 0.f;
+    // statistics enter negated so that P = 2^(S log2e + (-lse)) and dS = P (dP + (-D)) are one packed FMA / ADD each
+    float my_nlse = 0.f, my_nD = 0.f;
     if (!DKV && own_idx < p.Tq) {
-      my_lse = __ldg(p.lse + stat_base + own_idx);
-      my_D = __ldg(p.D + stat_base + own_idx);
+      my_nlse = -__ldg(p.lse + stat_base + own_idx);
+      my_nD = -__ldg(p.D + stat_base + own_idx);
     }
+    // dKV: the per-column (query) statistics of the streamed block are staged in shared memory (double buffered) by the
+    // first 64 threads and read back as float4 broadcasts -- two L1 loads per element in the first version of this kernel
+    float pre_nlse = 0.f, pre_nD = 0.f;
+    if (DKV && row < BLK && nblk > 0) {
+      const int q = min(blk0 * BLK + row, p.Tq - 1);
+      pre_nlse = -__ldg(p.lse + stat_base + q), pre_nD = -__ldg(p.D + stat_base + q);
+    }
+    const int w_lo = r0 + warp * 32, w_hi = w_lo + 31;  // owned rows of this warp
     for (int i = 0; i < nblk; ++i) {
       const int c0 = (blk0 + i) * BLK;  // first streamed row of the block (key for dQ, query for dKV)
+      float* st_nlse = s_stat + (i & 1) * 2 * BLK;
+      float* st_nD = st_nlse + BLK;
+      if (DKV) {
+        if (row < BLK) {
+          st_nlse[row] = pre_nlse, st_nD[row] = pre_nD;
+          if (i + 1 < nblk) {
+            const int q = min(c0 + BLK + row, p.Tq - 1);
+            pre_nlse = -__ldg(p.lse + stat_base + q), pre_nD = -__ldg(p.D + stat_base + q);
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      // warp-uniform: every (owned row, streamed row) pair of this warp's 32 x 64 tile is visible -> no masking
+      bool interior;
+      if (!DKV)
+        interior = w_hi < p.Tq && c0 + BLK - 1 < p.Tk && (!p.causal || c0 + BLK - 1 <= w_lo + off);
+      else
+        interior = c0 + BLK - 1 < p.Tq && w_hi < p.Tk && (!p.causal || w_hi <= c0 + off);
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll
@@ -201,31 +230,52 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_cons
         tmem_ld_x32(lane_addr + DP_COL + hc * 32, dr);
         tmem_ld_wait();
         uint32_t pp[16], ds[16];
+        if (interior) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int col = c0 + hc * 32 + c + u;
-            float lse_c, D_c;
-            bool vis;
-            if (!DKV) {  // row = query own_idx, column = key col
-              lse_c = my_lse, D_c = my_D;
-              vis = own_idx < p.Tq && col < p.Tk && (!p.causal || col <= own_idx + off);
-            } else {  // row = key own_idx, column = query col
-              vis = col < p.Tq && own_idx < p.Tk && (!p.causal || own_idx <= col + off);
-              const int cc = min(col, p.Tq - 1);
-              lse_c = __ldg(p.lse + stat_base + cc);
-              D_c = __ldg(p.D + stat_base + cc);
+          for (int c = 0; c < 32; c += 4) {
+            float4 nl, nd;
+            if (!DKV) {
+              nl = make_float4(my_nlse, my_nlse, my_nlse, my_nlse), nd = make_float4(my_nD, my_nD, my_nD, my_nD);
+            } else {
+              nl = *reinterpret_cast<const float4*>(st_nlse + hc * 32 + c);
+              nd = *reinterpret_cast<const float4*>(st_nD + hc * 32 + c);
             }
-            const float sv = __uint_as_float(sr[c + u]);
-            const float dp = __uint_as_float(dr[c + u]);
-            const float pr = vis ? fast_exp2(fmaf(sv, kLog2e, -lse_c)) : 0.f;
-            pv[u] = pr;
-            dv[u] = pr * (dp - D_c);
+            const float2 l2 = make_float2(kLog2e, kLog2e);
+            const float2 e0 = fma_f32x2(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), l2, make_float2(nl.x, nl.y));
+            const float2 e1 = fma_f32x2(make_float2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), l2, make_float2(nl.z, nl.w));
+            const float2 p0 = make_float2(fast_exp2(e0.x), fast_exp2(e0.y)), p1 = make_float2(fast_exp2(e1.x), fast_exp2(e1.y));
+            const float2 t0 = add_f32x2(make_float2(__uint_as_float(dr[c]), __uint_as_float(dr[c + 1])), make_float2(nd.x, nd.y));
+            const float2 t1 = add_f32x2(make_float2(__uint_as_float(dr[c + 2]), __uint_as_float(dr[c + 3])), make_float2(nd.z, nd.w));
+            const float2 z2 = make_float2(0.f, 0.f);
+            const float2 d0 = fma_f32x2(p0, t0, z2), d1 = fma_f32x2(p1, t1, z2);
+            pp[c >> 1] = pack_bf16(p0.x, p0.y), pp[(c >> 1) + 1] = pack_bf16(p1.x, p1.y);
+            ds[c >> 1] = pack_bf16(d0.x, d0.y), ds[(c >> 1) + 1] = pack_bf16(d1.x, d1.y);
           }
-          pp[c >> 1] = pack_bf16(pv[0], pv[1]);
-          ds[c >> 1] = pack_bf16(dv[0], dv[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = c0 + hc * 32 + c + u;
+              float nlse_c, nD_c;
+              bool vis;
+              if (!DKV) {  // row = query own_idx, column = key col
+                nlse_c = my_nlse, nD_c = my_nD;
+                vis = own_idx < p.Tq && col < p.Tk && (!p.causal || col <= own_idx + off);
+              } else {  // row = key own_idx, column = query col
+                vis = col < p.Tq && own_idx < p.Tk && (!p.causal || own_idx <= col + off);
+                nlse_c = st_nlse[hc * 32 + c + u], nD_c = st_nD[hc * 32 + c + u];
+              }
+              const float sv = __uint_as_float(sr[c + u]);
+              const float dp = __uint_as_float(dr[c + u]);
+              const float pr = vis ? fast_exp2(fmaf(sv, kLog2e, nlse_c)) : 0.f;
+              pv[u] = pr;
+              dv[u] = pr * (dp + nD_c);
+            }
+            pp[c >> 1] = pack_bf16(pv[0], pv[1]);
+            ds[c >> 1] = pack_bf16(dv[0], dv[1]);
+          }
         }
         // P / dS (bf16) go over the first 32 columns of S / dP: columns [16 hc, 16 hc + 16) were read in half 0 already
         tmem_st_x16(lane_addr + SP_COL + hc * 16, pp);

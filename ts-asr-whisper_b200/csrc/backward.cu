@@ -197,6 +197,237 @@ __global__ void __launch_bounds__(512) ln_fddt_bwd_kernel(const LnBwdParams p, c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Ring variant (default when d % 8 == 0): the register-resident kernel above is latency bound (ncu / torch.profiler r01:
+// 190 us per launch at B = 8 against a 47 us HBM floor -- three CTA-wide barriers per pair of rows and only two rows of
+// loads in flight).  Here one producer warp streams whole rows (x fp32 | delta1 | delta2 | dy bf16 | g_in fp32) into a
+// shared-memory ring with cp.async.bulk + mbarrier transaction counts, RB_NS "statistics" warps turn a staged row into
+// its scalars (mean, rstd, mean(dy gamma), mean(dy gamma xhat) rstd, the 4 STNO weights) with warp shuffles only, and
+// the column-owner warps (thread t = float4 column t, FDDT tables / gamma / the 10 column accumulators in registers)
+// sweep the staged rows, write g_out / g_out_bf16 and release the stage.  No CTA-wide barrier in the loop; the HBM
+// latency is covered by the ring depth.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RB_NS = 4;        // statistics warps
+constexpr int RB_MAX_ST = 8;    // ring stages (one row each)
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// RB_VPL: float4 columns per statistics lane == number of column-owner warps (d <= 128 RB_VPL)
+template <int RB_VPL>
+__global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring_kernel(const LnBwdParams p, const int nst) {
+  constexpr int ncw = RB_VPL;
+  extern __shared__ __align__(128) uint8_t rsm[];
+  const int d = p.d, nvec = d >> 2;
+  const uint32_t xb = d * 4, hb = d * 2;
+  const uint32_t off_d1 = xb, off_d2 = xb + hb, off_dy = xb + 2 * hb, off_gin = xb + 3 * hb, stage_bytes = 2 * xb + 3 * hb;
+  const bool has_fddt = p.stno != nullptr, has_ln = p.gamma != nullptr;
+  uint8_t* ring = rsm;
+  float* tab = reinterpret_cast<float*>(rsm + (size_t)nst * stage_bytes);        // [8][d] FDDT w then b (statistics warps)
+  float* scal = tab + (has_fddt ? 8 * d : 0);                                     // [nst][8]
+  uint64_t* full = reinterpret_cast<uint64_t*>(scal + nst * 8);
+  uint64_t* stat = full + nst;
+  uint64_t* empty = stat + nst;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&stat[s], 1);
+      mbar_init(&empty[s], ncw);
+    }
+    fence_barrier_init();
+  }
+  if (has_fddt) {
+    for (int i = threadIdx.x; i < 4 * nvec; i += blockDim.x) {
+      reinterpret_cast<float4*>(tab)[i] =
+          p.fddt_w != nullptr ? __ldg(reinterpret_cast<const float4*>(p.fddt_w) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      reinterpret_cast<float4*>(tab)[4 * nvec + i] = __ldg(reinterpret_cast<const float4*>(p.fddt_b) + i);
+    }
+  }
+  __syncthreads();
+  const int n_local = (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // row = i * grid + block
+  const float inv_d = 1.0f / (float)d;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    const uint32_t tx = xb + (p.delta1 ? hb : 0) + (p.delta2 ? hb : 0) + (has_ln ? hb : 0) + (p.g_in ? xb : 0);
+    for (int i = 0; i < n_local; ++i) {
+      const int st = i % nst;
+      mbar_wait(&empty[st], ((i / nst) & 1) ^ 1);
+      if (elect_one()) {
+        const long long row = (long long)i * gridDim.x + blockIdx.x;
+        uint8_t* dst = ring + (size_t)st * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], tx);
+        bulk_g2s(dst, p.x + row * d, xb, &full[st]);
+        if (p.delta1) bulk_g2s(dst + off_d1, p.delta1 + row * d, hb, &full[st]);
+        if (p.delta2) bulk_g2s(dst + off_d2, p.delta2 + row * d, hb, &full[st]);
+        if (has_ln) bulk_g2s(dst + off_dy, p.dy + row * d, hb, &full[st]);
+        if (p.g_in) bulk_g2s(dst + off_gin, p.g_in + row * d, xb, &full[st]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  if (warp <= RB_NS) {
+    // ===================== statistics warps: one row each per turn =====================
+    for (int i = warp - 1; i < n_local; i += RB_NS) {
+      const int st = i % nst;
+      const int row = i * (int)gridDim.x + (int)blockIdx.x;
+      float m[4] = {0.f, 0.f, 0.f, 0.f};
+      if (has_fddt) {
+        const int b = row / p.T, t = row - b * p.T;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m[c] = __ldg(p.stno + (long long)b * p.stno_bs + (long long)c * p.T + t);
+      }
+      mbar_wait(&full[st], (i / nst) & 1);
+      float mean = 0.f, rstd = 0.f, c1 = 0.f, c2 = 0.f;
+      if (has_ln) {
+        const uint8_t* src = ring + (size_t)st * stage_bytes;
+        float4 xp[RB_VPL], dg[RB_VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < RB_VPL; ++k) {
+          const int c4 = lane + 32 * k;
+          xp[k] = make_float4(0.f, 0.f, 0.f, 0.f), dg[k] = xp[k];
+          if (c4 < nvec) {
+            float4 v = reinterpret_cast<const float4*>(src)[c4];
+            if (p.delta1) v = f4_add(v, bf16x4(reinterpret_cast<const uint2*>(src + off_d1)[c4]));
+            if (p.delta2) v = f4_add(v, bf16x4(reinterpret_cast<const uint2*>(src + off_d2)[c4]));
+            if (has_fddt) {
+              float4 w = make_float4(0.f, 0.f, 0.f, 0.f), bb = w;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                w = f4_add(w, f4_scale(reinterpret_cast<const float4*>(tab + c * d)[c4], m[c]));
+                bb = f4_add(bb, f4_scale(reinterpret_cast<const float4*>(tab + (4 + c) * d)[c4], m[c]));
+              }
+              v = f4_add(f4_mul(v, w), bb);
+            }
+            xp[k] = v;
+            dg[k] = f4_mul(bf16x4(reinterpret_cast<const uint2*>(src + off_dy)[c4]),
+                           __ldg(reinterpret_cast<const float4*>(p.gamma) + c4));
+            s1 += f4_sum(v), s2 += f4_sum(dg[k]);
+          }
+        }
+        mean = warp_sum(s1) * inv_d, c1 = warp_sum(s2) * inv_d;
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < RB_VPL; ++k) {
+          if (lane + 32 * k < nvec) {
+            const float4 xc = make_float4(xp[k].x - mean, xp[k].y - mean, xp[k].z - mean, xp[k].w - mean);
+            q1 += f4_sum(f4_mul(xc, xc)), q2 += f4_sum(f4_mul(dg[k], xc));
+          }
+        }
+        rstd = rsqrtf(warp_sum(q1) * inv_d + p.eps);
+        c2 = warp_sum(q2) * inv_d * rstd * rstd;
+      }
+      if (lane == 0) {
+        float4* sc = reinterpret_cast<float4*>(scal + st * 8);
+        sc[0] = make_float4(mean, rstd, c1, c2);
+        sc[1] = make_float4(m[0], m[1], m[2], m[3]);
+        mbar_arrive(&stat[st]);  // release: the scalars are visible to whoever observes this phase
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // ===================== column owners =====================
+  const int tid = (warp - 1 - RB_NS) * 32 + lane;
+  const bool own = tid < nvec;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 tw[4], tb[4], g4 = z4, acc_dg = z4, acc_db = z4, acc_w[4], acc_b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tw[c] = make_float4(1.f, 1.f, 1.f, 1.f), tb[c] = z4, acc_w[c] = z4, acc_b[c] = z4;
+    if (own && has_fddt) {
+      if (p.fddt_w != nullptr) tw[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_w + (long long)c * d) + tid);
+      tb[c] = __ldg(reinterpret_cast<const float4*>(p.fddt_b + (long long)c * d) + tid);
+    }
+  }
+  if (own && has_ln) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma) + tid);
+  for (int i = 0; i < n_local; ++i) {
+    const int st = i % nst;
+    const long long row = (long long)i * gridDim.x + blockIdx.x;
+    mbar_wait(&stat[st], (i / nst) & 1);
+    const uint8_t* src = ring + (size_t)st * stage_bytes;
+    float4 g = z4;
+    if (own) {
+      const float4 s0 = reinterpret_cast<const float4*>(scal + st * 8)[0];  // mean, rstd, c1, c2
+      const float4 mk = reinterpret_cast<const float4*>(scal + st * 8)[1];
+      const float mm[4] = {mk.x, mk.y, mk.z, mk.w};
+      float4 xs = reinterpret_cast<const float4*>(src)[tid];
+      if (p.delta1) xs = f4_add(xs, bf16x4(reinterpret_cast<const uint2*>(src + off_d1)[tid]));
+      if (p.delta2) xs = f4_add(xs, bf16x4(reinterpret_cast<const uint2*>(src + off_d2)[tid]));
+      float4 weff = make_float4(1.f, 1.f, 1.f, 1.f), xp = xs;
+      if (has_fddt) {
+        float4 w = z4, bb = z4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w = f4_add(w, f4_scale(tw[c], mm[c])), bb = f4_add(bb, f4_scale(tb[c], mm[c]));
+        weff = w;
+        xp = f4_add(f4_mul(xs, w), bb);
+      }
+      float4 dxp = z4;
+      if (has_ln) {
+        const float4 dy = bf16x4(reinterpret_cast<const uint2*>(src + off_dy)[tid]);
+        const float4 dyg = f4_mul(dy, g4);
+        const float4 xc = make_float4(xp.x - s0.x, xp.y - s0.x, xp.z - s0.x, xp.w - s0.x);
+        // dx' = rstd * (dyg - mean(dyg) - xc * mean(dyg xhat) rstd)
+        dxp = make_float4(s0.y * (dyg.x - s0.z - xc.x * s0.w), s0.y * (dyg.y - s0.z - xc.y * s0.w),
+                          s0.y * (dyg.z - s0.z - xc.z * s0.w), s0.y * (dyg.w - s0.z - xc.w * s0.w));
+        acc_dg = f4_add(acc_dg, f4_mul(dy, f4_scale(xc, s0.y)));
+        acc_db = f4_add(acc_db, dy);
+      }
+      if (p.g_in) dxp = f4_add(dxp, reinterpret_cast<const float4*>(src + off_gin)[tid]);
+      g = dxp;
+      if (has_fddt) {
+        const float4 dweff = f4_mul(dxp, xs);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc_w[c] = f4_add(acc_w[c], f4_scale(dweff, mm[c]));
+          acc_b[c] = f4_add(acc_b[c], f4_scale(dxp, mm[c]));
+        }
+        g = f4_mul(dxp, weff);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // this warp's smem reads of the stage are done
+    if (own) {
+      reinterpret_cast<float4*>(p.g_out + row * d)[tid] = g;
+      if (p.g_out_bf16 != nullptr)
+        reinterpret_cast<uint2*>(p.g_out_bf16 + row * d)[tid] = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+    }
+  }
+  if (own) {
+    if (has_ln && p.dgamma != nullptr) {
+      atomic_add4(p.dgamma + 4 * tid, acc_dg);
+      atomic_add4(p.dbeta + 4 * tid, acc_db);
+    }
+    if (has_fddt && p.dfddt_b != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (p.dfddt_w != nullptr) atomic_add4(p.dfddt_w + (long long)c * d + 4 * tid, acc_w[c]);
+        atomic_add4(p.dfddt_b + (long long)c * d + 4 * tid, acc_b[c]);
+      }
+    }
+  }
+}
+
+template <int VPL>
+int launch_ln_bwd_ring(dicow_ctx* ctx, const LnBwdParams& p, int nst, size_t smem, int grid, cudaStream_t stream) {
+  auto kfn = ln_fddt_bwd_ring_kernel<VPL>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  kfn<<<grid, (1 + RB_NS + VPL) * 32, smem, stream>>>(p, nst);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // out[n] += sum_rows X[row, n]     (bias gradients);  X bf16 or fp32
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -576,10 +807,30 @@ extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_arg
   p.gamma = a->gamma, p.eps = a->eps, p.dy = reinterpret_cast<const __nv_bfloat16*>(a->dy_bf16), p.g_in = a->g_in;
   p.g_out = a->g_out, p.g_out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->g_out_bf16);
   p.dgamma = a->dgamma, p.dbeta = a->dbeta, p.dfddt_w = a->dfddt_w, p.dfddt_b = a->dfddt_b;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool aligned = (a->d % 8) == 0 && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a->delta1_bf16) % 16) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a->delta2_bf16) % 16) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a->dy_bf16) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->g_in) % 16) == 0;
+  if (aligned && a->rows >= 64) {
+    // ring kernel: stage = one row of every input stream; as many stages as fit next to the FDDT tables
+    const size_t stage = (size_t)a->d * 14, fixed = (p.stno ? (size_t)32 * a->d : 0) + RB_MAX_ST * (32 + 24) + 256;
+    int nst = (int)(((size_t)ctx->max_smem_optin - fixed) / stage);
+    nst = nst > RB_MAX_ST ? RB_MAX_ST : nst;
+    if (nst >= 3) {
+      const int ncw = ceil_div(a->d / 4, 32);
+      const size_t smem = (size_t)nst * stage + fixed;
+      const int grid = a->rows < ctx->num_sms ? a->rows : ctx->num_sms;
+      if (ncw <= 4) return launch_ln_bwd_ring<4>(ctx, p, nst, smem, grid, stream);
+      if (ncw <= 8) return launch_ln_bwd_ring<8>(ctx, p, nst, smem, grid, stream);
+      if (ncw <= 10) return launch_ln_bwd_ring<10>(ctx, p, nst, smem, grid, stream);
+      return launch_ln_bwd_ring<16>(ctx, p, nst, smem, grid, stream);
+    }
+  }
   const int threads = ceil_div(a->d / 4, 32) * 32;
   const int groups = ceil_div(a->rows, LB_ROWS);
   const int grid = groups < 2 * ctx->num_sms ? groups : 2 * ctx->num_sms;
-  ln_fddt_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p, groups);
+  ln_fddt_bwd_kernel<<<grid, threads, 0, stream>>>(p, groups);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

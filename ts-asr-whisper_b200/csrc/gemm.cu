@@ -90,9 +90,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
   }
   if constexpr (EPI == DICOW_EPI_DGELU_BF16) {  // backward: out = acc * gelu'(pre)
     const __nv_bfloat16* a = p.aux + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+    if (ncols == 32 && p.out_vec_ok) {  // 4 x 16-byte loads per thread-row instead of 32 two-byte ones
+      uint4 q[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) v[j] *= dgelu_erf_fast(__bfloat162float(a[j]));
+      for (int j = 0; j < 4; ++j) q[j] = __ldg(reinterpret_cast<const uint4*>(a) + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+          v[8 * j + 2 * k] *= dgelu_erf_fast(f.x);
+          v[8 * j + 2 * k + 1] *= dgelu_erf_fast(f.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] *= dgelu_erf_fast(__bfloat162float(a[j]));
+    }
   }
   if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_FDDT_POS_F32 || EPI == DICOW_EPI_GELU_SAVE_BF16) {
 #pragma unroll

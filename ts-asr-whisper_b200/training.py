@@ -49,16 +49,61 @@ def _dev_scalar(v: float, dev: torch.device) -> torch.Tensor:
     return t
 
 
+# Set to a parallel.GradientExchange to all-reduce finished gradient groups on a communication stream while the backward
+# is still running (the one exchange step of the path).  None: gradients are only handed to autograd (a DDP
+# wrapper or parallel.allreduce_gradients can exchange them afterwards).
+gradient_exchange = None
+
+
 class _Grads:
     """fp32 gradient buffers keyed by parameter object; created on first use, only for parameters that require grad.
+    ``reserve`` lays the gradients of a parameter group (one layer) out as views of ONE flat buffer so that the group is
+    exchanged with a single collective and no packing copy (``flush``).
     A matrix whose row count is not a multiple of 8 (lm_head 51867, embed_tokens 51866) gets a row-padded buffer: the
     wgrad GEMM consumes dY MN-major and wants its M dimension a multiple of 8; the gradient handed to autograd is the
     [:rows] view."""
 
-    def __init__(self):
+    def __init__(self, exchange=None):
         self.buf: Dict[int, torch.Tensor] = {}
         self.full: Dict[int, torch.Tensor] = {}
         self.params: Dict[int, torch.nn.Parameter] = {}
+        self.exchange = exchange
+
+    def reserve(self, params) -> Optional[torch.Tensor]:
+        """allocate the (not yet existing) gradients of ``params`` contiguously; returns the flat buffer or None"""
+        todo, seen, total = [], set(), 0
+        for p in params:
+            if p is None or not p.requires_grad or id(p) in self.buf or id(p) in seen:
+                continue
+            seen.add(id(p))
+            shape = tuple(p.shape)
+            if p.dim() >= 2 and shape[0] % 8:
+                shape = (_ceil8(shape[0]),) + shape[1:]
+            n = 1
+            for v in shape:
+                n *= v
+            todo.append((p, shape, total, n))
+            total += -(-n // 32) * 32  # 128-byte aligned segments (TMA / vector accesses on the views)
+        if not todo:
+            return None
+        flat = torch.zeros(total, dtype=torch.float32, device=todo[0][0].device)
+        for p, shape, off, n in todo:
+            full = flat[off:off + n].view(shape)
+            self.full[id(p)], self.buf[id(p)], self.params[id(p)] = full, full[:p.shape[0]] if p.dim() >= 1 else full, p
+        return flat
+
+    def flush(self, flat: Optional[torch.Tensor]) -> None:
+        if flat is not None and self.exchange is not None:
+            self.exchange.bucket_ready(flat)
+
+    def finish(self, params) -> tuple:
+        """the gradients in the order of ``params`` (None for frozen ones); drops this object's references so that
+        autograd's AccumulateGrad can adopt the buffers instead of cloning them"""
+        if self.exchange is not None:
+            self.exchange.finish()
+        out = tuple(self.buf.get(id(p)) if p.requires_grad else None for p in params)
+        self.buf, self.full, self.params = {}, {}, {}
+        return out
 
     def want(self, p: Optional[torch.nn.Parameter]) -> bool:
         return p is not None and p.requires_grad
@@ -297,6 +342,8 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
     V1 = w["lm_head"].shape[0]
     dl = dlogits.view(B * T2, -1)
     ldd = dl.shape[1]
+    flat = g.reserve([enc.lm_head.weight, enc.subsample_conv1.weight, enc.subsample_conv2.weight]
+                     + list(enc.additional_self_attention_layer.parameters()))
     # lm_head (no bias): dneck = dlogits W ; dW += dlogits^T neck
     dneck = torch.empty(B * T2, d, dtype=torch.bfloat16, device=dl.device)
     ops.gemm(dl, w["lm_head"], dneck, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T, K=V1, lda=ldd, Mb=B * T2)
@@ -316,8 +363,11 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
                       H=H, Tq=T, Tk=T, q_row_stride=3 * d, q_batch_stride=T * 3 * d, kv_row_stride=3 * d,
                       kv_batch_stride=T * 3 * d, o_row_stride=d, o_batch_stride=T * d, dq_row_stride=3 * d,
                       dq_batch_stride=T * 3 * d, dkv_row_stride=3 * d, dkv_batch_stride=T * 3 * d)
-    return _attention_params_backward(g, att, e, dqkv, c["hidden"], d, need_dhidden,
-                                      dx_accum=dhidden_accum if need_dhidden else None)
+    dh = _attention_params_backward(g, att, e, dqkv, c["hidden"], d, need_dhidden,
+                                    dx_accum=dhidden_accum if need_dhidden else None)
+    _fold_conv_grads(g)
+    g.flush(flat)
+    return dh
 
 
 def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderTape) -> None:
@@ -332,11 +382,22 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
     G = torch.empty(rows, d, dtype=torch.float32, device=dev)
     Gb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
     ln = enc.layer_norm
+    n_layers = len(w["layers"])
+
+    def group(i):  # one exchange bucket per layer: its own parameters, its FDDT tables (+ the final LayerNorm with the last)
+        ps = list(enc.layers[i].parameters())
+        if tape.layers[i]["fd"] is not None:
+            ps += list(enc.fddts[i].parameters())
+        return ps + ([ln.weight, ln.bias] if i == n_layers - 1 else [])
+
+    flat = g.reserve(group(n_layers - 1)) if n_layers else g.reserve([ln.weight, ln.bias])
     ops.layernorm_fddt_bwd(f["x"], G, dy=d_hidden_bf16, gamma=w["lnf_g"], delta1=f["d1"], delta2=f["d2"], g_out_bf16=Gb,
                            dgamma=g.get(ln.weight) if g.want(ln.weight) else None,
                            dbeta=g.get(ln.bias) if g.want(ln.bias) else None)
-    for i in range(len(w["layers"]) - 1, -1, -1):
+    for i in range(n_layers - 1, -1, -1):
         e, s, lyr = w["layers"][i], tape.layers[i], enc.layers[i]
+        if i != n_layers - 1:
+            flat = g.reserve(group(i))
         # fc2 / fc1 (G is the gradient of x_post + d1 + d2, hence of d2 = fc2(...) as well)
         dpre = _linear_backward(g, Gb, s["hdn"], e["w2"], lyr.fc2.weight, lyr.fc2.bias, dx_epilogue=ops.EPI_DGELU_BF16,
                                 aux=s["pre"])
@@ -375,7 +436,15 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
                                dbeta=g.get(n1.bias) if g.want(n1.bias) else None, dfddt_w=dfw, dfddt_b=dfb)
         if dfw is not None:
             _scatter_fddt_grads(g, enc.fddts[i], dfw, dfb)
+        g.flush(flat)
+        tape.layers[i] = None  # this layer's activations are dead: let the allocator reuse them
+    if not n_layers:
+        g.flush(flat)
+    flat = g.reserve([enc.conv1.weight, enc.conv1.bias, enc.conv2.weight, enc.conv2.bias, enc.embed_positions.weight]
+                     + (list(enc.initial_fddt.parameters()) if (cfg.use_fddt and cfg.use_pre_pos_fddt) else []))
     _stem_backward(enc, g, G, tape)
+    _fold_conv_grads(g)
+    g.flush(flat)
 
 
 def _scatter_fddt_grads(g: _Grads, fmod, dfw: torch.Tensor, dfb: torch.Tensor) -> None:
@@ -531,6 +600,7 @@ def decoder_backward(model, g: _Grads, dlogits: torch.Tensor, tape: DecoderTape,
     dhid = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
     ops.gemm(dlogits, w["proj"], dhid, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T, K=V, lda=ldd, Mb=rows)
     emb = dec.embed_tokens.weight
+    flat_top = g.reserve([emb, dec.embed_positions.weight, dec.layer_norm.weight, dec.layer_norm.bias])
     if g.want(emb):
         ops.gemm(dlogits, f["hid_bf16"], g.get_padded(emb), epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T,
                  lda=ldd, Mb=ldd, K=rows, N=d)
@@ -539,6 +609,7 @@ def decoder_backward(model, g: _Grads, dlogits: torch.Tensor, tape: DecoderTape,
     for i in range(len(w["layers"]) - 1, -1, -1):
         e, t, lyr = w["layers"][i], tape.layers[i], dec.layers[i]
         s, c = e["self"], e["cross"]
+        flat = g.reserve(list(lyr.parameters()))
         # MLP
         dpre = _linear_backward(g, Gb, t["hdn"], e["w2"], lyr.fc2.weight, lyr.fc2.bias, dx_epilogue=ops.EPI_DGELU_BF16,
                                 aux=t["pre"])
@@ -571,10 +642,12 @@ def decoder_backward(model, g: _Grads, dlogits: torch.Tensor, tape: DecoderTape,
                           dkv_row_stride=3 * d, dkv_batch_stride=S * 3 * d, **_self_attn_strides(S, d))
         dln1 = _attention_params_backward(g, sa, s, dqkv, t["ln1"], d, True)
         G, Gb = _ln_bwd(g, lyr.self_attn_layer_norm, t["x0"], e["ln1_g"], dln1, G1, rows, d, dev)
+        g.flush(flat)
     pos = dec.embed_positions.weight
     if g.want(emb) or g.want(pos):
         ops.embedding_bwd(G, f["ids"].view(-1), S=S, d_tok=g.get(emb) if g.want(emb) else None,
                           d_pos=g.get(pos) if g.want(pos) else None)
+    g.flush(flat_top)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -621,16 +694,15 @@ class EncoderLogitsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_logits, _grad_hidden):
         enc, tape = ctx.enc, ctx.tape
-        g = _Grads()
+        g = _Grads(gradient_exchange)
         with torch.no_grad():
             V1 = grad_logits.shape[-1]
             dl = ops.cast_bf16_padded(grad_logits.reshape(-1, V1).float(), _ceil8(V1))
             dh = ctc_head_backward(enc, g, dl.view(grad_logits.shape[0], grad_logits.shape[1], -1), tape, need_dhidden=ctx.body)
             if ctx.body:
                 encoder_backward(enc, g, dh, tape)
-            _fold_conv_grads(g)
         ctx.tape = None
-        return (None, None, None) + tuple(g.buf.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        return (None, None, None) + g.finish(ctx.params)
 
 
 class CtcLossFn(torch.autograd.Function):
@@ -708,7 +780,7 @@ class DiCoWTrainStepFn(torch.autograd.Function):
         cfg = model.config
         enc = model.model.get_encoder()
         logits, labels, upp, enc_logits, enc_labels, ctc_ws, n_norm = ctx.saved
-        g = _Grads()
+        g = _Grads(gradient_exchange)
         B, S, V = logits.shape
         with torch.no_grad():
             gl = grad_loss.reshape(1).float()
@@ -728,6 +800,5 @@ class DiCoWTrainStepFn(torch.autograd.Function):
                 del dl
             if ctx.body:
                 encoder_backward(enc, g, ops.cast_bf16(d_enc), ctx.etape)
-            _fold_conv_grads(g)
         ctx.etape = ctx.dtape = ctx.saved = None
-        return (None,) * 7 + tuple(g.buf.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        return (None,) * 7 + g.finish(ctx.params)
