@@ -252,6 +252,11 @@ DICOW_API int dicow_conv1d_col2im(dicow_handle_t h, const void* dcol_bf16, void*
  * Backward of the GELUs of the conv stem (src/models/dicow/encoder.py:167-168) where no dgrad GEMM epilogue sits. */
 DICOW_API int dicow_dgelu_mul(dicow_handle_t h, const void* g, int g_is_bf16, int64_t ldg, const void* pre_bf16, int64_t ldp,
                               void* out_bf16, int64_t ldo, int rows, int cols, void* stream);
+/* backward of the SE-DiCoW gate (src/models/dicow/layers.py:79-93,168: q + tanh(gate) * upd) for g = dL/d(output) fp32:
+ * dupd_bf16[r, c] = tanh(*gate) * g[r, c];  *dgate += (1 - tanh^2(*gate)) * sum_rc g[r, c] * upd_bf16[r, c]  (dgate may be
+ * NULL).  cols and the leading dimensions (elements) must be even. */
+DICOW_API int dicow_gate_bwd(dicow_handle_t h, const float* g, int64_t ldg, const void* upd_bf16, int64_t ldu, const float* gate,
+                             void* dupd_bf16, int64_t ldd, int rows, int cols, float* dgate, void* stream);
 /* out_bf16[r, c] = in[r, c] for c < cols, 0 for cols <= c < cols_out: an fp32 gradient (e.g. d logits handed over by
  * autograd) re-laid as the zero-padded bf16 operand of the dgrad / wgrad GEMMs */
 DICOW_API int dicow_cast_f32_bf16_2d(dicow_handle_t h, const float* in, int64_t ldi, void* out_bf16, int64_t ldo, int rows,

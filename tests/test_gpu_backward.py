@@ -158,3 +158,20 @@ def test_softlabel_ce_backward(ops, soft):
     e = rel(dl[:, :V].cpu(), x.grad)
     print(f"ce grad rel err (soft={soft}): {e:.3e}")
     assert e < 1e-2 and float(dl[:, V:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(300, 128, 128), (1500, 1280, 2560), (7, 6, 8)])
+def test_gate_bwd(ops, rows, cols, ld):
+    """SE-DiCoW gate backward (layers.py:79-93,168): dupd = tanh(g) * G, dgate = (1 - tanh^2 g) * sum(G * upd)"""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    G = torch.randn(rows, ld, generator=gen, device="cuda")[:, :cols]
+    upd = torch.randn(rows, ld, generator=gen, device="cuda").bfloat16()[:, :cols]
+    gate = torch.tensor([0.37], device="cuda")
+    dgate = torch.tensor([0.25], device="cuda")  # accumulates
+    out = ops.gate_bwd(G, upd, gate, dgate)
+    th = torch.tanh(gate.double())
+    ref = (th * G.double())
+    ref_dg = 0.25 + ((1 - th * th) * (G.double() * upd.double()).sum()).item()
+    assert (out.double() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()  # bf16 output rounding
+    assert abs(dgate.item() - ref_dg) <= 1e-3 * max(1.0, abs(ref_dg))
+    assert torch.equal(ops.gate_bwd(G, upd, gate, None), out)

@@ -7,6 +7,9 @@ Both BASELINE training configurations are covered at miniature and whisper-tiny 
   * DiCoW fine-tuning (configs[2]): ``DiCoWForConditionalGeneration.forward(labels, upp_labels)`` -> 0.7 CE + 0.3 CTC, with
     the decoder frozen (the recipe) and with every parameter trainable.
 
+SE-DiCoW (enrollment streams through the speaker communication blocks, src/models/dicow/layers.py:145-193) is covered by
+``test_se_dicow_finetune_step`` / ``test_se_dicow_ctc_pretrain_step`` (gate off its zero init so every SCB gradient is live).
+
 Tolerance: the path computes with bf16 operands (fp32 accumulation / residual stream / statistics) against an fp32
 reference, so per-parameter gradients are required to agree to max |err| <= GRAD_TOL x max |ref| (north_star: 2e-2 bf16;
 gradients accumulate one bf16 rounding per layer on the way back and the max-norm is taken over up to 10^6 entries of a
@@ -23,6 +26,13 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GRAD_TOL = 5e-2
+# The SCB gate gradient is ONE scalar = sum over B*T*d signed terms G*upd.  At miniature dims the sum is well conditioned
+# (|sum| ~ 6 x the l2 norm of its terms) and the 5e-2 bound on the sum itself applies (scale = |sum|); at whisper-tiny
+# dims it cancels to 0.3 % of sum|terms| (measured on the fp32 oracle: 0.098 vs 31.8, l2 norm 0.13), where bf16 errors of
+# the heavy-tailed stream gradient G (bounded relative to max|G|, not per term) reach ~0.1 x the l2 norm.  The bound is
+# therefore taken against max(|sum|, l2 norm of the terms); tests/test_gpu_backward.py::test_gate_bwd pins the kernel's
+# arithmetic exactly on identical inputs.
+GATE_TOL = 0.25
 EOS, SOT, LANG, TASK, NOTS, TS_BEGIN, N_TS = 257, 258, 259, 260, 261, 262, 38
 HEAD = ("model.encoder.additional_self_attention_layer", "model.encoder.subsample_conv", "model.encoder.lm_head")
 
@@ -52,13 +62,25 @@ def _build(dm: synth.Dims):
     return model, p
 
 
-def _compare(model, p, names, label):
+def _compare(model, p, names, label, scalar_refs=None):
+    """scalar_refs: {name: (gradient, scale)} for scalar parameters whose gradient is a sum of many signed terms (the
+    SCB gate): the error is measured against the l2 norm of the terms (the random-walk size of the sum) when the sum
+    itself cancels below it -- a relative error on a cancelling sum measures the conditioning, not the kernels."""
     worst = 0.0
     named = dict(model.named_parameters())
     checked = 0
     for n in names:
-        got, ref = named[n].grad, p[n].grad
+        got = named[n].grad
         assert got is not None, f"{label}: no gradient for {n}"
+        if scalar_refs and n in scalar_refs:
+            ref, scale = scalar_refs[n]
+            err = abs(got.item() - ref) / scale
+            print(f"{label}: {n}: got {got.item():.4e} ref {ref:.4e} cancellation scale {scale:.4e} err/scale {err:.3e}")
+            tol = GRAD_TOL if abs(ref) >= scale else GATE_TOL  # well conditioned: the usual bound on the sum itself
+            assert err < tol, f"{label}: {n}: got {got.item():.4e} ref {ref:.4e} scale {scale:.4e}"
+            checked += 1
+            continue
+        ref = p[n].grad
         assert ref is not None, f"{label}: oracle has no gradient for {n}"
         scale = ref.abs().max().item()
         if scale < 1e-12:
@@ -174,3 +196,93 @@ def test_training_step_updates_and_second_step():
         ev = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
     out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
     assert abs(ev.loss.item() - out.loss.item()) < 1e-3 * max(1.0, abs(ev.loss.item()))
+
+
+# ---- SE-DiCoW: enrollment streams + speaker communication blocks in the training step -------------------------------
+SE_MINI = synth.GOLDEN_MINI  # 3 layers, 2 of them with an SCB, odd T
+SE_TINY = dataclasses.replace(TINY_SHORT, enc_layers=3, use_enrollments=True, scb_layers=2)
+
+
+def _expand_gates(p, names, B, dm):
+    """give the oracle one gate entry per element of the gated update (all equal to the scalar), so that autograd returns
+    the individual terms of the scalar gate gradient: their sum is the reference, their l2 norm its conditioning scale"""
+    gates = [n for n in names if n.endswith("cross_gate.gate")]
+    for n in gates:
+        p[n] = p[n].detach().reshape(1, 1, 1).expand(B, dm.T, dm.d).clone().requires_grad_(True)
+    return gates
+
+
+def _gate_refs(p, gates):
+    out = {}
+    for n in gates:
+        terms = p[n].grad.double()
+        total = terms.sum().item()
+        out[n] = (total, max(abs(total), terms.norm().item()))
+    return out
+
+
+def _enrollment_inputs(dm, B, tag):
+    return {"input_features": torch.from_numpy(synth.make_features(tag + "e", B, dm.n_mels, 2 * dm.T)).to(DEV),
+            "stno_mask": torch.from_numpy(synth.make_stno(tag + "e", B, dm.T, "hard")).to(DEV)}
+
+
+@pytest.mark.parametrize("dm,B,S", [(SE_MINI, 2, 11), (SE_TINY, 2, 20)], ids=["mini", "tiny-short"])
+@pytest.mark.parametrize("mode", ["decoder-frozen", "scb-only"])
+def test_se_dicow_finetune_step(dm, B, S, mode):
+    """the se_dicow recipe: DiCoWForConditionalGeneration.forward(..., enrollments=...) -> loss.backward()"""
+    model, p = _build(dm)
+    model.set_tokenizer(FakeTokenizer())
+    for n, q in model.named_parameters():
+        if mode == "decoder-frozen":
+            q.requires_grad_(n.startswith("model.encoder.") and "embed_positions" not in n)
+        else:  # configs/train/se_dicow.yaml prefixes_to_preheat: the new blocks first
+            q.requires_grad_("ca_enrolls" in n)
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    assert any("ca_enrolls" in n and "cross_gate" in n for n in trainable)
+    feats, stno = _inputs(dm, B, "se1")
+    enr = _enrollment_inputs(dm, B, "se1")
+    labels = torch.from_numpy(synth.make_labels("se1", B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK)))
+    labels = labels.to(DEV)
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels, enrollments=enr)
+    assert out.loss.requires_grad
+    out.loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    gates = _expand_gates(p, trainable, B, dm)
+    ref_loss, ref_logits, _ = orc.model_forward(p, dm, feats, stno, labels, labels, enrollments=enr,
+                                                ctc_prefix_tokens=(SOT, LANG, TASK), ts_begin=TS_BEGIN, n_ts=N_TS)
+    ref_loss.backward()
+    torch.cuda.synchronize()
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    err = ((out.logits.float() - ref_logits).abs().max() / ref_logits.abs().max()).item()
+    assert err < 2e-2, f"logits rel err {err:.3e}"
+    _compare(model, p, trainable, f"se-finetune[{mode}]", _gate_refs(p, gates))
+    # the no_grad evaluation (interleaved inference path) agrees with the stacked training path
+    with torch.no_grad():
+        ev = model(feats, stno_mask=stno, labels=labels, upp_labels=labels, enrollments=enr)
+    assert abs(ev.loss.item() - out.loss.item()) < 1e-2 * max(1.0, abs(ev.loss.item()))
+
+
+def test_se_dicow_ctc_pretrain_step():
+    """encoder(return_logits=True, enrollments=...) -> get_loss -> backward with the whole encoder trainable"""
+    dm, B = SE_MINI, 2
+    model, p = _build(dm)
+    enc = model.get_encoder()
+    for n, q in model.named_parameters():
+        q.requires_grad_(n.startswith("model.encoder.") and "embed_positions" not in n)
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    feats, stno = _inputs(dm, B, "se2")
+    enr = _enrollment_inputs(dm, B, "se2")
+    labels = torch.tensor([[5, 9, 17, 3], [8, 2, -100, -100]], dtype=torch.int64, device=DEV)
+    out = enc(feats, stno_mask=stno, return_logits=True, enrollments=enr)
+    loss = enc.get_loss(out.logits, labels)
+    loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    gates = _expand_gates(p, trainable, B, dm)
+    ref_logits = orc.encoder_forward(p, dm, feats, stno, enr, return_logits=True)
+    ref_loss = orc.ctc_loss(ref_logits, labels)
+    ref_loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    _compare(model, p, trainable, "se-ctc-pretrain", _gate_refs(p, gates))

@@ -480,6 +480,41 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const T* __restrict__ g,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// SCB gate backward (src/models/dicow/layers.py:79-93,168: q + tanh(gate) * upd):
+//   dupd_bf16 = tanh(gate) * G          dgate += (1 - tanh^2(gate)) * sum(G .* upd)
+// HBM-bound streaming pass (6 B read + 2 B written per element); one fp32 atomic per CTA for the scalar gradient.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ G, long long ldg,
+                                                       const __nv_bfloat16* __restrict__ upd, long long ldu,
+                                                       const float* __restrict__ gate, __nv_bfloat16* __restrict__ dupd,
+                                                       long long ldd, int rows, int cols, float* __restrict__ dgate) {
+  const float th = tanhf(*gate);
+  const int cp = cols >> 1;  // column pairs (cols is even)
+  const long long total = (long long)rows * cp;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cp;
+    const int c = (int)(i - r * cp) * 2;
+    const float2 gv = *reinterpret_cast<const float2*>(G + r * ldg + c);
+    const float2 uv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(upd + r * ldu + c));
+    acc = fmaf(gv.x, uv.x, fmaf(gv.y, uv.y, acc));
+    *reinterpret_cast<__nv_bfloat162*>(dupd + r * ldd + c) = __floats2bfloat162_rn(th * gv.x, th * gv.y);
+  }
+  if (dgate == nullptr) return;
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    acc = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffu, acc, o);
+    if (threadIdx.x == 0) atomicAdd(dgate, (1.f - th * th) * acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // decoder embedding backward: d_tok[ids[r], :] += g[r, :], d_pos[past + r % S, :] += g[r, :]   (fp32 atomics)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const float* __restrict__ g, const long long* __restrict__ ids,
@@ -922,6 +957,23 @@ extern "C" int dicow_dgelu_mul(dicow_handle_t h, const void* g, int g_is_bf16, i
     dgelu_mul_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g), ldg,
                                                       reinterpret_cast<const __nv_bfloat16*>(pre_bf16), ldp,
                                                       reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, rows, cols);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_gate_bwd(dicow_handle_t h, const float* g, int64_t ldg, const void* upd_bf16, int64_t ldu, const float* gate,
+                              void* dupd_bf16, int64_t ldd, int rows, int cols, float* dgate, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, g && upd_bf16 && gate && dupd_bf16 && rows >= 1 && cols >= 2 && (cols % 2) == 0 && (ldg % 2) == 0 &&
+                         (ldu % 2) == 0 && (ldd % 2) == 0,
+                "dicow_gate_bwd: bad args (cols and leading dimensions must be even)");
+  const long long total = (long long)rows * (cols / 2);
+  const long long want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);  // 8 resident CTAs of 256 threads per SM
+  gate_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      g, ldg, reinterpret_cast<const __nv_bfloat16*>(upd_bf16), ldu, gate, reinterpret_cast<__nv_bfloat16*>(dupd_bf16), ldd,
+      rows, cols, dgate);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

@@ -227,6 +227,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_conv1d_col2im.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, vp]
     lib.dicow_ctc_loss_bwd.argtypes = [vp, C.POINTER(CtcBwdArgs), vp]
     lib.dicow_dgelu_mul.argtypes = [vp, vp, C.c_int, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, vp]
+    lib.dicow_gate_bwd.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
     lib.dicow_cast_f32_bf16_2d.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_embedding_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.dicow_softlabel_ce_bwd.argtypes = [vp, C.POINTER(SoftlabelCeBwdArgs), vp]
@@ -251,7 +252,7 @@ EXPORTED_SYMBOLS = [
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
-    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d",
+    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd",
 ]
 
 

@@ -393,10 +393,13 @@ class DiCoWEncoder(nn.Module):
         if return_logits and input_features.is_cuda:
             from . import training
             if training.trainable(self):
-                if enrollments is not None or output_attentions or output_hidden_states or head_mask is not None:
-                    raise NotImplementedError("training forward: enrollments / attention outputs are not built yet")
+                if output_attentions or output_hidden_states or head_mask is not None:
+                    raise NotImplementedError("output_attentions / output_hidden_states / head_mask are not produced by "
+                                              "the fused B200 path")
                 params = [p for p in self.parameters() if p.requires_grad]
-                logits, hidden = training.EncoderLogitsFn.apply(self, input_features, stno_mask, *params)
+                enr = enrollments or {}
+                logits, hidden = training.EncoderLogitsFn.apply(self, input_features, stno_mask, enr.get("input_features"),
+                                                                enr.get("stno_mask"), *params)
                 return CausalLMOutput(loss=None, logits=logits, hidden_states=hidden)
         with torch.no_grad():
             return self._forward_inference(input_features, attention_mask, head_mask, output_attentions,

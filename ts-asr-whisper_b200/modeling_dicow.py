@@ -355,8 +355,6 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         if labels is not None and encoder_outputs is None and input_features is not None and input_features.is_cuda:
             from . import training
             if training.trainable(self):
-                if enrollments is not None:
-                    raise NotImplementedError("training with SE-DiCoW enrollment streams is not built yet (DESIGN.md)")
                 enc_model = self.model.get_encoder()
                 enc_labels = None
                 if cfg.ctc_weight > 0.0:
@@ -365,8 +363,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                         raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
                     enc_labels = enc_model.ctc_label_filter(enc_labels)
                 params = [p for p in self.parameters() if p.requires_grad]
+                enr = enrollments or {}
                 loss, logits, enc = training.DiCoWTrainStepFn.apply(self, input_features, stno_mask, decoder_input_ids, labels,
-                                                                    upp_labels, enc_labels, *params)
+                                                                    upp_labels, enc_labels, enr.get("input_features"),
+                                                                    enr.get("stno_mask"), *params)
                 if return_dict is False:
                     return (loss, logits, enc)
                 return Seq2SeqLMOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc)

@@ -585,6 +585,23 @@ def dgelu_mul(g: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gate_bwd(g: torch.Tensor, upd: torch.Tensor, gate: torch.Tensor, dgate: Optional[torch.Tensor]) -> torch.Tensor:
+    """SE-DiCoW gate backward (dicow_gate_bwd): returns bf16 tanh(gate) * g and accumulates the scalar gate gradient
+    (1 - tanh^2) * sum(g * upd) into ``dgate`` (fp32 [1] or None).  g fp32 [rows, cols], upd bf16 [rows, cols]."""
+    global launch_count
+    dev = _require_cuda(g, upd, gate, dgate)
+    assert g.dim() == 2 and upd.shape == g.shape and g.stride(1) == 1 and upd.stride(1) == 1
+    assert g.dtype == torch.float32 and upd.dtype == torch.bfloat16 and gate.dtype == torch.float32
+    out = torch.empty(g.shape, dtype=torch.bfloat16, device=dev)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_gate_bwd(h, _ptr(g), g.stride(0), _ptr(upd), upd.stride(0), _ptr(gate), _ptr(out),
+                                                out.stride(0), g.shape[0], g.shape[1], _ptr(dgate), _stream(dev))
+    _lib.check(rc, h, "dicow_gate_bwd")
+    launch_count += 1
+    return out
+
+
 def embedding_bwd(g: torch.Tensor, ids: torch.Tensor, *, S: int, d_tok: Optional[torch.Tensor],
                   d_pos: Optional[torch.Tensor], past: int = 0) -> None:
     """d_tok[ids[r]] += g[r], d_pos[past + r % S] += g[r] (dicow_embedding_bwd); g fp32 [B * S, d] contiguous."""

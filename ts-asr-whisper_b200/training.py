@@ -20,7 +20,10 @@ Three bridges into autograd (all return gradients for exactly the parameters tha
   CtcLossFn         DiCoWEncoder.get_loss(logits, labels)                                     (src/models/dicow/encoder.py:108-135)
   DiCoWTrainStepFn  DiCoWForConditionalGeneration.forward(labels=...) -> loss                 (modeling_dicow.py:248-354)
 
-Not covered yet (raises): SE-DiCoW enrollment streams (SCB) in training mode.
+SE-DiCoW enrollment streams (src/models/dicow/layers.py:145-193) train through the same step: the training path keeps
+the target and enrollment streams STACKED ([targets ; enrollments] on the batch axis, instead of the reference's
+interleave -- no op on the path couples different batch entries other than the speaker communication block, which pairs
+row b with row B + b), so both halves are contiguous GEMM / attention operands and gradient views.
 """
 from __future__ import annotations
 
@@ -159,12 +162,45 @@ class EncoderTape:
         self.ctc: dict = {}
 
 
-def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional[torch.Tensor], tape: EncoderTape):
-    """DiCoWEncoder.forward (src/models/dicow/encoder.py:140-246) in training mode: same kernels as inference, keeping
-    the per-layer inputs the backward needs.  Returns (last_hidden fp32 [B, T, d], bf16 copy [B*T, d])."""
+def _scb_forward_train(enc, e: dict, x: torch.Tensor, xb: torch.Tensor, B: int, T: int) -> dict:
+    """SpeakerCommunicationBlock (src/models/dicow/layers.py:145-170) on the stacked streams: x fp32 [2B*T, d] (target rows
+    [:B*T] updated in place), xb its bf16 copy.  Returns the activations the backward needs."""
     cfg = enc.config
-    if cfg.use_enrollments:
-        raise NotImplementedError("training with SE-DiCoW enrollment streams is not built yet (DESIGN.md section 8)")
+    d, H, ffn = cfg.d_model, cfg.encoder_attention_heads, e["w1"].shape[0]
+    dev = x.device
+    BT = B * T
+    xq, xe = xb[:BT], xb[BT:]
+    q = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    kv = torch.empty(BT, 2 * d, dtype=torch.bfloat16, device=dev)
+    ops.gemm(xq, e["wq"], q, epilogue=ops.EPI_BIAS_BF16, bias=e["bq"])
+    ops.gemm(xe, e["wkv"], kv, epilogue=ops.EPI_BIAS_BF16, bias=e["bkv"])
+    ctx = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, H, T, dtype=torch.float32, device=dev)
+    ops.attention(q, kv, kv[:, d:], ctx, B=B, H=H, Tq=T, Tk=T, q_row_stride=d, q_batch_stride=T * d, kv_row_stride=2 * d,
+                  kv_batch_stride=T * 2 * d, o_row_stride=d, o_batch_stride=T * d, lse=lse)
+    ao = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    ops.gemm(ctx, e["wo"], ao, epilogue=ops.EPI_BIAS_BF16, bias=e["bo"])
+    hdn = torch.empty(BT, ffn, dtype=torch.bfloat16, device=dev)
+    pre = torch.empty(BT, ffn, dtype=torch.bfloat16, device=dev)
+    # ffn.0 over cat([attn_out, q_stream]) as a two-source contraction (no concat buffer)
+    ops.gemm(ao, e["w1"], hdn, epilogue=ops.EPI_GELU_SAVE_BF16, bias=e["b1"], Mb=BT, K=2 * d, lda=d, A2=xq, lda2=d, K1=d,
+             aux=pre)
+    xt = x[:BT]
+    ops.gemm(hdn, e["w2"], xt, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=xt, ldr=d, gate=e["gate"])
+    return {"xb": xb, "q": q, "kv": kv, "ctx": ctx, "lse": lse, "ao": ao, "pre": pre, "hdn": hdn}
+
+
+def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional[torch.Tensor], tape: EncoderTape,
+                          enrollments: Optional[dict] = None):
+    """DiCoWEncoder.forward (src/models/dicow/encoder.py:140-246) in training mode: same kernels as inference, keeping
+    the per-layer inputs the backward needs.  Returns (last_hidden fp32 [B, T, d], bf16 copy [B*T, d]).
+    With ``enrollments`` the first ``scb_layers`` layers run on the stacked [targets ; enrollments] streams."""
+    cfg = enc.config
+    n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers and enrollments is not None) else 0
+    if n_scb:  # encoder.py:152-154 (stacked instead of interleaved, see the module docstring)
+        input_features = torch.cat((input_features, enrollments["input_features"].to(input_features.device)), dim=0)
+        if stno_mask is not None:
+            stno_mask = torch.cat((stno_mask, enrollments["stno_mask"].to(stno_mask.device)), dim=0)
     w = enc.prepare()
     dev = input_features.device
     d, F = cfg.d_model, input_features.shape[-1]
@@ -197,13 +233,32 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
     ffn = cfg.encoder_ffn_dim
     H = cfg.encoder_attention_heads
     d1 = d2 = None
+    x = x.view(rows, d)
+    if n_scb > len(w["layers"]):
+        raise ValueError("scb_layers exceeds the number of encoder layers")
     for i, e in enumerate(w["layers"]):
         fd = w["fddt"][i] if (cfg.use_fddt and i < len(w["fddt"])) else None
         x_pre = x
         x = x_pre.clone()  # the stream before this layer's pending deltas / FDDT is an input of the backward
-        ln1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
-        ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None, fddt_b=fd[1] if fd else None,
-                           gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln1, delta1=d1, delta2=d2, store_x=True)
+        scb = None
+        rows_in, stno_in = rows, stno
+        if i < n_scb:  # encoder.py:205-213: FDDT, speaker communication block, (last SCB layer) drop the enrollment stream
+            xb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+                               fddt_b=fd[1] if fd else None, x_out_bf16=xb, delta1=d1, delta2=d2, store_x=True)
+            scb = _scb_forward_train(enc, w["scb"][i], x, xb, B // 2, T)
+            if i == n_scb - 1:
+                B //= 2
+                rows = B * T
+                x = x[:rows]
+                stno = stno[:B] if stno is not None else None
+            ln1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln1, store_x=False)
+        else:
+            ln1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+                               fddt_b=fd[1] if fd else None, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln1, delta1=d1,
+                               delta2=d2, store_x=True)
         qkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
         ops.gemm(ln1, e["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=e["bqkv"])
         ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
@@ -221,7 +276,8 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
         d2n = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
         ops.gemm(hdn, e["w2"], d2n, epilogue=ops.EPI_BIAS_BF16, bias=e["b2"])
         tape.layers.append({"x_pre": x_pre, "d1_in": d1, "d2_in": d2, "x_post": x, "ln1": ln1, "qkv": qkv, "ctx": ctx,
-                            "lse": lse, "d1": d1n, "ln2": ln2, "pre": pre, "hdn": hdn, "d2": d2n, "fd": fd})
+                            "lse": lse, "d1": d1n, "ln2": ln2, "pre": pre, "hdn": hdn, "d2": d2n, "fd": fd, "scb": scb,
+                            "B": B, "rows_in": rows_in, "stno_in": stno_in})
         d1, d2 = d1n, d2n
     out = torch.empty(B, T, d, dtype=torch.float32, device=dev)
     out_bf16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
@@ -370,6 +426,56 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
     return dh
 
 
+def _scb_backward(enc, g: _Grads, cae, e: dict, a: dict, Gs: torch.Tensor, B: int, T: int) -> None:
+    """Backward of _scb_forward_train.  Gs fp32 [2B*T, d]: on entry the gradient of the block's OUTPUT streams (targets
+    [:B*T], enrollments [B*T:]); on exit the gradient of its INPUT streams (the FDDT output), accumulated in place:
+      targets      += d(ffn.0)/d(q half of the concat) + dq Wq           enrollments += dkv Wkv
+    (the target rows pass straight through the residual, src/models/dicow/layers.py:168)."""
+    cfg = enc.config
+    d, H, ffn = cfg.d_model, cfg.encoder_attention_heads, e["w1"].shape[0]
+    dev = Gs.device
+    BT = B * T
+    Gt, Ge = Gs[:BT], Gs[BT:]
+    xq, xe = a["xb"][:BT], a["xb"][BT:]
+    lin1, lin2 = cae.ffn[0], cae.ffn[3]
+    # gate: out = q + tanh(gate) * upd, upd = ffn.3(hdn) recomputed (one GEMM) instead of stored
+    upd = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    ops.gemm(a["hdn"], e["w2"], upd, epilogue=ops.EPI_BIAS_BF16, bias=e["b2"])
+    gate = cae.cross_gate.gate
+    dupd = ops.gate_bwd(Gt, upd, e["gate"], g.get(gate).view(-1) if g.want(gate) else None)
+    del upd
+    dpre = _linear_backward(g, dupd, a["hdn"], e["w2"], lin2.weight, lin2.bias, dx_epilogue=ops.EPI_DGELU_BF16, aux=a["pre"])
+    # ffn.0 over the concat [attn_out | q stream]: dgrad per half (the q half goes straight into the fp32 stream
+    # gradient), wgrad per column half of the [ffn, 2d] weight
+    w1 = e["w1"]
+    dao = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    ops.gemm(dpre, w1[:, :d], dao, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T, K=ffn, N=d)
+    ops.gemm(dpre, w1[:, d:], Gt, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_W_T, K=ffn, N=d, splits=1)
+    if g.want(lin1.weight):
+        gw1 = g.get(lin1.weight)
+        for half, X in ((gw1[:, :d], a["ao"]), (gw1[:, d:], xq)):
+            ops.gemm(dpre, X, half, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, lda=dpre.stride(0), Mb=ffn,
+                     K=BT, N=d, ldo=2 * d)
+    if g.want(lin1.bias):
+        ops.colsum(dpre, g.get(lin1.bias))
+    del dpre
+    att = cae.cross_attn
+    dctx = _linear_backward(g, dao, a["ctx"], e["wo"], att.out_proj.weight, att.out_proj.bias)
+    dq = torch.empty(BT, d, dtype=torch.bfloat16, device=dev)
+    dkv = torch.empty(BT, 2 * d, dtype=torch.bfloat16, device=dev)
+    q, kv = a["q"], a["kv"]
+    ops.attention_bwd(q, kv, kv[:, d:], a["ctx"], dctx, a["lse"], dq, dkv, dkv[:, d:], B=B, H=H, Tq=T, Tk=T, q_row_stride=d,
+                      q_batch_stride=T * d, kv_row_stride=2 * d, kv_batch_stride=T * 2 * d, o_row_stride=d,
+                      o_batch_stride=T * d, dq_row_stride=d, dq_batch_stride=T * d, dkv_row_stride=2 * d,
+                      dkv_batch_stride=T * 2 * d)
+    sc = 64 ** -0.5  # folded into the prepared Wq / bq (modeling._prep_attention)
+    _linear_backward(g, dq, xq, e["wq"], att.q_proj.weight, att.q_proj.bias, scale=sc, dx_accum=Gt)
+    ops.gemm(dkv, e["wkv"], Ge, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_W_T, splits=1)
+    _linear_backward(g, dkv, xe, e["wkv"], att.k_proj.weight, None, need_dx=False, dy_cols=slice(0, d), w_rows=slice(0, d))
+    _linear_backward(g, dkv, xe, e["wkv"], att.v_proj.weight, att.v_proj.bias, need_dx=False, dy_cols=slice(d, 2 * d),
+                     w_rows=slice(d, 2 * d))
+
+
 def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderTape) -> None:
     """Backward of encoder_forward_train given dL/d(last_hidden_state) as bf16 [B*T, d]."""
     cfg = enc.config
@@ -384,10 +490,12 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
     ln = enc.layer_norm
     n_layers = len(w["layers"])
 
-    def group(i):  # one exchange bucket per layer: its own parameters, its FDDT tables (+ the final LayerNorm with the last)
-        ps = list(enc.layers[i].parameters())
+    def group(i):  # one exchange bucket per layer: its own parameters, its FDDT tables, its speaker communication block
+        ps = list(enc.layers[i].parameters())  # (+ the final LayerNorm with the last layer)
         if tape.layers[i]["fd"] is not None:
             ps += list(enc.fddts[i].parameters())
+        if tape.layers[i]["scb"] is not None:
+            ps += list(enc.ca_enrolls[i].parameters())
         return ps + ([ln.weight, ln.bias] if i == n_layers - 1 else [])
 
     flat = g.reserve(group(n_layers - 1)) if n_layers else g.reserve([ln.weight, ln.bias])
@@ -396,6 +504,8 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
                            dbeta=g.get(ln.bias) if g.want(ln.bias) else None)
     for i in range(n_layers - 1, -1, -1):
         e, s, lyr = w["layers"][i], tape.layers[i], enc.layers[i]
+        B = s["B"]  # streams in this layer's attention / MLP blocks (targets only after the last SCB layer)
+        rows = B * T
         if i != n_layers - 1:
             flat = g.reserve(group(i))
         # fc2 / fc1 (G is the gradient of x_post + d1 + d2, hence of d2 = fc2(...) as well)
@@ -427,13 +537,27 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
             if any_grad:
                 dfw = torch.zeros(4, d, dtype=torch.float32, device=dev)
                 dfb = torch.zeros(4, d, dtype=torch.float32, device=dev)
-        G = torch.empty(rows, d, dtype=torch.float32, device=dev)
-        Gb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
-        ops.layernorm_fddt_bwd(s["x_pre"], G, dy=dln1, g_in=G2, gamma=e["ln1_g"], delta1=s["d1_in"], delta2=s["d2_in"], T=T,
-                               stno=stno if fd is not None else None, fddt_w=fd[0] if fd is not None else None,
-                               fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb,
-                               dgamma=g.get(n1.weight) if g.want(n1.weight) else None,
-                               dbeta=g.get(n1.bias) if g.want(n1.bias) else None, dfddt_w=dfw, dfddt_b=dfb)
+        rows_in, stno = s["rows_in"], s["stno_in"]
+        dgam = g.get(n1.weight) if g.want(n1.weight) else None
+        dbet = g.get(n1.bias) if g.want(n1.bias) else None
+        G = torch.empty(rows_in, d, dtype=torch.float32, device=dev)
+        Gb = torch.empty(rows_in, d, dtype=torch.bfloat16, device=dev)
+        if s["scb"] is None:
+            ops.layernorm_fddt_bwd(s["x_pre"], G, dy=dln1, g_in=G2, gamma=e["ln1_g"], delta1=s["d1_in"], delta2=s["d2_in"],
+                                   T=T, stno=stno if fd is not None else None, fddt_w=fd[0] if fd is not None else None,
+                                   fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dgamma=dgam, dbeta=dbet,
+                                   dfddt_w=dfw, dfddt_b=dfb)
+        else:
+            # LayerNorm 1 alone -> gradient of the stream after the speaker communication block; enrollment rows that
+            # were dropped after this layer (encoder.py:210-213) carry no gradient from above
+            Gs = torch.empty(rows_in, d, dtype=torch.float32, device=dev)
+            if rows_in != rows:
+                Gs[rows:].zero_()
+            ops.layernorm_fddt_bwd(s["x_post"], Gs[:rows], dy=dln1, g_in=G2, gamma=e["ln1_g"], dgamma=dgam, dbeta=dbet)
+            _scb_backward(enc, g, enc.ca_enrolls[i].cae, w["scb"][i], s["scb"], Gs, rows_in // (2 * T), T)
+            ops.layernorm_fddt_bwd(s["x_pre"], G, g_in=Gs, delta1=s["d1_in"], delta2=s["d2_in"], T=T,
+                                   stno=stno if fd is not None else None, fddt_w=fd[0] if fd is not None else None,
+                                   fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dfddt_w=dfw, dfddt_b=dfb)
         if dfw is not None:
             _scatter_fddt_grads(g, enc.fddts[i], dfw, dfb)
         g.flush(flat)
@@ -665,12 +789,16 @@ def trainable(module: torch.nn.Module) -> bool:
     return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
 
 
-def _encoder_hidden(enc, input_features, stno_mask, tape: EncoderTape, body: bool):
+def _enrollments(enr_features, enr_stno) -> Optional[dict]:
+    return None if enr_features is None else {"input_features": enr_features, "stno_mask": enr_stno}
+
+
+def _encoder_hidden(enc, input_features, stno_mask, tape: EncoderTape, body: bool, enrollments: Optional[dict] = None):
     """(hidden fp32 [B, T, d], hidden bf16 [B*T, d], B, T); activations are saved only when the body trains."""
     if body:
-        hidden, hidden_bf16 = encoder_forward_train(enc, input_features, stno_mask, tape)
+        hidden, hidden_bf16 = encoder_forward_train(enc, input_features, stno_mask, tape, enrollments)
         return hidden, hidden_bf16, tape.final["B"], tape.final["T"]
-    out = enc(input_features, stno_mask=stno_mask)  # frozen body: the inference path, nothing saved
+    out = enc(input_features, stno_mask=stno_mask, enrollments=enrollments)  # frozen body: inference path, nothing saved
     hidden = out.last_hidden_state
     B, T = hidden.shape[0], hidden.shape[1]
     return hidden, ops.cast_bf16(hidden).view(B * T, -1), B, T
@@ -681,11 +809,12 @@ class EncoderLogitsFn(torch.autograd.Function):
     everything but the CTC head, src/utils/trainers.py:76-103 then calls model.get_loss on these logits)."""
 
     @staticmethod
-    def forward(ctx, enc, input_features, stno_mask, *params):
+    def forward(ctx, enc, input_features, stno_mask, enr_features, enr_stno, *params):
         tape = EncoderTape()
         body = _body_trainable(enc)
         with torch.no_grad():
-            hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, tape, body)
+            hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, tape, body,
+                                                        _enrollments(enr_features, enr_stno))
             logits = ctc_head_forward_train(enc, hidden_bf16, B, T, tape)
         ctx.enc, ctx.tape, ctx.body, ctx.params = enc, tape, body, params
         ctx.mark_non_differentiable(hidden)
@@ -702,7 +831,7 @@ class EncoderLogitsFn(torch.autograd.Function):
             if ctx.body:
                 encoder_backward(enc, g, dh, tape)
         ctx.tape = None
-        return (None, None, None) + g.finish(ctx.params)
+        return (None,) * 5 + g.finish(ctx.params)
 
 
 class CtcLossFn(torch.autograd.Function):
@@ -731,7 +860,8 @@ class DiCoWTrainStepFn(torch.autograd.Function):
     (1 - w) * soft-label CE of the teacher-forced decoder + w * CTC of the encoder head, with one hand-scheduled backward."""
 
     @staticmethod
-    def forward(ctx, model, input_features, stno_mask, decoder_input_ids, labels, upp_labels, enc_labels, *params):
+    def forward(ctx, model, input_features, stno_mask, decoder_input_ids, labels, upp_labels, enc_labels, enr_features,
+                enr_stno, *params):
         cfg = model.config
         enc = model.model.get_encoder()
         etape, dtape = EncoderTape(), DecoderTape()
@@ -739,7 +869,8 @@ class DiCoWTrainStepFn(torch.autograd.Function):
         body = _body_trainable(enc)
         dec_trainable = any(p.requires_grad for p in model.model.decoder.parameters())
         with torch.no_grad():
-            hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, etape, body)
+            hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, etape, body,
+                                                        _enrollments(enr_features, enr_stno))
             dev = hidden.device
             if body or dec_trainable:
                 hid, hid_bf16 = decoder_forward_train(model.model, decoder_input_ids, hidden_bf16, B, T, dtape)
@@ -801,4 +932,4 @@ class DiCoWTrainStepFn(torch.autograd.Function):
             if ctx.body:
                 encoder_backward(enc, g, ops.cast_bf16(d_enc), ctx.etape)
         ctx.etape = ctx.dtape = ctx.saved = None
-        return (None,) * 7 + g.finish(ctx.params)
+        return (None,) * 9 + g.finish(ctx.params)
