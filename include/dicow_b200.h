@@ -363,8 +363,42 @@ typedef struct {
 } dicow_gemm_skinny_args_t;
 DICOW_API int dicow_gemm_skinny_bf16(dicow_handle_t h, const dicow_gemm_skinny_args_t* args, void* stream);
 
+/* [LayerNorm ->] Linear of one decode step in ONE kernel (M <= 64 rows):
+ *   A = x != NULL ? LayerNorm(x) * gamma + beta  (fp32 rows, two-pass statistics, K <= 1280; HF:modeling_whisper.py:471,
+ *       483,498 + 779) : A (bf16);   out[m, n] = epilogue(sum_k A[m, k] W[n, k] + bias[n])   (epilogues as above).
+ * Columns n >= n_split go to out2[m * ldo2 + (n - n_split)] when out2 != NULL (fused q | k,v projection:
+ * HF:modeling_whisper.py:310,331-332); `pos` advances the base of out2 (of out when out2 == NULL) by *pos * pos_stride
+ * elements (KV-cache append).  The kernel is launched with programmatic stream serialisation: it requests its weight
+ * slab before waiting for the previous kernel of the step.  K may be any multiple of 32 that splits into <= 8 slices of
+ * <= 1280 (multiples of 32); small-N layers split K over a thread-block cluster (deterministic DSMEM reduction). */
+typedef struct {
+  size_t struct_size;
+  const float* x; /* LayerNorm source [M, K] fp32, or NULL */
+  int64_t ldx;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const void* A; /* bf16 [M, K] when x == NULL */
+  int64_t lda;
+  const void* W; /* bf16 [N, K] */
+  int64_t ldw;
+  int32_t M, N, K;
+  const float* bias;
+  void* out;
+  int64_t ldo;
+  int32_t epilogue;
+  const float* resid;
+  int64_t ldr;
+  int32_t n_split;
+  void* out2;
+  int64_t ldo2;
+  const int32_t* pos;
+  int64_t pos_stride;
+} dicow_decode_linear_args_t;
+DICOW_API int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_args_t* args, void* stream);
+
 /* one query row per (batch, head), head_dim 64: out[b, h*64:] = softmax(q . K^T) V over Tk keys (Tk = *pos + 1 if pos).
- * Q/out bf16 [B, H*64]; K/V bf16 rows at K + b*kv_batch_stride + k*kv_row_stride + h*64. */
+ * Q/out bf16 [B, H*64]; K/V bf16 rows at K + b*kv_batch_stride + h*kv_head_stride + k*kv_row_stride. */
 typedef struct {
   size_t struct_size;
   const void* Q;
@@ -376,8 +410,14 @@ typedef struct {
   int64_t o_batch_stride;
   int32_t B, H, Tk;
   const int32_t* pos;
+  int64_t kv_head_stride; /* elements between heads; 0 = 64 (heads adjacent inside a row) */
 } dicow_decode_attention_args_t;
 DICOW_API int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_attention_args_t* args, void* stream);
+
+/* cross-attention K/V of one window, [B*T, (k | v) x H x 64] bf16 as the projection GEMM writes it -> [B, H, T, 128]
+ * (k | v of one key adjacent): decode_attention then reads one contiguous T x 256 B stream per (batch, head) with
+ * kv_row_stride = 128, kv_head_stride = T * 128, kv_batch_stride = H * T * 128, V = K + 64. */
+DICOW_API int dicow_kv_to_head_major(dicow_handle_t h, const void* kv_bf16, void* out_bf16, int B, int T, int H, void* stream);
 
 /* x[b, s, :] = embed_tokens[ids[b, p + s]] + embed_positions[p + s], p = pos ? *pos : past   (fp32 tables, fp32 out)
  * HF:modeling_whisper.py:741-760 */

@@ -17,7 +17,80 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--no-graphs", action="store_true")
+ap.add_argument("--unfused", action="store_true", help="one kernel per operation (the pre-fusion decode step)")
+ap.add_argument("--ln-prologue", action="store_true", help="LayerNorm as the prologue of the linear kernel")
+ap.add_argument("--workload", default="decoder", choices=["decoder", "se_dicow"],
+                help="decoder: token steps on synthetic encoder states; se_dicow: BASELINE configs[3] end to end "
+                     "(SE-DiCoW encoder with enrollment streams + 8 SCB layers, then the greedy loop)")
 args = ap.parse_args()
+
+
+def se_dicow_e2e():
+    """BASELINE configs[3]: SE-DiCoW (FDDT + enrollment cross-attention) greedy decode, batch = 16 windows, 1 x B200.
+    One pass = DiCoWEncoder.forward over 16 target + 16 enrollment windows (interleaved, 8 speaker communication
+    blocks) + cross-K/V projection + prompt + `steps` greedy tokens per window (EOS suppressed so every run decodes the
+    same number of tokens).  CUDA events around the whole pass, inputs resident, 3 batches rotate."""
+    dev = torch.device("cuda:0")
+    cfg = turbo_config()
+    cfg.use_enrollments, cfg.scb_layers = True, 8
+    cfg.pad_token_id = cfg.eos_token_id = 50257
+    with torch.device(dev):
+        model = DiCoWForConditionalGeneration(cfg)
+    from bench import make_inputs, perturb_
+    perturb_(model.get_encoder(), dev)
+    with torch.no_grad():
+        for blk in model.get_encoder().ca_enrolls:
+            blk.cae.cross_gate.gate.fill_(0.5)
+    model.eval()
+    model.use_cuda_graphs = not args.no_graphs
+    model.fused_decode_step = False if args.unfused else ("ln_prologue" if args.ln_prologue else True)
+    B = args.batch
+    batches = []
+    for i in range(3):
+        f, s = make_inputs(2 * B, 20 + i, device=dev)
+        batches.append((f[:B], s[:B], {"input_features": f[B:], "stno_mask": s[B:]}))
+    prompt = torch.tensor([[50258, 50259, 50360]] * B, device=dev)
+    rules = dict(eos=50257, pad=50257, no_timestamps=50364, ts_begin=50365, max_initial_timestamp_index=None,
+                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap([50257, 220, 50256], dev))
+    n = 3 + args.steps
+    enc = model.get_encoder()
+
+    def one(i):
+        f, s, e = batches[i % 3]
+        hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
+        return model.greedy_decode_window(hidden, prompt, n, rules)
+
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps = 5
+    l0 = ops.launch_count
+    t_enc = t_all = 0.0
+    for i in range(reps):
+        f, s, e = batches[i % 3]
+        ev[0].record()
+        hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
+        ev[1].record()
+        ids = model.greedy_decode_window(hidden, prompt, n, rules)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_enc += ev[0].elapsed_time(ev[1])
+        t_all += ev[0].elapsed_time(ev[2])
+    ms_all, ms_enc = t_all / reps, t_enc / reps
+    gflop_enc = 3577.0  # SURVEY section 8d: SE-DiCoW encoder forward per target utterance
+    print(json.dumps({"metric": "SE-DiCoW greedy decode (BASELINE configs[3]), large-v3-turbo + FDDT + 8 SCB layers",
+                      "batch": B, "new_tokens_per_window": args.steps, "ms_per_batch": ms_all, "ms_encoder": ms_enc,
+                      "ms_decode": ms_all - ms_enc, "utt_per_s": B / (ms_all * 1e-3),
+                      "tokens_per_s": B * args.steps / (ms_all * 1e-3),
+                      "encoder_tflops": B * gflop_enc / ms_enc, "cuda_graphs": model.use_cuda_graphs,
+                      "gpu_launches_per_batch": (ops.launch_count - l0) // reps, "data": "synthetic",
+                      "generated_tail": ids[0, -4:].tolist()}))
+
+
+if args.workload == "se_dicow":
+    se_dicow_e2e()
+    sys.exit(0)
 dev = torch.device("cuda:0")
 cfg = turbo_config()
 cfg.encoder_layers = 1  # the encoder is not what is measured here; hidden states are synthetic
@@ -26,6 +99,7 @@ with torch.device(dev):
     model = DiCoWForConditionalGeneration(cfg)
 model.eval()
 model.use_cuda_graphs = not args.no_graphs
+model.fused_decode_step = False if args.unfused else ("ln_prologue" if args.ln_prologue else True)
 B, T, d = args.batch, 1500, cfg.d_model
 enc = (torch.randn(B, T, d, device=dev) * 0.5).bfloat16()
 prompt = torch.tensor([[50258, 50259, 50360]] * B, device=dev)
@@ -54,6 +128,7 @@ step_ms = ms / (args.steps + 2)
 floor_ms = (wbytes + kvbytes) / (hbm * 1e9) * 1e3
 print(json.dumps({"metric": "greedy decode, turbo decoder", "batch": B, "steps": args.steps, "ms_total": ms,
                   "ms_per_step": step_ms, "tokens_per_s": B * args.steps / (ms * 1e-3), "cuda_graphs": model.use_cuda_graphs,
+                  "fused_step": model.fused_decode_step, "pdl": os.environ.get("DICOW_PDL", "0") == "1",
                   "bytes_per_step": wbytes + kvbytes, "hbm_floor_ms": floor_ms, "frac_of_hbm_roofline": floor_ms / step_ms,
                   "achieved_gbs": (wbytes + kvbytes) / (step_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
                   "note": "includes the per-window cross-K/V projection (4 GEMMs) and 2 prompt steps",

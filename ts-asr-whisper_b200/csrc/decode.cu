@@ -15,6 +15,7 @@
 // DiCoWGenerationMixin._sample (src/models/dicow/generation.py:707-782) with its logits processors
 // (HF:generation/logits_process.py:1905-2043; src/models/dicow/utils.py:5-14).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -59,6 +60,63 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p) {  // weights: re
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
+}
+
+// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, calls griddep_launch() early (the next kernel of the step may be
+// scheduled as soon as every CTA of this one has got here) and griddep_wait() before it touches anything an earlier
+// kernel of the step wrote.  What a kernel does before the wait -- index arithmetic and, for the linear layers, issuing
+// the loads of its (immutable) weight slab -- overlaps the tail of its predecessor, which is most of the per-kernel cost
+// of a step whose kernels each move a few MB.  Both instructions are no-ops for a launch without the attribute.
+// A kernel launched this way can be resident while its predecessors still run, so everything the step's kernels
+// exchange (x, q, ctx, h, the K/V cache, logits, ids, pos, unfinished) is read with ld.global.cg (L2 only): an L1 line
+// filled before the producer's store would otherwise be a stale hit.  Weights, biases and tables are immutable (nc).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, uint2 v) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_all() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_all() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+// Measured (tools/profile_decode.py, B = 16 turbo decoder, CUDA graph): with the attribute the kernels of a step do
+// overlap (485 us of overlap per 520 us step) but the step is no shorter (0.51-0.54 ms vs 0.49-0.53 ms without): the
+// step is bound by the kernels' own latency chains, not by launch gaps (idle gaps 9-12 us per step either way).  The
+// attribute is therefore OFF unless DICOW_PDL=1; the griddepcontrol instructions are no-ops then.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DICOW_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster_x, attrs[n].val.clusterDim.y = 1, attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs, cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // One CTA = 8 output columns; its 8 warps split K in 32-element blocks (warp w takes blocks w, w + 8, ...).  Lane
@@ -124,16 +182,248 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkinnyPar
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// decode_linear: [LayerNorm ->] Linear for the M <= 64 rows of one decode step, with everything around the weight
+// stream folded in (one kernel instead of LayerNorm + 1..2 skinny GEMMs):
+//   * the CTA's first weight slab is requested BEFORE griddep_wait(): weights do not depend on the previous kernel, so
+//     their HBM latency overlaps its tail;
+//   * the A operand is staged once per CTA in shared memory as bf16 -- either LayerNorm(x) computed in the prologue from
+//     the fp32 residual stream (two-pass statistics, one warp per row: the arithmetic of fddt_ln_kernel), or a copy of
+//     a bf16 activation -- with a row pitch = 64 (mod 128) bytes so that the fragment loads are bank-conflict free;
+//   * a CTA owns `tiles_per_cta` consecutive 8-column tiles (large N: proj_out has 6 484) and prefetches the next
+//     tile's weights into registers while the current one is multiplied, so A is staged ~600 times per step, not 6 484;
+//   * small-N / large-K layers (out_proj, fc2) split K over a thread-block cluster of `ksplit` CTAs; partial sums
+//     meet in rank 0's shared memory (DSMEM) and are added in rank order (deterministic, no atomics);
+//   * columns >= n_split go to a second output (fused q | k,v projection: q to its buffer, k,v appended to the cache).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DL_WARPS = 8;
+constexpr int DL_THREADS = DL_WARPS * 32;
+constexpr int DL_KBW = 5;         // 32-wide k-blocks per warp: K / ksplit <= DL_WARPS * DL_KBW * 32 = 1280
+constexpr int DL_MAX_KSPLIT = 8;  // portable cluster size
+constexpr int DL_LN_CLUSTER = 8;  // CTAs sharing one LayerNorm of the M rows (LN variant)
+
+struct DecLinParams {
+  const float* x;  // LayerNorm source [M, K] fp32 (LN variant)
+  long long ldx;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const __nv_bfloat16* A;  // bf16 source [M, K] (plain variant)
+  long long lda;
+  const __nv_bfloat16* W;
+  long long ldw;
+  int M, N, K;
+  const float* bias;
+  void* out;
+  long long ldo;
+  int epilogue;
+  const float* resid;
+  long long ldr;
+  int n_split;  // columns >= n_split go to out2 (n_split = N: single output)
+  void* out2;
+  long long ldo2;
+  const int* pos;  // out2 base advanced by *pos * pos_stride elements (KV-cache append); applies to out when out2 == NULL
+  long long pos_stride;
+  int ksplit, tiles_per_cta, Ks, a_pitch;  // Ks = K / ksplit; a_pitch = shared-memory row pitch of A in elements
+};
+
+__device__ __forceinline__ void dl_store(const DecLinParams& p, int row, int n, float v) {
+  if (row >= p.M || n >= p.N) return;
+  if (p.bias != nullptr) v += __ldg(p.bias + n);
+  void* dst = p.out;
+  long long o = (long long)row * p.ldo + n;
+  if (p.out2 != nullptr && n >= p.n_split) {
+    dst = p.out2;
+    o = (long long)row * p.ldo2 + (n - p.n_split);
+    if (p.pos != nullptr) o += (long long)__ldcg(p.pos) * p.pos_stride;
+  } else if (p.out2 == nullptr && p.pos != nullptr) {
+    o += (long long)__ldcg(p.pos) * p.pos_stride;
+  }
+  switch (p.epilogue) {
+    case DICOW_EPI_BIAS_BF16: reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v); break;
+    case DICOW_EPI_BIAS_GELU_BF16: reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(gelu_erf_fast(v)); break;
+    case DICOW_EPI_RESIDUAL_F32: reinterpret_cast<float*>(dst)[o] = __ldcg(p.resid + (long long)row * p.ldr + n) + v; break;
+    default: reinterpret_cast<float*>(dst)[o] = v; break;
+  }
+}
+
+template <int MT, bool LN>
+__global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinParams p) {
+  extern __shared__ __align__(16) unsigned char dl_smem[];
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(dl_smem);
+  float* red = reinterpret_cast<float*>(dl_smem + (size_t)MT * 16 * p.a_pitch * sizeof(__nv_bfloat16));
+  float* cpart = red + DL_WARPS * MT * 16 * 8;  // [ksplit - 1][MT * 16 * 8], used on cluster rank 0
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int krank = p.ksplit > 1 ? (int)cluster_ctarank() : 0;
+  const int ntiles = (p.N + 7) >> 3;
+  const int tile_first = ((int)blockIdx.x / p.ksplit) * p.tiles_per_cta;
+  const int tile_end = min(tile_first + p.tiles_per_cta, ntiles);
+  const int kblocks = p.Ks >> 5;
+  const int kbase = krank * p.Ks;
+
+  // cluster launches (LayerNorm sharing, split K) write into peer CTAs' shared memory: arrive now, wait right before the
+  // first remote store, so that "the peer has started" costs no latency
+  if (LN || p.ksplit > 1) cluster_arrive_all();
+  uint4 wv[DL_KBW], wn[DL_KBW];
+  auto load_w = [&](int tile, uint4(&w)[DL_KBW]) {
+    const int nrow = tile * 8 + g;
+    const bool ok = tile < tile_end && nrow < p.N;
+    const __nv_bfloat16* wrow = p.W + (long long)(ok ? nrow : 0) * p.ldw + kbase + t * 8;
+#pragma unroll
+    for (int i = 0; i < DL_KBW; ++i) {
+      const int kb = warp + i * DL_WARPS;
+      w[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok && kb < kblocks) w[i] = ldg_stream_128(wrow + kb * 32);
+    }
+  };
+  load_w(tile_first, wv);  // in flight across the dependency wait
+  griddep_launch();
+  griddep_wait();
+
+  // ---- stage A (bf16) in shared memory: rows >= M are zero ----
+  if constexpr (LN) {
+    // The LayerNorm of the M rows is shared by a cluster of DL_LN_CLUSTER CTAs (each needs ALL of A for its columns):
+    // rank r normalises rows [r * RPR, (r + 1) * RPR) -- one warp per row, two-pass statistics in registers -- and
+    // stores the bf16 row into the A slab of every CTA of the cluster through distributed shared memory.  Every CTA
+    // re-reading and re-normalising all rows instead costs 8x the L2 requests on the same 80 KB (measured: 14 us per
+    // layer instead of ~6 for the plain variant).
+    constexpr int RPR = MT * 16 / DL_LN_CLUSTER;  // rows per rank
+    const int crank = (int)cluster_ctarank();
+    const int nvec = p.K >> 2;  // K <= 1280: at most 10 float4 per lane
+    for (int r = p.M + warp; r < MT * 16; r += DL_WARPS) {  // local zero rows (disjoint from what the peers write)
+      __nv_bfloat16* srow = sA + (size_t)r * p.a_pitch;
+      for (int c = lane * 4; c < p.Ks; c += 128) *reinterpret_cast<uint2*>(srow + c) = make_uint2(0u, 0u);
+    }
+    const int r = crank * RPR + warp;
+    const bool mine = warp < RPR && r < p.M;
+    uint2 y[10];
+    if (mine) {
+      const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)r * p.ldx);
+      float4 v[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < nvec ? __ldcg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) / (float)p.K;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        if (lane + 32 * i < nvec) {
+          const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+          q += (a * a + b2 * b2) + (c * c + e * e);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)p.K + p.eps);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int c4 = lane + 32 * i;
+        y[i] = make_uint2(0u, 0u);
+        if (c4 < nvec) {
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+          const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+          const float y0 = fmaf((v[i].x - mean) * rstd, ga.x, be.x), y1 = fmaf((v[i].y - mean) * rstd, ga.y, be.y);
+          const float y2 = fmaf((v[i].z - mean) * rstd, ga.z, be.z), y3 = fmaf((v[i].w - mean) * rstd, ga.w, be.w);
+          y[i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+        }
+      }
+    }
+    cluster_wait_all();  // every CTA of the cluster is running (arrival at kernel entry): its A slab may be written
+    if (mine) {
+      const uint32_t row_local = smem_u32(sA + (size_t)r * p.a_pitch);
+      for (int dst = 0; dst < DL_LN_CLUSTER; ++dst) {
+        const uint32_t row_remote = map_to_cta(row_local, (uint32_t)dst);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int c4 = lane + 32 * i;
+          if (c4 < nvec) st_cluster_v2(row_remote + (uint32_t)c4 * 8u, y[i]);
+        }
+      }
+    }
+    cluster_sync_all();  // release / acquire: the rows written by the peers are visible
+  } else {
+    const int vec_per_row = p.Ks >> 3;
+    for (int i = threadIdx.x; i < MT * 16 * vec_per_row; i += DL_THREADS) {
+      const int r = i / vec_per_row, c = (i - r * vec_per_row) * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(p.A + (long long)r * p.lda + kbase + c));
+      *reinterpret_cast<uint4*>(sA + (size_t)r * p.a_pitch + c) = v;
+    }
+  }
+  __syncthreads();
+  if (!LN && p.ksplit > 1) cluster_wait_all();
+
+  for (int tile = tile_first; tile < tile_end; ++tile) {
+    load_w(tile + 1, wn);  // next tile's weights stream in while this one is multiplied (zeros past the last tile)
+    float acc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DL_KBW; ++i) {
+      const int kb = warp + i * DL_WARPS;
+      if (kb < kblocks) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const __nv_bfloat16* a0 = sA + (size_t)(m * 16 + g) * p.a_pitch + kb * 32 + t * 8;
+          const uint4 lo = *reinterpret_cast<const uint4*>(a0);
+          const uint4 hi = *reinterpret_cast<const uint4*>(a0 + 8 * (size_t)p.a_pitch);
+          mma_bf16_16816(acc[m], lo.x, hi.x, lo.y, hi.y, wv[i].x, wv[i].y);
+          mma_bf16_16816(acc[m], lo.z, hi.z, lo.w, hi.w, wv[i].z, wv[i].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float* r0 = red + ((size_t)warp * MT * 16 + m * 16 + g) * 8 + 2 * t;
+      r0[0] = acc[m][0], r0[1] = acc[m][1];
+      r0[64] = acc[m][2], r0[65] = acc[m][3];  // row g + 8
+    }
+    __syncthreads();
+    // cross-warp sums; with split K the partial sums of ranks 1.. meet in rank 0's shared memory and are added in rank order
+    float v[(MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS];
+#pragma unroll
+    for (int j = 0; j < (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS; ++j) {
+      const int e = threadIdx.x + j * DL_THREADS;
+      v[j] = 0.f;
+      if (e < MT * 16 * 8) {
+#pragma unroll
+        for (int w = 0; w < DL_WARPS; ++w) v[j] += red[(size_t)w * MT * 16 * 8 + e];
+        if (krank != 0) st_cluster_f32(map_to_cta(smem_u32(cpart + (size_t)(krank - 1) * MT * 16 * 8 + e), 0), v[j]);
+      }
+    }
+    if (p.ksplit > 1) cluster_sync_all();
+    if (krank == 0) {
+#pragma unroll
+      for (int j = 0; j < (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS; ++j) {
+        const int e = threadIdx.x + j * DL_THREADS;
+        if (e < MT * 16 * 8) {
+          for (int r = 1; r < p.ksplit; ++r) v[j] += cpart[(size_t)(r - 1) * MT * 16 * 8 + e];
+          dl_store(p, e >> 3, tile * 8 + (e & 7), v[j]);
+        }
+      }
+    }
+    __syncthreads();  // red is rewritten by the next tile
+#pragma unroll
+    for (int k = 0; k < DL_KBW; ++k) wv[k] = wn[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // decode attention: softmax(q . K^T) V for one query row per (batch, head), head_dim 64
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int DA_WARPS = 4;
+// DA_WARPS warps per (batch, head): 4 for the short self-attention cache, 8 for the 1500-key cross attention.  The kernel
+// is a pure K/V stream bound by the loads in flight per SM: B x H = 320 CTAs must be ONE wave (16 warps at 72 registers
+// fit one CTA per SM -> 2.2 waves, measured 42 us against 36 us with 4 warps; 8 warps fit three per SM)
 
 struct DecAttnParams {
   const __nv_bfloat16* Q;
   long long q_bs;
   const __nv_bfloat16* K;
   const __nv_bfloat16* V;
-  long long kv_rs, kv_bs;
+  long long kv_rs, kv_bs, kv_hs;
   __nv_bfloat16* out;
   long long o_bs;
   int Tk;
@@ -152,16 +442,19 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // grid (H, B), 4 warps.  A group of 8 lanes owns one key at a time (16 B = 8 dims per lane, so every K / V row is
 // read as one full 128-byte line); each group keeps an online-softmax state (m, l, o[8 dims per lane]); groups and
 // warps are merged at the end.
+template <int DA_WARPS>
 __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const DecAttnParams p) {
   __shared__ float sm_m[DA_WARPS], sm_l[DA_WARPS], sm_o[DA_WARPS][64];
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
-  const int Tk = p.pos != nullptr ? (*p.pos + 1) : p.Tk;
+  griddep_launch();
+  griddep_wait();
+  const int Tk = p.pos != nullptr ? (__ldcg(p.pos) + 1) : p.Tk;
   float q[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(p.Q + (long long)b * p.q_bs + h * 64 + sub * 8)), q);
-  const __nv_bfloat16* kb = p.K + (long long)b * p.kv_bs + h * 64 + sub * 8;
-  const __nv_bfloat16* vb = p.V + (long long)b * p.kv_bs + h * 64 + sub * 8;
+  unpack8(__ldcg(reinterpret_cast<const uint4*>(p.Q + (long long)b * p.q_bs + h * 64 + sub * 8)), q);
+  const __nv_bfloat16* kb = p.K + (long long)b * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
+  const __nv_bfloat16* vb = p.V + (long long)b * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -174,8 +467,8 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
     for (int u = 0; u < UNROLL; ++u) {
       const int k = k0 + u * stride;
       if (k < Tk) {
-        kv[u] = ldg_stream_128(kb + (long long)k * p.kv_rs);
-        vv[u] = ldg_stream_128(vb + (long long)k * p.kv_rs);
+        kv[u] = __ldcg(reinterpret_cast<const uint4*>(kb + (long long)k * p.kv_rs));  // L2 only: the newest row was
+        vv[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (long long)k * p.kv_rs));  // written by the previous kernel
       }
     }
 #pragma unroll
@@ -243,14 +536,33 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// cross-attention K/V re-layout, once per 30 s window: [B*T, (k | v) x H x 64] (the projection GEMM's output) ->
+// [B, H, T, 128] with k | v of one key adjacent.  A decode step then streams, per (batch, head), ONE contiguous
+// T x 256 B region instead of 2 x T 128-byte pieces 5 KB apart (measured: 3.0 -> see DESIGN.md TB/s in decode_attention).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) kv_to_head_major_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T,
+                                                               int H) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int per_half = H * 8;  // 16-byte vectors per k (or v) row
+  const uint4* src = in + ((long long)b * T + t) * (2 * per_half);
+  for (int i = threadIdx.x; i < 2 * per_half; i += blockDim.x) {
+    const int half = i / per_half, rem = i - half * per_half;
+    const int head = rem >> 3, j = rem & 7;
+    out[(((long long)b * H + head) * T + t) * 16 + half * 8 + j] = __ldg(src + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // x[b, s, :] = embed_tokens[ids[b, past + s], :] + embed_positions[past + s, :]      (fp32)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const long long* __restrict__ ids, long long ids_rs, const float* __restrict__ tok,
                              const float* __restrict__ posw, float* __restrict__ x, int S, int d, int past,
                              const int* pos, int vocab) {
   const int s = blockIdx.x, b = blockIdx.y;
-  const int pp = (pos != nullptr ? *pos : past) + s;
-  long long id = ids[(long long)b * ids_rs + pp];
+  griddep_launch();
+  griddep_wait();
+  const int pp = (pos != nullptr ? __ldcg(pos) : past) + s;
+  long long id = __ldcg(ids + (long long)b * ids_rs + pp);
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
   const float4* tr = reinterpret_cast<const float4*>(tok + id * d);
   const float4* pr = reinterpret_cast<const float4*>(posw + (long long)pp * d);
@@ -261,7 +573,11 @@ __global__ void embed_kernel(const long long* __restrict__ ids, long long ids_rs
   }
 }
 
-__global__ void advance_kernel(int* pos, int by) { *pos += by; }
+__global__ void advance_kernel(int* pos, int by) {
+  griddep_launch();
+  griddep_wait();
+  *pos = __ldcg(pos) + by;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // logits rules + argmax
@@ -299,31 +615,47 @@ __device__ __forceinline__ Best warp_best(Best x) {
   return x;
 }
 
-// One CTA per batch row.  Restates, in one pass over the row:
+// One CTA -- or a cluster of `csplit` CTAs, each scanning a slice of the vocabulary -- per batch row.  Restates, in one
+// pass over the row:
 //   SuppressTokensLogitsProcessor -> scores[suppress] = -inf
 //   WhisperTimeStampLogitsProcessor (HF:generation/logits_process.py:1996-2043): no_timestamps = -inf; timestamps come
 //   in pairs; no decreasing timestamps; first token must be a timestamp; "if the probability mass over timestamps
 //   exceeds the most likely text token, sample a timestamp"
 //   DiCoW: the EOS score survives at the first generated position (src/models/dicow/utils.py:10-12)
 //   argmax (lowest index on ties), finished rows emit pad, unfinished &= token != eos (generation.py:756-779)
-__global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesParams p) {
+// With a cluster the per-slice results (best text token, best timestamp token, online logsumexp of the timestamp region)
+// are written to rank 0's shared memory (DSMEM) and merged there in rank order.
+struct RulesPartial {
+  float text_v;
+  int text_i;
+  float ts_v;
+  int ts_i;
+  float tmax, tsum;
+};
+
+__global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesParams p, const int csplit) {
   __shared__ float s_max[16], s_sum[16];
   __shared__ Best s_text[16], s_ts[16];
-  const int b = blockIdx.x;
+  __shared__ RulesPartial s_part[8];  // slices of cluster ranks 1..7 (on rank 0)
+  __shared__ int s_text_off;
+  const int b = (int)blockIdx.x / csplit;
+  const int rank = csplit > 1 ? (int)cluster_ctarank() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  const int len = p.pos != nullptr ? (*p.pos + 1) : p.cur_len;  // tokens in the sequence so far
+  griddep_launch();
+  griddep_wait();
+  const int len = p.pos != nullptr ? (__ldcg(p.pos) + 1) : p.cur_len;  // tokens in the sequence so far
   long long* row_ids = p.ids + (long long)b * p.ids_rs;
   const int ngen = len - p.begin_index;
   const bool rules = p.ts_rules != 0;
   const bool at_begin = rules && ngen == 0;
-  const long long last = ngen >= 1 ? row_ids[len - 1] : -1;
-  const long long penult = ngen >= 2 ? row_ids[len - 2] : -1;
+  const long long last = ngen >= 1 ? __ldcg(row_ids + len - 1) : -1;
+  const long long penult = ngen >= 2 ? __ldcg(row_ids + len - 2) : -1;
   const bool last_was_ts = rules && ngen >= 1 && last >= p.ts_begin;
   const bool penult_was_ts = ngen < 2 || penult >= p.ts_begin;
   // last timestamp token of the generated part (timestamps never decrease, so it is the maximum)
   int ts_last = -1;
   for (int i = len - 1; rules && i >= p.begin_index; --i) {
-    const long long tk = row_ids[i];
+    const long long tk = __ldcg(row_ids + i);
     if (tk >= p.ts_begin) {
       ts_last = (int)tk;
       break;
@@ -337,11 +669,13 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
 
   const float* lg = p.logits + (long long)b * p.ld;
   float* proc = p.processed != nullptr ? p.processed + (long long)b * p.V : nullptr;
+  const int chunk = (((p.V + csplit - 1) / csplit) + 31) & ~31;  // whole bitmap words per slice
+  const int v_begin = rank * chunk, v_end = min(p.V, v_begin + chunk);
   Best bt{-INFINITY, p.V}, bs{-INFINITY, p.V};
   float tmax = -INFINITY, tsum = 0.f;  // online logsumexp over the timestamp region
-  for (int v = tid; v < p.V; v += blockDim.x) {
-    float x = lg[v];
-    bool masked = (p.suppress != nullptr && ((p.suppress[v >> 5] >> (v & 31)) & 1u)) || (rules && v == p.no_timestamps);
+  for (int v = v_begin + tid; v < v_end; v += blockDim.x) {
+    float x = __ldcg(lg + v);
+    bool masked = (p.suppress != nullptr && ((__ldg(p.suppress + (v >> 5)) >> (v & 31)) & 1u)) || (rules && v == p.no_timestamps);
     if (v < p.ts_begin) {
       masked = masked || at_begin || (text_lt_eos_masked && v < p.eos);
       if (masked) x = -INFINITY;
@@ -372,7 +706,6 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   }
   if (lane == 0) s_text[warp] = bt, s_ts[warp] = bs, s_max[warp] = tmax, s_sum[warp] = tsum;
   __syncthreads();
-  __shared__ int s_text_off;
   if (tid == 0) {
     for (int w = 1; w < nw; ++w) {
       bt = best_of(bt, s_text[w]);
@@ -383,25 +716,44 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
       tsum = tsum * c1 + s_sum[w] * c2;
       tmax = mn;
     }
+    if (rank != 0) {  // hand the slice to rank 0
+      const uint32_t dst = map_to_cta(smem_u32(&s_part[rank]), 0);
+      st_cluster_f32(dst + 0, bt.v), st_cluster_s32(dst + 4, bt.i);
+      st_cluster_f32(dst + 8, bs.v), st_cluster_s32(dst + 12, bs.i);
+      st_cluster_f32(dst + 16, tmax), st_cluster_f32(dst + 20, tsum);
+    }
+  }
+  if (csplit > 1) cluster_sync_all();
+  if (tid == 0 && rank == 0) {
+    for (int r = 1; r < csplit; ++r) {
+      const RulesPartial q = s_part[r];
+      bt = best_of(bt, Best{q.text_v, q.text_i});
+      bs = best_of(bs, Best{q.ts_v, q.ts_i});
+      const float mn = fmaxf(tmax, q.tmax);
+      const float c1 = tmax == -INFINITY ? 0.f : __expf(tmax - mn);
+      const float c2 = q.tmax == -INFINITY ? 0.f : __expf(q.tmax - mn);
+      tsum = tsum * c1 + q.tsum * c2;
+      tmax = mn;
+    }
     // logsumexp(timestamp log-probs) > max(text log-probs)  <=>  lse(ts scores) > max(text scores)
     const float ts_lse = tsum > 0.f ? tmax + __logf(tsum) : -INFINITY;
     const bool text_off = rules && ts_lse > bt.v;
     Best win = text_off ? bs : best_of(bt, bs);
     if (at_begin) {  // DiCoW: EOS keeps the score it had before the timestamp rules
-      float e = lg[p.eos];
+      float e = __ldcg(lg + p.eos);
       if ((p.suppress != nullptr && ((p.suppress[p.eos >> 5] >> (p.eos & 31)) & 1u)) || p.eos == p.no_timestamps)
         e = -INFINITY;
       win = best_of(win, Best{e, p.eos});
     }
     if (win.i >= p.V) win.i = p.eos;  // every score -inf: cannot happen with finite logits; stay defined
     long long tok = win.i;
-    const int unf = p.unfinished[b];
+    const int unf = __ldcg(p.unfinished + b);
     if (!unf) tok = p.pad;
     row_ids[len] = tok;
     p.unfinished[b] = unf && (tok != p.eos);
     s_text_off = text_off ? 1 : 0;
   }
-  if (proc != nullptr) {  // materialise the processed scores exactly like the reference processors (tests only)
+  if (proc != nullptr) {  // materialise the processed scores exactly like the reference processors (tests only; csplit = 1)
     __syncthreads();
     if (s_text_off)
       for (int v = tid; v < p.ts_begin; v += blockDim.x) proc[v] = -INFINITY;
@@ -450,6 +802,79 @@ extern "C" int dicow_gemm_skinny_bf16(dicow_handle_t h, const dicow_gemm_skinny_
   return DICOW_OK;
 }
 
+extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_args_t* a, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_decode_linear_args_t), "dicow_decode_linear: bad args struct");
+  const bool ln = a->x != nullptr;
+  DICOW_REQUIRE(ctx, (ln || a->A) && a->W && a->out, "dicow_decode_linear: null operand");
+  DICOW_REQUIRE(ctx, a->M >= 1 && a->M <= 64 && a->N >= 1 && a->K >= 32 && (a->K % 32) == 0,
+                "dicow_decode_linear: need 1 <= M <= 64, K %% 32 == 0 (got M=%d N=%d K=%d)", a->M, a->N, a->K);
+  DICOW_REQUIRE(ctx, (a->ldw % 8) == 0 && (reinterpret_cast<uintptr_t>(a->W) % 16) == 0, "dicow_decode_linear: W rows must be 16-byte aligned");
+  if (ln)
+    DICOW_REQUIRE(ctx, a->gamma && a->beta && a->K <= 1280 && (a->K % 4) == 0 && (a->ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
+                           (reinterpret_cast<uintptr_t>(a->gamma) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->beta) % 16) == 0,
+                  "dicow_decode_linear: the LayerNorm prologue needs gamma/beta, K <= 1280 and 16-byte aligned fp32 rows");
+  else
+    DICOW_REQUIRE(ctx, (a->lda % 8) == 0 && (reinterpret_cast<uintptr_t>(a->A) % 16) == 0, "dicow_decode_linear: A rows must be 16-byte aligned");
+  DICOW_REQUIRE(ctx, a->epilogue >= DICOW_EPI_BIAS_BF16 && a->epilogue <= DICOW_EPI_BIAS_F32, "dicow_decode_linear: unsupported epilogue %d", a->epilogue);
+  if (a->epilogue == DICOW_EPI_RESIDUAL_F32) DICOW_REQUIRE(ctx, a->resid != nullptr, "dicow_decode_linear: resid is NULL");
+  if (a->out2 != nullptr)
+    DICOW_REQUIRE(ctx, a->n_split > 0 && a->n_split < a->N && (a->n_split % 8) == 0, "dicow_decode_linear: bad n_split %d", a->n_split);
+  const int tiles = ceil_div(a->N, 8);
+  const int MT = ceil_div(a->M, 16);
+  // split K over a cluster until a CTA's slice fits the per-warp register slab (<= 1280), then once more while the grid
+  // would leave half of the SMs idle; slices stay multiples of 32.  The two-output form keeps K whole (fused q|k,v: N = 3d).
+  int ksplit = 1;
+  while ((a->K / ksplit > DL_WARPS * DL_KBW * 32 || (a->K % ksplit) != 0 || ((a->K / ksplit) % 32) != 0) && ksplit < DL_MAX_KSPLIT) ++ksplit;
+  DICOW_REQUIRE(ctx, a->K / ksplit <= DL_WARPS * DL_KBW * 32 && (a->K % ksplit) == 0 && ((a->K / ksplit) % 32) == 0,
+                "dicow_decode_linear: K = %d cannot be split into <= 8 slices of <= 1280 (multiples of 32)", a->K);
+  if (a->out2 != nullptr) DICOW_REQUIRE(ctx, ksplit == 1, "dicow_decode_linear: two outputs need K <= 1280");
+  if (!ln && a->out2 == nullptr && tiles * ksplit < 2 * ctx->num_sms && 2 * ksplit <= DL_MAX_KSPLIT && a->K / ksplit >= 640 &&
+      ((a->K / (2 * ksplit)) % 32) == 0)
+    ksplit *= 2;
+  DecLinParams p{};
+  p.x = a->x, p.ldx = a->ldx, p.gamma = a->gamma, p.beta = a->beta, p.eps = a->eps;
+  p.A = reinterpret_cast<const __nv_bfloat16*>(a->A), p.lda = a->lda;
+  p.W = reinterpret_cast<const __nv_bfloat16*>(a->W), p.ldw = a->ldw;
+  p.M = a->M, p.N = a->N, p.K = a->K, p.bias = a->bias, p.out = a->out, p.ldo = a->ldo, p.epilogue = a->epilogue;
+  p.resid = a->resid, p.ldr = a->ldr;
+  p.n_split = a->out2 != nullptr ? a->n_split : a->N, p.out2 = a->out2, p.ldo2 = a->ldo2, p.pos = a->pos, p.pos_stride = a->pos_stride;
+  p.ksplit = ksplit, p.Ks = a->K / ksplit, p.a_pitch = p.Ks + 32;
+  const size_t smem = (size_t)MT * 16 * p.a_pitch * 2 + (size_t)(DL_WARPS + ksplit - 1) * MT * 16 * 8 * sizeof(float);
+  DICOW_REQUIRE(ctx, smem <= (size_t)ctx->max_smem_optin, "dicow_decode_linear: %zu bytes of shared memory needed", smem);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  auto go = [&](auto kern) -> int {
+    DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (the carveout stays at the driver's default: forcing cudaSharedmemCarveoutMaxShared to fit four CTAs per SM made
+    // every instance SLOWER -- proj_out 32 -> 48 us, fc2 12 -> 16 us -- the weight stream needs the L1 array for its
+    // loads in flight more than it needs residency)
+    // one wave: a CTA takes as many consecutive tiles as it needs for the grid to fit the resident CTA slots
+    int per_sm = 1;
+    DICOW_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DL_THREADS, smem));
+    per_sm = per_sm < 1 ? 1 : per_sm;
+    p.tiles_per_cta = ksplit > 1 ? 1 : ceil_div(tiles, per_sm * ctx->num_sms);
+    int grid = ceil_div(tiles, p.tiles_per_cta) * ksplit;
+    unsigned cluster = (unsigned)ksplit;
+    if (ln) {  // clusters of DL_LN_CLUSTER CTAs share the LayerNorm; surplus CTAs of the last cluster own no tile
+      cluster = DL_LN_CLUSTER;
+      grid = ceil_div(grid, DL_LN_CLUSTER) * DL_LN_CLUSTER;
+    }
+    DICOW_CUDA_OK(ctx, launch_step_kernel(kern, dim3(grid), dim3(DL_THREADS), smem, stream, cluster, p));
+    return DICOW_OK;
+  };
+  switch (MT * 2 + (ln ? 1 : 0)) {
+    case 2: return go(decode_linear_kernel<1, false>);
+    case 3: return go(decode_linear_kernel<1, true>);
+    case 4: return go(decode_linear_kernel<2, false>);
+    case 5: return go(decode_linear_kernel<2, true>);
+    case 6: return go(decode_linear_kernel<3, false>);
+    case 7: return go(decode_linear_kernel<3, true>);
+    case 8: return go(decode_linear_kernel<4, false>);
+    default: return go(decode_linear_kernel<4, true>);
+  }
+}
+
 extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_attention_args_t* a, void* stream_) {
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;
   dicow_ctx* ctx = h;
@@ -465,10 +890,28 @@ extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_
   DecAttnParams p{};
   p.Q = reinterpret_cast<const __nv_bfloat16*>(a->Q), p.q_bs = a->q_batch_stride;
   p.K = reinterpret_cast<const __nv_bfloat16*>(a->K), p.V = reinterpret_cast<const __nv_bfloat16*>(a->V);
-  p.kv_rs = a->kv_row_stride, p.kv_bs = a->kv_batch_stride;
+  p.kv_rs = a->kv_row_stride, p.kv_bs = a->kv_batch_stride, p.kv_hs = a->kv_head_stride > 0 ? a->kv_head_stride : 64;
+  DICOW_REQUIRE(ctx, (p.kv_hs % 8) == 0, "dicow_decode_attention_bf16: kv_head_stride must be a multiple of 8 elements");
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out), p.o_bs = a->o_batch_stride, p.Tk = a->Tk, p.pos = a->pos;
   dim3 grid(a->H, a->B);
-  decode_attention_kernel<<<grid, DA_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // long fixed-length caches (cross attention, Tk = 1500) get 8 warps per (batch, head), the growing self-attention
+  // cache (Tk <= 448, read from the device scalar) 4
+  if (a->pos == nullptr && a->Tk >= 512)
+    DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_kernel<8>, grid, dim3(8 * 32), 0, stream, 1, p));
+  else
+    DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_kernel<4>, grid, dim3(4 * 32), 0, stream, 1, p));
+  return DICOW_OK;
+}
+
+extern "C" int dicow_kv_to_head_major(dicow_handle_t h, const void* kv_bf16, void* out_bf16, int B, int T, int H, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, kv_bf16 && out_bf16 && B >= 1 && B <= 65535 && T >= 1 && H >= 1 &&
+                         ((reinterpret_cast<uintptr_t>(kv_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) % 16) == 0,
+                "dicow_kv_to_head_major: bad args");
+  kv_to_head_major_kernel<<<dim3(T, B), 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const uint4*>(kv_bf16), reinterpret_cast<uint4*>(out_bf16), T, H);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }
@@ -481,9 +924,9 @@ extern "C" int dicow_embed_tokens(dicow_handle_t h, const int64_t* ids, int64_t 
   DICOW_REQUIRE(ctx, ids && embed_tokens && embed_positions && x && B >= 1 && B <= 65535 && S >= 1 && d >= 4 && (d % 4) == 0,
                 "dicow_embed_tokens: bad args");
   dim3 grid(S, B);
-  embed_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      reinterpret_cast<const long long*>(ids), ids_row_stride, embed_tokens, embed_positions, x, S, d, past, pos, vocab);
-  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  DICOW_CUDA_OK(ctx, launch_step_kernel(embed_kernel, grid, dim3(128), 0, reinterpret_cast<cudaStream_t>(stream_), 1,
+                                        reinterpret_cast<const long long*>(ids), (long long)ids_row_stride, embed_tokens,
+                                        embed_positions, x, S, d, past, pos, vocab));
   return DICOW_OK;
 }
 
@@ -491,8 +934,8 @@ extern "C" int dicow_advance(dicow_handle_t h, int32_t* pos, int by, void* strea
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;
   dicow_ctx* ctx = h;
   DICOW_REQUIRE(ctx, pos != nullptr, "dicow_advance: null pos");
-  advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(pos, by);
-  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  DICOW_CUDA_OK(ctx, launch_step_kernel(advance_kernel, dim3(1), dim3(1), 0, reinterpret_cast<cudaStream_t>(stream_), 1,
+                                        reinterpret_cast<int*>(pos), by));
   return DICOW_OK;
 }
 
@@ -510,7 +953,10 @@ extern "C" int dicow_logits_rules_argmax(dicow_handle_t h, const dicow_logits_ru
   p.begin_index = a->begin_index, p.eos = a->eos, p.pad = a->pad, p.no_timestamps = a->no_timestamps;
   p.ts_begin = a->ts_begin, p.max_initial_ts = a->max_initial_timestamp_index, p.ts_rules = a->timestamp_rules;
   p.suppress = a->suppress_bitmap, p.unfinished = a->unfinished, p.processed = a->processed_scores;
-  logits_rules_argmax_kernel<<<a->B, 512, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
-  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  // the vocabulary of one row is scanned by a cluster of 8 CTAs (B rows alone would occupy B of the 148 SMs); the
+  // test-only materialisation of the processed scores needs the row's verdict in every slice and runs unsplit
+  const int csplit = (a->processed_scores == nullptr && a->V >= 8192) ? 8 : 1;
+  DICOW_CUDA_OK(ctx, launch_step_kernel(logits_rules_argmax_kernel, dim3(a->B * csplit), dim3(512), 0,
+                                        reinterpret_cast<cudaStream_t>(stream_), (unsigned)csplit, p, csplit));
   return DICOW_OK;
 }

@@ -139,6 +139,63 @@ __global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm of a handful of rows (the decode step: one row per sequence).  One CTA of 128 threads per row, at most
+// three float4 per thread (d <= 1536), a loop-free body of ~150 instructions: the kernel runs once per launch per
+// warp, so a 10x unrolled body (fddt_ln_kernel<10>) is bound by instruction fetch -- measured 7.3 us for 16 rows.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_128(float v, float* sm) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(128) ln_rows_kernel(const float* __restrict__ x, int d, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps,
+                                                      __nv_bfloat16* __restrict__ ln_bf16, float* __restrict__ ln_f32) {
+  __shared__ float sm[4];
+  const int row = blockIdx.x, tid = threadIdx.x, nvec = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  float4 v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = tid + 128 * i;
+    v[i] = c < nvec ? __ldcg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = block_sum_128(s, sm) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (tid + 128 * i < nvec) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b2 * b2) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(block_sum_128(q, sm) / (float)d + eps);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c4 = tid + 128 * i;
+    if (c4 < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float4 y;
+      y.x = fmaf((v[i].x - mean) * rstd, g.x, be.x);
+      y.y = fmaf((v[i].y - mean) * rstd, g.y, be.y);
+      y.z = fmaf((v[i].z - mean) * rstd, g.z, be.z);
+      y.w = fmaf((v[i].w - mean) * rstd, g.w, be.w);
+      if (ln_bf16 != nullptr)
+        reinterpret_cast<uint2*>(ln_bf16 + (long long)row * d)[c4] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (ln_f32 != nullptr) reinterpret_cast<float4*>(ln_f32 + (long long)row * d)[c4] = y;
+    }
+  }
+}
+
 // TMA-pipelined variant (default): one producer warp streams rows (x fp32 + up to two bf16 deltas) into a 16-stage
 // shared-memory ring with cp.async.bulk + mbarrier transaction counts; 16 consumer warps each take a row from the ring,
 // so the HBM latency is hidden by the ring depth (160 KB in flight per SM) instead of by occupancy -- the register-
@@ -526,8 +583,18 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   p.delta2 = reinterpret_cast<const __nv_bfloat16*>(a->delta2_bf16);
   p.store_x = a->store_x;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  // default: TMA-pipelined kernel (needs 16-byte rows: d % 8 == 0); flags bit 0 -> warp-per-row, bit 1 -> column-owner
-  if ((a->d % 8) == 0 && a->d <= 1280 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
+  // default: TMA-pipelined kernel (needs 16-byte rows: d % 8 == 0); flags bit 0 -> warp-per-row, bit 1 -> column-owner.
+  // A handful of rows (the decode step: one row per sequence) cannot amortise the ring's set-up (measured 7.1 us for
+  // 16 rows): they take the warp-per-row kernel, two rows per CTA.
+  const bool few_rows = a->rows <= 128;
+  if (few_rows && a->gamma != nullptr && a->stno == nullptr && a->delta1_bf16 == nullptr && a->delta2_bf16 == nullptr &&
+      a->x_out_bf16 == nullptr && a->d <= 1536 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0) {
+    ln_rows_kernel<<<a->rows, 128, 0, stream>>>(a->x, a->d, a->gamma, a->beta, a->eps,
+                                                 reinterpret_cast<__nv_bfloat16*>(a->ln_out_bf16), a->ln_out_f32);
+    DICOW_CUDA_OK(ctx, cudaGetLastError());
+    return DICOW_OK;
+  }
+  if (!few_rows && (a->d % 8) == 0 && a->d <= 1280 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(a->delta1_bf16) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->delta2_bf16) % 16) == 0) {
     switch (ceil_div(a->d, 128)) {
 #define DICOW_CASE(V) \
@@ -547,7 +614,7 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
     DICOW_CUDA_OK(ctx, cudaGetLastError());
     return DICOW_OK;
   }
-  const int rows_per_block = 8;
+  const int rows_per_block = few_rows ? 2 : 8;
   const int grid = ceil_div(a->rows, rows_per_block);
   const int vpl = ceil_div(a->d, 128);
   switch (vpl) {

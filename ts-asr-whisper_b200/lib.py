@@ -140,13 +140,25 @@ class GemmSkinnyArgs(C.Structure):
     ]
 
 
+class DecodeLinearArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("x", C.c_void_p), ("ldx", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64), ("epilogue", C.c_int32),
+        ("resid", C.c_void_p), ("ldr", C.c_int64), ("n_split", C.c_int32), ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("pos", C.c_void_p), ("pos_stride", C.c_int64),
+    ]
+
+
 class DecodeAttentionArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
         ("Q", C.c_void_p), ("q_batch_stride", C.c_int64), ("K", C.c_void_p), ("V", C.c_void_p),
         ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("o_batch_stride", C.c_int64),
-        ("B", C.c_int32), ("H", C.c_int32), ("Tk", C.c_int32), ("pos", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tk", C.c_int32), ("pos", C.c_void_p), ("kv_head_stride", C.c_int64),
     ]
 
 
@@ -232,7 +244,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_embedding_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.dicow_softlabel_ce_bwd.argtypes = [vp, C.POINTER(SoftlabelCeBwdArgs), vp]
     lib.dicow_gemm_skinny_bf16.argtypes = [vp, C.POINTER(GemmSkinnyArgs), vp]
+    lib.dicow_decode_linear.argtypes = [vp, C.POINTER(DecodeLinearArgs), vp]
     lib.dicow_decode_attention_bf16.argtypes = [vp, C.POINTER(DecodeAttentionArgs), vp]
+    lib.dicow_kv_to_head_major.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_embed_tokens.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.dicow_advance.argtypes = [vp, vp, C.c_int, vp]
     lib.dicow_logits_rules_argmax.argtypes = [vp, C.POINTER(LogitsRulesArgs), vp]
@@ -252,7 +266,7 @@ EXPORTED_SYMBOLS = [
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
-    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd",
+    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major",
 ]
 
 

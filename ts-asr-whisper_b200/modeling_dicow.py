@@ -237,7 +237,9 @@ class _GreedyState:
         self.ctx = torch.empty(B, d, **bf)
         self.h = torch.empty(B, cfg.decoder_ffn_dim, **bf)
         self.self_kv = torch.zeros(L, B, self.S_max, 2 * d, **bf)
-        self.cross_kv = torch.empty(L, B, T, 2 * d, **bf)
+        # cross-attention cache, head-major [L, B, H, T, k(64) | v(64)]: one contiguous stream per (batch, head) and step
+        self.cross_kv = torch.empty(L, B, cfg.decoder_attention_heads, T, 128, **bf)
+        self.cross_kv_rows = torch.empty(B * T, 2 * d, **bf)  # the projection GEMM's output before the re-layout
         self.logits = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.weights_id = None  # id() of the prepared-weight dict the graphs were captured with
@@ -251,6 +253,9 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
     _no_split_modules = ["EncoderLayerParams", "DecoderLayerParams"]
     # step graphs are captured once per batch size; set False to launch the step kernels eagerly (debugging)
     use_cuda_graphs = True
+    # True: fused q|k,v projection, cluster split-K linear layers, few-rows LayerNorm kernel; "ln_prologue": LayerNorm as
+    # the prologue of the linear kernel instead; False: one kernel per operation (_decode_step_unfused), the baseline
+    fused_decode_step = True
 
     def __init__(self, config: DiCoWConfig):
         super().__init__(config)
@@ -410,7 +415,49 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
 
     # ---- greedy decoding of one 30 s window batch ----------------------------------------------------------------
     def _decode_step(self, st: _GreedyState, w: dict, sample: bool, gen: dict) -> None:
-        """One token for every row: fixed launch sequence, position read from the device scalar ``st.pos``."""
+        """One token for every row: fixed launch sequence, position read from the device scalar ``st.pos``.
+        Per decoder layer (HF:modeling_whisper.py:449-506): LayerNorm, q | k,v as ONE projection whose k,v columns are
+        appended to the cache, attention over the cache, out_proj + residual, ... -- the linear layers are
+        ops.decode_linear (weights requested first, A staged once in shared memory, K split over a cluster for the
+        small-N layers)."""
+        cfg = self.config
+        d, H, B, T = cfg.d_model, cfg.decoder_attention_heads, st.B, st.T
+        if not self.fused_decode_step or d % 32:
+            return self._decode_step_unfused(st, w, sample, gen)
+        ln_prologue = self.fused_decode_step == "ln_prologue" and d <= 1280  # the prologue holds a row in registers
+
+        def ln_linear(W, out, g, b, **kw):
+            """LayerNorm(x) -> Linear: LayerNorm as the prologue of the linear kernel, or (default: measured faster,
+            DESIGN.md section 4.2) the few-rows LayerNorm kernel followed by the linear kernel on its bf16 output"""
+            if ln_prologue:
+                return ops.decode_linear(W, out, x=st.x, gamma=g, beta=b, **kw)
+            ops.fddt_layernorm(st.x, gamma=g, beta=b, ln_out_bf16=st.ln)
+            return ops.decode_linear(W, out, A=st.ln, **kw)
+
+        ops.embed_tokens(st.ids, w["tok"], w["pos"], st.x, S=1, pos=st.pos)
+        for li, e in enumerate(w["layers"]):
+            s, c = e["self"], e["cross"]
+            kvc = st.self_kv[li]
+            ln_linear(s["wqkv"], st.q, e["ln1_g"], e["ln1_b"], epilogue=ops.EPI_BIAS_BF16, bias=s["bqkv"], out2=kvc,
+                      n_split=d, ldo2=st.S_max * 2 * d, pos=st.pos, pos_stride=2 * d)
+            ops.decode_attention(st.q, kvc, kvc[:, :, d:], st.ctx, B=B, H=H, Tk=0, kv_row_stride=2 * d,
+                                 kv_batch_stride=st.S_max * 2 * d, pos=st.pos)
+            ops.decode_linear(s["wo"], st.x, A=st.ctx, epilogue=ops.EPI_RESIDUAL_F32, bias=s["bo"], resid=st.x)
+            ln_linear(c["wq"], st.q, e["ln2_g"], e["ln2_b"], epilogue=ops.EPI_BIAS_BF16, bias=c["bq"])
+            ckv = st.cross_kv[li]
+            ops.decode_attention(st.q, ckv, ckv[..., 64:], st.ctx, B=B, H=H, Tk=T, kv_row_stride=128,
+                                 kv_batch_stride=H * T * 128, kv_head_stride=T * 128)
+            ops.decode_linear(c["wo"], st.x, A=st.ctx, epilogue=ops.EPI_RESIDUAL_F32, bias=c["bo"], resid=st.x)
+            ln_linear(e["w1"], st.h, e["ln3_g"], e["ln3_b"], epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
+            ops.decode_linear(e["w2"], st.x, A=st.h, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=st.x)
+        if sample:
+            ln_linear(w["proj"], st.logits, w["lnf_g"], w["lnf_b"], epilogue=ops.EPI_BIAS_F32)
+            ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **gen)
+        ops.advance(st.pos, 1)
+
+    def _decode_step_unfused(self, st: _GreedyState, w: dict, sample: bool, gen: dict) -> None:
+        """the same step with one kernel per operation (LayerNorm, q, k|v, ... 13 per layer): kept as the comparison
+        baseline of the fused step (tests/test_gpu_decoder.py, tools/bench_decode.py --unfused)"""
         cfg = self.config
         d, H, B, T = cfg.d_model, cfg.decoder_attention_heads, st.B, st.T
         ops.embed_tokens(st.ids, w["tok"], w["pos"], st.x, S=1, pos=st.pos)
@@ -427,8 +474,8 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             ops.fddt_layernorm(st.x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=st.ln)
             ops.gemm_skinny(st.ln, c["wq"], st.q, epilogue=ops.EPI_BIAS_BF16, bias=c["bq"])
             ckv = st.cross_kv[li]
-            ops.decode_attention(st.q, ckv, ckv[:, :, d:], st.ctx, B=B, H=H, Tk=T, kv_row_stride=2 * d,
-                                 kv_batch_stride=T * 2 * d)
+            ops.decode_attention(st.q, ckv, ckv[..., 64:], st.ctx, B=B, H=H, Tk=T, kv_row_stride=128,
+                                 kv_batch_stride=H * T * 128, kv_head_stride=T * 128)
             ops.gemm_skinny(st.ctx, c["wo"], st.x, epilogue=ops.EPI_RESIDUAL_F32, bias=c["bo"], resid=st.x)
             ops.fddt_layernorm(st.x, gamma=e["ln3_g"], beta=e["ln3_b"], ln_out_bf16=st.ln)
             ops.gemm_skinny(st.ln, e["w1"], st.h, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
@@ -459,9 +506,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             st = self._greedy[key] = _GreedyState(self, B, T, dev)
         enc_bf16 = enc_hidden if enc_hidden.dtype == torch.bfloat16 else ops.cast_bf16(enc_hidden.float())
         encf = enc_bf16.reshape(B * T, d)
+        H = cfg.decoder_attention_heads
         for li, e in enumerate(w["layers"]):  # cross-attention K/V once per window (HF caches them after step 0)
-            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv[li].view(B * T, 2 * d), epilogue=ops.EPI_BIAS_BF16,
-                     bias=e["cross"]["bkv"])
+            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv_rows, epilogue=ops.EPI_BIAS_BF16, bias=e["cross"]["bkv"])
+            ops.kv_to_head_major(st.cross_kv_rows, st.cross_kv[li], B=B, T=T, H=H)
         if st.weights_id != id(w):  # parameters changed since capture: the graphs hold stale weight pointers
             st.graphs.clear()
             st.weights_id = id(w)
@@ -475,7 +523,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             if not self.use_cuda_graphs:
                 self._decode_step(st, w, sample, gen)
                 return
-            gkey = (sample, P, tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+            gkey = (sample, P, self.fused_decode_step, tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                             for k, v in gen.items())))
             g = st.graphs.get(gkey)
             if g is None:

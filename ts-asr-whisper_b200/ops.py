@@ -296,8 +296,43 @@ def gemm_skinny(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue
     return out
 
 
+def decode_linear(W: torch.Tensor, out: torch.Tensor, *, epilogue: int, A: Optional[torch.Tensor] = None,
+                  x: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                  beta: Optional[torch.Tensor] = None, eps: float = 1e-5, bias: Optional[torch.Tensor] = None,
+                  M: Optional[int] = None, ldo: Optional[int] = None, resid: Optional[torch.Tensor] = None,
+                  out2: Optional[torch.Tensor] = None, n_split: int = 0, ldo2: int = 0,
+                  pos: Optional[torch.Tensor] = None, pos_stride: int = 0) -> torch.Tensor:
+    """[LayerNorm ->] Linear of one decode step in one kernel (dicow_decode_linear): the A operand is either
+    LayerNorm(``x``) (fp32 [M, K], gamma / beta) or the bf16 ``A``; columns >= ``n_split`` go to ``out2`` (KV-cache
+    append at device position ``pos``)."""
+    src = x if x is not None else A
+    dev = _require_cuda(src, W, out, gamma, beta, bias, resid, out2, pos)
+    a = _lib.DecodeLinearArgs()
+    a.struct_size = C.sizeof(_lib.DecodeLinearArgs)
+    if x is not None:
+        assert x.dtype == torch.float32 and gamma is not None and beta is not None
+        a.x, a.ldx, a.gamma, a.beta, a.eps = _ptr(x), x.stride(-2) if x.dim() > 1 else x.shape[-1], _ptr(gamma), _ptr(beta), eps
+    else:
+        assert A is not None and A.dtype == torch.bfloat16
+        a.A, a.lda = _ptr(A), A.stride(-2) if A.dim() > 1 else A.shape[-1]
+    a.W, a.ldw = _ptr(W), W.stride(0)
+    a.M = M if M is not None else src.numel() // src.shape[-1]
+    a.N, a.K = W.shape
+    a.bias = _ptr(bias)
+    a.out = _ptr(out)
+    a.ldo = ldo if ldo is not None else out.stride(-2)
+    a.epilogue = epilogue
+    a.resid = _ptr(resid)
+    a.ldr = resid.stride(-2) if resid is not None else 0
+    a.n_split, a.out2, a.ldo2 = n_split, _ptr(out2), ldo2
+    a.pos, a.pos_stride = _ptr(pos), pos_stride
+    _call("dicow_decode_linear", dev, a, "decode_linear", 2.0 * a.M * a.N * a.K)
+    return out
+
+
 def decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tk: int,
-                     kv_row_stride: int, kv_batch_stride: int, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     kv_row_stride: int, kv_batch_stride: int, pos: Optional[torch.Tensor] = None,
+                     kv_head_stride: int = 0) -> torch.Tensor:
     """one query row per (batch, head) against a K/V cache (dicow_decode_attention_bf16); q/out bf16 [B, H*64]."""
     dev = _require_cuda(q, k, v, out, pos)
     a = _lib.DecodeAttentionArgs()
@@ -308,7 +343,23 @@ def decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: tor
     a.out, a.o_batch_stride = _ptr(out), out.stride(0)
     a.B, a.H, a.Tk = B, H, Tk
     a.pos = _ptr(pos)
+    a.kv_head_stride = kv_head_stride
     _call("dicow_decode_attention_bf16", dev, a, "decode_attention")
+    return out
+
+
+def kv_to_head_major(kv: torch.Tensor, out: torch.Tensor, *, B: int, T: int, H: int) -> torch.Tensor:
+    """[B*T, (k | v) x H x 64] bf16 -> [B, H, T, 128] (dicow_kv_to_head_major): the cross-attention cache layout of the
+    decode step (one contiguous K|V stream per (batch, head))."""
+    global launch_count
+    dev = _require_cuda(kv, out)
+    assert kv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and kv.is_contiguous() and out.is_contiguous()
+    assert kv.numel() == B * T * 2 * H * 64 == out.numel()
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_kv_to_head_major(h, _ptr(kv), _ptr(out), B, T, H, _stream(dev))
+    _lib.check(rc, h, "dicow_kv_to_head_major")
+    launch_count += 1
     return out
 
 
