@@ -261,8 +261,14 @@ def main():
                 "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[0] else None} for k, v in by_kind.items()}
     gemm = by_kind.get("gemm", [0.0, 1.0, 1])
     achieved = gemm[0] / (gemm[1] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,*> (tcgen05 GEMM family: QKV/out/fc1/fc2/conv)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+    traffic = None  # dram read + write bytes per launch of the same kernel family from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch_avg"]
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<256,*> (tcgen05 GEMM family: QKV/out/fc1/fc2/conv)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "peak_source": peak_src, "launches_per_step": gemm[2] // max(1, args.steps),
                 "gflop_per_launch_avg": gemm[0] / max(1, gemm[2]) / 1e9,
                 "us_per_launch_avg": 1e3 * gemm[1] / max(1, gemm[2]),
