@@ -102,3 +102,63 @@ def test_log_mel(n_mels):
     assert feat.shape == g[f"feat{n_mels}"].shape
     _close(feat, g[f"feat{n_mels}"], 2e-5)
     assert np.array_equal(mask, g[f"mask{n_mels}"])
+
+
+# ---- joint CTC / attention decoding: oracle/ctc_prefix.py vs the reference's own classes --------
+def _ctc_golden():
+    return np.load(os.path.join(GOLD, "ctc_joint.npz"))
+
+
+def test_ctc_prefix_scorer_known_answers():
+    """CTCPrefixScore.__call__ (decoding.py:121-159) on two hypotheses per call, first with empty prefixes, then with
+    prefixes of different lengths (the forward recursion starts at the SHORTER prefix for both: module docstring)"""
+    from oracle import ctc_prefix as cp
+    g = _ctc_golden()
+    V, EOS, SOT, BLANK, TS0, T, B, K, STEPS = [int(v) for v in g["meta"]]
+    x = torch.log_softmax(torch.from_numpy(g["enc_logits"][:2]), dim=-1)
+    cs = g["kat_cs"]
+    for b in range(2):
+        r0, _ = cp.initial_state(x[b], BLANK)
+        psi, r = cp.prefix_scores(x[b], cs[b].tolist(), BLANK, 0, r0, BLANK, EOS, loop_start=1)
+        np.testing.assert_allclose(psi.numpy(), g["kat_psi0"][b], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(r.numpy(), g["kat_r0"][b], rtol=2e-5, atol=2e-5)
+    lens, lasts = [2, 1], [2, 4]
+    for b in range(2):
+        psi, r = cp.prefix_scores(x[b], cs[b].tolist(), lasts[b], lens[b], torch.from_numpy(g["kat_r1_in"][b]), BLANK, EOS,
+                                  loop_start=min(lens))
+        np.testing.assert_allclose(psi.numpy(), g["kat_psi1"][b], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(r.numpy(), g["kat_r1"][b], rtol=2e-5, atol=2e-5)
+
+
+def test_joint_ctc_rescorer_matches_reference_steps():
+    """CTCRescorerLogitsProcessor driven like the greedy loop (generation.py:728-769): per step the combined scores, the
+    chosen tokens and the carried CTC state / score of every unfinished hypothesis"""
+    from oracle import ctc_prefix as cp
+    g = _ctc_golden()
+    V, EOS, SOT, BLANK, TS0, T, B, K, STEPS = [int(v) for v in g["meta"]]
+    up = dict(zip(g["upper_lo"].tolist(), g["upper_up"].tolist()))
+    resc = cp.JointCtcRescorer(torch.from_numpy(g["enc_logits"]), blank=BLANK, eos=EOS, bos=SOT, prefix_len=3,
+                               first_timestamp=TS0, ctc_weight=float(g["ctc_weight"]), top_k=K, upper_cased=up)
+    ids = torch.tensor([[SOT, SOT + 1, SOT + 2]] * B)
+    unfinished = torch.ones(B, dtype=torch.long)
+    n_text = 0
+    for step in range(STEPS):
+        nxt = resc(ids, torch.from_numpy(g[f"att_{step}"]))
+        ref = torch.from_numpy(g[f"next_{step}"])
+        live = ref > -1e8  # candidates and timestamps; everything else carries w * LOGZERO
+        assert torch.equal(live, nxt > -1e8)
+        np.testing.assert_allclose(nxt[live].numpy(), ref[live].numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(nxt[~live & torch.isfinite(ref)].numpy(), ref[~live & torch.isfinite(ref)].numpy(), rtol=1e-5)
+        tok = torch.argmax(nxt, dim=-1)
+        tok = tok * unfinished + EOS * (1 - unfinished)
+        assert tok.tolist() == g[f"tok_{step}"].tolist(), f"step {step}"
+        resc.update_state(tok)
+        for b in range(B):
+            if int(unfinished[b]) and int(tok[b]) != EOS:
+                np.testing.assert_allclose(float(resc.score_prev[b]), g[f"score_prev_{step}"][b], rtol=1e-4, atol=1e-4)
+                np.testing.assert_allclose(resc.r_prev[b].numpy(), g[f"state_prev_{step}"][b], rtol=1e-4, atol=1e-4)
+                n_text += int(tok[b]) < TS0
+        ids = torch.cat([ids, tok[:, None]], dim=1)
+        unfinished = unfinished & (tok != EOS).long()
+    assert ids.tolist() == g["ids"].tolist()
+    assert n_text >= 8 and int(unfinished.sum()) < B  # text tokens moved the state; a row finished
