@@ -446,9 +446,47 @@ typedef struct {
   int32_t timestamp_rules;             /* 1 = return_timestamps (timestamp processor on); 0 = suppress list + argmax only */
   const uint32_t* suppress_bitmap;     /* ceil(V / 32) words, bit v set = suppressed; or NULL */
   int32_t* unfinished;                 /* [B] */
-  float* processed_scores;             /* optional [B, V]: the scores after all processors (tests) */
+  float* processed_scores;             /* optional [B, V]: the scores after all processors (tests; input of the joint CTC step) */
+  int32_t no_select;                   /* 1 = only write processed_scores: leave ids / unfinished alone (joint CTC decoding
+                                          selects after the CTC rescoring, dicow_ctc_joint_step) */
 } dicow_logits_rules_args_t;
 DICOW_API int dicow_logits_rules_argmax(dicow_handle_t h, const dicow_logits_rules_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Joint CTC / attention decoding, one generated token for B hypotheses.  Replaces
+ * LogSoftmaxProcessor + CTCRescorerLogitsProcessor.__call__ + argmax + CTCRescorerLogitsProcessor.update_state
+ * (src/models/dicow/generation.py:250-268, 756-769; src/models/dicow/decoding.py:8-159, 253-338):
+ *   scores  = log_softmax(processed_scores)                      (the suppress / timestamp processors ran before)
+ *   cands   = top-K text ids of scores (EOS forced in)
+ *   ctc[c]  = CTC prefix score of prefix + c for c in cands (forward variables over the T CTC frames), LOGZERO elsewhere,
+ *             row maximum for timestamp ids
+ *   token   = argmax (1 - w) scores + w (ctc - ctc_prev);  finished rows emit pad;  ids[b, len] = token
+ *   a text token moves (r_prev, score_prev) of the hypothesis to its candidate's forward variables / prefix score.
+ * ctc_logp: [B, T, V1] fp32 log-posteriors of the window (dicow_log_softmax_rows of the CTC logits; blank = V1 - 1 class).
+ * workspace_i32: 4 B + 4 + B K ints; workspace_f32: B + 2 B K floats; states: B T 2 K floats; r_prev: [B, T, 2] initialised
+ * to (LOGZERO, cumsum of the blank log-posteriors), score_prev: [B] zeros (decoding.py:37-44).  B <= 64, K <= 512.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  int64_t* ids; /* [B, >= len + 1] */
+  int64_t ids_row_stride;
+  const int32_t* pos; /* device scalar: len = *pos + 1 (or cur_len when NULL) */
+  int32_t cur_len;
+  int32_t B, V, T, V1, K;
+  int32_t bos, eos, pad, blank, first_timestamp, prefix_len; /* prefix_len = len(tokenizer.prefix_tokens) */
+  float ctc_weight;
+  const float* ctc_logp;
+  const float* processed_scores; /* [B, V] */
+  int32_t* workspace_i32;
+  float* workspace_f32;
+  float* states;
+  float* r_prev;
+  float* score_prev;
+  int32_t* unfinished;
+} dicow_ctc_joint_args_t;
+DICOW_API int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args_t* args, void* stream);
+/* out[r, :] = in[r, :] - logsumexp(in[r, :]) over V columns (in place allowed) */
+DICOW_API int dicow_log_softmax_rows(dicow_handle_t h, const float* in, float* out, int64_t rows, int V, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Losses.  soft-label CE: src/models/dicow/modeling_dicow.py:95-144 (soft_mode = 1: Gaussian-smoothed timestamp targets,

@@ -1,7 +1,7 @@
 """CPU oracle (test infrastructure, NOT product code) for joint CTC / attention decoding -- SURVEY.md section 8(f).1.
 
-Restates, hypothesis by hypothesis and frame by frame (plain loops over small tensors, fp64 optional), what the reference
-computes with batched tensor code:
+Restates, hypothesis by hypothesis and frame by frame (a Python loop over hypotheses and over the CTC frames, torch
+vectors over the candidates of one hypothesis), what the reference computes with tensor code batched over hypotheses:
 
   * ``prefix_scores``   -- CTCPrefixScore.__call__            (src/models/dicow/decoding.py:8-159; ESPnet's vectorised form of
                            Watanabe et al., "Hybrid CTC/attention architecture for end-to-end speech recognition", Alg. 2)
@@ -55,27 +55,30 @@ def prefix_scores(x: torch.Tensor, cs: Sequence[int], last: int, decoded_len: in
     T = x.shape[0]
     C = len(cs)
     dt = x.dtype
+    cs_t = torch.tensor(list(cs), dtype=torch.long)
+    xs = x[:, cs_t]                                                  # [T, C] posteriors of the candidates
     r = torch.full((T, 2, C), LOGZERO, dtype=dt)
-    psi = torch.full((C,), LOGZERO, dtype=dt)
-    r_sum = _lae(r_prev[:, 0], r_prev[:, 1])
-    for j, c in enumerate(cs):
-        xs = x[:, c]
-        if decoded_len == 0:
-            r[0, 0, j] = xs[0]
-        phi = r_prev[:, 1] if (decoded_len > 0 and c == last) else r_sum
-        start = max(decoded_len, 1)
-        p = r[start - 1, 0, j]
-        terms = [phi[t - 1] + xs[t] if t >= decoded_len else torch.tensor(LOGZERO, dtype=dt) for t in range(1, T)]
-        if terms:
-            p = _lae(p, torch.logsumexp(torch.stack(terms), dim=0))
-        for t in range(loop_start, T):
-            r[t, 0, j] = _lae(r[t - 1, 0, j], phi[t - 1]) + xs[t]
-            r[t, 1, j] = _lae(r[t - 1, 0, j], r[t - 1, 1, j]) + x[t, blank]
-        if c == eos:
-            p = r_sum[T - 1]
-        elif c == blank:
-            p = torch.tensor(LOGZERO, dtype=dt)
-        psi[j] = p
+    r_sum = _lae(r_prev[:, 0], r_prev[:, 1])                         # log(r^n(g) + r^b(g)) of the prefix g
+    # log phi: paths of the prefix that may be extended by c at the next frame -- all of them, except for c == last label
+    # where only the paths ending in blank count (a repeated label needs a blank in between)
+    phi = r_sum[:, None].repeat(1, C)
+    if decoded_len > 0:
+        phi[:, cs_t == last] = r_prev[:, 1:2]
+    if decoded_len == 0:
+        r[0, 0] = xs[0]
+    start = max(decoded_len, 1)
+    psi = r[start - 1, 0].clone()
+    if T > 1:
+        terms = phi[:-1] + xs[1:]                                    # new label starts at frame t = 1 .. T-1
+        frames = torch.arange(1, T)[:, None]
+        terms = torch.where(frames >= decoded_len, terms, torch.full_like(terms, LOGZERO))
+        psi = _lae(psi, torch.logsumexp(terms, dim=0))
+    for t in range(loop_start, T):                                   # frame by frame (decoding.py:100-104)
+        r[t, 0] = _lae(r[t - 1, 0], phi[t - 1]) + xs[t]
+        r[t, 1] = _lae(r[t - 1, 0], r[t - 1, 1]) + x[t, blank]
+    psi[cs_t == eos] = r_sum[T - 1]
+    if eos != blank:
+        psi[cs_t == blank] = LOGZERO
     return psi, r
 
 

@@ -594,6 +594,7 @@ struct RulesParams {
   const unsigned* suppress;  // bitmap, ceil(V / 32) words, or NULL
   int* unfinished;           // [B] 1 = still decoding
   float* processed;          // optional [B, V] fp32 copy of the processed scores (tests)
+  int no_select;             // only materialise the processed scores
 };
 
 struct Best {
@@ -749,8 +750,10 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
     long long tok = win.i;
     const int unf = __ldcg(p.unfinished + b);
     if (!unf) tok = p.pad;
-    row_ids[len] = tok;
-    p.unfinished[b] = unf && (tok != p.eos);
+    if (!p.no_select) {
+      row_ids[len] = tok;
+      p.unfinished[b] = unf && (tok != p.eos);
+    }
     s_text_off = text_off ? 1 : 0;
   }
   if (proc != nullptr) {  // materialise the processed scores exactly like the reference processors (tests only; csplit = 1)
@@ -953,6 +956,8 @@ extern "C" int dicow_logits_rules_argmax(dicow_handle_t h, const dicow_logits_ru
   p.begin_index = a->begin_index, p.eos = a->eos, p.pad = a->pad, p.no_timestamps = a->no_timestamps;
   p.ts_begin = a->ts_begin, p.max_initial_ts = a->max_initial_timestamp_index, p.ts_rules = a->timestamp_rules;
   p.suppress = a->suppress_bitmap, p.unfinished = a->unfinished, p.processed = a->processed_scores;
+  p.no_select = a->no_select;
+  DICOW_REQUIRE(ctx, !a->no_select || a->processed_scores != nullptr, "dicow_logits_rules_argmax: no_select needs processed_scores");
   // the vocabulary of one row is scanned by a cluster of 8 CTAs (B rows alone would occupy B of the 148 SMs); the
   // test-only materialisation of the processed scores needs the row's verdict in every slice and runs unsplit
   const int csplit = (a->processed_scores == nullptr && a->V >= 8192) ? 8 : 1;

@@ -170,6 +170,20 @@ class LogitsRulesArgs(C.Structure):
         ("begin_index", C.c_int32), ("eos", C.c_int32), ("pad", C.c_int32), ("no_timestamps", C.c_int32),
         ("ts_begin", C.c_int32), ("max_initial_timestamp_index", C.c_int32), ("timestamp_rules", C.c_int32),
         ("suppress_bitmap", C.c_void_p), ("unfinished", C.c_void_p), ("processed_scores", C.c_void_p),
+        ("no_select", C.c_int32),
+    ]
+
+
+class CtcJointArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("ids", C.c_void_p), ("ids_row_stride", C.c_int64), ("pos", C.c_void_p), ("cur_len", C.c_int32),
+        ("B", C.c_int32), ("V", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32), ("K", C.c_int32),
+        ("bos", C.c_int32), ("eos", C.c_int32), ("pad", C.c_int32), ("blank", C.c_int32), ("first_timestamp", C.c_int32),
+        ("prefix_len", C.c_int32), ("ctc_weight", C.c_float),
+        ("ctc_logp", C.c_void_p), ("processed_scores", C.c_void_p), ("workspace_i32", C.c_void_p),
+        ("workspace_f32", C.c_void_p), ("states", C.c_void_p), ("r_prev", C.c_void_p), ("score_prev", C.c_void_p),
+        ("unfinished", C.c_void_p),
     ]
 
 
@@ -250,6 +264,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_embed_tokens.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.dicow_advance.argtypes = [vp, vp, C.c_int, vp]
     lib.dicow_logits_rules_argmax.argtypes = [vp, C.POINTER(LogitsRulesArgs), vp]
+    lib.dicow_ctc_joint_step.argtypes = [vp, C.POINTER(CtcJointArgs), vp]
+    lib.dicow_log_softmax_rows.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp]
     lib.dicow_softlabel_ce.argtypes = [vp, C.POINTER(SoftlabelCeArgs), vp]
     lib.dicow_ctc_loss.argtypes = [vp, C.POINTER(CtcLossArgs), vp]
     for name in EXPORTED_SYMBOLS:
@@ -266,7 +282,8 @@ EXPORTED_SYMBOLS = [
     "dicow_gemm_skinny_bf16", "dicow_decode_attention_bf16", "dicow_embed_tokens", "dicow_advance",
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
-    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major",
+    "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
+    "dicow_log_softmax_rows",
 ]
 
 

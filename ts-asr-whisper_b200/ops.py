@@ -394,9 +394,10 @@ def logits_rules_argmax(logits: torch.Tensor, ids: torch.Tensor, unfinished: tor
                         pad: int, no_timestamps: int, ts_begin: int, cur_len: int = 0,
                         pos: Optional[torch.Tensor] = None, max_initial_timestamp_index: Optional[int] = None,
                         suppress_bitmap: Optional[torch.Tensor] = None,
-                        processed_scores: Optional[torch.Tensor] = None, timestamp_rules: bool = True) -> None:
+                        processed_scores: Optional[torch.Tensor] = None, timestamp_rules: bool = True,
+                        no_select: bool = False) -> None:
     """suppress + Whisper timestamp rules + DiCoW EOS exception + argmax; appends the token to ``ids`` in place
-    (dicow_logits_rules_argmax)."""
+    (dicow_logits_rules_argmax).  ``no_select``: only write ``processed_scores`` (joint CTC decoding selects later)."""
     dev = _require_cuda(logits, ids, unfinished, pos, suppress_bitmap, processed_scores)
     assert logits.dtype == torch.float32 and logits.stride(1) == 1 and ids.dtype == torch.int64
     assert unfinished.dtype == torch.int32
@@ -412,7 +413,65 @@ def logits_rules_argmax(logits: torch.Tensor, ids: torch.Tensor, unfinished: tor
     a.suppress_bitmap = _ptr(suppress_bitmap)
     a.unfinished = _ptr(unfinished)
     a.processed_scores = _ptr(processed_scores)
+    a.no_select = 1 if no_select else 0
     _call("dicow_logits_rules_argmax", dev, a, "logits_rules")
+
+
+class CtcJointState:
+    """Device buffers of joint CTC / attention decoding for one batch of hypotheses (dicow_ctc_joint_step):
+    the window's CTC log-posteriors, the forward variables / prefix score of every hypothesis, candidate workspaces."""
+
+    def __init__(self, ctc_logits: torch.Tensor, top_k: int = 500, upper_cased: Optional[dict] = None):
+        global launch_count
+        assert ctc_logits.dim() == 3 and ctc_logits.dtype == torch.float32 and ctc_logits.is_contiguous()
+        dev = _require_cuda(ctc_logits)
+        B, T, V1 = ctc_logits.shape
+        self.B, self.T, self.V1, self.K = B, T, V1, top_k
+        self.logp = torch.empty_like(ctc_logits)
+        h = _lib.handle(dev.index or 0)
+        with torch.cuda.device(dev):
+            rc = _lib.load_library().dicow_log_softmax_rows(h, _ptr(ctc_logits), _ptr(self.logp), B * T, V1, _stream(dev))
+        _lib.check(rc, h, "dicow_log_softmax_rows")
+        launch_count += 1
+        if upper_cased:  # decoding.py:183-186: an upper-cased token shares its lower-cased twin's posterior (column copy)
+            lo = torch.tensor(list(upper_cased.keys()), device=dev)
+            up = torch.tensor(list(upper_cased.values()), device=dev)
+            self.logp[..., up] = self.logp[..., lo]
+        # decoding.py:37-44: r[:, 0] = LOGZERO, r[:, 1] = running sum of the blank log-posteriors, score 0
+        self.r_prev = torch.full((B, T, 2), -1e10, dtype=torch.float32, device=dev)
+        self.r_prev[:, :, 1] = torch.cumsum(self.logp[:, :, V1 - 1], dim=1)
+        self.score_prev = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.states = torch.empty(B, T, 2, top_k, dtype=torch.float32, device=dev)
+        self.ws_i32 = torch.zeros(4 * B + 4 + B * top_k, dtype=torch.int32, device=dev)
+        self.ws_f32 = torch.zeros(B + 2 * B * top_k, dtype=torch.float32, device=dev)
+
+    @property
+    def candidates(self) -> torch.Tensor:
+        return self.ws_i32[4 * self.B + 4:].view(self.B, self.K)
+
+    @property
+    def prefix_scores(self) -> torch.Tensor:
+        return self.ws_f32[self.B + self.B * self.K:].view(self.B, self.K)
+
+
+def ctc_joint_step(state: CtcJointState, processed_scores: torch.Tensor, ids: torch.Tensor, unfinished: torch.Tensor, *,
+                   bos: int, eos: int, pad: int, first_timestamp: int, prefix_len: int, ctc_weight: float,
+                   cur_len: int = 0, pos: Optional[torch.Tensor] = None) -> None:
+    """one token of joint CTC / attention greedy decoding for every hypothesis (dicow_ctc_joint_step): appends the token
+    to ``ids`` in place, updates ``unfinished`` and the CTC state."""
+    dev = _require_cuda(processed_scores, ids, unfinished, pos, state.logp)
+    assert processed_scores.dtype == torch.float32 and processed_scores.is_contiguous() and ids.dtype == torch.int64
+    assert unfinished.dtype == torch.int32 and processed_scores.shape[0] == state.B
+    a = _lib.CtcJointArgs()
+    a.struct_size = C.sizeof(_lib.CtcJointArgs)
+    a.ids, a.ids_row_stride, a.pos, a.cur_len = _ptr(ids), ids.stride(0), _ptr(pos), cur_len
+    a.B, a.V, a.T, a.V1, a.K = state.B, processed_scores.shape[1], state.T, state.V1, state.K
+    a.bos, a.eos, a.pad, a.blank, a.first_timestamp, a.prefix_len = bos, eos, pad, state.V1 - 1, first_timestamp, prefix_len
+    a.ctc_weight = ctc_weight
+    a.ctc_logp, a.processed_scores = _ptr(state.logp), _ptr(processed_scores)
+    a.workspace_i32, a.workspace_f32, a.states = _ptr(state.ws_i32), _ptr(state.ws_f32), _ptr(state.states)
+    a.r_prev, a.score_prev, a.unfinished = _ptr(state.r_prev), _ptr(state.score_prev), _ptr(unfinished)
+    _call("dicow_ctc_joint_step", dev, a, "ctc_joint")
 
 
 def suppress_bitmap(token_ids, vocab: int, device) -> torch.Tensor:
