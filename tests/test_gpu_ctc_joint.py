@@ -99,3 +99,72 @@ def test_joint_step_matches_oracle_at_whisper_sizes(ops):
             np.testing.assert_allclose(st.score_prev[b].item(), float(resc.score_prev[b]), rtol=1e-3, atol=1e-2)
             np.testing.assert_allclose(st.r_prev[b].cpu().numpy(), resc.r_prev[b].numpy(), rtol=1e-3, atol=1e-2)
         ids_ref = torch.cat([ids_ref, ref_tok[:, None]], dim=1)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_joint_ctc_greedy_decode_matches_oracle(graphs):
+    """greedy_decode_window(ctc=...) on the miniature model: decoder step + suppress / timestamp rules + log-softmax + CTC
+    rescoring + argmax + update_state per token (generation.py:728-769 with generation_config.ctc_weight > 0), against the
+    same loop built from the oracle's pieces.  Token identity; a divergence is tolerated only where the oracle's own
+    top-2 margin of the combined score is below MARGIN (bf16 decoder vs fp32 oracle)."""
+    import test_gpu_decoder as tgd
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    import torch.nn.functional as F
+    dm = synth.GOLDEN_MINI
+    dmp = synth.Dims(**{**dm.__dict__, "use_enrollments": False, "scb_layers": 0})
+    model, p = tgd.build_model(dmp)
+    model.use_cuda_graphs = graphs
+    feats = torch.from_numpy(synth.make_features("g0", 2, dm.n_mels, 2 * dm.T))
+    stno = torch.from_numpy(synth.make_stno("g0", 2, dm.T, "soft", pad_tail=7))
+    W, K, NEW = 0.3, 40, 20
+    prompt = torch.tensor([[tgd.SOT, tgd.LANG, tgd.TASK]] * 2)
+    enc_mod = model.get_encoder()
+    hidden = enc_mod(feats.to(DEV), stno_mask=stno.to(DEV)).last_hidden_state
+    ctc_logits = model.get_enc_logits(hidden)
+    rules = dict(eos=tgd.EOS, pad=tgd.EOS, no_timestamps=tgd.NOTS, ts_begin=tgd.TS_BEGIN, max_initial_timestamp_index=None,
+                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap(tgd.SUPPRESS, torch.device(DEV)))
+    ctc = {"logits": ctc_logits, "weight": W, "prefix_len": 3, "bos": tgd.SOT, "top_k": K}
+    ids = model.greedy_decode_window(hidden, prompt.to(DEV), 3 + NEW, rules, ctc=ctc)
+    ids2 = model.greedy_decode_window(hidden, prompt.to(DEV), 3 + NEW, rules, ctc=ctc)  # buffers / graphs reused
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids2)
+    ids = ids.cpu()
+    # ---- the same loop from the oracle's pieces ----
+    with torch.no_grad():
+        ref_enc = orc.encoder_forward(p, dmp, feats, stno)
+        ref_ctc = orc.ctc_logits(p, dmp, ref_enc)
+        err = ((ctc_logits.cpu() - ref_ctc).abs().max() / ref_ctc.abs().max()).item()
+        assert err < 2e-2
+        resc = cp.JointCtcRescorer(ref_ctc, blank=dmp.vocab, eos=tgd.EOS, bos=tgd.SOT, prefix_len=3,
+                                   first_timestamp=tgd.TS_BEGIN, ctc_weight=W, top_k=K)
+        ref_ids = prompt.clone()
+        unfinished = torch.ones(2, dtype=torch.long)
+        sup = torch.tensor(tgd.SUPPRESS)
+        n_same, diverged = 0, [False, False]
+        for step in range(NEW):
+            hid = orc.decoder_forward(p, dmp, ref_ids, ref_enc)
+            logits = F.linear(hid[:, -1], p["proj_out.weight"]).float()
+            logits[:, sup] = -float("inf")
+            logits = orc.timestamp_rules(ref_ids, logits, begin_index=3, eos=tgd.EOS, no_timestamps=tgd.NOTS,
+                                         ts_begin=tgd.TS_BEGIN)
+            comb = resc(ref_ids, torch.log_softmax(logits, dim=-1))
+            tok = torch.argmax(comb, dim=-1)
+            tok = tok * unfinished + tgd.EOS * (1 - unfinished)
+            for b in range(2):
+                if diverged[b] or 3 + step >= ids.shape[1]:
+                    continue
+                got = int(ids[b, 3 + step])
+                if got == int(tok[b]):
+                    n_same += 1
+                    continue
+                margin = float(comb[b, int(tok[b])] - comb[b, got])
+                assert margin < tgd.MARGIN, f"row {b} step {step}: token {got} vs {int(tok[b])}, margin {margin:.3f}"
+                diverged[b] = True  # after a tolerated near-tie flip the continuations legitimately differ
+            resc.update_state(tok)
+            ref_ids = torch.cat([ref_ids, tok[:, None]], dim=1)
+            unfinished = unfinished & (tok != tgd.EOS).long()
+            if int(unfinished.max()) == 0:
+                break
+    print("joint greedy ids (cuda):", ids.tolist(), "\n                (oracle):", ref_ids.tolist())
+    assert n_same >= 12, "too few compared tokens for the check to mean anything"

@@ -241,6 +241,9 @@ class _GreedyState:
         self.cross_kv = torch.empty(L, B, cfg.decoder_attention_heads, T, 128, **bf)
         self.cross_kv_rows = torch.empty(B * T, 2 * d, **bf)  # the projection GEMM's output before the re-layout
         self.logits = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
+        self.ctc = None      # ops.CtcJointState of joint CTC / attention decoding (allocated on first use)
+        self.ctc_key = None
+        self.proc = None     # [B, V] processed scores handed from the rules kernel to the joint CTC step
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.weights_id = None  # id() of the prepared-weight dict the graphs were captured with
 
@@ -452,8 +455,23 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             ops.decode_linear(e["w2"], st.x, A=st.h, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=st.x)
         if sample:
             ln_linear(w["proj"], st.logits, w["lnf_g"], w["lnf_b"], epilogue=ops.EPI_BIAS_F32)
-            ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **gen)
+            self._select_token(st, gen)
         ops.advance(st.pos, 1)
+
+    def _select_token(self, st: _GreedyState, gen: dict) -> None:
+        """logits -> next token of every row.  Attention-only greedy: the fused rules + argmax kernel.  Joint CTC /
+        attention (generation_config.ctc_weight > 0; generation.py:250-268): the rules kernel only materialises the
+        processed scores, the CTC step log-softmaxes them, scores the top-k candidates' prefixes and selects."""
+        ctc = gen.get("ctc")
+        rules = {k: v for k, v in gen.items() if k != "ctc"}
+        if ctc is None:
+            ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **rules)
+            return
+        ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, processed_scores=st.proc, no_select=True,
+                                **rules)
+        ops.ctc_joint_step(st.ctc, st.proc, st.ids, st.unfinished, pos=st.pos, bos=ctc["bos"], eos=rules["eos"],
+                           pad=rules["pad"], first_timestamp=rules["ts_begin"], prefix_len=ctc["prefix_len"],
+                           ctc_weight=ctc["weight"])
 
     def _decode_step_unfused(self, st: _GreedyState, w: dict, sample: bool, gen: dict) -> None:
         """the same step with one kernel per operation (LayerNorm, q, k|v, ... 13 per layer): kept as the comparison
@@ -483,15 +501,16 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         if sample:
             ops.fddt_layernorm(st.x, gamma=w["lnf_g"], beta=w["lnf_b"], ln_out_bf16=st.ln)
             ops.gemm_skinny(st.ln, w["proj"], st.logits, epilogue=ops.EPI_BIAS_F32)
-            ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **gen)
+            self._select_token(st, gen)
         ops.advance(st.pos, 1)
 
     @torch.no_grad()
     def greedy_decode_window(self, enc_hidden: torch.Tensor, prompt: torch.Tensor, max_total_len: int, gen: dict,
-                             return_first_logits: bool = False):
+                             return_first_logits: bool = False, ctc: Optional[dict] = None):
         """Greedy branch of DiCoWGenerationMixin._sample (generation.py:707-782) for one batch of 30 s windows.
         enc_hidden [B, T, d] (fp32 or bf16), prompt int64 [B, P] (forced init tokens).  Returns int64 ids [B, n] on
-        the device (prompt + generated, finished rows padded)."""
+        the device (prompt + generated, finished rows padded).  ``ctc`` = {"logits": fp32 [B, T', V + 1] CTC logits of the
+        window, "weight", "prefix_len", "bos", "top_k", "upper_cased"} switches to joint CTC / attention selection."""
         cfg = self.config
         dev = enc_hidden.device
         B, T, d = enc_hidden.shape
@@ -518,13 +537,26 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         st.pos.zero_()
         st.unfinished.fill_(1)
         gen = dict(gen, begin_index=P)
+        if ctc is not None:
+            lg = ctc["logits"].float().contiguous()
+            ckey = (tuple(lg.shape), int(ctc.get("top_k", 500)), tuple(sorted((ctc.get("upper_cased") or {}).items())))
+            if st.ctc is None or st.ctc_key != ckey:  # buffers are kept across windows: captured graphs hold their pointers
+                st.ctc = ops.CtcJointState(lg, top_k=ckey[1], upper_cased=ctc.get("upper_cased"))
+                st.ctc_key = ckey
+                st.proc = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
+                st.graphs.clear()
+            else:
+                st.ctc.reset(lg)
+            gen["ctc"] = {"bos": int(ctc["bos"]), "prefix_len": int(ctc["prefix_len"]), "weight": float(ctc["weight"]),
+                          "state": id(st.ctc)}
 
         def run(sample: bool):
             if not self.use_cuda_graphs:
                 self._decode_step(st, w, sample, gen)
                 return
-            gkey = (sample, P, self.fused_decode_step, tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
-                                            for k, v in gen.items())))
+            gkey = (sample, P, self.fused_decode_step,
+                    tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else
+                                  (tuple(sorted(v.items())) if isinstance(v, dict) else v)) for k, v in gen.items())))
             g = st.graphs.get(gkey)
             if g is None:
                 # warm-up launch outside capture (kernel attributes, lazy module load), then restore the state it touched
@@ -575,8 +607,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         num_beams = get("num_beams", 1)
         if num_beams != 1:
             raise NotImplementedError("beam search is a SURVEY section 8f 'next' row; the B200 path decodes greedily")
-        if (get("ctc_weight", 0) or 0) > 0:
-            raise NotImplementedError("joint CTC/attention decoding is a SURVEY section 8f 'next' row")
+        ctc_weight = float(get("ctc_weight", 0) or 0)
         if get("do_sample", False):
             raise ValueError("Provided generation mode is not supported (greedy only)")
         ts_begin = get("no_timestamps_token_id")
@@ -590,7 +621,8 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 "return_timestamps": bool(get("return_timestamps", True)),
                 "max_initial_timestamp_index": get("max_initial_timestamp_index"),
                 "max_new_tokens": get("max_new_tokens"), "max_length": get("max_length", self.config.max_target_positions),
-                "forced_decoder_ids": get("forced_decoder_ids")}
+                "forced_decoder_ids": get("forced_decoder_ids"), "ctc_weight": ctc_weight,
+                "ctc_tokens_to_score": int(get("ctc_tokens_to_score", 500) or 500)}
 
     @torch.no_grad()
     def generate(self, input_features: Optional[torch.Tensor] = None, generation_config=None,
@@ -680,8 +712,19 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 idx = torch.as_tensor(batch_idx_map, device=dev)
                 enr = {k: v[idx] for k, v in enrollments.items()}
             hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr).last_hidden_state
+            ctc = None
+            if gs["ctc_weight"] > 0:  # generation.py:49-51, 250-268: the encoder's CTC posteriors rescore every step
+                if not hasattr(enc, "lm_head"):
+                    raise ValueError("generation_config.ctc_weight > 0 needs an encoder with a CTC head (config.ctc_weight > 0)")
+                Bw, Tw, _ = hidden.shape
+                self.encoder_logits = enc.ctc_logits_from_hidden(ops.cast_bf16(hidden.float()), Bw, Tw)
+                tok = self.tokenizer
+                ctc = {"logits": self.encoder_logits, "weight": gs["ctc_weight"], "top_k": gs["ctc_tokens_to_score"],
+                       "bos": cfg.decoder_start_token_id,
+                       "prefix_len": len(tok.prefix_tokens) if tok is not None else P,
+                       "upper_cased": dict(getattr(tok, "upper_cased_tokens", None) or {}) if tok is not None else None}
             ids = self.greedy_decode_window(hidden, init_tokens[torch.as_tensor(batch_idx_map, device=dev)], max_total,
-                                            rules)
+                                            rules, ctc=ctc)
             self.stno_mask_seek = None
             ids_host = ids.cpu()
             for i, prev in enumerate(batch_idx_map):

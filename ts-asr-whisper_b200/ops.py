@@ -422,28 +422,38 @@ class CtcJointState:
     the window's CTC log-posteriors, the forward variables / prefix score of every hypothesis, candidate workspaces."""
 
     def __init__(self, ctc_logits: torch.Tensor, top_k: int = 500, upper_cased: Optional[dict] = None):
-        global launch_count
-        assert ctc_logits.dim() == 3 and ctc_logits.dtype == torch.float32 and ctc_logits.is_contiguous()
+        assert ctc_logits.dim() == 3 and ctc_logits.dtype == torch.float32
         dev = _require_cuda(ctc_logits)
         B, T, V1 = ctc_logits.shape
         self.B, self.T, self.V1, self.K = B, T, V1, top_k
-        self.logp = torch.empty_like(ctc_logits)
-        h = _lib.handle(dev.index or 0)
-        with torch.cuda.device(dev):
-            rc = _lib.load_library().dicow_log_softmax_rows(h, _ptr(ctc_logits), _ptr(self.logp), B * T, V1, _stream(dev))
-        _lib.check(rc, h, "dicow_log_softmax_rows")
-        launch_count += 1
-        if upper_cased:  # decoding.py:183-186: an upper-cased token shares its lower-cased twin's posterior (column copy)
-            lo = torch.tensor(list(upper_cased.keys()), device=dev)
-            up = torch.tensor(list(upper_cased.values()), device=dev)
-            self.logp[..., up] = self.logp[..., lo]
-        # decoding.py:37-44: r[:, 0] = LOGZERO, r[:, 1] = running sum of the blank log-posteriors, score 0
-        self.r_prev = torch.full((B, T, 2), -1e10, dtype=torch.float32, device=dev)
-        self.r_prev[:, :, 1] = torch.cumsum(self.logp[:, :, V1 - 1], dim=1)
-        self.score_prev = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.logp = torch.empty(B, T, V1, dtype=torch.float32, device=dev)
+        self.r_prev = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
+        self.score_prev = torch.empty(B, dtype=torch.float32, device=dev)
         self.states = torch.empty(B, T, 2, top_k, dtype=torch.float32, device=dev)
         self.ws_i32 = torch.zeros(4 * B + 4 + B * top_k, dtype=torch.int32, device=dev)
         self.ws_f32 = torch.zeros(B + 2 * B * top_k, dtype=torch.float32, device=dev)
+        self._upper = None
+        if upper_cased:  # decoding.py:183-186: an upper-cased token shares its lower-cased twin's posterior (column copy)
+            self._upper = (torch.tensor(list(upper_cased.keys()), device=dev), torch.tensor(list(upper_cased.values()), device=dev))
+        self.reset(ctc_logits)
+
+    def reset(self, ctc_logits: torch.Tensor) -> None:
+        """start a new window in the SAME buffers (captured CUDA graphs keep their pointers): posteriors of the window,
+        initial forward variables r = (LOGZERO, running sum of the blank log-posteriors), score 0 (decoding.py:37-44,185)"""
+        global launch_count
+        assert tuple(ctc_logits.shape) == (self.B, self.T, self.V1) and ctc_logits.is_contiguous()
+        dev = ctc_logits.device
+        h = _lib.handle(dev.index or 0)
+        with torch.cuda.device(dev):
+            rc = _lib.load_library().dicow_log_softmax_rows(h, _ptr(ctc_logits), _ptr(self.logp), self.B * self.T, self.V1,
+                                                            _stream(dev))
+        _lib.check(rc, h, "dicow_log_softmax_rows")
+        launch_count += 1
+        if self._upper is not None:
+            self.logp[..., self._upper[1]] = self.logp[..., self._upper[0]]
+        self.r_prev[:, :, 0] = -1e10
+        self.r_prev[:, :, 1] = torch.cumsum(self.logp[:, :, self.V1 - 1], dim=1)
+        self.score_prev.zero_()
 
     @property
     def candidates(self) -> torch.Tensor:
