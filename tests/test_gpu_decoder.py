@@ -473,3 +473,30 @@ def test_generate_long_form_runs_and_segments(mini):
     seqs = model.generate(long_feats.to(DEV), attention_mask=attn.to(DEV), stno_mask=long_stno.to(DEV),
                           forced_decoder_ids=torch.tensor([[SOT, LANG, TASK]] * 2))
     assert torch.equal(seqs, out["sequences"])
+
+
+def test_generate_joint_ctc_long_form(mini):
+    """generate(ctc_weight > 0): the long-form seek loop with joint CTC / attention selection per window (encoder CTC
+    logits -> rescoring inside the CUDA-graphed step); shrinking batch (second recording shorter) re-allocates the CTC state"""
+    g, dmp, model, p, feats, stno = mini
+    model.tokenizer, model.soft_label_creator = None, None
+    F2 = 2 * dmp.T
+    long_feats = torch.cat([feats, torch.from_numpy(synth.make_features("g1", 2, dmp.n_mels, F2))], dim=-1)
+    long_stno = torch.cat([stno, torch.from_numpy(synth.make_stno("g1", 2, dmp.T, "hard"))], dim=-1)
+    attn = torch.ones(2, 2 * F2, dtype=torch.long)
+    attn[1, F2 + 31:] = 0
+    gc = model.generation_config
+    gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = NOTS, EOS, EOS
+    gc.suppress_tokens, gc.return_timestamps, gc.max_new_tokens, gc.num_beams = SUPPRESS, True, 24, 1
+    kw = dict(attention_mask=attn.to(DEV), stno_mask=long_stno.to(DEV), forced_decoder_ids=torch.tensor([[SOT, LANG, TASK]] * 2),
+              return_segments=True)
+    plain = model.generate(long_feats.to(DEV), **kw)
+    joint = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, **kw)
+    again = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, **kw)
+    assert torch.equal(joint["sequences"], again["sequences"])
+    assert model.encoder_logits is None  # generation.py:559
+    assert joint["sequences"].shape[0] == 2
+    # the CTC evidence changes what is decoded on this model (attention alone repeats one token until max_new_tokens)
+    assert not torch.equal(joint["sequences"], plain["sequences"])
+    with pytest.raises(NotImplementedError):
+        model.generate(long_feats.to(DEV), ctc_weight=0.3, num_beams=5, **kw)

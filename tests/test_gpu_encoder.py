@@ -33,6 +33,8 @@ CASES = {
     "tiny": (synth.WHISPER_TINY, 2, False),
     # large-v3-turbo dims, 2 layers (full-depth runs are covered by bench.py / smoke at B200 sizes)
     "turbo2": (dataclasses.replace(synth.LARGE_V3_TURBO, enc_layers=2, vocab=2047), 1, False),
+    # BASELINE configs[1] at full depth: large-v3-turbo, 32 layers, 30 s windows (small vocabulary for the CTC head only)
+    "turbo32": (dataclasses.replace(synth.LARGE_V3_TURBO, vocab=2047), 2, False),
     # SE-DiCoW: enrollment stream + 2 SCB layers, tiny dims
     "tiny_se": (dataclasses.replace(synth.WHISPER_TINY, use_enrollments=True, scb_layers=2, vocab=1000), 2, True),
     # the golden miniature (odd T, every feature on)

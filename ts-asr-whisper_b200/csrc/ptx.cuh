@@ -393,6 +393,27 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// tcgen05.wait::ld that also names the destination registers of the loads it completes: the compiler cannot move a use
+// of r above the wait (the loads are asynchronous; their asm statement only "defines" r formally)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// mbarrier arrive without release semantics: handing a TMEM accumulator back to the MMA warp only has to follow the
+// completed tcgen05.ld (tcgen05.wait::ld + fence::before_thread_sync); a release arrive additionally waits until the
+// epilogue's global STORES are visible (MEMBAR + ERRBAR: 11 % of the stall samples of the GELU GEMM, ncu r01)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // CTA pairs (cluster of 2, tcgen05 cta_group::2): both SMs execute one M=256 MMA; each CTA stages its own 128 rows of A
 // and half of the B tile, so the L2 -> SM operand traffic per FLOP drops by a third against two independent 128-row CTAs.
