@@ -12,6 +12,8 @@
 // Replaces nn.Linear / nn.Conv1d calls of the reference (see include/dicow_b200.h for the call-site list).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -42,6 +44,7 @@ struct GemmParams {
   const float* fddt_b;
   const float* pos;
   __nv_bfloat16* aux;  // [.., N] bf16, leading dimension ldo: pre-activation saved by GELU_SAVE / read by DGELU
+  int serial_drain;    // 1 (default): one chunk at a time, accumulator handed back after the last store; 0: pipelined
 };
 
 template <int BN>
@@ -210,6 +213,23 @@ __device__ __forceinline__ void drain_accumulator(const GemmParams& p, uint32_t 
   int nvalid = (p.N - n_base + 31) / 32;  // warp-uniform
   nvalid = nvalid > NCH ? NCH : nvalid;
   if (nvalid <= 0) {
+    release();
+    return;
+  }
+  if (p.serial_drain) {  // default (see dicow_gemm_bf16): one chunk at a time
+#pragma unroll 1
+    for (int c = 0; c < nvalid; ++c) {
+      uint32_t r1[32];
+      tmem_ld_x32(taddr + c * 32, r1);
+      tmem_ld_wait_regs(r1);
+      if (row_ok) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+        epilogue_chunk<EPI>(p, v, b, m, n_base + c * 32, min(32, p.N - n_base - c * 32), mask);
+      }
+    }
+    __threadfence_block();
     release();
     return;
   }
@@ -727,6 +747,14 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   p.resid = a->resid, p.ldr = a->ldr, p.resid_bs = a->resid_batch_stride, p.gate = a->gate;
   p.stno = a->stno, p.stno_bs = a->stno_batch_stride, p.fddt_w = a->fddt_w, p.fddt_b = a->fddt_b, p.pos = a->pos;
   p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux_bf16);
+  // default: the serial drain.  A/B on one box, interleaved, 3 runs each (tools/gpu_ab.sh): serial 398.9 / 402.6 / 405.2
+  // utt/s (GEMM family 47.8 / 47.3 / 47.0 ms per step), pipelined 395.8 / 399.0 / 398.3 (48.7 / 48.4 / 48.4 ms) -- the
+  // step is power-capped, the pipelined schedule removes stalls but not energy and runs 2.5 % slower.
+  static const int serial_drain = [] {
+    const char* e = getenv("DICOW_GEMM_PIPELINED_DRAIN");
+    return (e != nullptr && e[0] == '1') ? 0 : 1;
+  }();
+  p.serial_drain = serial_drain;
   const bool out_is_bf16 = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16 ||
                            a->epilogue == DICOW_EPI_GELU_SAVE_BF16 || a->epilogue == DICOW_EPI_DGELU_BF16;
   if (a->epilogue == DICOW_EPI_GELU_SAVE_BF16 || a->epilogue == DICOW_EPI_DGELU_BF16)
