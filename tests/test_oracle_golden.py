@@ -162,3 +162,30 @@ def test_joint_ctc_rescorer_matches_reference_steps():
         unfinished = unfinished & (tok != EOS).long()
     assert ids.tolist() == g["ids"].tolist()
     assert n_text >= 8 and int(unfinished.sum()) < B  # text tokens moved the state; a row finished
+
+
+# ---- beam search bookkeeping: oracle/beam_search.py vs the HF helper methods the reference's
+# ---- _beam_search override calls (tests/golden/make_golden_beam.py) ----------------------------------------------------
+@pytest.mark.parametrize("case,lp,early", [("lp1_noearly", 1.0, False), ("lp01_early", 0.1, True), ("lp0_never", 0.0, "never")])
+def test_beam_search_bookkeeping_matches_hf_helpers(case, lp, early):
+    from oracle import beam_search as obs
+    g = np.load(os.path.join(GOLD, "beam_search.npz"))
+    V, EOS, U, K, P, MAXLEN = [int(v) for v in g["meta"]]
+    bs = obs.BeamSearch([[9, 10, 11]] * U, K, eos=EOS, pad=EOS, max_length=MAXLEN, length_penalty=lp, early_stopping=early)
+    steps = int(g[f"{case}/steps"])
+    for step in range(steps):
+        toks, parents = bs.step(torch.from_numpy(g[f"{case}/lp_{step}"]))
+        if not all(all(h) for h in bs.last_hits):
+            # (when EVERY continuation hit the length limit all running scores collapse to -1e9 in fp32: torch.topk's
+            # order among those ties is unspecified and the running beams are not used any more)
+            assert toks.tolist() == g[f"{case}/tok_{step}"].tolist(), f"step {step}"
+            assert parents.tolist() == g[f"{case}/parent_{step}"].tolist(), f"step {step}"
+        np.testing.assert_allclose(np.array(bs.run_score, dtype=np.float32), g[f"{case}/run_score_{step}"], rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(np.array(bs.fin_score, dtype=np.float32), g[f"{case}/fin_score_{step}"], rtol=1e-6, atol=1e-5)
+        assert np.array(bs.fin_flag).tolist() == g[f"{case}/fin_flag_{step}"].tolist()
+        assert [[u] for u in bs.unsat] == g[f"{case}/unsat_{step}"].tolist()
+        assert bs.unfinished() == (step < steps - 1), f"loop condition at step {step}"
+    best = g[f"{case}/best"]
+    for u in range(U):
+        seq = bs.best()[u]
+        assert seq == best[u, :len(seq)].tolist() and all(int(t) == EOS for t in best[u, len(seq):])
