@@ -411,6 +411,11 @@ typedef struct {
   int32_t B, H, Tk;
   const int32_t* pos;
   int64_t kv_head_stride; /* elements between heads; 0 = 64 (heads adjacent inside a row) */
+  int32_t kv_batch_div;   /* > 1: K/V batch index = query row / kv_batch_div (the beams of an utterance share its cross K/V) */
+  const int32_t* ancestry; /* optional [B, ancestry_stride]: key t of query row b is read from cache row ancestry[b][t] --
+                              beam search keeps every hypothesis' K/V where it was computed and only re-links prefixes
+                              (replaces past_key_values.reorder_cache(beam_idx), src/models/dicow/generation.py:1080-1085) */
+  int64_t ancestry_stride;
 } dicow_decode_attention_args_t;
 DICOW_API int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_attention_args_t* args, void* stream);
 
@@ -483,8 +488,55 @@ typedef struct {
   float* r_prev;
   float* score_prev;
   int32_t* unfinished;
+  const float* raw_logits; /* optional [B, V]: the log-softmax normaliser is taken over these (beam search applies
+                              log_softmax BEFORE the processors, generation.py:1003-1004) instead of over processed_scores */
+  int32_t score_only;      /* 1: stop after the prefix scores (no selection / state update): beam search selects across
+                              the beams of an utterance (dicow_beam_step) */
 } dicow_ctc_joint_args_t;
 DICOW_API int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args_t* args, void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Beam search, one step for U utterances x NB beams (rows r = u * NB + k), on the device.  Replaces the bookkeeping of
+ * DiCoWGenerationMixin._beam_search (src/models/dicow/generation.py:992-1107 = HF GenerationMixin._beam_search with the
+ * CTC hook): accumulated score = (1 - w) log-prob + w (ctc - ctc_prev) + running beam score over the candidates of every
+ * beam (the top-K text ids scored by dicow_ctc_joint_step(score_only) + all timestamp ids), top-2NB continuations,
+ * EOS / max_length hits, next running beams, finished set with length penalty, early-stop heuristic, then the re-linking
+ * of token sequences, self-attention ancestry and CTC states to the chosen parents (update_state, generation.py:1087-1088).
+ * flags[u] = {any continuation without a hit, all finished slots full, early-stop heuristic unsatisfied}: the caller ends
+ * the loop when HF's _beam_search_has_unfinished_sequences over all utterances turns false.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  size_t struct_size;
+  int32_t U, NB, V, K;
+  const float* processed_scores; /* [U NB, V] */
+  const int32_t* joint_workspace_i32; /* of dicow_ctc_joint_step(score_only): candidates */
+  const float* joint_workspace_f32;   /* lse, attention log-probs and prefix scores of the candidates */
+  float ctc_weight;                   /* 0: attention-only beam search */
+  const float* ctc_states;            /* [U NB, T, 2, K] (ctc_weight > 0) */
+  float* ctc_r_prev;                  /* [U NB, T, 2] */
+  float* ctc_score_prev;              /* [U NB] */
+  float* ctc_r_tmp;                   /* scratch like ctc_r_prev */
+  int32_t T;
+  float* run_score;  /* [U NB] running beam scores (first beam 0, others -1e9 at start) */
+  float* fin_score;  /* [U NB] (-1e9 at start) */
+  int32_t* fin_flag; /* [U NB] */
+  int32_t* unsat;    /* [U] (1 at start) */
+  int64_t* ids;      /* [U NB, ids_row_stride] running sequences */
+  int64_t* fin_ids;  /* [U NB, ids_row_stride] finished sequences */
+  int64_t* ids_tmp;  /* scratch [2 U NB, ids_row_stride] */
+  int64_t ids_row_stride;
+  int32_t* ancestry;     /* [U NB, ancestry_stride] */
+  int32_t* ancestry_tmp; /* scratch */
+  int64_t ancestry_stride;
+  const int32_t* pos; /* device scalar: the sequences hold *pos + 1 tokens */
+  int32_t eos, pad, first_timestamp, max_length, prompt_len;
+  float length_penalty;
+  int32_t early_stopping; /* 0 = False, 1 = True, 2 = "never" */
+  int32_t* scratch_i32;   /* 3 U NB ints */
+  float* scratch_f32;     /* 2 U NB floats */
+  int32_t* flags;         /* [U, 4] */
+} dicow_beam_step_args_t;
+DICOW_API int dicow_beam_step(dicow_handle_t h, const dicow_beam_step_args_t* args, void* stream);
+
 /* out[r, :] = in[r, :] - logsumexp(in[r, :]) over V columns (in place allowed) */
 DICOW_API int dicow_log_softmax_rows(dicow_handle_t h, const float* in, float* out, int64_t rows, int V, void* stream);
 

@@ -498,5 +498,6 @@ def test_generate_joint_ctc_long_form(mini):
     assert joint["sequences"].shape[0] == 2
     # the CTC evidence changes what is decoded on this model (attention alone repeats one token until max_new_tokens)
     assert not torch.equal(joint["sequences"], plain["sequences"])
-    with pytest.raises(NotImplementedError):
-        model.generate(long_feats.to(DEV), ctc_weight=0.3, num_beams=5, **kw)
+    beams = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, num_beams=3, length_penalty=0.1, **kw)
+    beams2 = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, num_beams=3, length_penalty=0.1, **kw)
+    assert beams["sequences"].shape[0] == 2 and torch.equal(beams["sequences"], beams2["sequences"])

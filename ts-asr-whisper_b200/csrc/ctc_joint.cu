@@ -51,6 +51,7 @@ struct CtcJointParams {
   float w;
   const float* x;          // [B, T, V1] CTC log-posteriors of the window
   const float* proc;       // [B, V] attention scores after the other logits processors (-inf = masked)
+  const float* raw;        // optional [B, V]: rows the log-softmax normaliser is taken over (NULL: proc)
   int* meta;               // [B, 4]: decoded_len, last label, to_be_decoded, unused;  meta[4 * B] = loop start
   float* lse;              // [B] log-sum-exp of the processed attention scores
   int* cs;                 // [B, K] candidate ids
@@ -113,10 +114,12 @@ __global__ void __launch_bounds__(TK_THREADS) ctc_topk_kernel(const CtcJointPara
   __shared__ int s_has_eos;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* row = p.proc + (long long)b * p.V;
-  // ---- log-sum-exp of the whole row (LogSoftmaxProcessor, generation.py:252) ----
+  const float* nrow = p.raw != nullptr ? p.raw + (long long)b * p.V : row;
+  // ---- log-sum-exp of the whole row (greedy: LogSoftmaxProcessor after the other processors, generation.py:252;
+  // ---- beam search: log_softmax of the raw logits before them, generation.py:1003) ----
   float m = -INFINITY, s = 0.f;
   for (int v = tid; v < p.V; v += TK_THREADS) {
-    const float x = row[v];
+    const float x = nrow[v];
     if (x > -INFINITY) {
       const float mn = fmaxf(m, x);
       s = s * __expf(m - mn) + __expf(x - mn);
@@ -410,11 +413,12 @@ extern "C" int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;
   dicow_ctx* ctx = h;
   DICOW_REQUIRE(ctx, a != nullptr && a->struct_size == sizeof(dicow_ctc_joint_args_t), "dicow_ctc_joint_step: bad args struct");
-  DICOW_REQUIRE(ctx, a->ids && a->ctc_logp && a->processed_scores && a->workspace_i32 && a->workspace_f32 && a->states &&
-                         a->r_prev && a->score_prev && a->unfinished,
+  const bool cand_only = a->score_only && a->ctc_weight == 0.f;  // attention-only beam search: normaliser + candidates
+  DICOW_REQUIRE(ctx, a->ids && a->processed_scores && a->workspace_i32 && a->workspace_f32 &&
+                         (cand_only || (a->ctc_logp && a->states && a->r_prev && a->score_prev && a->unfinished)),
                 "dicow_ctc_joint_step: null argument");
-  DICOW_REQUIRE(ctx, a->B >= 1 && a->B <= 64 && a->T >= 2 && a->T <= 4096 && a->K >= 1 && a->K <= 512 &&
-                         a->first_timestamp >= a->K && a->first_timestamp <= a->V && a->V1 > a->blank && a->eos < a->first_timestamp,
+  DICOW_REQUIRE(ctx, a->B >= 1 && a->B <= 64 && (cand_only || (a->T >= 2 && a->T <= 4096)) && a->K >= 1 && a->K <= 512 &&
+                         a->first_timestamp >= a->K && a->first_timestamp <= a->V && (cand_only || a->V1 > a->blank) && a->eos < a->first_timestamp,
                 "dicow_ctc_joint_step: need 1 <= B <= 64, 2 <= T <= 4096, 1 <= K <= 512 <= first_timestamp <= V (B=%d T=%d K=%d)",
                 a->B, a->T, a->K);
   CtcJointParams p{};
@@ -423,7 +427,7 @@ extern "C" int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args
   p.B = a->B, p.V = a->V, p.T = a->T, p.V1 = a->V1, p.K = a->K;
   p.bos = a->bos, p.eos = a->eos, p.pad = a->pad, p.blank = a->blank, p.first_ts = a->first_timestamp, p.prefix_len = a->prefix_len;
   p.w = a->ctc_weight;
-  p.x = a->ctc_logp, p.proc = a->processed_scores;
+  p.x = a->ctc_logp, p.proc = a->processed_scores, p.raw = a->raw_logits;
   p.meta = a->workspace_i32;                      // 4 B + 1
   p.cs = a->workspace_i32 + 4 * a->B + 4;         // B K
   p.lse = a->workspace_f32;                       // B
@@ -434,8 +438,8 @@ extern "C" int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args
   ctc_prepare_kernel<<<1, 64, 0, stream>>>(p);
   ctc_topk_kernel<<<a->B, TK_THREADS, 0, stream>>>(p);
   const int threads = ((a->K + 31) / 32) * 32;
-  ctc_prefix_score_kernel<<<a->B, threads, 3 * a->T * sizeof(float), stream>>>(p);
-  ctc_combine_select_kernel<<<a->B, 512, 0, stream>>>(p);
+  if (!cand_only) ctc_prefix_score_kernel<<<a->B, threads, 3 * a->T * sizeof(float), stream>>>(p);
+  if (!a->score_only) ctc_combine_select_kernel<<<a->B, 512, 0, stream>>>(p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

@@ -428,6 +428,9 @@ struct DecAttnParams {
   long long o_bs;
   int Tk;
   const int* pos;
+  int kv_batch_div;      // K/V batch index = query row / kv_batch_div (beam search: the beams of an utterance share its cross K/V)
+  const int* ancestry;   // [B, anc_stride] or NULL: key t of query row b lives in cache row ancestry[b][t] (beam search
+  long long anc_stride;  //  self-attention: hypotheses share prefixes without the cache ever being re-ordered)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -453,8 +456,11 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
   const int Tk = p.pos != nullptr ? (__ldcg(p.pos) + 1) : p.Tk;
   float q[8];
   unpack8(__ldcg(reinterpret_cast<const uint4*>(p.Q + (long long)b * p.q_bs + h * 64 + sub * 8)), q);
-  const __nv_bfloat16* kb = p.K + (long long)b * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
-  const __nv_bfloat16* vb = p.V + (long long)b * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
+  const int bkv = p.kv_batch_div > 1 ? b / p.kv_batch_div : b;
+  const long long head_off = (long long)h * p.kv_hs + sub * 8;
+  const __nv_bfloat16* kb = p.K + (long long)bkv * p.kv_bs + head_off;
+  const __nv_bfloat16* vb = p.V + (long long)bkv * p.kv_bs + head_off;
+  const int* anc = p.ancestry != nullptr ? p.ancestry + (long long)b * p.anc_stride : nullptr;
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -467,8 +473,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
     for (int u = 0; u < UNROLL; ++u) {
       const int k = k0 + u * stride;
       if (k < Tk) {
-        kv[u] = __ldcg(reinterpret_cast<const uint4*>(kb + (long long)k * p.kv_rs));  // L2 only: the newest row was
-        vv[u] = __ldcg(reinterpret_cast<const uint4*>(vb + (long long)k * p.kv_rs));  // written by the previous kernel
+        long long off = (long long)k * p.kv_rs;
+        if (anc != nullptr) off += (long long)(__ldcg(anc + k) - bkv) * p.kv_bs;  // the cache row that holds key k
+        kv[u] = __ldcg(reinterpret_cast<const uint4*>(kb + off));  // L2 only: the newest row was
+        vv[u] = __ldcg(reinterpret_cast<const uint4*>(vb + off));  // written by the previous kernel
       }
     }
 #pragma unroll
@@ -896,6 +904,8 @@ extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_
   p.kv_rs = a->kv_row_stride, p.kv_bs = a->kv_batch_stride, p.kv_hs = a->kv_head_stride > 0 ? a->kv_head_stride : 64;
   DICOW_REQUIRE(ctx, (p.kv_hs % 8) == 0, "dicow_decode_attention_bf16: kv_head_stride must be a multiple of 8 elements");
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out), p.o_bs = a->o_batch_stride, p.Tk = a->Tk, p.pos = a->pos;
+  p.kv_batch_div = a->kv_batch_div > 1 ? a->kv_batch_div : 1;
+  p.ancestry = a->ancestry, p.anc_stride = a->ancestry_stride;
   dim3 grid(a->H, a->B);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   // long fixed-length caches (cross attention, Tk = 1500) get 8 warps per (batch, head), the growing self-attention

@@ -159,6 +159,7 @@ class DecodeAttentionArgs(C.Structure):
         ("kv_row_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("o_batch_stride", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Tk", C.c_int32), ("pos", C.c_void_p), ("kv_head_stride", C.c_int64),
+        ("kv_batch_div", C.c_int32), ("ancestry", C.c_void_p), ("ancestry_stride", C.c_int64),
     ]
 
 
@@ -183,7 +184,23 @@ class CtcJointArgs(C.Structure):
         ("prefix_len", C.c_int32), ("ctc_weight", C.c_float),
         ("ctc_logp", C.c_void_p), ("processed_scores", C.c_void_p), ("workspace_i32", C.c_void_p),
         ("workspace_f32", C.c_void_p), ("states", C.c_void_p), ("r_prev", C.c_void_p), ("score_prev", C.c_void_p),
-        ("unfinished", C.c_void_p),
+        ("unfinished", C.c_void_p), ("raw_logits", C.c_void_p), ("score_only", C.c_int32),
+    ]
+
+
+class BeamStepArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("U", C.c_int32), ("NB", C.c_int32), ("V", C.c_int32), ("K", C.c_int32),
+        ("processed_scores", C.c_void_p), ("joint_workspace_i32", C.c_void_p), ("joint_workspace_f32", C.c_void_p),
+        ("ctc_weight", C.c_float), ("ctc_states", C.c_void_p), ("ctc_r_prev", C.c_void_p), ("ctc_score_prev", C.c_void_p),
+        ("ctc_r_tmp", C.c_void_p), ("T", C.c_int32),
+        ("run_score", C.c_void_p), ("fin_score", C.c_void_p), ("fin_flag", C.c_void_p), ("unsat", C.c_void_p),
+        ("ids", C.c_void_p), ("fin_ids", C.c_void_p), ("ids_tmp", C.c_void_p), ("ids_row_stride", C.c_int64),
+        ("ancestry", C.c_void_p), ("ancestry_tmp", C.c_void_p), ("ancestry_stride", C.c_int64),
+        ("pos", C.c_void_p), ("eos", C.c_int32), ("pad", C.c_int32), ("first_timestamp", C.c_int32),
+        ("max_length", C.c_int32), ("prompt_len", C.c_int32), ("length_penalty", C.c_float), ("early_stopping", C.c_int32),
+        ("scratch_i32", C.c_void_p), ("scratch_f32", C.c_void_p), ("flags", C.c_void_p),
     ]
 
 
@@ -265,6 +282,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_advance.argtypes = [vp, vp, C.c_int, vp]
     lib.dicow_logits_rules_argmax.argtypes = [vp, C.POINTER(LogitsRulesArgs), vp]
     lib.dicow_ctc_joint_step.argtypes = [vp, C.POINTER(CtcJointArgs), vp]
+    lib.dicow_beam_step.argtypes = [vp, C.POINTER(BeamStepArgs), vp]
     lib.dicow_log_softmax_rows.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp]
     lib.dicow_softlabel_ce.argtypes = [vp, C.POINTER(SoftlabelCeArgs), vp]
     lib.dicow_ctc_loss.argtypes = [vp, C.POINTER(CtcLossArgs), vp]
@@ -283,7 +301,7 @@ EXPORTED_SYMBOLS = [
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
-    "dicow_log_softmax_rows",
+    "dicow_log_softmax_rows", "dicow_beam_step",
 ]
 
 

@@ -222,10 +222,12 @@ class DiCoW(nn.Module):
 class _GreedyState:
     """Per-(device, batch size) buffers and the two captured CUDA graphs of one decoder step."""
 
-    def __init__(self, model: "DiCoWForConditionalGeneration", B: int, T: int, dev: torch.device):
+    def __init__(self, model: "DiCoWForConditionalGeneration", B: int, T: int, dev: torch.device, beams: int = 1):
+        """B = decoder rows (hypotheses); with ``beams`` > 1 the rows are utterance-major (row = u * beams + k), the
+        cross-attention cache is per utterance (B / beams entries) and the beam-search state is allocated"""
         cfg = model.config
         d, L = cfg.d_model, cfg.decoder_layers
-        self.B, self.T = B, T
+        self.B, self.T, self.beams = B, T, beams
         self.S_max = cfg.max_target_positions
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.ids = torch.zeros(B, self.S_max + 1, dtype=torch.int64, device=dev)
@@ -238,8 +240,22 @@ class _GreedyState:
         self.h = torch.empty(B, cfg.decoder_ffn_dim, **bf)
         self.self_kv = torch.zeros(L, B, self.S_max, 2 * d, **bf)
         # cross-attention cache, head-major [L, B, H, T, k(64) | v(64)]: one contiguous stream per (batch, head) and step
-        self.cross_kv = torch.empty(L, B, cfg.decoder_attention_heads, T, 128, **bf)
-        self.cross_kv_rows = torch.empty(B * T, 2 * d, **bf)  # the projection GEMM's output before the re-layout
+        U = B // beams
+        self.cross_kv = torch.empty(L, U, cfg.decoder_attention_heads, T, 128, **bf)
+        self.cross_kv_rows = torch.empty(U * T, 2 * d, **bf)  # the projection GEMM's output before the re-layout
+        self.ancestry = None
+        if beams > 1:  # beam search: see DiCoWForConditionalGeneration.beam_decode_window
+            i32, f32 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.float32, device=dev)
+            self.ancestry = torch.empty(B, self.S_max, **i32)
+            self.ancestry_tmp = torch.empty(B, self.S_max, **i32)
+            self.run_score, self.fin_score = torch.empty(B, **f32), torch.empty(B, **f32)
+            self.fin_flag, self.unsat = torch.empty(B, **i32), torch.empty(U, **i32)
+            self.fin_ids = torch.empty(B, self.S_max + 1, dtype=torch.int64, device=dev)
+            self.ids_tmp = torch.empty(2 * B, self.S_max + 1, dtype=torch.int64, device=dev)
+            self.scratch_i32, self.scratch_f32 = torch.empty(3 * B, **i32), torch.empty(2 * B, **f32)
+            self.flags = torch.zeros(U, 4, **i32)
+            self.cand = None
+            self.ctc_r_tmp = None
         self.logits = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
         self.ctc = None      # ops.CtcJointState of joint CTC / attention decoding (allocated on first use)
         self.ctc_key = None
@@ -426,6 +442,8 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         cfg = self.config
         d, H, B, T = cfg.d_model, cfg.decoder_attention_heads, st.B, st.T
         if not self.fused_decode_step or d % 32:
+            if st.beams > 1:
+                raise NotImplementedError("beam search runs on the fused decode step (d_model % 32 == 0)")
             return self._decode_step_unfused(st, w, sample, gen)
         ln_prologue = self.fused_decode_step == "ln_prologue" and d <= 1280  # the prologue holds a row in registers
 
@@ -444,12 +462,12 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             ln_linear(s["wqkv"], st.q, e["ln1_g"], e["ln1_b"], epilogue=ops.EPI_BIAS_BF16, bias=s["bqkv"], out2=kvc,
                       n_split=d, ldo2=st.S_max * 2 * d, pos=st.pos, pos_stride=2 * d)
             ops.decode_attention(st.q, kvc, kvc[:, :, d:], st.ctx, B=B, H=H, Tk=0, kv_row_stride=2 * d,
-                                 kv_batch_stride=st.S_max * 2 * d, pos=st.pos)
+                                 kv_batch_stride=st.S_max * 2 * d, pos=st.pos, ancestry=st.ancestry)
             ops.decode_linear(s["wo"], st.x, A=st.ctx, epilogue=ops.EPI_RESIDUAL_F32, bias=s["bo"], resid=st.x)
             ln_linear(c["wq"], st.q, e["ln2_g"], e["ln2_b"], epilogue=ops.EPI_BIAS_BF16, bias=c["bq"])
             ckv = st.cross_kv[li]
             ops.decode_attention(st.q, ckv, ckv[..., 64:], st.ctx, B=B, H=H, Tk=T, kv_row_stride=128,
-                                 kv_batch_stride=H * T * 128, kv_head_stride=T * 128)
+                                 kv_batch_stride=H * T * 128, kv_head_stride=T * 128, kv_batch_div=st.beams)
             ops.decode_linear(c["wo"], st.x, A=st.ctx, epilogue=ops.EPI_RESIDUAL_F32, bias=c["bo"], resid=st.x)
             ln_linear(e["w1"], st.h, e["ln3_g"], e["ln3_b"], epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
             ops.decode_linear(e["w2"], st.x, A=st.h, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], resid=st.x)
@@ -463,7 +481,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         attention (generation_config.ctc_weight > 0; generation.py:250-268): the rules kernel only materialises the
         processed scores, the CTC step log-softmaxes them, scores the top-k candidates' prefixes and selects."""
         ctc = gen.get("ctc")
-        rules = {k: v for k, v in gen.items() if k != "ctc"}
+        rules = {k: v for k, v in gen.items() if k not in ("ctc", "beam")}
+        beam = gen.get("beam")
+        if beam is not None:
+            return self._beam_select(st, rules, ctc, beam)
         if ctc is None:
             ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, **rules)
             return
@@ -472,6 +493,139 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         ops.ctc_joint_step(st.ctc, st.proc, st.ids, st.unfinished, pos=st.pos, bos=ctc["bos"], eos=rules["eos"],
                            pad=rules["pad"], first_timestamp=rules["ts_begin"], prefix_len=ctc["prefix_len"],
                            ctc_weight=ctc["weight"])
+
+    def _beam_select(self, st: _GreedyState, rules: dict, ctc: Optional[dict], beam: dict) -> None:
+        """one beam-search step after the logits (generation.py:1003-1088): processed scores of every hypothesis, their
+        log-softmax normaliser (over the RAW logits: beam search normalises before the processors) and top-k candidates,
+        CTC prefix scores of the candidates (ctc_weight > 0), then selection across the beams of each utterance,
+        finished-set bookkeeping and the re-linking of sequences / ancestry / CTC states -- all on the device."""
+        w = float(ctc["weight"]) if ctc is not None else 0.0
+        joint = st.ctc if ctc is not None else st.cand
+        ops.logits_rules_argmax(st.logits, st.ids, st.unfinished, pos=st.pos, processed_scores=st.proc, no_select=True,
+                                **rules)
+        ops.ctc_joint_step(joint, st.proc, st.ids, st.unfinished, pos=st.pos, bos=beam["bos"], eos=rules["eos"],
+                           pad=rules["pad"], first_timestamp=rules["ts_begin"], prefix_len=beam["prefix_len"], ctc_weight=w,
+                           raw_logits=st.logits, score_only=True)
+        ops.beam_step(U=st.B // st.beams, NB=st.beams, processed_scores=st.proc, joint=joint, ctc_weight=w,
+                      run_score=st.run_score, fin_score=st.fin_score, fin_flag=st.fin_flag, unsat=st.unsat, ids=st.ids,
+                      fin_ids=st.fin_ids, ids_tmp=st.ids_tmp, ancestry=st.ancestry, ancestry_tmp=st.ancestry_tmp, pos=st.pos,
+                      eos=rules["eos"], pad=rules["pad"], first_timestamp=rules["ts_begin"], max_length=beam["max_length"],
+                      prompt_len=beam["prompt_len"], length_penalty=beam["length_penalty"],
+                      early_stopping=beam["early_stopping"], scratch_i32=st.scratch_i32, scratch_f32=st.scratch_f32,
+                      flags=st.flags, ctc_r_tmp=st.ctc_r_tmp)
+
+    @torch.no_grad()
+    def beam_decode_window(self, enc_hidden: torch.Tensor, prompt: torch.Tensor, max_total_len: int, gen: dict, *,
+                           num_beams: int, length_penalty: float = 1.0, early_stopping=False, ctc: Optional[dict] = None,
+                           top_k: int = 500) -> torch.Tensor:
+        """Beam search over one batch of 30 s windows (DiCoWGenerationMixin._beam_search, generation.py:815-1154), with the
+        joint CTC / attention rescoring of the published recipe when ``ctc`` is given (configs/decode/*_beam_joint.yaml:
+        5 beams, ctc_weight 0.2, length_penalty 0.1).  Rows are utterance-major hypotheses; the beams of an utterance share
+        its cross-attention K/V; the self-attention cache is never re-ordered (ancestry table).  Returns the best
+        finished sequence per utterance, int64 [U, n], padded with ``pad``."""
+        cfg = self.config
+        dev = enc_hidden.device
+        U, T, d = enc_hidden.shape
+        NB = int(num_beams)
+        B = U * NB
+        P = prompt.shape[1]
+        max_total_len = min(max_total_len, cfg.max_target_positions)
+        if B > 64:
+            raise NotImplementedError(f"beam search over {U} windows x {NB} beams = {B} hypotheses: at most 64 per call")
+        w = self.model.prepare_decoder()
+        key = (dev.index, B, T, NB)
+        st = self._greedy.get(key)
+        if st is None:
+            st = self._greedy[key] = _GreedyState(self, B, T, dev, beams=NB)
+        enc_bf16 = enc_hidden if enc_hidden.dtype == torch.bfloat16 else ops.cast_bf16(enc_hidden.float())
+        encf = enc_bf16.reshape(U * T, d)
+        H = cfg.decoder_attention_heads
+        for li, e in enumerate(w["layers"]):
+            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv_rows, epilogue=ops.EPI_BIAS_BF16, bias=e["cross"]["bkv"])
+            ops.kv_to_head_major(st.cross_kv_rows, st.cross_kv[li], B=U, T=T, H=H)
+        if st.weights_id != id(w):
+            st.graphs.clear()
+            st.weights_id = id(w)
+        # ---- state of a new window (generation.py:940-975) ----
+        st.ids.zero_()
+        st.ids[:, :P] = prompt.to(device=dev, dtype=torch.int64).repeat_interleave(NB, dim=0)
+        st.fin_ids.fill_(gen["pad"])
+        st.fin_ids[:, :P] = st.ids[:, :P]
+        st.pos.zero_()
+        st.unfinished.fill_(1)
+        st.run_score.fill_(-1.0e9)
+        st.run_score.view(U, NB)[:, 0] = 0.0
+        st.fin_score.fill_(-1.0e9)
+        st.fin_flag.zero_()
+        st.unsat.fill_(1)
+        st.flags.zero_()
+        st.ancestry.copy_(torch.arange(B, dtype=torch.int32, device=dev)[:, None].expand(B, st.S_max))
+        if st.proc is None:
+            st.proc = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
+        k_eff = min(int(top_k), gen["ts_begin"])
+        gen = dict(gen, begin_index=P)
+        if ctc is not None:
+            lg = ctc["logits"].float().repeat_interleave(NB, dim=0).contiguous()  # generation.py:253
+            ckey = (tuple(lg.shape), k_eff, tuple(sorted((ctc.get("upper_cased") or {}).items())))
+            if st.ctc is None or st.ctc_key != ckey:
+                st.ctc = ops.CtcJointState(lg, top_k=k_eff, upper_cased=ctc.get("upper_cased"))
+                st.ctc_key = ckey
+                st.ctc_r_tmp = torch.empty_like(st.ctc.r_prev)
+                st.graphs.clear()
+            else:
+                st.ctc.reset(lg)
+            gen["ctc"] = {"weight": float(ctc["weight"]), "state": id(st.ctc)}
+        elif st.cand is None or st.cand.K != k_eff:
+            st.cand = ops.CandidateState(B, k_eff, dev)
+            st.graphs.clear()
+        gen["beam"] = {"bos": int(cfg.decoder_start_token_id), "prefix_len": int(ctc["prefix_len"]) if ctc is not None else P,
+                       "max_length": int(max_total_len), "prompt_len": P, "length_penalty": float(length_penalty),
+                       "early_stopping": early_stopping}
+
+        def run(sample: bool):
+            if not self.use_cuda_graphs:
+                self._decode_step(st, w, sample, gen)
+                return
+            gkey = (sample, P, self.fused_decode_step,
+                    tuple(sorted((k, v.data_ptr() if isinstance(v, torch.Tensor) else
+                                  (tuple(sorted(v.items())) if isinstance(v, dict) else v)) for k, v in gen.items())))
+            g = st.graphs.get(gkey)
+            if g is None:
+                # warm-up outside capture, then restore everything the step changed
+                keep = [t.clone() for t in self._beam_mutable(st)]
+                self._decode_step(st, w, sample, gen)
+                torch.cuda.synchronize(dev)
+                for t, k0 in zip(self._beam_mutable(st), keep):
+                    t.copy_(k0)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode_step(st, w, sample, gen)
+                st.graphs[gkey] = g
+                for t, k0 in zip(self._beam_mutable(st), keep):
+                    t.copy_(k0)
+            g.replay()
+
+        for _ in range(P - 1):
+            run(False)
+        early_true = early_stopping is True
+        for _ in range(max_total_len - P):
+            run(True)
+            f = st.flags.cpu()  # the loop condition is a property of the whole batch (generation.py:1101-1106)
+            improvement = bool(f[:, 2].any())
+            open_beam = not (bool(f[:, 1].all()) and early_true)
+            valid = bool(f[:, 0].any())
+            if not (improvement and open_beam and valid):
+                break
+        best = st.fin_ids.view(U, NB, -1)[:, 0, :max_total_len].clone()
+        return best
+
+    @staticmethod
+    def _beam_mutable(st: _GreedyState):
+        ts = [st.ids, st.pos, st.unfinished, st.run_score, st.fin_score, st.fin_flag, st.unsat, st.fin_ids, st.ancestry,
+              st.flags]  # (the warm-up step's K/V rows are rewritten by the captured step at the same position)
+        if st.ctc is not None:
+            ts += [st.ctc.r_prev, st.ctc.score_prev]
+        return ts
 
     def _decode_step_unfused(self, st: _GreedyState, w: dict, sample: bool, gen: dict) -> None:
         """the same step with one kernel per operation (LayerNorm, q, k|v, ... 13 per layer): kept as the comparison
@@ -604,9 +758,11 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 return kwargs[name]
             v = getattr(gc, name, None)
             return default if v is None else v
-        num_beams = get("num_beams", 1)
-        if num_beams != 1:
-            raise NotImplementedError("beam search is a SURVEY section 8f 'next' row; the B200 path decodes greedily")
+        num_beams = int(get("num_beams", 1) or 1)
+        if num_beams > 8:
+            raise NotImplementedError("beam search with more than 8 beams")
+        if int(get("num_return_sequences", 1) or 1) != 1:
+            raise NotImplementedError("num_return_sequences > 1")
         ctc_weight = float(get("ctc_weight", 0) or 0)
         if get("do_sample", False):
             raise ValueError("Provided generation mode is not supported (greedy only)")
@@ -621,7 +777,8 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 "return_timestamps": bool(get("return_timestamps", True)),
                 "max_initial_timestamp_index": get("max_initial_timestamp_index"),
                 "max_new_tokens": get("max_new_tokens"), "max_length": get("max_length", self.config.max_target_positions),
-                "forced_decoder_ids": get("forced_decoder_ids"), "ctc_weight": ctc_weight,
+                "forced_decoder_ids": get("forced_decoder_ids"), "ctc_weight": ctc_weight, "num_beams": num_beams,
+                "length_penalty": float(get("length_penalty", 1.0)), "early_stopping": get("early_stopping", False),
                 "ctc_tokens_to_score": int(get("ctc_tokens_to_score", 500) or 500)}
 
     @torch.no_grad()
@@ -723,8 +880,21 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                        "bos": cfg.decoder_start_token_id,
                        "prefix_len": len(tok.prefix_tokens) if tok is not None else P,
                        "upper_cased": dict(getattr(tok, "upper_cased_tokens", None) or {}) if tok is not None else None}
-            ids = self.greedy_decode_window(hidden, init_tokens[torch.as_tensor(batch_idx_map, device=dev)], max_total,
-                                            rules, ctc=ctc)
+            prompts = init_tokens[torch.as_tensor(batch_idx_map, device=dev)]
+            if gs["num_beams"] > 1:  # generation.py:815-1154; at most 64 hypotheses per decode batch
+                NB = gs["num_beams"]
+                per = max(1, 64 // NB)
+                parts = []
+                for c0 in range(0, hidden.shape[0], per):
+                    sub = None if ctc is None else dict(ctc, logits=ctc["logits"][c0:c0 + per])
+                    parts.append(self.beam_decode_window(hidden[c0:c0 + per], prompts[c0:c0 + per], max_total, rules,
+                                                         num_beams=NB, length_penalty=gs["length_penalty"],
+                                                         early_stopping=gs["early_stopping"], ctc=sub,
+                                                         top_k=gs["ctc_tokens_to_score"]))
+                n = max(q.shape[1] for q in parts)
+                ids = torch.cat([torch.nn.functional.pad(q, (0, n - q.shape[1]), value=gs["pad"]) for q in parts], 0)
+            else:
+                ids = self.greedy_decode_window(hidden, prompts, max_total, rules, ctc=ctc)
             self.stno_mask_seek = None
             ids_host = ids.cpu()
             for i, prev in enumerate(batch_idx_map):

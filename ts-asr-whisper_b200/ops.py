@@ -332,7 +332,7 @@ def decode_linear(W: torch.Tensor, out: torch.Tensor, *, epilogue: int, A: Optio
 
 def decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tk: int,
                      kv_row_stride: int, kv_batch_stride: int, pos: Optional[torch.Tensor] = None,
-                     kv_head_stride: int = 0) -> torch.Tensor:
+                     kv_head_stride: int = 0, kv_batch_div: int = 1, ancestry: Optional[torch.Tensor] = None) -> torch.Tensor:
     """one query row per (batch, head) against a K/V cache (dicow_decode_attention_bf16); q/out bf16 [B, H*64]."""
     dev = _require_cuda(q, k, v, out, pos)
     a = _lib.DecodeAttentionArgs()
@@ -344,6 +344,10 @@ def decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: tor
     a.B, a.H, a.Tk = B, H, Tk
     a.pos = _ptr(pos)
     a.kv_head_stride = kv_head_stride
+    a.kv_batch_div = kv_batch_div
+    if ancestry is not None:
+        assert ancestry.dtype == torch.int32 and ancestry.is_cuda and ancestry.stride(1) == 1
+        a.ancestry, a.ancestry_stride = _ptr(ancestry), ancestry.stride(0)
     _call("dicow_decode_attention_bf16", dev, a, "decode_attention")
     return out
 
@@ -466,22 +470,64 @@ class CtcJointState:
 
 def ctc_joint_step(state: CtcJointState, processed_scores: torch.Tensor, ids: torch.Tensor, unfinished: torch.Tensor, *,
                    bos: int, eos: int, pad: int, first_timestamp: int, prefix_len: int, ctc_weight: float,
-                   cur_len: int = 0, pos: Optional[torch.Tensor] = None) -> None:
+                   cur_len: int = 0, pos: Optional[torch.Tensor] = None, raw_logits: Optional[torch.Tensor] = None,
+                   score_only: bool = False) -> None:
     """one token of joint CTC / attention greedy decoding for every hypothesis (dicow_ctc_joint_step): appends the token
     to ``ids`` in place, updates ``unfinished`` and the CTC state."""
-    dev = _require_cuda(processed_scores, ids, unfinished, pos, state.logp)
+    dev = _require_cuda(processed_scores, ids, unfinished, pos, state.logp, raw_logits)
     assert processed_scores.dtype == torch.float32 and processed_scores.is_contiguous() and ids.dtype == torch.int64
     assert unfinished.dtype == torch.int32 and processed_scores.shape[0] == state.B
     a = _lib.CtcJointArgs()
     a.struct_size = C.sizeof(_lib.CtcJointArgs)
     a.ids, a.ids_row_stride, a.pos, a.cur_len = _ptr(ids), ids.stride(0), _ptr(pos), cur_len
     a.B, a.V, a.T, a.V1, a.K = state.B, processed_scores.shape[1], state.T, state.V1, state.K
-    a.bos, a.eos, a.pad, a.blank, a.first_timestamp, a.prefix_len = bos, eos, pad, state.V1 - 1, first_timestamp, prefix_len
+    a.bos, a.eos, a.pad, a.blank, a.first_timestamp, a.prefix_len = bos, eos, pad, max(state.V1 - 1, 0), first_timestamp, prefix_len
     a.ctc_weight = ctc_weight
     a.ctc_logp, a.processed_scores = _ptr(state.logp), _ptr(processed_scores)
     a.workspace_i32, a.workspace_f32, a.states = _ptr(state.ws_i32), _ptr(state.ws_f32), _ptr(state.states)
     a.r_prev, a.score_prev, a.unfinished = _ptr(state.r_prev), _ptr(state.score_prev), _ptr(unfinished)
+    a.raw_logits = _ptr(raw_logits)
+    a.score_only = 1 if score_only else 0
     _call("dicow_ctc_joint_step", dev, a, "ctc_joint")
+
+
+class CandidateState:
+    """workspaces of dicow_ctc_joint_step(score_only, ctc_weight = 0): attention-only beam search needs the log-softmax
+    normaliser and the top-k candidates of every hypothesis, no CTC buffers"""
+
+    def __init__(self, rows: int, top_k: int, device):
+        self.B, self.K, self.T, self.V1 = rows, top_k, 0, 0
+        self.logp = self.r_prev = self.score_prev = self.states = None
+        self.ws_i32 = torch.zeros(4 * rows + 4 + rows * top_k, dtype=torch.int32, device=device)
+        self.ws_f32 = torch.zeros(rows + 2 * rows * top_k, dtype=torch.float32, device=device)
+
+
+def beam_step(*, U: int, NB: int, processed_scores: torch.Tensor, joint, ctc_weight: float, run_score: torch.Tensor,
+              fin_score: torch.Tensor, fin_flag: torch.Tensor, unsat: torch.Tensor, ids: torch.Tensor, fin_ids: torch.Tensor,
+              ids_tmp: torch.Tensor, ancestry: torch.Tensor, ancestry_tmp: torch.Tensor, pos: torch.Tensor, eos: int, pad: int,
+              first_timestamp: int, max_length: int, prompt_len: int, length_penalty: float, early_stopping,
+              scratch_i32: torch.Tensor, scratch_f32: torch.Tensor, flags: torch.Tensor,
+              ctc_r_tmp: Optional[torch.Tensor] = None) -> None:
+    """one step of beam search bookkeeping + re-linking on the device (dicow_beam_step); ``joint`` is the CtcJointState /
+    CandidateState whose workspaces dicow_ctc_joint_step(score_only) just filled."""
+    dev = _require_cuda(processed_scores, run_score, ids)
+    a = _lib.BeamStepArgs()
+    a.struct_size = C.sizeof(_lib.BeamStepArgs)
+    a.U, a.NB, a.V, a.K = U, NB, processed_scores.shape[1], joint.K
+    a.processed_scores = _ptr(processed_scores)
+    a.joint_workspace_i32, a.joint_workspace_f32 = _ptr(joint.ws_i32), _ptr(joint.ws_f32)
+    a.ctc_weight = ctc_weight
+    if ctc_weight > 0:
+        a.ctc_states, a.ctc_r_prev, a.ctc_score_prev = _ptr(joint.states), _ptr(joint.r_prev), _ptr(joint.score_prev)
+        a.ctc_r_tmp, a.T = _ptr(ctc_r_tmp), joint.T
+    a.run_score, a.fin_score, a.fin_flag, a.unsat = _ptr(run_score), _ptr(fin_score), _ptr(fin_flag), _ptr(unsat)
+    a.ids, a.fin_ids, a.ids_tmp, a.ids_row_stride = _ptr(ids), _ptr(fin_ids), _ptr(ids_tmp), ids.stride(0)
+    a.ancestry, a.ancestry_tmp, a.ancestry_stride = _ptr(ancestry), _ptr(ancestry_tmp), ancestry.stride(0)
+    a.pos, a.eos, a.pad, a.first_timestamp = _ptr(pos), eos, pad, first_timestamp
+    a.max_length, a.prompt_len, a.length_penalty = max_length, prompt_len, length_penalty
+    a.early_stopping = 2 if early_stopping == "never" else (1 if early_stopping is True else 0)
+    a.scratch_i32, a.scratch_f32, a.flags = _ptr(scratch_i32), _ptr(scratch_f32), _ptr(flags)
+    _call("dicow_beam_step", dev, a, "beam_step")
 
 
 def suppress_bitmap(token_ids, vocab: int, device) -> torch.Tensor:
