@@ -19,6 +19,8 @@ ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--no-graphs", action="store_true")
 ap.add_argument("--unfused", action="store_true", help="one kernel per operation (the pre-fusion decode step)")
 ap.add_argument("--ln-prologue", action="store_true", help="LayerNorm as the prologue of the linear kernel")
+ap.add_argument("--beams", type=int, default=1, help="se_dicow workload: beam search with this many beams")
+ap.add_argument("--ctc-weight", type=float, default=0.0, help="se_dicow workload: joint CTC / attention decoding weight")
 ap.add_argument("--workload", default="decoder", choices=["decoder", "se_dicow"],
                 help="decoder: token steps on synthetic encoder states; se_dicow: BASELINE configs[3] end to end "
                      "(SE-DiCoW encoder with enrollment streams + 8 SCB layers, then the greedy loop)")
@@ -34,6 +36,9 @@ def se_dicow_e2e():
     cfg = turbo_config()
     cfg.use_enrollments, cfg.scb_layers = True, 8
     cfg.pad_token_id = cfg.eos_token_id = 50257
+    cfg.decoder_start_token_id = 50258
+    if args.ctc_weight > 0:  # the CTC head of the recipe (configs/base.yaml:5,19-21)
+        cfg.ctc_weight, cfg.additional_self_attention_layer, cfg.pre_ctc_sub_sample = 0.3, True, True
     with torch.device(dev):
         model = DiCoWForConditionalGeneration(cfg)
     from bench import make_inputs, perturb_
@@ -55,10 +60,18 @@ def se_dicow_e2e():
     n = 3 + args.steps
     enc = model.get_encoder()
 
+    def decode(hidden):
+        ctc = None
+        if args.ctc_weight > 0:
+            ctc = {"logits": model.get_enc_logits(hidden), "weight": args.ctc_weight, "prefix_len": 3, "bos": 50258}
+        if args.beams > 1:  # configs/decode/se_dicow_beam_joint.yaml: 5 beams, ctc 0.2, length_penalty 0.1
+            return model.beam_decode_window(hidden, prompt, n, rules, num_beams=args.beams, length_penalty=0.1, ctc=ctc)
+        return model.greedy_decode_window(hidden, prompt, n, rules, ctc=ctc)
+
     def one(i):
         f, s, e = batches[i % 3]
         hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
-        return model.greedy_decode_window(hidden, prompt, n, rules)
+        return decode(hidden)
 
     for i in range(3):
         one(i)
@@ -72,7 +85,7 @@ def se_dicow_e2e():
         ev[0].record()
         hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
         ev[1].record()
-        ids = model.greedy_decode_window(hidden, prompt, n, rules)
+        ids = decode(hidden)
         ev[2].record()
         torch.cuda.synchronize()
         t_enc += ev[0].elapsed_time(ev[1])
@@ -80,7 +93,7 @@ def se_dicow_e2e():
     ms_all, ms_enc = t_all / reps, t_enc / reps
     gflop_enc = 3577.0  # SE-DiCoW encoder forward per target utterance
     print(json.dumps({"metric": "SE-DiCoW greedy decode (BASELINE configs[3]), large-v3-turbo + FDDT + 8 SCB layers",
-                      "batch": B, "new_tokens_per_window": args.steps, "ms_per_batch": ms_all, "ms_encoder": ms_enc,
+                      "batch": B, "beams": args.beams, "ctc_weight": args.ctc_weight, "new_tokens_per_window": args.steps, "ms_per_batch": ms_all, "ms_encoder": ms_enc,
                       "ms_decode": ms_all - ms_enc, "utt_per_s": B / (ms_all * 1e-3),
                       "tokens_per_s": B * args.steps / (ms_all * 1e-3),
                       "encoder_tflops": B * gflop_enc / ms_enc, "cuda_graphs": model.use_cuda_graphs,

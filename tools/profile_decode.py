@@ -21,6 +21,8 @@ ap.add_argument("--steps", type=int, default=24)
 ap.add_argument("--unfused", action="store_true")
 ap.add_argument("--ln-prologue", action="store_true")
 ap.add_argument("--no-graphs", action="store_true")
+ap.add_argument("--beams", type=int, default=1)
+ap.add_argument("--ctc-weight", type=float, default=0.0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = turbo_config()
@@ -37,12 +39,24 @@ prompt = torch.tensor([[50258, 50259, 50360]] * B, device=dev)
 rules = dict(eos=50257, pad=50257, no_timestamps=50364, ts_begin=50365, max_initial_timestamp_index=None,
              timestamp_rules=True, suppress_bitmap=model._suppress_bitmap([50257, 220, 50256], dev))
 n = 3 + args.steps
+ctc = None
+if args.ctc_weight > 0:
+    ctc = {"logits": torch.randn(B, 375, cfg.vocab_size + 1, device=dev) * 2.0, "weight": args.ctc_weight, "prefix_len": 3,
+           "bos": 50258}
+
+
+def decode():
+    if args.beams > 1:
+        return model.beam_decode_window(enc, prompt, n, rules, num_beams=args.beams, length_penalty=0.1, ctc=ctc)
+    return model.greedy_decode_window(enc, prompt, n, rules, ctc=ctc)
+
+
 for _ in range(2):
-    model.greedy_decode_window(enc, prompt, n, rules)
+    decode()
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    model.greedy_decode_window(enc, prompt, n, rules)
+    decode()
     torch.cuda.synchronize()
 evs = []
 for ev in prof.events():

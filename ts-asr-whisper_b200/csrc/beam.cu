@@ -101,33 +101,63 @@ __global__ void __launch_bounds__(BS_THREADS) beam_select_kernel(const BeamParam
   }
   __syncthreads();
   // ---- the 2 x NB best continuations, in order ----
+  // Scores of all candidates of the utterance are evaluated once into shared memory; every round is then a scan of that
+  // array for the best item strictly after the previous winner in (score desc, flat index asc) order.
+  extern __shared__ float s_sc[];
   const int n_ts = p.V - p.first_ts;
   const int per_beam = p.K + n_ts;
-  Item last{INFINITY, -1, -1};
-  for (int round = 0; round < K2; ++round) {
-    Item best{-INFINITY, 0x7fffffff, -1};
-    for (int it = tid; it < NB * per_beam; it += BS_THREADS) {
-      const int i = it / per_beam, j = it - i * per_beam;
-      const int r = R0 + i;
-      Item c;
-      if (j < p.K) {
-        const float a = p.att[(long long)r * p.K + j];
-        if (!(a > -INFINITY)) continue;
-        const int t = p.cs[(long long)r * p.K + j];
-        float sc = a;
+  const int n_items = NB * per_beam;
+  auto flat_of = [&](int it) {
+    const int i = it / per_beam, j = it - i * per_beam;
+    return i * p.V + (j < p.K ? p.cs[(long long)(R0 + i) * p.K + j] : p.first_ts + (j - p.K));
+  };
+  for (int it = tid; it < n_items; it += BS_THREADS) {
+    const int i = it / per_beam, j = it - i * per_beam;
+    const int r = R0 + i;
+    float sc = -INFINITY;
+    if (j < p.K) {
+      const float a = p.att[(long long)r * p.K + j];
+      if (a > -INFINITY) {
+        sc = a;
         if (p.w > 0.f) sc = (1.f - p.w) * a + p.w * (p.psi[(long long)r * p.K + j] - s_prev[i]);
-        c = Item{sc + s_run[i], i * p.V + t, j};
-      } else {
-        const int v = p.first_ts + (j - p.K);
-        const float x = p.proc[(long long)r * p.V + v];
-        if (!(x > -INFINITY)) continue;
-        const float a = x - s_lse[i];
-        float sc = a;
-        if (p.w > 0.f) sc = (1.f - p.w) * a + p.w * (s_maxpsi[i] - s_prev[i]);
-        c = Item{sc + s_run[i], i * p.V + v, -1};
+        sc += s_run[i];
       }
-      if (item_before(last, c) && item_before(c, best)) best = c;  // strictly after the previous winner
+    } else {
+      const float x = p.proc[(long long)r * p.V + p.first_ts + (j - p.K)];
+      if (x > -INFINITY) {
+        const float a = x - s_lse[i];
+        sc = a;
+        if (p.w > 0.f) sc = (1.f - p.w) * a + p.w * (s_maxpsi[i] - s_prev[i]);
+        sc += s_run[i];
+      }
     }
+    s_sc[it] = sc;
+  }
+  __syncthreads();
+  float last_s = INFINITY;
+  int last_flat = -1;
+  for (int round = 0; round < K2; ++round) {
+    float bs = -INFINITY;
+    int bit = -1, bflat = 0x7fffffff;
+    for (int it = tid; it < n_items; it += BS_THREADS) {
+      const float sc = s_sc[it];
+      if (!(sc > -INFINITY) || sc > last_s || sc < bs) continue;
+      int fl = -1;
+      if (sc == last_s) {  // a tie with the previous winner: only items after it in flat order remain
+        fl = flat_of(it);
+        if (fl <= last_flat) continue;
+      }
+      if (sc == bs) {
+        if (fl < 0) fl = flat_of(it);
+        if (bflat == 0x7fffffff && bit >= 0) bflat = flat_of(bit);
+        if (fl >= bflat) continue;
+        bflat = fl;
+      } else {
+        bflat = fl >= 0 ? fl : 0x7fffffff;
+      }
+      bs = sc, bit = it;
+    }
+    Item best{bs, bit >= 0 ? (bflat != 0x7fffffff ? bflat : flat_of(bit)) : 0x7fffffff, bit};  // slot field carries the item index here
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       Item q;
@@ -141,10 +171,14 @@ __global__ void __launch_bounds__(BS_THREADS) beam_select_kernel(const BeamParam
     if (tid == 0) {
       for (int w = 1; w < BS_THREADS / 32; ++w)
         if (item_before(s_red[w], best)) best = s_red[w];
+      if (best.slot >= 0) {  // item index -> candidate slot (-1 for a timestamp id)
+        const int j = best.slot % per_beam;
+        best.slot = j < p.K ? j : -1;
+      }
       s_top[round] = best;
     }
     __syncthreads();
-    last = s_top[round];
+    last_s = s_top[round].s, last_flat = s_top[round].flat;
   }
   // ---- bookkeeping (generation.py:1023-1105) ----
   if (tid == 0) {
@@ -324,7 +358,10 @@ extern "C" int dicow_beam_step(dicow_handle_t h, const dicow_beam_step_args_t* a
   p.new_run = a->scratch_f32, p.new_score = a->scratch_f32 + R;
   p.flags = a->flags;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  beam_select_kernel<<<a->U, BS_THREADS, 0, stream>>>(p);
+  const size_t sel_smem = (size_t)a->NB * (a->K + (a->V - a->first_timestamp)) * sizeof(float);
+  DICOW_REQUIRE(ctx, sel_smem <= (size_t)ctx->max_smem_optin - 4096, "dicow_beam_step: %zu bytes of candidate scores per utterance", sel_smem);
+  DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(beam_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  beam_select_kernel<<<a->U, BS_THREADS, sel_smem, stream>>>(p);
   beam_gather_kernel<<<R, 128, 0, stream>>>(p);
   beam_commit_kernel<<<R, 128, 0, stream>>>(p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());

@@ -186,34 +186,36 @@ __global__ void __launch_bounds__(TK_THREADS) ctc_topk_kernel(const CtcJointPara
   }
   __syncthreads();
   const unsigned base = s_count_gt;
-  // entries equal to the threshold: the lowest ids first (one thread walks them: there are few)
-  if (tid == 0) {
-    unsigned taken = 0;
-    for (int v = 0; v < n && taken < need_eq; ++v) {
-      const float x = row[v];
-      if (ordered_key(x) == kth) {
-        cs[base + taken] = v, att[base + taken] = x - lse;
+  // entries equal to the threshold fill the remaining need_eq slots (which of several equal scores get in is as
+  // unspecified as in torch.topk; with continuous scores there is exactly one).  All threads scan: a single thread walking
+  // the 50 365 text ids cost 1.5-2 ms per step.
+  for (int v = tid; v < n; v += TK_THREADS) {
+    const float x = row[v];
+    if (ordered_key(x) == kth) {
+      const unsigned e = atomicAdd(&s_count_eq, 1u);
+      if (e < need_eq) {
+        cs[base + e] = v, att[base + e] = x - lse;
         if (v == p.eos) s_has_eos = 1;
-        ++taken;
       }
     }
-    // decoding.py:296-297: EOS is always scored; it takes the place of the weakest candidate
-    if (!s_has_eos && p.eos < n) {
-      const unsigned slot = base + taken - 1;
-      cs[slot] = p.eos, att[slot] = row[p.eos] - lse;
-    }
+  }
+  __syncthreads();
+  // decoding.py:296-297: EOS is always scored; it takes the place of the weakest candidate
+  if (tid == 0 && !s_has_eos && p.eos < n) {
+    const unsigned slot = base + need_eq - 1;
+    cs[slot] = p.eos, att[slot] = row[p.eos] - lse;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward variables and prefix scores: one CTA per hypothesis, one thread per candidate
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) ctc_prefix_score_kernel(const CtcJointParams p) {
+__global__ void __launch_bounds__(128) ctc_prefix_score_kernel(const CtcJointParams p) {
   extern __shared__ float cps_smem[];  // r_sum [T] | r_prev blank branch [T] | blank posterior [T]
   float* r_sum = cps_smem;
   float* r_pb = cps_smem + p.T;
   float* xb = cps_smem + 2 * p.T;
-  const int b = blockIdx.x, j = threadIdx.x;
+  const int b = blockIdx.x, j = blockIdx.y * blockDim.x + threadIdx.x;  // candidates of a hypothesis spread over CTAs
   const int decoded_len = p.meta[4 * b + 0], last = p.meta[4 * b + 1], todo = p.meta[4 * b + 2];
   const int loop_start = p.meta[4 * p.B];
   float* psi_out = p.psi + (long long)b * p.K;
@@ -437,8 +439,8 @@ extern "C" int dicow_ctc_joint_step(dicow_handle_t h, const dicow_ctc_joint_args
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ctc_prepare_kernel<<<1, 64, 0, stream>>>(p);
   ctc_topk_kernel<<<a->B, TK_THREADS, 0, stream>>>(p);
-  const int threads = ((a->K + 31) / 32) * 32;
-  if (!cand_only) ctc_prefix_score_kernel<<<a->B, threads, 3 * a->T * sizeof(float), stream>>>(p);
+  // one thread per candidate, 128 per CTA: the per-frame recursion is issue-bound on one SM with 512 candidates per CTA
+  if (!cand_only) ctc_prefix_score_kernel<<<dim3(a->B, (a->K + 127) / 128), 128, 3 * a->T * sizeof(float), stream>>>(p);
   if (!a->score_only) ctc_combine_select_kernel<<<a->B, 512, 0, stream>>>(p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
