@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int krank = p.ksplit > 1 ? (int)cluster_ctarank() : 0;
+  const int m0 = (int)blockIdx.y * (MT * 16);  // M > 32 rows are split over blockIdx.y (two 32-row CTAs per column tile)
   const int ntiles = (p.N + 7) >> 3;
   const int tile_first = ((int)blockIdx.x / p.ksplit) * p.tiles_per_cta;
   const int tile_end = min(tile_first + p.tiles_per_cta, ntiles);
@@ -290,15 +291,15 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     constexpr int RPR = MT * 16 / DL_LN_CLUSTER;  // rows per rank
     const int crank = (int)cluster_ctarank();
     const int nvec = p.K >> 2;  // K <= 1280: at most 10 float4 per lane
-    for (int r = p.M + warp; r < MT * 16; r += DL_WARPS) {  // local zero rows (disjoint from what the peers write)
+    for (int r = max(p.M - m0, 0) + warp; r < MT * 16; r += DL_WARPS) {  // local zero rows (disjoint from the peers' writes)
       __nv_bfloat16* srow = sA + (size_t)r * p.a_pitch;
       for (int c = lane * 4; c < p.Ks; c += 128) *reinterpret_cast<uint2*>(srow + c) = make_uint2(0u, 0u);
     }
     const int r = crank * RPR + warp;
-    const bool mine = warp < RPR && r < p.M;
+    const bool mine = warp < RPR && m0 + r < p.M;
     uint2 y[10];
     if (mine) {
-      const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)r * p.ldx);
+      const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)(m0 + r) * p.ldx);
       float4 v[10];
 #pragma unroll
       for (int i = 0; i < 10; ++i) {
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     for (int i = threadIdx.x; i < MT * 16 * vec_per_row; i += DL_THREADS) {
       const int r = i / vec_per_row, c = (i - r * vec_per_row) * 8;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(p.A + (long long)r * p.lda + kbase + c));
+      if (m0 + r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(p.A + (long long)(m0 + r) * p.lda + kbase + c));
       *reinterpret_cast<uint4*>(sA + (size_t)r * p.a_pitch + c) = v;
     }
   }
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
         const int e = threadIdx.x + j * DL_THREADS;
         if (e < MT * 16 * 8) {
           for (int r = 1; r < p.ksplit; ++r) v[j] += cpart[(size_t)(r - 1) * MT * 16 * 8 + e];
-          dl_store(p, e >> 3, tile * 8 + (e & 7), v[j]);
+          dl_store(p, m0 + (e >> 3), tile * 8 + (e & 7), v[j]);
         }
       }
     }
@@ -540,6 +541,115 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
       ot = fmaf(sm_o[w][threadIdx.x], c, ot);
     }
     p.out[(long long)b * p.o_bs + h * 64 + threadIdx.x] = __float2bfloat16_rn(ot / lt);
+  }
+}
+
+// Several queries against ONE K/V stream: beam search, where the NQ hypotheses of an utterance attend to the same encoder
+// states (cross attention).  One CTA per (head, utterance): every key / value row is loaded once and used by all NQ
+// queries (the single-query kernel re-reads the 384 KB stream once per hypothesis: 5 x at 5 beams, 74 us per layer for
+// 60 hypotheses).  Same thread mapping as decode_attention_kernel: an 8-lane group owns a key.  NOT the default: see the
+// measurement at the launch site.
+template <int NQ>
+__global__ void __launch_bounds__(256) decode_attention_mq_kernel(const DecAttnParams p) {
+  constexpr int NWARPS = 8;
+  __shared__ float sm_m[NWARPS][NQ], sm_l[NWARPS][NQ], sm_o[NWARPS][NQ][64];
+  const int h = blockIdx.x, u = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  griddep_launch();
+  griddep_wait();
+  const int Tk = p.Tk;
+  float q[NQ][8];
+#pragma unroll
+  for (int n = 0; n < NQ; ++n)
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(p.Q + (long long)(u * NQ + n) * p.q_bs + h * 64 + sub * 8)), q[n]);
+  const __nv_bfloat16* kb = p.K + (long long)u * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
+  const __nv_bfloat16* vb = p.V + (long long)u * p.kv_bs + (long long)h * p.kv_hs + sub * 8;
+  float m[NQ], l[NQ], o[NQ][8];
+#pragma unroll
+  for (int n = 0; n < NQ; ++n) {
+    m[n] = -INFINITY, l[n] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[n][i] = 0.f;
+  }
+  constexpr int UNROLL = 2;
+  const int stride = NWARPS * 4;
+  for (int kw = warp * 4; kw < Tk; kw += stride * UNROLL) {  // warp-uniform trip count
+    const int k0 = kw + grp;
+    uint4 kv[UNROLL], vv[UNROLL];
+#pragma unroll
+    for (int x = 0; x < UNROLL; ++x) {
+      const int k = k0 + x * stride;
+      if (k < Tk) {
+        kv[x] = __ldcg(reinterpret_cast<const uint4*>(kb + (long long)k * p.kv_rs));
+        vv[x] = __ldcg(reinterpret_cast<const uint4*>(vb + (long long)k * p.kv_rs));
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < UNROLL; ++x) {
+      const int k = k0 + x * stride;
+      const bool ok = k < Tk;  // uniform within the 8-lane group
+      float kf[8], vf[8];
+      if (ok) unpack8(kv[x], kf), unpack8(vv[x], vf);
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) {
+        float s = 0.f;
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s = fmaf(q[n][i], kf[i], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (ok) {
+          const float mn = fmaxf(m[n], s);
+          const float corr = __expf(m[n] - mn);
+          const float pw = __expf(s - mn);
+          l[n] = fmaf(l[n], corr, pw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[n][i] = fmaf(o[n][i], corr, pw * vf[i]);
+          m[n] = mn;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NQ; ++n) {
+#pragma unroll
+    for (int x = 8; x <= 16; x <<= 1) {  // merge the 4 groups of the warp
+      const float m2 = __shfl_xor_sync(0xffffffffu, m[n], x);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l[n], x);
+      const float mn = fmaxf(m[n], m2);
+      const float c1 = (m[n] == -INFINITY) ? 0.f : __expf(m[n] - mn);
+      const float c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+      l[n] = l[n] * c1 + l2 * c2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float o2 = __shfl_xor_sync(0xffffffffu, o[n][i], x);
+        o[n][i] = o[n][i] * c1 + o2 * c2;
+      }
+      m[n] = mn;
+    }
+    if (grp == 0) {
+      if (sub == 0) sm_m[warp][n] = m[n], sm_l[warp][n] = l[n];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm_o[warp][n][sub * 8 + i] = o[n][i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NQ * 64; idx += blockDim.x) {
+    const int n = idx >> 6, c = idx & 63;
+    float mt = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) mt = fmaxf(mt, sm_m[w][n]);
+    float lt = 0.f, ot = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      const float cc = (sm_m[w][n] == -INFINITY) ? 0.f : __expf(sm_m[w][n] - mt);
+      lt = fmaf(sm_l[w][n], cc, lt);
+      ot = fmaf(sm_o[w][n][c], cc, ot);
+    }
+    p.out[(long long)(u * NQ + n) * p.o_bs + h * 64 + c] = __float2bfloat16_rn(ot / lt);
   }
 }
 
@@ -833,7 +943,11 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
   if (a->out2 != nullptr)
     DICOW_REQUIRE(ctx, a->n_split > 0 && a->n_split < a->N && (a->n_split % 8) == 0, "dicow_decode_linear: bad n_split %d", a->n_split);
   const int tiles = ceil_div(a->N, 8);
-  const int MT = ceil_div(a->M, 16);
+  // more than 32 rows (beam search: utterances x beams hypotheses) are split over two CTAs of 32 rows per column tile:
+  // a 64-row A slab is 168 KB of shared memory = one CTA per SM and too few weight loads in flight (measured 22.6 us
+  // per layer at M = 60 against 8 us at M = 16); the second CTA's weight requests are L2 hits
+  const int msplit = a->M > 32 ? ceil_div(a->M, 32) : 1;
+  const int MT = msplit > 1 ? 2 : ceil_div(a->M, 16);
   // split K over a cluster until a CTA's slice fits the per-warp register slab (<= 1280), then once more while the grid
   // would leave half of the SMs idle; slices stay multiples of 32.  The two-output form keeps K whole (fused q|k,v: N = 3d).
   int ksplit = 1;
@@ -864,14 +978,14 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
     int per_sm = 1;
     DICOW_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DL_THREADS, smem));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    p.tiles_per_cta = ksplit > 1 ? 1 : ceil_div(tiles, per_sm * ctx->num_sms);
+    p.tiles_per_cta = ksplit > 1 ? 1 : ceil_div(tiles * msplit, per_sm * ctx->num_sms);
     int grid = ceil_div(tiles, p.tiles_per_cta) * ksplit;
     unsigned cluster = (unsigned)ksplit;
     if (ln) {  // clusters of DL_LN_CLUSTER CTAs share the LayerNorm; surplus CTAs of the last cluster own no tile
       cluster = DL_LN_CLUSTER;
       grid = ceil_div(grid, DL_LN_CLUSTER) * DL_LN_CLUSTER;
     }
-    DICOW_CUDA_OK(ctx, launch_step_kernel(kern, dim3(grid), dim3(DL_THREADS), smem, stream, cluster, p));
+    DICOW_CUDA_OK(ctx, launch_step_kernel(kern, dim3(grid, msplit), dim3(DL_THREADS), smem, stream, cluster, p));
     return DICOW_OK;
   };
   switch (MT * 2 + (ln ? 1 : 0)) {
@@ -910,6 +1024,26 @@ extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   // long fixed-length caches (cross attention, Tk = 1500) get 8 warps per (batch, head), the growing self-attention
   // cache (Tk <= 448, read from the device scalar) 4
+  // Measured (60 hypotheses = 12 utterances x 5 beams, tools/profile_decode.py): 92.8 us per layer against 73.9 us for the
+  // single-query kernel -- NQ = 5 needs 150 registers (one CTA per SM) and leaves 240 CTAs for 148 SMs; the re-reads it
+  // saves are L2 hits anyway.  Opt-in (DICOW_MQ_ATTENTION=1) until it splits the keys over more CTAs.
+  static const bool mq_enabled = [] {
+    const char* e = getenv("DICOW_MQ_ATTENTION");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (mq_enabled && a->pos == nullptr && a->ancestry == nullptr && p.kv_batch_div > 1 && p.kv_batch_div <= 8 &&
+      (a->B % p.kv_batch_div) == 0) {
+    // beam search cross attention: the beams of an utterance share one K/V stream -> one CTA per (head, utterance)
+    const dim3 g2(a->H, a->B / p.kv_batch_div);
+    switch (p.kv_batch_div) {
+#define DICOW_MQ(N) \
+  case N: DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_mq_kernel<N>, g2, dim3(256), 0, stream, 1, p)); break;
+      DICOW_MQ(2) DICOW_MQ(3) DICOW_MQ(4) DICOW_MQ(5) DICOW_MQ(6) DICOW_MQ(7) DICOW_MQ(8)
+#undef DICOW_MQ
+      default: break;
+    }
+    return DICOW_OK;
+  }
   if (a->pos == nullptr && a->Tk >= 512)
     DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_kernel<8>, grid, dim3(8 * 32), 0, stream, 1, p));
   else
