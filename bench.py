@@ -113,8 +113,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def time_reference(steps, warmup, B=1, threads=None):
-    """The reference's CPU implementation of the path (oracle port, fp32, SDPA, all host threads)."""
+def time_reference(steps, warmup, B=1, threads=None, device="cpu"):
+    """The reference's implementation of the path as stock PyTorch (oracle port, SDPA): fp32 on all host threads (the
+    baseline the contract asks for), or -- ``--reference-device cuda``, context only -- the same eager code under bf16
+    autocast on the GPU (cuBLAS + the SDPA flash kernel: what the reference's own modules run there)."""
     from oracle import dicow_oracle as orc
     from oracle import synth
     threads = threads or os.cpu_count()
@@ -135,16 +137,25 @@ def time_reference(steps, warmup, B=1, threads=None):
             p[k] = torch.randn(shp, generator=g) * 0.1
     feats, stno = make_inputs(B, 100)
     times = []
-    with torch.no_grad():
+    if device != "cpu":
+        dev = torch.device(device)
+        p = {k: v.to(dev) for k, v in p.items()}
+        feats, stno = feats.to(dev), stno.to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=device != "cpu"):
         for i in range(warmup + steps):
+            if device != "cpu":
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
             orc.encoder_forward(p, dm, feats, stno)
+            if device != "cpu":
+                torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     total = sum(times)
+    how = "fp32" if device == "cpu" else f"bf16 autocast on {device} (eager cuBLAS / SDPA, context only)"
     return {"utt_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads,
-            "sample": f"{len(times)} forward(s) of B={B} utterance(s), fp32, torch {torch.__version__} SDPA, "
+            "sample": f"{len(times)} forward(s) of B={B} utterance(s), {how}, torch {torch.__version__} SDPA, "
                       f"{warmup} warm-up"}
 
 
@@ -156,6 +167,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-device", default="cpu", help="--impl reference: 'cpu' (the baseline) or 'cuda' (the same "
+                    "stock PyTorch code under bf16 autocast on the GPU, for context)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,10 +183,13 @@ def main():
             return
         W = max(1, min(args.warmup, 1))
         K = max(1, min(args.steps, 3))
-        r = time_reference(K, W, B=1)
+        on_gpu = args.reference_device != "cpu"
+        if on_gpu:
+            K, W = max(args.steps, 5), max(args.warmup, 2)
+        r = time_reference(K, W, B=args.batch if on_gpu else 1, device=args.reference_device)
         line = {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": "utt/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "vs_baseline": None, "dtype": "bf16" if on_gpu else "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
                                  "sample": r["sample"]},
                 "e2e": {"value": r["utt_per_s"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
