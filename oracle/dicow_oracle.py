@@ -107,19 +107,28 @@ def log_mel(wave: np.ndarray, n_mels: int, chunk_samples: int = 480000, n_fft: i
 _FDDT_ORDER = ("silence", "target", "non_target", "overlap")  # STNO mask channel order, FDDT.py:56-62
 
 
-def fddt_tables(p: Params, prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[4, d] weights and biases in STNO channel order."""
+def fddt_tables(p: Params, prefix: str) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    """weights ([4, d] diagonal, [4, d, d] full-matrix, None for the bias-only variant) and biases [4, d] in STNO order"""
+    if f"{prefix}.{_FDDT_ORDER[0]}_linear" in p:  # bias-only: the parameter IS the bias vector (FDDT.py:10,43-51)
+        return None, torch.stack([p[f"{prefix}.{c}_linear"] for c in _FDDT_ORDER])
     w = torch.stack([p[f"{prefix}.{c}_linear.weight"] for c in _FDDT_ORDER])
     b = torch.stack([p[f"{prefix}.{c}_linear.bias"] for c in _FDDT_ORDER])
     return w, b
 
 
-def fddt(x: torch.Tensor, stno: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """sum_c stno[:, c, :, None] * (w_c * x + b_c) -- src/models/dicow/FDDT.py:52-62 with diagonal linears
-    (src/models/dicow/layers.py:73-77).  x [B, T, d], stno [B, 4, T]."""
+def fddt(x: torch.Tensor, stno: torch.Tensor, w: Optional[torch.Tensor], b: torch.Tensor) -> torch.Tensor:
+    """src/models/dicow/FDDT.py:41-63.  Default: sum_c stno[:, c, :, None] * lin_c(x) with lin_c diagonal (w_c * x + b_c,
+    layers.py:73-77) or a full nn.Linear (x W_c^T + b_c, layers.py:7-47); bias-only: x + sum_c stno_c * b_c.
+    x [B, T, d], stno [B, 4, T]."""
+    if w is None:
+        out = x
+        for c in range(4):
+            out = out + stno[:, c, :, None] * b[c]
+        return out
     out = torch.zeros_like(x)
     for c in range(4):
-        out = out + (x * w[c] + b[c]) * stno[:, c, :, None]
+        y = F.linear(x, w[c], b[c]) if w.dim() == 3 else x * w[c] + b[c]
+        out = out + y * stno[:, c, :, None]
     return out
 
 
@@ -226,7 +235,9 @@ def ctc_logits(p: Params, dm: Dims, h: torch.Tensor) -> torch.Tensor:
     """possibly_update_last_hidden_states + lm_head: src/models/dicow/encoder.py:87-106,236.  The attention output
     REPLACES the hidden state (no residual, no LN); two stride-2 convs without bias; lm_head without bias."""
     e = "model.encoder"
-    if dm.additional_self_attention_layer:
+    if dm.additional_layer:  # encoder.py:88-89: a whole WhisperEncoderLayer
+        h = encoder_layer(p, e + ".additional_layer", h, dm.heads)
+    elif dm.additional_self_attention_layer:
         h = attention(p, e + ".additional_self_attention_layer", h, h, dm.heads)
     if dm.pre_ctc_sub_sample:
         h = h.transpose(1, 2)

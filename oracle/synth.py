@@ -87,6 +87,9 @@ class Dims:
     use_enrollments: bool = False
     scb_layers: int = 0
     apply_fddt_to_n_layers: int = -1
+    fddt_is_diagonal: bool = True    # False: full d x d CustomLinear per class (src/models/dicow/layers.py:7-47)
+    fddt_bias_only: bool = False     # True: one bias vector per class (src/models/dicow/FDDT.py:43-51)
+    additional_layer: bool = False   # a whole encoder layer in front of the CTC head (encoder.py:17-18, 88-89)
     pad_token_id: int = 50257
     eos_token_id: int = 50257
     decoder_start_token_id: int = 50258
@@ -102,7 +105,8 @@ class Dims:
             encoder_attention_heads=self.heads, decoder_layers=self.dec_layers, decoder_attention_heads=self.dec_heads,
             encoder_ffn_dim=self.ffn, decoder_ffn_dim=self.dec_ffn, max_source_positions=self.T,
             max_target_positions=self.max_target, use_fddt=self.use_fddt, use_pre_pos_fddt=self.use_pre_pos_fddt,
-            fddt_is_diagonal=True, non_target_fddt_value=self.non_target_fddt_value, fddt_init="suppressive",
+            fddt_is_diagonal=self.fddt_is_diagonal, fddt_bias_only=self.fddt_bias_only, additional_layer=self.additional_layer,
+            non_target_fddt_value=self.non_target_fddt_value, fddt_init="suppressive",
             ctc_weight=self.ctc_weight, additional_self_attention_layer=self.additional_self_attention_layer,
             pre_ctc_sub_sample=self.pre_ctc_sub_sample, use_enrollments=self.use_enrollments,
             scb_layers=self.scb_layers if self.use_enrollments else None,
@@ -143,8 +147,20 @@ def param_shapes(dm: Dims, decoder: bool = True) -> Dict[str, Tuple[int, ...]]:
 
     def fddt(prefix: str):
         for c in ("target", "non_target", "overlap", "silence"):
-            sh[f"{prefix}.{c}_linear.weight"] = (d,)
+            if dm.fddt_bias_only:
+                sh[f"{prefix}.{c}_linear"] = (d,)
+                continue
+            sh[f"{prefix}.{c}_linear.weight"] = (d,) if dm.fddt_is_diagonal else (d, d)
             sh[f"{prefix}.{c}_linear.bias"] = (d,)
+
+    def layer(p: str):
+        attn(p + ".self_attn")
+        ln(p + ".self_attn_layer_norm")
+        sh[p + ".fc1.weight"] = (dm.ffn, d)
+        sh[p + ".fc1.bias"] = (dm.ffn,)
+        sh[p + ".fc2.weight"] = (d, dm.ffn)
+        sh[p + ".fc2.bias"] = (d,)
+        ln(p + ".final_layer_norm")
 
     e = "model.encoder"
     sh[e + ".conv1.weight"] = (d, dm.n_mels, 3)
@@ -163,6 +179,8 @@ def param_shapes(dm: Dims, decoder: bool = True) -> Dict[str, Tuple[int, ...]]:
         ln(p + ".final_layer_norm")
     ln(e + ".layer_norm")
     if dm.ctc_weight > 0:
+        if dm.additional_layer:
+            layer(e + ".additional_layer")
         if dm.additional_self_attention_layer:
             attn(e + ".additional_self_attention_layer")
         if dm.pre_ctc_sub_sample:
@@ -206,6 +224,10 @@ def make_param(name: str, shape: Tuple[int, ...], seed: str = "w0") -> np.ndarra
     key = f"{seed}/{name}"
     leaf = name.rsplit(".", 1)[-1]
     if "fddt" in name:  # perturbed off the identity (weights 1 -> U(0.5, 1.5), biases 0 -> U(-0.2, 0.2))
+        if leaf == "weight" and len(shape) == 2:  # full-matrix FDDT: a perturbed identity plus a dense component
+            a = math.sqrt(3.0 / shape[1]) * 0.5
+            return (np.eye(shape[0], dtype=np.float32) * uniform(key + "/diag", (shape[0],), 0.5, 1.5)[:, None]
+                    + uniform(key, shape, -a, a)).astype(np.float32)
         return uniform(key, shape, 0.5, 1.5) if leaf == "weight" else uniform(key, shape, -0.2, 0.2)
     if leaf == "gate":
         return np.full(shape, 0.5, np.float32)

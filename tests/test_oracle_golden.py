@@ -189,3 +189,20 @@ def test_beam_search_bookkeeping_matches_hf_helpers(case, lp, early):
     for u in range(U):
         seq = bs.best()[u]
         assert seq == best[u, :len(seq)].tolist() and all(int(t) == EOS for t in best[u, len(seq):])
+
+
+# ---- non-default variants of rows A4 / A5 / A9: full-matrix FDDT, bias-only FDDT, additional encoder layer -------------
+@pytest.mark.parametrize("name,over", [("full_matrix", {"fddt_is_diagonal": False}), ("bias_only", {"fddt_bias_only": True}),
+                                       ("additional_layer", {"additional_layer": True})])
+def test_oracle_variants_match_reference(name, over):
+    g = np.load(os.path.join(GOLD, "variants.npz"))
+    base = {**synth.GOLDEN_MINI.__dict__, "use_enrollments": False, "scb_layers": 0}
+    dm = synth.Dims(**{**base, **over})
+    p = orc.to_torch(synth.make_params(dm, decoder=False))
+    feats = torch.from_numpy(synth.make_features("v0", 2, dm.n_mels, 2 * dm.T))
+    stno = torch.from_numpy(synth.make_stno("v0", 2, dm.T, "soft", pad_tail=5))
+    with torch.no_grad():
+        h = orc.encoder_forward(p, dm, feats, stno)
+        lg = orc.ctc_logits(p, dm, h)
+    np.testing.assert_allclose(h.numpy(), g[name + "/enc"], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(lg.numpy(), g[name + "/ctc_logits"], rtol=2e-4, atol=2e-4)
