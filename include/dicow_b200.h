@@ -100,7 +100,7 @@ typedef struct {
   /* DICOW_EPI_GELU_FDDT_POS_F32 */
   const float* stno;   /* [nb, 4, Mb] fp32, class order S,T,N,O (src/models/dicow/FDDT.py:41-63) */
   int64_t stno_batch_stride; /* elements between batches (4*Mb when dense) */
-  const float* fddt_w; /* [4, N] fp32, rows in S,T,N,O order */
+  const float* fddt_w; /* [4, N] fp32, rows in S,T,N,O order; NULL = bias-only FDDT */
   const float* fddt_b; /* [4, N] */
   const float* pos;    /* [Mb, N] fp32 (embed_positions.weight) or NULL */
   int32_t flags;       /* 0 = auto; bit 0: force the single-CTA kernel; bit 1: force the CTA-pair (cta_group::2) kernel;
@@ -146,6 +146,12 @@ typedef struct {
 
 DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* args, void* stream);
 
+/* full-matrix FDDT (src/models/dicow/layers.py:7-47, FDDT.py:52-62): y bf16 [rows, >= 4 d] holds the four class transforms
+ * of every row side by side (one dicow_gemm_bf16 against the stacked [4 d, d] weight, class order S, T, N, O);
+ * x[r, :] = sum_c stno[r / T, c, r % T] * y[r, c d : (c + 1) d] (+ pos[r % T, :] when pos != NULL), fp32. */
+DICOW_API int dicow_fddt_full_combine(dicow_handle_t h, const void* y_bf16, int64_t ldy, const float* stno,
+                                      int64_t stno_batch_stride, int T, int rows, int d, const float* pos, float* x,
+                                      void* stream);
 /* input_features fp32 [B, C, F] -> zero-padded channels-last bf16 [B, F + 2, C] (the buffer conv1's implicit GEMM
  * reads; src/models/dicow/encoder.py:167 nn.Conv1d(padding=1)). */
 DICOW_API int dicow_features_to_channels_last(dicow_handle_t h, const float* in, void* out_bf16, int B, int C, int F,

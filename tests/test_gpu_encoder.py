@@ -91,3 +91,35 @@ def test_no_cpu_fallback():
     enc, _ = build_encoder(dm, torch.device("cuda:0"))
     with pytest.raises(ops.DicowError):
         enc.cpu()(torch.zeros(1, dm.n_mels, 2 * dm.T), stno_mask=torch.zeros(1, 4, dm.T))
+
+
+@pytest.mark.parametrize("name,over", [("full_matrix", {"fddt_is_diagonal": False}), ("bias_only", {"fddt_bias_only": True}),
+                                       ("additional_layer", {"additional_layer": True})])
+def test_variants_match_reference_golden_and_oracle(name, over):
+    """non-default variants of rows A4 / A5 / A9 (full-matrix FDDT, bias-only FDDT, additional encoder layer) against the
+    reference's own outputs (tests/golden/variants.npz) and the oracle"""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "variants.npz"))
+    base = {**synth.GOLDEN_MINI.__dict__, "use_enrollments": False, "scb_layers": 0}
+    dm = synth.Dims(**{**base, **over})
+    dev = torch.device("cuda:0")
+    enc, p = build_encoder(dm, dev)
+    feats = torch.from_numpy(synth.make_features("v0", 2, dm.n_mels, 2 * dm.T)).to(dev)
+    stno = torch.from_numpy(synth.make_stno("v0", 2, dm.T, "soft", pad_tail=5)).to(dev)
+    with torch.no_grad():
+        out = enc(feats, stno_mask=stno).last_hidden_state
+        lg = enc(feats, stno_mask=stno, return_logits=True).logits
+    e1, e2 = rel_err(out, torch.from_numpy(g[name + "/enc"])), rel_err(lg, torch.from_numpy(g[name + "/ctc_logits"]))
+    print(f"{name}: hidden rel err {e1:.3e}, ctc logits rel err {e2:.3e}")
+    assert e1 < BF16_TOL and e2 < BF16_TOL
+    # whisper-tiny widths as well (d = 384: other tile shapes), against the oracle
+    dm2 = dataclasses.replace(synth.WHISPER_TINY, vocab=1000, enc_layers=2, T=200, **over)
+    enc2, p2 = build_encoder(dm2, dev)
+    f2 = torch.from_numpy(synth.make_features("v1", 2, dm2.n_mels, 2 * dm2.T))
+    s2 = torch.from_numpy(synth.make_stno("v1", 2, dm2.T, "soft", pad_tail=9))
+    with torch.no_grad():
+        ref = orc.encoder_forward(p2, dm2, f2, s2)
+        ref_l = orc.ctc_logits(p2, dm2, ref)
+        o2 = enc2(f2.to(dev), stno_mask=s2.to(dev), return_logits=True)
+    assert rel_err(o2.hidden_states, ref) < BF16_TOL and rel_err(o2.logits, ref_l) < BF16_TOL

@@ -43,12 +43,6 @@ class DiCoWConfig(WhisperConfig):
     # what the CUDA path supports today; anything else raises at model construction instead of silently diverging
     def check_supported(self) -> None:
         unsupported = []
-        if self.use_fddt and not self.fddt_is_diagonal:
-            unsupported.append("fddt_is_diagonal=False (full d x d FDDT)")
-        if self.use_fddt and self.fddt_bias_only:
-            unsupported.append("fddt_bias_only=True")
-        if self.additional_layer and self.ctc_weight > 0:
-            unsupported.append("additional_layer=True (recipes use additional_self_attention_layer)")
         if self.d_model // self.encoder_attention_heads != 64 or self.d_model // self.decoder_attention_heads != 64:
             unsupported.append("head_dim != 64")
         if self.activation_function != "gelu":

@@ -196,6 +196,37 @@ __global__ void __launch_bounds__(128) ln_rows_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// full-matrix FDDT (CustomLinear per class, src/models/dicow/layers.py:7-47 + FDDT.py:52-62): the four class transforms are
+// ONE GEMM y = x [W_S; W_T; W_N; W_O]^T + [b_S; ...] (bf16 [rows, 4 d], like the reference's autocast Linear outputs);
+// this kernel forms the mask-weighted sum in fp32:  x'[r, :] = sum_c stno[b, c, t] * y[r, c d : (c + 1) d]  (+ pos[t, :]).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fddt_full_combine_kernel(const __nv_bfloat16* __restrict__ y, long long ldy,
+                                                                const float* __restrict__ stno, long long stno_bs, int T,
+                                                                int rows, int d, const float* __restrict__ pos,
+                                                                float* __restrict__ x) {
+  const int nvec = d >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / nvec), c4 = (int)(i - (long long)r * nvec);
+    const int b = r / T, t = r - b * T;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float m = __ldg(stno + (long long)b * stno_bs + (long long)c * T + t);
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(y + (long long)r * ldy + (long long)c * d) + c4);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      acc.x = fmaf(m, a.x, acc.x), acc.y = fmaf(m, a.y, acc.y), acc.z = fmaf(m, e.x, acc.z), acc.w = fmaf(m, e.y, acc.w);
+    }
+    if (pos != nullptr) {
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(pos + (long long)t * d) + c4);
+      acc.x += pv.x, acc.y += pv.y, acc.z += pv.z, acc.w += pv.w;
+    }
+    reinterpret_cast<float4*>(x + (long long)r * d)[c4] = acc;
+  }
+}
+
 // TMA-pipelined variant (default): one producer warp streams rows (x fp32 + up to two bf16 deltas) into a 16-stage
 // shared-memory ring with cp.async.bulk + mbarrier transaction counts; 16 consumer warps each take a row from the ring,
 // so the HBM latency is hidden by the ring depth (160 KB in flight per SM) instead of by occupancy -- the register-
@@ -305,6 +336,7 @@ __global__ void __launch_bounds__((LT_NW + 1) * 32, 1) fddt_ln_tma_kernel(const 
             bb.x = fmaf(m[c], bc.x, bb.x), bb.y = fmaf(m[c], bc.y, bb.y), bb.z = fmaf(m[c], bc.z, bb.z),
             bb.w = fmaf(m[c], bc.w, bb.w);
           }
+          if (p.fddt_w == nullptr) w = make_float4(1.f, 1.f, 1.f, 1.f);  // bias-only FDDT (FDDT.py:43-51): h += sum_c m_c b_c
           v[k].x = fmaf(v[k].x, w.x, bb.x), v[k].y = fmaf(v[k].y, w.y, bb.y);
           v[k].z = fmaf(v[k].z, w.z, bb.z), v[k].w = fmaf(v[k].w, w.w, bb.w);
         }
@@ -443,6 +475,7 @@ __global__ void __launch_bounds__(512) fddt_ln_cols_kernel(const FddtLnParams p,
             bb.x = fmaf(m, tb[c].x, bb.x), bb.y = fmaf(m, tb[c].y, bb.y), bb.z = fmaf(m, tb[c].z, bb.z),
             bb.w = fmaf(m, tb[c].w, bb.w);
           }
+          if (p.fddt_w == nullptr) w = make_float4(1.f, 1.f, 1.f, 1.f);  // bias-only FDDT
           v[r].x = fmaf(v[r].x, w.x, bb.x), v[r].y = fmaf(v[r].y, w.y, bb.y);
           v[r].z = fmaf(v[r].z, w.z, bb.z), v[r].w = fmaf(v[r].w, w.w, bb.w);
         }
@@ -625,6 +658,23 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
 #undef DICOW_CASE
     default: return set_error(ctx, DICOW_ERR_UNSUPPORTED, "dicow_fddt_layernorm: d=%d unsupported", a->d);
   }
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_fddt_full_combine(dicow_handle_t h, const void* y_bf16, int64_t ldy, const float* stno,
+                                       int64_t stno_batch_stride, int T, int rows, int d, const float* pos, float* x,
+                                       void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, y_bf16 && stno && x && rows >= 1 && T >= 1 && (rows % T) == 0 && d >= 4 && (d % 4) == 0 && (ldy % 4) == 0 &&
+                         (reinterpret_cast<uintptr_t>(y_bf16) % 8) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0,
+                "dicow_fddt_full_combine: bad args");
+  const long long total = (long long)rows * (d / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  fddt_full_combine_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy, stno, stno_batch_stride, T, rows, d, pos, x);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

@@ -182,9 +182,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
           float w = 0.f, bb = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            w = fmaf(mask[c], __ldg(p.fddt_w + (long long)c * p.N + n + j), w);
+            if (p.fddt_w != nullptr) w = fmaf(mask[c], __ldg(p.fddt_w + (long long)c * p.N + n + j), w);
             bb = fmaf(mask[c], __ldg(p.fddt_b + (long long)c * p.N + n + j), bb);
           }
+          if (p.fddt_w == nullptr) w = 1.f;  // bias-only FDDT (FDDT.py:43-51)
           float x = fmaf(v[j], w, bb);
           if (p.pos != nullptr) x += __ldg(p.pos + (long long)m * p.N + n + j);
           v[j] = x;
@@ -713,7 +714,7 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   }
   if (a->epilogue == DICOW_EPI_RESIDUAL_F32) DICOW_REQUIRE(ctx, a->resid != nullptr, "dicow_gemm_bf16: resid is NULL");
   if (a->epilogue == DICOW_EPI_GELU_FDDT_POS_F32)
-    DICOW_REQUIRE(ctx, a->stno && a->fddt_w && a->fddt_b, "dicow_gemm_bf16: FDDT epilogue needs stno/fddt_w/fddt_b");
+    DICOW_REQUIRE(ctx, a->stno && a->fddt_b, "dicow_gemm_bf16: FDDT epilogue needs stno / fddt_b (fddt_w NULL = bias-only)");
 
   const bool a_t = (a->flags & 4) != 0;  // A given as At[k][m] (row stride lda)
   const bool w_t = (a->flags & 8) != 0;  // W given as Wt[k][n] (row stride ldw)

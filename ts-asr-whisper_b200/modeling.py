@@ -51,32 +51,77 @@ class CustomDiagonalLinear(nn.Module):
                 self.weight.fill_(self.init_eye_val)
 
 
+class CustomLinear(nn.Linear):
+    """nn.Linear with the FDDT inits of src/models/dicow/layers.py:7-47 (full d x d class transform)."""
+
+    def __init__(self, *args, init_eye_val: float = 0.0, fddt_init: Optional[str] = None, **kwargs):
+        self.init_eye_val, self.fddt_init = init_eye_val, fddt_init
+        super().__init__(*args, **kwargs)
+
+    def reset_parameters(self) -> None:
+        with torch.no_grad():
+            nn.init.xavier_uniform_(self.weight)
+            if self.bias is not None:
+                self.bias.zero_()
+            scale = {"non-disturbing": 1.0, "suppressive": self.init_eye_val}.get(self.fddt_init)
+            if scale is not None:
+                n = min(self.weight.shape)
+                self.weight.zero_()
+                self.weight[:n, :n] = scale * torch.eye(n, device=self.weight.device)
+
+
 class FDDT(nn.Module):
-    """Diagonal Frame-level Diarization-Dependent Transformation parameters (src/models/dicow/FDDT.py:6-40)."""
+    """Frame-level Diarization-Dependent Transformation parameters (src/models/dicow/FDDT.py:6-40): per STNO class a
+    diagonal transform (default), a full d x d one (``is_diagonal=False``) or a bias vector (``bias_only``)."""
 
     def __init__(self, d_model: int, non_target_rate: float = 0.01, fddt_init: Optional[str] = None,
-                 use_silence: bool = True, use_target: bool = True, use_overlap: bool = True,
-                 use_non_target: bool = True):
+                 is_diagonal: bool = True, bias_only: bool = False, use_silence: bool = True, use_target: bool = True,
+                 use_overlap: bool = True, use_non_target: bool = True):
         super().__init__()
-        self.d_model = d_model
+        self.d_model, self.is_diagonal, self.bias_only = d_model, is_diagonal, bias_only
+
+        def make(eye_val: float):
+            if bias_only:
+                return nn.Parameter(torch.zeros(d_model))
+            if is_diagonal:
+                return CustomDiagonalLinear(d_model, True, eye_val, fddt_init)
+            return CustomLinear(d_model, d_model, bias=True, fddt_init=fddt_init, init_eye_val=eye_val)
+
         if use_target:
-            self.target_linear = CustomDiagonalLinear(d_model, True, 1.0, fddt_init)
+            self.target_linear = make(1.0)
         if use_non_target:
-            self.non_target_linear = CustomDiagonalLinear(d_model, True, non_target_rate, fddt_init)
+            self.non_target_linear = make(non_target_rate)
         if use_overlap:
-            self.overlap_linear = CustomDiagonalLinear(d_model, True, 1.0, fddt_init)
+            self.overlap_linear = make(1.0)
         if use_silence:
-            self.silence_linear = CustomDiagonalLinear(d_model, True, non_target_rate, fddt_init)
+            self.silence_linear = make(non_target_rate)
 
     def tables(self):
-        """([4, d] weights, [4, d] biases) in STNO order; a disabled class is the identity (FDDT.py:54-62)."""
+        """([4, d] weights or None for the bias-only variant, [4, d] biases) in STNO order; a disabled class is the
+        identity (FDDT.py:54-62).  Diagonal / bias-only variants."""
         ref = next(self.parameters())
         ws, bs = [], []
         for c in _FDDT_ORDER:
             lin = getattr(self, c + "_linear", None)
+            if self.bias_only:
+                bs.append(lin if lin is not None else torch.zeros(self.d_model, device=ref.device))
+                continue
             ws.append(lin.weight if lin is not None else torch.ones(self.d_model, device=ref.device))
             bs.append(lin.bias if lin is not None else torch.zeros(self.d_model, device=ref.device))
-        return torch.stack(ws).float().contiguous(), torch.stack(bs).float().contiguous()
+        w = None if self.bias_only else torch.stack(ws).detach().float().contiguous()
+        return w, torch.stack(bs).detach().float().contiguous()
+
+    def full_tables(self):
+        """full-matrix variant: the four class transforms stacked into ONE projection (bf16 [4 d, d], fp32 bias [4 d]) in
+        STNO order; a disabled class is the identity"""
+        ref = next(self.parameters())
+        d = self.d_model
+        ws, bs = [], []
+        for c in _FDDT_ORDER:
+            lin = getattr(self, c + "_linear", None)
+            ws.append(lin.weight.detach().float() if lin is not None else torch.eye(d, device=ref.device))
+            bs.append(lin.bias.detach().float() if lin is not None else torch.zeros(d, device=ref.device))
+        return ops.cast_bf16(torch.cat(ws, 0).contiguous()), torch.cat(bs).contiguous()
 
 
 class Gate(nn.Module):
@@ -195,6 +240,8 @@ class DiCoWEncoder(nn.Module):
         self.layers = nn.ModuleList([EncoderLayerParams(d, config.encoder_ffn_dim)
                                      for _ in range(config.encoder_layers)])
         self.layer_norm = nn.LayerNorm(d)
+        if config.additional_layer and self.ctc_weight > 0.0:  # encoder.py:16-17
+            self.additional_layer = EncoderLayerParams(d, config.encoder_ffn_dim)
         if config.additional_self_attention_layer and self.ctc_weight > 0.0:
             self.additional_self_attention_layer = AttentionParams(d)
         if config.pre_ctc_sub_sample and self.ctc_weight > 0.0:
@@ -204,7 +251,8 @@ class DiCoWEncoder(nn.Module):
             self.lm_head = nn.Linear(d, config.vocab_size + 1, bias=False)
         if config.use_fddt:
             n = config.apply_fddt_to_n_layers if config.apply_fddt_to_n_layers != -1 else len(self.layers)
-            kw = dict(fddt_init=config.fddt_init, use_silence=config.fddt_use_silence,
+            kw = dict(fddt_init=config.fddt_init, is_diagonal=config.fddt_is_diagonal, bias_only=config.fddt_bias_only,
+                      use_silence=config.fddt_use_silence,
                       use_target=config.fddt_use_target, use_overlap=config.fddt_use_overlap,
                       use_non_target=config.fddt_use_non_target)
             self.fddts = nn.ModuleList([FDDT(d, non_target_rate=1.0, **kw) for _ in range(n)])
@@ -262,11 +310,17 @@ class DiCoWEncoder(nn.Module):
         w["conv1_w"], w["conv1_b"] = _conv_weight(self.conv1.weight), _f32(self.conv1.bias)
         w["conv2_w"], w["conv2_b"] = _conv_weight(self.conv2.weight), _f32(self.conv2.bias)
         w["pos"] = _f32(self.embed_positions.weight)
-        if cfg.use_fddt and cfg.use_pre_pos_fddt:
+        full = cfg.use_fddt and not cfg.fddt_is_diagonal and not cfg.fddt_bias_only  # CustomLinear per class
+        w["fddt_full"] = full
+        if cfg.use_fddt and cfg.use_pre_pos_fddt and not full:
             w["fddt0"] = self.initial_fddt.tables()
         else:  # identity FDDT for the conv2 epilogue
             w["fddt0"] = (torch.ones(4, d, device=dev), torch.zeros(4, d, device=dev))
-        w["fddt"] = [f.tables() for f in self.fddts] if cfg.use_fddt else []
+        if full:
+            w["fddt"] = [f.full_tables() for f in self.fddts]
+            w["fddt0_full"] = self.initial_fddt.full_tables() if cfg.use_pre_pos_fddt else None
+        else:
+            w["fddt"] = [f.tables() for f in self.fddts] if cfg.use_fddt else []
         layers = []
         for lyr in self.layers:
             e = _prep_attention(lyr.self_attn)
@@ -286,7 +340,15 @@ class DiCoWEncoder(nn.Module):
                 e["gate"] = _f32(blk.cae.cross_gate.gate)
                 scbs.append(e)
             w["scb"] = scbs
-        if hasattr(self, "additional_self_attention_layer"):
+        if hasattr(self, "additional_layer"):  # used INSTEAD of the extra self-attention (encoder.py:88-100)
+            lyr = self.additional_layer
+            e = _prep_attention(lyr.self_attn)
+            e["ln1_g"], e["ln1_b"] = _f32(lyr.self_attn_layer_norm.weight), _f32(lyr.self_attn_layer_norm.bias)
+            e["ln2_g"], e["ln2_b"] = _f32(lyr.final_layer_norm.weight), _f32(lyr.final_layer_norm.bias)
+            e["w1"], e["b1"] = _bf16(lyr.fc1.weight), _f32(lyr.fc1.bias)
+            e["w2"], e["b2"] = _bf16(lyr.fc2.weight), _f32(lyr.fc2.bias)
+            w["ctc_layer"] = e
+        elif hasattr(self, "additional_self_attention_layer"):
             w["ctc_attn"] = _prep_attention(self.additional_self_attention_layer)
         if hasattr(self, "subsample_conv1"):
             w["sub1"] = _conv_weight(self.subsample_conv1.weight)
@@ -346,7 +408,28 @@ class DiCoWEncoder(nn.Module):
         d = cfg.d_model
         dev = hb.device
         sub = "sub1" in w
-        if "ctc_attn" in w:
+        if "ctc_layer" in w:  # a whole pre-LN encoder layer on the final hidden state (encoder.py:88-93)
+            e = w["ctc_layer"]
+            rows, ffn = B * T, e["w1"].shape[0]
+            x = hb.view(rows, d).float()
+            ln = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln)
+            ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            self._self_attention(e, ln, B, T, ctx, d, T * d)
+            d1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(ctx, e["wo"], d1, epilogue=ops.EPI_BIAS_BF16, bias=e["bo"])
+            ops.fddt_layernorm(x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=ln, delta1=d1, store_x=False)
+            hdn = torch.empty(rows, ffn, dtype=torch.bfloat16, device=dev)
+            ops.gemm(ln, e["w1"], hdn, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"])
+            d2 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(hdn, e["w2"], d2, epilogue=ops.EPI_BIAS_BF16, bias=e["b2"])
+            hb = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, x_out_bf16=hb.view(rows, d), delta1=d1, delta2=d2, store_x=False)  # x + d1 + d2 -> bf16
+            if not sub:
+                return hb
+            buf = torch.zeros(B, T + 2, d, dtype=torch.bfloat16, device=dev)
+            buf[:, 1:T + 1] = hb
+        elif "ctc_attn" in w:
             e = w["ctc_attn"]
             ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=dev)
             self._self_attention(e, hb.view(B * T, d), B, T, ctx, d, T * d)
@@ -447,9 +530,21 @@ class DiCoWEncoder(nn.Module):
             stno0 = torch.zeros(Bx, 4, T, dtype=torch.float32, device=dev)
             stno0[:, 0] = 1.0
         fw0, fb0 = w["fddt0"]
-        ops.gemm(a1, w["conv2_w"], x, epilogue=ops.EPI_GELU_FDDT_POS_F32, bias=w["conv2_b"], nb=Bx, Mb=T, K=3 * d,
-                 lda=2 * d, a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, stno=stno0,
-                 stno_batch_stride=4 * T, fddt_w=fw0, fddt_b=fb0, pos=w["pos"])
+        if w["fddt_full"] and w.get("fddt0_full") is not None:
+            # full-matrix initial FDDT (encoder.py:173-179 with CustomLinear): gelu(conv2) in bf16, the four class
+            # transforms as one GEMM, mask-weighted sum + positions in fp32
+            g2 = torch.empty(Bx * T, d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(a1, w["conv2_w"], g2, epilogue=ops.EPI_BIAS_GELU_BF16, bias=w["conv2_b"], nb=Bx, Mb=T, K=3 * d,
+                     lda=2 * d, a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d)
+            W4, b4 = w["fddt0_full"]
+            y = torch.empty(Bx * T, 4 * d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(g2, W4, y, epilogue=ops.EPI_BIAS_BF16, bias=b4)
+            ops.fddt_full_combine(y, stno, x, T=T, pos=w["pos"])
+            del g2, y
+        else:
+            ops.gemm(a1, w["conv2_w"], x, epilogue=ops.EPI_GELU_FDDT_POS_F32, bias=w["conv2_b"], nb=Bx, Mb=T, K=3 * d,
+                     lda=2 * d, a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, stno=stno0,
+                     stno_batch_stride=4 * T, fddt_w=fw0, fddt_b=fb0, pos=w["pos"])
         del a0, a1
         # ---- layers (encoder.py:191-223) ----
         # The out_proj / fc2 GEMMs write their bf16 outputs (d1, d2) instead of read-modify-writing the fp32 residual
@@ -466,6 +561,16 @@ class DiCoWEncoder(nn.Module):
             rows = Bx * T
             ln = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
             fd = w["fddt"][i] if (cfg.use_fddt and i < len(w["fddt"])) else None
+            if fd is not None and w["fddt_full"]:
+                # full-matrix FDDT (layers.py:7-47): fold the pending deltas, project the bf16 stream with the stacked
+                # [4 d, d] class transforms, take the mask-weighted sum back into the fp32 stream
+                xb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+                ops.fddt_layernorm(x, x_out_bf16=xb, delta1=d1, delta2=d2, store_x=True)
+                y = torch.empty(rows, 4 * d, dtype=torch.bfloat16, device=dev)
+                ops.gemm(xb, fd[0], y, epilogue=ops.EPI_BIAS_BF16, bias=fd[1])
+                ops.fddt_full_combine(y, stno, x.view(rows, d), T=T)
+                del xb, y
+                fd, d1, d2 = None, None, None
             if i < n_scb:
                 xb = torch.empty(Bx, T, d, dtype=torch.bfloat16, device=dev)
                 ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,

@@ -176,6 +176,24 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
     _call("dicow_fddt_layernorm", dev, a, "fddt_ln")
 
 
+def fddt_full_combine(y: torch.Tensor, stno: torch.Tensor, x: torch.Tensor, *, T: int, pos: Optional[torch.Tensor] = None
+                      ) -> torch.Tensor:
+    """x[r] = sum_c stno[r // T, c, r % T] * y[r, c d:(c + 1) d] (+ pos[r % T]) -- the mask-weighted sum of the four class
+    transforms of full-matrix FDDT (dicow_fddt_full_combine); y bf16 [rows, 4 d], x fp32 [rows, d]."""
+    global launch_count
+    dev = _require_cuda(y, stno, x, pos)
+    rows, d = x.numel() // x.shape[-1], x.shape[-1]
+    assert y.dtype == torch.bfloat16 and y.stride(-1) == 1 and x.dtype == torch.float32 and x.is_contiguous()
+    assert stno.dtype == torch.float32 and stno.stride(2) == 1 and stno.stride(1) == stno.shape[2]
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_fddt_full_combine(h, _ptr(y), y.stride(-2), _ptr(stno), stno.stride(0), T, rows, d,
+                                                         _ptr(pos), _ptr(x), _stream(dev))
+    _lib.check(rc, h, "dicow_fddt_full_combine")
+    launch_count += 1
+    return x
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tq: int,
               Tk: int, q_row_stride: int, q_batch_stride: int, kv_row_stride: int, kv_batch_stride: int,
               o_row_stride: int, o_batch_stride: int, causal: bool = False, variant: int = 0,

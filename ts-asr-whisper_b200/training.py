@@ -196,6 +196,9 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
     the per-layer inputs the backward needs.  Returns (last_hidden fp32 [B, T, d], bf16 copy [B*T, d]).
     With ``enrollments`` the first ``scb_layers`` layers run on the stacked [targets ; enrollments] streams."""
     cfg = enc.config
+    if cfg.use_fddt and (cfg.fddt_bias_only or not cfg.fddt_is_diagonal):
+        raise NotImplementedError("training step: only the recipes' diagonal FDDT has a backward on the B200 path "
+                                  "(bias-only / full-matrix FDDT run forward-only)")
     n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers and enrollments is not None) else 0
     if n_scb:  # encoder.py:152-154 (stacked instead of interleaved, see the module docstring)
         input_features = torch.cat((input_features, enrollments["input_features"].to(input_features.device)), dim=0)
@@ -289,6 +292,9 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
 
 def ctc_head_forward_train(enc, hidden_bf16: torch.Tensor, B: int, T: int, tape: EncoderTape) -> torch.Tensor:
     """possibly_update_last_hidden_states + lm_head (encoder.py:87-106,236) keeping the backward's inputs."""
+    if hasattr(enc, "additional_layer"):
+        raise NotImplementedError("training step: additional_layer=True runs forward-only on the B200 path (the recipes "
+                                  "use additional_self_attention_layer)")
     cfg = enc.config
     w = enc.prepare()
     d, H = cfg.d_model, cfg.encoder_attention_heads
