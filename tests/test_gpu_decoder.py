@@ -501,3 +501,34 @@ def test_generate_joint_ctc_long_form(mini):
     beams = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, num_beams=3, length_penalty=0.1, **kw)
     beams2 = model.generate(long_feats.to(DEV), ctc_weight=0.3, ctc_tokens_to_score=40, num_beams=3, length_penalty=0.1, **kw)
     assert beams["sequences"].shape[0] == 2 and torch.equal(beams["sequences"], beams2["sequences"])
+
+
+def test_detect_language_and_prompt_without_forced_ids(mini):
+    """generation.py:151-221: one decoder step on <|sot|> over the first window, non-language logits masked, argmax --
+    against the oracle's forward; generate() without forced_decoder_ids builds <|sot|> <|lang|> <|task|> from it"""
+    g, dmp, model, p, feats, stno = mini
+    model.tokenizer, model.soft_label_creator = None, None
+    lang_to_id = {"<|aa|>": 259, "<|bb|>": 30, "<|cc|>": 77, "<|dd|>": 201}
+    gc = model.generation_config
+    gc.lang_to_id, gc.task_to_id = lang_to_id, {"transcribe": TASK, "translate": 5}
+    gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = NOTS, EOS, EOS
+    gc.suppress_tokens, gc.return_timestamps, gc.max_new_tokens, gc.num_beams = SUPPRESS, True, 6, 1
+    gc.decoder_start_token_id = SOT
+    ids = model.detect_language(input_features=feats.to(DEV), stno_mask=stno.to(DEV))
+    with torch.no_grad():
+        ref_enc = orc.encoder_forward(p, dmp, feats, stno)
+        hid = orc.decoder_forward(p, dmp, torch.full((2, 1), SOT), ref_enc)
+        logits = torch.nn.functional.linear(hid[:, -1], p["proj_out.weight"])
+    keep = torch.tensor(sorted(lang_to_id.values()))
+    ref = keep[logits[:, keep].argmax(-1)]
+    top2 = logits[:, keep].topk(2, dim=-1).values
+    for b in range(2):
+        if float(top2[b, 0] - top2[b, 1]) > MARGIN:
+            assert int(ids[b]) == int(ref[b])
+    out = model.generate(feats.to(DEV), stno_mask=stno.to(DEV), return_segments=True)
+    assert out["sequences"].shape[0] == 2
+    forced = model.generate(feats.to(DEV), stno_mask=stno.to(DEV), return_segments=True,
+                            forced_decoder_ids=torch.stack([torch.full((2,), SOT), ids.cpu(), torch.full((2,), TASK)], 1))
+    assert torch.equal(out["sequences"], forced["sequences"])
+    with pytest.raises(ValueError):
+        model.generate(feats.to(DEV), stno_mask=stno.to(DEV), language="zz")

@@ -799,10 +799,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         fdi = gs["forced_decoder_ids"]
         if fdi is None:
             fdi = getattr(cfg, "forced_decoder_ids", None)
-        if fdi is None:
-            raise NotImplementedError("language detection (no forced_decoder_ids) is a SURVEY section 8f 'next' row; "
-                                      "the recipes always pass the language/task prompt (provide_gt_lang)")
         dev = input_features.device
+        if fdi is None:  # generation.py:145-147 -> HF _retrieve_init_tokens: <|sot|> <|lang|> <|task|> [<|notimestamps|>]
+            self.stno_mask = stno_mask
+            fdi = self._init_tokens_without_forced_ids(input_features, stno_mask, enrollments, generation_config, kwargs, gs)
         init_tokens = torch.as_tensor(fdi, dtype=torch.int64, device=dev)
         if init_tokens.dim() == 1:
             init_tokens = init_tokens[None].expand(input_features.shape[0], -1)
@@ -925,6 +925,70 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         if self.tokenizer is not None:
             return self._fix_timestamps_from_segmentation(outputs)
         return outputs["sequences"]
+
+    # ---- language detection / prompt construction without forced_decoder_ids ------------------------------------------
+    @torch.no_grad()
+    def detect_language(self, input_features: Optional[torch.Tensor] = None, encoder_outputs=None, generation_config=None,
+                        num_segment_frames: int = 3000, stno_mask: Optional[torch.Tensor] = None,
+                        enrollments: Optional[dict] = None) -> torch.Tensor:
+        """src/models/dicow/generation.py:151-221: one decoder step on <|startoftranscript|> over the first window, every
+        non-language logit masked, argmax.  Returns int64 language token ids [B]."""
+        if input_features is None and encoder_outputs is None:
+            raise ValueError("You have to specify either `input_features` or `encoder_outputs`")
+        if input_features is not None and encoder_outputs is not None:
+            raise ValueError("Make sure to specify only one of `input_features` or `encoder_outputs` - not both!")
+        gc = generation_config or self.generation_config
+        lang_to_id = getattr(gc, "lang_to_id", None)
+        if not lang_to_id:
+            raise ValueError("detect_language needs generation_config.lang_to_id")
+        stno = stno_mask if stno_mask is not None else self.stno_mask
+        if input_features is not None:
+            B = input_features.shape[0]
+            feats = input_features[:, :, :num_segment_frames]
+            dev = feats.device
+        else:
+            enc0 = encoder_outputs[0] if not isinstance(encoder_outputs, torch.Tensor) else encoder_outputs
+            B, dev, feats = enc0.shape[0], enc0.device, None
+        start = getattr(gc, "decoder_start_token_id", None) or self.config.decoder_start_token_id
+        ids = torch.full((B, 1), int(start), dtype=torch.int64, device=dev)
+        out = self._forward_inference(feats, stno[:, :, :num_segment_frames // 2] if stno is not None else None, ids,
+                                      encoder_outputs, None, None, True, enrollments)
+        logits = out.logits[:, -1].float()
+        keep = torch.zeros(logits.shape[-1], dtype=torch.bool, device=dev)
+        keep[torch.as_tensor(sorted(int(v) for v in lang_to_id.values()), device=dev)] = True
+        return logits.masked_fill(~keep, -float("inf")).argmax(-1)
+
+    def _init_tokens_without_forced_ids(self, input_features, stno_mask, enrollments, generation_config, kwargs, gs):
+        """HF WhisperGenerationMixin._retrieve_init_tokens (third-party; reached from generation.py:145-147 when no
+        forced_decoder_ids are given): <|startoftranscript|>, the language token (given or detected per recording on its
+        first window), the task token (default transcribe), <|notimestamps|> unless timestamps are returned."""
+        gc = generation_config if generation_config is not None else self.generation_config
+        lang_to_id, task_to_id = getattr(gc, "lang_to_id", None), getattr(gc, "task_to_id", None)
+        if not lang_to_id or not task_to_id:
+            raise ValueError("generate() without forced_decoder_ids needs generation_config.lang_to_id / task_to_id "
+                             "(a multilingual Whisper generation config)")
+        B = input_features.shape[0]
+        start = int(getattr(gc, "decoder_start_token_id", None) or self.config.decoder_start_token_id)
+        language = kwargs.get("language", getattr(gc, "language", None))
+        task = kwargs.get("task", getattr(gc, "task", None)) or "transcribe"
+        if task not in task_to_id:
+            raise ValueError(f"The `{task}` task is not supported. The task should be one of `{list(task_to_id)}`")
+        if language is not None:
+            langs = [language] * B if isinstance(language, str) else list(language)
+            lang_ids = []
+            for lg in langs:
+                tok = lg if lg in lang_to_id else f"<|{lg}|>"
+                if tok not in lang_to_id:
+                    raise ValueError(f"Unsupported language: {lg}. Language should be one of: {list(lang_to_id)}.")
+                lang_ids.append(int(lang_to_id[tok]))
+            lang_ids = torch.tensor(lang_ids, dtype=torch.int64)
+        else:
+            lang_ids = self.detect_language(input_features=input_features, generation_config=gc, stno_mask=stno_mask,
+                                            enrollments=enrollments).cpu()
+        cols = [torch.full((B,), start, dtype=torch.int64), lang_ids, torch.full((B,), int(task_to_id[task]), dtype=torch.int64)]
+        if not gs["return_timestamps"]:
+            cols.append(torch.full((B,), gs["no_timestamps"], dtype=torch.int64))
+        return torch.stack(cols, dim=1)
 
     @staticmethod
     def _retrieve_segment(seq: torch.Tensor, time_offset: float, timestamp_begin: int, seek_num_frames: int,
