@@ -341,6 +341,13 @@ typedef struct {
 
 DICOW_API int dicow_logmel(dicow_handle_t h, const dicow_logmel_args_t* args, void* stream);
 
+/* STNO mask of one recording from per-speaker sample-level activity (src/data/local_datasets.py:162-196: get_stno_mask /
+ * _create_stno_masks).  activity: uint8 [n_speakers, ld >= n_samples] (non-zero = speaking); target = row of the target
+ * speaker or -1; frames = padded length / frame_samples (320); out[t * frame_stride + c * class_stride], c = S, T, N, O. */
+DICOW_API int dicow_stno_mask(dicow_handle_t h, const uint8_t* activity, int64_t ld, int n_speakers, int64_t n_samples,
+                              int target, int frame_samples, int64_t frames, float* out, int64_t frame_stride,
+                              int64_t class_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Token-by-token decoder step (greedy generate()).  Replaces, per generated token, HF WhisperDecoder.forward with a KV
  * cache (HF:modeling_whisper.py:449-506, 691-796), proj_out (src/models/dicow/modeling_dicow.py:302) and the greedy

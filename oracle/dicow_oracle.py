@@ -102,6 +102,36 @@ def log_mel(wave: np.ndarray, n_mels: int, chunk_samples: int = 480000, n_fft: i
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# A2  STNO mask from per-speaker sample-level activity (src/data/local_datasets.py:162-196)
+# ----------------------------------------------------------------------------------------------------------------
+def stno_mask(activity: np.ndarray, target: int, window_samples: int = 480000, frame_samples: int = 320) -> np.ndarray:
+    """activity [n_speakers, n_samples] bool, ``target`` = row of the target speaker (-1: none of them).  Zero-pad to whole
+    30 s windows, a_i[t] = mean activity of speaker i over the 320 samples of encoder frame t, then per frame
+      S = prod_i (1 - a_i),  T = a_s prod_{i != s} (1 - a_i),  N = (1 - a_s)(1 - prod_{i != s} (1 - a_i)),  O = a_s - T
+    in float32, speakers multiplied in row order.  Returns [frames, 4] (S, T, N, O) like the reference."""
+    n_spk, n = activity.shape
+    pad = (window_samples - n) % window_samples
+    frames = (n + pad) // frame_samples
+    a = np.zeros((n_spk, frames), np.float32)
+    for i in range(n_spk):
+        row = np.zeros(n + pad, np.float32)
+        row[:n] = activity[i]
+        a[i] = row.reshape(frames, frame_samples).sum(axis=1) / np.float32(frame_samples)
+    out = np.zeros((frames, 4), np.float32)
+    one = np.float32(1.0)
+    sil = np.ones(frames, np.float32)
+    others = np.ones(frames, np.float32)
+    for i in range(n_spk):
+        sil = sil * (one - a[i])
+        if i != target:
+            others = others * (one - a[i])
+    a_s = a[target] if target >= 0 else np.zeros(frames, np.float32)
+    tgt = a_s * others
+    out[:, 0], out[:, 1], out[:, 2], out[:, 3] = sil, tgt, (one - a_s) * (one - others), a_s - tgt
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # A4/A5  FDDT
 # ----------------------------------------------------------------------------------------------------------------
 _FDDT_ORDER = ("silence", "target", "non_target", "overlap")  # STNO mask channel order, FDDT.py:56-62

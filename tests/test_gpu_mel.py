@@ -55,3 +55,20 @@ def test_logmel_matches_oracle(n_samples):
         err = np.abs(out[i].cpu().numpy() - rf).max()
         assert err < TOL, f"row {i}: max abs err {err}"
         assert np.array_equal(mask[i].cpu().numpy(), rm)
+
+
+@pytest.mark.parametrize("name", ["three_spk", "one_spk", "no_target", "four_spk_first"])
+def test_stno_mask_kernel_bit_exact(name):
+    """A2 (src/data/local_datasets.py:162-196) on the GPU: bit-exact against the reference's own output and the oracle"""
+    import os
+    import numpy as np
+    from ts_asr_whisper_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stno_mask.npz"))
+    n_spk, n_samples, target = [int(v) for v in g[name + "/meta"]]
+    act = np.unpackbits(g[name + "/activity"], axis=1)[:, :n_samples].astype(bool)
+    out = ops.stno_mask(torch.from_numpy(act).to("cuda:0"), target)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), g[name + "/stno"])
+    assert np.array_equal(out.cpu().numpy(), orc.stno_mask(act, target))
+    cf = ops.stno_mask(torch.from_numpy(act).to("cuda:0"), target, channels_first=True)
+    assert torch.equal(cf.t().contiguous(), out)

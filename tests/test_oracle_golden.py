@@ -206,3 +206,22 @@ def test_oracle_variants_match_reference(name, over):
         lg = orc.ctc_logits(p, dm, h)
     np.testing.assert_allclose(h.numpy(), g[name + "/enc"], rtol=2e-4, atol=2e-4)
     np.testing.assert_allclose(lg.numpy(), g[name + "/ctc_logits"], rtol=2e-4, atol=2e-4)
+
+
+# ---- A2: STNO mask from speaker activity, oracle vs the reference's own _create_stno_masks --------------------------------
+STNO_CASES = ["three_spk", "one_spk", "no_target", "four_spk_first"]
+
+
+def _stno_case(name):
+    g = np.load(os.path.join(GOLD, "stno_mask.npz"))
+    n_spk, n_samples, target = [int(v) for v in g[name + "/meta"]]
+    act = np.unpackbits(g[name + "/activity"], axis=1)[:, :n_samples].astype(bool)
+    return act, target, g[name + "/stno"]
+
+
+@pytest.mark.parametrize("name", STNO_CASES)
+def test_stno_mask_oracle_matches_reference(name):
+    act, target, ref = _stno_case(name)
+    out = orc.stno_mask(act, target)
+    assert out.shape == ref.shape
+    np.testing.assert_array_equal(out, ref)  # bit-exact: 0/1 means and products in the reference's order

@@ -213,6 +213,38 @@ __global__ void __launch_bounds__(256) logmel_finalize_kernel(const MelParams p)
 
 constexpr size_t kMelSmem = (size_t)(2 * NFP * FR + RAW) * sizeof(float) + 256 * sizeof(int);
 
+// ------------------------------------------------------------------------------------------------------------------
+// STNO mask from per-speaker sample-level activity (src/data/local_datasets.py:162-196): one thread per encoder frame;
+// a_i = mean of speaker i's 0/1 activity over the frame's 320 samples (zero past the end of the recording), then
+//   S = prod_i (1 - a_i), T = a_s prod_{i != s} (1 - a_i), N = (1 - a_s)(1 - prod_{i != s} (1 - a_i)), O = a_s - T
+// in fp32 with the speakers multiplied in row order (bit-exact against numpy).  HBM-bound: n_speakers bytes per sample.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stno_mask_kernel(const unsigned char* __restrict__ act, long long ld, int n_spk,
+                                                        long long n_samples, int target, int frame_samples, long long frames,
+                                                        float* __restrict__ out, long long frame_stride, long long class_stride) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  const long long s0 = t * frame_samples;
+  float sil = 1.f, others = 1.f, a_s = 0.f;
+  for (int i = 0; i < n_spk; ++i) {
+    const unsigned char* row = act + (long long)i * ld + s0;
+    int cnt = 0;
+    for (int k = 0; k < frame_samples; ++k)
+      if (s0 + k < n_samples) cnt += row[k] != 0;
+    const float a = __fdiv_rn((float)cnt, (float)frame_samples);
+    const float na = __fsub_rn(1.f, a);
+    sil = __fmul_rn(sil, na);
+    if (i != target) others = __fmul_rn(others, na);
+    else a_s = a;
+  }
+  const float tgt = __fmul_rn(a_s, others);
+  float* o = out + t * frame_stride;
+  o[0] = sil;
+  o[class_stride] = tgt;
+  o[2 * class_stride] = __fmul_rn(__fsub_rn(1.f, a_s), __fsub_rn(1.f, others));
+  o[3 * class_stride] = __fsub_rn(a_s, tgt);
+}
+
 }  // namespace
 
 // window + DFT basis, built in double on the host once per handle (dicow_create)
@@ -267,6 +299,20 @@ extern "C" int dicow_logmel(dicow_handle_t h, const dicow_logmel_args_t* a, void
   const long long n = (long long)p.n_mels * p.frames;
   dim3 grid2((unsigned)((n + 256 * 8 - 1) / (256 * 8)), a->B);
   logmel_finalize_kernel<<<grid2, 256, 0, stream>>>(p);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
+
+extern "C" int dicow_stno_mask(dicow_handle_t h, const uint8_t* activity, int64_t ld, int n_speakers, int64_t n_samples,
+                               int target, int frame_samples, int64_t frames, float* out, int64_t frame_stride,
+                               int64_t class_stride, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, activity && out && n_speakers >= 1 && n_samples >= 1 && target >= -1 && target < n_speakers &&
+                         frame_samples >= 1 && frames >= 1 && ld >= n_samples,
+                "dicow_stno_mask: bad args");
+  stno_mask_kernel<<<(unsigned)((frames + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      activity, ld, n_speakers, n_samples, target, frame_samples, frames, out, frame_stride, class_stride);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }

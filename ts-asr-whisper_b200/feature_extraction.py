@@ -105,3 +105,16 @@ class DiCoWFeatureExtractor:
         if return_tensors == "np":
             data = {k: v.cpu().numpy() for k, v in data.items()}
         return BatchFeature(data)
+
+    def stno_mask(self, speaker_activity, speaker_index: int, model_features_subsample_factor: int = 2,
+                  device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
+        """STNO mask of one recording on the GPU -- what the reference's dataset computes with numpy per sample
+        (src/data/local_datasets.py:162-196: ``get_stno_mask`` / ``_create_stno_masks``): ``speaker_activity`` is the
+        sample-level 0/1 matrix [n_speakers, n_samples] (``cut.speakers_audio_mask``), ``speaker_index`` the target's row
+        (-1: none).  Returns fp32 [frames, 4] (silence, target, non-target, overlap), frames = padded samples / 320."""
+        dev = torch.device(device) if device is not None else self.device
+        if dev.type != "cuda":
+            raise ops.DicowError("DiCoWFeatureExtractor runs on an sm_100 CUDA device only (no CPU fallback)")
+        act = torch.as_tensor(np.asarray(speaker_activity) if not isinstance(speaker_activity, torch.Tensor) else speaker_activity)
+        return ops.stno_mask(act.to(dev), int(speaker_index), window_samples=self.n_samples,
+                             frame_samples=model_features_subsample_factor * self.hop_length)

@@ -258,6 +258,27 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def stno_mask(activity: torch.Tensor, target: int, *, window_samples: int = 480000, frame_samples: int = 320,
+              channels_first: bool = False) -> torch.Tensor:
+    """STNO mask of one recording from per-speaker sample-level activity (dicow_stno_mask; reference
+    src/data/local_datasets.py:162-196).  activity: bool / uint8 [n_speakers, n_samples] on the GPU; returns fp32
+    [frames, 4] like the reference's get_stno_mask, or [4, frames] (the collated layout) with ``channels_first``."""
+    global launch_count
+    dev = _require_cuda(activity)
+    act = activity.to(torch.uint8).contiguous()
+    n_spk, n = act.shape
+    frames = (n + (window_samples - n) % window_samples) // frame_samples
+    out = torch.empty((4, frames) if channels_first else (frames, 4), dtype=torch.float32, device=dev)
+    fs, cs = (1, frames) if channels_first else (4, 1)
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_stno_mask(h, _ptr(act), act.stride(0), n_spk, n, int(target), frame_samples, frames,
+                                                 _ptr(out), fs, cs, _stream(dev))
+    _lib.check(rc, h, "dicow_stno_mask")
+    launch_count += 1
+    return out
+
+
 def logmel(audio: torch.Tensor, mel_filters: torch.Tensor, lengths: Optional[torch.Tensor] = None,
            return_attention_mask: bool = False):
     """Whisper log-mel of a batch of zero-padded recordings (dicow_logmel): audio fp32 [B, n_pad] (n_pad % 160 == 0),
