@@ -1,0 +1,90 @@
+"""Checkpoint / hub interop of the mirrored model classes (SURVEY.md section 8b "parameter naming/shape contract", 8(f).4),
+on CPU (parameter containers only; no kernel is launched):
+
+  * save_pretrained -> from_pretrained round-trips every tensor exactly and keeps proj_out tied to the decoder embedding
+    (src/train.py:109-113) -- from_pretrained() runs _init_weights over EVERY module after loading, so an unguarded init
+    there silently replaces the checkpoint;
+  * from_pretrained(dir, **DiCoWConfig overrides) as WhisperContainer does (src/models/containers.py:24-52): modules the
+    checkpoint does not have (SCB, CTC head, FDDT) get the reference's own inits, everything else is untouched;
+  * the reference's re-initialisation calls (src/train.py:102-113, src/pretrain_encoder.py:39-40) work on the state_dict
+    names: encoder-only load without the FDDT tables, whole-model load with the re-tied proj_out.
+"""
+import tempfile
+
+import pytest
+import torch
+
+from oracle import synth
+
+
+@pytest.fixture(scope="module")
+def saved():
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = synth.Dims(**{**synth.GOLDEN_MINI.__dict__, "use_enrollments": False, "scb_layers": 0})
+    torch.manual_seed(0)
+    m = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.3)  # "trained": nothing sits at its init value any more
+    with tempfile.TemporaryDirectory() as d:
+        m.save_pretrained(d)
+        yield d, {k: v.clone() for k, v in m.state_dict().items()}, DiCoWForConditionalGeneration, dm
+
+
+def _max_diff(a, b):
+    return max((a[k].float() - b[k].float()).abs().max().item() for k in a)
+
+
+def test_round_trip_exact_and_tied(saved):
+    d, sd0, cls, _ = saved
+    m = cls.from_pretrained(d)
+    sd = m.state_dict()
+    assert set(sd) == set(sd0)
+    assert _max_diff(sd0, sd) == 0.0
+    assert m.proj_out.weight.data_ptr() == m.model.decoder.embed_tokens.weight.data_ptr()
+    assert m.config.model_type == "DiCoW" and m.config.use_fddt
+
+
+def test_from_pretrained_with_overrides_adds_reference_inits(saved):
+    d, sd0, cls, dm = saved
+    m = cls.from_pretrained(d, use_enrollments=True, scb_layers=2)
+    sd = m.state_dict()
+    assert _max_diff(sd0, sd) == 0.0, "loaded tensors must not be re-initialised"
+    cae = m.model.encoder.ca_enrolls[1].cae
+    eye = torch.eye(dm.d)
+    assert (cae.ffn[0].weight[:dm.d, :dm.d] - eye).abs().max() < 0.05   # layers.py:95-110: copy-through start
+    assert (cae.ffn[3].weight[:, :dm.d] - eye).abs().max() < 0.05
+    assert float(cae.cross_gate.gate.detach()) == 0.0                            # layers.py:79-93
+    assert 0.01 < float(cae.cross_attn.q_proj.weight.std()) < 0.03      # HF init_std
+    m2 = cls.from_pretrained(d, fddt_bias_only=True)                     # FDDT.py:10: bias vectors start at zero
+    assert all(float(v.abs().max()) == 0.0 for k, v in m2.state_dict().items() if "fddt" in k)
+    # full-matrix FDDT over a diagonal checkpoint: the [d] tables cannot be loaded into [d, d] (the reference raises the
+    # same size mismatch); with ignore_mismatched_sizes they start from layers.py:37-44's suppressive identities
+    m3 = cls.from_pretrained(d, fddt_is_diagonal=False, ignore_mismatched_sizes=True)
+    w = m3.model.encoder.fddts[0].target_linear.weight
+    assert w.shape == (dm.d, dm.d) and torch.allclose(w, torch.eye(dm.d))
+    w = m3.model.encoder.initial_fddt.non_target_linear.weight  # encoder.py:66-73: the pre-positional FDDT suppresses
+    assert torch.allclose(w, m3.config.non_target_fddt_value * torch.eye(dm.d))
+
+
+def test_reference_reinit_calls(saved):
+    d, sd0, cls, dm = saved
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    fresh = cls(DiCoWConfig(**dm.hf_kwargs()))
+    # src/train.py:102-106: encoder weights without the FDDT tables
+    enc_sd = {k[len("model.encoder."):]: v for k, v in sd0.items() if k.startswith("model.encoder.")}
+    res = fresh.get_encoder().load_state_dict({k: v for k, v in enc_sd.items() if "fddt" not in k}, strict=False)
+    assert res.unexpected_keys == [] and all("fddt" in k for k in res.missing_keys)
+    assert torch.equal(fresh.state_dict()["model.encoder.layers.0.fc1.weight"], sd0["model.encoder.layers.0.fc1.weight"])
+    # src/train.py:108-113: whole model, proj_out re-tied from the embedding
+    state = {k: v for k, v in sd0.items() if k != "proj_out.weight"}
+    state["proj_out.weight"] = state["model.decoder.embed_tokens.weight"]
+    res = fresh.load_state_dict(state, strict=False)
+    assert res.unexpected_keys == [] and res.missing_keys == []
+    assert _max_diff(sd0, fresh.state_dict()) == 0.0
+    # src/models/containers.py:80-97 / src/pretrain_encoder.py:42-51: name-keyword freezing works on these names
+    for n, p in fresh.get_encoder().named_parameters():
+        p.requires_grad = n.startswith(("additional_self_attention_layer", "lm_head", "subsample_conv"))
+    n_train = sum(p.requires_grad for p in fresh.get_encoder().parameters())
+    assert n_train == 4 + 3 + 2 + 1  # extra attention (q, k, v, out weights + 3 biases) + 2 sub-sampling convs + lm_head

@@ -39,16 +39,18 @@ class CustomDiagonalLinear(nn.Module):
         self.bias = nn.Parameter(torch.zeros(d_model)) if bias else None
         self.reset_parameters()
 
-    def reset_parameters(self) -> None:
+    def reset_parameters(self, weight: bool = True, bias: bool = True) -> None:
+        """``weight`` / ``bias`` = False leaves that tensor alone (it came from a checkpoint)"""
         with torch.no_grad():
-            bound = math.sqrt(3.0 / self.weight.numel())
-            self.weight.uniform_(-bound, bound)
-            if self.bias is not None:
+            if weight:
+                bound = math.sqrt(3.0 / self.weight.numel())
+                self.weight.uniform_(-bound, bound)
+                if self.fddt_init == "non-disturbing":
+                    self.weight.fill_(1.0)
+                elif self.fddt_init == "suppressive":
+                    self.weight.fill_(self.init_eye_val)
+            if bias and self.bias is not None:
                 self.bias.zero_()
-            if self.fddt_init == "non-disturbing":
-                self.weight.fill_(1.0)
-            elif self.fddt_init == "suppressive":
-                self.weight.fill_(self.init_eye_val)
 
 
 class CustomLinear(nn.Linear):
@@ -58,16 +60,17 @@ class CustomLinear(nn.Linear):
         self.init_eye_val, self.fddt_init = init_eye_val, fddt_init
         super().__init__(*args, **kwargs)
 
-    def reset_parameters(self) -> None:
+    def reset_parameters(self, weight: bool = True, bias: bool = True) -> None:
         with torch.no_grad():
-            nn.init.xavier_uniform_(self.weight)
-            if self.bias is not None:
+            if weight:
+                nn.init.xavier_uniform_(self.weight)
+                scale = {"non-disturbing": 1.0, "suppressive": self.init_eye_val}.get(self.fddt_init)
+                if scale is not None:
+                    n = min(self.weight.shape)
+                    self.weight.zero_()
+                    self.weight[:n, :n] = scale * torch.eye(n, device=self.weight.device)
+            if bias and self.bias is not None:
                 self.bias.zero_()
-            scale = {"non-disturbing": 1.0, "suppressive": self.init_eye_val}.get(self.fddt_init)
-            if scale is not None:
-                n = min(self.weight.shape)
-                self.weight.zero_()
-                self.weight[:n, :n] = scale * torch.eye(n, device=self.weight.device)
 
 
 class FDDT(nn.Module):
@@ -166,12 +169,20 @@ class CrossAttentionEnrollBlock(nn.Module):
         self.cross_gate = Gate(1, init_val=0.0)
         self.ffn = nn.Sequential(nn.Linear(2 * d, ffn), nn.Identity(), nn.Identity(), nn.Linear(ffn, d), nn.Identity())
         self.ffn[0]._dicow_custom_init = self.ffn[3]._dicow_custom_init = True  # keep through HF post_init()
-        with torch.no_grad():  # layers.py:95-110: start as "copy the first half through"
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        """layers.py:95-110: the update network starts as "copy the query stream through" (also re-run by
+        DiCoWForConditionalGeneration._init_weights when from_pretrained() adds the block to a checkpoint without it)"""
+        d = self.ffn[3].weight.shape[0]
+        if self.ffn[0].weight.device.type == "meta":
+            return
+        with torch.no_grad():
             nn.init.xavier_uniform_(self.ffn[0].weight, gain=1e-1)
-            self.ffn[0].weight[:d, :d] += torch.eye(d)
+            self.ffn[0].weight[:d, :d] += torch.eye(d, device=self.ffn[0].weight.device)
             self.ffn[0].bias.zero_()
             nn.init.xavier_uniform_(self.ffn[3].weight, gain=1e-1)
-            self.ffn[3].weight[:, :d] += torch.eye(d)
+            self.ffn[3].weight[:, :d] += torch.eye(d, device=self.ffn[3].weight.device)
             self.ffn[3].bias.zero_()
 
 

@@ -20,6 +20,8 @@ import re
 from decimal import ROUND_HALF_UP, Decimal
 from typing import Dict, List, Optional
 
+import math
+
 import torch
 from torch import nn
 from transformers import GenerationConfig, PreTrainedModel
@@ -294,28 +296,62 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
 
     # ---- HF plumbing ---------------------------------------------------------------------------------------
     def _init_weights(self, module):
-        """HF WhisperPreTrainedModel._init_weights semantics for the container modules; FDDT / Gate / SCB modules
-        initialise themselves (src/models/dicow/encoder.py:79-82)."""
+        """HF WhisperPreTrainedModel._init_weights semantics for the container modules + the DiCoW modules' own inits
+        (src/models/dicow/encoder.py:79-82).  from_pretrained() calls this on EVERY module after loading and marks the
+        tensors that came from the checkpoint with ``_is_hf_initialized``: only unmarked tensors are touched (an unguarded
+        init here would overwrite the loaded weights)."""
         std = getattr(self.config, "init_std", 0.02)
-        from .modeling import CustomDiagonalLinear, Gate
-        if isinstance(module, (CustomDiagonalLinear, Gate)):
-            module.reset_parameters()
+        from .modeling import FDDT, CrossAttentionEnrollBlock, CustomDiagonalLinear, CustomLinear, DiCoWEncoder, Gate
+
+        def fresh(t) -> bool:
+            return t is not None and not getattr(t, "_is_hf_initialized", False) and t.device.type != "meta"
+
+        if isinstance(module, (CustomDiagonalLinear, CustomLinear)):
+            module.reset_parameters(weight=fresh(module.weight), bias=fresh(module.bias))  # encoder.py:79-82
+        elif isinstance(module, Gate):
+            if all(fresh(p) for p in module.parameters(recurse=False)):
+                module.reset_parameters()
+        elif isinstance(module, CrossAttentionEnrollBlock):
+            if fresh(module.ffn[0].weight) and fresh(module.ffn[3].weight):
+                module.reset_parameters()  # layers.py:95-110
+        elif isinstance(module, FDDT) and module.bias_only:
+            for c in ("target", "non_target", "overlap", "silence"):
+                p = getattr(module, c + "_linear", None)
+                if fresh(p):
+                    p.data.zero_()  # FDDT.py:10
+        elif isinstance(module, DiCoWEncoder):  # HF WhisperPreTrainedModel._init_weights: sinusoidal positions
+            pos = module.embed_positions.weight
+            if fresh(pos):
+                n, ch = pos.shape
+                inc = math.log(10000.0) / (ch // 2 - 1)
+                inv = torch.exp(-inc * torch.arange(ch // 2, dtype=torch.float32))
+                ang = torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]
+                pos.data.copy_(torch.cat([ang.sin(), ang.cos()], dim=1).to(pos.device))
         elif isinstance(module, (nn.Linear, nn.Conv1d)):
             if getattr(module, "_dicow_custom_init", False):
                 return
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
+            if fresh(module.weight):
+                module.weight.data.normal_(mean=0.0, std=std)
+            if fresh(module.bias):
                 module.bias.data.zero_()
         elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.padding_idx is not None:
-                module.weight.data[module.padding_idx].zero_()
+            if fresh(module.weight) and module is not getattr(getattr(self.model, "encoder", None), "embed_positions", None):
+                module.weight.data.normal_(mean=0.0, std=std)
+                if module.padding_idx is not None:
+                    module.weight.data[module.padding_idx].zero_()
         elif isinstance(module, nn.LayerNorm):
-            module.weight.data.fill_(1.0)
-            module.bias.data.zero_()
+            if fresh(module.weight):
+                module.weight.data.fill_(1.0)
+            if fresh(module.bias):
+                module.bias.data.zero_()
 
-    def tie_weights(self, *args, **kwargs):
+    def tie_weights(self, missing_keys=None, **kwargs):
+        """proj_out is tied to the decoder's token embedding (src/train.py:109-113).  A checkpoint stores the tensor
+        once: the tied key is not "missing" (left in the set, from_pretrained() would re-initialise proj_out.weight --
+        which IS the embedding -- and overwrite the loaded embeddings)."""
         self.proj_out.weight = self.model.decoder.embed_tokens.weight
+        if missing_keys is not None:
+            missing_keys.discard("proj_out.weight")
 
     def get_encoder(self):
         return self.model.get_encoder()
