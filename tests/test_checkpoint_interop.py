@@ -88,3 +88,41 @@ def test_reference_reinit_calls(saved):
         p.requires_grad = n.startswith(("additional_self_attention_layer", "lm_head", "subsample_conv"))
     n_train = sum(p.requires_grad for p in fresh.get_encoder().parameters())
     assert n_train == 4 + 3 + 2 + 1  # extra attention (q, k, v, out weights + 3 biases) + 2 sub-sampling convs + lm_head
+
+
+def test_whisper_container_and_optimizer(saved):
+    """src/models/containers.py:19-114 over a local checkpoint directory (no hub, no tokenizer files offline: a stub
+    tokenizer with the attributes the model reads is passed in)"""
+    import types
+    d, sd0, cls, dm = saved
+    from ts_asr_whisper_b200.containers import WhisperContainer, get_optimizer
+
+    class Tok:
+        prefix_tokens = [258, 259, 260]
+        pad_token_id = 257
+
+        def set_prefix_tokens(self, **kw):
+            self.prefix_kw = kw
+
+        def get_vocab(self):
+            return {f"<|{0.02 * i:.2f}|>": 262 + i for i in range(38)}
+
+    margs = types.SimpleNamespace(whisper_model=d, ctc_weight=0.3, fddt_is_diagonal=True, fddt_bias_only=False,
+                                  fddt_use_silence=True, fddt_use_target=True, fddt_use_overlap=True, fddt_use_non_target=True,
+                                  apply_fddt_to_n_layers=-1, fddt_init="suppressive", non_target_fddt_value=0.5,
+                                  use_pre_pos_fddt=True, pre_ctc_sub_sample=True, additional_layer=False,
+                                  additional_self_attention_layer=True, scb_layers=2)
+    dargs = types.SimpleNamespace(use_timestamps=True, global_lang_id="en", use_enrollments=True)
+    c = WhisperContainer(model_args=margs, data_args=dargs, use_fddt=True, params_to_keep_frozen_keywords=["decoder"],
+                         tokenizer=Tok(), feature_extractor=object())
+    assert c.tokenizer.prefix_kw == {"predict_timestamps": True, "task": "transcribe", "language": "en"}
+    assert c.model.soft_label_creator is not None and c.model.config.forced_decoder_ids is None
+    assert hasattr(c.model.get_encoder(), "ca_enrolls") and len(c.model.get_encoder().ca_enrolls) == 2
+    assert all(p.requires_grad != ("decoder" in n) for n, p in c.model.named_parameters())
+    c.freeze_except(["model.encoder.fddts", "model.encoder.initial_fddt", "model.encoder.ca_enrolls"])
+    on = [n for n, p in c.model.named_parameters() if p.requires_grad]
+    assert on and all(n.startswith(("model.encoder.fddts", "model.encoder.initial_fddt", "model.encoder.ca_enrolls")) for n in on)
+    targs = types.SimpleNamespace(use_custom_optimizer=True, fddt_lr_multiplier=100.0, learning_rate=2e-6, weight_decay=0.01)
+    opt = get_optimizer(c.model, targs, ["model.encoder.fddts", "model.encoder.ca_enrolls"])
+    assert len(opt.param_groups) == 2 and abs(opt.param_groups[1]["lr"] - 2e-4) < 1e-12 and opt.param_groups[1]["weight_decay"] == 0.0
+    assert get_optimizer(c.model, types.SimpleNamespace(use_custom_optimizer=False)) is None
