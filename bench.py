@@ -14,7 +14,8 @@ N GPUs run N replicas with no data-path collective ("weak" scaling: B per GPU fi
   e2e    : utt/s through the public API with pinned HOST buffers: H2D of features + masks and D2H of
            last_hidden_state inside the timed region, every step
   roofline: the tcgen05 GEMM kernel family (dominant: ~60 % of the step), algorithmic FLOPs / CUDA-event time per
-           launch measured live in the timed steps, against the measured cuBLAS bf16 peak (MEASURED_PEAKS.json)
+           launch measured live in extra instrumented steps right after the timed region (an event pair around every
+           launch perturbs the step by up to 6 %), against the measured cuBLAS bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference: the reference's algorithm (oracle/dicow_oracle.py -- the reference itself is Python
            over HF transformers and /root/reference does not exist on the GPU box) in fp32 on all host cores, on a
            bounded sample (B=1 forwards) of the same workload.
@@ -94,13 +95,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self) -> int:
+        """number of samples taken so far (brackets the timed region: the sampler is started before the warm-up so that
+        nvidia-smi's own start-up -- process launch, NVML initialisation -- does not land inside it)"""
+        return len(self.rows)
+
+    def stop(self, first: int = 0, last: int = None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[first:last] or self.rows[-3:]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -221,13 +228,16 @@ def main():
         parallel.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        enc(resident[i % 3][0], stno_mask=resident[i % 3][1])
-    # ---- timed: device-resident inputs ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.timing_log = []
+    for i in range(args.warmup):
+        enc(resident[i % 3][0], stno_mask=resident[i % 3][1])
+    torch.cuda.synchronize()
+    time.sleep(0.3)  # let nvidia-smi finish starting up before the timed region
+    # ---- timed: device-resident inputs ----
+    m0 = sampler.mark()
+    ops.timing_log = None
     l0 = ops.launch_count
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,8 +248,21 @@ def main():
     barrier()
     launches = ops.launch_count - l0
     ms = e0.elapsed_time(e1)
+    m1 = sampler.mark()
+    # ---- per-kernel durations for the roofline: the same steps again with a CUDA event pair around every launch.  Kept
+    # out of the region `value` is timed over: 458 event records per step open gaps between the kernels (measured on one
+    # box: 79.6 ms/step without them, 84.7 ms with them)
+    roofline_steps = min(args.steps, 3)
+    ops.timing_log = []
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(roofline_steps):
+        enc(resident[i % 3][0], stno_mask=resident[i % 3][1])
+    e3.record()
+    barrier()
+    ms_instr = e2.elapsed_time(e3)
     log, ops.timing_log = ops.timing_log, None
-    clocks = sampler.stop() if rank == 0 else None
     # ---- timed: end to end through the public API with host buffers ----
     for i in range(2):
         enc(host[i][0].to(dev, non_blocking=True), stno_mask=host[i][1].to(dev, non_blocking=True))
@@ -252,6 +275,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(m0, max(m1, m0 + 1)) if rank == 0 else None  # samples taken during the resident timed region
     ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], dev)  # multi-GPU numbers are the slowest rank's
     if rank != 0:
         if world > 1:
@@ -273,7 +297,7 @@ def main():
         d[0] += fl
         d[1] += a.elapsed_time(b)
         d[2] += 1
-    kern = {k: {"launches": v[2], "ms_per_step": v[1] / args.steps,
+    kern = {k: {"launches": v[2], "ms_per_step": v[1] / roofline_steps,
                 "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[0] else None} for k, v in by_kind.items()}
     gemm = by_kind.get("gemm", [0.0, 1.0, 1])
     achieved = gemm[0] / (gemm[1] * 1e-3) / 1e12
@@ -285,10 +309,12 @@ def main():
         pass
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<256,*> (tcgen05 GEMM family: QKV/out/fc1/fc2/conv)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_source": peak_src, "launches_per_step": gemm[2] // max(1, args.steps),
+                "peak_source": peak_src, "launches_per_step": gemm[2] // max(1, roofline_steps),
                 "gflop_per_launch_avg": gemm[0] / max(1, gemm[2]) / 1e9,
                 "us_per_launch_avg": 1e3 * gemm[1] / max(1, gemm[2]),
-                "share_of_step": gemm[1] / ms if ms else None}
+                "share_of_step": (gemm[1] / roofline_steps) / (ms / args.steps) if ms else None,
+                "measured_over_steps": roofline_steps, "instrumented_ms_per_step": ms_instr / roofline_steps,
+                "note": "per-launch CUDA-event times from extra instrumented steps after the timed region"}
     utts = world * B * args.steps
     value = utts / (ms * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
