@@ -264,14 +264,50 @@ def main():
     ms_instr = e2.elapsed_time(e3)
     log, ops.timing_log = ops.timing_log, None
     # ---- timed: end to end through the public API with host buffers ----
-    for i in range(2):
-        enc(host[i][0].to(dev, non_blocking=True), stno_mask=host[i][1].to(dev, non_blocking=True))
+    # Every step copies its inputs from pinned host memory and its result back (inside the timed region); the copies run
+    # on two side streams, double-buffered, so that step i + 1's H2D and step i - 1's D2H overlap step i's kernels -- what
+    # a caller feeding the encoder from a DataLoader does (pin_memory + non_blocking).
+    cur = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+
+    def e2e_pass(n):
+        ev_in = [None, None]
+        ev_free = [None, None]  # compute that last read input buffer k has finished
+        ev_out = [None, None]   # D2H out of host buffer k has finished
+
+        def h2d(i):
+            k = i % 2
+            with torch.cuda.stream(s_in):
+                if ev_free[k] is not None:
+                    s_in.wait_event(ev_free[k])
+                dev_in[k][0].copy_(host[i % 3][0], non_blocking=True)
+                dev_in[k][1].copy_(host[i % 3][1], non_blocking=True)
+                ev_in[k] = s_in.record_event()
+
+        h2d(0)
+        for i in range(n):
+            k = i % 2
+            cur.wait_event(ev_in[k])
+            o = enc(dev_in[k][0], stno_mask=dev_in[k][1]).last_hidden_state
+            ev_free[k] = cur.record_event()
+            if i + 1 < n:
+                h2d(i + 1)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[k])
+                if ev_out[k] is not None:
+                    s_out.wait_event(ev_out[k])
+                out_hosts[k].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+                ev_out[k] = s_out.record_event()
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+
+    e2e_pass(2)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        f, s = host[i % 3]
-        o = enc(f.to(dev, non_blocking=True), stno_mask=s.to(dev, non_blocking=True)).last_hidden_state
-        out_host.copy_(o, non_blocking=True)
+    e2e_pass(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
