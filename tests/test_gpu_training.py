@@ -144,6 +144,27 @@ def test_ctc_pretrain_step(dm, B, body):
 @pytest.mark.parametrize("dm,B,S", [(MINI, 2, 11), (TINY_SHORT, 3, 24)], ids=["mini", "tiny-short"])
 @pytest.mark.parametrize("mode", ["decoder-frozen", "all", "fddt-only"])
 def test_finetune_step(dm, B, S, mode):
+    _finetune_case(dm, B, S, mode, "tr1")
+
+
+# FDDT(bias_only=True) (src/models/dicow/FDDT.py:10-13, 43-51): the per-class parameter is a bias vector only.
+# The "tr1" draw is ill-conditioned for these tables at whisper-tiny widths: on the fp32 CPU oracle alone, rounding the
+# weight matrices to bf16 moves d(loss)/d(encoder output) by 28 % and conv1.weight's gradient by 11 % (loss 22.2329 ->
+# 22.2296), against 0.9 % / 0.8 % for "tr2" (tools/cond_cpu.py) -- a bf16 path cannot be held to 5 % there, so these
+# cases use the well-conditioned draw.  The decoder does not see the FDDT variant, so its parameters stay frozen here
+# ("all" is covered above; on "tr2" the near-uniform cross-attention makes the q/k weight gradients of BOTH variants
+# cancel to 6-8 % bf16 noise with cos 0.9995, measured on the diagonal variant too).
+MINI_BIAS = dataclasses.replace(MINI, fddt_bias_only=True)
+TINY_BIAS = dataclasses.replace(TINY_SHORT, fddt_bias_only=True)
+
+
+@pytest.mark.parametrize("dm,B,S", [(MINI_BIAS, 2, 11), (TINY_BIAS, 3, 24)], ids=["mini", "tiny-short"])
+@pytest.mark.parametrize("mode", ["decoder-frozen", "fddt-only"])
+def test_finetune_step_bias_only_fddt(dm, B, S, mode):
+    _finetune_case(dm, B, S, mode, "tr2")
+
+
+def _finetune_case(dm, B, S, mode, tag):
     """configs[2]: loss = 0.7 soft-label CE + 0.3 CTC through DiCoWForConditionalGeneration.forward, loss.backward()"""
     model, p = _build(dm)
     model.set_tokenizer(FakeTokenizer())
@@ -155,8 +176,8 @@ def test_finetune_step(dm, B, S, mode):
         else:
             q.requires_grad_("encoder.embed_positions" not in n)
     trainable = [n for n, q in model.named_parameters() if q.requires_grad]
-    feats, stno = _inputs(dm, B, "tr1")
-    labels = torch.from_numpy(synth.make_labels("tr1", B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK)))
+    feats, stno = _inputs(dm, B, tag)
+    labels = torch.from_numpy(synth.make_labels(tag, B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK)))
     upp = labels.clone()
     upp[:, ::3] = torch.where(upp[:, ::3] >= 0, (upp[:, ::3] + 3) % 250, upp[:, ::3])
     labels, upp = labels.to(DEV), upp.to(DEV)

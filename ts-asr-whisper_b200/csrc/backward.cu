@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(512) ln_fddt_bwd_kernel(const LnBwdParams p, c
           w = f4_add(w, f4_scale(tw[c], m[r][c]));
           bb = f4_add(bb, f4_scale(tb[c], m[r][c]));
         }
+        if (p.fddt_w == nullptr) w = make_float4(1.f, 1.f, 1.f, 1.f);  // bias-only FDDT (FDDT.py:43-51): x' = x + sum_c m_c b_c
         weff[r] = w;
         if (ok) xp[r] = f4_add(f4_mul(xs[r], w), bb);
       }
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring
                 w = f4_add(w, f4_scale(reinterpret_cast<const float4*>(tab + c * d)[c4], m[c]));
                 bb = f4_add(bb, f4_scale(reinterpret_cast<const float4*>(tab + (4 + c) * d)[c4], m[c]));
               }
+              if (p.fddt_w == nullptr) w = make_float4(1.f, 1.f, 1.f, 1.f);  // bias-only FDDT
               v = f4_add(f4_mul(v, w), bb);
             }
             xp[k] = v;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring
         float4 w = z4, bb = z4;
 #pragma unroll
         for (int c = 0; c < 4; ++c) w = f4_add(w, f4_scale(tw[c], mm[c])), bb = f4_add(bb, f4_scale(tb[c], mm[c]));
+        if (p.fddt_w == nullptr) w = make_float4(1.f, 1.f, 1.f, 1.f);  // bias-only FDDT
         weff = w;
         xp = f4_add(f4_mul(xs, w), bb);
       }

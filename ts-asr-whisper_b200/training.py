@@ -196,9 +196,9 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
     the per-layer inputs the backward needs.  Returns (last_hidden fp32 [B, T, d], bf16 copy [B*T, d]).
     With ``enrollments`` the first ``scb_layers`` layers run on the stacked [targets ; enrollments] streams."""
     cfg = enc.config
-    if cfg.use_fddt and (cfg.fddt_bias_only or not cfg.fddt_is_diagonal):
-        raise NotImplementedError("training step: only the recipes' diagonal FDDT has a backward on the B200 path "
-                                  "(bias-only / full-matrix FDDT run forward-only)")
+    if cfg.use_fddt and not cfg.fddt_is_diagonal and not cfg.fddt_bias_only:
+        raise NotImplementedError("training step: full-matrix FDDT runs forward-only on the B200 path (the recipes use "
+                                  "the diagonal FDDT; bias-only has a backward too)")
     n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers and enrollments is not None) else 0
     if n_scb:  # encoder.py:152-154 (stacked instead of interleaved, see the module docstring)
         input_features = torch.cat((input_features, enrollments["input_features"].to(input_features.device)), dim=0)
@@ -581,6 +581,10 @@ def _scatter_fddt_grads(g: _Grads, fmod, dfw: torch.Tensor, dfb: torch.Tensor) -
     for c, name in enumerate(_FDDT_ORDER):
         lin = getattr(fmod, name + "_linear", None)
         if lin is None:
+            continue
+        if isinstance(lin, torch.nn.Parameter):  # bias-only FDDT: the parameter is the class bias (FDDT.py:10)
+            if g.want(lin):
+                g.get(lin).add_(dfb[c])
             continue
         if g.want(lin.weight):
             g.get(lin.weight).add_(dfw[c])
