@@ -348,6 +348,37 @@ DICOW_API int dicow_stno_mask(dicow_handle_t h, const uint8_t* activity, int64_t
                               int target, int frame_samples, int64_t frames, float* out, int64_t frame_stride,
                               int64_t class_stride, void* stream);
 
+/* Training-time augmentations of a padded batch (src/data/collators.py:184-210, DataCollator.__call__: soft_segment_augmentation
+ * :77-136, add_gaussian_noise_and_rescale :50-75, SpecAug on [mel || STNO repeated x factor] :205-210 with
+ * src/data/augmentations.py time_warp :70-98 / mask_along_axis :20-66 / SpecAug.forward :414-434).  The reference draws every
+ * random number from torch's CPU generator in a data-independent order; the caller draws them in that order (the "plan") and
+ * this call applies the plan, in the reference's order: segments, noise (both in place on `stno`), SpecAug (feats, stno ->
+ * feats_out, stno_out; skipped when spec == 0).  All device pointers; fp32 tensors contiguous. */
+typedef struct {
+  size_t struct_size;
+  float* stno;             /* [B, C, Ts] class probabilities (C = 4: S, T, N, O) */
+  int32_t B, C, Ts;
+  const int32_t* seg;      /* [n_seg, 4]: batch row, start, end, index into the classes other than the dominant one */
+  const float* seg_soft;   /* [n_seg, 2]: softness, 1 - softness (the latter rounded from double, as the reference's scalar is) */
+  int32_t n_seg;
+  const int32_t* noise_rows; /* [n_noise] distinct batch rows */
+  const float* noise;      /* [n_noise, C, Ts], already scaled by sqrt(variance) */
+  int32_t n_noise;
+  int32_t spec;            /* 0: no SpecAug */
+  const float* feats;      /* [B, M, Tf], Tf = factor * Ts */
+  float* feats_out;        /* [B, M, Tf] */
+  float* stno_out;         /* [B, C, Ts] */
+  int32_t M, Tf, factor;
+  int32_t center, warped;  /* time warp: frames [0, center) -> [0, warped), the rest -> the rest (bicubic); center < 0: none */
+  const int32_t* freq_masks; /* [B, n_freq_masks, 2] (pos, length) over the first min(mask_channels, M + C) channels */
+  int32_t n_freq_masks;
+  const int32_t* time_masks; /* [B, n_time_masks, 2] (pos, length) in mel frames */
+  int32_t n_time_masks;
+  int32_t mask_channels;   /* 128 in the reference (augmentations.py:425-431), whatever M is */
+} dicow_augment_args_t;
+
+DICOW_API int dicow_augment_batch(dicow_handle_t h, const dicow_augment_args_t* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Token-by-token decoder step (greedy generate()).  Replaces, per generated token, HF WhisperDecoder.forward with a KV
  * cache (HF:modeling_whisper.py:449-506, 691-796), proj_out (src/models/dicow/modeling_dicow.py:302) and the greedy

@@ -225,3 +225,45 @@ def test_stno_mask_oracle_matches_reference(name):
     out = orc.stno_mask(act, target)
     assert out.shape == ref.shape
     np.testing.assert_array_equal(out, ref)  # bit-exact: 0/1 means and products in the reference's order
+
+
+# ---- (f).2: collator augmentations, oracle vs the reference's own DataCollator.__call__ output ------------------------------
+def _augment_case(name):
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden_augment as G
+    from oracle import augment as A
+    np_seed, torch_seed, n_mels, frames, fields = G.CASES[name]
+    samples = G.make_inputs(np_seed, n_mels, frames)
+    B, Tf, Ts = len(samples), max(f.shape[1] for f, _ in samples), max(s.shape[0] for _, s in samples)
+    feats, stno = np.zeros((B, n_mels, Tf), np.float32), np.zeros((B, 4, Ts), np.float32)
+    for b, (f, s) in enumerate(samples):  # pad_sequence + silence padding, src/data/collators.py:153-163
+        feats[b, :, :f.shape[1]] = f
+        stno[b, :, :s.shape[0]] = s.T
+        stno[b, 0, s.shape[0]:] = 1.0
+    return A, A.AugmentConfig(**fields), torch_seed, feats, stno, samples
+
+
+AUGMENT_CASES = ["v3_all", "mel80_all", "recipe_probs_a", "recipe_probs_b", "short_no_warp"]
+# bicubic time warp: the reference's own numbers depend on where its PyTorch build fuses multiply-adds (oracle/augment.py
+# _bicubic_rows); everything else -- the draws, segments, noise, masks, pair means -- is bit-exact
+AUGMENT_WARP_TOL = 2e-6
+
+
+@pytest.mark.parametrize("name", AUGMENT_CASES)
+def test_augment_oracle_matches_reference_collator(name):
+    A, cfg, torch_seed, feats, stno, _ = _augment_case(name)
+    gold = np.load(os.path.join(GOLD, "augment.npz"))
+    torch.manual_seed(torch_seed)
+    plan = A.draw_plan(feats.shape[0], 4, stno.shape[2], feats.shape[1], feats.shape[2], cfg)
+    f2, s2 = A.augment(feats, stno, plan, cfg)
+    gf, gs = gold[name + "/input_features"], gold[name + "/stno_mask"]
+    if plan.warp is None:
+        assert np.array_equal(f2, gf) and np.array_equal(s2, gs)
+    else:
+        assert np.abs(f2 - gf).max() <= AUGMENT_WARP_TOL * max(1.0, np.abs(gf).max())
+        assert np.abs(s2 - gs).max() <= AUGMENT_WARP_TOL
+        assert np.array_equal(f2 == 0, gf == 0)  # the masks are exact
+    # the stages before SpecAug, against the reference's rows that SpecAug did not touch at all
+    if not plan.spec:
+        assert np.array_equal(A.noise_rescale(A.segment_augment(stno, plan), plan), gs)

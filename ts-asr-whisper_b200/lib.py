@@ -175,6 +175,19 @@ class LogitsRulesArgs(C.Structure):
     ]
 
 
+class AugmentArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("stno", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("Ts", C.c_int32),
+        ("seg", C.c_void_p), ("seg_soft", C.c_void_p), ("n_seg", C.c_int32),
+        ("noise_rows", C.c_void_p), ("noise", C.c_void_p), ("n_noise", C.c_int32),
+        ("spec", C.c_int32), ("feats", C.c_void_p), ("feats_out", C.c_void_p), ("stno_out", C.c_void_p),
+        ("M", C.c_int32), ("Tf", C.c_int32), ("factor", C.c_int32), ("center", C.c_int32), ("warped", C.c_int32),
+        ("freq_masks", C.c_void_p), ("n_freq_masks", C.c_int32), ("time_masks", C.c_void_p), ("n_time_masks", C.c_int32),
+        ("mask_channels", C.c_int32),
+    ]
+
+
 class CtcJointArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -262,6 +275,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_features_to_channels_last.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_fddt_full_combine.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.dicow_stno_mask.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, vp, C.c_int64, C.c_int64, vp]
+    lib.dicow_augment_batch.argtypes = [vp, C.POINTER(AugmentArgs), vp]
     lib.dicow_zero_pad_rows.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_cast_f32_bf16.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.dicow_debug_set_attention_profile.argtypes = [vp, vp]
@@ -303,7 +317,7 @@ EXPORTED_SYMBOLS = [
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
-    "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask",
+    "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch",
 ]
 
 

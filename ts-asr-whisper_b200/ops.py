@@ -279,6 +279,42 @@ def stno_mask(activity: torch.Tensor, target: int, *, window_samples: int = 4800
     return out
 
 
+def augment_batch(stno: torch.Tensor, *, seg: Optional[torch.Tensor] = None, seg_soft: Optional[torch.Tensor] = None,
+                  noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                  feats: Optional[torch.Tensor] = None, factor: int = 2, spec: bool = False, warp: Optional[tuple] = None,
+                  freq_masks: Optional[torch.Tensor] = None, time_masks: Optional[torch.Tensor] = None,
+                  mask_channels: int = 128):
+    """Apply a drawn augmentation plan to a padded batch (dicow_augment_batch; reference src/data/collators.py:184-210).
+    stno fp32 [B, C, Ts] is changed in place by the segment / noise steps; with ``spec`` the SpecAug result is returned as
+    new tensors (feats [B, M, factor * Ts], stno).  Index tables are int32, everything on the GPU."""
+    dev = _require_cuda(stno, seg, seg_soft, noise_rows, noise, feats, freq_masks, time_masks)
+    assert stno.dtype == torch.float32 and stno.is_contiguous() and stno.dim() == 3
+    for t in (seg, noise_rows, freq_masks, time_masks):
+        assert t is None or (t.dtype == torch.int32 and t.is_contiguous())
+    for t in (seg_soft, noise, feats):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    a = _lib.AugmentArgs()
+    a.struct_size = C.sizeof(_lib.AugmentArgs)
+    a.stno = _ptr(stno)
+    a.B, a.C, a.Ts = stno.shape
+    a.seg, a.seg_soft, a.n_seg = _ptr(seg), _ptr(seg_soft), 0 if seg is None else seg.shape[0]
+    a.noise_rows, a.noise, a.n_noise = _ptr(noise_rows), _ptr(noise), 0 if noise_rows is None else noise_rows.shape[0]
+    assert noise is None or tuple(noise.shape) == (a.n_noise, a.C, a.Ts)
+    a.spec = int(bool(spec))
+    feats_out = stno_out = None
+    if spec:
+        assert feats is not None and feats.dim() == 3 and feats.shape[0] == a.B and feats.shape[2] == factor * a.Ts
+        feats_out, stno_out = torch.empty_like(feats), torch.empty_like(stno)
+        a.feats, a.feats_out, a.stno_out = _ptr(feats), _ptr(feats_out), _ptr(stno_out)
+        a.M, a.Tf, a.factor = feats.shape[1], feats.shape[2], factor
+        a.center, a.warped = (int(warp[0]), int(warp[1])) if warp is not None else (-1, -1)
+        a.freq_masks, a.n_freq_masks = _ptr(freq_masks), 0 if freq_masks is None else freq_masks.shape[1]
+        a.time_masks, a.n_time_masks = _ptr(time_masks), 0 if time_masks is None else time_masks.shape[1]
+        a.mask_channels = mask_channels
+    _call("dicow_augment_batch", dev, a, "augment")
+    return (feats_out, stno_out) if spec else (feats, stno)
+
+
 def logmel(audio: torch.Tensor, mel_filters: torch.Tensor, lengths: Optional[torch.Tensor] = None,
            return_attention_mask: bool = False):
     """Whisper log-mel of a batch of zero-padded recordings (dicow_logmel): audio fp32 [B, n_pad] (n_pad % 160 == 0),
