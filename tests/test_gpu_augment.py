@@ -100,3 +100,50 @@ def test_empty_plan_and_argument_checks():
         ops.augment_batch(s, feats=f, spec=True, warp=(0, 3), freq_masks=torch.zeros(2, 1, 2, dtype=torch.int32, device="cuda"))
     with pytest.raises(AssertionError):
         ops.augment_batch(s, feats=torch.randn(2, 80, 21, device="cuda"), spec=True)
+
+
+def test_device_input_pipeline_raw_audio_to_augmented_batch():
+    """8(f).2 end to end: raw audio + sample-level speaker activity -> log-mel, STNO, padding, augmentation, all on the GPU;
+    every stage against the oracle (mel <= 1e-3 like tests/test_gpu_mel.py, everything after it bit-exact on the same input)"""
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    from ts_asr_whisper_b200.collators import DataCollator
+    from ts_asr_whisper_b200.feature_extraction import DiCoWFeatureExtractor
+    from ts_asr_whisper_b200.input_pipeline import DeviceInputPipeline
+    fields = dict(stno_gaussian_noise_var=0.01, stno_gaussian_noise_prob=1.0, stno_segment_augment_prob=1.0,
+                  stno_segment_change_prob=0.3, spec_aug_prob=1.0)
+    rng = np.random.default_rng(9)
+    raw = []
+    for i, (n, n_spk, target) in enumerate(((16000 * 9 + 77, 3, 1), (16000 * 14, 2, -1), (16000 * 41, 4, 0))):
+        act = np.zeros((n_spk, n), dtype=bool)
+        for s in range(n_spk):
+            t = 0
+            while t < n:
+                gap, dur = int(rng.integers(0, 40000)), int(rng.integers(3000, 60000))
+                act[s, t + gap:t + gap + dur] = True
+                t += gap + dur
+        raw.append({"audio": synth.make_audio(f"pipe{i}", n), "speaker_activity": act, "speaker_index": target, "transcript": "x"})
+    fe = DiCoWFeatureExtractor(feature_size=128, device="cuda")
+
+    def pipeline(**f):
+        return DeviceInputPipeline(fe, DataCollator(feature_extractor=fe, tokenizer=Tok(), bos_token_id=0, max_length=16,
+                                                    device="cuda", **f))
+    plain = pipeline(stno_segment_augment_prob=0.0, spec_aug_prob=0.0)(raw)
+    feats, stno = plain["input_features"].cpu().numpy(), plain["stno_mask"].cpu().numpy()
+    assert feats.shape == (3, 128, 6000) and stno.shape == (3, 4, 3000) and plain["attention_mask"].shape == (3, 6000)
+    for b, r in enumerate(raw):
+        rf, rm = orc.log_mel(r["audio"], 128)
+        n = rf.shape[1]
+        assert np.abs(feats[b, :, :n] - rf).max() < 1e-3 and not feats[b, :, n:].any()
+        assert np.array_equal(plain["attention_mask"][b, :n].cpu().numpy(), rm) and int(plain["attention_mask"][b, n:].sum()) == 0
+        rs = orc.stno_mask(r["speaker_activity"], r["speaker_index"])
+        assert np.array_equal(stno[b, :, :rs.shape[0]], rs.T)
+        assert np.array_equal(stno[b, :, rs.shape[0]:], np.array([1, 0, 0, 0], np.float32)[:, None].repeat(3000 - rs.shape[0], 1))
+    torch.manual_seed(5)
+    aug = pipeline(**fields)(raw)
+    torch.manual_seed(5)
+    cfg = A.AugmentConfig(**fields)
+    plan = A.draw_plan(3, 4, 3000, 128, 6000, cfg)
+    rf, rs = A.augment(feats, stno, plan, cfg)
+    assert plan.warp is not None and len(plan.segments) > 0
+    assert np.array_equal(aug["input_features"].cpu().numpy(), rf) and np.array_equal(aug["stno_mask"].cpu().numpy(), rs)

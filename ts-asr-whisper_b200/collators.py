@@ -130,6 +130,8 @@ class DataCollator:
         B = len(inputs)
         f0 = inputs[0]["input_features"]
         M = f0.shape[0]
+        if f0.is_cuda:  # samples produced on the GPU (input_pipeline.DeviceInputPipeline): pad in place, nothing crosses PCIe
+            return self._pad_on_device(inputs, f0.device)
         Tf = max(s["input_features"].shape[-1] for s in inputs)
         Ts = max(s["stno_mask"].shape[0] for s in inputs)
         C = inputs[0]["stno_mask"].shape[1]
@@ -147,6 +149,23 @@ class DataCollator:
         on = stage.to(dev, non_blocking=True)
         return (on[:n_f].view(B, M, Tf), on[n_f:n_f + n_s].view(B, C, Ts),
                 on[n_f + n_s:].view(B, Ta).to(inputs[0]["attention_mask"].dtype))
+
+    @staticmethod
+    def _pad_on_device(inputs, dev) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        B, M, C = len(inputs), inputs[0]["input_features"].shape[0], inputs[0]["stno_mask"].shape[1]
+        Tf = max(s["input_features"].shape[-1] for s in inputs)
+        Ts = max(s["stno_mask"].shape[0] for s in inputs)
+        Ta = max(s["attention_mask"].shape[0] for s in inputs)
+        feats = torch.zeros(B, M, Tf, dtype=torch.float32, device=dev)
+        stno = torch.zeros(B, C, Ts, dtype=torch.float32, device=dev)
+        att = torch.zeros(B, Ta, dtype=inputs[0]["attention_mask"].dtype, device=dev)
+        for b, s in enumerate(inputs):
+            f, m, a = s["input_features"], s["stno_mask"], s["attention_mask"]
+            feats[b, :, :f.shape[-1]] = f
+            stno[b, :, :m.shape[0]] = m.T
+            stno[b, 0, m.shape[0]:] = 1.0
+            att[b, :a.shape[0]] = a
+        return feats, stno, att
 
     def __call__(self, inputs: List[Dict[str, Union[List[int], torch.Tensor]]], nested: bool = False) -> BatchFeature:
         longform = [sample["is_long_form"] for sample in inputs]
