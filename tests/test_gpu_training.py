@@ -34,7 +34,8 @@ GRAD_TOL = 5e-2
 # arithmetic exactly on identical inputs.
 GATE_TOL = 0.25
 EOS, SOT, LANG, TASK, NOTS, TS_BEGIN, N_TS = 257, 258, 259, 260, 261, 262, 38
-HEAD = ("model.encoder.additional_self_attention_layer", "model.encoder.subsample_conv", "model.encoder.lm_head")
+HEAD = ("model.encoder.additional_self_attention_layer", "model.encoder.additional_layer", "model.encoder.subsample_conv",
+        "model.encoder.lm_head")
 
 
 class FakeTokenizer:
@@ -71,6 +72,11 @@ def _compare(model, p, names, label, scalar_refs=None):
     checked = 0
     for n in names:
         got = named[n].grad
+        if p[n].grad is None and not (scalar_refs and n in scalar_refs):
+            # a module the forward does not use (additional_self_attention_layer next to additional_layer,
+            # encoder.py:88-100): autograd leaves .grad unset in the reference, and so does the B200 step
+            assert got is None, f"{label}: gradient for {n}, which the oracle's forward never touches"
+            continue
         assert got is not None, f"{label}: no gradient for {n}"
         if scalar_refs and n in scalar_refs:
             ref, scale = scalar_refs[n]
@@ -107,7 +113,13 @@ TINY_SHORT = dataclasses.replace(synth.WHISPER_TINY, T=200, vocab=1000, max_targ
                                  decoder_start_token_id=258, enc_layers=2, dec_layers=2)
 
 
-@pytest.mark.parametrize("dm,B", [(MINI, 2), (TINY_SHORT, 3)], ids=["mini", "tiny-short"])
+# additional_layer=True: a whole encoder layer in front of the CTC head instead of the bare self-attention (encoder.py:17-18, 88-93)
+MINI_LAYER = dataclasses.replace(MINI, additional_layer=True)
+TINY_LAYER = dataclasses.replace(TINY_SHORT, additional_layer=True)
+
+
+@pytest.mark.parametrize("dm,B", [(MINI, 2), (TINY_SHORT, 3), (MINI_LAYER, 2), (TINY_LAYER, 3)],
+                         ids=["mini", "tiny-short", "mini-additional-layer", "tiny-short-additional-layer"])
 @pytest.mark.parametrize("body", [False, True], ids=["head-only", "all-encoder"])
 def test_ctc_pretrain_step(dm, B, body):
     """configs[4]: encoder(return_logits=True) -> get_loss -> backward, as CustomTrainerEncoder.compute_loss does"""
@@ -162,6 +174,12 @@ TINY_BIAS = dataclasses.replace(TINY_SHORT, fddt_bias_only=True)
 @pytest.mark.parametrize("mode", ["decoder-frozen", "fddt-only"])
 def test_finetune_step_bias_only_fddt(dm, B, S, mode):
     _finetune_case(dm, B, S, mode, "tr2")
+
+
+@pytest.mark.parametrize("dm,B,S", [(MINI_LAYER, 2, 11), (TINY_LAYER, 3, 24)], ids=["mini", "tiny-short"])
+def test_finetune_step_additional_layer(dm, B, S):
+    """the CTC branch's gradient reaches the encoder body through the whole extra layer (accumulated into the decoder's)"""
+    _finetune_case(dm, B, S, "decoder-frozen", "tr1")
 
 
 def _finetune_case(dm, B, S, mode, tag):

@@ -16,7 +16,9 @@ TINY_SHORT = dataclasses.replace(synth.WHISPER_TINY, T=200, vocab=1000, max_targ
                                  decoder_start_token_id=258, enc_layers=2, dec_layers=2)
 CASES = {"mini": (MINI, 2, 11), "tiny": (TINY_SHORT, 3, 24),
          "mini-bias": (dataclasses.replace(MINI, fddt_bias_only=True), 2, 11),
-         "tiny-bias": (dataclasses.replace(TINY_SHORT, fddt_bias_only=True), 3, 24)}
+         "tiny-bias": (dataclasses.replace(TINY_SHORT, fddt_bias_only=True), 3, 24),
+         "mini-layer": (dataclasses.replace(MINI, additional_layer=True), 2, 11),
+         "tiny-layer": (dataclasses.replace(TINY_SHORT, additional_layer=True), 3, 24)}
 
 
 def grads(dm, B, S, rounded, tag):
@@ -40,9 +42,12 @@ def grads(dm, B, S, rounded, tag):
 
 
 def main():
-    tags = sys.argv[1:] or ["tr1", "tr2"]
+    only = [a for a in sys.argv[1:] if a in CASES]
+    tags = [a for a in sys.argv[1:] if a not in CASES] or ["tr1", "tr2"]
     for tag in tags:
         for name, (dm, B, S) in CASES.items():
+            if only and name not in only:
+                continue
             g0, de0 = grads(dm, B, S, False, tag)
             g1, de1 = grads(dm, B, S, True, tag)
             rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()  # noqa: E731

@@ -292,28 +292,48 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
 
 def ctc_head_forward_train(enc, hidden_bf16: torch.Tensor, B: int, T: int, tape: EncoderTape) -> torch.Tensor:
     """possibly_update_last_hidden_states + lm_head (encoder.py:87-106,236) keeping the backward's inputs."""
-    if hasattr(enc, "additional_layer"):
-        raise NotImplementedError("training step: additional_layer=True runs forward-only on the B200 path (the recipes "
-                                  "use additional_self_attention_layer)")
     cfg = enc.config
     w = enc.prepare()
     d, H = cfg.d_model, cfg.encoder_attention_heads
     dev = hidden_bf16.device
-    if "ctc_attn" not in w or "sub1" not in w:
-        raise NotImplementedError("training the CTC head needs additional_self_attention_layer + pre_ctc_sub_sample "
-                                  "(the recipes' configuration)")
-    e = w["ctc_attn"]
+    if ("ctc_attn" not in w and "ctc_layer" not in w) or "sub1" not in w:
+        raise NotImplementedError("training the CTC head needs additional_self_attention_layer (or additional_layer) + "
+                                  "pre_ctc_sub_sample (the recipes' configuration)")
     rows = B * T
+    full = "ctc_layer" in w  # a whole pre-LN encoder layer instead of the bare self-attention (encoder.py:88-93)
+    e = w["ctc_layer"] if full else w["ctc_attn"]
+    extra = {}
+    attn_in = hidden_bf16
+    if full:
+        x = hidden_bf16.float()  # the layer's fp32 residual stream
+        attn_in = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=attn_in, store_x=False)
     qkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
-    ops.gemm(hidden_bf16, e["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=e["bqkv"])
+    ops.gemm(attn_in, e["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=e["bqkv"])
     ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
     lse = torch.empty(B, H, T, dtype=torch.float32, device=dev)
     ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], ctx, B=B, H=H, Tq=T, Tk=T, q_row_stride=3 * d, q_batch_stride=T * 3 * d,
                   kv_row_stride=3 * d, kv_batch_stride=T * 3 * d, o_row_stride=d, o_batch_stride=T * d, lse=lse)
     buf = torch.empty(B, T + 2, d, dtype=torch.bfloat16, device=dev)
     ops.zero_pad_rows(buf)
-    ops.gemm(ctx, e["wo"], buf[:, 1:], epilogue=ops.EPI_BIAS_BF16, bias=e["bo"], nb=B, Mb=T, lda=d, a_batch_stride=T * d,
-             ldo=d, out_batch_stride=(T + 2) * d)
+    if full:
+        ffn = e["w1"].shape[0]
+        d1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(ctx, e["wo"], d1, epilogue=ops.EPI_BIAS_BF16, bias=e["bo"])
+        ln2 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ops.fddt_layernorm(x, gamma=e["ln2_g"], beta=e["ln2_b"], ln_out_bf16=ln2, delta1=d1, store_x=False)
+        hdn = torch.empty(rows, ffn, dtype=torch.bfloat16, device=dev)
+        pre = torch.empty(rows, ffn, dtype=torch.bfloat16, device=dev)
+        ops.gemm(ln2, e["w1"], hdn, epilogue=ops.EPI_GELU_SAVE_BF16, bias=e["b1"], aux=pre)
+        d2 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(hdn, e["w2"], d2, epilogue=ops.EPI_BIAS_BF16, bias=e["b2"])
+        out_bf16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+        ops.fddt_layernorm(x, x_out_bf16=out_bf16, delta1=d1, delta2=d2, store_x=False)  # x + d1 + d2 -> bf16
+        buf[:, 1:T + 1] = out_bf16.view(B, T, d)
+        extra = {"x": x, "ln1": attn_in, "d1": d1, "ln2": ln2, "hdn": hdn, "pre": pre}
+    else:
+        ops.gemm(ctx, e["wo"], buf[:, 1:], epilogue=ops.EPI_BIAS_BF16, bias=e["bo"], nb=B, Mb=T, lda=d, a_batch_stride=T * d,
+                 ldo=d, out_batch_stride=(T + 2) * d)
     T1 = (T + 2 - 3) // 2 + 1
     buf1 = torch.empty(B, T1 + 2, d, dtype=torch.bfloat16, device=dev)
     ops.zero_pad_rows(buf1)
@@ -327,7 +347,7 @@ def ctc_head_forward_train(enc, hidden_bf16: torch.Tensor, B: int, T: int, tape:
     logits = torch.empty(B, T2, V1, dtype=torch.float32, device=dev)
     ops.gemm(neck.view(B * T2, d), w["lm_head"], logits.view(B * T2, V1), epilogue=ops.EPI_BIAS_F32)
     tape.ctc = {"hidden": hidden_bf16, "qkv": qkv, "ctx": ctx, "lse": lse, "buf": buf, "buf1": buf1, "neck": neck,
-                "T1": T1, "T2": T2, "B": B, "T": T}
+                "T1": T1, "T2": T2, "B": B, "T": T, **extra}
     return logits
 
 
@@ -404,8 +424,9 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
     V1 = w["lm_head"].shape[0]
     dl = dlogits.view(B * T2, -1)
     ldd = dl.shape[1]
-    flat = g.reserve([enc.lm_head.weight, enc.subsample_conv1.weight, enc.subsample_conv2.weight]
-                     + list(enc.additional_self_attention_layer.parameters()))
+    full = "ctc_layer" in w
+    front = enc.additional_layer if full else enc.additional_self_attention_layer
+    flat = g.reserve([enc.lm_head.weight, enc.subsample_conv1.weight, enc.subsample_conv2.weight] + list(front.parameters()))
     # lm_head (no bias): dneck = dlogits W ; dW += dlogits^T neck
     dneck = torch.empty(B * T2, d, dtype=torch.bfloat16, device=dl.device)
     ops.gemm(dl, w["lm_head"], dneck, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T, K=V1, lda=ldd, Mb=B * T2)
@@ -416,8 +437,13 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
                            T_out=T2, C_in=d, stride=2, need_dx=True)
     dbuf = _conv_backward(g, dbuf1, c["buf"], w["sub1"], enc.subsample_conv1.weight, None, B=B, T_in=T, T_out=T1, C_in=d,
                           stride=2, need_dx=True)
-    att, e = enc.additional_self_attention_layer, w["ctc_attn"]
     dbuf_f = dbuf.view(B * T, d)
+    if full:
+        dh = _ctc_layer_backward(enc, g, dbuf_f, c, w["ctc_layer"], B, T, need_dhidden, dhidden_accum)
+        _fold_conv_grads(g)
+        g.flush(flat)
+        return dh
+    att, e = enc.additional_self_attention_layer, w["ctc_attn"]
     dctx = _linear_backward(g, dbuf_f, c["ctx"], e["wo"], att.out_proj.weight, att.out_proj.bias)
     dqkv = torch.empty(B * T, 3 * d, dtype=torch.bfloat16, device=dl.device)
     qkv = c["qkv"]
@@ -430,6 +456,47 @@ def ctc_head_backward(enc, g: _Grads, dlogits: torch.Tensor, tape: EncoderTape, 
     _fold_conv_grads(g)
     g.flush(flat)
     return dh
+
+
+def _ctc_layer_backward(enc, g: _Grads, dout: torch.Tensor, c: dict, e: dict, B: int, T: int, need_dhidden: bool,
+                        dhidden_accum: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Backward of the whole encoder layer in front of the CTC head (``additional_layer=True``, encoder.py:88-93; the layer is
+    HF WhisperEncoderLayer, HF:modeling_whisper.py:380-430).  dout bf16 [B*T, d] = gradient of the layer output x + d1 + d2."""
+    cfg = enc.config
+    lyr = enc.additional_layer
+    d, H = cfg.d_model, cfg.encoder_attention_heads
+    rows, dev = B * T, dout.device
+    G = dout.float()
+    dpre = _linear_backward(g, dout, c["hdn"], e["w2"], lyr.fc2.weight, lyr.fc2.bias, dx_epilogue=ops.EPI_DGELU_BF16,
+                            aux=c["pre"])
+    dln2 = _linear_backward(g, dpre, c["ln2"], e["w1"], lyr.fc1.weight, lyr.fc1.bias)
+    G2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    G2b = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+    n2, n1 = lyr.final_layer_norm, lyr.self_attn_layer_norm
+    ops.layernorm_fddt_bwd(c["x"], G2, dy=dln2, g_in=G, gamma=e["ln2_g"], delta1=c["d1"], g_out_bf16=G2b,
+                           dgamma=g.get(n2.weight) if g.want(n2.weight) else None,
+                           dbeta=g.get(n2.bias) if g.want(n2.bias) else None)
+    dctx = _linear_backward(g, G2b, c["ctx"], e["wo"], lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias)
+    dqkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
+    qkv = c["qkv"]
+    ops.attention_bwd(qkv, qkv[:, d:], qkv[:, 2 * d:], c["ctx"], dctx, c["lse"], dqkv, dqkv[:, d:], dqkv[:, 2 * d:], B=B,
+                      H=H, Tq=T, Tk=T, q_row_stride=3 * d, q_batch_stride=T * 3 * d, kv_row_stride=3 * d,
+                      kv_batch_stride=T * 3 * d, o_row_stride=d, o_batch_stride=T * d, dq_row_stride=3 * d,
+                      dq_batch_stride=T * 3 * d, dkv_row_stride=3 * d, dkv_batch_stride=T * 3 * d)
+    dln1 = _attention_params_backward(g, lyr.self_attn, e, dqkv, c["ln1"], d, True)
+    want_g1 = g.want(n1.weight)
+    if not need_dhidden and not want_g1 and not g.want(n1.bias):
+        return None
+    Gh = torch.empty(rows, d, dtype=torch.float32, device=dev)
+    Ghb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+    ops.layernorm_fddt_bwd(c["x"], Gh, dy=dln1, g_in=G2, gamma=e["ln1_g"], g_out_bf16=Ghb,
+                           dgamma=g.get(n1.weight) if want_g1 else None, dbeta=g.get(n1.bias) if g.want(n1.bias) else None)
+    if not need_dhidden:
+        return None
+    if dhidden_accum is not None:
+        dhidden_accum.add_(Gh)
+        return None
+    return Ghb
 
 
 def _scb_backward(enc, g: _Grads, cae, e: dict, a: dict, Gs: torch.Tensor, B: int, T: int) -> None:
