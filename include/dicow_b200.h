@@ -152,6 +152,10 @@ DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t*
 DICOW_API int dicow_fddt_full_combine(dicow_handle_t h, const void* y_bf16, int64_t ldy, const float* stno,
                                       int64_t stno_batch_stride, int T, int rows, int d, const float* pos, float* x,
                                       void* stream);
+/* backward of dicow_fddt_full_combine: dy[r, c d : (c + 1) d] = stno[r / T, c, r % T] * g[r, :] (bf16 [rows, >= 4 d]); what
+ * autograd computes for `sum_c mask_c * CustomLinear_c(x)` (FDDT.py:52-62) before the four Linear backward passes. */
+DICOW_API int dicow_fddt_full_scatter(dicow_handle_t h, const float* g, const float* stno, int64_t stno_batch_stride, int T,
+                                      int rows, int d, void* dy_bf16, int64_t ldy, void* stream);
 /* input_features fp32 [B, C, F] -> zero-padded channels-last bf16 [B, F + 2, C] (the buffer conv1's implicit GEMM
  * reads; src/models/dicow/encoder.py:167 nn.Conv1d(padding=1)). */
 DICOW_API int dicow_features_to_channels_last(dicow_handle_t h, const float* in, void* out_bf16, int B, int C, int F,

@@ -175,3 +175,17 @@ def test_gate_bwd(ops, rows, cols, ld):
     assert (out.double() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()  # bf16 output rounding
     assert abs(dgate.item() - ref_dg) <= 1e-3 * max(1.0, abs(ref_dg))
     assert torch.equal(ops.gate_bwd(G, upd, gate, None), out)
+
+
+@pytest.mark.parametrize("rows,T,d", [(600, 200, 384), (96, 48, 128)])
+def test_fddt_full_scatter(rows, T, d):
+    """backward of the mask-weighted sum of full-matrix FDDT (FDDT.py:52-62): dY[:, c d:(c+1) d] = mask_c * G, bit-exact"""
+    from ts_asr_whisper_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    G = torch.randn(rows, d, generator=gen).cuda()
+    stno = torch.rand(rows // T, 4, T, generator=gen).cuda()
+    dY = torch.empty(rows, 4 * d, dtype=torch.bfloat16, device="cuda")
+    ops.fddt_full_scatter(G, stno, dY, T=T)
+    m = stno.permute(0, 2, 1).reshape(rows, 4)                       # [rows, class]
+    ref = (m[:, :, None] * G[:, None, :]).to(torch.bfloat16).reshape(rows, 4 * d)
+    assert torch.equal(dY, ref)

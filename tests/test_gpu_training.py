@@ -176,6 +176,17 @@ def test_finetune_step_bias_only_fddt(dm, B, S, mode):
     _finetune_case(dm, B, S, mode, "tr2")
 
 
+# full-matrix FDDT: a d x d CustomLinear per class (src/models/dicow/layers.py:7-47, FDDT.py:52-62)
+MINI_FULL = dataclasses.replace(MINI, fddt_is_diagonal=False)
+TINY_FULL = dataclasses.replace(TINY_SHORT, fddt_is_diagonal=False)
+
+
+@pytest.mark.parametrize("dm,B,S,tag", [(MINI_FULL, 2, 11, "tr1"), (TINY_FULL, 3, 24, "tr1")], ids=["mini", "tiny-short"])
+@pytest.mark.parametrize("mode", ["decoder-frozen", "fddt-only"])
+def test_finetune_step_full_matrix_fddt(dm, B, S, tag, mode):
+    _finetune_case(dm, B, S, mode, tag)
+
+
 @pytest.mark.parametrize("dm,B,S", [(MINI_LAYER, 2, 11), (TINY_LAYER, 3, 24)], ids=["mini", "tiny-short"])
 def test_finetune_step_additional_layer(dm, B, S):
     """the CTC branch's gradient reaches the encoder body through the whole extra layer (accumulated into the decoder's)"""

@@ -17,6 +17,8 @@ TINY_SHORT = dataclasses.replace(synth.WHISPER_TINY, T=200, vocab=1000, max_targ
 CASES = {"mini": (MINI, 2, 11), "tiny": (TINY_SHORT, 3, 24),
          "mini-bias": (dataclasses.replace(MINI, fddt_bias_only=True), 2, 11),
          "tiny-bias": (dataclasses.replace(TINY_SHORT, fddt_bias_only=True), 3, 24),
+         "mini-full": (dataclasses.replace(MINI, fddt_is_diagonal=False), 2, 11),
+         "tiny-full": (dataclasses.replace(TINY_SHORT, fddt_is_diagonal=False), 3, 24),
          "mini-layer": (dataclasses.replace(MINI, additional_layer=True), 2, 11),
          "tiny-layer": (dataclasses.replace(TINY_SHORT, additional_layer=True), 3, 24)}
 

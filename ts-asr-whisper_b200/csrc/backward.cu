@@ -431,6 +431,29 @@ int launch_ln_bwd_ring(dicow_ctx* ctx, const LnBwdParams& p, int nst, size_t sme
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// backward of fddt_full_combine (elementwise.cu): dY[r, c d : (c + 1) d] = stno[b, c, t] * G[r, :]  (bf16), the gradient
+// of the four stacked class transforms of full-matrix FDDT (src/models/dicow/FDDT.py:52-62); dx and the CustomLinear
+// weight / bias gradients follow from ordinary dgrad / wgrad GEMMs and column sums on dY.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fddt_full_scatter_kernel(const float* __restrict__ g, const float* __restrict__ stno,
+                                                                long long stno_bs, int T, int rows, int d,
+                                                                __nv_bfloat16* __restrict__ dy, long long ldy) {
+  const int nvec = d >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / nvec), c4 = (int)(i - (long long)r * nvec);
+    const int b = r / T, t = r - b * T;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + (long long)r * d) + c4);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float m = __ldg(stno + (long long)b * stno_bs + (long long)c * T + t);
+      reinterpret_cast<uint2*>(dy + (long long)r * ldy + (long long)c * d)[c4] =
+          make_uint2(pack_bf16(m * v.x, m * v.y), pack_bf16(m * v.z, m * v.w));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // out[n] += sum_rows X[row, n]     (bias gradients);  X bf16 or fp32
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -827,6 +850,22 @@ __global__ void __launch_bounds__(512) ce_bwd_kernel(const CeBwdParams p) {
 }  // namespace dicow
 
 using namespace dicow;
+
+extern "C" int dicow_fddt_full_scatter(dicow_handle_t h, const float* g, const float* stno, int64_t stno_batch_stride, int T,
+                                       int rows, int d, void* dy_bf16, int64_t ldy, void* stream_) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  dicow_ctx* ctx = h;
+  DICOW_REQUIRE(ctx, g && stno && dy_bf16 && rows >= 1 && T >= 1 && (rows % T) == 0 && d >= 4 && (d % 4) == 0 && (ldy % 4) == 0 &&
+                         (reinterpret_cast<uintptr_t>(dy_bf16) % 8) == 0 && (reinterpret_cast<uintptr_t>(g) % 16) == 0,
+                "dicow_fddt_full_scatter: bad args");
+  const long long total = (long long)rows * (d / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  fddt_full_scatter_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      g, stno, stno_batch_stride, T, rows, d, reinterpret_cast<__nv_bfloat16*>(dy_bf16), ldy);
+  DICOW_CUDA_OK(ctx, cudaGetLastError());
+  return DICOW_OK;
+}
 
 extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_args_t* a, void* stream_) {
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;

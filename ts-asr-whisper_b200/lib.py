@@ -274,6 +274,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_attention_bf16.argtypes = [vp, C.POINTER(AttentionArgs), vp]
     lib.dicow_features_to_channels_last.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dicow_fddt_full_combine.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.dicow_fddt_full_scatter.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, vp]
     lib.dicow_stno_mask.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, vp, C.c_int64, C.c_int64, vp]
     lib.dicow_augment_batch.argtypes = [vp, C.POINTER(AugmentArgs), vp]
     lib.dicow_zero_pad_rows.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
@@ -317,7 +318,7 @@ EXPORTED_SYMBOLS = [
     "dicow_logits_rules_argmax", "dicow_softlabel_ce", "dicow_ctc_loss", "dicow_attention_bwd_bf16",
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
-    "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch",
+    "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch", "dicow_fddt_full_scatter",
 ]
 
 

@@ -194,6 +194,23 @@ def fddt_full_combine(y: torch.Tensor, stno: torch.Tensor, x: torch.Tensor, *, T
     return x
 
 
+def fddt_full_scatter(g: torch.Tensor, stno: torch.Tensor, dy: torch.Tensor, *, T: int) -> torch.Tensor:
+    """dy[r, c d:(c + 1) d] = stno[r // T, c, r % T] * g[r] -- backward of fddt_full_combine (dicow_fddt_full_scatter);
+    g fp32 [rows, d], dy bf16 [rows, 4 d]."""
+    global launch_count
+    dev = _require_cuda(g, stno, dy)
+    rows, d = g.numel() // g.shape[-1], g.shape[-1]
+    assert dy.dtype == torch.bfloat16 and dy.stride(-1) == 1 and g.dtype == torch.float32 and g.is_contiguous()
+    assert stno.dtype == torch.float32 and stno.stride(2) == 1 and stno.stride(1) == stno.shape[2]
+    h = _lib.handle(dev.index or 0)
+    with torch.cuda.device(dev):
+        rc = _lib.load_library().dicow_fddt_full_scatter(h, _ptr(g), _ptr(stno), stno.stride(0), T, rows, d, _ptr(dy),
+                                                         dy.stride(-2), _stream(dev))
+    _lib.check(rc, h, "dicow_fddt_full_scatter")
+    launch_count += 1
+    return dy
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, Tq: int,
               Tk: int, q_row_stride: int, q_batch_stride: int, kv_row_stride: int, kv_batch_stride: int,
               o_row_stride: int, o_batch_stride: int, causal: bool = False, variant: int = 0,

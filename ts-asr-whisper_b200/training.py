@@ -196,9 +196,6 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
     the per-layer inputs the backward needs.  Returns (last_hidden fp32 [B, T, d], bf16 copy [B*T, d]).
     With ``enrollments`` the first ``scb_layers`` layers run on the stacked [targets ; enrollments] streams."""
     cfg = enc.config
-    if cfg.use_fddt and not cfg.fddt_is_diagonal and not cfg.fddt_bias_only:
-        raise NotImplementedError("training step: full-matrix FDDT runs forward-only on the B200 path (the recipes use "
-                                  "the diagonal FDDT; bias-only has a backward too)")
     n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers and enrollments is not None) else 0
     if n_scb:  # encoder.py:152-154 (stacked instead of interleaved, see the module docstring)
         input_features = torch.cat((input_features, enrollments["input_features"].to(input_features.device)), dim=0)
@@ -228,10 +225,21 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
         stno0 = torch.zeros(B, 4, T, dtype=torch.float32, device=dev)
         stno0[:, 0] = 1.0
     fw0, fb0 = w["fddt0"]
-    ops.gemm(a1, w["conv2_w"], x, epilogue=ops.EPI_GELU_FDDT_POS_F32, bias=w["conv2_b"], nb=B, Mb=T, K=3 * d, lda=2 * d,
-             a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, stno=stno0, stno_batch_stride=4 * T, fddt_w=fw0,
-             fddt_b=fb0, pos=w["pos"])
-    tape.stem = {"a0": a0, "a1": a1, "pre1": pre1, "stno0": stno0, "B": B, "T": T, "F": F}
+    full0 = bool(w.get("fddt_full")) and w.get("fddt0_full") is not None
+    if full0:  # full-matrix initial FDDT (encoder.py:173-179 with CustomLinear): see DiCoWEncoder._forward_hidden
+        g2 = torch.empty(B * T, d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(a1, w["conv2_w"], g2, epilogue=ops.EPI_BIAS_GELU_BF16, bias=w["conv2_b"], nb=B, Mb=T, K=3 * d, lda=2 * d,
+                 a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d)
+        W4, b4 = w["fddt0_full"]
+        y = torch.empty(B * T, 4 * d, dtype=torch.bfloat16, device=dev)
+        ops.gemm(g2, W4, y, epilogue=ops.EPI_BIAS_BF16, bias=b4)
+        ops.fddt_full_combine(y, stno0, x, T=T, pos=w["pos"])
+        del g2, y
+    else:
+        ops.gemm(a1, w["conv2_w"], x, epilogue=ops.EPI_GELU_FDDT_POS_F32, bias=w["conv2_b"], nb=B, Mb=T, K=3 * d, lda=2 * d,
+                 a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, stno=stno0, stno_batch_stride=4 * T, fddt_w=fw0,
+                 fddt_b=fb0, pos=w["pos"])
+    tape.stem = {"a0": a0, "a1": a1, "pre1": pre1, "stno0": stno0, "B": B, "T": T, "F": F, "full": full0}
     rows = B * T
     ffn = cfg.encoder_ffn_dim
     H = cfg.encoder_attention_heads
@@ -245,6 +253,19 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
         x = x_pre.clone()  # the stream before this layer's pending deltas / FDDT is an input of the backward
         scb = None
         rows_in, stno_in = rows, stno
+        full = None
+        if fd is not None and w.get("fddt_full"):
+            # full-matrix FDDT (layers.py:7-47, FDDT.py:52-62): fold the pending deltas, project the bf16 stream with the
+            # stacked [4 d, d] class transforms, mask-weighted sum back into the fp32 stream.  For the rest of the layer
+            # (and its backward) the transformed stream is the layer input: no table, no pending deltas.
+            xb_in = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+            ops.fddt_layernorm(x, x_out_bf16=xb_in, delta1=d1, delta2=d2, store_x=True)
+            y = torch.empty(rows, 4 * d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(xb_in, fd[0], y, epilogue=ops.EPI_BIAS_BF16, bias=fd[1])
+            ops.fddt_full_combine(y, stno, x, T=T)
+            del y
+            full = {"xb": xb_in, "W4": fd[0]}
+            x_pre, fd, d1, d2 = x, None, None, None
         if i < n_scb:  # encoder.py:205-213: FDDT, speaker communication block, (last SCB layer) drop the enrollment stream
             xb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
             ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
@@ -280,7 +301,7 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
         ops.gemm(hdn, e["w2"], d2n, epilogue=ops.EPI_BIAS_BF16, bias=e["b2"])
         tape.layers.append({"x_pre": x_pre, "d1_in": d1, "d2_in": d2, "x_post": x, "ln1": ln1, "qkv": qkv, "ctx": ctx,
                             "lse": lse, "d1": d1n, "ln2": ln2, "pre": pre, "hdn": hdn, "d2": d2n, "fd": fd, "scb": scb,
-                            "B": B, "rows_in": rows_in, "stno_in": stno_in})
+                            "B": B, "rows_in": rows_in, "stno_in": stno_in, "full": full})
         d1, d2 = d1n, d2n
     out = torch.empty(B, T, d, dtype=torch.float32, device=dev)
     out_bf16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
@@ -565,7 +586,7 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
 
     def group(i):  # one exchange bucket per layer: its own parameters, its FDDT tables, its speaker communication block
         ps = list(enc.layers[i].parameters())  # (+ the final LayerNorm with the last layer)
-        if tape.layers[i]["fd"] is not None:
+        if tape.layers[i]["fd"] is not None or tape.layers[i]["full"] is not None:
             ps += list(enc.fddts[i].parameters())
         if tape.layers[i]["scb"] is not None:
             ps += list(enc.ca_enrolls[i].parameters())
@@ -633,6 +654,8 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
                                    fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dfddt_w=dfw, dfddt_b=dfb)
         if dfw is not None:
             _scatter_fddt_grads(g, enc.fddts[i], dfw, dfb)
+        if s["full"] is not None:  # G is the gradient of the TRANSFORMED stream: back through the four class transforms
+            G, Gb = _fddt_full_backward(g, enc.fddts[i], G, stno, s["full"]["xb"], s["full"]["W4"], T)
         g.flush(flat)
         tape.layers[i] = None  # this layer's activations are dead: let the allocator reuse them
     if not n_layers:
@@ -642,6 +665,24 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
     _stem_backward(enc, g, G, tape)
     _fold_conv_grads(g)
     g.flush(flat)
+
+
+def _fddt_full_backward(g: _Grads, fmod, G: torch.Tensor, stno: torch.Tensor, xb: torch.Tensor, W4: torch.Tensor, T: int):
+    """Backward of x' = sum_c mask_c * CustomLinear_c(x) (full-matrix FDDT, src/models/dicow/FDDT.py:52-62) computed as one
+    stacked projection: G fp32 [rows, d] = dL/dx' -> (dL/dx fp32, its bf16 copy); class weight / bias gradients accumulated.
+    A disabled class is an identity block of W4 and only contributes to dx."""
+    rows, d = G.shape
+    dY = torch.empty(rows, 4 * d, dtype=torch.bfloat16, device=G.device)
+    ops.fddt_full_scatter(G, stno, dY, T=T)
+    dx = torch.zeros(rows, d, dtype=torch.float32, device=G.device)
+    ops.gemm(dY, W4, dx, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_W_T, splits=1)
+    for c, name in enumerate(_FDDT_ORDER):
+        lin = getattr(fmod, name + "_linear", None)
+        if lin is None:
+            continue
+        blk = slice(c * d, (c + 1) * d)
+        _linear_backward(g, dY, xb, W4, lin.weight, lin.bias, need_dx=False, dy_cols=blk, w_rows=blk)
+    return dx, ops.cast_bf16(dx)
 
 
 def _scatter_fddt_grads(g: _Grads, fmod, dfw: torch.Tensor, dfb: torch.Tensor) -> None:
@@ -680,14 +721,17 @@ def _stem_backward(enc, g: _Grads, G0: torch.Tensor, tape: EncoderTape) -> None:
     ops.gemm(s["a1"], w["conv2_w"], g2, epilogue=ops.EPI_GELU_SAVE_BF16, bias=w["conv2_b"], nb=B, Mb=T, K=3 * d, lda=2 * d,
              a_batch_stride=(F + 2) * d, ldo=d, out_batch_stride=T * d, aux=pre2)
     fw0, fb0 = w["fddt0"]
-    dfw = torch.zeros(4, d, dtype=torch.float32, device=dev) if has_f0 else None
-    dfb = torch.zeros(4, d, dtype=torch.float32, device=dev) if has_f0 else None
-    dg2 = torch.empty(B * T, d, dtype=torch.float32, device=dev)
-    zero_x = torch.zeros(B * T, d, dtype=torch.float32, device=dev)
-    ops.layernorm_fddt_bwd(zero_x, dg2, g_in=G0, delta1=g2, T=T, stno=s["stno0"], fddt_w=fw0, fddt_b=fb0, dfddt_w=dfw,
-                           dfddt_b=dfb)
-    if has_f0:
-        _scatter_fddt_grads(g, enc.initial_fddt, dfw, dfb)
+    if s.get("full"):
+        dg2, _ = _fddt_full_backward(g, enc.initial_fddt, G0, s["stno0"], g2, w["fddt0_full"][0], T)
+    else:
+        dfw = torch.zeros(4, d, dtype=torch.float32, device=dev) if has_f0 else None
+        dfb = torch.zeros(4, d, dtype=torch.float32, device=dev) if has_f0 else None
+        dg2 = torch.empty(B * T, d, dtype=torch.float32, device=dev)
+        zero_x = torch.zeros(B * T, d, dtype=torch.float32, device=dev)
+        ops.layernorm_fddt_bwd(zero_x, dg2, g_in=G0, delta1=g2, T=T, stno=s["stno0"], fddt_w=fw0, fddt_b=fb0, dfddt_w=dfw,
+                               dfddt_b=dfb)
+        if has_f0:
+            _scatter_fddt_grads(g, enc.initial_fddt, dfw, dfb)
     if not any(p.requires_grad for p in stem_params):
         return
     dpre2 = ops.dgelu_mul(dg2, pre2)  # bf16 [B*T, d]
