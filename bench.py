@@ -180,7 +180,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "whisper-large-v3-turbo + FDDT encoder forward, batch=32 synthetic 30s, 1xB200 "
+    config = {"workload": "whisper-large-v3-turbo + FDDT encoder forward, batch=32 synthetic 30s per B200 "
                           "(BASELINE configs[1])", "batch_per_gpu": args.batch, "mel_bins": 128, "frames": 3000,
               "layers": 32, "d_model": 1280, "parallelism": f"replicas x{world}, no data-path collective",
               "l2": "per-step working set (2.5 GB weights+activations per layer pass) >> 126 MB L2; 3 input batches rotate"}
