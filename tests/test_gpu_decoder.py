@@ -532,3 +532,93 @@ def test_detect_language_and_prompt_without_forced_ids(mini):
     assert torch.equal(out["sequences"], forced["sequences"])
     with pytest.raises(ValueError):
         model.generate(feats.to(DEV), stno_mask=stno.to(DEV), language="zz")
+
+
+# ---- SE-DiCoW generate(): enrollments, and the enrollment key/value cache of the long-form loop ---------------------------
+@pytest.fixture(scope="module")
+def mini_se():
+    dm = synth.GOLDEN_MINI  # use_enrollments, 2 speaker communication blocks
+    model, p = build_model(dm)
+    feats = torch.from_numpy(synth.make_features("g0", 2, dm.n_mels, 2 * dm.T))
+    stno = torch.from_numpy(synth.make_stno("g0", 2, dm.T, "soft", pad_tail=7))
+    enr = {"input_features": torch.from_numpy(synth.make_features("g0e", 2, dm.n_mels, 2 * dm.T)),
+           "stno_mask": torch.from_numpy(synth.make_stno("g0e", 2, dm.T, "hard"))}
+    return dm, model, p, feats, stno, enr
+
+
+def _gen_cfg(model, max_new):
+    model.tokenizer, model.soft_label_creator = None, None
+    gc = model.generation_config
+    gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = NOTS, EOS, EOS
+    gc.suppress_tokens, gc.return_timestamps, gc.max_new_tokens, gc.num_beams = SUPPRESS, True, max_new, 1
+
+
+def test_encoder_enrollment_kv_cache_is_exact(mini_se):
+    """the enrollment stream never reads the target stream (layers.py:145-170): its projected keys / values captured on one
+    window reproduce the full two-stream forward of ANOTHER window bit for bit"""
+    dm, model, p, feats, stno, enr = mini_se
+    enc = model.get_encoder()
+    enr_d = {k: v.to(DEV) for k, v in enr.items()}
+    cap = []
+    first = enc(feats.to(DEV), stno_mask=stno.to(DEV), enrollments=enr_d, capture_enrollment_kv=cap).last_hidden_state
+    assert len(cap) == dm.scb_layers and cap[0].shape == (2, dm.T, 2 * dm.d)
+    feats2 = torch.from_numpy(synth.make_features("g2", 2, dm.n_mels, 2 * dm.T)).to(DEV)
+    stno2 = torch.from_numpy(synth.make_stno("g2", 2, dm.T, "soft")).to(DEV)
+    full = enc(feats2, stno_mask=stno2, enrollments=enr_d).last_hidden_state
+    cached = enc(feats2, stno_mask=stno2, enrollment_kv=cap).last_hidden_state
+    assert torch.equal(full, cached) and not torch.equal(full, first)
+    swapped = enc(feats2, stno_mask=stno2, enrollment_kv=[c.flip(0) for c in cap]).last_hidden_state
+    assert not torch.equal(swapped, full)  # the cache really is what conditions the targets
+    with pytest.raises(ValueError, match="either"):
+        enc(feats2, stno_mask=stno2, enrollments=enr_d, enrollment_kv=cap)
+
+
+def test_generate_se_dicow_matches_oracle_and_cache_is_transparent(mini_se):
+    dm, model, p, feats, stno, enr = mini_se
+    _gen_cfg(model, 16)
+    prompt = torch.tensor([[SOT, LANG, TASK]] * 2)
+    enr_d = {k: v.to(DEV) for k, v in enr.items()}
+    # one window: token parity with the oracle's two-stream encoder + greedy loop
+    out = model.generate(feats.to(DEV), stno_mask=stno.to(DEV), enrollments=enr_d, forced_decoder_ids=prompt,
+                         return_segments=True)
+    with torch.no_grad():
+        ref_enc = orc.encoder_forward(p, dm, feats, stno, enrollments=enr)
+        ref_ids, ref_lg = orc.greedy_decode(p, dm, ref_enc, prompt, 16, suppress=SUPPRESS, no_timestamps=NOTS,
+                                            ts_begin=TS_BEGIN, return_logits=True)
+    enc_dev = model.get_encoder()(feats.to(DEV), stno_mask=stno.to(DEV), enrollments=enr_d).last_hidden_state
+    assert rel_err(enc_dev, ref_enc) < BF16_TOL
+    rules = dict(eos=EOS, pad=EOS, no_timestamps=NOTS, ts_begin=TS_BEGIN, max_initial_timestamp_index=None,
+                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap(SUPPRESS, torch.device(DEV)))
+    ids = model.greedy_decode_window(enc_dev, prompt.to(DEV), 3 + 16, rules)
+    _check_greedy(ids, ref_ids, ref_lg, 3, dm)
+    assert out["sequences"].shape[0] == 2
+    # three windows per recording (second one shorter): the cached long-form loop returns exactly what the uncached one does
+    F2 = 2 * dm.T
+    more = [torch.from_numpy(synth.make_features(f"g{k}", 2, dm.n_mels, F2)) for k in (1, 3)]
+    long_feats = torch.cat([feats] + more, dim=-1).to(DEV)
+    long_stno = torch.cat([stno] + [torch.from_numpy(synth.make_stno(f"g{k}", 2, dm.T, "soft")) for k in (1, 3)], dim=-1).to(DEV)
+    attn = torch.ones(2, 3 * F2, dtype=torch.long)
+    attn[1, F2 + 31:] = 0
+    kw = dict(attention_mask=attn.to(DEV), stno_mask=long_stno, enrollments=enr_d, forced_decoder_ids=prompt, return_segments=True)
+    calls = []
+    enc = model.get_encoder()
+    orig = enc._forward_inference
+
+    def spy(*a, **k):
+        calls.append(a[9] is not None if len(a) > 9 else k.get("enrollment_kv") is not None)
+        return orig(*a, **k)
+    enc._forward_inference = spy
+    try:
+        model.cache_enrollment_kv = True
+        with_cache = model.generate(long_feats, **kw)
+        used = list(calls)
+        calls.clear()
+        model.cache_enrollment_kv = False
+        without = model.generate(long_feats, **kw)
+    finally:
+        enc._forward_inference = orig
+        model.cache_enrollment_kv = True
+    assert used[0] is False and all(used[1:]) and len(used) >= 2 and not any(calls)
+    assert torch.equal(with_cache["sequences"], without["sequences"])
+    assert [[s["tokens"].tolist() for s in r] for r in with_cache["segments"]] == \
+           [[s["tokens"].tolist() for s in r] for r in without["segments"]]

@@ -380,18 +380,23 @@ class DiCoWEncoder(nn.Module):
                       q_batch_stride=T * 3 * d, kv_row_stride=3 * d, kv_batch_stride=T * 3 * d,
                       o_row_stride=o_row_stride, o_batch_stride=o_batch_stride, variant=self.attention_variant)
 
-    def _scb(self, e: dict, x: torch.Tensor, xb: torch.Tensor, B: int, T: int) -> None:
-        """SE-DiCoW speaker communication block (layers.py:145-170) on the interleaved [2B, T, d] streams:
-        x (fp32 residual, target rows updated in place), xb = bf16 copy of x."""
+    def _scb(self, e: dict, x: torch.Tensor, xb: torch.Tensor, B: int, T: int, kv: Optional[torch.Tensor] = None
+             ) -> torch.Tensor:
+        """SE-DiCoW speaker communication block (layers.py:145-170).  Default: the interleaved [2B, T, d] streams --
+        x (fp32 residual, target rows updated in place), xb = bf16 copy of x.  With ``kv`` (bf16 [B, T, 2d], the
+        enrollment stream's projected keys / values of this block from an earlier window of the same recording) x / xb
+        hold the B target streams only.  Returns kv."""
         d, H = self.config.d_model, self.config.encoder_attention_heads
         dev = x.device
+        sb = (1 if kv is not None else 2) * T * d  # batch stride of the target rows inside x / xb
         q = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
-        kv = torch.empty(B, T, 2 * d, dtype=torch.bfloat16, device=dev)
         # q from the target rows (even), k/v from the enrollment rows (odd) -- no LayerNorm
         ops.gemm(xb, e["wq"], q, epilogue=ops.EPI_BIAS_BF16, bias=e["bq"], nb=B, Mb=T, lda=d,
-                 a_batch_stride=2 * T * d, ldo=d, out_batch_stride=T * d)
-        ops.gemm(xb[1], e["wkv"], kv, epilogue=ops.EPI_BIAS_BF16, bias=e["bkv"], nb=B, Mb=T, lda=d,
-                 a_batch_stride=2 * T * d, ldo=2 * d, out_batch_stride=T * 2 * d)
+                 a_batch_stride=sb, ldo=d, out_batch_stride=T * d)
+        if kv is None:
+            kv = torch.empty(B, T, 2 * d, dtype=torch.bfloat16, device=dev)
+            ops.gemm(xb[1], e["wkv"], kv, epilogue=ops.EPI_BIAS_BF16, bias=e["bkv"], nb=B, Mb=T, lda=d,
+                     a_batch_stride=2 * T * d, ldo=2 * d, out_batch_stride=T * 2 * d)
         ctx = torch.empty(B, T, d, dtype=torch.bfloat16, device=dev)
         ops.attention(q, kv, kv[:, :, d:], ctx, B=B, H=H, Tq=T, Tk=T, q_row_stride=d, q_batch_stride=T * d,
                       kv_row_stride=2 * d, kv_batch_stride=T * 2 * d, o_row_stride=d, o_batch_stride=T * d,
@@ -401,12 +406,13 @@ class DiCoWEncoder(nn.Module):
         # ffn.0 over cat([attn_out, q_stream]) without materialising the concat: split-K over two sources
         hdn = torch.empty(B, T, e["w1"].shape[0], dtype=torch.bfloat16, device=dev)
         ops.gemm(ao, e["w1"], hdn, epilogue=ops.EPI_BIAS_GELU_BF16, bias=e["b1"], nb=B, Mb=T, K=2 * d, lda=d,
-                 a_batch_stride=T * d, A2=xb, lda2=d, a2_batch_stride=2 * T * d, K1=d, ldo=hdn.shape[-1],
+                 a_batch_stride=T * d, A2=xb, lda2=d, a2_batch_stride=sb, K1=d, ldo=hdn.shape[-1],
                  out_batch_stride=T * hdn.shape[-1])
         # target rows: x += tanh(gate) * (ffn.3(hdn))
         ops.gemm(hdn, e["w2"], x, epilogue=ops.EPI_RESIDUAL_F32, bias=e["b2"], nb=B, Mb=T, lda=hdn.shape[-1],
-                 a_batch_stride=T * hdn.shape[-1], ldo=d, out_batch_stride=2 * T * d, resid=x, ldr=d,
-                 resid_batch_stride=2 * T * d, gate=e["gate"])
+                 a_batch_stride=T * hdn.shape[-1], ldo=d, out_batch_stride=sb, resid=x, ldr=d,
+                 resid_batch_stride=sb, gate=e["gate"])
+        return kv
 
     def possibly_update_last_hidden_states(self, hidden_states: torch.Tensor) -> torch.Tensor:
         """encoder.py:87-106: extra self-attention (replaces the hidden state), two stride-2 convs.  fp32 in/out."""
@@ -479,7 +485,8 @@ class DiCoWEncoder(nn.Module):
         return logits
 
     def forward(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
-                output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False, enrollments=None):
+                output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False, enrollments=None,
+                enrollment_kv=None, capture_enrollment_kv=None):
         """encoder.py:140-246.  With autograd recording, trainable parameters and ``return_logits`` (the CTC pre-training
         call, src/utils/trainers.py:76-103) the logits carry a grad_fn (training.EncoderLogitsFn); every other call is
         the inference path.  Fine-tuning goes through DiCoWForConditionalGeneration.forward, which owns the encoder's
@@ -497,12 +504,20 @@ class DiCoWEncoder(nn.Module):
                 return CausalLMOutput(loss=None, logits=logits, hidden_states=hidden)
         with torch.no_grad():
             return self._forward_inference(input_features, attention_mask, head_mask, output_attentions,
-                                           output_hidden_states, return_dict, stno_mask, return_logits, enrollments)
+                                           output_hidden_states, return_dict, stno_mask, return_logits, enrollments,
+                                           enrollment_kv, capture_enrollment_kv)
 
     def _forward_inference(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
                            output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False,
-                           enrollments=None):
+                           enrollments=None, enrollment_kv=None, capture_enrollment_kv=None):
+        """``capture_enrollment_kv`` (a list) receives, per speaker communication block, the enrollment stream's projected
+        keys / values (bf16 [B, T, 2d]); ``enrollment_kv`` takes such a list back instead of ``enrollments``: the
+        enrollment stream never reads the target stream (layers.py:145-170 updates the query stream only), so for the
+        next windows of the same recording its 8 layer passes and stem are skipped -- same numbers, 16 % fewer FLOPs per
+        long-form window (generate() does this)."""
         cfg = self.config
+        if enrollment_kv is not None and enrollments is not None:
+            raise ValueError("pass either enrollments or enrollment_kv")
         if output_attentions or output_hidden_states or head_mask is not None:
             raise NotImplementedError("output_attentions / output_hidden_states / head_mask are not produced by the "
                                       "fused B200 path")
@@ -564,7 +579,10 @@ class DiCoWEncoder(nn.Module):
         #   next layer : x <- FDDT(x + d1 + d2), LN1(x)
         # which is the reference's bf16-autocast arithmetic (bf16 Linear output + fp32 residual) with 30 % less HBM traffic.
         n_scb = cfg.scb_layers if (cfg.use_enrollments and cfg.scb_layers) else 0
-        if n_scb and (Bx % 2):
+        cached = enrollment_kv is not None
+        if cached and len(enrollment_kv) != n_scb:
+            raise ValueError(f"enrollment_kv needs one entry per speaker communication block ({n_scb})")
+        if n_scb and not cached and (Bx % 2):
             raise ValueError("use_enrollments expects interleaved target/enrollment streams (even batch)")
         ffn = cfg.encoder_ffn_dim
         d1 = d2 = None  # pending bf16 residual updates of the previous layer
@@ -587,8 +605,10 @@ class DiCoWEncoder(nn.Module):
                 ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
                                    fddt_b=fd[1] if fd else None, x_out_bf16=xb, delta1=d1, delta2=d2)
                 d1 = d2 = None
-                self._scb(w["scb"][i], x, xb, Bx // 2, T)
-                if i == n_scb - 1:  # encoder.py:210-213: the enrollment stream is no longer needed
+                kv = self._scb(w["scb"][i], x, xb, Bx if cached else Bx // 2, T, kv=enrollment_kv[i] if cached else None)
+                if capture_enrollment_kv is not None and not cached:
+                    capture_enrollment_kv.append(kv)
+                if i == n_scb - 1 and not cached:  # encoder.py:210-213: the enrollment stream is no longer needed
                     x = x.view(Bx // 2, 2, T, d)[:, 0].contiguous()
                     stno = stno.view(Bx // 2, 2, 4, T)[:, 0].contiguous() if stno is not None else None
                     Bx //= 2

@@ -872,6 +872,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         segments: List[List[dict]] = [[] for _ in range(B0)]
         batch_idx_map = list(range(B0))
         feats = input_features
+        enr_cache, enr_rows = None, {}
         while bool((seek < max_frames).any()):
             # drop finished recordings from the batch (HF:_maybe_reduce_batch)
             keep = [i for i, prev in enumerate(batch_idx_map) if seek[prev] < max_frames[prev]]
@@ -900,11 +901,22 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             seg_in = torch.cat(seg_in, 0)
             seg_stno = torch.cat(seg_stno, 0) if seg_stno else None
             self.stno_mask_seek = seg_stno
-            enr = None
+            enr = enr_kv = capture = None
             if cfg.use_enrollments and enrollments is not None:
-                idx = torch.as_tensor(batch_idx_map, device=dev)
-                enr = {k: v[idx] for k, v in enrollments.items()}
-            hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr).last_hidden_state
+                if enr_cache is not None:
+                    # later windows of a recording: the enrollment stream's keys / values of every speaker communication
+                    # block are those of its first window (the stream never reads the target stream) -- reuse them
+                    rows_of = torch.as_tensor([enr_rows[prev] for prev in batch_idx_map], device=dev)
+                    enr_kv = [c.index_select(0, rows_of) for c in enr_cache]
+                else:
+                    idx = torch.as_tensor(batch_idx_map, device=dev)
+                    enr = {k: v[idx] for k, v in enrollments.items()}
+                    if getattr(self, "cache_enrollment_kv", True) and bool((max_frames > num_segment_frames).any()):
+                        capture = []
+            hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr, enrollment_kv=enr_kv,
+                         capture_enrollment_kv=capture).last_hidden_state
+            if capture:
+                enr_cache, enr_rows = capture, {prev: i for i, prev in enumerate(batch_idx_map)}
             ctc = None
             if gs["ctc_weight"] > 0:  # generation.py:49-51, 250-268: the encoder's CTC posteriors rescore every step
                 if not hasattr(enc, "lm_head"):
