@@ -147,3 +147,25 @@ def test_device_input_pipeline_raw_audio_to_augmented_batch():
     rf, rs = A.augment(feats, stno, plan, cfg)
     assert plan.warp is not None and len(plan.segments) > 0
     assert np.array_equal(aug["input_features"].cpu().numpy(), rf) and np.array_equal(aug["stno_mask"].cpu().numpy(), rs)
+
+
+def test_augment_of_a_cpu_collated_batch_equals_collating_on_the_gpu():
+    """workers collate on the CPU (no augmentation), the training process augments on the GPU: same draws, same batch"""
+    from ts_asr_whisper_b200.collators import DataCollator
+    np_seed, torch_seed, n_mels, frames, fields = G.CASES["v3_all"]
+    ins = [{"is_long_form": False, "transcript": "x", "input_features": torch.from_numpy(f),
+            "attention_mask": torch.ones(f.shape[1], dtype=torch.long), "stno_mask": torch.from_numpy(s)}
+           for f, s in G.make_inputs(np_seed, n_mels, frames)]
+    col = DataCollator(feature_extractor=None, tokenizer=Tok(), bos_token_id=0, max_length=16, device="cuda", **fields)
+    torch.manual_seed(torch_seed)
+    direct = col(ins)
+    off = DataCollator(feature_extractor=None, tokenizer=Tok(), bos_token_id=0, max_length=16, device="cpu",
+                       stno_segment_augment_prob=0.0, spec_aug_prob=0.0)
+    torch.manual_seed(999)
+    cpu_batch = off(ins)  # consumes one draw (the SpecAug coin) like the reference with its augmentations off
+    assert not cpu_batch["input_features"].is_cuda
+    keep = cpu_batch["stno_mask"].clone()
+    torch.manual_seed(torch_seed)
+    later = col.augment(cpu_batch)
+    assert torch.equal(later["input_features"], direct["input_features"]) and torch.equal(later["stno_mask"], direct["stno_mask"])
+    assert torch.equal(keep, off(ins)["stno_mask"])  # the CPU batch the workers produced was not modified in place

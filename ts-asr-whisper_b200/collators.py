@@ -122,6 +122,21 @@ class DataCollator:
                                  feats=feats, factor=self.conv_subsample_factor, spec=plan.spec, warp=plan.warp,
                                  freq_masks=plan.freq_masks, time_masks=plan.time_masks, mask_channels=self.mask_channels)
 
+    def augment(self, batch):
+        """Augment an already collated batch: ``input_features`` [B, M, Tf] / ``stno_mask`` [B, 4, Tf / 2] as the reference's
+        collator returns them with its own augmentations switched off (stno_segment_augment_prob=0, stno_gaussian_noise_var
+        =None, spec_aug_prob=0).  DataLoader workers keep padding / tokenising on the CPU; the training process moves the
+        batch to the GPU and calls this -- same draws, same result as ``__call__`` on the samples."""
+        dev = torch.device(self.device)
+        feats = batch["input_features"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        stno = batch["stno_mask"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if stno is batch["stno_mask"]:
+            stno = stno.clone()  # the segment / noise steps work in place
+        B, C, Ts = stno.shape
+        plan = self.draw_plan(B, C, Ts, feats.shape[1], feats.shape[2])
+        batch["input_features"], batch["stno_mask"] = self.apply_plan(feats, stno, plan)
+        return batch
+
     # ------------------------------------------------------------------------------------------------------------
     def _pad_to_device(self, inputs) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """pad_sequence of features / attention masks / STNO masks (collators.py:153-163) into ONE pinned staging buffer,
