@@ -248,6 +248,37 @@ def test_training_step_updates_and_second_step():
     assert abs(ev.loss.item() - out.loss.item()) < 1e-3 * max(1.0, abs(ev.loss.item()))
 
 
+def test_unfreeze_after_fddt_warmup_phase():
+    """CustomTrainer.training_step (src/utils/trainers.py:116-139) flips requires_grad in the middle of training: the first
+    steps train the FDDT tables only, then everything except the frozen keywords.  The step after the flip must see the
+    new trainable set (no stale gradient buckets / tapes) and match the oracle's autograd on it."""
+    dm, B, S = TINY_SHORT, 3, 24
+    model, p = _build(dm)
+    model.set_tokenizer(FakeTokenizer())
+    feats, stno = _inputs(dm, B, "tr1")
+    labels = torch.from_numpy(synth.make_labels("tr1", B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK))).to(DEV)
+    for n, q in model.named_parameters():
+        q.requires_grad_("fddt" in n)
+    model(feats, stno_mask=stno, labels=labels, upp_labels=labels).loss.backward()
+    with_grad = {n for n, q in model.named_parameters() if q.grad is not None}
+    assert with_grad and all("fddt" in n for n in with_grad)
+    model.zero_grad(set_to_none=True)
+    frozen_keywords = ("decoder", "embed_positions")  # the flip of trainers.py:121-131
+    for n, q in model.named_parameters():
+        q.requires_grad_(not any(k in n for k in frozen_keywords))
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+    out.loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    ref_loss, _, _ = orc.model_forward(p, dm, feats, stno, labels, labels, ctc_prefix_tokens=(SOT, LANG, TASK),
+                                       ts_begin=TS_BEGIN, n_ts=N_TS)
+    ref_loss.backward()
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    _compare(model, p, trainable, "after-unfreeze")
+    assert all(q.grad is None for n, q in model.named_parameters() if not q.requires_grad)
+
+
 # ---- SE-DiCoW: enrollment streams + speaker communication blocks in the training step -------------------------------
 SE_MINI = synth.GOLDEN_MINI  # 3 layers, 2 of them with an SCB, odd T
 SE_TINY = dataclasses.replace(TINY_SHORT, enc_layers=3, use_enrollments=True, scb_layers=2)
