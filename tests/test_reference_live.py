@@ -65,3 +65,65 @@ def test_oracle_equals_reference_collator_on_random_cases(case):
     else:
         assert np.abs(f2 - gf).max() <= 2e-6 * max(1.0, np.abs(gf).max()) and np.abs(s2 - gs).max() <= 2e-6
         assert np.array_equal(f2 == 0, gf == 0)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_joint_ctc_rescorer_equals_reference_on_random_cases(case):
+    """oracle/ctc_prefix.py against the reference's CTCRescorerLogitsProcessor / CTCPrefixScore (src/models/dicow/
+    decoding.py:8-338) driven like the greedy loop, on random sizes, weights and score patterns (tests/golden/ctc_joint.npz
+    stores one such run)."""
+    from oracle import ctc_prefix as cp
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.decoding import CTCRescorerLogitsProcessor  # the reference
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"reference decoding module not importable: {e}")
+    finally:
+        sys.path.remove(REF)
+    rng = np.random.default_rng(500 + case)
+    n_text = int(rng.integers(20, 60))
+    EOS, SOT = n_text, n_text + 1
+    TS0, n_ts = n_text + 5, int(rng.integers(6, 20))
+    V = TS0 + n_ts
+    BLANK = V
+    B, T, K = int(rng.integers(1, 6)), int(rng.integers(6, 30)), int(rng.integers(3, min(15, n_text)))
+    W, steps = float(rng.choice([0.1, 0.3, 0.7])), int(rng.integers(5, 12))
+    upper = {2: 11, 4: 13} if case % 2 else {1: 7}  # the reference cannot take an empty mapping (decoding.py:183-186)
+
+    class Tok:
+        prefix_tokens = [SOT, SOT + 1, SOT + 2]
+        upper_cased_tokens = upper
+
+        def get_vocab(self):
+            return {"<|0.00|>": TS0}
+
+    enc_logits = torch.from_numpy(rng.normal(size=(B, T, V + 1)).astype(np.float32)) * 2.5
+    enc_logits[..., BLANK] += 1.0
+    ref = CTCRescorerLogitsProcessor(enc_logits.clone(), torch.full((B,), T), BLANK, EOS, EOS, SOT, Tok(), 0, W, 1, False,
+                                     ctc_tokens_to_score=K)
+    mine = cp.JointCtcRescorer(enc_logits.clone(), blank=BLANK, eos=EOS, bos=SOT, prefix_len=3, first_timestamp=TS0,
+                               ctc_weight=W, top_k=K, upper_cased=upper or None)
+    ids = torch.tensor([[SOT, SOT + 1, SOT + 2]] * B)
+    unfinished = torch.ones(B, dtype=torch.long)
+    for step in range(steps):
+        s = torch.from_numpy(rng.normal(size=(B, V)).astype(np.float32)) * 2.0
+        s[:, SOT:TS0] = -float("inf")
+        if step == 0:
+            s[:, :EOS] = -float("inf")
+        if rng.random() < 0.3:
+            s[int(rng.integers(0, B)), TS0:] += 6.0       # a timestamp wins somewhere
+        s = torch.log_softmax(s, dim=-1)
+        want = ref(ids, s.clone())
+        got = mine(ids, s.clone())
+        live = want > -1e8
+        assert torch.equal(live, got > -1e8), f"step {step}: candidate sets differ"
+        np.testing.assert_allclose(got[live].numpy(), want[live].numpy(), rtol=2e-4, atol=2e-4)
+        tok = torch.argmax(want, dim=-1)
+        assert torch.equal(tok, torch.argmax(got, dim=-1)) or float((want.max(-1).values - want.gather(1, torch.argmax(got, -1)[:, None])[:, 0]).abs().max()) < 1e-3
+        tok = tok * unfinished + EOS * (1 - unfinished)
+        ref.update_state(tok, torch.arange(B))
+        mine.update_state(tok)
+        ids = torch.cat([ids, tok[:, None]], dim=1)
+        unfinished = unfinished & (tok != EOS).long()
+        if int(unfinished.max()) == 0:
+            break
