@@ -200,3 +200,24 @@ def test_oracle_forward_loss_and_gradients_equal_reference_model(vi):
         assert checked > 40
     finally:
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd  # undo the shim for whatever runs next in this process
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_stno_oracle_equals_reference_create_stno_masks_on_random_cases(case):
+    """dicow_oracle.stno_mask against the reference's own _create_stno_masks (src/data/local_datasets.py:186-196, cut out of
+    the file with ast because the module imports lhotse) behind the down-sampling of get_stno_mask (:167-180), bit-exact"""
+    import make_golden_stno as MS
+    from oracle import dicow_oracle as orc
+    create = MS.reference_create_stno_masks()
+    rng = np.random.default_rng(700 + case)
+    n_spk = int(rng.integers(1, 6))
+    n = int(rng.integers(16000, 16000 * 70))
+    target = int(rng.integers(-1, n_spk))
+    act = MS.activity(rng, n_spk, n)
+    spk = np.pad(act, ((0, 0), (0, (480000 - n) % 480000)), mode="constant")
+    spk = spk.astype(np.float32).reshape(n_spk, -1, 320).mean(axis=-1)
+    if target == -1:
+        spk = np.pad(spk, ((0, 1), (0, 0)), mode="constant")
+    want = create(spk, target).astype(np.float32)
+    got = orc.stno_mask(act, target)
+    assert got.shape == want.shape and np.array_equal(got, want)
