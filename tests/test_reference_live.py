@@ -221,3 +221,44 @@ def test_stno_oracle_equals_reference_create_stno_masks_on_random_cases(case):
     want = create(spk, target).astype(np.float32)
     got = orc.stno_mask(act, target)
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_timestamp_rules_oracle_equals_reference_processors_on_random_sequences(case):
+    """dicow_oracle.timestamp_rules against SuppressTokensLogitsProcessor + the reference's
+    WhisperTimeStampLogitsProcessorCustom (src/models/dicow/utils.py:5-14 over HF:generation/logits_process.py:1905-2043)
+    on random prefixes that end in text, one timestamp or a timestamp pair, incl. the first generated position"""
+    import types
+    import make_golden as MG
+    from oracle import dicow_oracle as orc
+    rng = np.random.default_rng(900 + case)
+    V, EOS, NOTS, TS0 = 300, MG.EOS, MG.NOTS, MG.TS_BEGIN
+    max_init = None if case % 2 else int(rng.integers(1, 20))
+    gcfg = types.SimpleNamespace(no_timestamps_token_id=NOTS, eos_token_id=EOS, bos_token_id=EOS,
+                                 max_initial_timestamp_index=max_init, _detect_timestamp_from_logprob=True)
+    procs = [MG.SuppressTokensLogitsProcessor(MG.SUPPRESS), MG.WhisperTimeStampLogitsProcessorCustom(gcfg, begin_index=3)]
+    for length in (0, 1, 2, 3, 5, 9):
+        B = 4
+        body = np.empty((B, length), dtype=np.int64)
+        for b in range(B):
+            t = TS0
+            for i in range(length):
+                if rng.random() < 0.45:
+                    t = min(t + int(rng.integers(0, 4)), V - 1)
+                    body[b, i] = t
+                else:
+                    body[b, i] = int(rng.integers(0, 250))
+        ids = torch.cat([torch.tensor([[MG.SOT, MG.LANG, MG.TASK]] * B), torch.from_numpy(body)], dim=1)
+        scores = torch.from_numpy(rng.normal(size=(B, V)).astype(np.float32)) * 3.0
+        if rng.random() < 0.5:
+            scores[:, TS0:] += 4.0  # makes the "timestamp mass beats the best text token" rule fire
+        want = scores.clone()
+        for pr in procs:
+            want = pr(ids, want)
+        raw = scores.clone()
+        raw[:, MG.SUPPRESS] = -float("inf")
+        got = orc.timestamp_rules(ids, raw, begin_index=3, eos=EOS, no_timestamps=NOTS, ts_begin=TS0,
+                                  max_initial_timestamp_index=max_init)
+        assert torch.equal(torch.isinf(got), torch.isinf(want)), f"length {length}"
+        fin = ~torch.isinf(want)
+        assert torch.equal(got[fin], want[fin])
