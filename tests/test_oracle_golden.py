@@ -104,6 +104,25 @@ def test_log_mel(n_mels):
     assert np.array_equal(mask, g[f"mask{n_mels}"])
 
 
+@pytest.mark.parametrize("case", range(4))
+def test_log_mel_equals_installed_whisper_extractor_on_random_lengths(case):
+    """the log-mel oracle against the installed HF WhisperFeatureExtractor called exactly as the reference does
+    (src/data/local_datasets.py:208-214), 30 s windows: sub-window, exact, and multi-window recordings (shared floor)"""
+    from transformers import WhisperFeatureExtractor
+    rng = np.random.default_rng(60 + case)
+    n_mels = 80 if case % 2 else 128
+    n = int([rng.integers(4000, 400000), 480000, rng.integers(480001, 900000), rng.integers(960001, 1100000)][case])
+    wav = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    wav[: n // 3] *= 0.01  # a quiet stretch: exercises the (max - 8) floor
+    fe = WhisperFeatureExtractor(feature_size=n_mels)
+    f = fe(wav, return_tensors="pt", sampling_rate=16000, return_attention_mask=True, truncation=False, padding="longest",
+           pad_to_multiple_of=fe.n_samples)
+    feat, mask = orc.log_mel(wav, n_mels)
+    assert feat.shape == tuple(f.input_features[0].shape)
+    _close(feat, f.input_features[0].numpy(), 5e-5)
+    assert np.array_equal(mask, f.attention_mask[0].numpy())
+
+
 # ---- joint CTC / attention decoding (SURVEY.md section 8(f).1): oracle/ctc_prefix.py vs the reference's own classes --------
 def _ctc_golden():
     return np.load(os.path.join(GOLD, "ctc_joint.npz"))
