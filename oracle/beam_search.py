@@ -26,7 +26,7 @@ Ties: torch.topk leaves the order of equal scores unspecified; this restatement 
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Sequence, Tuple
 
 import torch
 
@@ -131,4 +131,3 @@ def beam_decode(step_scores: Callable[[torch.Tensor], torch.Tensor], prompt: Seq
 
 
 __all__ = ["BeamSearch", "beam_decode", "NEG"]
-_ = Optional

@@ -26,7 +26,6 @@ Reference behaviours kept on purpose (they change numbers):
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -181,4 +180,3 @@ def greedy_joint_decode(rescorer: JointCtcRescorer, att_scores_fn, prompt: torch
 
 
 __all__ = ["LOGZERO", "initial_state", "prefix_scores", "JointCtcRescorer", "greedy_joint_decode"]
-_ = math

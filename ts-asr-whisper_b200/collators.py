@@ -224,4 +224,3 @@ class DataCollator:
 
 
 __all__ = ["AugmentPlan", "DataCollator"]
-_ = Optional

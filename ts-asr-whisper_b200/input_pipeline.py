@@ -11,10 +11,7 @@ no CPU fallback.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence
-
-import numpy as np
-import torch
+from typing import Any, Dict, Optional, Sequence
 
 from .collators import DataCollator
 from .feature_extraction import DiCoWFeatureExtractor
@@ -52,4 +49,3 @@ class DeviceInputPipeline:
 
 
 __all__ = ["DeviceInputPipeline"]
-_ = (List, np, torch)
