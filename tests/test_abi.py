@@ -41,7 +41,11 @@ def test_exports_match_header(lib):
                                           ("dicow_decode_attention_args_t", "DecodeAttentionArgs"),
                                           ("dicow_logits_rules_args_t", "LogitsRulesArgs"),
                                           ("dicow_softlabel_ce_args_t", "SoftlabelCeArgs"),
-                                          ("dicow_ctc_loss_args_t", "CtcLossArgs")])
+                                          ("dicow_ctc_loss_args_t", "CtcLossArgs"),
+                                          ("dicow_decode_linear_args_t", "DecodeLinearArgs"),
+                                          ("dicow_ctc_joint_args_t", "CtcJointArgs"),
+                                          ("dicow_beam_step_args_t", "BeamStepArgs"),
+                                          ("dicow_augment_args_t", "AugmentArgs")])
 def test_struct_mirrors(lib, cname, pyname):
     m = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", _header_text(), flags=re.S)
     assert m, cname
@@ -56,6 +60,34 @@ def test_struct_mirrors(lib, cname, pyname):
         fields += [n.strip().lstrip("*") for n in names[1:]]
     py = [f[0] for f in getattr(lib, pyname)._fields_]
     assert py == fields, f"{cname}: header {fields} vs ctypes {py}"
+
+
+def test_every_header_struct_has_a_mirror_of_the_same_size(lib, tmp_path):
+    """sizeof() of every args struct as gcc lays it out from include/dicow_b200.h == ctypes.sizeof of its mirror: catches a
+    field type / padding drift that the name comparison above cannot see (the library checks struct_size at run time, but
+    only on a GPU box)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    names = re.findall(r"\}\s*(dicow_\w+_args_t)\s*;", _header_text())
+    assert len(names) >= 17
+    mirrors = {}
+    for attr in dir(lib):
+        obj = getattr(lib, attr)
+        if isinstance(obj, type) and issubclass(obj, C.Structure) and obj is not C.Structure:
+            key = "dicow_" + re.sub(r"(?<!^)(?=[A-Z])", "_", attr[:-4]).lower() + "_args_t"  # GemmSkinnyArgs -> dicow_gemm_skinny_args_t
+            mirrors[key] = obj
+    assert sorted(mirrors) == sorted(names), (sorted(set(names) ^ set(mirrors)))
+    src = tmp_path / "sizes.c"
+    body = "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names)
+    src.write_text(f'#include <stdio.h>\n#include "{HEADER}"\nint main(void) {{\n{body}  return 0;\n}}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        n, size = line.split()
+        assert C.sizeof(mirrors[n]) == int(size), f"{n}: header {size} bytes, ctypes {C.sizeof(mirrors[n])}"
 
 
 def test_no_device_fails_loudly(lib):
