@@ -90,6 +90,40 @@ def test_every_header_struct_has_a_mirror_of_the_same_size(lib, tmp_path):
         assert C.sizeof(mirrors[n]) == int(size), f"{n}: header {size} bytes, ctypes {C.sizeof(mirrors[n])}"
 
 
+def test_plain_c_client_links_and_fails_loudly_without_a_device(lib, tmp_path):
+    """the boundary is a C ABI: a C99 program that only sees include/dicow_b200.h links against libdicow_b200.so, reads the
+    ABI version, and -- in this container, without a GPU -- gets a non-zero status from dicow_create instead of a handle"""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from ts_asr_whisper_b200 import build
+    so = build.build()
+    src = tmp_path / "client.c"
+    src.write_text(f"""#include <stdio.h>
+#include "{HEADER}"
+int main(void) {{
+  dicow_handle_t h = 0;
+  int rc = dicow_create(0, &h);
+  printf("abi %d create %d handle %d\\n", dicow_abi_version(), rc, h != 0);
+  if (rc == 0) dicow_destroy(h);
+  return 0;
+}}
+""")
+    exe = tmp_path / "client"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src), so, f"-Wl,-rpath,{os.path.dirname(so)}"], check=True)
+    env = dict(os.environ)
+    cuda_lib = "/usr/local/cuda/lib64"
+    env["LD_LIBRARY_PATH"] = cuda_lib + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env).stdout.split()
+    assert out[0] == "abi" and int(out[1]) >= 1
+    if torch.cuda.is_available():
+        assert int(out[3]) == 0 and int(out[5]) == 1
+    else:
+        assert int(out[3]) != 0 and int(out[5]) == 0
+
+
 def test_no_device_fails_loudly(lib):
     """without an sm_100 GPU the handle cannot be created and ops raise -- there is no CPU fallback"""
     import torch
