@@ -262,3 +262,64 @@ def test_timestamp_rules_oracle_equals_reference_processors_on_random_sequences(
         assert torch.equal(torch.isinf(got), torch.isinf(want)), f"length {length}"
         fin = ~torch.isinf(want)
         assert torch.equal(got[fin], want[fin])
+
+
+class _LiveTok:
+    """tokenizer stand-in with the members both collators use (src/data/collators.py:151-186)"""
+    prefix_tokens = [50258, 50259, 50360]
+    upper_cased_tokens = {7: 70, 9: 90, 3: 33}
+
+    def __call__(self, texts, padding=None, max_length=None, return_tensors=None):
+        n = max(len(t) for t in texts)
+        ids = torch.zeros(len(texts), n + 1, dtype=torch.long)
+        att = torch.zeros_like(ids)
+        for i, t in enumerate(texts):
+            ids[i, 0] = 50258
+            ids[i, 1:1 + len(t)] = torch.tensor([int(c) for c in t], dtype=torch.long)
+            att[i, :1 + len(t)] = 1
+
+        class E(dict):
+            attention_mask = att
+        return E(input_ids=ids)
+
+    def convert_tokens_to_ids(self, toks):
+        return [50259 + len(t) for t in toks]
+
+
+@pytest.mark.parametrize("long_form,language,enroll", [(False, None, False), (False, "en", False), (True, "cs", False),
+                                                       (True, None, False), (False, None, True)])
+def test_collator_host_outputs_equal_reference_collator(long_form, language, enroll):
+    """labels / upp_labels / forced_decoder_ids / attention_mask / padded features and STNO masks of
+    ts_asr_whisper_b200.collators.DataCollator (device="cpu", augmentations off) against the reference DataCollator"""
+    import make_golden_augment as G
+    from ts_asr_whisper_b200.collators import DataCollator
+    RefCollator = _reference_collator()
+    rng = np.random.default_rng(77)
+    frames = (60, 44, 52)
+    samples = G.make_inputs(5, 80, frames)
+
+    def sample(i, f, s):
+        d = {"is_long_form": long_form, "transcript": "".join(str(int(c)) for c in rng.integers(1, 10, size=3 + i)),
+             "input_features": torch.from_numpy(f), "attention_mask": torch.ones(f.shape[1], dtype=torch.long),
+             "stno_mask": torch.from_numpy(s), "language": language}
+        return d
+    ins = [sample(i, f, s) for i, (f, s) in enumerate(samples)]
+    if enroll:
+        for d, (f, s) in zip(ins, G.make_inputs(6, 80, (40, 40, 36))):
+            d["enrollment"] = {"is_long_form": long_form, "transcript": "1", "input_features": torch.from_numpy(f),
+                               "attention_mask": torch.ones(f.shape[1], dtype=torch.long), "stno_mask": torch.from_numpy(s),
+                               "language": language}
+    off = dict(stno_segment_augment_prob=0.0, spec_aug_prob=0.0, use_enrollments=enroll)
+    torch.manual_seed(1)
+    want = RefCollator(feature_extractor=None, tokenizer=_LiveTok(), bos_token_id=50258, max_length=32, **off)(ins)
+    torch.manual_seed(1)
+    got = DataCollator(feature_extractor=None, tokenizer=_LiveTok(), bos_token_id=50258, max_length=32, device="cpu", **off)(ins)
+
+    def same(a, b, path=""):
+        assert sorted(a.keys()) == sorted(b.keys()), (path, sorted(a.keys()), sorted(b.keys()))
+        for k in a.keys():
+            if hasattr(a[k], "keys"):
+                same(a[k], b[k], path + k + ".")
+            else:
+                assert a[k].shape == b[k].shape and torch.equal(a[k].to(b[k].dtype), b[k]), path + k
+    same(want, got)
