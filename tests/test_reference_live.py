@@ -323,3 +323,51 @@ def test_collator_host_outputs_equal_reference_collator(long_form, language, enr
             else:
                 assert a[k].shape == b[k].shape and torch.equal(a[k].to(b[k].dtype), b[k]), path + k
     same(want, got)
+
+
+def test_config_fields_and_defaults_equal_reference_config():
+    """A3: DiCoWConfig (src/models/dicow/config.py:6-59) -- every field the reference adds to WhisperConfig, its default,
+    model_type, and the serialised dictionary for a non-default instance"""
+    from ts_asr_whisper_b200.configuration import DiCoWConfig as Mine
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.config import DiCoWConfig as Ref
+    finally:
+        sys.path.remove(REF)
+    assert Mine.model_type == Ref.model_type
+    a, b = Ref().to_dict(), Mine().to_dict()
+    skip = {"transformers_version", "architectures", "auto_map", "_name_or_path"}
+    extra = {k for k in a if k not in b} | {k for k in b if k not in a}
+    assert not (extra - skip), f"fields only on one side: {sorted(extra - skip)}"
+    for k in a:
+        if k not in skip:
+            assert a[k] == b[k], f"default of {k}: reference {a[k]!r}, here {b[k]!r}"
+    kw = dict(ctc_weight=0.3, use_fddt=True, fddt_is_diagonal=False, fddt_bias_only=False, use_enrollments=True, scb_layers=4,
+              additional_layer=True, apply_fddt_to_n_layers=2, non_target_fddt_value=0.5, fddt_init="suppressive",
+              d_model=64, encoder_layers=3, vocab_size=300)
+    a, b = Ref(**kw).to_dict(), Mine(**kw).to_dict()
+    for k in a:
+        if k not in skip:
+            assert a[k] == b[k], k
+
+
+@pytest.mark.parametrize("vi", range(len(_VARIANTS)))
+def test_state_dict_names_and_shapes_equal_reference_model(vi):
+    """the parameter naming / shape contract of SURVEY 8b (name-keyword freezing, checkpoint loading, prefixes_to_preheat):
+    state_dict of the B200 model == state_dict of the reference model, for every variant"""
+    import dataclasses
+    import make_golden as MG
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    base = dict(use_enrollments=False, scb_layers=0, ffn=160, dec_ffn=96, enc_layers=3, T=24)  # d = 128: head_dim 64
+    dm = dataclasses.replace(synth.GOLDEN_MINI, **{**base, **_VARIANTS[vi]})
+    ref = MG.build_reference(dm)
+    mine = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert sorted(a) == sorted(b), sorted(set(a) ^ set(b))
+    assert a == b
+    ra = {n for n, q in ref.named_parameters() if q.requires_grad}
+    rb = {n for n, q in mine.named_parameters() if q.requires_grad}
+    assert ra == rb, sorted(ra ^ rb)  # e.g. the frozen sinusoidal encoder positions
