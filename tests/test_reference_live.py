@@ -371,3 +371,26 @@ def test_state_dict_names_and_shapes_equal_reference_model(vi):
     ra = {n for n, q in ref.named_parameters() if q.requires_grad}
     rb = {n for n, q in mine.named_parameters() if q.requires_grad}
     assert ra == rb, sorted(ra ^ rb)  # e.g. the frozen sinusoidal encoder positions
+
+
+@pytest.mark.parametrize("fddt_init", ["suppressive", "non-disturbing"])
+@pytest.mark.parametrize("vi", [0, 1, 2, 4])
+def test_deterministic_initialisations_equal_reference_model(vi, fddt_init):
+    """freshly constructed models: the FDDT tables (FDDT.py:10-40 with layers.py reset_parameters, `non_target_fddt_value`
+    for the initial FDDT, 1.0 inside the layers: encoder.py:46-76) and the speaker communication gates are deterministic
+    -- they must equal the reference's tensor for tensor"""
+    import dataclasses
+    import make_golden as MG
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    base = dict(use_enrollments=False, scb_layers=0, ffn=160, dec_ffn=96, enc_layers=3, T=24, non_target_fddt_value=0.5)
+    dm = dataclasses.replace(synth.GOLDEN_MINI, **{**base, **_VARIANTS[vi]})
+    kw = dict(dm.hf_kwargs(), fddt_init=fddt_init)
+    ref = MG.DiCoWForConditionalGeneration(MG.DiCoWConfig(**kw))
+    mine = DiCoWForConditionalGeneration(DiCoWConfig(**kw))
+    a, b = dict(ref.named_parameters()), dict(mine.named_parameters())
+    names = [n for n in a if "fddt" in n or n.endswith("cross_gate.gate")]
+    assert len(names) >= 16
+    for n in names:
+        assert torch.equal(a[n].detach(), b[n].detach()), n
