@@ -394,3 +394,23 @@ def test_deterministic_initialisations_equal_reference_model(vi, fddt_init):
     assert len(names) >= 16
     for n in names:
         assert torch.equal(a[n].detach(), b[n].detach()), n
+
+
+def test_pretraining_collator_equals_reference():
+    """DataCollatorForPretraining (src/data/collators.py:225-243): the dataset hands over [1, M, frames] features and
+    [1, frames] masks (feature extractor output with its batch axis), padded to the longest sample"""
+    import make_golden_augment as G
+    from ts_asr_whisper_b200.collators import DataCollatorForPretraining as Mine
+    _reference_collator()
+    sys.path.insert(0, REF)
+    try:
+        from data.collators import DataCollatorForPretraining as Ref
+    finally:
+        sys.path.remove(REF)
+    ins = [{"transcript": "79" + "3" * i, "input_features": torch.from_numpy(f)[None],
+            "attention_mask": torch.ones(1, f.shape[1], dtype=torch.long)} for i, (f, _) in enumerate(G.make_inputs(8, 80, (60, 44, 52)))]
+    kw = dict(feature_extractor=None, tokenizer=_LiveTok(), bos_token_id=50258, max_length=32)
+    want, got = Ref(**kw)(ins), Mine(device="cpu", **kw)(ins)
+    assert sorted(want.keys()) == sorted(got.keys())
+    for k in want.keys():
+        assert want[k].shape == got[k].shape and torch.equal(want[k].to(got[k].dtype), got[k]), k

@@ -223,4 +223,33 @@ class DataCollator:
         return batch
 
 
-__all__ = ["AugmentPlan", "DataCollator"]
+@dataclasses.dataclass
+class DataCollatorForPretraining(DataCollator):
+    """src/data/collators.py:225-243 (CTC pre-training of the encoder, src/pretrain_encoder.py): features and attention masks
+    padded to the longest sample, labels with -100 padding and the leading bos stripped; no STNO mask, no augmentation."""
+    use_timestamps: bool = False
+
+    def __call__(self, inputs: List[Dict[str, Union[List[int], torch.Tensor]]]) -> BatchFeature:  # type: ignore[override]
+        dev = torch.device(self.device)
+        labels = self.tokenizer([sample["transcript"] for sample in inputs], padding="longest", max_length=self.max_length,
+                                return_tensors="pt")
+        feats = [s["input_features"].squeeze() for s in inputs]          # [M, frames]
+        masks = [s["attention_mask"].reshape(-1) for s in inputs]
+        B, M = len(inputs), feats[0].shape[0]
+        Tf, Ta = max(f.shape[-1] for f in feats), max(m.shape[0] for m in masks)
+        stage = torch.zeros(B * M * Tf + B * Ta, dtype=torch.float32, pin_memory=dev.type == "cuda")
+        fv, mv = stage[:B * M * Tf].view(B, M, Tf), stage[B * M * Tf:].view(B, Ta)
+        for b, (f, m) in enumerate(zip(feats, masks)):
+            fv[b, :, :f.shape[-1]] = f
+            mv[b, :m.shape[0]] = m
+        on = stage.to(dev, non_blocking=True)
+        batch = BatchFeature({"input_features": on[:B * M * Tf].view(B, M, Tf),
+                              "attention_mask": on[B * M * Tf:].view(B, Ta).to(masks[0].dtype)})
+        ids = labels["input_ids"].masked_fill(labels.attention_mask.ne(1), -100)
+        if (ids[:, 0] == self.bos_token_id).all().item():
+            ids = ids[:, 1:]
+        batch["labels"] = ids
+        return batch
+
+
+__all__ = ["AugmentPlan", "DataCollator", "DataCollatorForPretraining"]
