@@ -70,3 +70,25 @@ def test_shift_tokens_right():
     from ts_asr_whisper_b200.modeling_dicow import shift_tokens_right
     lab = torch.tensor([[5, 6, -100, -100], [7, 8, 9, 10]])
     assert shift_tokens_right(lab, 1, 2).tolist() == [[2, 5, 6, 1], [2, 7, 8, 9]]
+
+
+def test_unsupported_logits_processors_are_refused_not_ignored():
+    """update_generation_config (src/utils/general.py:19-37) sets begin_suppress_tokens=None and leaves repetition_penalty
+    at None; a generation config that asks for either must not be decoded without it"""
+    import dataclasses
+    import pytest
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    model.generation_config.no_timestamps_token_id = 261
+    gs = model._generation_settings(None, {"max_new_tokens": 5, "length_penalty": 0.1, "ctc_weight": 0.2, "num_beams": 5})
+    assert gs["num_beams"] == 5 and gs["ctc_weight"] == 0.2 and gs["length_penalty"] == 0.1 and gs["ts_begin"] == 262
+    for bad in ({"begin_suppress_tokens": [220, 257]}, {"repetition_penalty": 1.2}, {"no_repeat_ngram_size": 3},
+                {"num_return_sequences": 2}, {"num_beams": 9}):
+        with pytest.raises(NotImplementedError):
+            model._generation_settings(None, dict(bad))
+    with pytest.raises(ValueError):
+        model._generation_settings(None, {"do_sample": True})
+    assert model._generation_settings(None, {"repetition_penalty": 1.0, "begin_suppress_tokens": []})["num_beams"] == 1

@@ -800,6 +800,14 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         if int(get("num_return_sequences", 1) or 1) != 1:
             raise NotImplementedError("num_return_sequences > 1")
         ctc_weight = float(get("ctc_weight", 0) or 0)
+        # logits processors the reference switches off (update_generation_config, src/utils/general.py:19-37:
+        # begin_suppress_tokens=None, repetition_penalty from the decoding args, default None) are not built: refuse
+        # instead of silently decoding without them
+        if get("begin_suppress_tokens"):
+            raise NotImplementedError("begin_suppress_tokens is not applied by the B200 decode step; the reference sets it "
+                                      "to None (src/utils/general.py:26) -- do the same on this generation config")
+        if get("repetition_penalty") not in (None, 1.0) or get("no_repeat_ngram_size") not in (None, 0):
+            raise NotImplementedError("repetition_penalty / no_repeat_ngram_size are not applied by the B200 decode step")
         if get("do_sample", False):
             raise ValueError("Provided generation mode is not supported (greedy only)")
         ts_begin = get("no_timestamps_token_id")
