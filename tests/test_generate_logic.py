@@ -89,6 +89,11 @@ def test_unsupported_logits_processors_are_refused_not_ignored():
                 {"num_return_sequences": 2}, {"num_beams": 9}):
         with pytest.raises(NotImplementedError):
             model._generation_settings(None, dict(bad))
+    for bad in ({"temperature": (0.0, 0.2, 0.4)}, {"no_speech_threshold": 0.6}, {"logprob_threshold": -1.0},
+                {"compression_ratio_threshold": 1.35}, {"prompt_ids": [1, 2]}, {"return_token_timestamps": True}):
+        with pytest.raises(NotImplementedError):
+            model._generation_settings(None, dict(bad))
+    assert model._generation_settings(None, {"temperature": 0.0})["num_beams"] == 1
     with pytest.raises(ValueError):
         model._generation_settings(None, {"do_sample": True})
     assert model._generation_settings(None, {"repetition_penalty": 1.0, "begin_suppress_tokens": []})["num_beams"] == 1

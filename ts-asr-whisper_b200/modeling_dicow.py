@@ -808,6 +808,16 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                                       "to None (src/utils/general.py:26) -- do the same on this generation config")
         if get("repetition_penalty") not in (None, 1.0) or get("no_repeat_ngram_size") not in (None, 0):
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size are not applied by the B200 decode step")
+        # explicit requests for HF long-form features the reference's recipes never use (temperature fallback with its
+        # thresholds, prompts, token-level timestamps): refuse rather than return something else than what was asked for
+        temp = kwargs.get("temperature")
+        if isinstance(temp, (list, tuple)) and len(temp) > 1:
+            raise NotImplementedError("temperature fallback (a tuple of temperatures) is not built")
+        for name in ("no_speech_threshold", "logprob_threshold", "compression_ratio_threshold", "prompt_ids"):
+            if kwargs.get(name) is not None:
+                raise NotImplementedError(f"{name} is not supported by the B200 generate()")
+        if kwargs.get("return_token_timestamps"):
+            raise NotImplementedError("return_token_timestamps needs cross-attention weights, which the fused path does not produce")
         if get("do_sample", False):
             raise ValueError("Provided generation mode is not supported (greedy only)")
         ts_begin = get("no_timestamps_token_id")
