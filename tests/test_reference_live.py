@@ -414,3 +414,31 @@ def test_pretraining_collator_equals_reference():
     assert sorted(want.keys()) == sorted(got.keys())
     for k in want.keys():
         assert want[k].shape == got[k].shape and torch.equal(want[k].to(got[k].dtype), got[k]), k
+
+
+def test_forward_and_generate_signatures_cover_the_reference_names():
+    """parameter NAMES of forward() are part of the contract (HF generate() routes kwargs by
+    inspect.signature(encoder.forward); the trainer leaves upp_labels / forced_decoder_ids in the batch)"""
+    import inspect
+    import make_golden as MG
+    from ts_asr_whisper_b200.modeling import DiCoWEncoder
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.encoder import DiCoWEncoder as RefEncoder
+    finally:
+        sys.path.remove(REF)
+
+    def names(fn):
+        return [n for n, p in inspect.signature(fn).parameters.items() if n != "self" and p.kind != p.VAR_KEYWORD]
+    for ref_fn, my_fn in ((MG.DiCoWForConditionalGeneration.forward, DiCoWForConditionalGeneration.forward),
+                          (RefEncoder.forward, DiCoWEncoder.forward)):
+        ref_names, my_names = names(ref_fn), names(my_fn)
+        missing = [n for n in ref_names if n not in my_names]
+        assert not missing, f"{my_fn.__qualname__} lacks reference parameters {missing}"
+        shared = [n for n in my_names if n in ref_names]
+        assert shared == [n for n in ref_names if n in shared], "reference parameters in a different order (positional calls)"
+    gen = names(DiCoWForConditionalGeneration.generate)
+    for n in ("generation_config", "condition_on_prev_tokens", "assistant_model"):  # src/models/dicow/generation.py:536-541
+        assert n in gen
+    assert any(p.kind == p.VAR_KEYWORD for p in inspect.signature(DiCoWForConditionalGeneration.generate).parameters.values())
