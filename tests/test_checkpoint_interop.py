@@ -126,3 +126,29 @@ def test_whisper_container_and_optimizer(saved):
     opt = get_optimizer(c.model, targs, ["model.encoder.fddts", "model.encoder.ca_enrolls"])
     assert len(opt.param_groups) == 2 and abs(opt.param_groups[1]["lr"] - 2e-4) < 1e-12 and opt.param_groups[1]["weight_decay"] == 0.0
     assert get_optimizer(c.model, types.SimpleNamespace(use_custom_optimizer=False)) is None
+
+
+def test_python_surface_of_survey_8b_exists():
+    """the members src/train.py, src/pretrain_encoder.py, src/utils/trainers.py and utils/export_dicow.py touch"""
+    import dataclasses
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    for name in ("from_pretrained", "post_init", "set_tokenizer", "get_encoder", "get_enc_logits", "generate", "forward",
+                 "named_parameters", "state_dict", "load_state_dict", "register_for_auto_class", "save_pretrained"):
+        assert callable(getattr(model, name)), name
+    assert model.main_input_name == "input_features" and model.get_encoder().main_input_name == "input_features"
+    model.config.forced_decoder_ids = None  # src/models/containers.py:68 (not a config field any more in transformers 5.x)
+    for name in ("forced_decoder_ids", "decoder_start_token_id", "pad_token_id", "eos_token_id", "vocab_size"):
+        assert hasattr(model.config, name), name
+    unused = model.generation_config.update(max_new_tokens=7, num_beams=1, ctc_weight=0.2, length_penalty=0.1,
+                                            return_timestamps=True, begin_suppress_tokens=None, forced_decoder_ids=None)
+    assert model.generation_config.max_new_tokens == 7 and isinstance(unused, dict)
+    enc = model.get_encoder()
+    for name in ("forward", "get_loss", "get_max_len", "possibly_update_last_hidden_states"):
+        assert callable(getattr(enc, name)), name
+    assert enc.get_max_len() == 2 * dm.T
+    DiCoWConfig.register_for_auto_class()
+    DiCoWForConditionalGeneration.register_for_auto_class("AutoModelForSpeechSeq2Seq")  # utils/export_dicow.py:22-23
