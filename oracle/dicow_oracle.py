@@ -277,6 +277,17 @@ def ctc_logits(p: Params, dm: Dims, h: torch.Tensor) -> torch.Tensor:
     return F.linear(h, p[e + ".lm_head.weight"])
 
 
+def ctc_label_filter(labels: torch.Tensor, dm: Dims) -> torch.Tensor:
+    """encoder.py:76,111-113: with ``remove_timestamps_from_ctc`` the CTC targets keep only ids below
+    vocab - 30 * 50 - 1 - 6 (the first task token; padding -100 stays), re-padded with -100 to the longest row"""
+    if not dm.remove_timestamps_from_ctc:
+        return labels
+    first_task_token = dm.vocab - 30 * 50 - 1 - 6
+    rows = [[int(v) for v in row if int(v) < first_task_token] for row in labels]
+    n = max(len(r) for r in rows)
+    return torch.tensor([r + [-100] * (n - len(r)) for r in rows], dtype=labels.dtype, device=labels.device).reshape(len(rows), n)
+
+
 def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
     """src/models/dicow/encoder.py:108-135: fp32 log-softmax, blank = last class, input length = all frames,
     targets = labels >= 0, zero_infinity=True."""
@@ -376,7 +387,7 @@ def model_forward(p: Params, dm: Dims, input_features, stno_mask, labels, upp_la
             if bool((enc_labels[:, 0] == tok).all()):
                 enc_labels = enc_labels[:, 1:]
         enc_labels[enc_labels == dm.eos_token_id] = -100
-        loss = (1 - dm.ctc_weight) * dec_loss + dm.ctc_weight * ctc_loss(enc_logits, enc_labels)
+        loss = (1 - dm.ctc_weight) * dec_loss + dm.ctc_weight * ctc_loss(enc_logits, ctc_label_filter(enc_labels, dm))
     else:
         loss = dec_loss
     return loss, logits, enc

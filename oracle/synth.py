@@ -90,6 +90,7 @@ class Dims:
     fddt_is_diagonal: bool = True    # False: full d x d CustomLinear per class (src/models/dicow/layers.py:7-47)
     fddt_bias_only: bool = False     # True: one bias vector per class (src/models/dicow/FDDT.py:43-51)
     additional_layer: bool = False   # a whole encoder layer in front of the CTC head (encoder.py:17-18, 88-89)
+    remove_timestamps_from_ctc: bool = False  # CTC targets without timestamp / task tokens (encoder.py:76, 111-113)
     pad_token_id: int = 50257
     eos_token_id: int = 50257
     decoder_start_token_id: int = 50258
@@ -106,6 +107,7 @@ class Dims:
             encoder_ffn_dim=self.ffn, decoder_ffn_dim=self.dec_ffn, max_source_positions=self.T,
             max_target_positions=self.max_target, use_fddt=self.use_fddt, use_pre_pos_fddt=self.use_pre_pos_fddt,
             fddt_is_diagonal=self.fddt_is_diagonal, fddt_bias_only=self.fddt_bias_only, additional_layer=self.additional_layer,
+            remove_timestamps_from_ctc=self.remove_timestamps_from_ctc,
             non_target_fddt_value=self.non_target_fddt_value, fddt_init="suppressive",
             ctc_weight=self.ctc_weight, additional_self_attention_layer=self.additional_self_attention_layer,
             pre_ctc_sub_sample=self.pre_ctc_sub_sample, use_enrollments=self.use_enrollments,

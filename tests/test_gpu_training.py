@@ -187,6 +187,12 @@ def test_finetune_step_full_matrix_fddt(dm, B, S, tag, mode):
     _finetune_case(dm, B, S, mode, tag)
 
 
+def test_finetune_step_remove_timestamps_from_ctc():
+    """remove_timestamps_from_ctc=True (encoder.py:76, 111-113): the CTC branch is trained on the labels below the first task
+    token only (vocab 1700 -> ids < 193); loss and gradients vs the oracle, whose filter is pinned to the reference live"""
+    _finetune_case(dataclasses.replace(MINI, remove_timestamps_from_ctc=True, vocab=1700), 2, 11, "decoder-frozen", "tr1")
+
+
 @pytest.mark.parametrize("dm,B,S", [(MINI_LAYER, 2, 11), (TINY_LAYER, 3, 24)], ids=["mini", "tiny-short"])
 def test_finetune_step_additional_layer(dm, B, S):
     """the CTC branch's gradient reaches the encoder body through the whole extra layer (accumulated into the decoder's)"""
