@@ -138,6 +138,8 @@ _VARIANTS = [
     dict(use_enrollments=True, scb_layers=2),
     dict(use_enrollments=True, scb_layers=1, fddt_is_diagonal=False),
     dict(remove_timestamps_from_ctc=True, vocab=1700),           # CTC targets without timestamp / task tokens
+    dict(apply_fddt_to_n_layers=1),                              # FDDT in the first layer only
+    dict(use_pre_pos_fddt=False),                                # no FDDT in front of the positional embedding
 ]
 
 
