@@ -123,3 +123,25 @@ def test_variants_match_reference_golden_and_oracle(name, over):
         ref_l = orc.ctc_logits(p2, dm2, ref)
         o2 = enc2(f2.to(dev), stno_mask=s2.to(dev), return_logits=True)
     assert rel_err(o2.hidden_states, ref) < BF16_TOL and rel_err(o2.logits, ref_l) < BF16_TOL
+
+
+@pytest.mark.parametrize("name,over", [("fddt_first_layer_only", {"apply_fddt_to_n_layers": 1}),
+                                       ("no_pre_pos_fddt", {"use_pre_pos_fddt": False})])
+def test_fddt_placement_variants_match_oracle(name, over):
+    """apply_fddt_to_n_layers (encoder.py:45-47, 205) and use_pre_pos_fddt=False (encoder.py:62, 173-176): which layers carry
+    an FDDT -- against the oracle, whose forward and gradients for these variants are pinned to the reference model live
+    (tests/test_reference_live.py)"""
+    base = {**synth.GOLDEN_MINI.__dict__, "use_enrollments": False, "scb_layers": 0}
+    dev = torch.device("cuda:0")
+    for dm, tag, B in ((synth.Dims(**{**base, **over}), "p0", 2),
+                       (dataclasses.replace(synth.WHISPER_TINY, vocab=1000, enc_layers=3, T=200, **over), "p1", 2)):
+        enc, p = build_encoder(dm, dev)
+        f = torch.from_numpy(synth.make_features(tag, B, dm.n_mels, 2 * dm.T))
+        s = torch.from_numpy(synth.make_stno(tag, B, dm.T, "soft", pad_tail=9))
+        with torch.no_grad():
+            ref = orc.encoder_forward(p, dm, f, s)
+            ref_l = orc.ctc_logits(p, dm, ref)
+            o = enc(f.to(dev), stno_mask=s.to(dev), return_logits=True)
+        e1, e2 = rel_err(o.hidden_states, ref), rel_err(o.logits, ref_l)
+        print(f"{name} d={dm.d}: hidden rel err {e1:.3e}, ctc logits rel err {e2:.3e}")
+        assert e1 < BF16_TOL and e2 < BF16_TOL

@@ -187,6 +187,12 @@ def test_finetune_step_full_matrix_fddt(dm, B, S, tag, mode):
     _finetune_case(dm, B, S, mode, tag)
 
 
+@pytest.mark.parametrize("over", [{"apply_fddt_to_n_layers": 1}, {"use_pre_pos_fddt": False}], ids=["first-layer-only", "no-pre-pos"])
+def test_finetune_step_fddt_placement_variants(over):
+    """FDDT in the first layer only / no FDDT in front of the positions: gradients of what is left (encoder.py:45-47, 62)"""
+    _finetune_case(dataclasses.replace(TINY_SHORT, enc_layers=3, **over), 3, 24, "decoder-frozen", "tr2")
+
+
 def test_finetune_step_remove_timestamps_from_ctc():
     """remove_timestamps_from_ctc=True (encoder.py:76, 111-113): the CTC branch is trained on the labels below the first task
     token only (vocab 1700 -> ids < 193); loss and gradients vs the oracle, whose filter is pinned to the reference live"""

@@ -20,6 +20,8 @@ CASES = {"mini": (MINI, 2, 11), "tiny": (TINY_SHORT, 3, 24),
          "mini-full": (dataclasses.replace(MINI, fddt_is_diagonal=False), 2, 11),
          "tiny-full": (dataclasses.replace(TINY_SHORT, fddt_is_diagonal=False), 3, 24),
          "mini-nots": (dataclasses.replace(MINI, remove_timestamps_from_ctc=True, vocab=1700), 2, 11),
+         "tiny-l1": (dataclasses.replace(TINY_SHORT, enc_layers=3, apply_fddt_to_n_layers=1), 3, 24),
+         "tiny-nopre": (dataclasses.replace(TINY_SHORT, enc_layers=3, use_pre_pos_fddt=False), 3, 24),
          "mini-layer": (dataclasses.replace(MINI, additional_layer=True), 2, 11),
          "tiny-layer": (dataclasses.replace(TINY_SHORT, additional_layer=True), 3, 24)}
 
