@@ -445,3 +445,37 @@ def test_forward_and_generate_signatures_cover_the_reference_names():
     for n in ("generation_config", "condition_on_prev_tokens", "assistant_model"):  # src/models/dicow/generation.py:536-541
         assert n in gen
     assert any(p.kind == p.VAR_KEYWORD for p in inspect.signature(DiCoWForConditionalGeneration.generate).parameters.values())
+
+
+@pytest.mark.parametrize("bias_only", [False, True])
+@pytest.mark.parametrize("off", ["silence", "target", "non_target", "overlap"])
+def test_fddt_tables_with_a_disabled_class_equal_reference_forward(bias_only, off):
+    """fddt_use_{silence,target,non_target,overlap}=False (FDDT.py:9-31, 43-62): a disabled class is the identity (diagonal)
+    or contributes nothing (bias-only).  The [4, d] tables the kernels consume, applied as x' = sum_c m_c (w_c x + b_c),
+    against the reference module's own forward with the same parameters"""
+    from ts_asr_whisper_b200.modeling import FDDT as Mine
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.FDDT import FDDT as Ref
+    finally:
+        sys.path.remove(REF)
+    d, B, T = 24, 2, 9
+    use = {f"use_{c}": c != off for c in ("silence", "target", "non_target", "overlap")}
+    ref = Ref(d, non_target_rate=0.5, fddt_init="suppressive", is_diagonal=True, bias_only=bias_only, **use)
+    mine = Mine(d, non_target_rate=0.5, fddt_init="suppressive", is_diagonal=True, bias_only=bias_only, **use)
+    assert sorted(k for k, _ in ref.named_parameters()) == sorted(k for k, _ in mine.named_parameters())
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for (_, a), (_, b) in zip(sorted(ref.named_parameters()), sorted(mine.named_parameters())):
+            a.copy_(torch.randn(a.shape, generator=gen) * 0.3 + 1.0)
+            b.copy_(a)
+    x = torch.randn(B, T, d, generator=gen)
+    m = torch.softmax(torch.randn(B, 4, T, generator=gen) * 2, dim=1)
+    m[:, :, -2:] = 0.0  # padded frames: every class weight zero
+    with torch.no_grad():
+        want = ref(x.clone(), m)
+        w, b = mine.tables()
+        mm = m.permute(0, 2, 1)                                   # [B, T, class]
+        weff = (mm @ w) if w is not None else torch.ones(B, T, d)
+        got = x * weff + mm @ b
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
