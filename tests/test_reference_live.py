@@ -143,8 +143,8 @@ _VARIANTS = [
 ]
 
 
-@pytest.mark.parametrize("vi", range(len(_VARIANTS)))
-def test_oracle_forward_loss_and_gradients_equal_reference_model(vi):
+@pytest.mark.parametrize("vi,soft", [(i, False) for i in range(9)] + [(0, True), (4, True), (6, True)])
+def test_oracle_forward_loss_and_gradients_equal_reference_model(vi, soft):
     """DiCoWForConditionalGeneration.forward with labels (src/models/dicow/modeling_dicow.py:248-354) of the REFERENCE, built
     from the same synthetic parameters, against oracle.dicow_oracle.model_forward: loss, logits, encoder states and the
     autograd gradient of every parameter -- the oracle's backward is what the B200 training step is judged against."""
@@ -163,7 +163,10 @@ def test_oracle_forward_loss_and_gradients_equal_reference_model(vi):
         dm = dataclasses.replace(synth.GOLDEN_MINI, **{**base, **over})
         B, S = 2, 9
         model = MG.build_reference(dm).train()  # dropout probabilities are all 0
-        model.tokenizer = types.SimpleNamespace(prefix_tokens=[MG.SOT, MG.LANG, MG.TASK])
+        if soft:  # SoftLabelCreator (modeling_dicow.py:23-144): Gaussian-smoothed timestamp targets, min over case streams
+            model.set_tokenizer(MG.FakeTokenizer(dm.vocab, MG.TS_BEGIN, MG.N_TS, [MG.SOT, MG.LANG, MG.TASK]))
+        else:     # hard-label fallback (modeling_dicow.py:312-323)
+            model.tokenizer = types.SimpleNamespace(prefix_tokens=[MG.SOT, MG.LANG, MG.TASK])
         p = orc.to_torch(synth.make_params(dm))
         p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
         names = [n for n, q in model.named_parameters() if "embed_positions" not in n]
@@ -183,7 +186,8 @@ def test_oracle_forward_loss_and_gradients_equal_reference_model(vi):
         out = model(input_features=feats, stno_mask=stno, labels=labels, upp_labels=upp, enrollments=enr)
         out.loss.backward()
         loss, logits, enc = orc.model_forward(p, dm, feats, stno, labels, upp, enrollments=enr,
-                                              ctc_prefix_tokens=(MG.SOT, MG.LANG, MG.TASK))
+                                              ctc_prefix_tokens=(MG.SOT, MG.LANG, MG.TASK),
+                                              **(dict(ts_begin=MG.TS_BEGIN, n_ts=MG.N_TS) if soft else {}))
         loss.backward()
         assert abs(loss.item() - out.loss.item()) < 1e-4 * max(1.0, abs(out.loss.item()))
         assert torch.allclose(logits, out.logits, rtol=1e-3, atol=2e-4)
