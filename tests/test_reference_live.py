@@ -483,3 +483,59 @@ def test_fddt_tables_with_a_disabled_class_equal_reference_forward(bias_only, of
         weff = (mm @ w) if w is not None else torch.ones(B, T, d)
         got = x * weff + mm @ b
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_greedy_decode_oracle_equals_reference_forward_plus_processors(case):
+    """A13 / A14: token-by-token greedy decoding with the reference's forward (KV-cache-free, use_cache=False) and its own
+    logits processors -- the loop of src/models/dicow/generation.py:707-782 -- against oracle.greedy_decode, on several
+    seeded models / inputs incl. SE-DiCoW; ids must be identical, first-step logits equal"""
+    import dataclasses
+    import types
+    import make_golden as MG
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    MG.mw.WhisperEncoderLayer.forward = MG._layer_fwd_tuple
+    try:
+        se = case == 3
+        dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=se, scb_layers=2 if se else 0, T=30 + 4 * case)
+        model = MG.build_reference(dm)
+        p = orc.to_torch(synth.make_params(dm))
+        p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
+        B, tag = 3, f"greedy{case}"
+        feats = torch.from_numpy(synth.make_features(tag, B, dm.n_mels, 2 * dm.T))
+        stno = torch.from_numpy(synth.make_stno(tag, B, dm.T, "soft", pad_tail=case))
+        enr = None
+        if se:
+            enr = {"input_features": torch.from_numpy(synth.make_features(tag + "e", B, dm.n_mels, 2 * dm.T)),
+                   "stno_mask": torch.from_numpy(synth.make_stno(tag + "e", B, dm.T, "hard"))}
+        gcfg = types.SimpleNamespace(no_timestamps_token_id=MG.NOTS, eos_token_id=MG.EOS, bos_token_id=MG.EOS,
+                                     max_initial_timestamp_index=None, _detect_timestamp_from_logprob=True)
+        procs = [MG.SuppressTokensLogitsProcessor(MG.SUPPRESS), MG.WhisperTimeStampLogitsProcessorCustom(gcfg, begin_index=3)]
+        steps = 14
+        with torch.no_grad():
+            enc_h = model.get_encoder()(feats, stno_mask=stno, enrollments=enr).last_hidden_state
+            ids = torch.tensor([[MG.SOT, MG.LANG, MG.TASK]] * B)
+            unfinished = torch.ones(B, dtype=torch.bool)
+            first = None
+            for _ in range(steps):
+                o = model(encoder_outputs=MG.BaseModelOutput(last_hidden_state=enc_h), decoder_input_ids=ids, use_cache=False)
+                sc = o.logits[:, -1].float()
+                first = sc.clone() if first is None else first
+                for pr in procs:
+                    sc = pr(ids, sc)
+                nxt = sc.argmax(-1)
+                nxt = torch.where(unfinished, nxt, torch.full_like(nxt, MG.EOS))
+                ids = torch.cat([ids, nxt[:, None]], 1)
+                unfinished &= nxt != MG.EOS
+                if not unfinished.any():
+                    break
+            ref_enc = orc.encoder_forward(p, dm, feats, stno, enrollments=enr)
+            got, lg = orc.greedy_decode(p, dm, ref_enc, torch.tensor([[MG.SOT, MG.LANG, MG.TASK]] * B), steps,
+                                        suppress=MG.SUPPRESS, no_timestamps=MG.NOTS, ts_begin=MG.TS_BEGIN, return_logits=True)
+        assert torch.allclose(ref_enc, enc_h, rtol=1e-3, atol=2e-4)
+        assert torch.allclose(lg[0], first, rtol=1e-3, atol=5e-4)
+        n = min(got.shape[1], ids.shape[1])
+        assert got[:, :n].tolist() == ids[:, :n].tolist()
+    finally:
+        MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
