@@ -1,12 +1,13 @@
 """Conditioning probe (CPU, fp32 oracle only -- test infrastructure): how far do the training-step gradients move when the
 weight matrices are merely rounded to bf16?  A seeded draw where this alone exceeds the parity bound cannot be used to
-judge a bf16 path; tests/test_gpu_training.py picks its draws with this.   python tools/cond_cpu.py [tag ...]"""
+judge a bf16 path; tests/test_gpu_training.py picks its draws with this.   python tests/cond_cpu.py [tag ...]"""
 import dataclasses
+import os
 import sys
 
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle import dicow_oracle as orc  # noqa: E402
 from oracle import synth  # noqa: E402
 

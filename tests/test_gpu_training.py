@@ -162,7 +162,7 @@ def test_finetune_step(dm, B, S, mode):
 # FDDT(bias_only=True) (src/models/dicow/FDDT.py:10-13, 43-51): the per-class parameter is a bias vector only.
 # The "tr1" draw is ill-conditioned for these tables at whisper-tiny widths: on the fp32 CPU oracle alone, rounding the
 # weight matrices to bf16 moves d(loss)/d(encoder output) by 28 % and conv1.weight's gradient by 11 % (loss 22.2329 ->
-# 22.2296), against 0.9 % / 0.8 % for "tr2" (tools/cond_cpu.py) -- a bf16 path cannot be held to 5 % there, so these
+# 22.2296), against 0.9 % / 0.8 % for "tr2" (tests/cond_cpu.py) -- a bf16 path cannot be held to 5 % there, so these
 # cases use the well-conditioned draw.  The decoder does not see the FDDT variant, so its parameters stay frozen here
 # ("all" is covered above; on "tr2" the near-uniform cross-attention makes the q/k weight gradients of BOTH variants
 # cancel to 6-8 % bf16 noise with cos 0.9995, measured on the diagonal variant too).
