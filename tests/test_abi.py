@@ -134,3 +134,29 @@ def test_no_device_fails_loudly(lib):
         lib.handle(0)
     with pytest.raises(ops.DicowError):
         ops.cast_bf16(torch.zeros(4))
+
+
+def test_oracle_is_imported_by_test_infrastructure_only():
+    """only tests/, __graft_entry__ (build / smoke) and the CPU-baseline leg of bench.py may import oracle/: the product
+    package and the tools never do (a product path routed through the oracle would void every parity claim)"""
+    import ast
+    import glob
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                hits.append(node)
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle" and node.level == 0:
+                hits.append(node)
+        return tree, hits
+    for path in glob.glob(os.path.join(ROOT, "ts-asr-whisper_b200", "**", "*.py"), recursive=True) + \
+            glob.glob(os.path.join(ROOT, "tools", "*.py")):
+        assert not oracle_imports(path)[1], f"{path} imports oracle/"
+    tree, hits = oracle_imports(os.path.join(ROOT, "bench.py"))
+    assert hits
+    allowed = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "time_reference"]
+    assert allowed
+    inside = {id(n) for n in ast.walk(allowed[0])}
+    assert all(id(h) in inside for h in hits), "bench.py imports oracle/ outside the CPU-baseline / reference leg"
