@@ -539,3 +539,70 @@ def test_greedy_decode_oracle_equals_reference_forward_plus_processors(case):
         assert got[:, :n].tolist() == ids[:, :n].tolist()
     finally:
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
+
+
+@pytest.mark.parametrize("K,penalty,tag,eos_scale", [(3, 1.0, "g0", None), (5, 0.1, "g1", None), (2, 0.0, "g2", None),
+                                                      (4, 2.0, "g3", 1.2), (3, 1.0, "g0", 1.15)])
+def test_beam_search_oracle_equals_hf_beam_search_through_reference_generate(K, penalty, tag, eos_scale):
+    """End to end: the reference's generate() (its long-form loop, logits processors and segment post-processing) running
+    the installed HF beam search -- the reference's own `_beam_search` / `_sample` overrides call transformers-4.55 private
+    APIs that no longer exist, so they are removed and the stock loop they were copied from runs instead --
+    against oracle.beam_search.beam_decode driven by the oracle's decoder + timestamp rules.  Complements the per-step pin
+    of the bookkeeping against HF's helper methods (tests/golden/beam_search.npz)."""
+    import dataclasses
+    import torch.nn.functional as F
+    import make_golden as MG
+    from oracle import beam_search as obs
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.generation import DiCoWGenerationMixin
+    finally:
+        sys.path.remove(REF)
+    saved = {n: DiCoWGenerationMixin.__dict__[n] for n in ("_beam_search", "_sample") if n in DiCoWGenerationMixin.__dict__}
+    MG.mw.WhisperEncoderLayer.forward = MG._layer_fwd_tuple
+    try:
+        for n in saved:
+            delattr(DiCoWGenerationMixin, n)
+        dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+        model = MG.build_reference(dm)
+        if eos_scale is not None:  # make <|endoftext|> competitive so that hypotheses finish
+            with torch.no_grad():
+                W = model.model.decoder.embed_tokens.weight
+                W[MG.EOS] = eos_scale * (W[217] + W[187]) / 2
+        model._fix_timestamps_from_segmentation = lambda out: out  # needs a real tokenizer (SURVEY 8c, shim #4)
+        B, NEW = 2, 10
+        feats = torch.from_numpy(synth.make_features(tag, B, dm.n_mels, 2 * dm.T))
+        stno = torch.from_numpy(synth.make_stno(tag, B, dm.T, "soft", pad_tail=7))
+        gc = model.generation_config
+        gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = MG.NOTS, MG.EOS, MG.EOS
+        gc.suppress_tokens, gc.begin_suppress_tokens = MG.SUPPRESS, None
+        gc.return_timestamps, gc.max_new_tokens, gc.num_beams, gc.length_penalty = True, NEW, K, penalty
+        gc.forced_decoder_ids = torch.tensor([[MG.SOT, MG.LANG, MG.TASK]] * B)
+        gc.is_multilingual, gc.lang_to_id, gc.task_to_id, gc.ctc_weight = True, {"<|en|>": MG.LANG}, {"transcribe": MG.TASK}, 0.0
+        out = model.generate(input_features=feats, stno_mask=stno, attention_mask=torch.ones(B, 2 * dm.T, dtype=torch.long))
+        p = orc.to_torch(synth.make_params(dm))
+        p["model.decoder.embed_tokens.weight"] = model.model.decoder.embed_tokens.weight.detach().clone()
+        p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
+        with torch.no_grad():
+            enc = orc.encoder_forward(p, dm, feats, stno)
+
+            def step_scores(ids):
+                hid = orc.decoder_forward(p, dm, ids, enc.repeat_interleave(K, dim=0))
+                lp = F.log_softmax(F.linear(hid[:, -1], p["proj_out.weight"]).float(), dim=-1)
+                lp[:, MG.SUPPRESS] = -float("inf")
+                return orc.timestamp_rules(ids, lp, begin_index=3, eos=MG.EOS, no_timestamps=MG.NOTS, ts_begin=MG.TS_BEGIN)
+            best, _ = obs.beam_decode(step_scores, [[MG.SOT, MG.LANG, MG.TASK]] * B, K, eos=MG.EOS, pad=MG.EOS,
+                                      max_length=3 + NEW, length_penalty=penalty, early_stopping=False)
+
+        def strip(tokens):
+            tokens = [int(t) for t in tokens]
+            while tokens and tokens[-1] == MG.EOS:
+                tokens.pop()
+            return tokens
+        assert [strip(r) for r in out["sequences"].tolist()] == [strip(b[3:]) for b in best]
+    finally:
+        for n, fn in saved.items():
+            setattr(DiCoWGenerationMixin, n, fn)
+        MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
