@@ -606,3 +606,87 @@ def test_beam_search_oracle_equals_hf_beam_search_through_reference_generate(K, 
         for n, fn in saved.items():
             setattr(DiCoWGenerationMixin, n, fn)
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
+
+
+@pytest.mark.parametrize("se,windows", [(False, 3), (True, 3), (False, 2)])
+def test_long_form_generate_host_loop_equals_reference_generate(se, windows):
+    """A12: the long-form loop of the B200 generate() -- seek bookkeeping, per-window STNO slicing with silence padding
+    (generation.py:73-118), shrinking batch, _retrieve_segment (:415-534), segment / sequence assembly -- against the
+    reference's generate() (the HF long-form loop with the DiCoW hooks; its 4.55-only `_sample` override removed so the
+    stock greedy loop runs, `_fix_timestamps_from_segmentation` bypassed: SURVEY 8c shims).  The two device calls of the
+    product loop (encoder forward, greedy window decode) are backed by the oracle here, so this runs on the CPU and pins
+    the HOST logic; the device calls themselves are pinned against the same oracle in the GPU suite."""
+    import dataclasses
+    import types
+    import make_golden as MG
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.generation import DiCoWGenerationMixin
+    finally:
+        sys.path.remove(REF)
+    saved = {n: DiCoWGenerationMixin.__dict__[n] for n in ("_beam_search", "_sample") if n in DiCoWGenerationMixin.__dict__}
+    MG.mw.WhisperEncoderLayer.forward = MG._layer_fwd_tuple
+    try:
+        for n in saved:
+            delattr(DiCoWGenerationMixin, n)
+        dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=se, scb_layers=2 if se else 0)
+        ref = MG.build_reference(dm)
+        ref._fix_timestamps_from_segmentation = lambda out: out
+        B, NEW, F2 = 2, 12, 2 * dm.T
+        feats = torch.cat([torch.from_numpy(synth.make_features(f"lf{k}", B, dm.n_mels, F2)) for k in range(windows)], dim=-1)
+        stno = torch.cat([torch.from_numpy(synth.make_stno(f"lf{k}", B, dm.T, "soft")) for k in range(windows)], dim=-1)
+        attn = torch.ones(B, windows * F2, dtype=torch.long)
+        attn[1, F2 + 31:] = 0  # the second recording ends early inside its second window
+        enr = None
+        if se:
+            enr = {"input_features": torch.from_numpy(synth.make_features("lfe", B, dm.n_mels, F2)),
+                   "stno_mask": torch.from_numpy(synth.make_stno("lfe", B, dm.T, "hard"))}
+        prompt = torch.tensor([[MG.SOT, MG.LANG, MG.TASK]] * B)
+
+        def setup(gc):
+            gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = MG.NOTS, MG.EOS, MG.EOS
+            gc.suppress_tokens, gc.begin_suppress_tokens = MG.SUPPRESS, None
+            gc.return_timestamps, gc.max_new_tokens, gc.num_beams = True, NEW, 1
+            gc.is_multilingual, gc.lang_to_id, gc.task_to_id, gc.ctc_weight = True, {"<|en|>": MG.LANG}, {"transcribe": MG.TASK}, 0.0
+        setup(ref.generation_config)
+        ref.generation_config.forced_decoder_ids = prompt
+        kw = dict(input_features=feats, stno_mask=stno, attention_mask=attn)
+        if se:
+            kw["enrollments"] = enr
+        want = ref.generate(**kw)
+
+        mine = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+        mine.tokenizer = None
+        setup(mine.generation_config)
+        p = orc.to_torch(synth.make_params(dm))
+        p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
+
+        def oracle_encoder(seg_in, stno_mask=None, enrollments=None, enrollment_kv=None, capture_enrollment_kv=None, **_):
+            assert enrollment_kv is None
+            with torch.no_grad():
+                return types.SimpleNamespace(last_hidden_state=orc.encoder_forward(p, dm, seg_in, stno_mask, enrollments=enrollments))
+
+        def oracle_greedy(hidden, prompts, max_total, rules, ctc=None, **_):
+            with torch.no_grad():
+                return orc.greedy_decode(p, dm, hidden, prompts, max_total - prompts.shape[1], suppress=MG.SUPPRESS,
+                                         no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"])
+        mine.get_encoder().forward = oracle_encoder
+        mine.greedy_decode_window = oracle_greedy
+        mine.cache_enrollment_kv = False  # the cache replaces the encoder call's arguments; exercised in the GPU suite
+        got = mine.generate(feats, attention_mask=attn, stno_mask=stno, forced_decoder_ids=prompt, enrollments=enr,
+                            return_segments=True)
+        assert got["sequences"].tolist() == want["sequences"].tolist()
+        assert len(got["segments"]) == len(want["segments"]) == B
+        for a, b in zip(got["segments"], want["segments"]):
+            assert len(a) == len(b) and len(a) >= 1
+            for sa, sb in zip(a, b):
+                assert sa["tokens"].tolist() == sb["tokens"].tolist()
+                assert abs(float(sa["start"]) - float(sb["start"])) < 1e-9 and abs(float(sa["end"]) - float(sb["end"])) < 1e-9
+    finally:
+        for n, fn in saved.items():
+            setattr(DiCoWGenerationMixin, n, fn)
+        MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
