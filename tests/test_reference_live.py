@@ -608,8 +608,8 @@ def test_beam_search_oracle_equals_hf_beam_search_through_reference_generate(K, 
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
 
 
-@pytest.mark.parametrize("se,windows", [(False, 3), (True, 3), (False, 2)])
-def test_long_form_generate_host_loop_equals_reference_generate(se, windows):
+@pytest.mark.parametrize("se,windows,beams", [(False, 3, 1), (True, 3, 1), (False, 2, 1), (False, 3, 3), (True, 2, 2)])
+def test_long_form_generate_host_loop_equals_reference_generate(se, windows, beams):
     """A12: the long-form loop of the B200 generate() -- seek bookkeeping, per-window STNO slicing with silence padding
     (generation.py:73-118), shrinking batch, _retrieve_segment (:415-534), segment / sequence assembly -- against the
     reference's generate() (the HF long-form loop with the DiCoW hooks; its 4.55-only `_sample` override removed so the
@@ -650,7 +650,7 @@ def test_long_form_generate_host_loop_equals_reference_generate(se, windows):
         def setup(gc):
             gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = MG.NOTS, MG.EOS, MG.EOS
             gc.suppress_tokens, gc.begin_suppress_tokens = MG.SUPPRESS, None
-            gc.return_timestamps, gc.max_new_tokens, gc.num_beams = True, NEW, 1
+            gc.return_timestamps, gc.max_new_tokens, gc.num_beams, gc.length_penalty = True, NEW, beams, 0.5
             gc.is_multilingual, gc.lang_to_id, gc.task_to_id, gc.ctc_weight = True, {"<|en|>": MG.LANG}, {"transcribe": MG.TASK}, 0.0
         setup(ref.generation_config)
         ref.generation_config.forced_decoder_ids = prompt
@@ -674,8 +674,25 @@ def test_long_form_generate_host_loop_equals_reference_generate(se, windows):
             with torch.no_grad():
                 return orc.greedy_decode(p, dm, hidden, prompts, max_total - prompts.shape[1], suppress=MG.SUPPRESS,
                                          no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"])
+        def oracle_beams(hidden, prompts, max_total, rules, num_beams=1, length_penalty=1.0, early_stopping=False, ctc=None,
+                         top_k=None, **_):
+            import torch.nn.functional as F
+            from oracle import beam_search as obs
+
+            def step_scores(ids):
+                hid = orc.decoder_forward(p, dm, ids, hidden.repeat_interleave(num_beams, dim=0))
+                lp = F.log_softmax(F.linear(hid[:, -1], p["proj_out.weight"]).float(), dim=-1)
+                lp[:, MG.SUPPRESS] = -float("inf")
+                return orc.timestamp_rules(ids, lp, begin_index=prompts.shape[1], eos=rules["eos"],
+                                           no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"])
+            with torch.no_grad():
+                best, _ = obs.beam_decode(step_scores, prompts.tolist(), num_beams, eos=rules["eos"], pad=rules["pad"],
+                                          max_length=max_total, length_penalty=length_penalty, early_stopping=early_stopping)
+            n = max(len(b) for b in best)
+            return torch.tensor([b + [rules["pad"]] * (n - len(b)) for b in best], dtype=torch.long)
         mine.get_encoder().forward = oracle_encoder
         mine.greedy_decode_window = oracle_greedy
+        mine.beam_decode_window = oracle_beams
         mine.cache_enrollment_kv = False  # the cache replaces the encoder call's arguments; exercised in the GPU suite
         got = mine.generate(feats, attention_mask=attn, stno_mask=stno, forced_decoder_ids=prompt, enrollments=enr,
                             return_segments=True)
