@@ -97,3 +97,36 @@ def test_unsupported_logits_processors_are_refused_not_ignored():
     with pytest.raises(ValueError):
         model._generation_settings(None, {"do_sample": True})
     assert model._generation_settings(None, {"repetition_penalty": 1.0, "begin_suppress_tokens": []})["num_beams"] == 1
+
+
+def test_init_tokens_without_forced_ids_follow_hf_rules():
+    """HF WhisperGenerationMixin._retrieve_init_tokens ("Update init_tokens with task"): the task token follows a given task,
+    or a given language (default transcribe); a detected language without a task leaves <|sot|><|lang|>; <|notimestamps|> is
+    appended unless timestamps are returned.  (Pinned end to end against the reference's generate() in
+    tests/test_reference_live.py.)"""
+    import dataclasses
+    import pytest
+    import torch
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    gc = model.generation_config
+    gc.no_timestamps_token_id, gc.decoder_start_token_id = 261, 258
+    gc.lang_to_id, gc.task_to_id = {"<|aa|>": 259, "<|bb|>": 30}, {"transcribe": 260, "translate": 5}
+    model.detect_language = lambda **kw: torch.tensor([30, 259])
+    feats = torch.zeros(2, dm.n_mels, 2 * dm.T)
+
+    def tokens(**kw):
+        gs = model._generation_settings(None, dict(kw))
+        return model._init_tokens_without_forced_ids(feats, None, None, None, dict(kw), gs).tolist()
+    assert tokens() == [[258, 30], [258, 259]]                                           # detected language, no task
+    assert tokens(task="translate") == [[258, 30, 5], [258, 259, 5]]                     # given task
+    assert tokens(language="aa") == [[258, 259, 260], [258, 259, 260]]                   # given language -> transcribe
+    assert tokens(language=["<|bb|>", "aa"], task="transcribe") == [[258, 30, 260], [258, 259, 260]]
+    assert tokens(return_timestamps=False) == [[258, 30, 261], [258, 259, 261]]          # + <|notimestamps|>
+    with pytest.raises(ValueError):
+        tokens(task="summarise")
+    with pytest.raises(ValueError):
+        tokens(language="zz")

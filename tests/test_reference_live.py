@@ -707,3 +707,88 @@ def test_long_form_generate_host_loop_equals_reference_generate(se, windows, bea
         for n, fn in saved.items():
             setattr(DiCoWGenerationMixin, n, fn)
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
+
+
+def test_language_detection_and_prompt_without_forced_ids_equal_reference_generate():
+    """generation.py:120-221: no forced_decoder_ids -> HF _retrieve_init_tokens -> the reference's detect_language (one decoder
+    step on <|startoftranscript|>, non-language logits masked) -> <|sot|><|lang|><|task|>; the product's
+    _init_tokens_without_forced_ids / detect_language with their device call (DiCoW forward) backed by the oracle.  SE-DiCoW
+    model with enrollments: the reference's path needs `self.enrollments`."""
+    import dataclasses
+    import types
+    import torch.nn.functional as F
+    import make_golden as MG
+    from oracle import dicow_oracle as orc
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.generation import DiCoWGenerationMixin
+    finally:
+        sys.path.remove(REF)
+    saved = {n: DiCoWGenerationMixin.__dict__[n] for n in ("_beam_search", "_sample") if n in DiCoWGenerationMixin.__dict__}
+    MG.mw.WhisperEncoderLayer.forward = MG._layer_fwd_tuple
+    try:
+        for n in saved:
+            delattr(DiCoWGenerationMixin, n)
+        dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=True, scb_layers=2)
+        ref = MG.build_reference(dm)
+        ref._fix_timestamps_from_segmentation = lambda out: out
+        B, NEW, F2 = 3, 8, 2 * dm.T
+        feats = torch.from_numpy(synth.make_features("lang", B, dm.n_mels, F2))
+        stno = torch.from_numpy(synth.make_stno("lang", B, dm.T, "soft"))
+        enr = {"input_features": torch.from_numpy(synth.make_features("lange", B, dm.n_mels, F2)),
+               "stno_mask": torch.from_numpy(synth.make_stno("lange", B, dm.T, "hard"))}
+        p = orc.to_torch(synth.make_params(dm))
+        with torch.no_grad():  # make the language logits differ between recordings: rows of the tied embedding
+            for k, tok in enumerate((259, 30, 77, 201)):
+                p["model.decoder.embed_tokens.weight"][tok] *= 1.0 + 0.6 * k
+            ref.model.decoder.embed_tokens.weight.copy_(p["model.decoder.embed_tokens.weight"])
+        p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
+        lang_to_id = {"<|aa|>": 259, "<|bb|>": 30, "<|cc|>": 77, "<|dd|>": 201}
+
+        def setup(gc):
+            gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = MG.NOTS, MG.EOS, MG.EOS
+            gc.suppress_tokens, gc.begin_suppress_tokens = MG.SUPPRESS, None
+            gc.return_timestamps, gc.max_new_tokens, gc.num_beams = True, NEW, 1
+            gc.is_multilingual, gc.lang_to_id, gc.ctc_weight = True, lang_to_id, 0.0
+            gc.task_to_id, gc.decoder_start_token_id, gc.forced_decoder_ids = {"transcribe": MG.TASK, "translate": 5}, MG.SOT, None
+        setup(ref.generation_config)
+        ref.config.forced_decoder_ids = None
+        want = ref.generate(input_features=feats, stno_mask=stno, attention_mask=torch.ones(B, F2, dtype=torch.long),
+                            enrollments=enr)
+        ref.stno_mask, ref.enrollments = stno, enr
+        want_lang = ref.detect_language(input_features=feats, generation_config=ref.generation_config, num_segment_frames=F2)
+
+        mine = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+        mine.tokenizer = None
+        setup(mine.generation_config)
+
+        def oracle_forward(feats_, stno_, ids, encoder_outputs, *_a):
+            enrollments = _a[-1] if _a else None
+            with torch.no_grad():
+                enc = orc.encoder_forward(p, dm, feats_, stno_, enrollments=enrollments)
+                hid = orc.decoder_forward(p, dm, ids, enc)
+                return types.SimpleNamespace(logits=F.linear(hid, p["proj_out.weight"]))
+
+        def oracle_encoder(seg_in, stno_mask=None, enrollments=None, **_):
+            with torch.no_grad():
+                return types.SimpleNamespace(last_hidden_state=orc.encoder_forward(p, dm, seg_in, stno_mask, enrollments=enrollments))
+
+        def oracle_greedy(hidden, prompts, max_total, rules, ctc=None, **_):
+            with torch.no_grad():
+                return orc.greedy_decode(p, dm, hidden, prompts, max_total - prompts.shape[1], suppress=MG.SUPPRESS,
+                                         no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"])
+        mine._forward_inference = oracle_forward
+        mine.get_encoder().forward = oracle_encoder
+        mine.greedy_decode_window = oracle_greedy
+        got_lang = mine.detect_language(input_features=feats, stno_mask=stno, enrollments=enr)
+        assert got_lang.tolist() == want_lang.tolist() and len(set(got_lang.tolist())) >= 1
+        got = mine.generate(feats, attention_mask=torch.ones(B, F2, dtype=torch.long), stno_mask=stno, enrollments=enr,
+                            return_segments=True)
+        assert got["sequences"].tolist() == want["sequences"].tolist()
+    finally:
+        for n, fn in saved.items():
+            setattr(DiCoWGenerationMixin, n, fn)
+        MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd

@@ -1036,9 +1036,9 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         B = input_features.shape[0]
         start = int(getattr(gc, "decoder_start_token_id", None) or self.config.decoder_start_token_id)
         language = kwargs.get("language", getattr(gc, "language", None))
-        task = kwargs.get("task", getattr(gc, "task", None)) or "transcribe"
-        if task not in task_to_id:
-            raise ValueError(f"The `{task}` task is not supported. The task should be one of `{list(task_to_id)}`")
+        task = kwargs.get("task", getattr(gc, "task", None))
+        if task is not None and task not in ("translate", "transcribe"):  # HF TASK_IDS
+            raise ValueError(f"The `{task}` task is not supported. The task should be one of `['translate', 'transcribe']`")
         if language is not None:
             langs = [language] * B if isinstance(language, str) else list(language)
             lang_ids = []
@@ -1051,7 +1051,14 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         else:
             lang_ids = self.detect_language(input_features=input_features, generation_config=gc, stno_mask=stno_mask,
                                             enrollments=enrollments).cpu()
-        cols = [torch.full((B,), start, dtype=torch.int64), lang_ids, torch.full((B,), int(task_to_id[task]), dtype=torch.int64)]
+        cols = [torch.full((B,), start, dtype=torch.int64), lang_ids]
+        # the task token follows a GIVEN task, or a GIVEN language (default transcribe); with a detected language and no task
+        # HF leaves the prompt at <|sot|><|lang|> (generation_whisper.py, "Update init_tokens with task").  The reference's
+        # container sets generation_config.task = "transcribe" (src/models/containers.py:59), i.e. the first case.
+        if task is not None:
+            cols.append(torch.full((B,), int(task_to_id[task]), dtype=torch.int64))
+        elif language is not None:
+            cols.append(torch.full((B,), int(task_to_id["transcribe"]), dtype=torch.int64))
         if not gs["return_timestamps"]:
             cols.append(torch.full((B,), gs["no_timestamps"], dtype=torch.int64))
         return torch.stack(cols, dim=1)
