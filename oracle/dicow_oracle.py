@@ -438,7 +438,7 @@ def timestamp_rules(input_ids: torch.Tensor, scores: torch.Tensor, *, begin_inde
 
 def greedy_decode(p: Params, dm: Dims, enc: torch.Tensor, prompt: torch.Tensor, max_new_tokens: int, *,
                   suppress: Sequence[int], no_timestamps: int, ts_begin: int,
-                  return_logits: bool = False):
+                  return_logits: bool = False, timestamps: bool = True):
     """Greedy branch of DiCoWGenerationMixin._sample (src/models/dicow/generation.py:707-782): per step
     logits[:, -1].float() -> SuppressTokensLogitsProcessor -> timestamp processor -> argmax; finished rows emit pad
     (= eos); stop when all rows are finished or max_new_tokens reached.  Returns token ids [B, prompt+n]."""
@@ -455,8 +455,9 @@ def greedy_decode(p: Params, dm: Dims, enc: torch.Tensor, prompt: torch.Tensor, 
             all_logits.append(logits.clone())
         if sup.numel():
             logits[:, sup] = -float("inf")
-        logits = timestamp_rules(ids, logits, begin_index=begin_index, eos=dm.eos_token_id,
-                                 no_timestamps=no_timestamps, ts_begin=ts_begin)
+        if timestamps:  # return_timestamps=False: HF adds no timestamp processor (generation_whisper.py _retrieve_logit_processors)
+            logits = timestamp_rules(ids, logits, begin_index=begin_index, eos=dm.eos_token_id,
+                                     no_timestamps=no_timestamps, ts_begin=ts_begin)
         nxt = torch.argmax(logits, dim=-1)
         nxt = torch.where(unfinished, nxt, torch.full_like(nxt, dm.pad_token_id))
         ids = torch.cat([ids, nxt[:, None]], dim=1)

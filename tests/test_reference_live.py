@@ -608,8 +608,9 @@ def test_beam_search_oracle_equals_hf_beam_search_through_reference_generate(K, 
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
 
 
-@pytest.mark.parametrize("se,windows,beams", [(False, 3, 1), (True, 3, 1), (False, 2, 1), (False, 3, 3), (True, 2, 2)])
-def test_long_form_generate_host_loop_equals_reference_generate(se, windows, beams):
+@pytest.mark.parametrize("se,windows,beams,ts", [(False, 3, 1, True), (True, 3, 1, True), (False, 2, 1, True),
+                                                    (False, 3, 3, True), (True, 2, 2, True), (False, 1, 1, False)])
+def test_long_form_generate_host_loop_equals_reference_generate(se, windows, beams, ts):
     """A12: the long-form loop of the B200 generate() -- seek bookkeeping, per-window STNO slicing with silence padding
     (generation.py:73-118), shrinking batch, _retrieve_segment (:415-534), segment / sequence assembly -- against the
     reference's generate() (the HF long-form loop with the DiCoW hooks; its 4.55-only `_sample` override removed so the
@@ -650,7 +651,7 @@ def test_long_form_generate_host_loop_equals_reference_generate(se, windows, bea
         def setup(gc):
             gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = MG.NOTS, MG.EOS, MG.EOS
             gc.suppress_tokens, gc.begin_suppress_tokens = MG.SUPPRESS, None
-            gc.return_timestamps, gc.max_new_tokens, gc.num_beams, gc.length_penalty = True, NEW, beams, 0.5
+            gc.return_timestamps, gc.max_new_tokens, gc.num_beams, gc.length_penalty = ts, NEW, beams, 0.5
             gc.is_multilingual, gc.lang_to_id, gc.task_to_id, gc.ctc_weight = True, {"<|en|>": MG.LANG}, {"transcribe": MG.TASK}, 0.0
         setup(ref.generation_config)
         ref.generation_config.forced_decoder_ids = prompt
@@ -673,7 +674,9 @@ def test_long_form_generate_host_loop_equals_reference_generate(se, windows, bea
         def oracle_greedy(hidden, prompts, max_total, rules, ctc=None, **_):
             with torch.no_grad():
                 return orc.greedy_decode(p, dm, hidden, prompts, max_total - prompts.shape[1], suppress=MG.SUPPRESS,
-                                         no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"])
+                                         no_timestamps=rules["no_timestamps"], ts_begin=rules["ts_begin"],
+                                         timestamps=bool(rules["timestamp_rules"]))
+
         def oracle_beams(hidden, prompts, max_total, rules, num_beams=1, length_penalty=1.0, early_stopping=False, ctc=None,
                          top_k=None, **_):
             import torch.nn.functional as F
