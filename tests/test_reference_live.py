@@ -795,3 +795,43 @@ def test_language_detection_and_prompt_without_forced_ids_equal_reference_genera
         for n, fn in saved.items():
             setattr(DiCoWGenerationMixin, n, fn)
         MG.mw.WhisperEncoderLayer.forward = MG._orig_layer_fwd
+
+
+def test_get_optimizer_groups_equal_reference():
+    """src/models/containers.py:100-114 (imported with a stub `peft`, which this image lacks): the same parameters land in the
+    same two AdamW groups with the same learning rates / weight decay; None without `use_custom_optimizer`"""
+    import dataclasses
+    import types
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.containers import get_optimizer as mine
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    stub = types.ModuleType("peft")
+    stub.LoraConfig = stub.get_peft_model = None
+    had = sys.modules.get("peft")
+    sys.modules["peft"] = stub
+    sys.path.insert(0, REF)
+    try:
+        from models.containers import get_optimizer as ref
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"reference containers not importable: {e}")
+    finally:
+        sys.path.remove(REF)
+        if had is None:
+            sys.modules.pop("peft", None)
+        else:
+            sys.modules["peft"] = had
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=True, scb_layers=2)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    args = types.SimpleNamespace(use_custom_optimizer=True, learning_rate=2e-4, weight_decay=0.01, fddt_lr_multiplier=50.0)
+    prefixes = ["model.encoder.initial_fddt", "model.encoder.fddts", "model.encoder.ca_enrolls"]
+    a, b = ref(model, args, prefixes), mine(model, args, prefixes)
+    assert type(a) is type(b) and len(a.param_groups) == len(b.param_groups) == 2
+    for ga, gb in zip(a.param_groups, b.param_groups):
+        assert [id(q) for q in ga["params"]] == [id(q) for q in gb["params"]]
+        assert ga["lr"] == gb["lr"] and ga["weight_decay"] == gb["weight_decay"] and ga["betas"] == gb["betas"]
+    assert len(a.param_groups[1]["params"]) > 0
+    a, b = ref(model, args, None), mine(model, args, None)
+    assert [len(g["params"]) for g in a.param_groups] == [len(g["params"]) for g in b.param_groups]
+    args.use_custom_optimizer = False
+    assert ref(model, args, prefixes) is None and mine(model, args, prefixes) is None
