@@ -835,3 +835,42 @@ def test_get_optimizer_groups_equal_reference():
     assert [len(g["params"]) for g in a.param_groups] == [len(g["params"]) for g in b.param_groups]
     args.use_custom_optimizer = False
     assert ref(model, args, prefixes) is None and mine(model, args, prefixes) is None
+
+
+def test_freeze_except_equals_reference_container():
+    """WhisperContainer.freeze_except (src/models/containers.py:92-97), called on an instance built without __init__ (which
+    needs the hub): the same parameters stay trainable for the recipes' prefixes_to_preheat"""
+    import dataclasses
+    import types
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.containers import WhisperContainer as Mine
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    stub = types.ModuleType("peft")
+    stub.LoraConfig = stub.get_peft_model = None
+    had = sys.modules.get("peft")
+    sys.modules["peft"] = stub
+    sys.path.insert(0, REF)
+    try:
+        from models.containers import WhisperContainer as Ref
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"reference containers not importable: {e}")
+    finally:
+        sys.path.remove(REF)
+        if had is None:
+            sys.modules.pop("peft", None)
+        else:
+            sys.modules["peft"] = had
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=True, scb_layers=2)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    for prefixes in (["model.encoder.initial_fddt", "model.encoder.fddts"],           # configs/base.yaml: prefixes_to_preheat
+                     ["model.encoder.ca_enrolls", "model.encoder.fddts"], []):         # configs/train/se_dicow.yaml
+        sets = []
+        for cls in (Ref, Mine):
+            c = object.__new__(cls)
+            c.model = model
+            for q in model.parameters():
+                q.requires_grad_(True)
+            c.freeze_except(prefixes)
+            sets.append({n for n, q in model.named_parameters() if q.requires_grad})
+        assert sets[0] == sets[1] and (bool(sets[0]) == bool(prefixes))
