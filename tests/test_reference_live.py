@@ -874,3 +874,23 @@ def test_freeze_except_equals_reference_container():
             c.freeze_except(prefixes)
             sets.append({n for n, q in model.named_parameters() if q.requires_grad})
         assert sets[0] == sets[1] and (bool(sets[0]) == bool(prefixes))
+
+
+def test_soft_label_tables_equal_reference_smoothing_matrix():
+    """SoftLabelCreator (modeling_dicow.py:23-70): the reference's dense [num_ts, vocab] smoothing matrix is zero outside the
+    contiguous timestamp block and equals the [num_ts, num_ts] Gaussian table the B200 loss kernel reads (ts_begin + table)"""
+    import make_golden as MG
+    from ts_asr_whisper_b200.modeling_dicow import SoftLabelCreator as Mine
+    sys.path.insert(0, REF)
+    try:
+        from models.dicow.modeling_dicow import SoftLabelCreator as Ref
+    finally:
+        sys.path.remove(REF)
+    for vocab, ts_begin, n_ts in ((300, 262, 38), (1700, 199, 1501)):
+        tok = MG.FakeTokenizer(vocab, ts_begin, n_ts, [MG.SOT, MG.LANG, MG.TASK])
+        a, b = Ref(tok), Mine(tok)
+        dense = a.ts_smoothing_matrix
+        assert b.ts_begin == ts_begin and tuple(b.ts_smoothing_weights.shape) == (n_ts, n_ts)
+        assert torch.equal(dense[:, ts_begin:ts_begin + n_ts], b.ts_smoothing_weights)
+        outside = torch.cat([dense[:, :ts_begin], dense[:, ts_begin + n_ts:]], dim=1)
+        assert float(outside.abs().max()) == 0.0
