@@ -152,3 +152,27 @@ def test_python_surface_of_survey_8b_exists():
     assert enc.get_max_len() == 2 * dm.T
     DiCoWConfig.register_for_auto_class()
     DiCoWForConditionalGeneration.register_for_auto_class("AutoModelForSpeechSeq2Seq")  # utils/export_dicow.py:22-23
+
+
+def test_reference_checkpoint_with_smoothing_matrix_buffer_loads_quietly(tmp_path, caplog):
+    """a checkpoint saved by the reference after set_tokenizer() contains soft_label_creator.ts_smoothing_matrix
+    (persistent buffer, modeling_dicow.py:33): from_pretrained accepts it without an unexpected-key report"""
+    import dataclasses
+    import logging
+    import os
+    from safetensors.torch import load_file, save_file
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    model.save_pretrained(tmp_path)
+    path = os.path.join(tmp_path, "model.safetensors")
+    sd = load_file(path)
+    sd["soft_label_creator.ts_smoothing_matrix"] = torch.zeros(38, dm.vocab)
+    save_file(sd, path, metadata={"format": "pt"})
+    with caplog.at_level(logging.WARNING):
+        again, info = DiCoWForConditionalGeneration.from_pretrained(tmp_path, output_loading_info=True)
+    assert not info["unexpected_keys"], info["unexpected_keys"]
+    for (n, a), (_, b) in zip(model.state_dict().items(), again.state_dict().items()):
+        assert torch.equal(a, b), n

@@ -271,6 +271,9 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
     base_model_prefix = "model"
     main_input_name = "input_features"
     _tied_weights_keys = {"proj_out.weight": "model.decoder.embed_tokens.weight"}
+    # checkpoints written by the reference after set_tokenizer() carry its dense [num_ts, vocab] smoothing matrix as a
+    # persistent buffer (modeling_dicow.py:33); here the table is rebuilt from the tokenizer and is not part of the state
+    _keys_to_ignore_on_load_unexpected = [r"soft_label_creator\.ts_smoothing_matrix"]
     _no_split_modules = ["EncoderLayerParams", "DecoderLayerParams"]
     # step graphs are captured once per batch size; set False to launch the step kernels eagerly (debugging)
     use_cuda_graphs = True
