@@ -176,3 +176,29 @@ def test_reference_checkpoint_with_smoothing_matrix_buffer_loads_quietly(tmp_pat
     assert not info["unexpected_keys"], info["unexpected_keys"]
     for (n, a), (_, b) in zip(model.state_dict().items(), again.state_dict().items()):
         assert torch.equal(a, b), n
+
+
+def test_training_refuses_dropout_it_would_not_apply():
+    """training.trainable() is the gate both forward()s consult: zero dropout / LayerDrop (every Whisper checkpoint, the
+    reference's defaults) passes; a config that asks for stochastic regularisation is refused in train mode only"""
+    import dataclasses
+    import pytest
+    from oracle import synth
+    from ts_asr_whisper_b200 import training
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs())).train()
+    assert training.trainable(model) is True and training.trainable(model.get_encoder()) is True
+    with torch.no_grad():
+        assert training.trainable(model) is False
+    for key, value in (("dropout", 0.1), ("attention_dropout", 0.1), ("final_dropout", 0.05), ("encoder_layerdrop", 0.1),
+                       ("apply_spec_augment", True)):
+        old = getattr(model.config, key)
+        setattr(model.config, key, value)
+        with pytest.raises(NotImplementedError, match=key):
+            training.trainable(model)
+        assert training.trainable(model.eval()) is True  # evaluation is deterministic either way
+        model.train()
+        setattr(model.config, key, old)
+    assert training.trainable(model) is True

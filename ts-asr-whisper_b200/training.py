@@ -905,9 +905,26 @@ def _body_trainable(enc) -> bool:
     return any(p.requires_grad for n, p in enc.named_parameters() if not n.startswith(_HEAD_PREFIXES))
 
 
+_STOCHASTIC = ("dropout", "attention_dropout", "activation_dropout", "final_dropout", "encoder_layerdrop", "decoder_layerdrop")
+
+
+def refuse_stochastic_regularisation(config) -> None:
+    """The training step applies no dropout / LayerDrop / in-model SpecAugment: every Whisper checkpoint and the reference's
+    DiCoWConfig default have them at zero (config.py:14; apply_spec_augment False).  A config that asks for them must not be
+    trained silently without them."""
+    asked = [f"{k}={getattr(config, k)}" for k in _STOCHASTIC if float(getattr(config, k, 0.0) or 0.0) > 0.0]
+    if getattr(config, "apply_spec_augment", False):
+        asked.append("apply_spec_augment=True")
+    if asked:
+        raise NotImplementedError("the B200 training step does not implement: " + ", ".join(asked))
+
+
 def trainable(module: torch.nn.Module) -> bool:
     """route forward() to the training path: autograd is recording and something can receive a gradient"""
-    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+    on = torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+    if on and module.training and getattr(module, "config", None) is not None:
+        refuse_stochastic_regularisation(module.config)
+    return on
 
 
 def _enrollments(enr_features, enr_stno) -> Optional[dict]:
