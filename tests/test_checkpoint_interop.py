@@ -202,3 +202,19 @@ def test_training_refuses_dropout_it_would_not_apply():
         model.train()
         setattr(model.config, key, old)
     assert training.trainable(model) is True
+
+
+def test_forward_refuses_outputs_the_fused_path_does_not_produce():
+    import dataclasses
+    import pytest
+    from oracle import synth
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    feats = torch.zeros(1, dm.n_mels, 2 * dm.T)
+    ids = torch.tensor([[258, 259]])
+    for kw in (dict(output_attentions=True), dict(output_hidden_states=True), dict(head_mask=torch.ones(3, 2)),
+               dict(decoder_head_mask=torch.ones(2, 2)), dict(past_key_values=()), dict(decoder_inputs_embeds=torch.zeros(1, 2, dm.d))):
+        with pytest.raises(NotImplementedError):
+            model(feats, stno_mask=torch.zeros(1, 4, dm.T), decoder_input_ids=ids, **kw)

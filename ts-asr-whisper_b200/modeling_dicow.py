@@ -415,6 +415,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
         if past_key_values is not None or decoder_inputs_embeds is not None:
             raise NotImplementedError("forward() is the teacher-forced path; token-by-token decoding is generate()")
+        if output_attentions or output_hidden_states or any(m is not None for m in (head_mask, decoder_head_mask,
+                                                                                    cross_attn_head_mask)):
+            raise NotImplementedError("output_attentions / output_hidden_states / head masks are not produced by the fused "
+                                      "B200 path")
         if labels is not None and encoder_outputs is None and input_features is not None and input_features.is_cuda:
             from . import training
             if training.trainable(self):
