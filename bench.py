@@ -16,9 +16,14 @@ N GPUs run N replicas with no data-path collective ("weak" scaling: B per GPU fi
   roofline: the tcgen05 GEMM kernel family (dominant: ~60 % of the step), algorithmic FLOPs / CUDA-event time per
            launch measured live in extra instrumented steps right after the timed region (an event pair around every
            launch perturbs the step by up to 6 %), against the measured cuBLAS bf16 peak (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference: the reference's algorithm (oracle/dicow_oracle.py -- the reference itself is Python
-           over HF transformers and /root/reference does not exist on the GPU box) in fp32 on all host cores, on a
-           bounded sample (B=1 forwards) of the same workload.
+  cpu_baseline / --impl reference: the REFERENCE's own DiCoWEncoder.forward (oracle/_ref: its src/models/dicow modules,
+           copied there unmodified by oracle/make_ref.py in the build container; kind "reference") in fp32 on all host
+           cores, on a bounded sample (B=1 forwards) of the same workload; where oracle/_ref is missing, the oracle port
+           (oracle/dicow_oracle.py, kind "port").
+  secondary: BASELINE configs[2], [3], [4] measured in the same process after the headline (tools/workloads.py): the
+           fine-tune step with the gradient all-reduce (under torchrun: NCCL over NVLink, exposed communication time
+           reported), the CTC pre-train step, SE-DiCoW greedy decode -- each with its own bracketed clock sample and
+           roofline fraction.  --secondary none skips them.
 """
 from __future__ import annotations
 
@@ -40,38 +45,7 @@ METRIC = "encoder-fwd utterances/sec (30s@16kHz) large-v3-turbo+FDDT"
 GFLOP_PER_UTT = 2273.8  # conv stem 17.7 + 32 x (QKVO 19.661 + QK^T/PV 11.520 + MLP 39.322)
 
 
-def turbo_config():
-    from ts_asr_whisper_b200.configuration import DiCoWConfig
-    return DiCoWConfig(vocab_size=51866, num_mel_bins=128, d_model=1280, encoder_layers=32, encoder_attention_heads=20,
-                       decoder_layers=4, decoder_attention_heads=20, encoder_ffn_dim=5120, decoder_ffn_dim=5120,
-                       max_source_positions=1500, max_target_positions=448, use_fddt=True, use_pre_pos_fddt=True,
-                       fddt_is_diagonal=True, non_target_fddt_value=0.5, fddt_init="suppressive", ctc_weight=0.0,
-                       activation_function="gelu")
-
-
-def perturb_(enc, gen_device):
-    """Move FDDT / LayerNorm parameters off their identity init -- seeded."""
-    g = torch.Generator(device=gen_device).manual_seed(1234)
-    with torch.no_grad():
-        for name, p in enc.named_parameters():
-            if "fddt" in name:
-                if name.endswith("weight"):
-                    p.copy_(torch.rand(p.shape, generator=g, device=gen_device) + 0.5)
-                else:
-                    p.copy_(torch.randn(p.shape, generator=g, device=gen_device) * 0.1)
-            elif "layer_norm.weight" in name:
-                p.copy_(torch.rand(p.shape, generator=g, device=gen_device) * 0.4 + 0.8)
-            elif "embed_positions" in name:
-                p.copy_(torch.randn(p.shape, generator=g, device=gen_device) * 0.1)
-
-
-def make_inputs(B, seed, device="cpu", pin=False):
-    g = torch.Generator().manual_seed(seed)
-    feats = (torch.randn(B, 128, 3000, generator=g) * 0.4 - 0.3).clamp_(-1.0, 1.5)
-    stno = torch.softmax(3.0 * torch.randn(B, 4, 1500, generator=g), dim=1)
-    if pin:
-        feats, stno = feats.pin_memory(), stno.pin_memory()
-    return feats.to(device), stno.to(device)
+from tools.workloads import make_inputs, perturb_, turbo_config  # noqa: E402,F401  (re-exported for tools/)
 
 
 class ClockSampler:
@@ -100,13 +74,13 @@ class ClockSampler:
         nvidia-smi's own start-up -- process launch, NVML initialisation -- does not land inside it)"""
         return len(self.rows)
 
-    def stop(self, first: int = 0, last: int = None):
+    def window(self, first: int = 0, last: int = None):
+        """summary of the samples [first, last) (marks taken around a timed region)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = self.rows[first:last] or self.rows[-3:]
+        rows = self.rows[first:max(last, first + 1) if last is not None else None] or self.rows[-3:]
         for r in rows:
             try:
                 sm.append(float(r[0]))
@@ -119,41 +93,64 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
+    def stop(self, first: int = 0, last: int = None):
+        out = self.window(first, last)
+        if self.proc is not None:
+            self.proc.terminate()
+        return out
 
-def time_reference(steps, warmup, B=1, threads=None, device="cpu"):
-    """The reference's implementation of the path as stock PyTorch (oracle port, SDPA): fp32 on all host threads (the
-    baseline the contract asks for), or -- ``--reference-device cuda``, context only -- the same eager code under bf16
-    autocast on the GPU (cuBLAS + the SDPA flash kernel: what the reference's own modules run there)."""
-    from oracle import dicow_oracle as orc
-    from oracle import synth
+
+def time_reference(steps, warmup, B=1, threads=None, device="cpu", force_port=False):
+    """The reference's implementation of the path on the host cores: its own DiCoWEncoder.forward from oracle/_ref (kind
+    "reference") or, where that copy is missing, the oracle port (kind "port"); fp32, SDPA, all host threads.
+    ``--reference-device cuda`` (context only): the same eager code under bf16 autocast on the GPU (cuBLAS + SDPA flash)."""
+    from oracle import ref_loader
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    dm = synth.LARGE_V3_TURBO
-    g = torch.Generator().manual_seed(7)
-    p = {}
-    for k, shp in synth.param_shapes(dm, decoder=False).items():
-        if "lm_head" in k or "subsample" in k or "additional" in k:
-            continue
-        if k.endswith("weight") and len(shp) >= 2:
-            p[k] = torch.randn(shp, generator=g) * (1.0 / (shp[1] * (shp[2] if len(shp) > 2 else 1)) ** 0.5)
-        elif "fddt" in k and k.endswith("weight"):
-            p[k] = torch.rand(shp, generator=g) + 0.5
-        elif "layer_norm.weight" in k:
-            p[k] = torch.rand(shp, generator=g) * 0.4 + 0.8
-        else:
-            p[k] = torch.randn(shp, generator=g) * 0.1
     feats, stno = make_inputs(B, 100)
-    times = []
-    if device != "cpu":
-        dev = torch.device(device)
+    dev = torch.device(device)
+    if ref_loader.available() and not force_port:
+        kind = "reference"
+        RefConfig, RefEncoder = ref_loader.load()
+        cfg = RefConfig(**turbo_config().to_dict())
+        cfg._attn_implementation = "sdpa"
+        torch.manual_seed(7)
+        enc = RefEncoder(cfg).eval()
+        perturb_(enc, "cpu")
+        enc = enc.to(dev)
+
+        def fwd(f, s):
+            return enc(f, stno_mask=s).last_hidden_state
+    else:
+        kind = "port"
+        from oracle import dicow_oracle as orc
+        from oracle import synth
+        dm = synth.LARGE_V3_TURBO
+        g = torch.Generator().manual_seed(7)
+        p = {}
+        for k, shp in synth.param_shapes(dm, decoder=False).items():
+            if "lm_head" in k or "subsample" in k or "additional" in k:
+                continue
+            if k.endswith("weight") and len(shp) >= 2:
+                p[k] = torch.randn(shp, generator=g) * (1.0 / (shp[1] * (shp[2] if len(shp) > 2 else 1)) ** 0.5)
+            elif "fddt" in k and k.endswith("weight"):
+                p[k] = torch.rand(shp, generator=g) + 0.5
+            elif "layer_norm.weight" in k:
+                p[k] = torch.rand(shp, generator=g) * 0.4 + 0.8
+            else:
+                p[k] = torch.randn(shp, generator=g) * 0.1
         p = {k: v.to(dev) for k, v in p.items()}
-        feats, stno = feats.to(dev), stno.to(dev)
+
+        def fwd(f, s):
+            return orc.encoder_forward(p, dm, f, s)
+    feats, stno = feats.to(dev), stno.to(dev)
+    times = []
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=device != "cpu"):
         for i in range(warmup + steps):
             if device != "cpu":
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
-            orc.encoder_forward(p, dm, feats, stno)
+            fwd(feats, stno)
             if device != "cpu":
                 torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -161,9 +158,11 @@ def time_reference(steps, warmup, B=1, threads=None, device="cpu"):
                 times.append(dt)
     total = sum(times)
     how = "fp32" if device == "cpu" else f"bf16 autocast on {device} (eager cuBLAS / SDPA, context only)"
-    return {"utt_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads,
-            "sample": f"{len(times)} forward(s) of B={B} utterance(s), {how}, torch {torch.__version__} SDPA, "
-                      f"{warmup} warm-up"}
+    what = ("the reference's own DiCoWEncoder.forward (oracle/_ref)" if kind == "reference" else
+            "oracle port of the reference's algorithm (oracle/dicow_oracle.py)")
+    return {"utt_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads, "kind": kind,
+            "sample": f"{len(times)} forward(s) of B={B} utterance(s) of the same workload, {what}, {how}, torch "
+                      f"{torch.__version__} SDPA, {warmup} warm-up"}
 
 
 def main():
@@ -174,8 +173,11 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--secondary", default="all", help="comma list of finetune_step,ctc_pretrain_step,se_dicow_greedy; "
+                    "'all' (default) or 'none'")
     ap.add_argument("--reference-device", default="cpu", help="--impl reference: 'cpu' (the baseline) or 'cuda' (the same "
                     "stock PyTorch code under bf16 autocast on the GPU, for context)")
+    ap.add_argument("--reference-port", action="store_true", help="--impl reference: time the oracle port even if oracle/_ref exists")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,16 +190,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        W = max(1, min(args.warmup, 1))
-        K = max(1, min(args.steps, 3))
         on_gpu = args.reference_device != "cpu"
-        if on_gpu:
-            K, W = max(args.steps, 5), max(args.warmup, 2)
-        r = time_reference(K, W, B=args.batch if on_gpu else 1, device=args.reference_device)
+        # the caller's step / warm-up counts, bounded so that the run ends within a few minutes on the host cores
+        # (one step = one B=1 forward of the same workload, ~1.2-1.5 s on the GPU box's 16 threads)
+        K, W = max(1, min(args.steps, 40)), max(1, min(args.warmup, 5))
+        r = time_reference(K, W, B=args.batch if on_gpu else 1, device=args.reference_device, force_port=args.reference_port)
         line = {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": "utt/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if on_gpu else "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
+                "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": r["kind"],
                                  "sample": r["sample"]},
                 "e2e": {"value": r["utt_per_s"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -277,7 +278,7 @@ def main():
         ev_free = [None, None]  # compute that last read input buffer k has finished
         ev_out = [None, None]   # D2H out of host buffer k has finished
 
-        def h2d(i):
+        def h2d_copy(i):
             k = i % 2
             with torch.cuda.stream(s_in):
                 if ev_free[k] is not None:
@@ -286,14 +287,14 @@ def main():
                 dev_in[k][1].copy_(host[i % 3][1], non_blocking=True)
                 ev_in[k] = s_in.record_event()
 
-        h2d(0)
+        h2d_copy(0)
         for i in range(n):
             k = i % 2
             cur.wait_event(ev_in[k])
             o = enc(dev_in[k][0], stno_mask=dev_in[k][1]).last_hidden_state
             ev_free[k] = cur.record_event()
             if i + 1 < n:
-                h2d(i + 1)
+                h2d_copy(i + 1)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_free[k])
                 if ev_out[k] is not None:
@@ -311,20 +312,42 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    clocks = sampler.stop(m0, max(m1, m0 + 1)) if rank == 0 else None  # samples taken during the resident timed region
+    clocks = sampler.window(m0, max(m1, m0 + 1)) if rank == 0 else None  # samples taken during the resident timed region
     ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], dev)  # multi-GPU numbers are the slowest rank's
+
+    # ---- secondary workloads (BASELINE configs[2], [4], [3]); every rank takes part, rank 0 reports ----
+    del enc, resident, dev_in, out_hosts, out_host, host
+    torch.cuda.empty_cache()
+    names = {"all": ["finetune_step", "ctc_pretrain_step", "se_dicow_greedy"], "none": []}.get(
+        args.secondary, [n for n in args.secondary.split(",") if n])
+    secondary = {}
+    from tools import workloads
+    smp = sampler if rank == 0 else None
+    for name in names:
+        try:
+            if name == "finetune_step":
+                secondary[name] = workloads.train_step("finetune", dev, rank, world, steps=5, warmup=3, sampler=smp)
+            elif name == "ctc_pretrain_step":
+                secondary[name] = workloads.train_step("ctc_pretrain", dev, rank, world, steps=5, warmup=3, sampler=smp)
+            elif name == "se_dicow_greedy":
+                secondary[name] = workloads.se_dicow_greedy(dev, rank, world, sampler=smp)
+            else:
+                raise SystemExit(f"unknown secondary workload {name}")
+        except Exception as exc:  # a secondary failure must not take the headline line down; it is reported, not hidden
+            if world > 1:
+                raise
+            secondary[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank == 0:
+        sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
+    from tools.workloads import peaks as read_peaks
+    peaks = read_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    hbm = peaks.get("hbm_gbs") or 6650.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback B200_PROFILING.md sustained"
     by_kind = {}
@@ -333,37 +356,56 @@ def main():
         d[0] += fl
         d[1] += a.elapsed_time(b)
         d[2] += 1
-    kern = {k: {"launches": v[2], "ms_per_step": v[1] / roofline_steps,
-                "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[0] else None} for k, v in by_kind.items()}
+    step_ms = ms / args.steps
+    others = []
+    for k, v in by_kind.items():
+        if k == "gemm":
+            continue
+        o = {"kernel": k, "launches_per_step": v[2] // max(1, roofline_steps), "ms_per_step": v[1] / roofline_steps,
+             "share_of_step": (v[1] / roofline_steps) / step_ms if step_ms else None}
+        if v[0]:
+            tf = v[0] / (v[1] * 1e-3) / 1e12
+            o.update({"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf})
+        elif k in ("fddt_ln", "layernorm"):
+            # SURVEY 8d / DESIGN section 4: LN1 14 B/element + LN2 8 B/element per layer + final LN
+            nbytes = B * 1500 * 1280 * (32 * (14 + 8) + 12) * roofline_steps
+            gbs = nbytes / (v[1] * 1e-3) / 1e9
+            o.update({"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm})
+        others.append(o)
     gemm = by_kind.get("gemm", [0.0, 1.0, 1])
     achieved = gemm[0] / (gemm[1] * 1e-3) / 1e12
-    traffic = None  # dram read + write bytes per launch of the same kernel family from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-            traffic = json.load(f)["dram_bytes_per_launch_avg"]
-    except (OSError, KeyError, ValueError):
-        pass
+    traffic, traffic_src = None, None
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                traffic = json.load(f)["dram_bytes_per_launch_avg"]
+            traffic_src = f"committed ncu --set full capture (profiles/{name}); NOT measured by this run"
+            break
+        except (OSError, KeyError, ValueError):
+            pass
+    utts = world * B * args.steps
+    value = utts / (ms * 1e-3)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<256,*> (tcgen05 GEMM family: QKV/out/fc1/fc2/conv)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_per_step": gemm[2] // max(1, roofline_steps),
                 "gflop_per_launch_avg": gemm[0] / max(1, gemm[2]) / 1e9,
                 "us_per_launch_avg": 1e3 * gemm[1] / max(1, gemm[2]),
-                "share_of_step": (gemm[1] / roofline_steps) / (ms / args.steps) if ms else None,
+                "share_of_step": (gemm[1] / roofline_steps) / step_ms if ms else None,
                 "measured_over_steps": roofline_steps, "instrumented_ms_per_step": ms_instr / roofline_steps,
-                "note": "per-launch CUDA-event times from extra instrumented steps after the timed region"}
-    utts = world * B * args.steps
-    value = utts / (ms * 1e-3)
+                "note": "per-launch CUDA-event times from extra instrumented steps after the timed region",
+                "others": others,
+                "whole_step": {"tflops_per_gpu": value / world * GFLOP_PER_UTT / 1e3,
+                               "frac_of_sustained_peak": value / world * GFLOP_PER_UTT / 1e3 / peak_tf}}
     line = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
-            "whole_step": {"tflops_per_gpu": value / world * GFLOP_PER_UTT / 1e3,
-                           "frac_of_sustained_peak": value / world * GFLOP_PER_UTT / 1e3 / peak_tf}}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "secondary": secondary}
     if world == 1 and not args.no_cpu_baseline:
         r = time_reference(2, 1, B=1)
-        line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
+        line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"]}
     print(json.dumps(line), flush=True)
     if world > 1:

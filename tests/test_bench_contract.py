@@ -21,9 +21,19 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "utt/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["metric"].startswith("encoder-fwd utterances/sec") and "workload" in d["config"] and "model" not in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    want = "reference" if os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "models", "dicow", "encoder.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["dtype"] == "f32"
+
+
+def test_reference_arm_port_fallback():
+    """where oracle/_ref is missing the arm times the oracle port (forced here with --reference-port)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--reference-port"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
 def test_product_arm_needs_a_device():

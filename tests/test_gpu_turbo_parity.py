@@ -1,0 +1,274 @@
+"""GPU parity at the BENCHMARKED dimensions (whisper-large-v3-turbo: d 1280, 20 heads, ffn 5120, 32 + 4 layers, T 1500,
+vocabulary 51 866) for BASELINE configs[2], [3], [4] -- the kernels the bench numbers come from (2-CTA tcgen05 GEMM dgrad /
+wgrad at M = B x 1500 rows, attention backward at H = 20, decode_linear's cluster split-K at N = 51 866, 8 speaker
+communication blocks at d = 1280), against the fp32 oracle run with torch autograd ON THE SAME GPU (TF32 off).
+
+Bounds (bf16 operands / fp32 accumulation against an fp32 reference; stated next to each assertion):
+  forward tensors   max|err| <= 2e-2 max|ref| (north_star) AND per-row relative RMS / cosine (tests/parity.py)
+  gradients         per parameter tensor: max|err| <= tol_class x max|ref| and cosine >= cos_class, per tensor class
+  greedy tokens     every generated token equals the oracle's arg-max GIVEN THE SAME PREFIX (the oracle is teacher-forced on
+                    the CUDA tokens, so checking continues after a tolerated flip instead of stopping); a mismatch is
+                    tolerated only where the oracle's own margin between the two tokens is below MARGIN, and the NUMBER of
+                    tolerated flips is asserted."""
+import dataclasses
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dicow_oracle as orc
+from oracle import synth
+from parity import assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+EOS, SOT, LANG, TASK, NOTS, TS_BEGIN, N_TS = 50257, 50258, 50259, 50360, 50364, 50365, 1501
+SUPPRESS = [1, 2, 7, 8, 9, 10, 14, 25, 220, 50256, 50258, 50259, 50360]
+TURBO = synth.LARGE_V3_TURBO
+MARGIN = 0.15      # logit units: a flipped token must be a near-tie for the fp32 oracle itself
+MAX_FLIPS = 6      # of B x 32 = 128 generated tokens (measured: see the printed count)
+
+
+class WhisperIds:
+    prefix_tokens = [SOT, LANG, TASK]
+    pad_token_id = EOS
+
+    def get_vocab(self):
+        return {f"<|{0.02 * i:.2f}|>": TS_BEGIN + i for i in range(N_TS)}
+
+
+@pytest.fixture(scope="module")
+def turbo():
+    """the full large-v3-turbo DiCoW model (encoder + FDDT + CTC head + 4-layer decoder) on the GPU, and the oracle's fp32
+    parameter dict on the same device"""
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dm = TURBO
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    params = synth.make_params(dm)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    model.tie_weights()
+    model = model.to(DEV)
+    p = orc.to_torch(params, device=DEV)
+    p["proj_out.weight"] = p["model.decoder.embed_tokens.weight"]
+    del params
+    yield dm, model, p
+    del model, p
+    torch.cuda.empty_cache()
+
+
+def _inputs(dm, B, tag):
+    feats = torch.from_numpy(synth.make_features(tag, B, dm.n_mels, 2 * dm.T)).to(DEV)
+    stno = torch.from_numpy(synth.make_stno(tag, B, dm.T, "soft", pad_tail=37)).to(DEV)
+    return feats, stno
+
+
+# ---- (b) configs[3] decoder side: teacher-forced logits + greedy tokens at turbo dimensions ---------------------------
+def test_turbo_teacher_forced_logits(turbo):
+    dm, model, p = turbo
+    model.eval()
+    model.tokenizer, model.soft_label_creator = None, None
+    model.ctc_prefix_tokens = (SOT, LANG, TASK)
+    B, S = 2, 32
+    feats, stno = _inputs(dm, B, "tq0")
+    labels = torch.from_numpy(synth.make_labels("tq0", B, S, 51866, EOS, TS_BEGIN, prefix=(LANG, TASK))).to(DEV)
+    with torch.no_grad():
+        out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+        ref_loss, ref_logits, ref_enc = orc.model_forward(p, dm, feats, stno, labels, labels,
+                                                          ctc_prefix_tokens=(SOT, LANG, TASK))
+    torch.cuda.synchronize()
+    # bounds: north_star 2e-2 of max; per row (frame / token): relative RMS 3e-2, cosine 0.9995
+    assert_close(out.encoder_last_hidden_state, ref_enc, tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo encoder states")
+    assert_close(out.logits, ref_logits, tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo teacher-forced logits")
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item())), (out.loss.item(), ref_loss.item())
+
+
+def _oracle_choices(p, dm, ids, enc_ref, P):
+    """oracle arg-max (and processed scores) for every generated position GIVEN the prefix ``ids[:, :t]``: one teacher-forced
+    decoder pass over the CUDA tokens (generation.py:707-782 semantics: suppress -> timestamp rules -> argmax)"""
+    n = ids.shape[1]
+    hid = orc.decoder_forward(p, dm, ids[:, :-1], enc_ref)
+    logits_all = F.linear(hid, p["proj_out.weight"]).float()
+    sup = torch.tensor(SUPPRESS, dtype=torch.long, device=ids.device)
+    out = []
+    for t in range(P, n):
+        lg = logits_all[:, t - 1].clone()
+        lg[:, sup] = -float("inf")
+        proc = orc.timestamp_rules(ids[:, :t], lg, begin_index=P, eos=EOS, no_timestamps=NOTS, ts_begin=TS_BEGIN)
+        out.append(proc)
+    return out
+
+
+def test_turbo_greedy_tokens(turbo):
+    """32 greedy tokens for 4 windows through the CUDA-graphed decode step at full turbo dimensions"""
+    dm, model, p = turbo
+    model.eval()
+    B, P, NEW = 4, 3, 32
+    feats, stno = _inputs(dm, B, "tq1")
+    prompt = torch.tensor([[SOT, LANG, TASK]] * B, device=DEV)
+    rules = dict(eos=EOS, pad=EOS, no_timestamps=NOTS, ts_begin=TS_BEGIN, max_initial_timestamp_index=None,
+                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap(SUPPRESS, torch.device(DEV)))
+    with torch.no_grad():
+        enc = model.get_encoder()(feats, stno_mask=stno).last_hidden_state
+        ids, first = model.greedy_decode_window(enc, prompt, P + NEW, rules, return_first_logits=True)
+        ref_enc = orc.encoder_forward(p, dm, feats, stno)
+        procs = _oracle_choices(p, dm, ids, ref_enc, P)
+        ref_first = F.linear(orc.decoder_forward(p, dm, prompt, ref_enc)[:, -1], p["proj_out.weight"])
+    torch.cuda.synchronize()
+    assert_close(first, ref_first, tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo first-step logits (decode_linear N=51866)")
+    flips, checked, finished = 0, 0, torch.zeros(B, dtype=torch.bool)
+    ids_c = ids.cpu()
+    for t in range(P, ids.shape[1]):
+        proc = procs[t - P].cpu()
+        for b in range(B):
+            tok = int(ids_c[b, t])
+            if finished[b]:
+                assert tok == EOS, f"row {b} step {t - P}: finished rows emit pad"
+                continue
+            want = int(torch.argmax(proc[b]))
+            checked += 1
+            if tok != want:
+                margin = float(proc[b, want] - proc[b, tok])
+                assert margin < MARGIN, f"row {b} step {t - P}: token {tok} vs oracle {want}, oracle margin {margin:.3f}"
+                flips += 1
+            if tok == EOS:
+                finished[b] = True
+    print(f"turbo greedy: {checked} tokens checked against the oracle on the same prefix, {flips} tolerated near-tie flips "
+          f"(oracle margin < {MARGIN}); ids[0] = {ids_c[0].tolist()}")
+    assert checked >= B * NEW // 2 and flips <= MAX_FLIPS
+
+
+def test_generate_follows_weight_updates(turbo):
+    """captured decode graphs hold pointers to the prepared bf16 weights: after an optimizer-style update of the decoder
+    parameters generate() must decode with the NEW weights (id()-based staleness check)"""
+    dm, model, p = turbo
+    model.eval()
+    B, P = 2, 3
+    feats, stno = _inputs(dm, B, "tq2")
+    prompt = torch.tensor([[SOT, LANG, TASK]] * B, device=DEV)
+    rules = dict(eos=EOS, pad=EOS, no_timestamps=NOTS, ts_begin=TS_BEGIN, max_initial_timestamp_index=None,
+                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap(SUPPRESS, torch.device(DEV)))
+    with torch.no_grad():
+        enc = model.get_encoder()(feats, stno_mask=stno).last_hidden_state
+        _, first0 = model.greedy_decode_window(enc, prompt, P + 4, rules, return_first_logits=True)
+        ln = model.model.decoder.layer_norm
+        saved = ln.bias.detach().clone()
+        for _ in range(3):  # several rebuilds of the prepared dict, so a recycled id() would be likely
+            ln.bias.add_(0.25)
+            _, first1 = model.greedy_decode_window(enc, prompt, P + 4, rules, return_first_logits=True)
+        ln.bias.copy_(saved)
+        _, first2 = model.greedy_decode_window(enc, prompt, P + 4, rules, return_first_logits=True)
+    torch.cuda.synchronize()
+    assert (first1 - first0).abs().max().item() > 1e-2, "decode step still ran on the old weights"
+    assert torch.equal(first2, first0), "restoring the weights must restore the logits bit for bit"
+
+
+# ---- (a) configs[2]: one fine-tune step at full turbo dimensions --------------------------------------------------------
+# tolerance per tensor class: (max-norm bound, cosine bound).  north_star's 2e-2 applies to forward values; a gradient has
+# crossed up to 33 layers of bf16 dgrad GEMMs and the max-norm is taken over up to 6.5 M entries of a tensor.
+GRAD_CLASSES = {
+    "weight": (5e-2, 0.999),   # 2-D projection / conv / lm_head weights
+    "bias": (5e-2, 0.999),     # linear / conv biases
+    "norm": (5e-2, 0.999),     # LayerNorm gamma / beta
+    "fddt": (5e-2, 0.999),     # FDDT diagonal tables
+}
+
+
+def _grad_class(name: str) -> str:
+    if "fddt" in name:
+        return "fddt"
+    if "layer_norm" in name:
+        return "norm"
+    return "bias" if name.endswith("bias") else "weight"
+
+
+@pytest.mark.parametrize("B", [2])
+def test_turbo_finetune_step(turbo, B):
+    """loss = 0.7 soft-label CE + 0.3 CTC through DiCoWForConditionalGeneration.forward at d 1280 / 32 + 4 layers / V 51 866,
+    decoder frozen (the recipe); per-parameter gradients against torch autograd through the fp32 oracle"""
+    dm, model, p = turbo
+    model.train()
+    model.set_tokenizer(WhisperIds())
+    S = 24
+    for n, q in model.named_parameters():
+        q.requires_grad_(n.startswith("model.encoder.") and "embed_positions" not in n)
+        q.grad = None
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    feats, stno = _inputs(dm, B, "tf0")
+    labels = torch.from_numpy(synth.make_labels("tf0", B, S, 51866, EOS, TS_BEGIN, prefix=(LANG, TASK)))
+    upp = labels.clone()
+    upp[:, ::3] = torch.where((upp[:, ::3] >= 0) & (upp[:, ::3] < 50257), (upp[:, ::3] + 3) % 50257, upp[:, ::3])
+    labels, upp = labels.to(DEV), upp.to(DEV)
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=upp)
+    assert out.loss.requires_grad
+    out.loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    try:
+        ref_loss, ref_logits, _ = orc.model_forward(p, dm, feats, stno, labels, upp, ctc_prefix_tokens=(SOT, LANG, TASK),
+                                                    ts_begin=TS_BEGIN, n_ts=N_TS)
+        ref_loss.backward()
+        torch.cuda.synchronize()
+        assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item())), (out.loss.item(), ref_loss.item())
+        assert_close(out.logits, ref_logits.detach(), tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo train-forward logits")
+        named = dict(model.named_parameters())
+        worst = {c: (0.0, 1.0, "") for c in GRAD_CLASSES}
+        fails = []
+        for n in trainable:
+            got, ref = named[n].grad, p[n].grad
+            assert got is not None and ref is not None, n
+            scale = ref.abs().max().item()
+            if scale < 1e-12:
+                assert got.abs().max().item() < 1e-6, n
+                continue
+            err = (got.float() - ref).abs().max().item() / scale
+            cos = F.cosine_similarity(got.float().flatten(), ref.flatten(), dim=0).item()
+            c = _grad_class(n)
+            if err > worst[c][0]:
+                worst[c] = (err, min(cos, worst[c][1]), n)
+            tol, cmin = GRAD_CLASSES[c]
+            if not (err < tol and cos > cmin):
+                fails.append(f"{n}: rel err {err:.3e} cos {cos:.5f}")
+        for c, (e, cs, n) in worst.items():
+            print(f"turbo fine-tune gradients [{c}]: worst rel err {e:.3e} (cos {cs:.5f}) at {n}")
+        assert not fails, fails[:10]
+        assert all(q.grad is None for n, q in model.named_parameters() if not q.requires_grad)
+    finally:
+        for n in trainable:
+            p[n].requires_grad_(False)
+            p[n].grad = None
+        model.zero_grad(set_to_none=True)
+        model.eval()
+
+
+# ---- (c) configs[3] encoder side: SE-DiCoW at d = 1280 with 8 speaker communication blocks, full depth --------------------
+def test_turbo_se_dicow_encoder():
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling import DiCoWEncoder
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dm = dataclasses.replace(TURBO, use_enrollments=True, scb_layers=8, vocab=2047)
+    enc = DiCoWEncoder(DiCoWConfig(**dm.hf_kwargs()))
+    params = synth.make_params(dm, decoder=False)
+    enc.load_state_dict({k[len("model.encoder."):]: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    enc = enc.to(DEV).eval()
+    p = orc.to_torch(params, device=DEV)
+    del params
+    B = 2
+    feats, stno = _inputs(dm, B, "ts0")
+    enr = {"input_features": torch.from_numpy(synth.make_features("ts0e", B, dm.n_mels, 2 * dm.T)).to(DEV),
+           "stno_mask": torch.from_numpy(synth.make_stno("ts0e", B, dm.T, "hard")).to(DEV)}
+    with torch.no_grad():
+        ref = orc.encoder_forward(p, dm, feats, stno, enr)
+        ref_logits = orc.ctc_logits(p, dm, ref)
+        out = enc(feats, stno_mask=stno, enrollments=enr, return_logits=True)
+        cap = []
+        enc(feats, stno_mask=stno, enrollments=enr, capture_enrollment_kv=cap)
+        cached = enc(feats, stno_mask=stno, enrollment_kv=cap).last_hidden_state
+    torch.cuda.synchronize()
+    assert_close(out.encoder_last_hidden_state, ref, tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo SE-DiCoW encoder states")
+    assert_close(out.logits, ref_logits, tol=2e-2, row_rms=3e-2, row_cos=0.9995, what="turbo SE-DiCoW CTC logits")
+    assert torch.equal(cached, out.encoder_last_hidden_state), "enrollment K/V cache must be bit-transparent"
+    assert rel_err(out.hidden_states, out.hidden_states) == 0.0 and out.hidden_states.shape[1] == out.logits.shape[1]

@@ -28,95 +28,17 @@ args = ap.parse_args()
 
 
 def se_dicow_e2e():
-    """BASELINE configs[3]: SE-DiCoW (FDDT + enrollment cross-attention) greedy decode, batch = 16 windows, 1 x B200.
-    One pass = DiCoWEncoder.forward over 16 target + 16 enrollment windows (interleaved, 8 speaker communication
-    blocks) + cross-K/V projection + prompt + `steps` greedy tokens per window (EOS suppressed so every run decodes the
-    same number of tokens).  CUDA events around the whole pass, inputs resident, 3 batches rotate."""
+    """BASELINE configs[3] end to end: tools/workloads.se_dicow_greedy (the function bench.py's "secondary" runs)"""
+    from bench import ClockSampler
+    from tools import workloads
     dev = torch.device("cuda:0")
-    cfg = turbo_config()
-    cfg.use_enrollments, cfg.scb_layers = True, 8
-    cfg.pad_token_id = cfg.eos_token_id = 50257
-    cfg.decoder_start_token_id = 50258
-    if args.ctc_weight > 0:  # the CTC head of the recipe (configs/base.yaml:5,19-21)
-        cfg.ctc_weight, cfg.additional_self_attention_layer, cfg.pre_ctc_sub_sample = 0.3, True, True
-    with torch.device(dev):
-        model = DiCoWForConditionalGeneration(cfg)
-    from bench import make_inputs, perturb_
-    perturb_(model.get_encoder(), dev)
-    with torch.no_grad():
-        for blk in model.get_encoder().ca_enrolls:
-            blk.cae.cross_gate.gate.fill_(0.5)
-    model.eval()
-    model.use_cuda_graphs = not args.no_graphs
-    model.fused_decode_step = False if args.unfused else ("ln_prologue" if args.ln_prologue else True)
-    B = args.batch
-    batches = []
-    for i in range(3):
-        f, s = make_inputs(2 * B, 20 + i, device=dev)
-        batches.append((f[:B], s[:B], {"input_features": f[B:], "stno_mask": s[B:]}))
-    prompt = torch.tensor([[50258, 50259, 50360]] * B, device=dev)
-    rules = dict(eos=50257, pad=50257, no_timestamps=50364, ts_begin=50365, max_initial_timestamp_index=None,
-                 timestamp_rules=True, suppress_bitmap=model._suppress_bitmap([50257, 220, 50256], dev))
-    n = 3 + args.steps
-    enc = model.get_encoder()
-
-    def decode(hidden):
-        ctc = None
-        if args.ctc_weight > 0:
-            ctc = {"logits": model.get_enc_logits(hidden), "weight": args.ctc_weight, "prefix_len": 3, "bos": 50258}
-        if args.beams > 1:  # configs/decode/se_dicow_beam_joint.yaml: 5 beams, ctc 0.2, length_penalty 0.1
-            return model.beam_decode_window(hidden, prompt, n, rules, num_beams=args.beams, length_penalty=0.1, ctc=ctc)
-        return model.greedy_decode_window(hidden, prompt, n, rules, ctc=ctc)
-
-    def one(i):
-        f, s, e = batches[i % 3]
-        hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
-        return decode(hidden)
-
-    for i in range(3):
-        one(i)
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    reps = 5
-    l0 = ops.launch_count
-    t_enc = t_all = 0.0
-    for i in range(reps):
-        f, s, e = batches[i % 3]
-        ev[0].record()
-        hidden = enc(f, stno_mask=s, enrollments=e).last_hidden_state
-        ev[1].record()
-        ids = decode(hidden)
-        ev[2].record()
-        torch.cuda.synchronize()
-        t_enc += ev[0].elapsed_time(ev[1])
-        t_all += ev[0].elapsed_time(ev[2])
-    ms_all, ms_enc = t_all / reps, t_enc / reps
-    # later windows of a long-form recording: the enrollment stream's keys / values come from the first window
-    caps = []
-    for f, s, e in batches:
-        cap = []
-        enc(f, stno_mask=s, enrollments=e, capture_enrollment_kv=cap)
-        caps.append(cap)
-    for i in range(2):
-        enc(batches[i][0], stno_mask=batches[i][1], enrollment_kv=caps[i])
-    torch.cuda.synchronize()
-    t_cached = 0.0
-    for i in range(reps):
-        f, s, _ = batches[i % 3]
-        ev[0].record()
-        enc(f, stno_mask=s, enrollment_kv=caps[i % 3])
-        ev[1].record()
-        torch.cuda.synchronize()
-        t_cached += ev[0].elapsed_time(ev[1])
-    ms_enc_cached = t_cached / reps
-    gflop_enc = 3577.0  # SURVEY section 8d: SE-DiCoW encoder forward per target utterance
-    print(json.dumps({"metric": "SE-DiCoW greedy decode (BASELINE configs[3]), large-v3-turbo + FDDT + 8 SCB layers",
-                      "batch": B, "beams": args.beams, "ctc_weight": args.ctc_weight, "new_tokens_per_window": args.steps, "ms_per_batch": ms_all, "ms_encoder": ms_enc, "ms_encoder_cached_enrollment_kv": ms_enc_cached,
-                      "ms_decode": ms_all - ms_enc, "utt_per_s": B / (ms_all * 1e-3),
-                      "tokens_per_s": B * args.steps / (ms_all * 1e-3),
-                      "encoder_tflops": B * gflop_enc / ms_enc, "cuda_graphs": model.use_cuda_graphs,
-                      "gpu_launches_per_batch": (ops.launch_count - l0) // reps, "data": "synthetic",
-                      "generated_tail": ids[0, -4:].tolist()}))
+    sampler = ClockSampler(0)
+    sampler.start()
+    out = workloads.se_dicow_greedy(dev, 0, 1, batch=args.batch, new_tokens=args.steps, sampler=sampler, beams=args.beams,
+                                    ctc_weight=args.ctc_weight, graphs=not args.no_graphs,
+                                    fused=False if args.unfused else ("ln_prologue" if args.ln_prologue else True))
+    sampler.stop()
+    print(json.dumps(out))
 
 
 if args.workload == "se_dicow":

@@ -91,7 +91,13 @@ class DiCoWFeatureExtractor:
             target = max(target, max(lengths))
         if pad_to_multiple_of:
             target = -(-target // pad_to_multiple_of) * pad_to_multiple_of
-        target = -(-target // self.hop_length) * self.hop_length
+        if target % self.hop_length:
+            # HF emits floor(target / hop) frames with the STFT's reflect padding taken around the unaligned last sample;
+            # the B200 kernel frames hop-aligned audio only.  The reference recipe pads to a multiple of 30 s
+            # (src/data/local_datasets.py:208-214), so this only refuses callers that would otherwise get one frame more
+            # than HF (and an STNO alignment shifted by it).
+            raise ValueError(f"padded audio length {target} is not a multiple of hop_length={self.hop_length}: pass "
+                             f"pad_to_multiple_of (the reference uses n_samples={self.n_samples})")
         batch = torch.full((len(waves), target), self.padding_value, dtype=torch.float32)
         for i, (w, n) in enumerate(zip(waves, lengths)):
             batch[i, :n] = w[:n].cpu()

@@ -17,7 +17,17 @@ from typing import Dict, Optional
 
 import torch
 from torch import nn
+from dataclasses import dataclass
+
 from transformers.modeling_outputs import BaseModelOutput, CausalLMOutput
+
+
+@dataclass
+class DiCoWCTCOutput(CausalLMOutput):
+    """``DiCoWEncoder.forward(return_logits=True)``: the reference's CausalLMOutput (encoder.py:233-240) -- ``hidden_states``
+    is the CTC neck output it feeds to lm_head ([B, T/4, d] with pre_ctc_sub_sample) -- plus the final-LayerNorm output the
+    reference discards on this path (kept because the joint decoding / training callers here reuse it)."""
+    encoder_last_hidden_state: Optional[torch.FloatTensor] = None
 
 from . import ops
 from .configuration import DiCoWConfig
@@ -475,14 +485,14 @@ class DiCoWEncoder(nn.Module):
                  a_batch_stride=(T1 + 2) * d, ldo=d, out_batch_stride=T2 * d)
         return out
 
-    def ctc_logits_from_hidden(self, hidden_bf16: torch.Tensor, B: int, T: int) -> torch.Tensor:
+    def ctc_logits_from_hidden(self, hidden_bf16: torch.Tensor, B: int, T: int, return_neck: bool = False):
         w = self.prepare()
         neck = self._ctc_neck(w, hidden_bf16, B, T)
         Tp = neck.shape[1]
         V1 = w["lm_head"].shape[0]
         logits = torch.empty(B, Tp, V1, dtype=torch.float32, device=neck.device)
         ops.gemm(neck.view(B * Tp, -1), w["lm_head"], logits.view(B * Tp, V1), epilogue=ops.EPI_BIAS_F32)
-        return logits
+        return (logits, neck) if return_neck else logits
 
     def forward(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, stno_mask=None, return_logits=False, enrollments=None,
@@ -499,9 +509,9 @@ class DiCoWEncoder(nn.Module):
                                               "the fused B200 path")
                 params = [p for p in self.parameters() if p.requires_grad]
                 enr = enrollments or {}
-                logits, hidden = training.EncoderLogitsFn.apply(self, input_features, stno_mask, enr.get("input_features"),
-                                                                enr.get("stno_mask"), *params)
-                return CausalLMOutput(loss=None, logits=logits, hidden_states=hidden)
+                logits, hidden, neck = training.EncoderLogitsFn.apply(self, input_features, stno_mask,
+                                                                      enr.get("input_features"), enr.get("stno_mask"), *params)
+                return DiCoWCTCOutput(loss=None, logits=logits, hidden_states=neck, encoder_last_hidden_state=hidden)
         with torch.no_grad():
             return self._forward_inference(input_features, attention_mask, head_mask, output_attentions,
                                            output_hidden_states, return_dict, stno_mask, return_logits, enrollments,
@@ -635,8 +645,8 @@ class DiCoWEncoder(nn.Module):
         ops.fddt_layernorm(x, gamma=w["lnf_g"], beta=w["lnf_b"], ln_out_f32=out, ln_out_bf16=out_bf16, delta1=d1,
                            delta2=d2, store_x=False)
         if return_logits:  # encoder.py:233-240
-            logits = self.ctc_logits_from_hidden(out_bf16, Bx, T)
-            return CausalLMOutput(loss=None, logits=logits, hidden_states=out)
+            logits, neck = self.ctc_logits_from_hidden(out_bf16, Bx, T, return_neck=True)
+            return DiCoWCTCOutput(loss=None, logits=logits, hidden_states=neck.float(), encoder_last_hidden_state=out)
         if return_dict is False:
             return (out,)
         return BaseModelOutput(last_hidden_state=out)

@@ -116,6 +116,13 @@ class DiCoW(nn.Module):
         self.decoder = DiCoWDecoder(config)
         self._prepared: Optional[dict] = None
         self._prepared_key = None
+        self._prepared_gen = 0  # bumped every time the prepared weights are rebuilt (captured graphs compare it)
+
+    def invalidate_cache(self) -> None:
+        """drop the prepared bf16 weights of the decoder AND the encoder (needed after in-place updates that do not bump
+        ``Parameter._version``: ``p.data.copy_()``, EMA swaps, some sharded-optimizer paths)"""
+        self._prepared = None
+        self.encoder.invalidate_cache()
 
     def get_encoder(self):
         return self.encoder
@@ -154,6 +161,8 @@ class DiCoW(nn.Module):
             e["w2"], e["b2"] = _bf16(lyr.fc2.weight), _f32(lyr.fc2.bias)
             w["layers"].append(e)
         self._prepared, self._prepared_key = w, key
+        self._prepared_gen += 1
+        w["generation"] = self._prepared_gen
         return w
 
     # ---- teacher-forced decoder (training / evaluation forward) -------------------------------------------------
@@ -243,7 +252,7 @@ class _GreedyState:
         self.self_kv = torch.zeros(L, B, self.S_max, 2 * d, **bf)
         # cross-attention cache, head-major [L, B, H, T, k(64) | v(64)]: one contiguous stream per (batch, head) and step
         U = B // beams
-        self.cross_kv = torch.empty(L, U, cfg.decoder_attention_heads, T, 128, **bf)
+        self.cross_kv = torch.zeros(L, U, cfg.decoder_attention_heads, T, 128, **bf)  # (padding rows stay finite)
         self.cross_kv_rows = torch.empty(U * T, 2 * d, **bf)  # the projection GEMM's output before the re-layout
         self.ancestry = None
         if beams > 1:  # beam search: see DiCoWForConditionalGeneration.beam_decode_window
@@ -263,7 +272,52 @@ class _GreedyState:
         self.ctc_key = None
         self.proc = None     # [B, V] processed scores handed from the rules kernel to the joint CTC step
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.weights_id = None  # id() of the prepared-weight dict the graphs were captured with
+        # the prepared-weight dict the graphs were captured with: a STRONG reference compared with ``is`` (an id() of a
+        # freed dict can be handed to a later one, and the graphs would replay with pointers to freed weights)
+        self.weights = None
+        self.ctc_gen = 0  # bumped when the joint-CTC state object is replaced (part of the graph key)
+
+
+_DECODE_BUCKETS = (1, 2, 4, 8, 12, 16, 24, 32, 48, 64)
+
+
+def _bucket_rows(B: int) -> int:
+    """decode-state batch sizes are bucketed: the long-form loop shrinks its batch as recordings finish, and one state
+    (K/V caches, staging rows, captured graphs: ~47 MB x B for large-v3-turbo) per distinct size would pile up"""
+    for b in _DECODE_BUCKETS:
+        if B <= b:
+            return b
+    return B
+
+
+class _DecodeCache:
+    """LRU of _GreedyState objects (at most ``capacity``).  Evicted states drop their buffers and captured graphs.
+    ``copy.deepcopy(model)`` yields an empty cache (CUDA graphs cannot be copied; they are re-captured on demand)."""
+
+    def __init__(self, capacity: int = 3):
+        self.capacity = capacity
+        self.states: "Dict[tuple, _GreedyState]" = {}
+
+    def get(self, key, make):
+        st = self.states.pop(key, None)
+        if st is None:
+            while len(self.states) >= self.capacity:
+                old = self.states.pop(next(iter(self.states)))
+                old.graphs.clear()
+            st = make()
+        self.states[key] = st  # most recently used last
+        return st
+
+    def clear(self) -> None:
+        for st in self.states.values():
+            st.graphs.clear()
+        self.states.clear()
+
+    def __len__(self):
+        return len(self.states)
+
+    def __deepcopy__(self, memo):
+        return _DecodeCache(self.capacity)
 
 
 class DiCoWForConditionalGeneration(PreTrainedModel):
@@ -291,7 +345,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         self.stno_mask = None
         self.stno_mask_seek = None
         self.soft_label_creator = None
-        self._greedy: Dict[tuple, _GreedyState] = {}
+        self._greedy = _DecodeCache()
         self.post_init()
         self.tie_weights()
         if getattr(self, "generation_config", None) is None:
@@ -377,6 +431,26 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
     def freeze_encoder(self):
         for p in self.model.encoder.parameters():
             p.requires_grad_(False)
+
+    def clear_decode_cache(self) -> None:
+        """free the decode states (self / cross K/V caches, staging rows, captured CUDA graphs) kept between generate() calls"""
+        self._greedy.clear()
+
+    def invalidate_prepared(self) -> None:
+        """drop every prepared bf16 weight copy and everything captured against them; call after updating parameters in a
+        way that does not bump ``Parameter._version`` (``p.data.copy_()``, EMA weight swaps, offload / sharded optimizers)"""
+        self.model.invalidate_cache()
+        self.clear_decode_cache()
+
+    def train(self, mode: bool = True):
+        if mode:  # a training phase follows: the decode states (tens of MB per row) are dead weight until the next eval
+            self.clear_decode_cache()
+        return super().train(mode)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.invalidate_prepared()
+        return out
 
     # ---- reference API -------------------------------------------------------------------------------------
     def set_tokenizer(self, tokenizer):  # modeling_dicow.py:237-240
@@ -577,18 +651,16 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             raise NotImplementedError(f"beam search over {U} windows x {NB} beams = {B} hypotheses: at most 64 per call")
         w = self.model.prepare_decoder()
         key = (dev.index, B, T, NB)
-        st = self._greedy.get(key)
-        if st is None:
-            st = self._greedy[key] = _GreedyState(self, B, T, dev, beams=NB)
+        st = self._greedy.get(key, lambda: _GreedyState(self, B, T, dev, beams=NB))
         enc_bf16 = enc_hidden if enc_hidden.dtype == torch.bfloat16 else ops.cast_bf16(enc_hidden.float())
         encf = enc_bf16.reshape(U * T, d)
         H = cfg.decoder_attention_heads
         for li, e in enumerate(w["layers"]):
             ops.gemm(encf, e["cross"]["wkv"], st.cross_kv_rows, epilogue=ops.EPI_BIAS_BF16, bias=e["cross"]["bkv"])
             ops.kv_to_head_major(st.cross_kv_rows, st.cross_kv[li], B=U, T=T, H=H)
-        if st.weights_id != id(w):
+        if st.weights is not w:
             st.graphs.clear()
-            st.weights_id = id(w)
+            st.weights = w
         # ---- state of a new window (generation.py:940-975) ----
         st.ids.zero_()
         st.ids[:, :P] = prompt.to(device=dev, dtype=torch.int64).repeat_interleave(NB, dim=0)
@@ -614,10 +686,11 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 st.ctc = ops.CtcJointState(lg, top_k=k_eff, upper_cased=ctc.get("upper_cased"))
                 st.ctc_key = ckey
                 st.ctc_r_tmp = torch.empty_like(st.ctc.r_prev)
+                st.ctc_gen += 1
                 st.graphs.clear()
             else:
                 st.ctc.reset(lg)
-            gen["ctc"] = {"weight": float(ctc["weight"]), "state": id(st.ctc)}
+            gen["ctc"] = {"weight": float(ctc["weight"]), "state": st.ctc_gen}
         elif st.cand is None or st.cand.K != k_eff:
             st.cand = ops.CandidateState(B, k_eff, dev)
             st.graphs.clear()
@@ -714,25 +787,38 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         P = prompt.shape[1]
         max_total_len = min(max_total_len, cfg.max_target_positions)
         w = self.model.prepare_decoder()
-        if B > 64:
-            raise NotImplementedError("decode batch above 64 windows: split the batch")
-        key = (dev.index, B, T)
-        st = self._greedy.get(key)
-        if st is None:
-            st = self._greedy[key] = _GreedyState(self, B, T, dev)
+        if B > 64:  # the step kernels stage at most 64 rows: larger batches decode in chunks of 64 windows
+            outs, firsts = [], []
+            for lo in range(0, B, 64):
+                sl = slice(lo, min(B, lo + 64))
+                sub = None if ctc is None else dict(ctc, logits=ctc["logits"][sl])
+                r = self.greedy_decode_window(enc_hidden[sl], prompt[sl], max_total_len, gen, return_first_logits, sub)
+                outs.append(r[0] if return_first_logits else r)
+                if return_first_logits:
+                    firsts.append(r[1])
+            n = max(o.shape[1] for o in outs)
+            ids = torch.cat([torch.nn.functional.pad(o, (0, n - o.shape[1]), value=int(gen["pad"])) for o in outs], dim=0)
+            return (ids, torch.cat(firsts, dim=0)) if return_first_logits else ids
+        # rows of the decode state: B rounded up to a bucket (padding rows start finished and decode nothing that is read)
+        Bs = B if ctc is not None else _bucket_rows(B)
+        key = (dev.index, Bs, T)
+        st = self._greedy.get(key, lambda: _GreedyState(self, Bs, T, dev))
         enc_bf16 = enc_hidden if enc_hidden.dtype == torch.bfloat16 else ops.cast_bf16(enc_hidden.float())
         encf = enc_bf16.reshape(B * T, d)
         H = cfg.decoder_attention_heads
         for li, e in enumerate(w["layers"]):  # cross-attention K/V once per window (HF caches them after step 0)
-            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv_rows, epilogue=ops.EPI_BIAS_BF16, bias=e["cross"]["bkv"])
+            ops.gemm(encf, e["cross"]["wkv"], st.cross_kv_rows[:B * T], epilogue=ops.EPI_BIAS_BF16, bias=e["cross"]["bkv"])
             ops.kv_to_head_major(st.cross_kv_rows, st.cross_kv[li], B=B, T=T, H=H)
-        if st.weights_id != id(w):  # parameters changed since capture: the graphs hold stale weight pointers
+        if st.weights is not w:  # parameters changed since capture: the graphs hold stale weight pointers
             st.graphs.clear()
-            st.weights_id = id(w)
+            st.weights = w
         st.ids.zero_()
-        st.ids[:, :P] = prompt.to(device=dev, dtype=torch.int64)
+        st.ids[:B, :P] = prompt.to(device=dev, dtype=torch.int64)
         st.pos.zero_()
         st.unfinished.fill_(1)
+        if Bs > B:
+            st.ids[B:, :P] = st.ids[:1, :P]
+            st.unfinished[B:] = 0
         gen = dict(gen, begin_index=P)
         if ctc is not None:
             lg = ctc["logits"].float().contiguous()
@@ -741,11 +827,12 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 st.ctc = ops.CtcJointState(lg, top_k=ckey[1], upper_cased=ctc.get("upper_cased"))
                 st.ctc_key = ckey
                 st.proc = torch.empty(B, cfg.vocab_size, dtype=torch.float32, device=dev)
+                st.ctc_gen += 1
                 st.graphs.clear()
             else:
                 st.ctc.reset(lg)
             gen["ctc"] = {"bos": int(ctc["bos"]), "prefix_len": int(ctc["prefix_len"]), "weight": float(ctc["weight"]),
-                          "state": id(st.ctc)}
+                          "state": st.ctc_gen}
 
         def run(sample: bool):
             if not self.use_cuda_graphs:
@@ -775,11 +862,11 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         for step in range(n_new):
             run(True)
             if step == 0 and return_first_logits:
-                first_logits = st.logits.clone()
+                first_logits = st.logits[:B].clone()
             if (step & 7) == 7 and not bool(st.unfinished.any().item()):  # host check every 8 tokens only
                 n_new = step + 1
                 break
-        ids = st.ids[:, :P + n_new].clone()
+        ids = st.ids[:B, :P + n_new].clone()
         # rows that finished early were padded by the kernel; trim columns that are padding for every row
         return (ids, first_logits) if return_first_logits else ids
 

@@ -955,11 +955,12 @@ class EncoderLogitsFn(torch.autograd.Function):
                                                         _enrollments(enr_features, enr_stno))
             logits = ctc_head_forward_train(enc, hidden_bf16, B, T, tape)
         ctx.enc, ctx.tape, ctx.body, ctx.params = enc, tape, body, params
-        ctx.mark_non_differentiable(hidden)
-        return logits, hidden
+        neck = tape.ctc["neck"].float()  # what the reference returns as hidden_states (encoder.py:233-240)
+        ctx.mark_non_differentiable(hidden, neck)
+        return logits, hidden, neck
 
     @staticmethod
-    def backward(ctx, grad_logits, _grad_hidden):
+    def backward(ctx, grad_logits, _grad_hidden, _grad_neck):
         enc, tape = ctx.enc, ctx.tape
         g = _Grads(gradient_exchange)
         with torch.no_grad():
