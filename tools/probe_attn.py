@@ -49,7 +49,7 @@ def run(B, H, T, variant, iters=10):
 
 
 if __name__ == "__main__":
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         try:
             run(32, 20, 1500, variant)
         except Exception as ex:  # noqa: BLE001

@@ -403,9 +403,9 @@ extern "C" int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args
   // variant 0..3: ping-pong kernel (attention_fa.cu) with {2, 0, 4, 6} of every 8 exponentials on the FMA pipe.
   // variant 16 + v: the single-tile kernel of this file, kept for comparison -- v bits: [0] P through shared memory;
   // [1..2] poly-exp2 share: 0 -> 2/8, 1 -> 0/8, 2 -> 3/8, 3 -> 4/8; [3] single pass (hold the S row in registers)
-  DICOW_REQUIRE(ctx, a->lse == nullptr || (a->variant >= 0 && a->variant <= 3),
+  DICOW_REQUIRE(ctx, a->lse == nullptr || (a->variant >= 0 && a->variant <= 4),
                 "dicow_attention_bf16: the lse output needs the default kernel");
-  if (a->variant >= 0 && a->variant <= 3) return launch_attention_fa(ctx, tmQ, tmK, tmV, p, a->variant, stream);
+  if (a->variant >= 0 && a->variant <= 4) return launch_attention_fa(ctx, tmQ, tmK, tmV, p, a->variant, stream);
   switch (a->variant - 16) {
     case 0: return launch_attention<false, 2, true>(ctx, tmQ, tmK, tmV, p, stream);
     case 1: return launch_attention<true, 2, true>(ctx, tmQ, tmK, tmV, p, stream);

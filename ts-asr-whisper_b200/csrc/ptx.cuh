@@ -58,6 +58,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// two exponentials per SFU operation: packed bf16 in, packed bf16 out (the probabilities are rounded to bf16 for the P V
+// MMA anyway, so the packed result IS the operand)
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+// the two bf16 halves of a packed word as fp32 (exact: bf16 is the upper half of an fp32)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
 // Blackwell packed fp32 arithmetic (two lanes per instruction on the FMA pipe): halves the issue slots of the
 // softmax scale/offset and row-sum
 __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
