@@ -187,8 +187,10 @@ typedef struct {
   int64_t kv_row_stride, kv_batch_stride;
   int64_t o_row_stride, o_batch_stride;
   int32_t causal;
-  int32_t variant; /* 0 = default (two query tiles per CTA in ping-pong, 2 of every 8 exponentials evaluated as a
-                      polynomial on the FMA pipe); 1, 2, 3 = same with 0, 4, 6 of 8; 16+ = single-tile comparison kernels */
+  int32_t variant; /* 0 = default (persistent CTAs, two query tiles per CTA in ping-pong, every exponential on the SFU: the
+                      lowest energy per launch, which is what a power-capped step pays); 1, 2, 3 = 2, 4, 6 of every 8
+                      exponentials as a polynomial on the FMA pipe; 4 = packed bf16 exponentials; 16+ = single-tile
+                      comparison kernels */
   float* lse;      /* optional [B, H, Tq] fp32: log2(sum_k 2^(s_k log2 e)) per query row, saved for dicow_attention_bwd_bf16 */
 } dicow_attention_args_t;
 

@@ -400,7 +400,7 @@ extern "C" int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args
   p.prof = reinterpret_cast<long long*>(ctx->attn_prof);
   p.lse = a->lse;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  // variant 0..3: ping-pong kernel (attention_fa.cu) with {2, 0, 4, 6} of every 8 exponentials on the FMA pipe.
+  // variant 0..3: ping-pong kernel (attention_fa.cu) with {0, 2, 4, 6} of every 8 exponentials on the FMA pipe; 4: packed bf16.
   // variant 16 + v: the single-tile kernel of this file, kept for comparison -- v bits: [0] P through shared memory;
   // [1..2] poly-exp2 share: 0 -> 2/8, 1 -> 0/8, 2 -> 3/8, 3 -> 4/8; [3] single pass (hold the S row in registers)
   DICOW_REQUIRE(ctx, a->lse == nullptr || (a->variant >= 0 && a->variant <= 4),

@@ -509,11 +509,15 @@ int launch(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmK, const
 int launch_attention_fa(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                         const AttnParams& p, int emu, cudaStream_t stream) {
   switch (emu) {
-    case 0: return launch<2>(ctx, tmQ, tmK, tmV, p, stream);   // default: fp32 exponentials, 2 of 8 on the FMA pipe
+    // default: every exponential on the SFU.  Measured by looping each variant alone for 2 s at the bench shape (NVML energy
+    // counter, tools/energy_probe.py; every variant draws the ~1 kW board cap, so inside the power-capped encoder step a
+    // launch costs its JOULES, not its isolated time): EMU 0 = 500 mJ / launch, EMU 2 = 509 mJ (0.4 % faster alone at
+    // burst clocks, 2 % more energy), EMU 4 = 544 mJ, packed-bf16 exponentials = 579 mJ.
+    case 0: return launch<0>(ctx, tmQ, tmK, tmV, p, stream);
+    case 1: return launch<2>(ctx, tmQ, tmK, tmV, p, stream);   // 2 of 8 exponentials as a polynomial on the FMA pipe
     // packed bf16 exponentials: ptxas 12.9 lowers ex2.approx.ftz.bf16x2 to TWO MUFU.EX2.BF16 (+ PRMT) on sm_100a, so there
     // is no 2-per-SFU-op gain; kept as a measured variant
     case 4: return launch<-1>(ctx, tmQ, tmK, tmV, p, stream);
-    case 1: return launch<0>(ctx, tmQ, tmK, tmV, p, stream);
     case 2: return launch<4>(ctx, tmQ, tmK, tmV, p, stream);
     case 3: return launch<6>(ctx, tmQ, tmK, tmV, p, stream);
     default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_attention_bf16: bad poly-exp share %d", emu);
