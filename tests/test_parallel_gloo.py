@@ -67,6 +67,59 @@ def test_two_rank_gloo():
         assert torch.allclose(grads[2], torch.full((2, 2), 3.0 * (rank + 1)))  # frozen parameter: left alone
 
 
+def _ddp_worker(rank: int, world: int, port: int, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import dataclasses
+
+    from oracle import synth
+    from ts_asr_whisper_b200 import parallel, training
+    from ts_asr_whisper_b200.configuration import DiCoWConfig
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    dm = dataclasses.replace(synth.GOLDEN_MINI, use_enrollments=False, scb_layers=0)
+    torch.manual_seed(100 + rank)  # DIFFERENT initial weights per rank: the broadcast has to repair that
+    model = DiCoWForConditionalGeneration(DiCoWConfig(**dm.hf_kwargs()))
+    assert model._ddp_params_and_buffers_to_ignore == []  # no process group yet: nothing changes
+    parallel.init_process_group("gloo")
+    for n, p in model.named_parameters():
+        p.requires_grad_("fddt" in n)  # the recipe's warm-up phase: FDDT tables only
+    ddp = torch.nn.parallel.DistributedDataParallel(model)  # what accelerate does for HF Trainer
+    names = [n for n, _ in model.named_parameters()]
+    managed = [n for n in names if n not in ddp.parameters_to_ignore]
+    ex = training.gradient_exchange
+    before = model.model.decoder.layers[0].fc1.weight.detach().clone()
+    ex.ensure_synced(model)
+    ex.ensure_synced(model)  # idempotent
+    after = model.model.decoder.layers[0].fc1.weight.detach().clone()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, after.sum().item())
+    parallel.barrier()
+    q.put((rank, managed, isinstance(ex, parallel.GradientExchange) and ex.active, bool((before != after).any()), gathered,
+           [n for n, p in model.named_parameters() if p.requires_grad and n in managed]))
+    dist.destroy_process_group()
+
+
+def test_ddp_wrapper_leaves_the_gradients_to_the_overlapped_exchange():
+    """torch DDP around the model (HF Trainer / accelerate, the reference's launch) is told to ignore every parameter but
+    one small trainable one; the GradientExchange is installed for the hand-scheduled backward, and the parameters DDP no
+    longer broadcasts are synchronised from rank 0 by the exchange itself"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, managed, active, changed, sums, managed_trainable in res:
+        assert len(managed) == 1 and "fddt" in managed[0] and managed_trainable == managed
+        assert active
+        assert changed == (rank != 0)        # rank 1 had different weights before the broadcast
+        assert sums[0] == sums[1]            # ... and the same afterwards
+
+
 def test_shard_range_partitions():
     from ts_asr_whisper_b200.parallel import shard_range
     for n in (0, 1, 7, 32, 33):

@@ -167,7 +167,7 @@ def train_step(workload: str, dev, rank: int, world: int, steps: int = 5, warmup
         if state["exchange"] and not overlap:
             parallel.allreduce_gradients(params)
         opt.step()
-        state["loss"] = loss
+        state["loss"] = loss.detach()
 
     try:
         for i in range(max(3, warmup)):

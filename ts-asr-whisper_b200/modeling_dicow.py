@@ -432,6 +432,13 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         for p in self.model.encoder.parameters():
             p.requires_grad_(False)
 
+    @property
+    def _ddp_params_and_buffers_to_ignore(self):
+        """read by torch DistributedDataParallel when it wraps the model: see parallel.ddp_ignore_list (the per-layer
+        gradient exchange overlapped with the backward replaces DDP's end-of-backward all-reduce)"""
+        from . import parallel
+        return parallel.ddp_ignore_list(self)
+
     def clear_decode_cache(self) -> None:
         """free the decode states (self / cross K/V caches, staging rows, captured CUDA graphs) kept between generate() calls"""
         self._greedy.clear()

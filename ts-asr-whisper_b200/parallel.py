@@ -106,11 +106,31 @@ class GradientExchange:
 
     def __init__(self, group=None):
         self.group = group
-        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self._active: Optional[bool] = None  # decided at first use: the process group may be created after this object
         self.stream: Optional[torch.cuda.Stream] = None
         self.n_collectives = 0
         self.bytes = 0
         self._pending: List = []
+        self._synced: set = set()
+
+    @property
+    def active(self) -> bool:
+        if self._active is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                return False  # not decided yet
+            self._active = dist.get_world_size(self.group) > 1
+        return self._active
+
+    def ensure_synced(self, module: torch.nn.Module) -> None:
+        """Once per module: broadcast every parameter and buffer from rank 0.  A DistributedDataParallel wrapper does this
+        for the tensors it manages; the parameters this exchange takes off its hands (ddp_ignore_list) are not among them."""
+        if not self.active or id(module) in self._synced:
+            return
+        self._synced.add(id(module))
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                               group=self.group)
 
     def bucket_ready(self, flat: torch.Tensor) -> None:
         if not self.active or flat.numel() == 0:
@@ -140,3 +160,31 @@ class GradientExchange:
             work.wait()
             flat.div_(world)
         self._pending = []
+
+
+def ddp_overlap_enabled() -> bool:
+    return os.environ.get("DICOW_DDP_OVERLAP", "1") != "0"
+
+
+def ddp_ignore_list(model: torch.nn.Module) -> List[str]:
+    """What ``DiCoWForConditionalGeneration._ddp_params_and_buffers_to_ignore`` answers when torch
+    DistributedDataParallel (HF Trainer -> accelerate, the reference's launch: scripts/submit_slurm.sh:34) wraps the model.
+
+    The training step is ONE autograd node (training.DiCoWTrainStepFn): all gradients reach autograd together at the end of
+    its backward, so DDP's bucketed all-reduce would start only then -- 2.9 GB of exposed communication per fine-tune step.
+    Instead the hand-scheduled backward hands each finished layer's flat gradient bucket to a GradientExchange while the
+    earlier layers are still being differentiated (installed here as ``training.gradient_exchange``), and DDP is told to
+    leave those parameters alone.  DDP insists on managing at least one trainable parameter: the smallest trainable one
+    stays with it (it is averaged twice -- the same value).  Single-process runs and DICOW_DDP_OVERLAP=0 return [] and
+    change nothing."""
+    if not ddp_overlap_enabled() or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return []
+    from . import training
+    if training.gradient_exchange is None:
+        training.gradient_exchange = GradientExchange()
+    named = list(model.named_parameters())
+    trainable = [(p.numel(), n) for n, p in named if p.requires_grad]
+    if not trainable:
+        return []
+    keep = min(trainable)[1]
+    return [n for n, _ in named if n != keep]

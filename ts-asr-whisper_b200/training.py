@@ -948,6 +948,8 @@ class EncoderLogitsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, input_features, stno_mask, enr_features, enr_stno, *params):
+        if gradient_exchange is not None:
+            gradient_exchange.ensure_synced(enc)
         tape = EncoderTape()
         body = _body_trainable(enc)
         with torch.no_grad():
@@ -1002,6 +1004,8 @@ class DiCoWTrainStepFn(torch.autograd.Function):
     def forward(ctx, model, input_features, stno_mask, decoder_input_ids, labels, upp_labels, enc_labels, enr_features,
                 enr_stno, *params):
         cfg = model.config
+        if gradient_exchange is not None:
+            gradient_exchange.ensure_synced(model)
         enc = model.model.get_encoder()
         etape, dtape = EncoderTape(), DecoderTape()
         # the encoder states receive a gradient from the decoder's cross-attention whenever the body trains
