@@ -45,6 +45,7 @@ struct GemmParams {
   const float* pos;
   __nv_bfloat16* aux;  // [.., N] bf16, leading dimension ldo: pre-activation saved by GELU_SAVE / read by DGELU
   int serial_drain;    // 1 (default): one chunk at a time, accumulator handed back after the last store; 0: pipelined
+  int tma_out;         // CTA-pair kernel, bf16 outputs: drain through swizzled shared memory + cp.async.bulk.tensor stores
 };
 
 template <int BN>
@@ -261,6 +262,77 @@ __device__ __forceinline__ void drain_accumulator(const GemmParams& p, uint32_t 
   }
 }
 
+// ---- drain one accumulator through shared memory + TMA stores (CTA-pair kernel, bf16 outputs) ----------------------------
+// Each epilogue warp owns 32 accumulator rows x (BN / 2) columns.  Two 32-column chunks at a time go
+// TMEM -> registers -> bias (/ GELU) -> bf16 -> a [32 rows x 64 columns] tile in shared memory laid out as the output tensor
+// map's 128B-swizzled box (16-byte chunk index XOR row % 8: the 8 threads of a store phase hit 8 different bank groups), then
+// ONE cp.async.bulk.tensor store writes the 4 KB tile as full 128-byte lines.  The per-thread st.global.v4 path it replaces
+// touched 32 different lines per store instruction, 16 bytes each (8 partial writes per line).  The warp's two staging
+// tiles alternate; a tile is reused once the bulk group that reads it has finished reading (wait_group.read 1).
+// Rows / columns beyond the tensor are clipped by the TMA unit.
+template <int EPI, int NCH, typename Release>
+__device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const CUtensorMap* tmO, uint8_t* stage_base,
+                                                      uint32_t taddr, int b, int m_warp, int n_base, int lane, Release release) {
+  static_assert(NCH % 2 == 0, "pairs of 32-column chunks");
+  int nvalid = (p.N - n_base + 31) / 32;  // warp-uniform
+  nvalid = nvalid > NCH ? NCH : nvalid;
+  if (nvalid <= 0) {
+    release();
+    return;
+  }
+#pragma unroll 1
+  for (int pair = 0; pair * 2 < nvalid; ++pair) {
+    uint8_t* stage = stage_base + (pair & 1) * 4096;
+    if (lane == 0) bulk_wait_group_read<1>();  // the store issued two pairs ago has read this tile
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = pair * 2 + h;
+      if (c < nvalid) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c * 32, r);
+        tmem_ld_wait_regs(r);
+        if (c == nvalid - 1) release();  // last chunk in registers: the MMA warp may overwrite the accumulator
+        const int n = n_base + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+          }
+        }
+        if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        }
+        uint8_t* row = stage + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16(v[8 * j], v[8 * j + 1]), q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]), q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(row + (((h * 4 + j) ^ (lane & 7)) << 4)) = q;
+        }
+      }
+    }
+    fence_proxy_async_smem();  // the generic-proxy writes above -> visible to the TMA (async proxy) read
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmO, stage, n_base + pair * 64, m_warp, b);
+      bulk_commit_group();
+    }
+  }
+}
+
 // A_MN / B_MN: the operand is given transposed in memory (At[k][m] / Wt[k][n], contraction index on the rows) and is
 // consumed MN-major: the stage holds 64 x 64 atoms ([64 contraction rows] x [64 output elements = 128 B], 8 KB each, one
 // TMA box per atom), descriptors use SBO = 1024 (8 contraction rows), LBO = 8192 (next 64-element atom).  This is what
@@ -438,18 +510,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct GemmCfg2 {
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 5;  // (6 before the epilogue staging tiles took 64 KB)
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t BAR_BYTES = 1024;                      // barriers + TMEM slot, keeps the staging tiles 1024-aligned
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 2 * 4096;      // per epilogue warp: two [32 x 64] bf16 staging tiles
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                      const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using Cfg = GemmCfg2<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -471,6 +545,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if (p.K1 > 0) tma_prefetch_desc(&tmA2);
+    if (p.tma_out) tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -579,12 +654,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + half * (BN / 2);
       const uint32_t tempty_remote = map_to_cta(smem_u32(&tempty_bar[acc]), 0);
-      drain_accumulator<EPI, BN / 64>(p, taddr, b, m, n_base, row_ok, mask, [&] {
+      auto release = [&] {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(tempty_remote);
-      });
+      };
+      if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16) {
+        if (p.tma_out) {
+          uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + e * 2 * 4096;
+          drain_accumulator_tma<EPI, BN / 64>(p, &tmO, stage, taddr, b, m - lane, n_base, lane, release);
+          continue;
+        }
+      }
+      drain_accumulator<EPI, BN / 64>(p, taddr, b, m, n_base, row_ok, mask, release);
     }
+    if (p.tma_out && lane == 0) bulk_wait_group<0>();  // shared memory must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -614,7 +698,7 @@ int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2,
 
 template <int BN, int EPI>
 int launch_gemm_2cta(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
-                     const GemmParams& p, cudaStream_t stream) {
+                     const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg2<BN>;
   auto kfn = gemm_bf16_2cta_kernel<BN, EPI>;
   static bool attr_done = false;  // per instantiation
@@ -623,20 +707,20 @@ int launch_gemm_2cta(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
     attr_done = true;
   }
   int grid = 2 * (p.total_tiles < ctx->num_sms / 2 ? p.total_tiles : ctx->num_sms / 2);
-  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, p);
+  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, tmO, p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }
 
 int dispatch_epi_2cta(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
-                      const GemmParams& p, cudaStream_t stream) {
+                      const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
   switch (epi) {
-    case DICOW_EPI_BIAS_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_BF16>(ctx, tmA, tmA2, tmW, p, stream);
-    case DICOW_EPI_BIAS_GELU_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_GELU_BF16>(ctx, tmA, tmA2, tmW, p, stream);
-    case DICOW_EPI_RESIDUAL_F32: return launch_gemm_2cta<256, DICOW_EPI_RESIDUAL_F32>(ctx, tmA, tmA2, tmW, p, stream);
-    case DICOW_EPI_BIAS_F32: return launch_gemm_2cta<256, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+    case DICOW_EPI_BIAS_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_BF16>(ctx, tmA, tmA2, tmW, tmO, p, stream);
+    case DICOW_EPI_BIAS_GELU_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_GELU_BF16>(ctx, tmA, tmA2, tmW, tmO, p, stream);
+    case DICOW_EPI_RESIDUAL_F32: return launch_gemm_2cta<256, DICOW_EPI_RESIDUAL_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
+    case DICOW_EPI_BIAS_F32: return launch_gemm_2cta<256, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
     case DICOW_EPI_GELU_FDDT_POS_F32:
-      return launch_gemm_2cta<256, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, p, stream);
+      return launch_gemm_2cta<256, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
     default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: unknown epilogue %d", epi);
   }
 }
@@ -814,7 +898,26 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
     if (BN == 256) return dispatch_transposed<256>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
     return dispatch_transposed<128>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
   }
-  if (two_cta) return dispatch_epi_2cta(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
+  if (two_cta) {
+    // output tensor map for the TMA-store epilogue: [N, Mb, nb] bf16, box 64 columns x 32 rows (one epilogue warp's tile)
+    CUtensorMap tmO = tmA;
+    static const int tma_store = [] {
+      const char* e = getenv("DICOW_GEMM_TMA_STORE");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    const bool bf16_plain = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16;
+    if (tma_store && bf16_plain && (a->ldo % 8) == 0 && (a->out_batch_stride % 8) == 0 &&
+        (reinterpret_cast<uintptr_t>(a->out) % 16) == 0 && (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) % 16) == 0)) {
+      uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->Mb, (uint64_t)a->nb};
+      uint64_t bs = a->nb > 1 ? (uint64_t)a->out_batch_stride : (uint64_t)a->ldo * (uint64_t)a->Mb;
+      uint64_t strides[2] = {(uint64_t)a->ldo * 2, bs * 2};
+      uint32_t box[3] = {64, 32, 1};
+      int rc = make_tmap_bf16(ctx, &tmO, a->out, 3, dims, strides, box);
+      if (rc) return rc;
+      p.tma_out = 1;
+    }
+    return dispatch_epi_2cta(ctx, a->epilogue, tmA, tmA2, tmW, tmO, p, stream);
+  }
   if (BN == 256) return dispatch_epi<256>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
   return dispatch_epi<128>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
 }
