@@ -165,6 +165,17 @@ def fddt(x: torch.Tensor, stno: torch.Tensor, w: Optional[torch.Tensor], b: torc
 # ----------------------------------------------------------------------------------------------------------------
 # A8  attention / encoder layer (third-party HF:models/whisper/modeling_whisper.py)
 # ----------------------------------------------------------------------------------------------------------------
+def lora_linear(p: Params, name: str, x: torch.Tensor, bias: bool = True) -> torch.Tensor:
+    """nn.Linear ``name``, with a LoRA adapter when the dict holds one: y = x W^T + b + (alpha / r) * (x A^T) B^T
+    (peft.tuners.lora.layer.Linear.forward, third-party peft -- not in this image; the reference's use:
+    src/models/containers.py:69-78, r = 16, lora_alpha = 32, dropout 0, bias "none", decoder q/k/v/out_proj/fc1/fc2).
+    Keys: ``name + ".lora_A"`` [r, in], ``name + ".lora_B"`` [out, r], optional ``"lora_scale"`` (default alpha / r = 2)."""
+    y = F.linear(x, p[name + ".weight"], p.get(name + ".bias") if bias else None)
+    if (name + ".lora_A") in p:
+        y = y + float(p.get("lora_scale", 2.0)) * F.linear(F.linear(x, p[name + ".lora_A"]), p[name + ".lora_B"])
+    return y
+
+
 def attention(p: Params, prefix: str, x_q: torch.Tensor, x_kv: torch.Tensor, heads: int, causal: bool = False
               ) -> torch.Tensor:
     """HF:modeling_whisper.py:284-357: q = (x Wq + bq) * hd^-0.5 scaled BEFORE QK^T, k has no bias, softmax over
@@ -172,15 +183,15 @@ def attention(p: Params, prefix: str, x_q: torch.Tensor, x_kv: torch.Tensor, hea
     B, Tq, d = x_q.shape
     Tk = x_kv.shape[1]
     hd = d // heads
-    q = F.linear(x_q, p[prefix + ".q_proj.weight"], p[prefix + ".q_proj.bias"]) * (hd ** -0.5)
-    k = F.linear(x_kv, p[prefix + ".k_proj.weight"])
-    v = F.linear(x_kv, p[prefix + ".v_proj.weight"], p[prefix + ".v_proj.bias"])
+    q = lora_linear(p, prefix + ".q_proj", x_q) * (hd ** -0.5)
+    k = lora_linear(p, prefix + ".k_proj", x_kv, bias=False)
+    v = lora_linear(p, prefix + ".v_proj", x_kv)
     q = q.view(B, Tq, heads, hd).transpose(1, 2)
     k = k.view(B, Tk, heads, hd).transpose(1, 2)
     v = v.view(B, Tk, heads, hd).transpose(1, 2)
     o = F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=1.0)
     o = o.transpose(1, 2).reshape(B, Tq, d)
-    return F.linear(o, p[prefix + ".out_proj.weight"], p[prefix + ".out_proj.bias"])
+    return lora_linear(p, prefix + ".out_proj", o)
 
 
 def layer_norm(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
@@ -317,8 +328,8 @@ def decoder_forward(p: Params, dm: Dims, input_ids: torch.Tensor, enc: torch.Ten
         h = layer_norm(p, pre + ".encoder_attn_layer_norm", x)
         x = x + attention(p, pre + ".encoder_attn", h, enc, dm.dec_heads)
         h = layer_norm(p, pre + ".final_layer_norm", x)
-        h = F.gelu(F.linear(h, p[pre + ".fc1.weight"], p[pre + ".fc1.bias"]))
-        x = x + F.linear(h, p[pre + ".fc2.weight"], p[pre + ".fc2.bias"])
+        h = F.gelu(lora_linear(p, pre + ".fc1", h))
+        x = x + lora_linear(p, pre + ".fc2", h)
     return layer_norm(p, dd + ".layer_norm", x)
 
 

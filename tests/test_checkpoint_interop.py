@@ -128,6 +128,59 @@ def test_whisper_container_and_optimizer(saved):
     assert get_optimizer(c.model, types.SimpleNamespace(use_custom_optimizer=False)) is None
 
 
+def test_lora_adapters_like_the_reference_container(saved):
+    """WhisperContainer(use_lora=True) (src/models/containers.py:69-90): rank-16 adapters on the decoder's q/k/v/out_proj/
+    fc1/fc2, base model frozen, "lora_" parameters always trainable, B = 0 so the adapted model starts as the base model;
+    adapter export in peft's key format round-trips; merging folds W + (alpha / r) B A into the base weight"""
+    import types
+    d, sd0, cls, dm = saved
+    from ts_asr_whisper_b200.containers import WhisperContainer
+    from ts_asr_whisper_b200.modeling_dicow import effective_weight
+
+    class Tok:
+        prefix_tokens = [258, 259, 260]
+        pad_token_id = 257
+
+        def set_prefix_tokens(self, **kw):
+            pass
+
+        def get_vocab(self):
+            return {f"<|{0.02 * i:.2f}|>": 262 + i for i in range(38)}
+
+    margs = types.SimpleNamespace(whisper_model=d, ctc_weight=0.3, fddt_is_diagonal=True, fddt_bias_only=False,
+                                  fddt_use_silence=True, fddt_use_target=True, fddt_use_overlap=True, fddt_use_non_target=True,
+                                  apply_fddt_to_n_layers=-1, fddt_init="suppressive", non_target_fddt_value=0.5,
+                                  use_pre_pos_fddt=True, pre_ctc_sub_sample=True, additional_layer=False,
+                                  additional_self_attention_layer=True, scb_layers=None)
+    dargs = types.SimpleNamespace(use_timestamps=True, global_lang_id="en", use_enrollments=False)
+    c = WhisperContainer(model_args=margs, data_args=dargs, use_fddt=True, use_lora=True,
+                         params_to_keep_frozen_keywords=["decoder", "embed_positions"], tokenizer=Tok(), feature_extractor=object())
+    m = c.model
+    lora = [n for n, _ in m.named_parameters() if "lora_" in n]
+    assert len(lora) == 2 * 10 * dm.dec_layers and all(".decoder." in n for n in lora)
+    named = dict(m.named_parameters())
+    assert all(named[n].requires_grad for n in lora)
+    assert all(not p.requires_grad for n, p in named.items() if "decoder" in n and "lora_" not in n)
+    assert any(p.requires_grad for n, p in named.items() if n.startswith("model.encoder.layers"))
+    q = m.model.decoder.layers[0].self_attn.q_proj
+    assert q.lora_A.shape == (16, dm.d) and q.lora_B.shape == (dm.d, 16) and q.lora_scale == 2.0
+    assert float(q.lora_B.abs().max()) == 0.0 and torch.equal(effective_weight(q), q.weight.detach().float())
+    with torch.no_grad():
+        for n in lora:
+            named[n].normal_(0.0, 0.05)
+    sd = m.lora_state_dict()
+    assert "base_model.model.model.decoder.layers.0.self_attn.q_proj.lora_A.weight" in sd and len(sd) == len(lora)
+    want = effective_weight(q).clone()
+    assert torch.allclose(want, q.weight.detach() + 2.0 * q.lora_B.detach() @ q.lora_A.detach(), atol=1e-6)
+    m2 = cls.from_pretrained(d)
+    m2.add_lora()
+    m2.load_lora_state_dict(sd)
+    assert torch.equal(effective_weight(m2.model.decoder.layers[0].self_attn.q_proj), want)
+    m2.merge_lora()
+    assert not [n for n, _ in m2.named_parameters() if "lora_" in n]
+    assert torch.equal(m2.model.decoder.layers[0].self_attn.q_proj.weight.detach(), want)
+
+
 def test_python_surface_of_survey_8b_exists():
     """the members src/train.py, src/pretrain_encoder.py, src/utils/trainers.py and utils/export_dicow.py touch"""
     import dataclasses

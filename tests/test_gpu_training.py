@@ -239,6 +239,49 @@ def _finetune_case(dm, B, S, mode, tag):
     _compare(model, p, trainable, f"finetune[{mode}]")
 
 
+@pytest.mark.parametrize("dm,B,S", [(MINI, 2, 11), (TINY_SHORT, 3, 24)], ids=["mini", "tiny-short"])
+def test_finetune_step_with_decoder_lora(dm, B, S):
+    """use_lora (src/models/containers.py:69-90): rank-16 adapters on the decoder projections train together with the
+    encoder, the decoder's base weights stay frozen.  Loss, logits and the gradients of every lora_A / lora_B (and of the
+    encoder) against torch autograd through the oracle's restatement y = x W^T + b + (alpha / r) (x A^T) B^T."""
+    model, p = _build(dm)
+    model.set_tokenizer(FakeTokenizer())
+    model.add_lora(r=16, lora_alpha=32, seed=3)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():  # B off its zero init so that the gradients of A are live too
+        for n, q in model.named_parameters():
+            if n.endswith("lora_B"):
+                q.copy_((torch.randn(q.shape, generator=g) * 0.02).to(DEV))
+    for n, q in model.named_parameters():
+        q.requires_grad_("lora_" in n or (n.startswith("model.encoder.") and "embed_positions" not in n))
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    assert sum("lora_" in n for n in trainable) == 20 * dm.dec_layers
+    for n, q in model.named_parameters():
+        if "lora_" in n:
+            p[n] = q.detach().clone().float()
+    feats, stno = _inputs(dm, B, "tr1")
+    labels = torch.from_numpy(synth.make_labels("tr1", B, S, min(dm.vocab, 300), EOS, TS_BEGIN, prefix=(LANG, TASK))).to(DEV)
+    out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
+    out.loss.backward()
+    for n in trainable:
+        p[n].requires_grad_(True)
+    ref_loss, ref_logits, _ = orc.model_forward(p, dm, feats, stno, labels, labels, ctc_prefix_tokens=(SOT, LANG, TASK),
+                                                ts_begin=TS_BEGIN, n_ts=N_TS)
+    ref_loss.backward()
+    torch.cuda.synchronize()
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    err = ((out.logits.float() - ref_logits).abs().max() / ref_logits.abs().max()).item()
+    assert err < 2e-2, f"logits rel err {err:.3e}"
+    _compare(model, p, trainable, "finetune[lora]")
+    assert all(q.grad is None for n, q in model.named_parameters() if not q.requires_grad)
+    # generate() decodes with the merged weights: merging the adapters must not change the teacher-forced logits
+    with torch.no_grad():
+        before = model(feats, stno_mask=stno, labels=labels, upp_labels=labels).logits
+        model.merge_lora()
+        after = model(feats, stno_mask=stno, labels=labels, upp_labels=labels).logits
+    assert torch.equal(before, after)
+
+
 def test_training_step_updates_and_second_step():
     """two optimizer steps: the prepared bf16 weight copies follow the parameter updates (versioned cache), the loss
     moves, and evaluation under no_grad takes the inference path with identical loss"""

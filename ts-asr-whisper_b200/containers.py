@@ -3,8 +3,10 @@ src/train.py / src/pretrain_encoder.py build their model, feature extractor and 
 
 Same constructor arguments, attributes (.model, .feature_extractor, .tokenizer) and methods (freeze_except); differences:
   * use_flash_attention is accepted and ignored (attention always runs on the tcgen05 flash kernels);
-  * use_lora raises: the decoder's projections are parameter containers driven by the C-ABI kernels, not nn.Linear
-    forwards peft could wrap (SURVEY 8(f).4, not built);
+  * use_lora attaches the reference's adapter configuration (r = 16, lora_alpha = 32, decoder q/k/v/out_proj/fc1/fc2,
+    src/models/containers.py:69-78) through DiCoWForConditionalGeneration.add_lora -- peft is not needed (the kernels multiply
+    by the merged weight, the backward projects onto A / B); the model is NOT wrapped in a PeftModel, parameter names keep
+    their reference paths with ".lora_A" / ".lora_B" appended (lora_state_dict() exports peft's adapter keys);
   * the feature extractor is the GPU log-mel front-end with the reference's call signature;
   * ``tokenizer`` may be passed in (tests, offline use); by default WhisperTokenizerFast.from_pretrained as the reference.
 """
@@ -40,8 +42,6 @@ class WhisperContainer:
     def __init__(self, use_flash_attention=False, params_to_keep_frozen_keywords=None, remove_timestamps_from_ctc=False,
                  model_args=None, data_args=None, use_fddt=False, use_lora=False, tokenizer=None, feature_extractor=None):
         del use_flash_attention  # one attention implementation here
-        if use_lora:
-            raise NotImplementedError("use_lora: the B200 decoder is not built from nn.Linear forwards peft could wrap")
         name = self.model_type = model_args.whisper_model
         timestamps = data_args.use_timestamps
         self.model = DiCoWForConditionalGeneration.from_pretrained(
@@ -62,9 +62,11 @@ class WhisperContainer:
             tokenizer.set_prefix_tokens(predict_timestamps=timestamps)
         self.model.set_tokenizer(tokenizer)
         self.model.config.forced_decoder_ids = None
-        if params_to_keep_frozen_keywords is not None:  # src/models/containers.py:80-90
+        if use_lora:  # src/models/containers.py:69-78
+            self.model.add_lora(r=16, lora_alpha=32)
+        if params_to_keep_frozen_keywords is not None:  # src/models/containers.py:80-90 (adapters always train)
             frozen = tuple(params_to_keep_frozen_keywords)
-            _set_trainable(self.model, lambda n: not any(k in n for k in frozen))
+            _set_trainable(self.model, lambda n: "lora_" in n or not any(k in n for k in frozen))
 
     def freeze_except(self, prefixes_to_preheat):
         _set_trainable(self.model, lambda n: n.startswith(tuple(prefixes_to_preheat)))

@@ -60,6 +60,26 @@ class DiCoWDecoder(nn.Module):
         self.layer_norm = nn.LayerNorm(d)
 
 
+LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")  # src/models/containers.py:73 (decoder only)
+
+
+def lora_of(lin: nn.Module):
+    """(A [r, in], B [out, r], alpha / r) of a linear layer that carries a LoRA adapter, else None"""
+    A = getattr(lin, "lora_A", None)
+    return None if A is None else (A, lin.lora_B, float(lin.lora_scale))
+
+
+def effective_weight(lin: nn.Module) -> torch.Tensor:
+    """fp32 W + (alpha / r) B A: what a LoRA-adapted layer multiplies by (peft's merged weight); W itself without an adapter.
+    The kernels consume the merged weight -- one GEMM per layer, exactly as without the adapter."""
+    W = lin.weight.detach().float()
+    lo = lora_of(lin)
+    if lo is None:
+        return W
+    A, B, s = lo
+    return torch.addmm(W, B.detach().float(), A.detach().float(), alpha=s)
+
+
 def shift_tokens_right(labels: torch.Tensor, pad_token_id: int, decoder_start_token_id: int) -> torch.Tensor:
     """HF:modeling_whisper.py shift_tokens_right (index bookkeeping on int64 labels; call site modeling_dicow.py:275-279)."""
     shifted = labels.new_zeros(labels.shape)
@@ -141,10 +161,10 @@ class DiCoW(nn.Module):
         def att(a: AttentionParams) -> dict:
             d = a.q_proj.weight.shape[0]
             zeros = torch.zeros(d, device=a.q_proj.weight.device)
-            return {"wq": _bf16(a.q_proj.weight.detach().float() * sc), "bq": (a.q_proj.bias.detach().float() * sc).contiguous(),
-                    "wkv": _bf16(torch.cat([a.k_proj.weight.detach().float(), a.v_proj.weight.detach().float()], 0)),
+            return {"wq": _bf16(effective_weight(a.q_proj) * sc), "bq": (a.q_proj.bias.detach().float() * sc).contiguous(),
+                    "wkv": _bf16(torch.cat([effective_weight(a.k_proj), effective_weight(a.v_proj)], 0)),
                     "bkv": torch.cat([zeros, a.v_proj.bias.detach().float()]).contiguous(),
-                    "wo": _bf16(a.out_proj.weight), "bo": _f32(a.out_proj.bias)}
+                    "wo": _bf16(effective_weight(a.out_proj)), "bo": _f32(a.out_proj.bias)}
 
         w: dict = {"tok": _f32(dec.embed_tokens.weight), "pos": _f32(dec.embed_positions.weight),
                    "proj": _bf16(dec.embed_tokens.weight),  # proj_out is tied to embed_tokens (train.py:109-113)
@@ -157,8 +177,8 @@ class DiCoW(nn.Module):
             for nm, ln in (("ln1", lyr.self_attn_layer_norm), ("ln2", lyr.encoder_attn_layer_norm),
                            ("ln3", lyr.final_layer_norm)):
                 e[nm + "_g"], e[nm + "_b"] = _f32(ln.weight), _f32(ln.bias)
-            e["w1"], e["b1"] = _bf16(lyr.fc1.weight), _f32(lyr.fc1.bias)
-            e["w2"], e["b2"] = _bf16(lyr.fc2.weight), _f32(lyr.fc2.bias)
+            e["w1"], e["b1"] = _bf16(effective_weight(lyr.fc1)), _f32(lyr.fc1.bias)
+            e["w2"], e["b2"] = _bf16(effective_weight(lyr.fc2)), _f32(lyr.fc2.bias)
             w["layers"].append(e)
         self._prepared, self._prepared_key = w, key
         self._prepared_gen += 1
@@ -438,6 +458,61 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         gradient exchange overlapped with the backward replaces DDP's end-of-backward all-reduce)"""
         from . import parallel
         return parallel.ddp_ignore_list(self)
+
+    # ---- LoRA on the decoder (src/models/containers.py:69-78) -----------------------------------------------------
+    def add_lora(self, r: int = 16, lora_alpha: int = 32, target_modules=LORA_TARGETS, seed: Optional[int] = None):
+        """What ``get_peft_model(model, LoraConfig(r=16, lora_alpha=32, target_modules=r".*decoder.*(q_proj|k_proj|v_proj|
+        out_proj|fc1|fc2).*", lora_dropout=0.0, bias="none"))`` does to the reference model, without peft (not in this image):
+        every targeted decoder projection gets ``lora_A`` [r, in] (kaiming-uniform, a = sqrt(5): peft's init) and ``lora_B``
+        [out, r] (zeros), the base model is frozen and the adapters are trainable.  The kernels multiply by the merged weight
+        W + (alpha / r) B A (prepare_decoder); the backward projects onto A and B with four r-wide GEMMs per layer
+        (training._linear_backward).  Parameter names contain "lora_" as the reference's freezing loop expects."""
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        for p in self.parameters():
+            p.requires_grad_(False)
+        n = 0
+        for name, mod in self.model.decoder.named_modules():
+            if isinstance(mod, nn.Linear) and name.rsplit(".", 1)[-1] in target_modules and lora_of(mod) is None:
+                A = torch.empty(r, mod.in_features)
+                bound = 1.0 / math.sqrt(mod.in_features)  # kaiming_uniform_(a=sqrt(5)) on [r, in]: U(-1/sqrt(in), 1/sqrt(in))
+                A.uniform_(-bound, bound, generator=gen)
+                mod.register_parameter("lora_A", nn.Parameter(A.to(mod.weight.device)))
+                mod.register_parameter("lora_B", nn.Parameter(torch.zeros(mod.out_features, r, device=mod.weight.device)))
+                mod.lora_scale = float(lora_alpha) / float(r)
+                mod.weight._dicow_lora = mod  # how the backward finds the adapter from the base weight it is handed
+                n += 1
+        self.model.invalidate_cache()
+        self.clear_decode_cache()
+        return n
+
+    def lora_state_dict(self) -> dict:
+        """the adapter in peft's saved-adapter key format (``base_model.model.<module path>.lora_A.weight``)"""
+        out = {}
+        for name, mod in self.named_modules():
+            if lora_of(mod) is not None:
+                out[f"base_model.model.{name}.lora_A.weight"] = mod.lora_A.detach().clone()
+                out[f"base_model.model.{name}.lora_B.weight"] = mod.lora_B.detach().clone()
+        return out
+
+    def load_lora_state_dict(self, sd: dict) -> None:
+        mods = dict(self.named_modules())
+        with torch.no_grad():
+            for k, v in sd.items():
+                m = re.match(r"(?:base_model\.model\.)?(.*)\.lora_([AB])(?:\.default)?(?:\.weight)?$", k)
+                if m is None or m.group(1) not in mods or lora_of(mods[m.group(1)]) is None:
+                    raise KeyError(f"no LoRA adapter for {k}")
+                getattr(mods[m.group(1)], "lora_" + m.group(2)).copy_(v)
+        self.invalidate_prepared()
+
+    def merge_lora(self) -> None:
+        """fold the adapters into the base weights and drop them (peft's merge_and_unload)"""
+        with torch.no_grad():
+            for mod in self.modules():
+                if lora_of(mod) is not None:
+                    mod.weight.copy_(effective_weight(mod).to(mod.weight.dtype))
+                    del mod._parameters["lora_A"], mod._parameters["lora_B"]
+                    mod.weight._dicow_lora = None
+        self.invalidate_prepared()
 
     def clear_decode_cache(self) -> None:
         """free the decode states (self / cross K/V caches, staging rows, captured CUDA graphs) kept between generate() calls"""

@@ -149,7 +149,33 @@ def _linear_backward(g: _Grads, dY: torch.Tensor, X: torch.Tensor, W_prep: torch
                  gate=alpha, lda=dY.stride(0), Mb=Ws.shape[0], K=X.shape[0], N=X.shape[1])
     if g.want(bias):
         ops.colsum(dYs, g.get(bias), alpha=scale)
+    lora = getattr(weight, "_dicow_lora", None)
+    if lora is not None and (g.want(lora.lora_A) or g.want(lora.lora_B)):
+        _lora_backward(g, dYs, dY.stride(0), X, lora, scale)
     return dx
+
+
+def _lora_backward(g: _Grads, dYs: torch.Tensor, ldy: int, X: torch.Tensor, lin, scale: float) -> None:
+    """Gradients of a LoRA adapter Y = X (W + s B A)^T (the forward multiplies by the merged weight):
+        dB += s * dY^T (X A^T)        dA += s * (dY B)^T X
+    as four r-wide GEMMs on the tcgen05 kernel (r = 16: src/models/containers.py:71); ``scale`` is the factor already folded
+    into the prepared weight (the q projections' hd^-0.5)."""
+    A, B = lin.lora_A, lin.lora_B
+    r, M = A.shape[0], X.shape[0]
+    dev = X.device
+    alpha = _dev_scalar(float(lin.lora_scale) * scale, dev)
+    N_out = B.shape[0]
+    if g.want(B):
+        u = torch.empty(M, r, dtype=torch.bfloat16, device=dev)
+        ops.gemm(X, ops.cast_bf16(A.detach().float()), u, epilogue=ops.EPI_BIAS_BF16)                  # u = X A^T
+        ops.gemm(dYs, u, g.get_padded(B), epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, gate=alpha, lda=ldy,
+                 Mb=_ceil8(N_out), K=M, N=r)                                                             # dB += s dY^T u
+    if g.want(A):
+        v = torch.empty(M, r, dtype=torch.bfloat16, device=dev)
+        ops.gemm(dYs, ops.cast_bf16(B.detach().float()), v, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T, lda=ldy, Mb=M,
+                 K=N_out, N=r)                                                                           # v = dY B
+        ops.gemm(v, X, g.get(A), epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, gate=alpha, lda=r, Mb=r, K=M,
+                 N=X.shape[1])                                                                           # dA += s v^T X
 
 
 class EncoderTape:
