@@ -348,10 +348,9 @@ int launch_attention(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& 
                      const AttnParams& p, cudaStream_t stream) {
   using L = AttnSmem<P_SMEM>;
   auto kfn = attention_kernel<P_SMEM, EMU, TWO_PASS>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    attr_done = true;
   }
   dim3 grid(ceil_div(p.Tq, BQ), p.H, p.B);
   kfn<<<grid, kAttnThreads, L::BYTES, stream>>>(tmQ, tmK, tmV, p);

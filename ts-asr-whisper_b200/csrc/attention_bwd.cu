@@ -392,11 +392,10 @@ extern "C" int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_
         a->o_row_stride, obs, a->o_row_stride, obs);
     DICOW_CUDA_OK(ctx, cudaGetLastError());
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
   }
   BwdParams p{};
   p.B = a->B, p.H = a->H, p.Tq = a->Tq, p.Tk = a->Tk, p.causal = a->causal ? 1 : 0;

@@ -492,10 +492,9 @@ template <int EMU>
 int launch(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
            const AttnParams& p, cudaStream_t stream) {
   auto kfn = attention_fa_kernel<EMU>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
   }
   const int n_items = ceil_div(p.Tq, 2 * BQ) * p.H * p.B;
   const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;  // persistent: one CTA per SM

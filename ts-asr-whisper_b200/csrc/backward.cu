@@ -420,10 +420,9 @@ __global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring
 template <int VPL>
 int launch_ln_bwd_ring(dicow_ctx* ctx, const LnBwdParams& p, int nst, size_t smem, int grid, cudaStream_t stream) {
   auto kfn = ln_fddt_bwd_ring_kernel<VPL>;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static DeviceHighWater attr_smem;
+  if (attr_smem.raise(ctx, smem)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
   }
   kfn<<<grid, (1 + RB_NS + VPL) * 32, smem, stream>>>(p, nst);
   DICOW_CUDA_OK(ctx, cudaGetLastError());

@@ -45,4 +45,27 @@ int mel_tables_create(dicow_ctx* ctx);  // mel.cu
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Per-DEVICE once-flags / high-water marks for cudaFuncSetAttribute (opt-in shared memory): a function attribute belongs to the
+// device that was current when it was set, so a process that drives several devices (one handle each) must set it on each.
+// Usage:  static DeviceOnce once;  if (once.first(ctx)) cudaFuncSetAttribute(...);
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first(const dicow_ctx* ctx) {
+    const int d = ctx->device >= 0 && ctx->device < kMaxDevices ? ctx->device : 0;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+struct DeviceHighWater {
+  size_t mark[kMaxDevices] = {};
+  bool raise(const dicow_ctx* ctx, size_t v) {
+    const int d = ctx->device >= 0 && ctx->device < kMaxDevices ? ctx->device : 0;
+    if (v <= mark[d]) return false;
+    mark[d] = v;
+    return true;
+  }
+};
+
 }  // namespace dicow

@@ -396,10 +396,9 @@ template <int VPL>
 int launch_fddt_ln_tma(dicow_ctx* ctx, const FddtLnParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)LT_NST * 8 * p.d + (p.stno != nullptr ? (size_t)32 * p.d : 0) + 2 * LT_NST * 8 + 128;
   auto kfn = fddt_ln_tma_kernel<VPL>;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static DeviceHighWater attr_smem;
+  if (attr_smem.raise(ctx, smem)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
   }
   const int grid = p.rows < ctx->num_sms ? p.rows : ctx->num_sms;
   kfn<<<grid, (LT_NW + 1) * 32, smem, stream>>>(p);

@@ -684,10 +684,9 @@ int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2,
                 const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kfn = gemm_bf16_kernel<BN, EPI, A_MN, B_MN>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
   }
   const int work = p.total_tiles * p.splits;
   const int grid = work < ctx->num_sms ? work : ctx->num_sms;
@@ -701,10 +700,9 @@ int launch_gemm_2cta(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
                      const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg2<BN>;
   auto kfn = gemm_bf16_2cta_kernel<BN, EPI>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
   }
   int grid = 2 * (p.total_tiles < ctx->num_sms / 2 ? p.total_tiles : ctx->num_sms / 2);
   kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, tmO, p);

@@ -286,11 +286,10 @@ extern "C" int dicow_logmel(dicow_handle_t h, const dicow_logmel_args_t* a, void
   p.n_mels = a->n_mels, p.filters = a->mel_filters, p.tables = ctx->mel_tables;
   p.out = a->out, p.gmax = reinterpret_cast<unsigned*>(a->workspace);
   p.lengths = reinterpret_cast<const long long*>(a->lengths), p.mask = a->attention_mask;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)kMelSmem));
-    attr_done = true;
   }
   DICOW_CUDA_OK(ctx, cudaMemsetAsync(a->workspace, 0, sizeof(unsigned) * a->B, stream));
   dim3 grid(ceil_div(p.frames, FR), a->B);
