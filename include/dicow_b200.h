@@ -447,6 +447,63 @@ typedef struct {
 } dicow_decode_linear_args_t;
 DICOW_API int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_args_t* args, void* stream);
 
+/* The decoder LAYERS of one greedy token step in ONE persistent kernel (decode batch <= 16 rows): token + position
+ * embedding, then per layer LayerNorm -> q | k,v (k,v appended to the self-attention cache at *pos), self-attention over the
+ * cache, out_proj + residual, LayerNorm -> q, cross-attention over the head-major encoder K/V, out_proj + residual,
+ * LayerNorm -> fc1 + GELU, fc2 + residual -- one CTA per SM, grid-wide barriers between the phases, every weight tile of a
+ * phase requested at once.  Replaces the layer loop of HF WhisperDecoder.forward with a KV cache
+ * (HF:models/whisper/modeling_whisper.py:449-506, 691-796) inside one step of DiCoWGenerationMixin._sample
+ * (src/models/dicow/generation.py:707-782); what dicow_embed_tokens + 12 launches per layer of dicow_fddt_layernorm /
+ * dicow_decode_linear / dicow_decode_attention_bf16 compute.  The final LayerNorm, proj_out, the logits rules and the
+ * position advance stay separate calls.  `layers`: DEVICE array of L entries; weights bf16 [N, K] as in dicow_decode_linear
+ * (wqkv = [Wq * hd^-0.5 ; Wk ; Wv], bqkv = [bq * hd^-0.5 ; 0 ; bv]); self_kv = this layer's cache [B, S_max, 2 d] (k | v);
+ * cross_kv = [B, H, T, 128] (k(64) | v(64) per key).  x / q / ctx / hidden: step scratch [16, d] fp32, [16, d], [16, d],
+ * [16, ffn] bf16; attn_workspace: scratch; `barrier`: one zero-initialised uint64 owned by the caller for the lifetime of the buffers (monotonic
+ * arrival counter).  d_model <= 1280 (multiple of 64, head_dim 64), ffn <= 5120. */
+typedef struct {
+  const float* ln1_g;
+  const float* ln1_b;
+  const float* ln2_g;
+  const float* ln2_b;
+  const float* ln3_g;
+  const float* ln3_b;
+  const void* wqkv;
+  const float* bqkv;
+  const void* wo_self;
+  const float* bo_self;
+  const void* wq_cross;
+  const float* bq_cross;
+  const void* wo_cross;
+  const float* bo_cross;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  void* self_kv;
+  const void* cross_kv;
+} dicow_decode_layer_args_t;
+typedef dicow_decode_layer_args_t dicow_decode_layer_t;
+
+typedef struct {
+  size_t struct_size;
+  int32_t B, d, H, ffn, L, T, S_max, vocab;
+  const dicow_decode_layer_args_t* layers;
+  const int64_t* ids;
+  int64_t ids_row_stride;
+  const float* embed_tokens;
+  const float* embed_positions;
+  const int32_t* pos;
+  float* x;
+  void* q;
+  void* ctx;
+  void* hidden;
+  void* barrier;
+  float* attn_workspace; /* B * H * 136 floats: cross-attention partials exchanged between two phases */
+  float eps;
+  int32_t flags; /* tuning switches (bit 0: cp.async staging of activations, bit 1: L2 prefetch of the next phase's weights) */
+} dicow_decode_layers_args_t;
+DICOW_API int dicow_decode_layers(dicow_handle_t h, const dicow_decode_layers_args_t* args, void* stream);
+
 /* one query row per (batch, head), head_dim 64: out[b, h*64:] = softmax(q . K^T) V over Tk keys (Tk = *pos + 1 if pos).
  * Q/out bf16 [B, H*64]; K/V bf16 rows at K + b*kv_batch_stride + h*kv_head_stride + k*kv_row_stride. */
 typedef struct {

@@ -408,8 +408,21 @@ def _check_greedy(ids, ref_ids, ref_raw_logits, P, dm):
             break  # after a tolerated near-tie flip the continuations legitimately differ
 
 
+@pytest.fixture(params=[False, True], ids=["kernel-per-op", "megakernel"])
+def decode_path(request, mini):
+    """both decode-step implementations: the default kernel-per-operation sequence and the experimental persistent
+    decode-layers kernel (csrc/decode_mega.cu)"""
+    model = mini[2]
+    old = model.decode_megakernel
+    model.decode_megakernel = request.param
+    model.clear_decode_cache()
+    yield request.param
+    model.decode_megakernel = old
+    model.clear_decode_cache()
+
+
 @pytest.mark.parametrize("graphs", [False, True])
-def test_greedy_decode_matches_oracle_and_golden(mini, graphs):
+def test_greedy_decode_matches_oracle_and_golden(mini, graphs, decode_path):
     g, dmp, model, p, feats, stno = mini
     model.use_cuda_graphs = graphs
     prompt = torch.tensor([[SOT, LANG, TASK]] * 2)

@@ -101,10 +101,14 @@ def _oracle_choices(p, dm, ids, enc_ref, P):
     return out
 
 
-def test_turbo_greedy_tokens(turbo):
-    """32 greedy tokens for 4 windows through the CUDA-graphed decode step at full turbo dimensions"""
+@pytest.mark.parametrize("mega", [False, True], ids=["kernel-per-op", "megakernel"])
+def test_turbo_greedy_tokens(turbo, mega):
+    """32 greedy tokens for 4 windows through the CUDA-graphed decode step at full turbo dimensions, for both decode-step
+    implementations (the default kernel-per-operation sequence and the experimental persistent decode-layers kernel)"""
     dm, model, p = turbo
     model.eval()
+    model.decode_megakernel = mega
+    model.clear_decode_cache()
     B, P, NEW = 4, 3, 32
     feats, stno = _inputs(dm, B, "tq1")
     prompt = torch.tensor([[SOT, LANG, TASK]] * B, device=DEV)
@@ -137,6 +141,8 @@ def test_turbo_greedy_tokens(turbo):
                 finished[b] = True
     print(f"turbo greedy: {checked} tokens checked against the oracle on the same prefix, {flips} tolerated near-tie flips "
           f"(oracle margin < {MARGIN}); ids[0] = {ids_c[0].tolist()}")
+    model.decode_megakernel = False
+    model.clear_decode_cache()
     assert checked >= B * NEW // 2 and flips <= MAX_FLIPS
 
 

@@ -152,6 +152,24 @@ class DecodeLinearArgs(C.Structure):
     ]
 
 
+class DecodeLayerArgs(C.Structure):  # one entry of the device-resident layer table of dicow_decode_layers
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "wqkv", "bqkv", "wo_self", "bo_self", "wq_cross", "bq_cross",
+        "wo_cross", "bo_cross", "w1", "b1", "w2", "b2", "self_kv", "cross_kv")]
+
+
+class DecodeLayersArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("B", C.c_int32), ("d", C.c_int32), ("H", C.c_int32), ("ffn", C.c_int32), ("L", C.c_int32), ("T", C.c_int32),
+        ("S_max", C.c_int32), ("vocab", C.c_int32),
+        ("layers", C.c_void_p), ("ids", C.c_void_p), ("ids_row_stride", C.c_int64),
+        ("embed_tokens", C.c_void_p), ("embed_positions", C.c_void_p), ("pos", C.c_void_p),
+        ("x", C.c_void_p), ("q", C.c_void_p), ("ctx", C.c_void_p), ("hidden", C.c_void_p), ("barrier", C.c_void_p),
+        ("attn_workspace", C.c_void_p), ("eps", C.c_float), ("flags", C.c_int32),
+    ]
+
+
 class DecodeAttentionArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -319,6 +337,7 @@ EXPORTED_SYMBOLS = [
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
     "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch", "dicow_fddt_full_scatter",
+    "dicow_decode_layers",
 ]
 
 

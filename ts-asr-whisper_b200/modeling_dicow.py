@@ -16,6 +16,7 @@ no conditioning on previous text (the recipes' configs/decode/*_greedy.yaml).  N
 """
 from __future__ import annotations
 
+import os
 import re
 from decimal import ROUND_HALF_UP, Decimal
 from typing import Dict, List, Optional
@@ -296,6 +297,11 @@ class _GreedyState:
         # freed dict can be handed to a later one, and the graphs would replay with pointers to freed weights)
         self.weights = None
         self.ctc_gen = 0  # bumped when the joint-CTC state object is replaced (part of the graph key)
+        # persistent decode-layers kernel (ops.decode_layers): arrival counter of its grid barrier, layer pointer table
+        self.mega_bar = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.mega_ws = torch.zeros(B * cfg.decoder_attention_heads * 136, dtype=torch.float32, device=dev)
+        self.mega_table = None
+        self.mega_weights = None
 
 
 _DECODE_BUCKETS = (1, 2, 4, 8, 12, 16, 24, 32, 48, 64)
@@ -354,6 +360,10 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
     # True: fused q|k,v projection, cluster split-K linear layers, few-rows LayerNorm kernel; "ln_prologue": LayerNorm as
     # the prologue of the linear kernel instead; False: one kernel per operation (_decode_step_unfused), the baseline
     fused_decode_step = True
+    # EXPERIMENTAL, off by default: greedy steps of <= 16 rows run the decoder layers as ONE persistent kernel with grid
+    # barriers between the phases (csrc/decode_mega.cu; DICOW_DECODE_MEGA=1 or decode_megakernel = True).  Token-parity green,
+    # but measured SLOWER than the kernel-per-operation sequence at B = 16 (0.50 vs 0.42 ms per step): DESIGN.md section 4.2
+    decode_megakernel = os.environ.get("DICOW_DECODE_MEGA", "0") == "1"
 
     def __init__(self, config: DiCoWConfig):
         super().__init__(config)
@@ -654,6 +664,13 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             ops.fddt_layernorm(st.x, gamma=g, beta=b, ln_out_bf16=st.ln)
             return ops.decode_linear(W, out, A=st.ln, **kw)
 
+        if self._megakernel_ok(st):
+            self._decode_layers_mega(st, w)
+            if sample:
+                ln_linear(w["proj"], st.logits, w["lnf_g"], w["lnf_b"], epilogue=ops.EPI_BIAS_F32)
+                self._select_token(st, gen)
+            ops.advance(st.pos, 1)
+            return
         ops.embed_tokens(st.ids, w["tok"], w["pos"], st.x, S=1, pos=st.pos)
         for li, e in enumerate(w["layers"]):
             s, c = e["self"], e["cross"]
@@ -674,6 +691,31 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             ln_linear(w["proj"], st.logits, w["lnf_g"], w["lnf_b"], epilogue=ops.EPI_BIAS_F32)
             self._select_token(st, gen)
         ops.advance(st.pos, 1)
+
+    def _megakernel_ok(self, st: _GreedyState) -> bool:
+        cfg = self.config
+        d, ffn = cfg.d_model, cfg.decoder_ffn_dim
+        return bool(self.decode_megakernel) and st.beams == 1 and st.B <= 16 and d % 64 == 0 and d <= 1280 and \
+            cfg.decoder_attention_heads * 64 == d and ffn % 32 == 0 and ffn <= 5120
+
+    def _decode_layers_mega(self, st: _GreedyState, w: dict) -> None:
+        """embedding + every decoder layer of the step in one persistent kernel (csrc/decode_mega.cu)"""
+        cfg = self.config
+        if st.mega_table is None or st.mega_weights is not w:
+            rows = []
+            for li, e in enumerate(w["layers"]):
+                s, c = e["self"], e["cross"]
+                rows.append({"ln1_g": e["ln1_g"], "ln1_b": e["ln1_b"], "ln2_g": e["ln2_g"], "ln2_b": e["ln2_b"],
+                             "ln3_g": e["ln3_g"], "ln3_b": e["ln3_b"], "wqkv": s["wqkv"], "bqkv": s["bqkv"],
+                             "wo_self": s["wo"], "bo_self": s["bo"], "wq_cross": c["wq"], "bq_cross": c["bq"],
+                             "wo_cross": c["wo"], "bo_cross": c["bo"], "w1": e["w1"], "b1": e["b1"], "w2": e["w2"], "b2": e["b2"],
+                             "self_kv": st.self_kv[li], "cross_kv": st.cross_kv[li]})
+            st.mega_table = ops.decode_layer_table(rows, st.x.device)
+            st.mega_weights = w
+        ops.decode_layers(st.mega_table, B=st.B, d=cfg.d_model, H=cfg.decoder_attention_heads, ffn=cfg.decoder_ffn_dim,
+                          L=len(w["layers"]), T=st.T, S_max=st.S_max, vocab=cfg.vocab_size, ids=st.ids, tok=w["tok"],
+                          posw=w["pos"], pos=st.pos, x=st.x, q=st.q, ctx=st.ctx, hidden=st.h, barrier=st.mega_bar,
+                          workspace=st.mega_ws)
 
     def _select_token(self, st: _GreedyState, gen: dict) -> None:
         """logits -> next token of every row.  Attention-only greedy: the fused rules + argmax kernel.  Joint CTC /

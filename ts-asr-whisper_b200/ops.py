@@ -5,6 +5,7 @@ Every function enqueues CUDA work on torch's current stream of the tensors' devi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -474,6 +475,42 @@ def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, posw: torch.Tensor, x: to
     _lib.check(rc, h, "dicow_embed_tokens")
     launch_count += 1
     return x
+
+
+def decode_layer_table(layers: list, dev: torch.device) -> torch.Tensor:
+    """device-resident dicow_decode_layer_args_t[L] for decode_layers: ``layers`` = one dict per decoder layer mapping the
+    struct's field names to tensors (whose storage the caller keeps alive)"""
+    arr = (_lib.DecodeLayerArgs * len(layers))()
+    for i, entry in enumerate(layers):
+        for name, _ in _lib.DecodeLayerArgs._fields_:
+            t = entry[name]
+            assert t.is_cuda and t.is_contiguous(), name
+            setattr(arr[i], name, t.data_ptr())
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+    return raw.to(dev)
+
+
+def decode_layers(table: torch.Tensor, *, B: int, d: int, H: int, ffn: int, L: int, T: int, S_max: int, vocab: int,
+                  ids: torch.Tensor, tok: torch.Tensor, posw: torch.Tensor, pos: torch.Tensor, x: torch.Tensor,
+                  q: torch.Tensor, ctx: torch.Tensor, hidden: torch.Tensor, barrier: torch.Tensor, workspace: torch.Tensor,
+                  eps: float = 1e-5, flags: Optional[int] = None) -> None:
+    """the decoder layers of one greedy token step in one persistent kernel (dicow_decode_layers)"""
+    global launch_count
+    dev = _require_cuda(table, ids, tok, posw, pos, x, q, ctx, hidden, barrier, workspace)
+    assert workspace.dtype == torch.float32 and workspace.numel() >= B * H * 136
+    assert ids.dtype == torch.int64 and tok.dtype == torch.float32 and posw.dtype == torch.float32 and x.dtype == torch.float32
+    assert barrier.dtype == torch.int64 and pos.dtype == torch.int32
+    a = _lib.DecodeLayersArgs()
+    a.struct_size = C.sizeof(_lib.DecodeLayersArgs)
+    a.B, a.d, a.H, a.ffn, a.L, a.T, a.S_max, a.vocab = B, d, H, ffn, L, T, S_max, vocab
+    a.layers = _ptr(table)
+    a.ids, a.ids_row_stride = _ptr(ids), ids.stride(0)
+    a.embed_tokens, a.embed_positions, a.pos = _ptr(tok), _ptr(posw), _ptr(pos)
+    a.x, a.q, a.ctx, a.hidden, a.barrier = _ptr(x), _ptr(q), _ptr(ctx), _ptr(hidden), _ptr(barrier)
+    a.attn_workspace = _ptr(workspace)
+    a.eps = eps
+    a.flags = int(os.environ.get("DICOW_MEGA_FLAGS", "0")) if flags is None else flags
+    _call("dicow_decode_layers", dev, a, "decode_layers")
 
 
 def advance(pos: torch.Tensor, by: int = 1) -> None:
