@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""End-to-end check of the DDP hand-over on real GPUs (run under torchrun, 2+ ranks):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/check_ddp_overlap.py
+
+The reference trains through HF Trainer -> accelerate -> torch DistributedDataParallel.  This script wraps the B200 model in
+DDP exactly like that (no other change), runs fine-tune steps on DIFFERENT data per rank, and checks that
+  * DDP manages one small parameter only (parallel.ddp_ignore_list), the GradientExchange was installed and is active,
+  * after backward every rank holds the SAME gradients, equal to the mean of the per-rank local gradients (computed in a
+    second pass with the exchange switched off and an explicit all-reduce),
+  * parameters stay identical across ranks after optimizer steps, starting from DIFFERENT initial weights on rank 1
+    (the exchange broadcasts what DDP no longer does).
+Prints one JSON line on rank 0 (also the step time with / without the DDP wrapper)."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools import workloads  # noqa: E402
+from ts_asr_whisper_b200 import parallel, training  # noqa: E402
+from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration  # noqa: E402
+
+
+def main():
+    rank, world, local = parallel.rank_world()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    parallel.init_process_group("nccl", dev)
+    layers = int(os.environ.get("CHECK_LAYERS", "4"))
+    cfg = workloads.train_config()
+    cfg.encoder_layers = layers
+    torch.manual_seed(1234 + 17 * rank)  # rank 1 starts from other weights: the broadcast has to repair that
+    with torch.device(dev):
+        model = DiCoWForConditionalGeneration(cfg)
+    model.tie_weights()
+    model.set_tokenizer(workloads.WhisperIds())
+    model.to(dev)  # (HF Trainer moves the model, tokenizer-derived buffers included, before accelerate wraps it)
+    model.train()
+    for n, p in model.named_parameters():
+        p.requires_grad_(n.startswith("model.encoder.") and "embed_positions" not in n)
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])  # what accelerate does
+    managed = [n for n, _ in model.named_parameters() if n not in ddp.parameters_to_ignore]
+    ex = training.gradient_exchange
+    assert isinstance(ex, parallel.GradientExchange), "the exchange was not installed"
+    B = 2
+    feats, stno, labels, upp = workloads.make_train_batch(B, 32, 100 + rank, dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+
+    # (1) DDP path: gradients after backward must already be the mean over ranks
+    ddp.zero_grad(set_to_none=True)
+    loss = ddp(feats, stno_mask=stno, labels=labels, upp_labels=upp).loss
+    loss.backward()
+    torch.cuda.synchronize()
+    got = [p.grad.detach().clone() for p in params]
+    n_coll = ex.n_collectives
+    # (2) reference: local gradients (exchange off, bare model), explicit all-reduce mean
+    training.gradient_exchange = None
+    model.zero_grad(set_to_none=True)
+    model(feats, stno_mask=stno, labels=labels, upp_labels=upp).loss.backward()
+    ref = []
+    for p in params:
+        g = p.grad.detach().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        ref.append(g / world)
+    training.gradient_exchange = ex
+    worst, worst_name = 0.0, ""
+    for n, a, b in zip(names, got, ref):
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item() / max(scale, 1e-30)
+        if err > worst:
+            worst, worst_name = err, n
+    # parameters equal across ranks (after the broadcast) -- compare a checksum
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum()
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    # (3) a few optimizer steps under DDP, then the checksum again
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(4):
+        if i == 1:
+            torch.cuda.synchronize()
+            e0.record()
+        opt.zero_grad(set_to_none=True)
+        ddp(feats, stno_mask=stno, labels=labels, upp_labels=upp).loss.backward()
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    chk2 = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum()
+    both2 = [torch.zeros_like(chk2) for _ in range(world)]
+    dist.all_gather(both2, chk2)
+    out = {"world": world, "encoder_layers": layers, "ddp_managed_parameters": managed, "exchange_active": bool(ex.active),
+           "collectives_in_first_backward": n_coll, "worst_gradient_mismatch_vs_allreduced_local": worst,
+           "worst_at": worst_name, "param_checksums_equal_after_sync": bool(all(float(b) == float(both[0]) for b in both)),
+           "param_checksums_equal_after_3_steps": bool(all(float(b) == float(both2[0]) for b in both2)),
+           "ms_per_step_under_ddp": e0.elapsed_time(e1) / 3}
+    ok = len(managed) == 1 and ex.active and n_coll >= layers and worst < 1e-5 and \
+        out["param_checksums_equal_after_sync"] and out["param_checksums_equal_after_3_steps"]
+    out["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
