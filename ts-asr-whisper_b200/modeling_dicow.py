@@ -771,8 +771,17 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         B = U * NB
         P = prompt.shape[1]
         max_total_len = min(max_total_len, cfg.max_target_positions)
-        if B > 64:
-            raise NotImplementedError(f"beam search over {U} windows x {NB} beams = {B} hypotheses: at most 64 per call")
+        if B > 64:  # the step kernels stage at most 64 hypothesis rows: larger batches run in chunks of floor(64 / beams) windows
+            per = max(1, 64 // NB)
+            outs = []
+            for lo in range(0, U, per):
+                sl = slice(lo, min(U, lo + per))
+                sub = None if ctc is None else dict(ctc, logits=ctc["logits"][sl])
+                outs.append(self.beam_decode_window(enc_hidden[sl], prompt[sl], max_total_len, gen, num_beams=num_beams,
+                                                    length_penalty=length_penalty, early_stopping=early_stopping, ctc=sub,
+                                                    top_k=top_k))
+            n = max(o.shape[1] for o in outs)
+            return torch.cat([torch.nn.functional.pad(o, (0, n - o.shape[1]), value=int(gen["pad"])) for o in outs], dim=0)
         w = self.model.prepare_decoder()
         key = (dev.index, B, T, NB)
         st = self._greedy.get(key, lambda: _GreedyState(self, B, T, dev, beams=NB))
