@@ -391,12 +391,17 @@ def test_forward_losses_match_oracle_and_golden(mini):
     print(f"mini forward: logits rel err {rel_err(out2.logits, ref_logits):.3e}; loss {out2.loss.item():.5f} vs {ref_loss.item():.5f}")
 
 
-def _check_greedy(ids, ref_ids, ref_raw_logits, P, dm):
-    """token identity; a divergence is only tolerated where the oracle's own top-2 margin is below MARGIN"""
+def _check_greedy(ids, ref_ids, ref_raw_logits, P, dm, max_flips=1):
+    """token identity against the oracle's own greedy run; a divergence is only tolerated where the oracle's top-2 margin at
+    that step is below MARGIN, it ends the comparison of that row (the continuations legitimately differ afterwards), and
+    the NUMBER of rows that diverge is bounded.  (tests/test_gpu_turbo_parity.py checks every step of every row instead, by
+    teacher-forcing the oracle on the CUDA tokens.)"""
     ids, ref_ids = ids.cpu(), ref_ids.cpu()
     n = min(ids.shape[1], ref_ids.shape[1])
+    flips, compared = 0, 0
     for b in range(ids.shape[0]):
         for t in range(P, n):
+            compared += 1
             if int(ids[b, t]) == int(ref_ids[b, t]):
                 continue
             raw = ref_raw_logits[t - P][b:b + 1].clone()
@@ -405,7 +410,10 @@ def _check_greedy(ids, ref_ids, ref_raw_logits, P, dm):
                                        ts_begin=TS_BEGIN)[0]
             margin = float(proc[int(ref_ids[b, t])] - proc[int(ids[b, t])])
             assert margin < MARGIN, f"row {b} step {t - P}: token {int(ids[b, t])} vs {int(ref_ids[b, t])}, margin {margin:.3f}"
+            flips += 1
             break  # after a tolerated near-tie flip the continuations legitimately differ
+    print(f"greedy: {compared} tokens compared, {flips} row(s) diverged at a near-tie (oracle margin < {MARGIN})")
+    assert flips <= max_flips, f"{flips} rows diverged from the oracle (bound {max_flips})"
 
 
 @pytest.fixture(params=[False, True], ids=["kernel-per-op", "megakernel"])
