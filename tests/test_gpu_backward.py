@@ -60,7 +60,9 @@ def test_layernorm_fddt_backward(ops, d, T, B, fddt, ln):
         assert rel(dfw, fw.grad) < 1e-3 and rel(dfb, fb.grad) < 1e-3
 
 
-def test_colsum_and_gelu_epilogues(ops):
+@pytest.mark.parametrize("form,M,N,K", [(1, 640, 1536, 384), (2, 640, 1536, 384), (2, 3000, 5120, 1280), (2, 777, 1000, 264)])
+def test_colsum_and_gelu_epilogues(ops, form, M, N, K):
+    """form 1 = single-CTA kernel, 2 = CTA pairs (both outputs / the dgelu product leave through TMA stores)"""
     g = torch.Generator(device=DEV).manual_seed(1)
     X = (torch.randn(777, 1003, device=DEV, generator=g)).bfloat16()
     out = torch.ones(1003, device=DEV)
@@ -68,20 +70,19 @@ def test_colsum_and_gelu_epilogues(ops):
     torch.cuda.synchronize()
     assert rel(out, 1 + 0.5 * X.float().sum(0)) < 1e-3
     # fc1 training forward saves the pre-activation; the fc2 dgrad multiplies by gelu'(pre)
-    M, N, K = 640, 1536, 384
     A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=DEV, generator=g) * 0.08).bfloat16()
     b = torch.randn(N, device=DEV, generator=g) * 0.3
-    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    ops.gemm(A, W, h, epilogue=ops.EPI_GELU_SAVE_BF16, bias=b, aux=pre)
+    h = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    pre = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, h, epilogue=ops.EPI_GELU_SAVE_BF16, bias=b, aux=pre, flags=form)
     ref_pre = A.float() @ W.float().t() + b
     torch.cuda.synchronize()
     assert rel(pre, ref_pre) < 1e-2 and rel(h, F.gelu(ref_pre)) < 1e-2
     W2 = (torch.randn(K, N, device=DEV, generator=g) * 0.05).bfloat16()  # fc2 weight [d, ffn]
     dY = (torch.randn(M, K, device=DEV, generator=g) * 0.4).bfloat16()
-    dpre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    ops.gemm(dY, W2, dpre, epilogue=ops.EPI_DGELU_BF16, flags=ops.GEMM_W_T, aux=pre)
+    dpre = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(dY, W2, dpre, epilogue=ops.EPI_DGELU_BF16, flags=ops.GEMM_W_T | form, aux=pre)
     pf = pre.float().requires_grad_(True)
     (F.gelu(pf) * (dY.float() @ W2.float())).sum().backward()
     torch.cuda.synchronize()

@@ -136,8 +136,10 @@ def test_fddt_layernorm_pending_deltas(ops):
     assert (ln_f - ref2).abs().max().item() < 1e-4
 
 
-@pytest.mark.parametrize("M,N,K", [(1500, 1280, 1280), (777, 384, 1536), (128, 256, 64), (3000, 5120, 1280)])
-def test_gemm_backward_variants(ops, M, N, K):
+@pytest.mark.parametrize("form", [1, 2])  # 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2 with MN-major operands, split-K)
+@pytest.mark.parametrize("M,N,K", [(1500, 1280, 1280), (777, 384, 1536), (128, 256, 64), (3000, 5120, 1280),
+                                   (12000, 1280, 1280), (1000, 1000, 264)])
+def test_gemm_backward_variants(ops, M, N, K, form):
     """dgrad dX = dY W (W consumed MN-major from its forward layout) and wgrad dW += dY^T X (both operands MN-major,
     contraction split over CTAs, atomic fp32 accumulation) -- no transposed copies anywhere"""
     dev = torch.device("cuda:0")
@@ -147,7 +149,7 @@ def test_gemm_backward_variants(ops, M, N, K):
     dY = (torch.randn(M, N, device=dev, generator=g) * 0.3).bfloat16()
     # dgrad
     dX = torch.full((M, K), float("nan"), device=dev, dtype=torch.bfloat16)
-    ops.gemm(dY, W, dX, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T)
+    ops.gemm(dY, W, dX, epilogue=ops.EPI_BIAS_BF16, flags=ops.GEMM_W_T | form)
     ref = dY.float() @ W.float()
     torch.cuda.synchronize()
     assert not torch.isnan(dX.float()).any()
@@ -155,16 +157,22 @@ def test_gemm_backward_variants(ops, M, N, K):
     # wgrad with accumulation into an existing gradient
     dW0 = torch.randn(N, K, device=dev, generator=g)
     dW = dW0.clone()
-    ops.gemm(dY, X, dW, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T)
+    ops.gemm(dY, X, dW, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T | form)
     ref = dW0 + dY.float().t() @ X.float()
     torch.cuda.synchronize()
     assert _rel_err(dW, ref) < 2e-3
     # explicit single split and alpha scaling
     dW2 = torch.zeros(N, K, device=dev)
     alpha = torch.tensor([0.125], device=dev)
-    ops.gemm(dY, X, dW2, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T, splits=1, gate=alpha)
+    ops.gemm(dY, X, dW2, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T | form, splits=1, gate=alpha)
     torch.cuda.synchronize()
     assert _rel_err(dW2, 0.125 * (dY.float().t() @ X.float())) < 2e-3
+    # dgrad accumulated into an fp32 stream gradient (W MN-major, no split)
+    dXf0 = torch.randn(M, K, device=dev, generator=g)
+    dXf = dXf0.clone()
+    ops.gemm(dY, W, dXf, epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_W_T | form, splits=1)
+    torch.cuda.synchronize()
+    assert _rel_err(dXf, dXf0 + dY.float() @ W.float()) < 2e-3
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 3, 1500, 1500, False), (1, 2, 200, 200, True), (2, 2, 37, 300, False),

@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-import bench_train as bt  # noqa: E402
+import workloads as bt  # noqa: E402
 
 
 def main():
@@ -26,7 +26,7 @@ def main():
     fine = args.workload == "finetune"
     B = args.batch or (8 if fine else 16)
     with torch.device(dev):
-        model = DiCoWForConditionalGeneration(bt.config())
+        model = DiCoWForConditionalGeneration(bt.train_config())
     model.tie_weights()
     model.set_tokenizer(bt.WhisperIds())
     model.train()
@@ -36,7 +36,7 @@ def main():
         p.requires_grad_((n.startswith("model.encoder.") and "embed_positions" not in n) if fine else n.startswith(head))
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True)
-    batch = bt.make_batch(B, 64, 5, dev)
+    batch = bt.make_train_batch(B, 64, 5, dev)
 
     def step():
         feats, stno, labels, upp = batch
@@ -69,7 +69,7 @@ def main():
             a[1] += 1
             total += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
     print(f"total GPU kernel time {total / 1e3:.2f} ms over {sum(a[1] for a in agg.values())} launches")
-    for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+    for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:80]:
         print(f"{us / 1e3:9.3f} ms {100 * us / total:5.1f}%  x{n:<5d} {name}")
 
 

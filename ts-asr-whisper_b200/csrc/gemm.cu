@@ -271,9 +271,12 @@ __device__ __forceinline__ void drain_accumulator(const GemmParams& p, uint32_t 
 // tiles alternate; a tile is reused once the bulk group that reads it has finished reading (wait_group.read 1).
 // Rows / columns beyond the tensor are clipped by the TMA unit.
 template <int EPI, int NCH, typename Release>
-__device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const CUtensorMap* tmO, uint8_t* stage_base,
-                                                      uint32_t taddr, int b, int m_warp, int n_base, int lane, Release release) {
+__device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmX,
+                                                      uint8_t* stage_base, uint32_t taddr, int b, int m_warp, int n_base,
+                                                      int lane, Release release) {
   static_assert(NCH % 2 == 0, "pairs of 32-column chunks");
+  // GELU_SAVE writes two tensors (pre-activation -> tmX, activation -> tmO): one staging tile each, both reused every pair
+  constexpr bool kTwoOut = EPI == DICOW_EPI_GELU_SAVE_BF16;
   int nvalid = (p.N - n_base + 31) / 32;  // warp-uniform
   nvalid = nvalid > NCH ? NCH : nvalid;
   if (nvalid <= 0) {
@@ -282,8 +285,11 @@ __device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const
   }
 #pragma unroll 1
   for (int pair = 0; pair * 2 < nvalid; ++pair) {
-    uint8_t* stage = stage_base + (pair & 1) * 4096;
-    if (lane == 0) bulk_wait_group_read<1>();  // the store issued two pairs ago has read this tile
+    uint8_t* stage = kTwoOut ? stage_base + 4096 : stage_base + (pair & 1) * 4096;
+    if (lane == 0) {  // the store(s) that read this tile have finished reading it
+      if constexpr (kTwoOut) bulk_wait_group_read<0>();
+      else bulk_wait_group_read<1>();
+    }
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -310,7 +316,42 @@ __device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const
               if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
           }
         }
-        if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16) {
+        if constexpr (kTwoOut) {  // the pre-activation, as the backward's gelu' wants it
+          uint8_t* row = stage_base + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16(v[8 * j], v[8 * j + 1]), q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]), q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(row + (((h * 4 + j) ^ (lane & 7)) << 4)) = q;
+          }
+        }
+        if constexpr (EPI == DICOW_EPI_DGELU_BF16) {  // out = acc * gelu'(pre)
+          const int m = m_warp + lane;
+          if (m < p.Mb) {
+            const __nv_bfloat16* a = p.aux + (long long)b * p.out_bs + (long long)m * p.ldo + n;
+            if (n + 32 <= p.N) {
+              uint4 q[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) q[j] = __ldg(reinterpret_cast<const uint4*>(a) + j);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                  v[8 * j + 2 * k] *= dgelu_erf_fast(f.x);
+                  v[8 * j + 2 * k + 1] *= dgelu_erf_fast(f.y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) v[j] *= dgelu_erf_fast(__bfloat162float(a[j]));
+            }
+          }
+        }
+        if constexpr (EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_SAVE_BF16) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         }
@@ -327,6 +368,7 @@ __device__ __forceinline__ void drain_accumulator_tma(const GemmParams& p, const
     fence_proxy_async_smem();  // the generic-proxy writes above -> visible to the TMA (async proxy) read
     __syncwarp();
     if (lane == 0) {
+      if constexpr (kTwoOut) tma_store_3d(tmX, stage_base, n_base + pair * 64, m_warp, b);
       tma_store_3d(tmO, stage, n_base + pair * 64, m_warp, b);
       bulk_commit_group();
     }
@@ -520,10 +562,14 @@ struct GemmCfg2 {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
 
-template <int BN, int EPI>
+// A_MN / B_MN as in the single-CTA kernel: CTA r stages its 128 output rows of the transposed A as two 64 x 64 atoms and its
+// BN / 2 columns of the transposed W as BN / 128 atoms; the descriptors are the single-CTA ones (every CTA of the pair
+// describes its own half).  Split-K (ACCUM_F32): work item = (tile, split), partial sums reduced with fp32 red.global.
+template <int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                      const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   using Cfg = GemmCfg2<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -540,12 +586,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const bool leader = rank == 0;
   const int cluster = (int)cluster_id_x();
   const int nclusters = (int)cluster_nctaid_x();
+  const int total_work = p.total_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if (p.K1 > 0) tma_prefetch_desc(&tmA2);
     if (p.tma_out) tma_prefetch_desc(&tmO);
+    if (p.tma_out && EPI == DICOW_EPI_GELU_SAVE_BF16) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -571,13 +619,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ===================== TMA producer (each CTA loads its half of the pair's stage) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cluster; tile < p.total_tiles; tile += nclusters) {
+    for (int work = cluster; work < total_work; work += nclusters) {
+      const int tile = work % p.total_tiles, split = work / p.total_tiles;
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;
       const int b = mt / p.tiles_m;
       const int m0 = (mt % p.tiles_m) * (2 * BM) + (int)rank * BM;
       const int n0 = nt * BN + (int)rank * (BN / 2);
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
@@ -585,11 +635,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (p.K1 > 0 && k0 >= p.K1)
-            tma_load_3d_2cta(&tmA2, bar, sA, k0 - p.K1, m0, b);
-          else
-            tma_load_3d_2cta(&tmA, bar, sA, k0, m0, b);
-          tma_load_2d_2cta(&tmW, bar, sB, k0, n0, kEvictLast);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a) tma_load_3d_2cta(&tmA, bar, sA + a * 8192, m0 + 64 * a, k0, b);
+          } else {
+            if (p.K1 > 0 && k0 >= p.K1)
+              tma_load_3d_2cta(&tmA2, bar, sA, k0 - p.K1, m0, b);
+            else
+              tma_load_3d_2cta(&tmA, bar, sA, k0, m0, b);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int a = 0; a < BN / 128; ++a) tma_load_2d_2cta(&tmW, bar, sB + a * 8192, n0 + 64 * a, k0, kEvictLast);
+          } else {
+            tma_load_2d_2cta(&tmW, bar, sB, k0, n0, kEvictLast);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -598,28 +658,34 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint64_t a_step = A_MN ? 128 : 2;  // per 16-deep MMA: 16 contraction rows (2048 B) or 32 B along K
+      constexpr uint64_t b_step = B_MN ? 128 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster; tile < p.total_tiles; tile += nclusters, ++it) {
+      for (int work = cluster; work < total_work; work += nclusters, ++it) {
+        const int split = work / p.total_tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = make_sdesc_sw128(a_addr, 1024, 0);
-          const uint64_t db = make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
+          const uint64_t da = A_MN ? make_sdesc_sw128(a_addr, 1024, 8192) : make_sdesc_sw128(a_addr, 1024, 0);
+          const uint64_t db = B_MN ? make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 8192)
+                                   : make_sdesc_sw128(a_addr + Cfg::A_BYTES, 1024, 0);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss_2cta(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc,
+                                (kb != kb0 || k != 0) ? 1u : 0u);
             umma_commit_2cta(&empty_bar[stage]);
-            if (kb == p.kblocks - 1) umma_commit_2cta(&tfull_bar[acc]);
+            if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);
           }
           __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -632,7 +698,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int quad = e & 3;
     const int half = e >> 2;
     int it = 0;
-    for (int tile = cluster; tile < p.total_tiles; tile += nclusters, ++it) {
+    for (int work = cluster; work < total_work; work += nclusters, ++it) {
+      const int tile = work % p.total_tiles;
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;
       const int b = mt / p.tiles_m;
@@ -659,10 +726,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(tempty_remote);
       };
-      if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16) {
+      if constexpr (EPI == DICOW_EPI_BIAS_BF16 || EPI == DICOW_EPI_BIAS_GELU_BF16 || EPI == DICOW_EPI_GELU_SAVE_BF16 ||
+                    EPI == DICOW_EPI_DGELU_BF16) {
         if (p.tma_out) {
           uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + e * 2 * 4096;
-          drain_accumulator_tma<EPI, BN / 64>(p, &tmO, stage, taddr, b, m - lane, n_base, lane, release);
+          drain_accumulator_tma<EPI, BN / 64>(p, &tmO, &tmX, stage, taddr, b, m - lane, n_base, lane, release);
           continue;
         }
       }
@@ -695,32 +763,81 @@ int launch_gemm(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2,
   return DICOW_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool A_MN = false, bool B_MN = false>
 int launch_gemm_2cta(dicow_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
-                     const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+                     const CUtensorMap& tmO, const CUtensorMap& tmX, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg2<BN>;
-  auto kfn = gemm_bf16_2cta_kernel<BN, EPI>;
+  auto kfn = gemm_bf16_2cta_kernel<BN, EPI, A_MN, B_MN>;
   static DeviceOnce attr_once;  // per instantiation
   if (attr_once.first(ctx)) {
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
-  int grid = 2 * (p.total_tiles < ctx->num_sms / 2 ? p.total_tiles : ctx->num_sms / 2);
-  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, tmO, p);
+  const int work = p.total_tiles * p.splits;
+  int grid = 2 * (work < ctx->num_sms / 2 ? work : ctx->num_sms / 2);
+  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmW, tmO, tmX, p);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   return DICOW_OK;
 }
 
-int dispatch_epi_2cta(dicow_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
-                      const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
-  switch (epi) {
-    case DICOW_EPI_BIAS_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_BF16>(ctx, tmA, tmA2, tmW, tmO, p, stream);
-    case DICOW_EPI_BIAS_GELU_BF16: return launch_gemm_2cta<256, DICOW_EPI_BIAS_GELU_BF16>(ctx, tmA, tmA2, tmW, tmO, p, stream);
-    case DICOW_EPI_RESIDUAL_F32: return launch_gemm_2cta<256, DICOW_EPI_RESIDUAL_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
-    case DICOW_EPI_BIAS_F32: return launch_gemm_2cta<256, DICOW_EPI_BIAS_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
-    case DICOW_EPI_GELU_FDDT_POS_F32:
-      return launch_gemm_2cta<256, DICOW_EPI_GELU_FDDT_POS_F32>(ctx, tmA, tmA2, tmW, tmO, p, stream);
-    default: return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: unknown epilogue %d", epi);
+// which (epilogue, operand layout) combinations exist as CTA-pair instantiations
+bool has_2cta(int epi, bool a_t, bool w_t) {
+  if (!a_t && !w_t)
+    return epi == DICOW_EPI_BIAS_BF16 || epi == DICOW_EPI_BIAS_GELU_BF16 || epi == DICOW_EPI_RESIDUAL_F32 ||
+           epi == DICOW_EPI_BIAS_F32 || epi == DICOW_EPI_GELU_FDDT_POS_F32 || epi == DICOW_EPI_GELU_SAVE_BF16 ||
+           epi == DICOW_EPI_ACCUM_F32;
+  if (!a_t && w_t) return epi == DICOW_EPI_BIAS_BF16 || epi == DICOW_EPI_DGELU_BF16 || epi == DICOW_EPI_ACCUM_F32;
+  if (a_t && w_t) return epi == DICOW_EPI_ACCUM_F32;
+  return false;
+}
+
+int dispatch_epi_2cta(dicow_ctx* ctx, int epi, bool a_t, bool w_t, const CUtensorMap& tmA, const CUtensorMap& tmA2,
+                      const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmX, const GemmParams& p,
+                      cudaStream_t stream) {
+#define DICOW_2CTA(E, AT, WT) return launch_gemm_2cta<256, E, AT, WT>(ctx, tmA, tmA2, tmW, tmO, tmX, p, stream)
+  if (!a_t && !w_t) {
+    switch (epi) {
+      case DICOW_EPI_BIAS_BF16: DICOW_2CTA(DICOW_EPI_BIAS_BF16, false, false);
+      case DICOW_EPI_BIAS_GELU_BF16: DICOW_2CTA(DICOW_EPI_BIAS_GELU_BF16, false, false);
+      case DICOW_EPI_RESIDUAL_F32: DICOW_2CTA(DICOW_EPI_RESIDUAL_F32, false, false);
+      case DICOW_EPI_BIAS_F32: DICOW_2CTA(DICOW_EPI_BIAS_F32, false, false);
+      case DICOW_EPI_GELU_FDDT_POS_F32: DICOW_2CTA(DICOW_EPI_GELU_FDDT_POS_F32, false, false);
+      case DICOW_EPI_GELU_SAVE_BF16: DICOW_2CTA(DICOW_EPI_GELU_SAVE_BF16, false, false);
+      case DICOW_EPI_ACCUM_F32: DICOW_2CTA(DICOW_EPI_ACCUM_F32, false, false);
+      default: break;
+    }
+  } else if (!a_t && w_t) {
+    switch (epi) {
+      case DICOW_EPI_BIAS_BF16: DICOW_2CTA(DICOW_EPI_BIAS_BF16, false, true);
+      case DICOW_EPI_DGELU_BF16: DICOW_2CTA(DICOW_EPI_DGELU_BF16, false, true);
+      case DICOW_EPI_ACCUM_F32: DICOW_2CTA(DICOW_EPI_ACCUM_F32, false, true);
+      default: break;
+    }
+  } else if (a_t && w_t) {
+    if (epi == DICOW_EPI_ACCUM_F32) DICOW_2CTA(DICOW_EPI_ACCUM_F32, true, true);
   }
+#undef DICOW_2CTA
+  return set_error(ctx, DICOW_ERR_INVALID_ARG, "dicow_gemm_bf16: no CTA-pair kernel for epilogue %d (transposed %d, %d)", epi,
+                   (int)a_t, (int)w_t);
+}
+
+// Split-K factor of an accumulating GEMM: the one that minimises rounds x (k blocks per item + a per-item epilogue cost) over
+// `workers` persistent CTAs (CTA pairs).  "About two waves" (round 1) put e.g. 300 items on 148 CTAs: three rounds for 2.03
+// waves of work.
+int choose_splits(int tiles, int kblocks, int workers) {
+  const double epi_cost = 4.0;  // in k blocks: the exposed part of an item's drain + pipeline refill
+  int best = 1;
+  double best_cost = 1e30;
+  const int smax = kblocks < 48 ? kblocks : 48;
+  for (int s = 1; s <= smax; ++s) {
+    const int per = ceil_div(kblocks, s);
+    if (per < 6 && s > 1) break;  // keep the mainloop of an item longer than its drain
+    const int s_eff = ceil_div(kblocks, per);
+    const long long items = (long long)tiles * s_eff;
+    const long long rounds = (items + workers - 1) / workers;
+    const double cost = (double)rounds * (per + epi_cost);
+    if (cost < best_cost * 0.995) best_cost = cost, best = s_eff;
+  }
+  return best;
 }
 
 template <int BN>
@@ -804,12 +921,20 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   DICOW_REQUIRE(ctx, (!a_t || (a->Mb % 8) == 0) && (!w_t || (a->N % 8) == 0),
                 "dicow_gemm_bf16: transposed operands need Mb / N multiples of 8");
   const int BN = a->N >= 256 ? 256 : 128;
-  // CTA pairs (256-row tiles) when every pair gets at least ~2 tiles; `flags & 1` forces the single-CTA kernel,
-  // `flags & 2` forces pairs (tests / comparison)
+  // CTA pairs (256-row tiles) when every pair gets at least ~2 tiles (split-K GEMMs: whenever a tile has 256 rows to fill);
+  // `flags & 1` forces the single-CTA kernel, `flags & 2` forces pairs (tests / comparison).  DICOW_GEMM_2CTA_BWD=0 keeps
+  // the round-1 behaviour (backward / training epilogues on the single-CTA kernel) for A/B measurements.
+  static const int bwd_pairs = [] {
+    const char* e = getenv("DICOW_GEMM_2CTA_BWD");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
   const long long tiles128 = (long long)a->nb * ceil_div(a->Mb, BM) * ceil_div(a->N, BN);
-  bool two_cta = BN == 256 && tiles128 >= 2 * (long long)ctx->num_sms;
-  if ((a->flags & 1) || a_t || w_t || a->epilogue >= DICOW_EPI_ACCUM_F32) two_cta = false;
-  if ((a->flags & 2) && BN == 256) two_cta = true;
+  const bool auto_split = a->epilogue == DICOW_EPI_ACCUM_F32 && a->splits != 1;
+  bool two_cta = BN == 256 && has_2cta(a->epilogue, a_t, w_t) &&
+                 (auto_split ? a->Mb >= 2 * BM : tiles128 >= 2 * (long long)ctx->num_sms);
+  if (!bwd_pairs && (a_t || w_t || a->epilogue >= DICOW_EPI_ACCUM_F32)) two_cta = false;
+  if (a->flags & 1) two_cta = false;
+  if ((a->flags & 2) && BN == 256 && has_2cta(a->epilogue, a_t, w_t)) two_cta = true;
   GemmParams p{};
   p.nb = a->nb, p.Mb = a->Mb, p.N = a->N, p.K = a->K, p.K1 = split ? a->K1 : 0;
   p.tiles_m = ceil_div(a->Mb, two_cta ? 2 * BM : BM);
@@ -817,9 +942,8 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
   p.total_tiles = a->nb * p.tiles_m * p.tiles_n;
   p.kblocks = ceil_div(a->K, BK);
   p.splits = 1;
-  if (a->epilogue == DICOW_EPI_ACCUM_F32 && a->splits != 1) {
-    // split the contraction so that about two waves of CTAs are busy (explicit a->splits > 1 overrides)
-    int want = a->splits > 1 ? a->splits : ceil_div(2 * ctx->num_sms, p.total_tiles);
+  if (auto_split) {  // explicit a->splits > 1 overrides
+    int want = a->splits > 1 ? a->splits : choose_splits(p.total_tiles, p.kblocks, two_cta ? ctx->num_sms / 2 : ctx->num_sms);
     want = want < 1 ? 1 : (want > p.kblocks ? p.kblocks : want);
     p.splits = want;
   }
@@ -892,19 +1016,14 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
     int rc = make_tmap_bf16(ctx, &tmW, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  if (a_t || w_t) {
-    if (BN == 256) return dispatch_transposed<256>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
-    return dispatch_transposed<128>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
-  }
   if (two_cta) {
-    // output tensor map for the TMA-store epilogue: [N, Mb, nb] bf16, box 64 columns x 32 rows (one epilogue warp's tile)
-    CUtensorMap tmO = tmA;
+    // output tensor map(s) for the TMA-store epilogue: [N, Mb, nb] bf16, box 64 columns x 32 rows (one epilogue warp's tile)
+    CUtensorMap tmO = tmA, tmX = tmA;
     static const int tma_store = [] {
       const char* e = getenv("DICOW_GEMM_TMA_STORE");
       return (e != nullptr && e[0] == '0') ? 0 : 1;
     }();
-    const bool bf16_plain = a->epilogue == DICOW_EPI_BIAS_BF16 || a->epilogue == DICOW_EPI_BIAS_GELU_BF16;
-    if (tma_store && bf16_plain && (a->ldo % 8) == 0 && (a->out_batch_stride % 8) == 0 &&
+    if (tma_store && out_is_bf16 && (a->ldo % 8) == 0 && (a->out_batch_stride % 8) == 0 &&
         (reinterpret_cast<uintptr_t>(a->out) % 16) == 0 && (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) % 16) == 0)) {
       uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->Mb, (uint64_t)a->nb};
       uint64_t bs = a->nb > 1 ? (uint64_t)a->out_batch_stride : (uint64_t)a->ldo * (uint64_t)a->Mb;
@@ -912,9 +1031,17 @@ extern "C" int dicow_gemm_bf16(dicow_handle_t h, const dicow_gemm_args_t* a, voi
       uint32_t box[3] = {64, 32, 1};
       int rc = make_tmap_bf16(ctx, &tmO, a->out, 3, dims, strides, box);
       if (rc) return rc;
+      if (a->epilogue == DICOW_EPI_GELU_SAVE_BF16) {  // the saved pre-activation: same shape and strides as out
+        rc = make_tmap_bf16(ctx, &tmX, a->aux_bf16, 3, dims, strides, box);
+        if (rc) return rc;
+      }
       p.tma_out = 1;
     }
-    return dispatch_epi_2cta(ctx, a->epilogue, tmA, tmA2, tmW, tmO, p, stream);
+    return dispatch_epi_2cta(ctx, a->epilogue, a_t, w_t, tmA, tmA2, tmW, tmO, tmX, p, stream);
+  }
+  if (a_t || w_t) {
+    if (BN == 256) return dispatch_transposed<256>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
+    return dispatch_transposed<128>(ctx, a->epilogue, a_t, w_t, tmA, tmW, p, stream);
   }
   if (BN == 256) return dispatch_epi<256>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
   return dispatch_epi<128>(ctx, a->epilogue, tmA, tmA2, tmW, p, stream);
