@@ -196,9 +196,11 @@ typedef struct {
 
 DICOW_API int dicow_attention_bf16(dicow_handle_t h, const dicow_attention_args_t* args, void* stream);
 /* ------------------------------------------------------------------------------------------------------------
- * Attention backward (training): dQ, dK, dV from dO, the forward's Q / K / V / O and its saved lse.  Two tcgen05 passes
- * (dQ; dK + dV) that recompute the probabilities; no atomics.  dO shares O's strides; dK / dV share one stride pair.
- * workspace: B * H * Tq floats.  Replaces autograd through the SDPA call of HF WhisperAttention
+ * Attention backward (training): dQ, dK, dV from dO, the forward's Q / K / V / O and its saved lse.  Non-causal shapes with
+ * Tq >= 256 and a workspace of B * H * Tq * 65 + 4 floats: ONE tcgen05 pass per (batch, head, 128 keys) -- 5 GEMMs, dQ partial
+ * sums reduced with fp32 red.global into the workspace (summation order not deterministic).  Otherwise two passes
+ * (dQ; dK + dV) that recompute the probabilities; no atomics (workspace: B * H * Tq floats).  dO shares O's strides; dK / dV
+ * share one stride pair.  Replaces autograd through the SDPA call of HF WhisperAttention
  * (HF:modeling_whisper.py:342-352) in the fine-tuning step.
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -220,6 +222,7 @@ typedef struct {
   int64_t dkv_row_stride, dkv_batch_stride;
   int32_t causal;
   float* workspace;
+  int64_t workspace_floats; /* size of workspace; >= B*H*Tq*65 + 4 enables the single-pass kernel (0: B*H*Tq, two passes) */
 } dicow_attention_bwd_args_t;
 DICOW_API int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_bwd_args_t* args, void* stream);
 

@@ -69,6 +69,13 @@ def test_colsum_and_gelu_epilogues(ops, form, M, N, K):
     ops.colsum(X, out, alpha=0.5)
     torch.cuda.synchronize()
     assert rel(out, 1 + 0.5 * X.float().sum(0)) < 1e-3
+    # 16-byte vector path: aligned widths, a column block of a fused projection (row stride 3 N), ragged row count
+    Y = torch.randn(5001, 3 * 1280, device=DEV, generator=g).bfloat16()
+    for cols in (slice(0, 1280), slice(2560, 3840)):
+        out = torch.zeros(1280, device=DEV)
+        ops.colsum(Y[:, cols], out, alpha=0.125)
+        torch.cuda.synchronize()
+        assert rel(out, 0.125 * Y[:, cols].float().sum(0)) < 1e-3
     # fc1 training forward saves the pre-activation; the fc2 dgrad multiplies by gelu'(pre)
     A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=DEV, generator=g) * 0.08).bfloat16()

@@ -176,7 +176,10 @@ def test_gemm_backward_variants(ops, M, N, K, form):
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 3, 1500, 1500, False), (1, 2, 200, 200, True), (2, 2, 37, 300, False),
-                                              (1, 4, 448, 448, True), (3, 2, 64, 64, False)])
+                                              (1, 4, 448, 448, True), (3, 2, 64, 64, False),
+                                              # single-pass kernel (non-causal, Tq >= 256): ragged tails, one key tile, many items
+                                              (1, 2, 300, 520, False), (1, 1, 256, 128, False), (2, 2, 1000, 700, False),
+                                              (3, 20, 1500, 1500, False)])
 def test_attention_backward(ops, B, H, Tq, Tk, causal):
     """dQ / dK / dV of the tcgen05 backward passes vs torch autograd through fp32 softmax attention"""
     dev = torch.device("cuda:0")

@@ -21,8 +21,21 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static int make_tmap(dicow_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
 int make_tmap_bf16(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(ctx, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
+int make_tmap_f32(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(ctx, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+
+static int make_tmap(dicow_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   if (ctx->encode_tiled == nullptr)
     return set_error(ctx, DICOW_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[5];
@@ -36,7 +49,7 @@ int make_tmap_bf16(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank,
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = reinterpret_cast<encode_tiled_fn>(ctx->encode_tiled)(
-      out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+      out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -17,6 +17,9 @@
 // fine-tuning step (src/train.py -> HF Trainer.training_step -> loss.backward()).
 #include <math.h>
 
+#include <stdlib.h>
+
+#include "attention_common.h"
 #include "common.h"
 #include "ptx.cuh"
 
@@ -411,6 +414,23 @@ extern "C" int dicow_attention_bwd_bf16(dicow_handle_t h, const dicow_attention_
   rc |= make_map(ctx, &mQs, a->Q, a->Tq, a->H, a->B, a->q_row_stride, qbs, BLK);
   rc |= make_map(ctx, &mdOs, a->dO, a->Tq, a->H, a->B, a->o_row_stride, obs, BLK);
   if (rc) return DICOW_ERR_CUDA;
+  // Single pass (attention_bwd_fused.cu) at the encoder's shapes when the caller brought the dQ workspace:
+  // non-causal, at least two query blocks; DICOW_ATTN_BWD_FUSED=0 keeps the two passes (A/B measurements)
+  static const int fused_on = [] {
+    const char* e = getenv("DICOW_ATTN_BWD_FUSED");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  const long long n_stat = (((long long)a->B * a->H * a->Tq + 3) / 4) * 4;  // keeps the accumulator 16-byte aligned
+  const long long need = n_stat + (long long)a->B * a->H * a->Tq * HD;
+  if (fused_on && !a->causal && a->Tq >= 256 && a->Tk >= 128 && a->workspace_floats >= need) {
+    FusedBwdArgs f{};
+    f.B = a->B, f.H = a->H, f.Tq = a->Tq, f.Tk = a->Tk;
+    f.lse = a->lse, f.D = D, f.dq_acc = a->workspace + n_stat;
+    f.dQ = reinterpret_cast<__nv_bfloat16*>(a->dQ), f.dK = reinterpret_cast<__nv_bfloat16*>(a->dK);
+    f.dV = reinterpret_cast<__nv_bfloat16*>(a->dV);
+    f.dq_rs = a->dq_row_stride, f.dq_bs = a->dq_batch_stride, f.dkv_rs = a->dkv_row_stride, f.dkv_bs = a->dkv_batch_stride;
+    return launch_attention_bwd_fused(ctx, mQo, mdOo, mKo, mVo, f, stream);
+  }
   // pass dQ
   p.out1 = reinterpret_cast<__nv_bfloat16*>(a->dQ), p.o1_rs = a->dq_row_stride, p.o1_bs = a->dq_batch_stride;
   p.out2 = nullptr, p.o2_rs = p.o2_bs = 0;

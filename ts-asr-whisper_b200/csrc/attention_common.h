@@ -22,4 +22,18 @@ struct AttnParams {
 int launch_attention_fa(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                         const AttnParams& p, int emu, cudaStream_t stream);
 
+// single-pass backward (attention_bwd_fused.cu): non-causal, query blocks of 128; dq_acc is an fp32 [B, Tq, H * 64] workspace
+struct FusedBwdArgs {
+  int B, H, Tq, Tk;
+  const float* lse;
+  const float* D;
+  float* dq_acc;
+  __nv_bfloat16* dQ;
+  __nv_bfloat16* dK;
+  __nv_bfloat16* dV;
+  long long dq_rs, dq_bs, dkv_rs, dkv_bs;
+};
+int launch_attention_bwd_fused(dicow_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmdO, const CUtensorMap& tmK,
+                               const CUtensorMap& tmV, const FusedBwdArgs& a, cudaStream_t stream);
+
 }  // namespace dicow

@@ -40,6 +40,9 @@ int set_error(dicow_ctx* ctx, int code, const char* fmt, ...);
 //   rank 2 or 3; dims[] innermost first (elements); strides_bytes[] for dims 1..rank-1; box[] elements.
 int make_tmap_bf16(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// same for fp32 tensors (box inner extent <= 32 elements = one 128-byte swizzle row)
+int make_tmap_f32(dicow_ctx* ctx, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
 
 int mel_tables_create(dicow_ctx* ctx);  // mel.cu
 

@@ -25,6 +25,8 @@
 // (HF:models/whisper/modeling_whisper.py:449-506, 691-796) inside DiCoWGenerationMixin._sample (generation.py:707-782).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -673,14 +675,22 @@ extern "C" int dicow_decode_layers(dicow_handle_t h, const dicow_decode_layers_a
   static DeviceHighWater attr_smem;
   if (attr_smem.raise(ctx, smem))
     DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(decode_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // one CTA per SM, all co-resident (cooperative launch: the grid barrier needs every CTA running)
+  // One CTA per SM; the grid barrier needs every CTA running.  The shared-memory footprint admits exactly one CTA per SM and
+  // the grid is the SM count, so all CTAs become resident as soon as the kernels ahead of this one in the stream drain: a plain
+  // launch is enough.  DICOW_MEGA_COOPERATIVE=1 asks the driver to verify co-residency (cooperative launch) -- not the default:
+  // with driver 580.159 cuLaunchKernelEx crashed (SIGSEGV inside libcuda) on the first cooperative launch of a process that had
+  // run the training tests before (tests/test_gpu_training.py followed by tests/test_gpu_turbo_parity.py).
+  static const int cooperative = [] {
+    const char* e = getenv("DICOW_MEGA_COOPERATIVE");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctx->num_sms), cfg.blockDim = dim3(MK_THREADS), cfg.dynamicSmemBytes = smem;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream_);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.attrs = attr, cfg.numAttrs = cooperative ? 1 : 0;
   DICOW_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, decode_layers_kernel, p));
   return DICOW_OK;
 }

@@ -84,7 +84,7 @@ class AttentionBwdArgs(C.Structure):
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("dq_row_stride", C.c_int64), ("dq_batch_stride", C.c_int64),
         ("dkv_row_stride", C.c_int64), ("dkv_batch_stride", C.c_int64),
-        ("causal", C.c_int32), ("workspace", C.c_void_p),
+        ("causal", C.c_int32), ("workspace", C.c_void_p), ("workspace_floats", C.c_int64),
     ]
 
 

@@ -724,7 +724,9 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, *, B: int, H: int, Tq: int, T
     """dQ / dK / dV of softmax(Q K^T) V (dicow_attention_bwd_bf16); all tensors bf16 views addressed by explicit
     strides (elements), ``lse`` fp32 [B, H, Tq] as saved by attention(..., lse=...); ``do`` shares ``o``'s strides."""
     dev = _require_cuda(q, k, v, o, do, lse, dq, dk, dv)
-    ws = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
+    # per-query D = sum(dO * O), plus (non-causal encoder shapes) the fp32 dQ accumulator of the single-pass kernel
+    n_ws = B * H * Tq * 65 + 4 if (not causal and Tq >= 256 and Tk >= 128) else B * H * Tq
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
     a = _lib.AttentionBwdArgs()
     a.struct_size = C.sizeof(_lib.AttentionBwdArgs)
     a.Q, a.K, a.V, a.O, a.dO, a.lse = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(do), _ptr(lse)
@@ -737,6 +739,7 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, *, B: int, H: int, Tq: int, T
     a.dkv_row_stride, a.dkv_batch_stride = dkv_row_stride, dkv_batch_stride
     a.causal = 1 if causal else 0
     a.workspace = _ptr(ws)
+    a.workspace_floats = n_ws
     fl = 10.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)  # 5 GEMMs; S and dP are recomputed in the 2nd pass
     _call("dicow_attention_bwd_bf16", dev, a, "attention_bwd", fl)
 
