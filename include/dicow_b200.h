@@ -140,8 +140,9 @@ typedef struct {
   void* x_out_bf16;  /* [rows, d] bf16 copy of x' or NULL */
   const void* delta1_bf16; /* [rows, d] bf16 or NULL */
   const void* delta2_bf16; /* [rows, d] bf16 or NULL */
-  int32_t store_x;         /* write x' back into x */
+  int32_t store_x;         /* write x' back into x (or into x_out) */
   int32_t flags;           /* 0 = default (TMA-pipelined rows); bit 0: warp-per-row kernel, bit 1: column-owner kernel (comparison) */
+  float* x_out;            /* NULL: x' overwrites x; else x' goes to this [rows, d] fp32 buffer and x stays as it was */
 } dicow_fddt_ln_args_t;
 
 DICOW_API int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t* args, void* stream);
@@ -252,6 +253,8 @@ typedef struct {
   float* dbeta;
   float* dfddt_w;
   float* dfddt_b;
+  float* g_colsum; /* [d] += column sums of the rows written to g_out_bf16 (= the bias gradient of the Linear whose output
+                      was a pending delta of this LayerNorm), or NULL */
 } dicow_ln_bwd_args_t;
 DICOW_API int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_args_t* args, void* stream);
 

@@ -41,6 +41,7 @@ struct LnBwdParams {
   float* dbeta;                // [d] +=
   float* dfddt_w;              // [4, d] += (or NULL)
   float* dfddt_b;              // [4, d] +=
+  float* gsum;                 // [d] += column sums of g_out_bf16 (the bias gradient of the Linear that produced a delta), or NULL
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring
   const int tid = (warp - 1 - RB_NS) * 32 + lane;
   const bool own = tid < nvec;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 tw[4], tb[4], g4 = z4, acc_dg = z4, acc_db = z4, acc_w[4], acc_b[4];
+  float4 tw[4], tb[4], g4 = z4, acc_dg = z4, acc_db = z4, acc_gs = z4, acc_w[4], acc_b[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     tw[c] = make_float4(1.f, 1.f, 1.f, 1.f), tb[c] = z4, acc_w[c] = z4, acc_b[c] = z4;
@@ -398,11 +399,15 @@ __global__ void __launch_bounds__((1 + RB_NS + RB_VPL) * 32, 1) ln_fddt_bwd_ring
     if (lane == 0) mbar_arrive(&empty[st]);  // this warp's smem reads of the stage are done
     if (own) {
       reinterpret_cast<float4*>(p.g_out + row * d)[tid] = g;
-      if (p.g_out_bf16 != nullptr)
-        reinterpret_cast<uint2*>(p.g_out_bf16 + row * d)[tid] = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+      if (p.g_out_bf16 != nullptr) {
+        const uint2 pk = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+        reinterpret_cast<uint2*>(p.g_out_bf16 + row * d)[tid] = pk;
+        acc_gs = f4_add(acc_gs, bf16x4(pk));  // what a column sum over the stored bf16 rows would add
+      }
     }
   }
   if (own) {
+    if (p.gsum != nullptr && p.g_out_bf16 != nullptr) atomic_add4(p.gsum + 4 * tid, acc_gs);
     if (has_ln && p.dgamma != nullptr) {
       atomic_add4(p.dgamma + 4 * tid, acc_dg);
       atomic_add4(p.dbeta + 4 * tid, acc_db);
@@ -916,6 +921,9 @@ extern "C" int dicow_fddt_full_scatter(dicow_handle_t h, const float* g, const f
   return DICOW_OK;
 }
 
+extern "C" int dicow_colsum(dicow_handle_t h, const void* x, int is_bf16, int64_t ld, int rows, int N, float* out,
+                            float alpha, void* stream_);
+
 extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_args_t* a, void* stream_) {
   if (h == nullptr) return DICOW_ERR_INVALID_ARG;
   dicow_ctx* ctx = h;
@@ -933,6 +941,8 @@ extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_arg
   p.gamma = a->gamma, p.eps = a->eps, p.dy = reinterpret_cast<const __nv_bfloat16*>(a->dy_bf16), p.g_in = a->g_in;
   p.g_out = a->g_out, p.g_out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->g_out_bf16);
   p.dgamma = a->dgamma, p.dbeta = a->dbeta, p.dfddt_w = a->dfddt_w, p.dfddt_b = a->dfddt_b;
+  p.gsum = a->g_colsum;
+  DICOW_REQUIRE(ctx, a->g_colsum == nullptr || a->g_out_bf16 != nullptr, "dicow_layernorm_fddt_bwd: g_colsum needs g_out_bf16");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const bool aligned = (a->d % 8) == 0 && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&
                        (reinterpret_cast<uintptr_t>(a->delta1_bf16) % 16) == 0 &&
@@ -958,6 +968,8 @@ extern "C" int dicow_layernorm_fddt_bwd(dicow_handle_t h, const dicow_ln_bwd_arg
   const int grid = groups < 2 * ctx->num_sms ? groups : 2 * ctx->num_sms;
   ln_fddt_bwd_kernel<<<grid, threads, 0, stream>>>(p, groups);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
+  if (p.gsum != nullptr)  // this kernel does not carry the column sums: a separate pass over the bf16 rows
+    return dicow_colsum(h, p.g_out_bf16, 1, a->d, a->rows, a->d, p.gsum, 1.0f, stream_);
   return DICOW_OK;
 }
 

@@ -30,7 +30,8 @@ struct FddtLnParams {
   // pending residual updates (bf16 GEMM outputs: out_proj / fc2), added before FDDT: x' = FDDT(x + delta1 + delta2)
   const __nv_bfloat16* delta1;
   const __nv_bfloat16* delta2;
-  int store_x;  // write x' back to x
+  int store_x;  // write x' back (to xs)
+  float* xs;    // where x' goes: x itself, or a separate [rows, d] buffer (the training forward keeps x as a saved activation)
 };
 
 // one warp per row; VPL float4 per lane (d <= 128 * VPL)
@@ -91,10 +92,11 @@ __global__ void __launch_bounds__(256) fddt_ln_kernel(const FddtLnParams p) {
     }
   }
   if (p.store_x) {
+    float4* xsrow = reinterpret_cast<float4*>(p.xs + (long long)row * p.d);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c4 = lane + 32 * i;
-      if (c4 < nvec) xrow[c4] = v[i];
+      if (c4 < nvec) xsrow[c4] = v[i];
     }
   }
   if (p.x_bf16 != nullptr) {
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__((LT_NW + 1) * 32, 1) fddt_ln_tma_kernel(const 
       }
     }
     if (p.store_x) {
-      float4* xrow = reinterpret_cast<float4*>(p.x + (long long)row * d);
+      float4* xrow = reinterpret_cast<float4*>(p.xs + (long long)row * d);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int c4 = lane + 32 * k;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(512) fddt_ln_cols_kernel(const FddtLnParams p,
     for (int r = 0; r < LN_ROWS; ++r) {
       const int row = row0 + r;
       if (own && row < p.rows) {
-        if (p.store_x) reinterpret_cast<float4*>(p.x + (long long)row * p.d)[tid] = v[r];
+        if (p.store_x) reinterpret_cast<float4*>(p.xs + (long long)row * p.d)[tid] = v[r];
         if (p.x_bf16 != nullptr)
           reinterpret_cast<uint2*>(p.x_bf16 + (long long)row * p.d)[tid] =
               make_uint2(pack_bf16(v[r].x, v[r].y), pack_bf16(v[r].z, v[r].w));
@@ -631,6 +633,7 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   p.delta1 = reinterpret_cast<const __nv_bfloat16*>(a->delta1_bf16);
   p.delta2 = reinterpret_cast<const __nv_bfloat16*>(a->delta2_bf16);
   p.store_x = a->store_x;
+  p.xs = a->x_out != nullptr ? a->x_out : a->x;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   // default: TMA-pipelined kernel (needs 16-byte rows: d % 8 == 0); flags bit 0 -> warp-per-row, bit 1 -> column-owner.
   // A handful of rows (the decode step: one row per sequence) cannot amortise the ring's set-up (measured 7.1 us for

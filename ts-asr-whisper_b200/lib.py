@@ -58,6 +58,7 @@ class FddtLnArgs(C.Structure):
         ("eps", C.c_float),
         ("ln_out_bf16", C.c_void_p), ("ln_out_f32", C.c_void_p), ("x_out_bf16", C.c_void_p),
         ("delta1_bf16", C.c_void_p), ("delta2_bf16", C.c_void_p), ("store_x", C.c_int32), ("flags", C.c_int32),
+        ("x_out", C.c_void_p),
     ]
 
 
@@ -96,7 +97,7 @@ class LnBwdArgs(C.Structure):
         ("stno", C.c_void_p), ("stno_batch_stride", C.c_int64), ("fddt_w", C.c_void_p), ("fddt_b", C.c_void_p),
         ("gamma", C.c_void_p), ("eps", C.c_float), ("dy_bf16", C.c_void_p), ("g_in", C.c_void_p),
         ("g_out", C.c_void_p), ("g_out_bf16", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
-        ("dfddt_w", C.c_void_p), ("dfddt_b", C.c_void_p),
+        ("dfddt_w", C.c_void_p), ("dfddt_b", C.c_void_p), ("g_colsum", C.c_void_p),
     ]
 
 

@@ -143,7 +143,8 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
                    gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-5,
                    ln_out_bf16: Optional[torch.Tensor] = None, ln_out_f32: Optional[torch.Tensor] = None,
                    x_out_bf16: Optional[torch.Tensor] = None, delta1: Optional[torch.Tensor] = None,
-                   delta2: Optional[torch.Tensor] = None, store_x: Optional[bool] = None, flags: int = 0) -> None:
+                   delta2: Optional[torch.Tensor] = None, store_x: Optional[bool] = None, flags: int = 0,
+                   x_out: Optional[torch.Tensor] = None) -> None:
     """x' = FDDT(x + delta1 + delta2) on the fp32 residual rows of ``x`` ([..., d], contiguous), written back when
     ``store_x`` (default: whenever x' differs from x), + LayerNorm outputs (dicow_fddt_layernorm).  ``stno`` is
     [B, 4, T] fp32 with ``B*T == rows``; the deltas are bf16 [rows, d] (pending out_proj / fc2 outputs)."""
@@ -174,6 +175,9 @@ def fddt_layernorm(x: torch.Tensor, *, T: int = 0, stno: Optional[torch.Tensor] 
     a.delta1_bf16, a.delta2_bf16 = _ptr(delta1), _ptr(delta2)
     a.store_x = 1 if store_x else 0
     a.flags = flags
+    if x_out is not None:  # x' goes to x_out, x is left untouched
+        assert store_x and x_out.dtype == torch.float32 and x_out.is_contiguous() and x_out.numel() == x.numel() and x_out.is_cuda
+        a.x_out = _ptr(x_out)
     _call("dicow_fddt_layernorm", dev, a, "fddt_ln")
 
 
@@ -750,10 +754,12 @@ def layernorm_fddt_bwd(x: torch.Tensor, g_out: torch.Tensor, *, dy: Optional[tor
                        stno: Optional[torch.Tensor] = None, fddt_w: Optional[torch.Tensor] = None,
                        fddt_b: Optional[torch.Tensor] = None, g_out_bf16: Optional[torch.Tensor] = None,
                        dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
-                       dfddt_w: Optional[torch.Tensor] = None, dfddt_b: Optional[torch.Tensor] = None) -> None:
-    """backward of fddt_layernorm (dicow_layernorm_fddt_bwd); parameter gradients are accumulated (+=)."""
+                       dfddt_w: Optional[torch.Tensor] = None, dfddt_b: Optional[torch.Tensor] = None,
+                       g_colsum: Optional[torch.Tensor] = None) -> None:
+    """backward of fddt_layernorm (dicow_layernorm_fddt_bwd); parameter gradients are accumulated (+=).  ``g_colsum`` [d] fp32
+    += the column sums of ``g_out_bf16`` (the bias gradient of the Linear whose output was a pending delta)."""
     dev = _require_cuda(x, g_out, dy, g_in, gamma, delta1, delta2, stno, fddt_w, fddt_b, g_out_bf16, dgamma, dbeta,
-                        dfddt_w, dfddt_b)
+                        dfddt_w, dfddt_b, g_colsum)
     a = _lib.LnBwdArgs()
     a.struct_size = C.sizeof(_lib.LnBwdArgs)
     a.x, a.delta1_bf16, a.delta2_bf16 = _ptr(x), _ptr(delta1), _ptr(delta2)
@@ -766,6 +772,9 @@ def layernorm_fddt_bwd(x: torch.Tensor, g_out: torch.Tensor, *, dy: Optional[tor
     a.gamma, a.eps = _ptr(gamma), eps
     a.dy_bf16, a.g_in, a.g_out, a.g_out_bf16 = _ptr(dy), _ptr(g_in), _ptr(g_out), _ptr(g_out_bf16)
     a.dgamma, a.dbeta, a.dfddt_w, a.dfddt_b = _ptr(dgamma), _ptr(dbeta), _ptr(dfddt_w), _ptr(dfddt_b)
+    if g_colsum is not None:
+        assert g_colsum.dtype == torch.float32 and g_colsum.numel() == x.shape[-1] and g_out_bf16 is not None
+        a.g_colsum = _ptr(g_colsum)
     _call("dicow_layernorm_fddt_bwd", dev, a, "ln_bwd")
 
 

@@ -130,7 +130,8 @@ class _Grads:
 def _linear_backward(g: _Grads, dY: torch.Tensor, X: torch.Tensor, W_prep: torch.Tensor, weight: torch.nn.Parameter,
                      bias: Optional[torch.nn.Parameter], *, need_dx: bool = True, dx_epilogue: int = ops.EPI_BIAS_BF16,
                      aux: Optional[torch.Tensor] = None, scale: float = 1.0, dy_cols: Optional[slice] = None,
-                     w_rows: Optional[slice] = None, dx_accum: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                     w_rows: Optional[slice] = None, dx_accum: Optional[torch.Tensor] = None,
+                     bias_done: bool = False) -> Optional[torch.Tensor]:
     """Backward of Y = X W^T + b for bf16 operands: dX = dY W (bf16, optional gelu' epilogue; or accumulated into the
     fp32 ``dx_accum``), dW += scale * dY^T X, db += scale * colsum(dY).  ``dy_cols`` selects a column block of dY (fused
     projections), ``w_rows`` the matching rows of the prepared weight.  X [M, K], dY [M, N], W_prep [N, K] bf16."""
@@ -147,7 +148,7 @@ def _linear_backward(g: _Grads, dY: torch.Tensor, X: torch.Tensor, W_prep: torch
         alpha = None if scale == 1.0 else _dev_scalar(scale, X.device)
         ops.gemm(dYs, X, g.get(weight).view(Ws.shape[0], -1), epilogue=ops.EPI_ACCUM_F32, flags=ops.GEMM_A_T | ops.GEMM_W_T,
                  gate=alpha, lda=dY.stride(0), Mb=Ws.shape[0], K=X.shape[0], N=X.shape[1])
-    if g.want(bias):
+    if g.want(bias) and not bias_done:  # bias_done: the kernel that produced dY has added its column sums already
         ops.colsum(dYs, g.get(bias), alpha=scale)
     lora = getattr(weight, "_dicow_lora", None)
     if lora is not None and (g.want(lora.lora_A) or g.want(lora.lora_B)):
@@ -275,8 +276,8 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
         raise ValueError("scb_layers exceeds the number of encoder layers")
     for i, e in enumerate(w["layers"]):
         fd = w["fddt"][i] if (cfg.use_fddt and i < len(w["fddt"])) else None
-        x_pre = x
-        x = x_pre.clone()  # the stream before this layer's pending deltas / FDDT is an input of the backward
+        x_pre = x_in = x  # the stream before this layer's pending deltas / FDDT is an input of the backward:
+        x = torch.empty_like(x_pre)  # the first kernel of the layer reads x_in and writes the updated stream to x (no copy)
         scb = None
         rows_in, stno_in = rows, stno
         full = None
@@ -285,17 +286,18 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
             # stacked [4 d, d] class transforms, mask-weighted sum back into the fp32 stream.  For the rest of the layer
             # (and its backward) the transformed stream is the layer input: no table, no pending deltas.
             xb_in = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
-            ops.fddt_layernorm(x, x_out_bf16=xb_in, delta1=d1, delta2=d2, store_x=True)
+            ops.fddt_layernorm(x_in, x_out_bf16=xb_in, delta1=d1, delta2=d2, store_x=True, x_out=x)
             y = torch.empty(rows, 4 * d, dtype=torch.bfloat16, device=dev)
             ops.gemm(xb_in, fd[0], y, epilogue=ops.EPI_BIAS_BF16, bias=fd[1])
             ops.fddt_full_combine(y, stno, x, T=T)
             del y
             full = {"xb": xb_in, "W4": fd[0]}
-            x_pre, fd, d1, d2 = x, None, None, None
+            x_pre, x_in, fd, d1, d2 = x, x, None, None, None
         if i < n_scb:  # encoder.py:205-213: FDDT, speaker communication block, (last SCB layer) drop the enrollment stream
             xb = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
-            ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
-                               fddt_b=fd[1] if fd else None, x_out_bf16=xb, delta1=d1, delta2=d2, store_x=True)
+            ops.fddt_layernorm(x_in, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+                               fddt_b=fd[1] if fd else None, x_out_bf16=xb, delta1=d1, delta2=d2, store_x=True,
+                               x_out=None if x_in is x else x)
             scb = _scb_forward_train(enc, w["scb"][i], x, xb, B // 2, T)
             if i == n_scb - 1:
                 B //= 2
@@ -306,9 +308,9 @@ def encoder_forward_train(enc, input_features: torch.Tensor, stno_mask: Optional
             ops.fddt_layernorm(x, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln1, store_x=False)
         else:
             ln1 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
-            ops.fddt_layernorm(x, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
+            ops.fddt_layernorm(x_in, T=T, stno=stno if fd else None, fddt_w=fd[0] if fd else None,
                                fddt_b=fd[1] if fd else None, gamma=e["ln1_g"], beta=e["ln1_b"], ln_out_bf16=ln1, delta1=d1,
-                               delta2=d2, store_x=True)
+                               delta2=d2, store_x=True, x_out=None if x_in is x else x)
         qkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
         ops.gemm(ln1, e["wqkv"], qkv, epilogue=ops.EPI_BIAS_BF16, bias=e["bqkv"])
         ctx = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
@@ -619,27 +621,37 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
         return ps + ([ln.weight, ln.bias] if i == n_layers - 1 else [])
 
     flat = g.reserve(group(n_layers - 1)) if n_layers else g.reserve([ln.weight, ln.bias])
+
+    def fc2_bias_grad(j):  # Gb is dY of layer j's fc2: the kernel that writes Gb also adds its column sums to the bias gradient
+        if j < 0 or not g.want(enc.layers[j].fc2.bias):
+            return None
+        return g.get(enc.layers[j].fc2.bias)
+
+    gs = fc2_bias_grad(n_layers - 1)
     ops.layernorm_fddt_bwd(f["x"], G, dy=d_hidden_bf16, gamma=w["lnf_g"], delta1=f["d1"], delta2=f["d2"], g_out_bf16=Gb,
                            dgamma=g.get(ln.weight) if g.want(ln.weight) else None,
-                           dbeta=g.get(ln.bias) if g.want(ln.bias) else None)
+                           dbeta=g.get(ln.bias) if g.want(ln.bias) else None, g_colsum=gs)
+    fc2_bias_done = gs is not None
+    flat_next = None
     for i in range(n_layers - 1, -1, -1):
         e, s, lyr = w["layers"][i], tape.layers[i], enc.layers[i]
         B = s["B"]  # streams in this layer's attention / MLP blocks (targets only after the last SCB layer)
         rows = B * T
         if i != n_layers - 1:
-            flat = g.reserve(group(i))
+            flat = flat_next if flat_next is not None else g.reserve(group(i))
         # fc2 / fc1 (G is the gradient of x_post + d1 + d2, hence of d2 = fc2(...) as well)
         dpre = _linear_backward(g, Gb, s["hdn"], e["w2"], lyr.fc2.weight, lyr.fc2.bias, dx_epilogue=ops.EPI_DGELU_BF16,
-                                aux=s["pre"])
+                                aux=s["pre"], bias_done=fc2_bias_done)
         dln2 = _linear_backward(g, dpre, s["ln2"], e["w1"], lyr.fc1.weight, lyr.fc1.bias)
         G2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
         G2b = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
         n2 = lyr.final_layer_norm
+        ob = lyr.self_attn.out_proj.bias  # G2b is dY of out_proj: its column sums (the bias gradient) come with it
         ops.layernorm_fddt_bwd(s["x_post"], G2, dy=dln2, g_in=G, gamma=e["ln2_g"], delta1=s["d1"], g_out_bf16=G2b,
                                dgamma=g.get(n2.weight) if g.want(n2.weight) else None,
-                               dbeta=g.get(n2.bias) if g.want(n2.bias) else None)
+                               dbeta=g.get(n2.bias) if g.want(n2.bias) else None, g_colsum=g.get(ob) if g.want(ob) else None)
         # attention block
-        dctx = _linear_backward(g, G2b, s["ctx"], e["wo"], lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias)
+        dctx = _linear_backward(g, G2b, s["ctx"], e["wo"], lyr.self_attn.out_proj.weight, ob, bias_done=True)
         dqkv = torch.empty(rows, 3 * d, dtype=torch.bfloat16, device=dev)
         qkv = s["qkv"]
         ops.attention_bwd(qkv, qkv[:, d:], qkv[:, 2 * d:], s["ctx"], dctx, s["lse"], dqkv, dqkv[:, d:], dqkv[:, 2 * d:],
@@ -662,11 +674,16 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
         dbet = g.get(n1.bias) if g.want(n1.bias) else None
         G = torch.empty(rows_in, d, dtype=torch.float32, device=dev)
         Gb = torch.empty(rows_in, d, dtype=torch.bfloat16, device=dev)
+        # the Gb written below is dY of layer i - 1's fc2: reserve that layer's gradient bucket now so that the kernel can add
+        # the bias gradient (column sums) while it writes the rows
+        flat_next = g.reserve(group(i - 1)) if i > 0 else None
+        gs = fc2_bias_grad(i - 1) if (i > 0 and tape.layers[i - 1]["B"] * T == rows_in and s["full"] is None) else None
+        fc2_bias_done = gs is not None
         if s["scb"] is None:
             ops.layernorm_fddt_bwd(s["x_pre"], G, dy=dln1, g_in=G2, gamma=e["ln1_g"], delta1=s["d1_in"], delta2=s["d2_in"],
                                    T=T, stno=stno if fd is not None else None, fddt_w=fd[0] if fd is not None else None,
                                    fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dgamma=dgam, dbeta=dbet,
-                                   dfddt_w=dfw, dfddt_b=dfb)
+                                   dfddt_w=dfw, dfddt_b=dfb, g_colsum=gs)
         else:
             # LayerNorm 1 alone -> gradient of the stream after the speaker communication block; enrollment rows that
             # were dropped after this layer (encoder.py:210-213) carry no gradient from above
@@ -677,7 +694,8 @@ def encoder_backward(enc, g: _Grads, d_hidden_bf16: torch.Tensor, tape: EncoderT
             _scb_backward(enc, g, enc.ca_enrolls[i].cae, w["scb"][i], s["scb"], Gs, rows_in // (2 * T), T)
             ops.layernorm_fddt_bwd(s["x_pre"], G, g_in=Gs, delta1=s["d1_in"], delta2=s["d2_in"], T=T,
                                    stno=stno if fd is not None else None, fddt_w=fd[0] if fd is not None else None,
-                                   fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dfddt_w=dfw, dfddt_b=dfb)
+                                   fddt_b=fd[1] if fd is not None else None, g_out_bf16=Gb, dfddt_w=dfw, dfddt_b=dfb,
+                                   g_colsum=gs)
         if dfw is not None:
             _scatter_fddt_grads(g, enc.fddts[i], dfw, dfb)
         if s["full"] is not None:  # G is the gradient of the TRANSFORMED stream: back through the four class transforms
@@ -1054,7 +1072,7 @@ class DiCoWTrainStepFn(torch.autograd.Function):
             upp = upp_labels.to(dev).contiguous() if upp_labels is not None else None
             slc = model.soft_label_creator
             ce = dict(ts_begin=slc.ts_begin if slc is not None else 0,
-                      smoothing=slc.ts_smoothing_weights.to(dev) if (slc is not None and slc.smoothing) else None,
+                      smoothing=slc.smoothing_on(dev) if slc is not None else None,
                       soft_mode=slc is not None)
             dec_loss = ops.softlabel_ce(logits.view(B * S, V), labels, upp, **ce)
             wctc = float(cfg.ctc_weight)
