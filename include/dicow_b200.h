@@ -44,6 +44,11 @@ DICOW_API int dicow_destroy(dicow_handle_t h);
 DICOW_API const char* dicow_last_error(dicow_handle_t h);
 /* returns DICOW_ERR_CUDA (and records the message) if the device has a pending/sticky error */
 DICOW_API int dicow_check(dicow_handle_t h);
+/* Number of SMs the persistent kernels (GEMM, attention, LayerNorm rings) size their grids for in calls made AFTER this one;
+ * sms <= 0 or >= the device's SM count restores the whole device.  Returns the value in effect.  Used to run one encoder
+ * pass on part of the device next to latency-bound decode steps on another stream (long-form speculation: the reference's
+ * seek loop, src/models/dicow/generation.py:415-534, encodes window n + 1 only after window n is decoded). */
+DICOW_API int dicow_set_sm_budget(dicow_handle_t h, int sms);
 /* ABI version of this header (bumped when a struct changes) */
 DICOW_API int dicow_abi_version(void);
 

@@ -496,6 +496,43 @@ def test_generate_long_form_runs_and_segments(mini):
     assert torch.equal(seqs, out["sequences"])
 
 
+@pytest.mark.parametrize("timestamps", [True, False], ids=["timestamps", "no-timestamps"])
+def test_generate_speculative_next_window_is_transparent(mini, timestamps):
+    """with ``speculate_next_window`` the window at seek + 3000 is encoded on a second stream (part of the SMs)
+    under the decode steps of the current window.  Sequences and segments must be exactly those of the plain seek loop; without
+    timestamps every window advances by a full window, so every speculated window must be used."""
+    g, dmp, model, p, feats, stno = mini
+    model.tokenizer, model.soft_label_creator = None, None
+    F2 = 2 * dmp.T
+    more = [torch.from_numpy(synth.make_features(f"g{k}", 2, dmp.n_mels, F2)) for k in (1, 3, 4)]
+    long_feats = torch.cat([feats] + more, dim=-1).to(DEV)
+    long_stno = torch.cat([stno] + [torch.from_numpy(synth.make_stno(f"g{k}", 2, dmp.T, "hard")) for k in (1, 3, 4)], dim=-1).to(DEV)
+    attn = torch.ones(2, 4 * F2, dtype=torch.long)
+    attn[1, 2 * F2 + 31:] = 0  # second recording is shorter
+    gc = model.generation_config
+    gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = NOTS, EOS, EOS
+    gc.suppress_tokens, gc.return_timestamps, gc.max_new_tokens, gc.num_beams = SUPPRESS, timestamps, 24, 1
+    prompt = torch.tensor([[SOT, LANG, TASK] + ([] if timestamps else [NOTS])] * 2)
+    kw = dict(attention_mask=attn.to(DEV), stno_mask=long_stno, forced_decoder_ids=prompt, return_segments=True)
+    try:
+        model.speculate_next_window = False
+        plain = model.generate(long_feats, **kw)
+        model.speculate_next_window = True
+        model.speculation_sms = 64
+        spec = model.generate(long_feats, **kw)
+        stats = dict(model.speculation_stats)
+    finally:
+        model.speculate_next_window = False
+        gc.return_timestamps = True
+    print("speculation:", stats)
+    assert torch.equal(plain["sequences"], spec["sequences"])
+    assert [[(s["tokens"].tolist(), float(s["start"]), float(s["end"])) for s in r] for r in plain["segments"]] == \
+           [[(s["tokens"].tolist(), float(s["start"]), float(s["end"])) for s in r] for r in spec["segments"]]
+    assert stats["hits"] + stats["misses"] >= 1
+    if not timestamps:
+        assert stats["misses"] == 0 and stats["hits"] >= 3
+
+
 def test_generate_joint_ctc_long_form(mini):
     """generate(ctc_weight > 0): the long-form seek loop with joint CTC / attention selection per window (encoder CTC
     logits -> rescoring inside the CUDA-graphed step); shrinking batch (second recording shorter) re-allocates the CTC state"""
@@ -642,5 +679,12 @@ def test_generate_se_dicow_matches_oracle_and_cache_is_transparent(mini_se):
         model.cache_enrollment_kv = True
     assert used[0] is False and all(used[1:]) and len(used) >= 2 and not any(calls)
     assert torch.equal(with_cache["sequences"], without["sequences"])
+    try:  # speculative next-window encoding on top of the enrollment cache: same result
+        model.speculate_next_window = True
+        spec = model.generate(long_feats, **kw)
+    finally:
+        model.speculate_next_window = False
+    print("SE-DiCoW speculation:", model.speculation_stats)
+    assert torch.equal(with_cache["sequences"], spec["sequences"])
     assert [[s["tokens"].tolist() for s in r] for r in with_cache["segments"]] == \
            [[s["tokens"].tolist() for s in r] for r in without["segments"]]

@@ -82,7 +82,7 @@ extern "C" int dicow_create(int device, dicow_handle_t* out) {
   dicow_ctx* ctx = new (std::nothrow) dicow_ctx();
   if (ctx == nullptr) return DICOW_ERR_CUDA;
   ctx->device = device;
-  ctx->num_sms = prop.multiProcessorCount;
+  ctx->num_sms = ctx->phys_sms = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -104,6 +104,16 @@ extern "C" int dicow_destroy(dicow_handle_t h) {
   if (h != nullptr && h->mel_tables != nullptr) cudaFree(h->mel_tables);
   delete h;
   return DICOW_OK;
+}
+
+extern "C" int dicow_set_sm_budget(dicow_handle_t h, int sms) {
+  if (h == nullptr) return DICOW_ERR_INVALID_ARG;
+  if (sms <= 0 || sms >= h->phys_sms) {
+    h->num_sms = h->phys_sms;
+  } else {
+    h->num_sms = sms < 2 ? 2 : (sms & ~1);  // CTA pairs: an even number
+  }
+  return h->num_sms;
 }
 
 extern "C" const char* dicow_last_error(dicow_handle_t h) { return h ? h->err : "null handle"; }

@@ -10,7 +10,8 @@
 
 struct dicow_ctx {
   int device = 0;
-  int num_sms = 148;
+  int num_sms = 148;   // SMs the persistent kernels size their grids for (dicow_set_sm_budget can lower it)
+  int phys_sms = 148;  // multiProcessorCount
   int max_smem_optin = 0;
   char err[512] = {0};
   // cuTensorMapEncodeTiled fetched through cudaGetDriverEntryPoint (no link-time libcuda dependency)

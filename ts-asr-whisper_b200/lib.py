@@ -284,6 +284,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_last_error.argtypes = [vp]
     lib.dicow_last_error.restype = C.c_char_p
     lib.dicow_check.argtypes = [vp]
+    lib.dicow_set_sm_budget.argtypes = [vp, C.c_int]
     lib.dicow_check.restype = C.c_int
     lib.dicow_abi_version.argtypes = []
     lib.dicow_abi_version.restype = C.c_int
@@ -338,7 +339,7 @@ EXPORTED_SYMBOLS = [
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
     "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch", "dicow_fddt_full_scatter",
-    "dicow_decode_layers",
+    "dicow_decode_layers", "dicow_set_sm_budget",
 ]
 
 

@@ -360,6 +360,9 @@ class _DecodeCache:
         return _DecodeCache(self.capacity)
 
 
+_SPECULATION_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}  # one side stream per device (module level: models stay copyable)
+
+
 class DiCoWForConditionalGeneration(PreTrainedModel):
     config_class = DiCoWConfig
     base_model_prefix = "model"
@@ -1132,6 +1135,9 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         batch_idx_map = list(range(B0))
         feats = input_features
         enr_cache, enr_rows = None, {}
+        spec = None
+        speculate = bool(getattr(self, "speculate_next_window", False)) and dev.type == "cuda"
+        self.speculation_stats = {"hits": 0, "misses": 0}
         while bool((seek < max_frames).any()):
             # drop finished recordings from the batch (HF:_maybe_reduce_batch)
             keep = [i for i, prev in enumerate(batch_idx_map) if seek[prev] < max_frames[prev]]
@@ -1141,41 +1147,88 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             cur = len(batch_idx_map)
             time_offset = seek.to(torch.float64) * time_precision / input_stride
             seek_num_frames = (max_frames - seek).clamp(max=num_segment_frames)
-            seg_in, seg_stno = [], []
-            for i, prev in enumerate(batch_idx_map):
-                s0, n = int(seek[prev]), int(seek_num_frames[prev])
-                f = feats[i:i + 1, :, s0:s0 + n]
-                if f.shape[-1] < num_segment_frames:  # HF:_get_input_segment pads the mel with zeros
-                    f = torch.nn.functional.pad(f, (0, num_segment_frames - f.shape[-1]))
-                seg_in.append(f)
-                if stno_mask is not None:  # generation.py:73-118: STNO index = mel frame // 2, silence-padded
-                    v0 = s0 // 2
-                    nv = int((max_frames[prev] // 2 - v0).clamp(max=num_segment_frames // 2))
-                    m = stno_mask[prev:prev + 1, :, v0:v0 + nv]
-                    if m.shape[-1] < num_segment_frames // 2:
-                        orig = m.shape[-1]
-                        m = torch.nn.functional.pad(m, (0, num_segment_frames // 2 - orig))
-                        m[0, 0, orig:] = 1.0
-                    seg_stno.append(m)
-            seg_in = torch.cat(seg_in, 0)
-            seg_stno = torch.cat(seg_stno, 0) if seg_stno else None
-            self.stno_mask_seek = seg_stno
-            enr = enr_kv = capture = None
-            if cfg.use_enrollments and enrollments is not None:
+
+            def window_inputs(rows, at):
+                """mel / STNO windows of the recordings ``rows`` (positions in ``feats`` and original indices) starting at
+                mel frame ``at[prev]``"""
+                w_in, w_stno = [], []
+                for i, prev in rows:
+                    s0 = int(at[prev])
+                    n = int(min(int(max_frames[prev]) - s0, num_segment_frames))
+                    f = feats[i:i + 1, :, s0:s0 + n]
+                    if f.shape[-1] < num_segment_frames:  # HF:_get_input_segment pads the mel with zeros
+                        f = torch.nn.functional.pad(f, (0, num_segment_frames - f.shape[-1]))
+                    w_in.append(f)
+                    if stno_mask is not None:  # generation.py:73-118: STNO index = mel frame // 2, silence-padded
+                        v0 = s0 // 2
+                        nv = int((max_frames[prev] // 2 - v0).clamp(max=num_segment_frames // 2))
+                        m = stno_mask[prev:prev + 1, :, v0:v0 + nv]
+                        if m.shape[-1] < num_segment_frames // 2:
+                            orig = m.shape[-1]
+                            m = torch.nn.functional.pad(m, (0, num_segment_frames // 2 - orig))
+                            m[0, 0, orig:] = 1.0
+                        w_stno.append(m)
+                return torch.cat(w_in, 0), (torch.cat(w_stno, 0) if w_stno else None)
+
+            def enrollment_args(prevs, first_pass):
+                """(enrollments, enrollment_kv, capture list) for an encoder pass over the recordings ``prevs``"""
+                if not (cfg.use_enrollments and enrollments is not None):
+                    return None, None, None
                 if enr_cache is not None:
                     # later windows of a recording: the enrollment stream's keys / values of every speaker communication
                     # block are those of its first window (the stream never reads the target stream) -- reuse them
-                    rows_of = torch.as_tensor([enr_rows[prev] for prev in batch_idx_map], device=dev)
-                    enr_kv = [c.index_select(0, rows_of) for c in enr_cache]
+                    rows_of = torch.as_tensor([enr_rows[prev] for prev in prevs], device=dev)
+                    return None, [c.index_select(0, rows_of) for c in enr_cache], None
+                idx = torch.as_tensor(prevs, device=dev)
+                e = {k: v[idx] for k, v in enrollments.items()}
+                cap = None
+                if first_pass and getattr(self, "cache_enrollment_kv", True) and bool((max_frames > num_segment_frames).any()):
+                    cap = []
+                return e, None, cap
+
+            seg_in, seg_stno = window_inputs(list(enumerate(batch_idx_map)), seek)
+            self.stno_mask_seek = seg_stno
+            hidden = None
+            if spec is not None:
+                # the window encoded ahead (below) is this iteration's window for every recording still in the batch
+                if all(prev in spec["rows"] and spec["at"][prev] == int(seek[prev]) for prev in batch_idx_map):
+                    torch.cuda.current_stream(dev).wait_event(spec["done"])
+                    pick = [spec["rows"][prev] for prev in batch_idx_map]
+                    hidden = spec["hidden"] if pick == list(range(spec["hidden"].shape[0])) else \
+                        spec["hidden"].index_select(0, torch.as_tensor(pick, device=dev))
+                    hidden.record_stream(torch.cuda.current_stream(dev))
+                    self.speculation_stats["hits"] += 1
                 else:
-                    idx = torch.as_tensor(batch_idx_map, device=dev)
-                    enr = {k: v[idx] for k, v in enrollments.items()}
-                    if getattr(self, "cache_enrollment_kv", True) and bool((max_frames > num_segment_frames).any()):
-                        capture = []
-            hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr, enrollment_kv=enr_kv,
-                         capture_enrollment_kv=capture).last_hidden_state
-            if capture:
-                enr_cache, enr_rows = capture, {prev: i for i, prev in enumerate(batch_idx_map)}
+                    self.speculation_stats["misses"] += 1
+                spec = None
+            if hidden is None:
+                enr, enr_kv, capture = enrollment_args(batch_idx_map, True)
+                hidden = enc(seg_in, stno_mask=seg_stno, enrollments=enr, enrollment_kv=enr_kv,
+                             capture_enrollment_kv=capture).last_hidden_state
+                if capture:
+                    enr_cache, enr_rows = capture, {prev: i for i, prev in enumerate(batch_idx_map)}
+            if speculate:
+                # Encode the windows at seek + 3000 on a second stream, on part of the SMs, while the latency-bound decode steps
+                # of this window run: the seek of window n + 1 is only known after window n has been decoded
+                # (generation.py:415-534), but it IS seek + 3000 whenever the window closes on a single timestamp, carries no
+                # timestamp pair, or timestamps are off -- and the encoder output of a window does not depend on which other
+                # windows share its batch, so a hit is bit-identical to encoding after the fact.
+                ahead = [(i, prev) for i, prev in enumerate(batch_idx_map)
+                         if int(seek[prev]) + num_segment_frames < int(max_frames[prev])]
+                if ahead and not (cfg.use_enrollments and enrollments is not None and enr_cache is None
+                                  and getattr(self, "cache_enrollment_kv", True)):
+                    at = {prev: int(seek[prev]) + num_segment_frames for _, prev in ahead}
+                    side = self._speculation_stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    feats.record_stream(side)  # read by the side stream after this iteration may have dropped it
+                    with torch.cuda.stream(side):
+                        a_in, a_stno = window_inputs(ahead, at)
+                        a_enr, a_kv, _ = enrollment_args([prev for _, prev in ahead], False)
+                        with ops.sm_budget(dev, self.speculation_sms):
+                            a_hidden = enc(a_in, stno_mask=a_stno, enrollments=a_enr, enrollment_kv=a_kv).last_hidden_state
+                        done = torch.cuda.Event()
+                        done.record(side)
+                    spec = {"rows": {prev: j for j, (_, prev) in enumerate(ahead)}, "at": at, "hidden": a_hidden, "done": done}
             ctc = None
             if gs["ctc_weight"] > 0:  # generation.py:49-51, 250-268: the encoder's CTC posteriors rescore every step
                 if not hasattr(enc, "lm_head"):
@@ -1232,6 +1285,17 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         if self.tokenizer is not None:
             return self._fix_timestamps_from_segmentation(outputs)
         return outputs["sequences"]
+
+    # ---- long-form speculation -------------------------------------------------------------
+    speculate_next_window = False  # generate(): encode the window at seek + 3000 under the decode steps of the current one
+    speculation_sms = 64           # SMs the speculative encoder pass sizes its persistent kernels for (the rest: decode)
+
+    def _speculation_stream(self, dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        st = _SPECULATION_STREAMS.get(key)
+        if st is None:
+            st = _SPECULATION_STREAMS[key] = torch.cuda.Stream(device=dev)
+        return st
 
     # ---- language detection / prompt construction without forced_decoder_ids ------------------------------------------
     @torch.no_grad()

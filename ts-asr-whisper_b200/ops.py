@@ -46,6 +46,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class sm_budget:
+    """``with ops.sm_budget(dev, n):`` -- the persistent kernels launched inside size their grids for ``n`` SMs
+    (dicow_set_sm_budget), so that work on another stream keeps the rest of the device; restored on exit."""
+
+    def __init__(self, dev: torch.device, sms: int):
+        self.h, self.sms = _lib.handle(dev.index or 0), int(sms)
+
+    def __enter__(self):
+        self.effective = _lib.load_library().dicow_set_sm_budget(self.h, self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load_library().dicow_set_sm_budget(self.h, 0)
+        return False
+
+
 def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
