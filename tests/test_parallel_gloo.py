@@ -127,3 +127,32 @@ def test_shard_range_partitions():
             parts = [list(shard_range(n, r, world)) for r in range(world)]
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_ensure_synced_skips_host_tables_under_nccl(monkeypatch):
+    """NCCL cannot broadcast host memory: a host-resident constant buffer (the soft-label smoothing table of a tokenizer attached
+    after the model was moved to the GPU) is skipped, everything else is broadcast once.  (bench.py under torchrun failed on
+    exactly this before the check existed.)"""
+    import torch
+    import torch.distributed as dist
+    from ts_asr_whisper_b200 import parallel
+
+    class FakeCuda(torch.Tensor):
+        is_cuda = True  # stands in for a device tensor on this CPU-only box
+
+    m = torch.nn.Module()
+    m.w = torch.nn.Parameter(torch.zeros(3).as_subclass(FakeCuda))
+    m.register_buffer("table", torch.ones(4))  # host-resident constant
+    sent = []
+    monkeypatch.setattr(dist, "get_backend", lambda group=None: "nccl")
+    monkeypatch.setattr(dist, "broadcast", lambda t, src=0, group=None: sent.append(tuple(t.shape)))
+    ex = parallel.GradientExchange()
+    ex._active = True
+    ex.ensure_synced(m)
+    ex.ensure_synced(m)
+    assert sent == [(3,)]
+    monkeypatch.setattr(dist, "get_backend", lambda group=None: "gloo")
+    ex2 = parallel.GradientExchange()
+    ex2._active = True
+    ex2.ensure_synced(m)
+    assert sent == [(3,), (3,), (4,)]

@@ -127,8 +127,13 @@ class GradientExchange:
         if not self.active or id(module) in self._synced:
             return
         self._synced.add(id(module))
+        nccl = dist.get_backend(self.group) == "nccl"
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
+                if nccl and not t.is_cuda:
+                    # host-resident constant tables (the soft-label smoothing weights of a tokenizer attached after the model
+                    # was moved): derived identically on every rank, and NCCL cannot move host memory
+                    continue
                 dist.broadcast(t.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                                group=self.group)
 
