@@ -67,11 +67,23 @@ def main():
         g = p.grad.detach().clone()
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
         ref.append(g / world)
+    # (2b) the same reference once more: the single-pass attention backward reduces its dQ partial sums in an order that
+    # differs from run to run (fp32 adds at L2), so two backward passes over the same data are not bit-identical -- the
+    # exchange is judged against that run-to-run noise (with DICOW_ATTN_BWD_FUSED=0 the backward is deterministic up to the
+    # split-K atomics of the wgrad GEMMs: mismatch 5e-7)
+    model.zero_grad(set_to_none=True)
+    model(feats, stno_mask=stno, labels=labels, upp_labels=upp).loss.backward()
+    ref2 = []
+    for p in params:
+        g = p.grad.detach().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        ref2.append(g / world)
     training.gradient_exchange = ex
-    worst, worst_name = 0.0, ""
-    for n, a, b in zip(names, got, ref):
+    worst, worst_name, noise = 0.0, "", 0.0
+    for n, a, b, b2 in zip(names, got, ref, ref2):
         scale = b.abs().max().item()
         err = (a - b).abs().max().item() / max(scale, 1e-30)
+        noise = max(noise, (b2 - b).abs().max().item() / max(scale, 1e-30))
         if err > worst:
             worst, worst_name = err, n
     # parameters equal across ranks (after the broadcast) -- compare a checksum
@@ -95,10 +107,10 @@ def main():
     dist.all_gather(both2, chk2)
     out = {"world": world, "encoder_layers": layers, "ddp_managed_parameters": managed, "exchange_active": bool(ex.active),
            "collectives_in_first_backward": n_coll, "worst_gradient_mismatch_vs_allreduced_local": worst,
-           "worst_at": worst_name, "param_checksums_equal_after_sync": bool(all(float(b) == float(both[0]) for b in both)),
+           "worst_at": worst_name, "run_to_run_noise_of_the_local_backward": noise, "param_checksums_equal_after_sync": bool(all(float(b) == float(both[0]) for b in both)),
            "param_checksums_equal_after_3_steps": bool(all(float(b) == float(both2[0]) for b in both2)),
            "ms_per_step_under_ddp": e0.elapsed_time(e1) / 3}
-    ok = len(managed) == 1 and ex.active and n_coll >= layers and worst < 1e-5 and \
+    ok = len(managed) == 1 and ex.active and n_coll >= layers and worst < max(1e-5, 4.0 * noise) and \
         out["param_checksums_equal_after_sync"] and out["param_checksums_equal_after_3_steps"]
     out["ok"] = bool(ok)
     if rank == 0:
