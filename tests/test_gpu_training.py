@@ -306,6 +306,31 @@ def test_training_step_updates_and_second_step():
         ev = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
     out = model(feats, stno_mask=stno, labels=labels, upp_labels=labels)
     assert abs(ev.loss.item() - out.loss.item()) < 1e-3 * max(1.0, abs(ev.loss.item()))
+    # from the second optimizer step on the prepared weights are refreshed IN PLACE by a captured CUDA graph: what it left
+    # behind must be exactly what an eager rebuild from the current parameters gives
+    from ts_asr_whisper_b200 import modeling
+
+    def flat(o, pre=""):
+        if isinstance(o, torch.Tensor):
+            yield pre, o
+        elif isinstance(o, dict):
+            for k, v in o.items():
+                yield from flat(v, f"{pre}.{k}")
+        elif isinstance(o, (list, tuple)):
+            for i, v in enumerate(o):
+                yield from flat(v, f"{pre}[{i}]")
+
+    enc = model.get_encoder()
+    if modeling.prepare_graphs:
+        assert enc in modeling._PREPARE_GRAPHS, "the graph-captured refresh was not used"
+    snap = {k: v.clone() for k, v in flat(enc.prepare())}
+    enc.invalidate_cache()
+    fresh = dict(flat(enc.prepare()))
+    assert snap.keys() == fresh.keys() and len(snap) > 20
+    for k, v in snap.items():
+        assert torch.equal(v, fresh[k]), k
+    import copy
+    copy.deepcopy(model)  # stays copyable (the graph object lives outside the module)
 
 
 def test_unfreeze_after_fddt_warmup_phase():

@@ -68,6 +68,21 @@ def main():
             a[0] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
             a[1] += 1
             total += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+    # idle gaps of the device inside the step: the largest ones and the kernel that ends each
+    evs = sorted(((ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events()
+                  if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+    if evs:
+        span = (max(e[1] for e in evs) - evs[0][0]) / 1e3
+        gaps, busy_until, prev = [], evs[0][1], evs[0][2]
+        for st, en, nm in evs[1:]:
+            if st > busy_until:
+                gaps.append((st - busy_until, nm + "   <- after " + prev[:60]))
+            if en >= busy_until:
+                prev = nm
+            busy_until = max(busy_until, en)
+        print(f"device span of the step {span:.2f} ms; idle {sum(g[0] for g in gaps) / 1e3:.2f} ms in {len(gaps)} gaps; largest:")
+        for us, nm in sorted(gaps, reverse=True)[:12]:
+            print(f"   {us:8.1f} us before {nm[:170]}")
     print(f"total GPU kernel time {total / 1e3:.2f} ms over {sum(a[1] for a in agg.values())} launches")
     for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:80]:
         print(f"{us / 1e3:9.3f} ms {100 * us / total:5.1f}%  x{n:<5d} {name}")

@@ -262,6 +262,8 @@ _handles: dict[int, C.c_void_p] = {}
 def load_library() -> C.CDLL:
     """dlopen the shared library and declare prototypes (no GPU needed)."""
     global _lib
+    if _lib is not None:  # fast path: no lock once loaded (called on every launch)
+        return _lib
     with _lock:
         if _lib is not None:
             return _lib

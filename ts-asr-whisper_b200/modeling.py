@@ -12,6 +12,9 @@ is the reference's own bf16-autocast numerics (SURVEY.md Appendix A "Training nu
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import math
 from typing import Dict, Optional
 
@@ -206,6 +209,13 @@ class SpeakerCommunicationBlock(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------
 # prepared (bf16 / fused) weights
 # ----------------------------------------------------------------------------------------------------------------
+# refresh the prepared weights of a training run through a captured CUDA graph (DiCoWEncoder.prepare); DICOW_PREPARE_GRAPH=0
+# keeps the eager rebuild
+prepare_graphs = os.environ.get("DICOW_PREPARE_GRAPH", "1") != "0"
+_PREPARE_GRAPHS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # encoder module -> its captured refresh (kept out
+#                                                                             of the module: CUDA graphs cannot be deep-copied)
+
+
 def _bf16(t: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16(t.detach().float())
 
@@ -318,12 +328,47 @@ class DiCoWEncoder(nn.Module):
 
     def invalidate_cache(self) -> None:
         self._prepared = None
+        self.__dict__["_prepared_epoch"] = None
+        _PREPARE_GRAPHS.pop(self, None)
 
     def prepare(self) -> dict:
         """bf16 / fused copies of the weights for the kernels; rebuilt when a parameter tensor changed."""
+        ep = ops.prepare_epoch
+        if ep and self._prepared is not None and self.__dict__.get("_prepared_epoch") == ep:
+            return self._prepared  # same training step (see ops.prepare_epoch)
         key = self._cache_key()
         if self._prepared is not None and key == self._prepared_key:
+            self.__dict__["_prepared_epoch"] = ep
             return self._prepared
+        # Rebuild.  When the same parameter tensors merely carry new values (an optimizer step: same data_ptrs, new versions)
+        # the rebuild is ~400 small cast / cat / stack launches issued from Python -- 3 ms of host time at the start of every
+        # training step with the device idle.  From the second such rebuild on, the sequence is captured once into a CUDA graph
+        # (its outputs live in the graph's memory pool) and replayed: one launch, the prepared tensors are refreshed in place.
+        ptrs = tuple(k[0] for k in key)
+        st = _PREPARE_GRAPHS.get(self)
+        if st is not None and st["ptrs"] == ptrs and self._prepared is st["w"]:
+            st["graph"].replay()
+            self._prepared_key = key
+            self.__dict__["_prepared_epoch"] = ep
+            return self._prepared
+        _PREPARE_GRAPHS.pop(self, None)
+        same_tensors = self._prepared is not None and self._prepared_key is not None and \
+            tuple(k[0] for k in self._prepared_key) == ptrs
+        dev = self.conv1.weight.device
+        if same_tensors and dev.type == "cuda" and prepare_graphs and not torch.cuda.is_current_stream_capturing():
+            self._prepared = None  # release the eager copies before the graph's pool takes theirs
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                w = self._build_prepared()
+            graph.replay()  # capture records, replay computes
+            _PREPARE_GRAPHS[self] = {"ptrs": ptrs, "graph": graph, "w": w}
+        else:
+            w = self._build_prepared()
+        self._prepared, self._prepared_key = w, key
+        self.__dict__["_prepared_epoch"] = ep
+        return w
+
+    def _build_prepared(self) -> dict:
         cfg = self.config
         dev = self.conv1.weight.device
         d = cfg.d_model
@@ -376,7 +421,6 @@ class DiCoWEncoder(nn.Module):
             w["sub2"] = _conv_weight(self.subsample_conv2.weight)
         if hasattr(self, "lm_head"):
             w["lm_head"] = _bf16(self.lm_head.weight)
-        self._prepared, self._prepared_key = w, key
         return w
 
     # ---- kernels sequences -----------------------------------------------------------------------------------

@@ -81,6 +81,37 @@ def effective_weight(lin: nn.Module) -> torch.Tensor:
     return torch.addmm(W, B.detach().float(), A.detach().float(), alpha=s)
 
 
+_AUX_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class _HostCopy:
+    """A small device tensor on the host without stalling the launch queue: copied to pinned memory on a side stream that
+    waits only for what was queued before this call; ``get()`` blocks on that copy alone."""
+
+    def __init__(self, t: torch.Tensor):
+        self.ev = None
+        if not t.is_cuda:
+            self.host = t
+            return
+        idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        side = _AUX_STREAMS.get(idx)
+        if side is None:
+            side = _AUX_STREAMS[idx] = torch.cuda.Stream(device=t.device)
+        self.host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        side.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(side):
+            self.host.copy_(t, non_blocking=True)
+            self.ev = torch.cuda.Event()
+            self.ev.record(side)
+        t.record_stream(side)
+
+    def get(self) -> torch.Tensor:
+        if self.ev is not None:
+            self.ev.synchronize()
+            self.ev = None
+        return self.host
+
+
 def shift_tokens_right(labels: torch.Tensor, pad_token_id: int, decoder_start_token_id: int) -> torch.Tensor:
     """HF:modeling_whisper.py shift_tokens_right (index bookkeeping on int64 labels; call site modeling_dicow.py:275-279)."""
     shifted = labels.new_zeros(labels.shape)
@@ -157,6 +188,7 @@ class DiCoW(nn.Module):
         """drop the prepared bf16 weights of the decoder AND the encoder (needed after in-place updates that do not bump
         ``Parameter._version``: ``p.data.copy_()``, EMA swaps, some sharded-optimizer paths)"""
         self._prepared = None
+        self.__dict__["_prepared_epoch"] = None
         self.encoder.invalidate_cache()
 
     def get_encoder(self):
@@ -167,8 +199,12 @@ class DiCoW(nn.Module):
 
     # ---- bf16 / fused decoder weights ------------------------------------------------------------------------
     def prepare_decoder(self) -> dict:
+        ep = ops.prepare_epoch
+        if ep and self._prepared is not None and self.__dict__.get("_prepared_epoch") == ep:
+            return self._prepared  # same training step (see ops.prepare_epoch)
         key = tuple((p.data_ptr(), p._version) for p in self.decoder.parameters())
         if self._prepared is not None and key == self._prepared_key:
+            self.__dict__["_prepared_epoch"] = ep
             return self._prepared
         dec = self.decoder
         sc = 64 ** -0.5  # folded q scale (HF:modeling_whisper.py:310), exact in bf16
@@ -196,6 +232,7 @@ class DiCoW(nn.Module):
             e["w2"], e["b2"] = _bf16(effective_weight(lyr.fc2)), _f32(lyr.fc2.bias)
             w["layers"].append(e)
         self._prepared, self._prepared_key = w, key
+        self.__dict__["_prepared_epoch"] = ep
         self._prepared_gen += 1
         w["generation"] = self._prepared_gen
         return w
@@ -608,10 +645,20 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                 enc_model = self.model.get_encoder()
                 enc_labels = None
                 if cfg.ctc_weight > 0.0:
-                    enc_labels = self._ctc_labels(labels)
-                    if enc_labels.max() >= cfg.vocab_size:  # encoder.py:109-110
-                        raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
-                    enc_labels = enc_model.ctc_label_filter(enc_labels)
+                    # The CTC targets are data-dependent index bookkeeping (prefix tokens stripped only if the whole batch
+                    # carries them, the label range check, the optional timestamp filter: modeling_dicow.py:326-333,
+                    # encoder.py:109-113) -- each test is a device-to-host read.  Done here on the device labels they stalled
+                    # the launch queue at the start of every step (the host waited for the previous step's optimizer kernels,
+                    # then the device idled 2 ms while Python caught up).  The labels are copied to pinned memory on a side
+                    # stream instead and the bookkeeping runs on that copy when the CTC loss needs it, after the encoder
+                    # and decoder launches are queued.
+                    host = _HostCopy(labels)
+
+                    def enc_labels():
+                        lab = self._ctc_labels(host.get())
+                        if lab.numel() and lab.max() >= cfg.vocab_size:  # encoder.py:109-110
+                            raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
+                        return enc_model.ctc_label_filter(lab)
                 params = [p for p in self.parameters() if p.requires_grad]
                 enr = enrollments or {}
                 loss, logits, enc = training.DiCoWTrainStepFn.apply(self, input_features, stno_mask, decoder_input_ids, labels,

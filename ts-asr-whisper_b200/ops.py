@@ -17,6 +17,20 @@ from .lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16
 # number of kernels this module has launched (bench.py reports it as gpu_launches)
 launch_count = 0
 
+# Training-step scope for the prepared-weight caches (DiCoWEncoder.prepare / DiCoW.prepare_decoder): non-zero only INSIDE the
+# forward / backward of one of training.py's autograd Functions.  A cache filled under epoch N is returned without recomputing
+# its (data_ptr, version) key over every parameter while the epoch is N: the functions of one step ask for the prepared weights
+# ~8 times, and the backward must see the forward's weights anyway.  Outside those scopes (0) every call checks the key.
+prepare_epoch = 0
+_epoch_counter = 0
+
+
+def new_prepare_epoch() -> int:
+    global _epoch_counter
+    _epoch_counter += 1
+    return _epoch_counter
+
+
 # Optional per-launch timing hook (bench.py's roofline leg): when set to a list, gemm()/attention() append
 # (kind, flops, start_event, end_event) with CUDA events recorded on the launching stream around the launch.
 timing_log = None
@@ -42,6 +56,33 @@ class _Timed:
         return False
 
 
+class _Null:
+    """no-op context manager (one shared instance)"""
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _Null()
+
+
+def _timed(kind: str, flops: float, dev: torch.device):
+    return _NULL if timing_log is None else _Timed(kind, flops, dev)
+
+
+def _guard(dev: torch.device):
+    """device guard only when the tensor's device is not the current one (one process per GPU: practically never) -- a
+    torch.cuda.device context costs two runtime calls per launch, and the fine-tune step issues ~1 500 launches from Python"""
+    idx = dev.index
+    if idx is None or torch.cuda.current_device() == idx:
+        return _NULL
+    return torch.cuda.device(dev)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -62,7 +103,13 @@ class sm_budget:
         return False
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(dev: torch.device) -> int:
+    """cudaStream_t of torch's current stream on ``dev`` (the raw accessor skips building a torch.cuda.Stream object)"""
+    if _raw_stream is not None and dev.index is not None:
+        return _raw_stream(dev.index)
     return torch.cuda.current_stream(dev).cuda_stream
 
 
@@ -138,7 +185,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
     a.splits = splits
     a.aux_bf16 = _ptr(aux)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev), _Timed("gemm", 2.0 * nb * Mb * N * K, dev):
+    with _guard(dev), _timed("gemm", 2.0 * nb * Mb * N * K, dev):
         rc = _lib.load_library().dicow_gemm_bf16(h, C.byref(a), _stream(dev))
     _lib.check(rc, h, "dicow_gemm_bf16")
     launch_count += 1
@@ -148,7 +195,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, epilogue: int, 
 def _call(name: str, dev: torch.device, args_struct, kind: str = "", flops: float = 0.0) -> None:
     global launch_count
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev), _Timed(kind or name, flops, dev):
+    with _guard(dev), _timed(kind or name, flops, dev):
         rc = getattr(_lib.load_library(), name)(h, C.byref(args_struct), _stream(dev))
     _lib.check(rc, h, name)
     launch_count += 1
@@ -207,7 +254,7 @@ def fddt_full_combine(y: torch.Tensor, stno: torch.Tensor, x: torch.Tensor, *, T
     assert y.dtype == torch.bfloat16 and y.stride(-1) == 1 and x.dtype == torch.float32 and x.is_contiguous()
     assert stno.dtype == torch.float32 and stno.stride(2) == 1 and stno.stride(1) == stno.shape[2]
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_fddt_full_combine(h, _ptr(y), y.stride(-2), _ptr(stno), stno.stride(0), T, rows, d,
                                                          _ptr(pos), _ptr(x), _stream(dev))
     _lib.check(rc, h, "dicow_fddt_full_combine")
@@ -224,7 +271,7 @@ def fddt_full_scatter(g: torch.Tensor, stno: torch.Tensor, dy: torch.Tensor, *, 
     assert dy.dtype == torch.bfloat16 and dy.stride(-1) == 1 and g.dtype == torch.float32 and g.is_contiguous()
     assert stno.dtype == torch.float32 and stno.stride(2) == 1 and stno.stride(1) == stno.shape[2]
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_fddt_full_scatter(h, _ptr(g), _ptr(stno), stno.stride(0), T, rows, d, _ptr(dy),
                                                          dy.stride(-2), _stream(dev))
     _lib.check(rc, h, "dicow_fddt_full_scatter")
@@ -263,7 +310,7 @@ def features_to_channels_last(feats: torch.Tensor, out: torch.Tensor) -> torch.T
     assert feats.dtype == torch.float32 and feats.is_contiguous() and out.dtype == torch.bfloat16
     assert out.shape == (B, F + 2, Cc) and out.is_contiguous()
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_features_to_channels_last(h, _ptr(feats), _ptr(out), B, Cc, F, _stream(dev))
     _lib.check(rc, h, "dicow_features_to_channels_last")
     launch_count += 1
@@ -276,7 +323,7 @@ def zero_pad_rows(buf: torch.Tensor) -> None:
     dev = _require_cuda(buf)
     B, Tp, Cc = buf.shape
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_zero_pad_rows(h, _ptr(buf), B, Tp - 2, Cc, _stream(dev))
     _lib.check(rc, h, "dicow_zero_pad_rows")
     launch_count += 1
@@ -289,7 +336,7 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     src = src.contiguous()
     out = torch.empty(src.shape, dtype=torch.bfloat16, device=dev)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_cast_f32_bf16(h, _ptr(src), _ptr(out), src.numel(), _stream(dev))
     _lib.check(rc, h, "dicow_cast_f32_bf16")
     launch_count += 1
@@ -309,7 +356,7 @@ def stno_mask(activity: torch.Tensor, target: int, *, window_samples: int = 4800
     out = torch.empty((4, frames) if channels_first else (frames, 4), dtype=torch.float32, device=dev)
     fs, cs = (1, frames) if channels_first else (4, 1)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_stno_mask(h, _ptr(act), act.stride(0), n_spk, n, int(target), frame_samples, frames,
                                                  _ptr(out), fs, cs, _stream(dev))
     _lib.check(rc, h, "dicow_stno_mask")
@@ -473,7 +520,7 @@ def kv_to_head_major(kv: torch.Tensor, out: torch.Tensor, *, B: int, T: int, H: 
     assert kv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and kv.is_contiguous() and out.is_contiguous()
     assert kv.numel() == B * T * 2 * H * 64 == out.numel()
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_kv_to_head_major(h, _ptr(kv), _ptr(out), B, T, H, _stream(dev))
     _lib.check(rc, h, "dicow_kv_to_head_major")
     launch_count += 1
@@ -489,7 +536,7 @@ def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, posw: torch.Tensor, x: to
     assert tok.is_contiguous() and posw.is_contiguous() and x.is_contiguous() and x.dtype == torch.float32
     B = ids.shape[0]
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_embed_tokens(h, _ptr(ids), ids.stride(0), _ptr(tok), _ptr(posw), _ptr(x), B, S,
                                                     tok.shape[1], tok.shape[0], past, _ptr(pos), _stream(dev))
     _lib.check(rc, h, "dicow_embed_tokens")
@@ -537,7 +584,7 @@ def advance(pos: torch.Tensor, by: int = 1) -> None:
     global launch_count
     dev = _require_cuda(pos)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_advance(h, _ptr(pos), by, _stream(dev))
     _lib.check(rc, h, "dicow_advance")
     launch_count += 1
@@ -597,7 +644,7 @@ class CtcJointState:
         assert tuple(ctc_logits.shape) == (self.B, self.T, self.V1) and ctc_logits.is_contiguous()
         dev = ctc_logits.device
         h = _lib.handle(dev.index or 0)
-        with torch.cuda.device(dev):
+        with _guard(dev):
             rc = _lib.load_library().dicow_log_softmax_rows(h, _ptr(ctc_logits), _ptr(self.logp), self.B * self.T, self.V1,
                                                             _stream(dev))
         _lib.check(rc, h, "dicow_log_softmax_rows")
@@ -800,7 +847,7 @@ def colsum(x: torch.Tensor, out: torch.Tensor, alpha: float = 1.0) -> None:
     dev = _require_cuda(x, out)
     assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32 and x.dtype in (torch.bfloat16, torch.float32)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_colsum(h, _ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), x.shape[0],
                                               out.numel(), _ptr(out), alpha, _stream(dev))
     _lib.check(rc, h, "dicow_colsum")
@@ -812,7 +859,7 @@ def conv1d_col2im(dcol: torch.Tensor, dx: torch.Tensor, *, B: int, T: int, T_out
     global launch_count
     dev = _require_cuda(dcol, dx)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_conv1d_col2im(h, _ptr(dcol), _ptr(dx), B, T, T_out, C_in, stride, dx_batch_stride,
                                                      dx_row_stride, _stream(dev))
     _lib.check(rc, h, "dicow_conv1d_col2im")
@@ -900,7 +947,7 @@ def dgelu_mul(g: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
     assert pre.dtype == torch.bfloat16 and g.dtype in (torch.bfloat16, torch.float32)
     out = torch.empty(g.shape, dtype=torch.bfloat16, device=dev)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_dgelu_mul(h, _ptr(g), 1 if g.dtype == torch.bfloat16 else 0, g.stride(0), _ptr(pre),
                                                  pre.stride(0), _ptr(out), out.stride(0), g.shape[0], g.shape[1], _stream(dev))
     _lib.check(rc, h, "dicow_dgelu_mul")
@@ -917,7 +964,7 @@ def gate_bwd(g: torch.Tensor, upd: torch.Tensor, gate: torch.Tensor, dgate: Opti
     assert g.dtype == torch.float32 and upd.dtype == torch.bfloat16 and gate.dtype == torch.float32
     out = torch.empty(g.shape, dtype=torch.bfloat16, device=dev)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_gate_bwd(h, _ptr(g), g.stride(0), _ptr(upd), upd.stride(0), _ptr(gate), _ptr(out),
                                                 out.stride(0), g.shape[0], g.shape[1], _ptr(dgate), _stream(dev))
     _lib.check(rc, h, "dicow_gate_bwd")
@@ -934,7 +981,7 @@ def embedding_bwd(g: torch.Tensor, ids: torch.Tensor, *, S: int, d_tok: Optional
     rows, d = g.shape
     vocab = d_tok.shape[0] if d_tok is not None else 0
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_embedding_bwd(h, _ptr(g), _ptr(ids), rows, S, d, past, vocab, _ptr(d_tok), _ptr(d_pos),
                                                      _stream(dev))
     _lib.check(rc, h, "dicow_embedding_bwd")
@@ -948,7 +995,7 @@ def cast_bf16_padded(src: torch.Tensor, cols_out: int) -> torch.Tensor:
     assert src.dim() == 2 and src.dtype == torch.float32 and src.stride(1) == 1 and cols_out >= src.shape[1]
     out = torch.empty(src.shape[0], cols_out, dtype=torch.bfloat16, device=dev)
     h = _lib.handle(dev.index or 0)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         rc = _lib.load_library().dicow_cast_f32_bf16_2d(h, _ptr(src), src.stride(0), _ptr(out), cols_out, src.shape[0],
                                                         src.shape[1], cols_out, _stream(dev))
     _lib.check(rc, h, "dicow_cast_f32_bf16_2d")

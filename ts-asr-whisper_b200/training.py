@@ -996,10 +996,14 @@ class EncoderLogitsFn(torch.autograd.Function):
             gradient_exchange.ensure_synced(enc)
         tape = EncoderTape()
         body = _body_trainable(enc)
-        with torch.no_grad():
-            hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, tape, body,
-                                                        _enrollments(enr_features, enr_stno))
-            logits = ctc_head_forward_train(enc, hidden_bf16, B, T, tape)
+        ctx.epoch = ops.prepare_epoch = ops.new_prepare_epoch()
+        try:
+            with torch.no_grad():
+                hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, tape, body,
+                                                            _enrollments(enr_features, enr_stno))
+                logits = ctc_head_forward_train(enc, hidden_bf16, B, T, tape)
+        finally:
+            ops.prepare_epoch = 0
         ctx.enc, ctx.tape, ctx.body, ctx.params = enc, tape, body, params
         neck = tape.ctc["neck"].float()  # what the reference returns as hidden_states (encoder.py:233-240)
         ctx.mark_non_differentiable(hidden, neck)
@@ -1009,12 +1013,17 @@ class EncoderLogitsFn(torch.autograd.Function):
     def backward(ctx, grad_logits, _grad_hidden, _grad_neck):
         enc, tape = ctx.enc, ctx.tape
         g = _Grads(gradient_exchange)
-        with torch.no_grad():
-            V1 = grad_logits.shape[-1]
-            dl = ops.cast_bf16_padded(grad_logits.reshape(-1, V1).float(), _ceil8(V1))
-            dh = ctc_head_backward(enc, g, dl.view(grad_logits.shape[0], grad_logits.shape[1], -1), tape, need_dhidden=ctx.body)
-            if ctx.body:
-                encoder_backward(enc, g, dh, tape)
+        ops.prepare_epoch = ctx.epoch  # the prepared weights of this step's forward
+        try:
+            with torch.no_grad():
+                V1 = grad_logits.shape[-1]
+                dl = ops.cast_bf16_padded(grad_logits.reshape(-1, V1).float(), _ceil8(V1))
+                dh = ctc_head_backward(enc, g, dl.view(grad_logits.shape[0], grad_logits.shape[1], -1), tape,
+                                       need_dhidden=ctx.body)
+                if ctx.body:
+                    encoder_backward(enc, g, dh, tape)
+        finally:
+            ops.prepare_epoch = 0
         ctx.tape = None
         return (None,) * 5 + g.finish(ctx.params)
 
@@ -1055,6 +1064,17 @@ class DiCoWTrainStepFn(torch.autograd.Function):
         # the encoder states receive a gradient from the decoder's cross-attention whenever the body trains
         body = _body_trainable(enc)
         dec_trainable = any(p.requires_grad for p in model.model.decoder.parameters())
+        ctx.epoch = ops.prepare_epoch = ops.new_prepare_epoch()
+        try:
+            return DiCoWTrainStepFn._forward(ctx, model, enc, etape, dtape, body, dec_trainable, input_features, stno_mask,
+                                             decoder_input_ids, labels, upp_labels, enc_labels, enr_features, enr_stno, params)
+        finally:
+            ops.prepare_epoch = 0
+
+    @staticmethod
+    def _forward(ctx, model, enc, etape, dtape, body, dec_trainable, input_features, stno_mask, decoder_input_ids, labels,
+                 upp_labels, enc_labels, enr_features, enr_stno, params):
+        cfg = model.config
         with torch.no_grad():
             hidden, hidden_bf16, B, T = _encoder_hidden(enc, input_features, stno_mask, etape, body,
                                                         _enrollments(enr_features, enr_stno))
@@ -1079,6 +1099,8 @@ class DiCoWTrainStepFn(torch.autograd.Function):
             ctc_ws = enc_logits = None
             if wctc > 0.0:
                 enc_logits = ctc_head_forward_train(enc, hidden_bf16, B, T, etape)
+                if callable(enc_labels):  # deferred host-side bookkeeping (DiCoWForConditionalGeneration.forward)
+                    enc_labels = enc_labels()
                 enc_labels = enc_labels.to(dev).contiguous()
                 ctc, ctc_ws = ops.ctc_loss_with_lse(enc_logits, enc_labels, cfg.ctc_loss_reduction)
                 loss = (1 - wctc) * dec_loss + wctc * ctc
@@ -1100,6 +1122,17 @@ class DiCoWTrainStepFn(torch.autograd.Function):
         logits, labels, upp, enc_logits, enc_labels, ctc_ws, n_norm = ctx.saved
         g = _Grads(gradient_exchange)
         B, S, V = logits.shape
+        ops.prepare_epoch = ctx.epoch  # the prepared weights of this step's forward
+        try:
+            DiCoWTrainStepFn._backward(ctx, model, cfg, enc, g, grad_loss, logits, labels, upp, enc_logits, enc_labels, ctc_ws,
+                                       n_norm, B, S, V)
+        finally:
+            ops.prepare_epoch = 0
+        ctx.etape = ctx.dtape = ctx.saved = None
+        return (None,) * 9 + g.finish(ctx.params)
+
+    @staticmethod
+    def _backward(ctx, model, cfg, enc, g, grad_loss, logits, labels, upp, enc_logits, enc_labels, ctc_ws, n_norm, B, S, V):
         with torch.no_grad():
             gl = grad_loss.reshape(1).float()
             d_enc = None
@@ -1118,5 +1151,3 @@ class DiCoWTrainStepFn(torch.autograd.Function):
                 del dl
             if ctx.body:
                 encoder_backward(enc, g, ops.cast_bf16(d_enc), ctx.etape)
-        ctx.etape = ctx.dtape = ctx.saved = None
-        return (None,) * 9 + g.finish(ctx.params)
