@@ -308,6 +308,7 @@ typedef struct {
   int64_t ldd;
   const float* scale_dev; /* optional device scalar multiplying loss_scale (the upstream gradient stays on the GPU) */
   int32_t out_f32;        /* != 0: dlogits is fp32 (what autograd hands to a caller-visible logits tensor) */
+  int64_t ld;             /* row stride of logits in elements (0 = V1: contiguous rows) */
 } dicow_ctc_bwd_args_t;
 DICOW_API int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* args, void* stream);
 
@@ -681,13 +682,15 @@ DICOW_API int dicow_softlabel_ce(dicow_handle_t h, const dicow_softlabel_ce_args
 
 typedef struct {
   size_t struct_size;
-  const float* logits; /* [B, T, V1] fp32 contiguous */
+  const float* logits; /* [B, T, V1] fp32, rows `ld` elements apart */
   int32_t B, T, V1;
   const int64_t* labels; /* [B, Lmax], negative = padding */
   int32_t Lmax;
   int32_t reduction_mean; /* 1 = "mean" (per-utterance loss / target length, batch mean), 0 = "sum" */
   float* workspace;
   float* loss; /* [1] */
+  int64_t ld;  /* row stride of logits in elements (0 = V1).  The CTC head writes its logits with a stride that is a multiple of
+                  4 (V + 1 = 51 867 is odd): the GEMM epilogue then stores 16-byte vectors instead of 4-byte scalars */
 } dicow_ctc_loss_args_t;
 DICOW_API int dicow_ctc_loss(dicow_handle_t h, const dicow_ctc_loss_args_t* args, void* stream);
 

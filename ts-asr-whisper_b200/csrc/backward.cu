@@ -635,7 +635,8 @@ __device__ __forceinline__ float log_add(float a, float b) {
 }
 
 struct CtcBwdParams {
-  const float* logits;  // [B, T, V1]
+  const float* logits;  // [B, T, V1], rows ld elements apart
+  long long ld;
   const float* lse;     // [B * T] natural-log sum exp of every row
   int T, V1, Lmax;
   const long long* labels;
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p)
     skip_prev = s >= 3 && lab[(s >> 1) - 1] != cls;
     skip_next = s + 2 < S && lab[(s >> 1) + 1] != cls;
   }
-  const float* lg = p.logits + (long long)b * p.T * p.V1;
+  const float* lg = p.logits + (long long)b * p.T * p.ld;
   const float* ls = p.lse + (long long)b * p.T;
   float* lat = (dir == 0 ? p.alpha : p.beta) + (long long)b * p.T * Sm;
   float* cur = buf;
@@ -694,7 +695,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p)
         float a = cur[s];
         if (s >= 1) a = log_add(a, cur[s - 1]);
         if (skip_prev) a = log_add(a, cur[s - 2]);
-        a += lg[(long long)t * p.V1 + cls] - ls[t];
+        a += lg[(long long)t * p.ld + cls] - ls[t];
         nxt[s] = a, lat[(long long)t * Sm + s] = a;
       }
       __syncthreads();
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p)
   } else {
     const int tl = p.T - 1;
     if (active) {
-      const float v = (s >= S - 2) ? lg[(long long)tl * p.V1 + cls] - ls[tl] : -INFINITY;
+      const float v = (s >= S - 2) ? lg[(long long)tl * p.ld + cls] - ls[tl] : -INFINITY;
       cur[s] = v, lat[(long long)tl * Sm + s] = v;
     }
     __syncthreads();
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcBwdParams p)
         float a = cur[s];
         if (s + 1 < S) a = log_add(a, cur[s + 1]);
         if (skip_next) a = log_add(a, cur[s + 2]);
-        a += lg[(long long)t * p.V1 + cls] - ls[t];
+        a += lg[(long long)t * p.ld + cls] - ls[t];
         nxt[s] = a, lat[(long long)t * Sm + s] = a;
       }
       __syncthreads();
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(512) ctc_grad_kernel(const CtcBwdParams p) {
   const bool finite = nll < INFINITY;  // also false for NaN
   const float ls = p.loss_scale * (p.scale_dev != nullptr ? __ldg(p.scale_dev) : 1.f);
   const float scale = !finite ? 0.f : (p.mean ? ls / ((float)p.B * (float)max(L, 1)) : ls);
-  const float* lg = p.logits + (long long)bt * p.V1;
+  const float* lg = p.logits + (long long)bt * p.ld;
   const float lse = p.lse[bt];
   const bool f32 = p.out_f32 != 0;
   void* out = f32 ? static_cast<void*>(reinterpret_cast<float*>(p.dlogits) + (long long)bt * p.ldd)
@@ -1020,6 +1021,8 @@ extern "C" int dicow_ctc_loss_bwd(dicow_handle_t h, const dicow_ctc_bwd_args_t* 
   const int S = 2 * a->Lmax + 1;
   CtcBwdParams p{};
   p.logits = a->logits, p.lse = a->lse, p.T = a->T, p.V1 = a->V1, p.Lmax = a->Lmax, p.B = a->B;
+  p.ld = a->ld > 0 ? a->ld : a->V1;
+  DICOW_REQUIRE(ctx, p.ld >= a->V1, "dicow_ctc_loss_bwd: ld < V1");
   p.labels = reinterpret_cast<const long long*>(a->labels);
   p.alpha = a->workspace;
   p.beta = p.alpha + (long long)a->B * a->T * S;

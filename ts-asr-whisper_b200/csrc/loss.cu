@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(LT) masked_mean_kernel(const float* __restrict
 // CTC
 // ------------------------------------------------------------------------------------------------------------------
 struct CtcParams {
-  const float* logits;  // [B, T, V1]
+  const float* logits;  // [B, T, V1], rows ld elements apart
+  long long ld;
   const float* lse;     // [B * T]
   int T, V1, Lmax;
   const long long* labels;  // [B, Lmax], negative = padding (a prefix of each row is valid)
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(1024) ctc_alpha_kernel(const CtcParams p) {
     cls = (int)lab[s >> 1];
     skip = s >= 3 && lab[(s >> 1) - 1] != cls;  // s-2 holds a different non-blank label
   }
-  const float* lg = p.logits + (long long)b * p.T * p.V1;
+  const float* lg = p.logits + (long long)b * p.T * p.ld;
   const float* ls = p.lse + (long long)b * p.T;
   float* cur = alpha;
   float* nxt = alpha + 2 * p.Lmax + 1;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(1024) ctc_alpha_kernel(const CtcParams p) {
       float a = cur[s];
       if (s >= 1) a = log_add(a, cur[s - 1]);
       if (skip) a = log_add(a, cur[s - 2]);
-      nxt[s] = a + (lg[(long long)t * p.V1 + cls] - ls[t]);
+      nxt[s] = a + (lg[(long long)t * p.ld + cls] - ls[t]);
     }
     __syncthreads();
     float* tmp = cur;
@@ -238,10 +239,12 @@ extern "C" int dicow_ctc_loss(dicow_handle_t h, const dicow_ctc_loss_args_t* a, 
   float* lse = a->workspace;                   // [B * T]
   float* nll = lse + (long long)a->B * a->T;   // [B]
   float* scaled = nll + a->B;                  // [B]
-  row_lse_kernel<<<a->B * a->T, LT, 0, stream>>>(a->logits, a->V1, a->V1, lse);
+  const long long ld = a->ld > 0 ? a->ld : a->V1;
+  DICOW_REQUIRE(ctx, ld >= a->V1, "dicow_ctc_loss: ld < V1");
+  row_lse_kernel<<<a->B * a->T, LT, 0, stream>>>(a->logits, ld, a->V1, lse);
   DICOW_CUDA_OK(ctx, cudaGetLastError());
   CtcParams p{};
-  p.logits = a->logits, p.lse = lse, p.T = a->T, p.V1 = a->V1, p.Lmax = a->Lmax;
+  p.logits = a->logits, p.ld = ld, p.lse = lse, p.T = a->T, p.V1 = a->V1, p.Lmax = a->Lmax;
   p.labels = reinterpret_cast<const long long*>(a->labels), p.nll = nll, p.scaled = scaled, p.mean = a->reduction_mean;
   const int S = 2 * a->Lmax + 1;
   const int threads = ((S + 31) / 32) * 32;

@@ -107,7 +107,7 @@ class CtcBwdArgs(C.Structure):
         ("logits", C.c_void_p), ("lse", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32),
         ("labels", C.c_void_p), ("Lmax", C.c_int32), ("reduction_mean", C.c_int32), ("loss_scale", C.c_float),
         ("workspace", C.c_void_p), ("dlogits_bf16", C.c_void_p), ("ldd", C.c_int64),
-        ("scale_dev", C.c_void_p), ("out_f32", C.c_int32),
+        ("scale_dev", C.c_void_p), ("out_f32", C.c_int32), ("ld", C.c_int64),
     ]
 
 
@@ -250,7 +250,7 @@ class CtcLossArgs(C.Structure):
         ("struct_size", C.c_size_t),
         ("logits", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("V1", C.c_int32),
         ("labels", C.c_void_p), ("Lmax", C.c_int32), ("reduction_mean", C.c_int32),
-        ("workspace", C.c_void_p), ("loss", C.c_void_p),
+        ("workspace", C.c_void_p), ("loss", C.c_void_p), ("ld", C.c_int64),
     ]
 
 

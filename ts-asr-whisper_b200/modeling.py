@@ -313,7 +313,7 @@ class DiCoWEncoder(nn.Module):
         if torch.is_grad_enabled() and logits.requires_grad:
             from .training import CtcLossFn
             return CtcLossFn.apply(logits, labels, self.config.ctc_loss_reduction)
-        return ops.ctc_loss(logits.float().contiguous(), labels, reduction=self.config.ctc_loss_reduction)
+        return ops.ctc_loss(logits.float(), labels, reduction=self.config.ctc_loss_reduction)
 
     def ctc_label_filter(self, labels: torch.Tensor) -> torch.Tensor:
         """encoder.py:111-113: drop timestamp / task tokens from the CTC targets when configured"""
@@ -534,8 +534,11 @@ class DiCoWEncoder(nn.Module):
         neck = self._ctc_neck(w, hidden_bf16, B, T)
         Tp = neck.shape[1]
         V1 = w["lm_head"].shape[0]
-        logits = torch.empty(B, Tp, V1, dtype=torch.float32, device=neck.device)
-        ops.gemm(neck.view(B * Tp, -1), w["lm_head"], logits.view(B * Tp, V1), epilogue=ops.EPI_BIAS_F32)
+        # rows of the buffer padded to a multiple of 4 floats (V + 1 is odd for Whisper vocabularies): 16-byte stores in the GEMM
+        # epilogue; the result is the [B, T', V + 1] view of it (unit column stride, not contiguous)
+        ldl = -(-V1 // 4) * 4
+        logits = torch.empty(B, Tp, ldl, dtype=torch.float32, device=neck.device)[..., :V1]
+        ops.gemm(neck.view(B * Tp, -1), w["lm_head"], logits.as_strided((B * Tp, V1), (ldl, 1)), epilogue=ops.EPI_BIAS_F32)
         return (logits, neck) if return_neck else logits
 
     def forward(self, input_features, attention_mask=None, head_mask=None, output_attentions=None,

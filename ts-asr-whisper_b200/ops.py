@@ -760,11 +760,21 @@ def softlabel_ce(logits: torch.Tensor, labels: torch.Tensor, upp_labels: Optiona
     return loss
 
 
+def _ctc_rows(logits: torch.Tensor) -> torch.Tensor:
+    """[B, T, V1] fp32 logits as the CTC kernels address them: unit column stride, rows ``stride(1)`` elements apart and batches
+    T rows apart (a row-padded buffer, as the CTC head writes it, passes through; anything else is made contiguous)"""
+    if logits.dim() == 3 and logits.stride(2) == 1 and logits.stride(1) >= logits.shape[2] and \
+            (logits.shape[0] == 1 or logits.stride(0) == logits.shape[1] * logits.stride(1)):
+        return logits
+    return logits.contiguous()
+
+
 def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
     """CTC loss with blank = last class, all frames valid, zero_infinity (dicow_ctc_loss).  logits fp32 [B, T, V+1]
     contiguous, labels int64 [B, Lmax] (negative = padding)."""
     dev = _require_cuda(logits, labels)
-    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int64
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    logits = _ctc_rows(logits)
     if reduction not in ("mean", "sum"):
         raise NotImplementedError(f"ctc_loss_reduction={reduction}")
     labels = labels.contiguous()
@@ -777,6 +787,7 @@ def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean"
     a.labels, a.Lmax = _ptr(labels), labels.shape[1]
     a.reduction_mean = 1 if reduction == "mean" else 0
     a.workspace, a.loss = _ptr(ws), _ptr(loss)
+    a.ld = logits.stride(1)
     _call("dicow_ctc_loss", dev, a, "ctc_loss")
     return loss
 
@@ -869,7 +880,8 @@ def conv1d_col2im(dcol: torch.Tensor, dx: torch.Tensor, *, B: int, T: int, T_out
 def ctc_loss_with_lse(logits: torch.Tensor, labels: torch.Tensor, reduction: str = "mean"):
     """CTC loss value plus the per-row log-sum-exp workspace the backward consumes (dicow_ctc_loss)."""
     dev = _require_cuda(logits, labels)
-    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int64
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    logits = _ctc_rows(logits)
     if reduction not in ("mean", "sum"):
         raise NotImplementedError(f"ctc_loss_reduction={reduction}")
     labels = labels.contiguous()
@@ -882,6 +894,7 @@ def ctc_loss_with_lse(logits: torch.Tensor, labels: torch.Tensor, reduction: str
     a.labels, a.Lmax = _ptr(labels), labels.shape[1]
     a.reduction_mean = 1 if reduction == "mean" else 0
     a.workspace, a.loss = _ptr(ws_f), _ptr(loss)
+    a.ld = logits.stride(1)
     _call("dicow_ctc_loss", dev, a, "ctc_loss")
     return loss, ws_f
 
@@ -892,6 +905,7 @@ def ctc_loss_bwd(logits: torch.Tensor, labels: torch.Tensor, lse_ws: torch.Tenso
     (the wgrad GEMM's operand), or fp32 [B, T, V1] when ``out_f32`` (what autograd hands to a visible logits tensor)."""
     dev = _require_cuda(logits, labels, lse_ws, scale_dev)
     labels = labels.contiguous()
+    logits = _ctc_rows(logits)
     B, T, V1 = logits.shape
     Lmax = labels.shape[1]
     S = 2 * Lmax + 1
@@ -904,6 +918,7 @@ def ctc_loss_bwd(logits: torch.Tensor, labels: torch.Tensor, lse_ws: torch.Tenso
     b.labels, b.Lmax, b.reduction_mean, b.loss_scale = _ptr(labels), Lmax, 1 if reduction == "mean" else 0, loss_scale
     b.workspace, b.dlogits_bf16, b.ldd = _ptr(ws_b), _ptr(dlogits), ldd
     b.scale_dev, b.out_f32 = _ptr(scale_dev), 1 if out_f32 else 0
+    b.ld = logits.stride(1)
     _call("dicow_ctc_loss_bwd", dev, b, "ctc_bwd")
     return dlogits
 
