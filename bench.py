@@ -23,7 +23,8 @@ N GPUs run N replicas with no data-path collective ("weak" scaling: B per GPU fi
   secondary: BASELINE configs[2], [3], [4] measured in the same process after the headline (tools/workloads.py): the
            fine-tune step with the gradient all-reduce (under torchrun: NCCL over NVLink, exposed communication time
            reported), the CTC pre-train step, SE-DiCoW greedy decode -- each with its own bracketed clock sample and
-           roofline fraction.  --secondary none skips them.
+           roofline fraction -- and the long-form seek loop with / without the speculative next-window encoder pass
+           (SURVEY 8(f).3).  --secondary none skips them.
 """
 from __future__ import annotations
 
@@ -318,7 +319,7 @@ def main():
     # ---- secondary workloads (BASELINE configs[2], [4], [3]); every rank takes part, rank 0 reports ----
     del enc, resident, dev_in, out_hosts, out_host, host
     torch.cuda.empty_cache()
-    names = {"all": ["finetune_step", "ctc_pretrain_step", "se_dicow_greedy"], "none": []}.get(
+    names = {"all": ["finetune_step", "ctc_pretrain_step", "se_dicow_greedy", "longform_speculation"], "none": []}.get(
         args.secondary, [n for n in args.secondary.split(",") if n])
     secondary = {}
     from tools import workloads
@@ -331,6 +332,8 @@ def main():
                 secondary[name] = workloads.train_step("ctc_pretrain", dev, rank, world, steps=5, warmup=3, sampler=smp)
             elif name == "se_dicow_greedy":
                 secondary[name] = workloads.se_dicow_greedy(dev, rank, world, sampler=smp)
+            elif name == "longform_speculation":
+                secondary[name] = workloads.longform_speculation(dev, rank, world, sampler=smp)
             else:
                 raise SystemExit(f"unknown secondary workload {name}")
         except Exception as exc:  # a secondary failure must not take the headline line down; it is reported, not hidden

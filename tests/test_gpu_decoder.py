@@ -523,6 +523,7 @@ def test_generate_speculative_next_window_is_transparent(mini, timestamps):
         stats = dict(model.speculation_stats)
     finally:
         model.speculate_next_window = False
+        model.speculation_sms = None  # automatic budget (exercised by the SE-DiCoW long-form test)
         gc.return_timestamps = True
     print("speculation:", stats)
     assert torch.equal(plain["sequences"], spec["sequences"])

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--windows", type=int, default=4)
     ap.add_argument("--tokens", type=int, default=64)
-    ap.add_argument("--sms", type=int, default=64)
+    ap.add_argument("--sms", type=int, default=0, help="0 = automatic")
     ap.add_argument("--se", action="store_true")
     ap.add_argument("--timestamps", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
@@ -53,7 +53,7 @@ def main():
     kw = dict(stno_mask=stno, forced_decoder_ids=prompt, return_segments=True)
     if enr is not None:
         kw["enrollments"] = enr
-    model.speculation_sms = args.sms
+    model.speculation_sms = args.sms or None
 
     def run(spec):
         model.speculate_next_window = spec

@@ -325,3 +325,68 @@ def se_dicow_greedy(dev, rank: int, world: int, batch: int = 16, new_tokens: int
     del model, batches, ids
     torch.cuda.empty_cache()
     return out
+
+
+def longform_speculation(dev, rank: int, world: int, batch: int = 16, windows: int = 3, new_tokens: int = 64, reps: int = 3,
+                         sampler=None) -> dict:
+    """long-form generate() over synthetic multi-window recordings (large-v3-turbo + FDDT, timestamps
+    off so that every window advances by a full window, EOS suppressed: every window decodes ``new_tokens`` tokens), the plain
+    seek loop against ``speculate_next_window`` (the window at seek + 3000 encoded on part of the SMs under the decode steps
+    of the current one), interleaved in one process; the sequences must be identical."""
+    from ts_asr_whisper_b200 import parallel
+    from ts_asr_whisper_b200.modeling_dicow import DiCoWForConditionalGeneration
+    torch.manual_seed(4321)
+    with torch.device(dev):
+        model = DiCoWForConditionalGeneration(turbo_config(pad_token_id=EOS, eos_token_id=EOS,
+                                                           decoder_start_token_id=SOT)).eval()
+    perturb_(model.get_encoder(), dev)
+    B, W = batch, windows
+    g = torch.Generator().manual_seed(5 + rank)
+    feats = (torch.randn(B, 128, 3000 * W, generator=g) * 0.4 - 0.3).clamp_(-1.0, 1.5).to(dev)
+    stno = torch.softmax(3.0 * torch.randn(B, 4, 1500 * W, generator=g), dim=1).to(dev)
+    gc = model.generation_config
+    gc.no_timestamps_token_id, gc.eos_token_id, gc.pad_token_id = 50364, EOS, EOS
+    gc.suppress_tokens, gc.begin_suppress_tokens = [EOS, 220, 50256], None
+    gc.return_timestamps, gc.max_new_tokens, gc.num_beams = False, new_tokens, 1
+    prompt = torch.tensor([[SOT, LANG, TASK, 50364]] * B)
+    kw = dict(stno_mask=stno, forced_decoder_ids=prompt, return_segments=True)
+
+    def run(spec):
+        model.speculate_next_window = spec
+        _barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = model.generate(feats, **kw)
+        e1.record()
+        _barrier()
+        return e0.elapsed_time(e1), out["sequences"], dict(model.speculation_stats)
+
+    with torch.no_grad():
+        run(False), run(True)  # graphs, lazy loads
+        m0 = sampler.mark() if sampler else 0
+        ms = {False: [], True: []}
+        ref, identical, stats = None, True, None
+        for _ in range(reps):
+            for spec in (False, True):
+                t, seq, st = run(spec)
+                ms[spec].append(t)
+                ref = seq if ref is None else ref
+                identical = identical and bool(torch.equal(ref, seq))
+                stats = st if spec else stats
+        m1 = sampler.mark() if sampler else 0
+    med = {k: sorted(v)[len(v) // 2] for k, v in ms.items()}
+    plain, spec = parallel.max_over_ranks([med[False], med[True]], dev)
+    out = {
+        "workload": f"SURVEY 8(f).3: long-form generate(), {B} recordings x {W} windows per GPU, {new_tokens} tokens / window, "
+                    "large-v3-turbo + FDDT, timestamps off",
+        "value": world * B * W / (spec * 1e-3), "unit": "windows/s", "n_gpus": world,
+        "ms_per_call_plain_seek_loop": plain, "ms_per_call_speculative": spec, "speedup": plain / spec,
+        "windows_per_s_plain": world * B * W / (plain * 1e-3), "speculation_sms": model.speculation_sms if model.speculation_sms is not None else "auto",
+        "speculation_stats": stats, "identical_sequences": identical, "reps": reps, "dtype": "bf16",
+    }
+    if sampler:
+        out["clocks"] = sampler.window(m0, m1)
+    model.clear_decode_cache()
+    del model, feats, stno
+    torch.cuda.empty_cache()
+    return out

@@ -1185,6 +1185,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
         spec = None
         speculate = bool(getattr(self, "speculate_next_window", False)) and dev.type == "cuda"
         self.speculation_stats = {"hits": 0, "misses": 0}
+        timing: dict = {}  # the speculative pass' SM budget and whether the last pass kept the loop waiting
         while bool((seek < max_frames).any()):
             # drop finished recordings from the batch (HF:_maybe_reduce_batch)
             keep = [i for i, prev in enumerate(batch_idx_map) if seek[prev] < max_frames[prev]]
@@ -1239,6 +1240,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             if spec is not None:
                 # the window encoded ahead (below) is this iteration's window for every recording still in the batch
                 if all(prev in spec["rows"] and spec["at"][prev] == int(seek[prev]) for prev in batch_idx_map):
+                    timing["waited"] = not spec["done"].query()  # the decode finished first: the pass wants more SMs
                     torch.cuda.current_stream(dev).wait_event(spec["done"])
                     pick = [spec["rows"][prev] for prev in batch_idx_map]
                     hidden = spec["hidden"] if pick == list(range(spec["hidden"].shape[0])) else \
@@ -1271,7 +1273,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
                     with torch.cuda.stream(side):
                         a_in, a_stno = window_inputs(ahead, at)
                         a_enr, a_kv, _ = enrollment_args([prev for _, prev in ahead], False)
-                        with ops.sm_budget(dev, self.speculation_sms):
+                        with ops.sm_budget(dev, self._speculation_budget(dev, len(ahead), max_total - P, timing)):
                             a_hidden = enc(a_in, stno_mask=a_stno, enrollments=a_enr, enrollment_kv=a_kv).last_hidden_state
                         done = torch.cuda.Event()
                         done.record(side)
@@ -1335,7 +1337,40 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
 
     # ---- long-form speculation -------------------------------------------------------------
     speculate_next_window = False  # generate(): encode the window at seek + 3000 under the decode steps of the current one
-    speculation_sms = 64           # SMs the speculative encoder pass sizes its persistent kernels for (the rest: decode)
+    speculation_sms = None         # SMs the speculative encoder pass sizes its persistent kernels for (the rest: decode);
+    #                                None: chosen per window from the measured encoder / decode times (_speculation_budget)
+
+    def _speculation_budget(self, dev, windows: int, new_tokens: int, timing: dict) -> int:
+        """The speculative pass should end about when the decode steps of the current window do: with too few SMs the next
+        iteration waits for it at reduced width, with too many the decode steps starve (measured, 16 recordings x 4 windows:
+        64-token windows -- 64 SMs 275 -> 269 ms, 96 SMs 271 -> 247; SE-DiCoW with 128-token windows -- 64 SMs 441 -> 392,
+        96 SMs 409).  First window: device x encoder share of (encoder + decode) time, from a FLOP / step-count estimate; every
+        later window moves the budget towards the side that finished last (the previous pass was still running when its output
+        was needed: more SMs; it had finished: fewer), by 16 SMs at first, half as many after every reversal."""
+        if self.speculation_sms is not None:
+            return int(self.speculation_sms)
+        cfg = self.config
+        phys = torch.cuda.get_device_properties(dev).multi_processor_count
+        lo, hi = max(2, int(0.22 * phys) & ~1), int(0.8 * phys) & ~1
+        b = timing.get("budget")
+        if b is None:
+            T, d, ffn, L = cfg.max_source_positions, cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_layers
+            enc_ms = L * (2.0 * T * (4 * d * d + 2 * d * ffn) + 4.0 * T * T * d) / 1e12  # ~1 PFLOP/s, per window
+            if cfg.use_enrollments and cfg.scb_layers:
+                enc_ms *= 1.0 + cfg.scb_layers / max(1, L)
+            dec_ms = new_tokens * 0.11 * cfg.decoder_layers / max(1, windows)  # latency-bound steps, shared by the batch
+            b = int(phys * (0.1 + enc_ms / max(enc_ms + dec_ms, 1e-6)))
+        elif "waited" in timing:
+            up = bool(timing.pop("waited"))
+            step = timing.get("step", 16)
+            if "up" in timing and timing["up"] != up:  # overshot the balance point: smaller steps from here on
+                step = max(4, step // 2)
+            timing["step"], timing["up"] = step, up
+            b += step if up else -step
+        b = min(max(b & ~1, lo), hi)
+        timing["budget"] = b
+        self.speculation_stats.setdefault("sm_budgets", []).append(b)
+        return b
 
     def _speculation_stream(self, dev):
         key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())

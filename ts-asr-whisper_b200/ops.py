@@ -103,7 +103,7 @@ class sm_budget:
         return False
 
 
-_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) if os.environ.get("DICOW_RAW_STREAM", "1") != "0" else None
 
 
 def _stream(dev: torch.device) -> int:
