@@ -327,7 +327,7 @@ def se_dicow_greedy(dev, rank: int, world: int, batch: int = 16, new_tokens: int
     return out
 
 
-def longform_speculation(dev, rank: int, world: int, batch: int = 16, windows: int = 3, new_tokens: int = 64, reps: int = 3,
+def longform_speculation(dev, rank: int, world: int, batch: int = 16, windows: int = 6, new_tokens: int = 64, reps: int = 2,
                          sampler=None) -> dict:
     """long-form generate() over synthetic multi-window recordings (large-v3-turbo + FDDT, timestamps
     off so that every window advances by a full window, EOS suppressed: every window decodes ``new_tokens`` tokens), the plain
