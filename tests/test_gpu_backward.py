@@ -60,7 +60,8 @@ def test_layernorm_fddt_backward(ops, d, T, B, fddt, ln):
         assert rel(dfw, fw.grad) < 1e-3 and rel(dfb, fb.grad) < 1e-3
 
 
-@pytest.mark.parametrize("form,M,N,K", [(1, 640, 1536, 384), (2, 640, 1536, 384), (2, 3000, 5120, 1280), (2, 777, 1000, 264)])
+@pytest.mark.parametrize("form,M,N,K", [(1, 640, 1536, 384), (2, 640, 1536, 384), (2, 3000, 5120, 1280), (2, 777, 1000, 264),
+                                        (0, 12000, 1280, 640)])  # form 0: the library's choice at the fine-tune step's row count
 def test_colsum_and_gelu_epilogues(ops, form, M, N, K):
     """form 1 = single-CTA kernel, 2 = CTA pairs (both outputs / the dgelu product leave through TMA stores)"""
     g = torch.Generator(device=DEV).manual_seed(1)
