@@ -29,7 +29,8 @@ def test_exports_match_header(lib):
     so = lib.load_library()
     for name in declared:
         assert hasattr(so, name), f"{name} not exported by libdicow_b200.so"
-    assert so.dicow_abi_version() >= 1
+    from ts_asr_whisper_b200 import lib as _l
+    assert so.dicow_abi_version() == _l.ABI_VERSION
 
 
 @pytest.mark.parametrize("cname,pyname", [("dicow_gemm_args_t", "GemmArgs"), ("dicow_fddt_ln_args_t", "FddtLnArgs"),

@@ -68,7 +68,9 @@ static int make_tmap(dicow_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype
 
 using namespace dicow;
 
-extern "C" int dicow_abi_version(void) { return 1; }
+// 2: round 2 -- dicow_attention_bwd_args_t.workspace_floats, dicow_fddt_ln_args_t.x_out, dicow_ln_bwd_args_t.g_colsum,
+//    dicow_ctc_loss_args_t.ld / dicow_ctc_bwd_args_t.ld, dicow_set_sm_budget
+extern "C" int dicow_abi_version(void) { return 2; }
 
 extern "C" int dicow_create(int device, dicow_handle_t* out) {
   if (out == nullptr) return DICOW_ERR_INVALID_ARG;

@@ -259,6 +259,9 @@ _lib = None
 _handles: dict[int, C.c_void_p] = {}
 
 
+ABI_VERSION = 2  # what the struct mirrors in this file describe (dicow_abi_version() of the loaded library must match)
+
+
 def load_library() -> C.CDLL:
     """dlopen the shared library and declare prototypes (no GPU needed)."""
     global _lib
@@ -273,6 +276,9 @@ def load_library() -> C.CDLL:
                 "There is no fallback path.")
         lib = C.CDLL(LIB_PATH)
         _declare(lib)
+        if lib.dicow_abi_version() != ABI_VERSION:
+            raise DicowError(f"{LIB_PATH} has ABI version {lib.dicow_abi_version()}, the Python bindings expect {ABI_VERSION}: "
+                             "rebuild with `python __graft_entry__.py build`")
         _lib = lib
         return lib
 
