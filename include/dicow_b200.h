@@ -694,6 +694,27 @@ typedef struct {
 } dicow_ctc_loss_args_t;
 DICOW_API int dicow_ctc_loss(dicow_handle_t h, const dicow_ctc_loss_args_t* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * AdamW step over a list of fp32 tensors in ONE launch (the update rule of torch.optim.AdamW, which the reference's
+ * get_optimizer builds: src/models/containers.py:100-114).  tensors: device array, one entry per parameter; chunks: device array of
+ * n_chunks {tensor index, chunk index} int32 pairs covering every tensor in pieces of dicow_adamw_chunk_elems() elements.
+ * Per tensor: p *= 1 - lr * weight_decay; m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2;
+ *             p -= (lr / bias_correction1) * m / (sqrt(v) / bias_correction2_sqrt + eps).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* p;        /* parameter, updated in place */
+  const float* g;  /* gradient */
+  float* m;        /* exp_avg, updated in place */
+  float* v;        /* exp_avg_sq, updated in place */
+  int64_t n;       /* elements */
+  float lr, weight_decay;
+  float bias_correction1;      /* 1 - beta1^step */
+  float bias_correction2_sqrt; /* sqrt(1 - beta2^step) */
+} dicow_adamw_tensor_args_t;
+DICOW_API int dicow_adamw_chunk_elems(void);
+DICOW_API int dicow_adamw_step(dicow_handle_t h, const dicow_adamw_tensor_args_t* tensors, const int32_t* chunks, int n_chunks,
+                               float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,8 @@ def test_exports_match_header(lib):
                                           ("dicow_beam_step_args_t", "BeamStepArgs"),
                                           ("dicow_augment_args_t", "AugmentArgs"),
                                           ("dicow_decode_layer_args_t", "DecodeLayerArgs"),
-                                          ("dicow_decode_layers_args_t", "DecodeLayersArgs")])
+                                          ("dicow_decode_layers_args_t", "DecodeLayersArgs"),
+                                          ("dicow_adamw_tensor_args_t", "AdamwTensorArgs")])
 def test_struct_mirrors(lib, cname, pyname):
     m = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", _header_text(), flags=re.S)
     assert m, cname

@@ -452,3 +452,33 @@ def test_se_dicow_ctc_pretrain_step():
     torch.cuda.synchronize()
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
     _compare(model, p, trainable, "se-ctc-pretrain", _gate_refs(p, gates))
+
+
+def test_adamw_single_launch_matches_torch():
+    """ts_asr_whisper_b200.optim.AdamW (one launch over all tensors, csrc/optimizer.cu) against torch.optim.AdamW(fused=True) on
+    ragged tensor sizes, two parameter groups (the reference's get_optimizer: a higher learning rate and no weight decay for the
+    second one), several steps; state_dict round trip into torch's optimizer"""
+    from ts_asr_whisper_b200.optim import AdamW
+    g = torch.Generator(device=DEV).manual_seed(3)
+    shapes = [(1280, 1280), (5120,), (1, ), (3, 77), (16385,), (4, 1280), (51866, 8), (33,)]
+    a = [torch.nn.Parameter(torch.randn(*s, device=DEV, generator=g)) for s in shapes]
+    b = [torch.nn.Parameter(x.detach().clone()) for x in a]
+    kw = dict(lr=3e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    ours = AdamW([{"params": a[:5]}, {"params": a[5:], "lr": 3e-2, "weight_decay": 0.0}], **kw)
+    ref = torch.optim.AdamW([{"params": b[:5]}, {"params": b[5:], "lr": 3e-2, "weight_decay": 0.0}], fused=True, **kw)
+    for step in range(4):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, device=DEV, generator=g) * (0.1 if step else 3.0)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        if step == 2:  # a parameter without a gradient is skipped by both
+            a[1].grad = b[1].grad = None
+        ours.step()
+        ref.step()
+    torch.cuda.synchronize()
+    for x, y, s in zip(a, b, shapes):
+        err = (x - y).abs().max().item() / max(y.abs().max().item(), 1e-12)
+        assert err < 2e-6, (s, err)
+    for x, y in zip(a, b):
+        assert (ours.state[x]["exp_avg_sq"] - ref.state[y]["exp_avg_sq"]).abs().max().item() <= 1e-6 * ref.state[y]["exp_avg_sq"].abs().max().item() + 1e-12
+    fresh = torch.optim.AdamW([{"params": b[:5]}, {"params": b[5:]}], **kw)
+    fresh.load_state_dict(ours.state_dict())  # same state layout

@@ -35,7 +35,9 @@ def main():
     for n, p in model.named_parameters():
         p.requires_grad_((n.startswith("model.encoder.") and "embed_positions" not in n) if fine else n.startswith(head))
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True)
+    from ts_asr_whisper_b200.optim import AdamW
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True) if os.environ.get("DICOW_TORCH_ADAMW") == "1" \
+        else AdamW(params, lr=1e-5, weight_decay=0.0)
     batch = bt.make_train_batch(B, 64, 5, dev)
 
     def step():

@@ -147,7 +147,11 @@ def train_step(workload: str, dev, rank: int, world: int, steps: int = 5, warmup
             p.requires_grad_(n.startswith(head))
     params = [p for p in model.parameters() if p.requires_grad]
     n_train = sum(p.numel() for p in params)
-    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True)
+    if os.environ.get("DICOW_TORCH_ADAMW") == "1":
+        opt, opt_name = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True), "torch AdamW(fused=True)"
+    else:  # what containers.get_optimizer returns: torch.optim.AdamW's update in one launch (optim.py)
+        from ts_asr_whisper_b200.optim import AdamW
+        opt, opt_name = AdamW(params, lr=1e-5, weight_decay=0.0), "ts_asr_whisper_b200.optim.AdamW (single launch)"
     exchange = parallel.GradientExchange()
     batches = [make_train_batch(B, label_len, 100 + 10 * rank + i, dev) for i in range(3)]
     state = {"exchange": True, "loss": None}
@@ -198,7 +202,7 @@ def train_step(workload: str, dev, rank: int, world: int, steps: int = 5, warmup
                      "BASELINE configs[4]: CTC encoder pre-train step (CTC head trained), large-v3-turbo"),
         "value": value, "unit": "utt/s", "ms_per_step": ms / steps, "steps": steps, "warmup": max(3, warmup),
         "batch_per_gpu": B, "label_len": label_len, "n_gpus": world, "trainable_params": n_train,
-        "optimizer": "torch AdamW(fused=True), fp32 master weights", "dtype": "bf16",
+        "optimizer": opt_name + ", fp32 master weights", "dtype": "bf16",
         "gflop_per_utt": gf, "tflops_per_gpu": tf,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                      "floor_ms": B * gf / peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"

@@ -12,10 +12,13 @@ Same constructor arguments, attributes (.model, .feature_extractor, .tokenizer) 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .feature_extraction import DiCoWFeatureExtractor
 from .modeling_dicow import DiCoWForConditionalGeneration
+from .optim import AdamW
 
 
 # DiCoWConfig overrides and where the reference takes them from (src/models/containers.py:27-46); None = keep the checkpoint's
@@ -82,6 +85,9 @@ def get_optimizer(model, training_args, prefixes_with_higher_lr=None):
     for name, param in model.named_parameters():
         groups[bool(fast_prefixes) and name.startswith(fast_prefixes)].append(param)
     lr = training_args.learning_rate
-    return torch.optim.AdamW(
+    # the same optimizer (a torch.optim.AdamW subclass: update rule, param groups and state_dict unchanged); its step() updates
+    # all fp32 CUDA parameters in one launch (optim.py).  DICOW_TORCH_ADAMW=1 returns the stock class.
+    cls = torch.optim.AdamW if os.environ.get("DICOW_TORCH_ADAMW") == "1" else AdamW
+    return cls(
         [dict(params=groups[False]), dict(params=groups[True], lr=training_args.fddt_lr_multiplier * lr, weight_decay=0.0)],
         lr=lr, weight_decay=training_args.weight_decay)

@@ -245,6 +245,13 @@ class SoftlabelCeArgs(C.Structure):
     ]
 
 
+class AdamwTensorArgs(C.Structure):  # dicow_adamw_tensor_args_t: one entry of the device-resident tensor table
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64),
+        ("lr", C.c_float), ("weight_decay", C.c_float), ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float),
+    ]
+
+
 class CtcLossArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -293,6 +300,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.dicow_last_error.restype = C.c_char_p
     lib.dicow_check.argtypes = [vp]
     lib.dicow_set_sm_budget.argtypes = [vp, C.c_int]
+    lib.dicow_adamw_chunk_elems.argtypes = []
+    lib.dicow_adamw_step.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
     lib.dicow_check.restype = C.c_int
     lib.dicow_abi_version.argtypes = []
     lib.dicow_abi_version.restype = C.c_int
@@ -347,7 +356,7 @@ EXPORTED_SYMBOLS = [
     "dicow_layernorm_fddt_bwd", "dicow_colsum", "dicow_conv1d_col2im", "dicow_ctc_loss_bwd", "dicow_softlabel_ce_bwd",
     "dicow_dgelu_mul", "dicow_embedding_bwd", "dicow_cast_f32_bf16_2d", "dicow_gate_bwd", "dicow_decode_linear", "dicow_kv_to_head_major", "dicow_ctc_joint_step",
     "dicow_log_softmax_rows", "dicow_beam_step", "dicow_fddt_full_combine", "dicow_stno_mask", "dicow_augment_batch", "dicow_fddt_full_scatter",
-    "dicow_decode_layers", "dicow_set_sm_budget",
+    "dicow_decode_layers", "dicow_set_sm_budget", "dicow_adamw_step", "dicow_adamw_chunk_elems",
 ]
 
 
