@@ -544,6 +544,142 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attention_kernel(const D
   }
 }
 
+// Cross attention over the head-major cache ([B, H, T, k(64) | v(64)]: ONE contiguous 256 B x T stream per (batch, head)): the
+// stream goes through a shared-memory ring filled by cp.async.bulk instead of through registers.  With the register version a
+// CTA keeps 32 KB of loads in flight and streams at a fixed ~15 GB/s whatever runs next to it (tools/probe_decode_attn.py:
+// 160, 320 and 440 CTAs take 26, 31 and 33 us) -- B x H = 320 CTAs on 148 SMs (2.2 per SM, three fit) leave the device at
+// 3.95 TB/s.  Here a CTA keeps CX_STAGES x 16 KB in flight without holding a register for it.
+// Same mapping as decode_attention_kernel: an 8-lane group owns a key (lane = 8 dims), online softmax per group.
+constexpr int CX_WARPS = 8;       // consumer warps (+ 1 producer warp)
+constexpr int CX_KEYS = 64;       // keys per stage: 16 KB
+constexpr int CX_STAGES = 4;
+
+__device__ __forceinline__ void cx_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__((CX_WARPS + 1) * 32) decode_cross_attention_ring_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(128) uint8_t cx_smem[];
+  __shared__ uint64_t full[CX_STAGES], empty[CX_STAGES];
+  __shared__ float sm_m[CX_WARPS], sm_l[CX_WARPS], sm_o[CX_WARPS][64];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CX_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CX_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  griddep_launch();
+  const int Tk = p.Tk;
+  const int nchunks = (Tk + CX_KEYS - 1) / CX_KEYS;
+  const int bkv = p.kv_batch_div > 1 ? b / p.kv_batch_div : b;
+  const __nv_bfloat16* stream = p.K + (long long)bkv * p.kv_bs + (long long)h * p.kv_hs;  // 128 elements per key: k | v
+  if (warp == CX_WARPS) {
+    // ===================== producer: the cache is immutable during the step (written once per window) =====================
+    for (int c = 0; c < nchunks; ++c) {
+      const int st = c % CX_STAGES;
+      mbar_wait(&empty[st], ((c / CX_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        const int nk = min(CX_KEYS, Tk - c * CX_KEYS);
+        const uint32_t bytes = (uint32_t)nk * 256u;
+        mbar_arrive_expect_tx(&full[st], bytes);
+        cx_bulk_g2s(cx_smem + st * CX_KEYS * 256, stream + (long long)c * CX_KEYS * 128, bytes, &full[st]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  const int grp = lane >> 3, sub = lane & 7;
+  griddep_wait();  // q comes from the previous kernel of the step
+  float q[8];
+  unpack8(__ldcg(reinterpret_cast<const uint4*>(p.Q + (long long)b * p.q_bs + h * 64 + sub * 8)), q);
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % CX_STAGES;
+    mbar_wait(&full[st], (c / CX_STAGES) & 1);
+    const uint8_t* base = cx_smem + st * CX_KEYS * 256 + sub * 16;
+    constexpr int PER = CX_KEYS / (CX_WARPS * 4);  // keys of this chunk per 8-lane group
+    uint4 kv[PER], vv[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int kl = (u * CX_WARPS + warp) * 4 + grp;  // key within the chunk
+      kv[u] = *reinterpret_cast<const uint4*>(base + kl * 256);
+      vv[u] = *reinterpret_cast<const uint4*>(base + kl * 256 + 128);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // the stage is in registers
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int k = c * CX_KEYS + (u * CX_WARPS + warp) * 4 + grp;
+      const bool ok = k < Tk;  // uniform within the 8-lane group
+      float kf[8];
+      float s = 0.f;
+      if (ok) {
+        unpack8(kv[u], kf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (ok) {
+        const float mn = fmaxf(m, s);
+        const float corr = __expf(m - mn);  // 0 for the first key (m = -inf)
+        const float pw = __expf(s - mn);
+        float vf[8];
+        unpack8(vv[u], vf);
+        l = fmaf(l, corr, pw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(o[i], corr, pw * vf[i]);
+        m = mn;
+      }
+    }
+  }
+  // merge the 4 groups of the warp (lanes with the same `sub`), then the warps
+#pragma unroll
+  for (int x = 8; x <= 16; x <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, x);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, x);
+    const float mn = fmaxf(m, m2);
+    const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+    const float c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float o2 = __shfl_xor_sync(0xffffffffu, o[i], x);
+      o[i] = o[i] * c1 + o2 * c2;
+    }
+    m = mn;
+  }
+  if (grp == 0) {
+    if (sub == 0) sm_m[warp] = m, sm_l[warp] = l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm_o[warp][sub * 8 + i] = o[i];
+  }
+  named_bar_sync(1, CX_WARPS * 32);  // the producer warp has left
+  if (threadIdx.x < 64) {
+    float mt = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < CX_WARPS; ++w) mt = fmaxf(mt, sm_m[w]);
+    float lt = 0.f, ot = 0.f;
+#pragma unroll
+    for (int w = 0; w < CX_WARPS; ++w) {
+      const float c = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - mt);
+      lt = fmaf(sm_l[w], c, lt);
+      ot = fmaf(sm_o[w][threadIdx.x], c, ot);
+    }
+    p.out[(long long)b * p.o_bs + h * 64 + threadIdx.x] = __float2bfloat16_rn(ot / lt);
+  }
+}
+
 // Several queries against ONE K/V stream: beam search, where the NQ hypotheses of an utterance attend to the same encoder
 // states (cross attention).  One CTA per (head, utterance): every key / value row is loaded once and used by all NQ
 // queries (the single-query kernel re-reads the 384 KB stream once per hypothesis: 5 x at 5 beams, 74 us per layer for
@@ -1044,7 +1180,21 @@ extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_
     }
     return DICOW_OK;
   }
-  if (a->pos == nullptr && a->Tk >= 512)
+  // the head-major cross-attention cache: k | v of a key are 256 contiguous bytes, keys contiguous -> shared-memory ring kernel
+  static const bool ring_enabled = [] {
+    const char* e = getenv("DICOW_DECODE_ATTN_RING");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool ring_ok = ring_enabled && a->pos == nullptr && a->ancestry == nullptr && a->Tk >= 512 && a->kv_row_stride == 128 &&
+                       reinterpret_cast<const __nv_bfloat16*>(a->V) == reinterpret_cast<const __nv_bfloat16*>(a->K) + 64 &&
+                       (p.kv_hs % 8) == 0 && (p.kv_bs % 8) == 0;
+  if (ring_ok) {
+    constexpr size_t smem = (size_t)CX_STAGES * CX_KEYS * 256;
+    static DeviceOnce attr_once;
+    if (attr_once.first(ctx))
+      DICOW_CUDA_OK(ctx, cudaFuncSetAttribute(decode_cross_attention_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DICOW_CUDA_OK(ctx, launch_step_kernel(decode_cross_attention_ring_kernel, grid, dim3((CX_WARPS + 1) * 32), smem, stream, 1, p));
+  } else if (a->pos == nullptr && a->Tk >= 512)
     DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_kernel<8>, grid, dim3(8 * 32), 0, stream, 1, p));
   else
     DICOW_CUDA_OK(ctx, launch_step_kernel(decode_attention_kernel<4>, grid, dim3(4 * 32), 0, stream, 1, p));
