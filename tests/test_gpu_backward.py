@@ -198,3 +198,16 @@ def test_fddt_full_scatter(rows, T, d):
     m = stno.permute(0, 2, 1).reshape(rows, 4)                       # [rows, class]
     ref = (m[:, :, None] * G[:, None, :]).to(torch.bfloat16).reshape(rows, 4 * d)
     assert torch.equal(dY, ref)
+
+
+@pytest.mark.parametrize("rows,cols,cols_out", [(37, 51867, 51872), (5, 7, 8), (300, 1280, 1280), (3, 33, 40)])
+def test_cast_bf16_padded(ops, rows, cols, cols_out):
+    """fp32 [rows, cols] (odd row lengths: unaligned rows) -> bf16 [rows, cols_out] with zeroed padding columns"""
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    buf = torch.randn(rows, cols + 3, device=DEV, generator=g)
+    src = buf[:, :cols]  # row stride cols + 3
+    out = ops.cast_bf16_padded(src, cols_out)
+    torch.cuda.synchronize()
+    assert out.shape == (rows, cols_out) and out.dtype == torch.bfloat16
+    assert torch.equal(out[:, :cols], src.bfloat16())
+    assert not out[:, cols:].float().abs().any()

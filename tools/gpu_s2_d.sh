@@ -1,6 +1,6 @@
 #!/bin/bash
-echo "--- split"; python tools/probe_decode_attn.py 2>&1 | tail -6
-timeout 900 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_beam.py tests/test_gpu_ctc_joint.py tests/test_gpu_turbo_parity.py -q -x -k "not megakernel" 2>&1 | tail -2 | cut -c1-200
-for v in 1 2; do python tools/bench_decode.py --workload se_dicow 2>/dev/null | python -c "
+timeout 600 python -m pytest tests/test_gpu_backward.py tests/test_gpu_training.py -q -x -k "cast_bf16_padded or ctc_pretrain" 2>&1 | tail -2 | cut -c1-200
+python tools/profile_train.py --workload ctc_pretrain 2>&1 | grep -E "cast_2d|total GPU" | cut -c1-120
+python tools/bench_train.py --workload ctc_pretrain --steps 10 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('split', round(d['ms_per_batch'],2), round(d['ms_per_decode_step'],4), d.get('clocks'))"; done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ctc ms/step', round(d['ms_per_step'],2), d['clocks'])"
