@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/dicow_b200.h"
@@ -71,5 +72,36 @@ struct DeviceHighWater {
     return true;
   }
 };
+
+// Launch of a decode-step kernel: optional cluster dimension, and the programmatic-dependent-launch attribute (ptx.cuh:
+// griddep_wait / griddep_launch) unless DICOW_PDL=0.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DICOW_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster_x, attrs[n].val.clusterDim.y = 1, attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs, cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace dicow

@@ -62,17 +62,10 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p) {  // weights: re
   return v;
 }
 
-// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, calls griddep_launch() early (the next kernel of the step may be
-// scheduled as soon as every CTA of this one has got here) and griddep_wait() before it touches anything an earlier
-// kernel of the step wrote.  What a kernel does before the wait -- index arithmetic and, for the linear layers, issuing
-// the loads of its (immutable) weight slab -- overlaps the tail of its predecessor, which is most of the per-kernel cost
-// of a step whose kernels each move a few MB.  Both instructions are no-ops for a launch without the attribute.
-// A kernel launched this way can be resident while its predecessors still run, so everything the step's kernels
-// exchange (x, q, ctx, h, the K/V cache, logits, ids, pos, unfinished) is read with ld.global.cg (L2 only): an L1 line
-// filled before the producer's store would otherwise be a stale hit.  Weights, biases and tables are immutable (nc).
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_cg_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
@@ -84,39 +77,6 @@ __device__ __forceinline__ void cluster_arrive_all() { asm volatile("barrier.clu
 __device__ __forceinline__ void cluster_wait_all() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
   asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-
-// Measured (tools/profile_decode.py, B = 16 turbo decoder, CUDA graph): with the attribute the kernels of a step do
-// overlap (485 us of overlap per 520 us step) but the step is no shorter (0.51-0.54 ms vs 0.49-0.53 ms without): the
-// step is bound by the kernels' own latency chains, not by launch gaps (idle gaps 9-12 us per step either way).  The
-// attribute is therefore OFF unless DICOW_PDL=1; the griddepcontrol instructions are no-ops then.
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("DICOW_PDL");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_step_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                               unsigned cluster_x, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
-  unsigned n = 0;
-  if (cluster_x > 1) {
-    attrs[n].id = cudaLaunchAttributeClusterDimension;
-    attrs[n].val.clusterDim.x = cluster_x, attrs[n].val.clusterDim.y = 1, attrs[n].val.clusterDim.z = 1;
-    ++n;
-  }
-  if (pdl_enabled()) {
-    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  cfg.attrs = attrs, cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // One CTA = 8 output columns; its 8 warps split K in 32-element blocks (warp w takes blocks w, w + 8, ...).  Lane
@@ -226,22 +186,22 @@ struct DecLinParams {
   int ksplit, tiles_per_cta, Ks, a_pitch;  // Ks = K / ksplit; a_pitch = shared-memory row pitch of A in elements
 };
 
-__device__ __forceinline__ void dl_store(const DecLinParams& p, int row, int n, float v) {
+// bias / resid / pos_off: the epilogue's operands, requested by the caller before the multiply (they do not depend on it)
+__device__ __forceinline__ void dl_store(const DecLinParams& p, int row, int n, float v, float bias, float resid, long long pos_off) {
   if (row >= p.M || n >= p.N) return;
-  if (p.bias != nullptr) v += __ldg(p.bias + n);
+  v += bias;
   void* dst = p.out;
   long long o = (long long)row * p.ldo + n;
   if (p.out2 != nullptr && n >= p.n_split) {
     dst = p.out2;
-    o = (long long)row * p.ldo2 + (n - p.n_split);
-    if (p.pos != nullptr) o += (long long)__ldcg(p.pos) * p.pos_stride;
-  } else if (p.out2 == nullptr && p.pos != nullptr) {
-    o += (long long)__ldcg(p.pos) * p.pos_stride;
+    o = (long long)row * p.ldo2 + (n - p.n_split) + pos_off;
+  } else if (p.out2 == nullptr) {
+    o += pos_off;
   }
   switch (p.epilogue) {
     case DICOW_EPI_BIAS_BF16: reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v); break;
     case DICOW_EPI_BIAS_GELU_BF16: reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(gelu_erf_fast(v)); break;
-    case DICOW_EPI_RESIDUAL_F32: reinterpret_cast<float*>(dst)[o] = __ldcg(p.resid + (long long)row * p.ldr + n) + v; break;
+    case DICOW_EPI_RESIDUAL_F32: reinterpret_cast<float*>(dst)[o] = resid + v; break;
     default: reinterpret_cast<float*>(dst)[o] = v; break;
   }
 }
@@ -346,19 +306,40 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     }
     cluster_sync_all();  // release / acquire: the rows written by the peers are visible
   } else {
+    // cp.async (L2 only, like ld.global.cg): every 16-byte piece of the slab is in flight at once.  The load + st.shared
+    // loop this replaces compiled to one L2 round trip per piece and thread (ten in a row for 16 rows of K = 1280), which
+    // was most of the duration of a layer's linear kernel.
     const int vec_per_row = p.Ks >> 3;
     for (int i = threadIdx.x; i < MT * 16 * vec_per_row; i += DL_THREADS) {
       const int r = i / vec_per_row, c = (i - r * vec_per_row) * 8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m0 + r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(p.A + (long long)(m0 + r) * p.lda + kbase + c));
-      *reinterpret_cast<uint4*>(sA + (size_t)r * p.a_pitch + c) = v;
+      __nv_bfloat16* dst = sA + (size_t)r * p.a_pitch + c;
+      if (m0 + r < p.M)
+        cp_async_cg_16(smem_u32(dst), p.A + (long long)(m0 + r) * p.lda + kbase + c);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
+    cp_async_wait_all();
   }
+  // the KV-cache append position: one L2 read here instead of one per stored element after the multiply
+  const long long pos_off = p.pos != nullptr ? (long long)__ldcg(p.pos) * p.pos_stride : 0ll;
   __syncthreads();
   if (!LN && p.ksplit > 1) cluster_wait_all();
 
+  constexpr int NV = (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS;  // output elements per thread and tile
   for (int tile = tile_first; tile < tile_end; ++tile) {
     load_w(tile + 1, wn);  // next tile's weights stream in while this one is multiplied (zeros past the last tile)
+    // bias and residual of the elements this thread stores: requested now, needed after the cross-warp / cluster sums
+    float ebias[NV], eres[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int e = threadIdx.x + j * DL_THREADS;
+      const int row = m0 + (e >> 3), n = tile * 8 + (e & 7);
+      ebias[j] = eres[j] = 0.f;
+      if (krank == 0 && e < MT * 16 * 8 && row < p.M && n < p.N) {
+        if (p.bias != nullptr) ebias[j] = __ldg(p.bias + n);
+        if (p.epilogue == DICOW_EPI_RESIDUAL_F32) eres[j] = __ldcg(p.resid + (long long)row * p.ldr + n);
+      }
+    }
     float acc[MT][4];
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
@@ -384,9 +365,9 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     }
     __syncthreads();
     // cross-warp sums; with split K the partial sums of ranks 1.. meet in rank 0's shared memory and are added in rank order
-    float v[(MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS];
+    float v[NV];
 #pragma unroll
-    for (int j = 0; j < (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int e = threadIdx.x + j * DL_THREADS;
       v[j] = 0.f;
       if (e < MT * 16 * 8) {
@@ -398,11 +379,11 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     if (p.ksplit > 1) cluster_sync_all();
     if (krank == 0) {
 #pragma unroll
-      for (int j = 0; j < (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS; ++j) {
+      for (int j = 0; j < NV; ++j) {
         const int e = threadIdx.x + j * DL_THREADS;
         if (e < MT * 16 * 8) {
           for (int r = 1; r < p.ksplit; ++r) v[j] += cpart[(size_t)(r - 1) * MT * 16 * 8 + e];
-          dl_store(p, m0 + (e >> 3), tile * 8 + (e & 7), v[j]);
+          dl_store(p, m0 + (e >> 3), tile * 8 + (e & 7), v[j], ebias[j], eres[j], pos_off);
         }
       }
     }
@@ -893,6 +874,7 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   __shared__ Best s_text[16], s_ts[16];
   __shared__ RulesPartial s_part[8];  // slices of cluster ranks 1..7 (on rank 0)
   __shared__ int s_text_off;
+  __shared__ unsigned long long s_last_ts;
   const int b = (int)blockIdx.x / csplit;
   const int rank = csplit > 1 ? (int)cluster_ctarank() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
@@ -907,15 +889,17 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   const long long penult = ngen >= 2 ? __ldcg(row_ids + len - 2) : -1;
   const bool last_was_ts = rules && ngen >= 1 && last >= p.ts_begin;
   const bool penult_was_ts = ngen < 2 || penult >= p.ts_begin;
-  // last timestamp token of the generated part (timestamps never decrease, so it is the maximum)
-  int ts_last = -1;
-  for (int i = len - 1; rules && i >= p.begin_index; --i) {
+  // last timestamp token of the generated part: every thread looks at its own positions and the latest one wins through
+  // a shared-memory maximum of (position, token).  (Every thread walking back from the end was a chain of dependent L2
+  // reads as long as the text since the last timestamp -- the whole sequence when there is none.)
+  if (tid == 0) s_last_ts = 0ull;
+  __syncthreads();
+  for (int i = p.begin_index + tid; rules && i < len; i += blockDim.x) {
     const long long tk = __ldcg(row_ids + i);
-    if (tk >= p.ts_begin) {
-      ts_last = (int)tk;
-      break;
-    }
+    if (tk >= p.ts_begin) atomicMax(&s_last_ts, ((unsigned long long)(i + 1) << 32) | (unsigned long long)(unsigned)tk);
   }
+  __syncthreads();
+  const int ts_last = s_last_ts != 0ull ? (int)(unsigned)(s_last_ts & 0xffffffffull) : -1;
   int ts_floor = p.ts_begin;  // timestamp ids below this are forbidden
   if (ts_last >= 0) ts_floor = (last_was_ts && !penult_was_ts) ? ts_last : ts_last + 1;
   const bool ts_all_masked = last_was_ts && penult_was_ts;
@@ -928,24 +912,40 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   const int v_begin = rank * chunk, v_end = min(p.V, v_begin + chunk);
   Best bt{-INFINITY, p.V}, bs{-INFINITY, p.V};
   float tmax = -INFINITY, tsum = 0.f;  // online logsumexp over the timestamp region
-  for (int v = v_begin + tid; v < v_end; v += blockDim.x) {
-    float x = __ldcg(lg + v);
-    bool masked = (p.suppress != nullptr && ((__ldg(p.suppress + (v >> 5)) >> (v & 31)) & 1u)) || (rules && v == p.no_timestamps);
-    if (v < p.ts_begin) {
-      masked = masked || at_begin || (text_lt_eos_masked && v < p.eos);
-      if (masked) x = -INFINITY;
-      bt = best_of(bt, Best{x, v});
-    } else {
-      masked = masked || ts_all_masked || v < ts_floor || v > ts_cap;
-      if (masked) x = -INFINITY;
-      bs = best_of(bs, Best{x, v});
-      if (x > -INFINITY) {
-        const float mn = fmaxf(tmax, x);
-        tsum = tsum * __expf(tmax - mn) + __expf(x - mn);
-        tmax = mn;
-      }
+  // RU scores (and their bitmap words) per thread are requested before any is looked at; the order in which a thread
+  // folds its scores is unchanged
+  constexpr int RU = 8;
+  for (int v0 = v_begin + tid; v0 < v_end; v0 += RU * (int)blockDim.x) {
+    float xs[RU];
+    unsigned sw[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int v = v0 + u * (int)blockDim.x;
+      xs[u] = v < v_end ? __ldcg(lg + v) : 0.f;
+      sw[u] = (p.suppress != nullptr && v < v_end) ? __ldg(p.suppress + (v >> 5)) : 0u;
     }
-    if (proc != nullptr) proc[v] = x;
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int v = v0 + u * (int)blockDim.x;
+      if (v >= v_end) break;
+      float x = xs[u];
+      bool masked = ((sw[u] >> (v & 31)) & 1u) || (rules && v == p.no_timestamps);
+      if (v < p.ts_begin) {
+        masked = masked || at_begin || (text_lt_eos_masked && v < p.eos);
+        if (masked) x = -INFINITY;
+        bt = best_of(bt, Best{x, v});
+      } else {
+        masked = masked || ts_all_masked || v < ts_floor || v > ts_cap;
+        if (masked) x = -INFINITY;
+        bs = best_of(bs, Best{x, v});
+        if (x > -INFINITY) {
+          const float mn = fmaxf(tmax, x);
+          tsum = tsum * __expf(tmax - mn) + __expf(x - mn);
+          tmax = mn;
+        }
+      }
+      if (proc != nullptr) proc[v] = x;
+    }
   }
   bt = warp_best(bt);
   bs = warp_best(bs);

@@ -161,6 +161,21 @@ __global__ void __launch_bounds__(128) ln_rows_kernel(const float* __restrict__ 
   __shared__ float sm[4];
   const int row = blockIdx.x, tid = threadIdx.x, nvec = d >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  // gamma / beta are requested before the row (loads are not moved across the barriers of the block sums by the
+  // compiler: after them they were a third memory round trip in a kernel that is nothing but latency) -- and before the
+  // dependency wait of a decode-step launch: they are immutable
+  float4 gv[3], bv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c4 = tid + 128 * i;
+    gv[i] = bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < nvec) {
+      gv[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      bv[i] = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    }
+  }
+  griddep_launch();
+  griddep_wait();
   float4 v[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -184,8 +199,8 @@ __global__ void __launch_bounds__(128) ln_rows_kernel(const float* __restrict__ 
   for (int i = 0; i < 3; ++i) {
     const int c4 = tid + 128 * i;
     if (c4 < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-      const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      const float4 g = gv[i];
+      const float4 be = bv[i];
       float4 y;
       y.x = fmaf((v[i].x - mean) * rstd, g.x, be.x);
       y.y = fmaf((v[i].y - mean) * rstd, g.y, be.y);
@@ -641,9 +656,8 @@ extern "C" int dicow_fddt_layernorm(dicow_handle_t h, const dicow_fddt_ln_args_t
   const bool few_rows = a->rows <= 128;
   if (few_rows && a->gamma != nullptr && a->stno == nullptr && a->delta1_bf16 == nullptr && a->delta2_bf16 == nullptr &&
       a->x_out_bf16 == nullptr && a->d <= 1536 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0) {
-    ln_rows_kernel<<<a->rows, 128, 0, stream>>>(a->x, a->d, a->gamma, a->beta, a->eps,
-                                                 reinterpret_cast<__nv_bfloat16*>(a->ln_out_bf16), a->ln_out_f32);
-    DICOW_CUDA_OK(ctx, cudaGetLastError());
+    DICOW_CUDA_OK(ctx, launch_step_kernel(ln_rows_kernel, dim3(a->rows), dim3(128), 0, stream, 1u, a->x, a->d, a->gamma, a->beta,
+                                          a->eps, reinterpret_cast<__nv_bfloat16*>(a->ln_out_bf16), a->ln_out_f32));
     return DICOW_OK;
   }
   if (!few_rows && (a->d % 8) == 0 && a->d <= 1280 && !(a->flags & 3) && (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 &&

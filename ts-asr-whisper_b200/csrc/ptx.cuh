@@ -557,4 +557,16 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (common.h: launch_step_kernel), calls griddep_launch() early (the
+// next kernel of the step may be scheduled as soon as every CTA of this one has got here) and griddep_wait() before it
+// touches anything an earlier kernel of the step wrote.  What a kernel does before the wait -- index arithmetic and
+// issuing the loads of its (immutable) weights -- overlaps the tail of its predecessor.  Both instructions are no-ops
+// for a launch without the attribute.  A kernel launched this way can be resident while its predecessors still run, so
+// everything the step's kernels exchange (x, q, ctx, h, the K/V cache, logits, ids, pos, unfinished) is read with
+// ld.global.cg (L2 only): an L1 line filled before the producer's store would otherwise be a stale hit.  Weights, biases
+// and tables are immutable (nc).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace dicow
