@@ -122,7 +122,10 @@ def test_decode_attention(ops, B, H, Tk, use_pos):
 # cluster of 2 / 4 / 8 CTAs (N = 1280 with K = 1280 / 5120 / 4096+), row tiles MT = 1..4, ragged N and tiny shapes
 DL_CASES = [(16, 3840, 1280, 0, True), (16, 1280, 1280, 2, False), (16, 1280, 5120, 2, False), (16, 5120, 1280, 1, True),
             (16, 51866, 1280, 3, True), (33, 1000, 384, 3, True), (64, 264, 256, 0, False), (1, 8, 32, 3, False),
-            (5, 1280, 1280, 0, True), (48, 384, 1536, 2, False), (2, 128, 128, 1, True), (16, 640, 8192, 3, False)]
+            (5, 1280, 1280, 0, True), (48, 384, 1536, 2, False), (2, 128, 128, 1, True), (16, 640, 8192, 3, False),
+            # LayerNorm prologue with K split over a cluster pair and several tiles per pass (the cross-attention q
+            # projection of the step), 17..32 rows with the prologue, a ragged last tile group
+            (16, 1280, 1280, 2, True), (20, 2560, 1280, 0, True), (32, 5120, 1280, 1, True), (16, 3000, 640, 3, True)]
 
 
 @pytest.mark.parametrize("M,N,K,epi,ln", DL_CASES)

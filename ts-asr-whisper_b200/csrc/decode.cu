@@ -73,6 +73,12 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
 __device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, uint2 v) {
   asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v),
+               "r"(cluster_mbar)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_all() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_all() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
@@ -155,11 +161,8 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkinnyPar
 //     meet in rank 0's shared memory (DSMEM) and are added in rank order (deterministic, no atomics);
 //   * columns >= n_split go to a second output (fused q | k,v projection: q to its buffer, k,v appended to the cache).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int DL_WARPS = 8;
-constexpr int DL_THREADS = DL_WARPS * 32;
-constexpr int DL_KBW = 5;         // 32-wide k-blocks per warp: K / ksplit <= DL_WARPS * DL_KBW * 32 = 1280
+constexpr int DL_MAX_KS = 1280;   // K / ksplit: the CTA's k-slice, held in registers as 32-wide k-blocks dealt to the warps
 constexpr int DL_MAX_KSPLIT = 8;  // portable cluster size
-constexpr int DL_LN_CLUSTER = 8;  // CTAs sharing one LayerNorm of the M rows (LN variant)
 
 struct DecLinParams {
   const float* x;  // LayerNorm source [M, K] fp32 (LN variant)
@@ -206,12 +209,23 @@ __device__ __forceinline__ void dl_store(const DecLinParams& p, int row, int n, 
   }
 }
 
-template <int MT, bool LN>
-__global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinParams p) {
+// NT = 8-column tiles a CTA multiplies AT ONCE (single pass, tiles_per_cta == NT): the layers' linears at M <= 32 take
+// NT = 2..4 so that ~one CTA per SM has its whole weight share in flight from its first instruction and the A slab is
+// staged 2-4 x less often (it was 1-2 x the weight bytes in L2 -> SM traffic); NT = 1 loops over tiles_per_cta tiles with
+// the next tile's weights prefetched (proj_out).
+// NW = warps per CTA (8 or 16): warp w multiplies k-blocks w, w + NW, ...  The single-pass variants take 16: a warp of
+// this kernel executes a few hundred dependent integer / address instructions around its loads, and with two warps per
+// scheduler nothing hides their latency (ncu, profiles/r02c_ncu_decode_linear.md: issue slots 10 % busy, "wait" stalls 20 %).
+template <int MT, bool LN, int NT, int NW>
+__global__ void __launch_bounds__(NW * 32) decode_linear_kernel(const DecLinParams p) {
+  constexpr int DL_WARPS = NW, DL_THREADS = NW * 32;
+  constexpr int DL_KBW = (DL_MAX_KS / 32 + NW - 1) / NW;  // k-blocks per warp: 5 (8 warps) or 3 (16 warps)
+  constexpr int TE = MT * 16 * 8;  // output elements of one tile
+  constexpr int GE = NT * TE;      // ... of the tiles of one pass
   extern __shared__ __align__(16) unsigned char dl_smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(dl_smem);
   float* red = reinterpret_cast<float*>(dl_smem + (size_t)MT * 16 * p.a_pitch * sizeof(__nv_bfloat16));
-  float* cpart = red + DL_WARPS * MT * 16 * 8;  // [ksplit - 1][MT * 16 * 8], used on cluster rank 0
+  float* cpart = red + DL_WARPS * GE;  // [ksplit - 1][GE], used on cluster rank 0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int krank = p.ksplit > 1 ? (int)cluster_ctarank() : 0;
@@ -224,8 +238,16 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
 
   // cluster launches (LayerNorm sharing, split K) write into peer CTAs' shared memory: arrive now, wait right before the
   // first remote store, so that "the peer has started" costs no latency
-  if (LN || p.ksplit > 1) cluster_arrive_all();
-  uint4 wv[DL_KBW], wn[DL_KBW];
+  __shared__ __align__(8) uint64_t split_bar;  // rank 0: counts the bytes of the peers' partial sums (split K)
+  if (p.ksplit > 1) {
+    if (krank == 0 && threadIdx.x == 0) {
+      mbar_init(&split_bar, 1);
+      mbar_arrive_expect_tx(&split_bar, (uint32_t)((p.ksplit - 1) * GE * sizeof(float)));
+      fence_barrier_init();
+    }
+    cluster_arrive_relaxed();  // (a release here is a MEMBAR.ALL.GPU: 10 % of the kernel's stall samples)
+  }
+  uint4 wv[NT][DL_KBW], wn[DL_KBW];
   auto load_w = [&](int tile, uint4(&w)[DL_KBW]) {
     const int nrow = tile * 8 + g;
     const bool ok = tile < tile_end && nrow < p.N;
@@ -237,112 +259,126 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
       if (ok && kb < kblocks) w[i] = ldg_stream_128(wrow + kb * 32);
     }
   };
-  load_w(tile_first, wv);  // in flight across the dependency wait
+#pragma unroll
+  for (int j = 0; j < NT; ++j) load_w(tile_first + j, wv[j]);  // in flight across the dependency wait
+  if constexpr (LN) {  // gamma | beta -> shared memory, once per CTA (fetched per use they were twenty load round trips in a row)
+    float* sGB = cpart + (size_t)(p.ksplit - 1) * GE;
+    const int nvec = p.K >> 2;
+    for (int c = threadIdx.x; c < 2 * nvec; c += DL_THREADS)
+      cp_async_cg_16(smem_u32(sGB + 4 * c), (c < nvec ? p.gamma : p.beta - p.K) + 4 * c);
+  }
   griddep_launch();
   griddep_wait();
 
   // ---- stage A (bf16) in shared memory: rows >= M are zero ----
   if constexpr (LN) {
-    // The LayerNorm of the M rows is shared by a cluster of DL_LN_CLUSTER CTAs (each needs ALL of A for its columns):
-    // rank r normalises rows [r * RPR, (r + 1) * RPR) -- one warp per row, two-pass statistics in registers -- and
-    // stores the bf16 row into the A slab of every CTA of the cluster through distributed shared memory.  Every CTA
-    // re-reading and re-normalising all rows instead costs 8x the L2 requests on the same 80 KB (measured: 14 us per
-    // layer instead of ~6 for the plain variant).
-    constexpr int RPR = MT * 16 / DL_LN_CLUSTER;  // rows per rank
-    const int crank = (int)cluster_ctarank();
+    // Opt-in form (fused_decode_step = "ln_prologue"); the default is the few-rows LayerNorm kernel in front of this one.
+    // Every CTA normalises the rows itself (one warp per row, two rows of a warp in flight, two-pass statistics in
+    // registers: the arithmetic of fddt_ln_kernel) and keeps the bf16 columns of its k-slice: 80 KB of fp32 rows from L2
+    // per CTA instead of 40 KB of bf16.  Measured at B = 16: 10.9-14.4 us per layer linear against 2.1 (LayerNorm kernel)
+    // + 4.0-6.3 us -- the ~160 CTAs re-reading the same rows cost more than the launch they replace.  (Round 1 shared the
+    // LayerNorm over a cluster of 8 through DSMEM instead: 15-17 us, half of it in the cluster barriers' fences.)
     const int nvec = p.K >> 2;  // K <= 1280: at most 10 float4 per lane
-    for (int r = max(p.M - m0, 0) + warp; r < MT * 16; r += DL_WARPS) {  // local zero rows (disjoint from the peers' writes)
-      __nv_bfloat16* srow = sA + (size_t)r * p.a_pitch;
-      for (int c = lane * 4; c < p.Ks; c += 128) *reinterpret_cast<uint2*>(srow + c) = make_uint2(0u, 0u);
-    }
-    const int r = crank * RPR + warp;
-    const bool mine = warp < RPR && m0 + r < p.M;
-    uint2 y[10];
-    if (mine) {
-      const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)(m0 + r) * p.ldx);
-      float4 v[10];
+    const int c_lo = kbase >> 2, c_hi = (kbase + p.Ks) >> 2;
+    const float4* sG = reinterpret_cast<const float4*>(cpart + (size_t)(p.ksplit - 1) * GE);  // gamma | beta, staged at kernel entry
+    const float4* sB = sG + nvec;
+    float4 v[2][10];
+    auto load_rows = [&](int r0) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = c < nvec ? __ldcg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float s = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int r = r0 + u * DL_WARPS;
+        const bool ok = r < MT * 16 && m0 + r < p.M;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)(ok ? m0 + r : 0) * p.ldx);
 #pragma unroll
-      for (int i = 0; i < 10; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      const float mean = warp_sum(s) / (float)p.K;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        if (lane + 32 * i < nvec) {
-          const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-          q += (a * a + b2 * b2) + (c * c + e * e);
+        for (int i = 0; i < 10; ++i) {
+          const int c = lane + 32 * i;
+          v[u][i] = (ok && c < nvec) ? __ldcg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      const float rstd = rsqrtf(warp_sum(q) / (float)p.K + p.eps);
+    };
+    load_rows(warp);
+    cp_async_wait_all();  // gamma / beta
+    __syncthreads();
+    for (int r0 = warp;;) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int c4 = lane + 32 * i;
-        y[i] = make_uint2(0u, 0u);
-        if (c4 < nvec) {
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
-          const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
-          const float y0 = fmaf((v[i].x - mean) * rstd, ga.x, be.x), y1 = fmaf((v[i].y - mean) * rstd, ga.y, be.y);
-          const float y2 = fmaf((v[i].z - mean) * rstd, ga.z, be.z), y3 = fmaf((v[i].w - mean) * rstd, ga.w, be.w);
-          y[i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+      for (int u = 0; u < 2; ++u) {
+        const int r = r0 + u * DL_WARPS;
+        if (r >= MT * 16) break;
+        __nv_bfloat16* srow = sA + (size_t)r * p.a_pitch;
+        if (m0 + r >= p.M) {  // rows past M multiply as zeros
+          for (int c = lane * 4; c < p.Ks; c += 128) *reinterpret_cast<uint2*>(srow + c) = make_uint2(0u, 0u);
+          continue;
         }
-      }
-    }
-    cluster_wait_all();  // every CTA of the cluster is running (arrival at kernel entry): its A slab may be written
-    if (mine) {
-      const uint32_t row_local = smem_u32(sA + (size_t)r * p.a_pitch);
-      for (int dst = 0; dst < DL_LN_CLUSTER; ++dst) {
-        const uint32_t row_remote = map_to_cta(row_local, (uint32_t)dst);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) sum += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+        const float mean = warp_sum(sum) / (float)p.K;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          if (lane + 32 * i < nvec) {
+            const float a = v[u][i].x - mean, b2 = v[u][i].y - mean, c = v[u][i].z - mean, e = v[u][i].w - mean;
+            q += (a * a + b2 * b2) + (c * c + e * e);
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)p.K + p.eps);
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
           const int c4 = lane + 32 * i;
-          if (c4 < nvec) st_cluster_v2(row_remote + (uint32_t)c4 * 8u, y[i]);
+          if (c4 >= c_lo && c4 < c_hi) {
+            const float4 ga = sG[c4], be = sB[c4];
+            const float y0 = fmaf((v[u][i].x - mean) * rstd, ga.x, be.x), y1 = fmaf((v[u][i].y - mean) * rstd, ga.y, be.y);
+            const float y2 = fmaf((v[u][i].z - mean) * rstd, ga.z, be.z), y3 = fmaf((v[u][i].w - mean) * rstd, ga.w, be.w);
+            *reinterpret_cast<uint2*>(srow + (size_t)(c4 - c_lo) * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+          }
         }
       }
+      r0 += 2 * DL_WARPS;
+      if (r0 >= MT * 16) break;
+      load_rows(r0);
     }
-    cluster_sync_all();  // release / acquire: the rows written by the peers are visible
   } else {
     // cp.async (L2 only, like ld.global.cg): every 16-byte piece of the slab is in flight at once.  The load + st.shared
     // loop this replaces compiled to one L2 round trip per piece and thread (ten in a row for 16 rows of K = 1280), which
     // was most of the duration of a layer's linear kernel.
     const int vec_per_row = p.Ks >> 3;
-    for (int i = threadIdx.x; i < MT * 16 * vec_per_row; i += DL_THREADS) {
-      const int r = i / vec_per_row, c = (i - r * vec_per_row) * 8;
-      __nv_bfloat16* dst = sA + (size_t)r * p.a_pitch + c;
-      if (m0 + r < p.M)
-        cp_async_cg_16(smem_u32(dst), p.A + (long long)(m0 + r) * p.lda + kbase + c);
-      else
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = warp; r < MT * 16; r += DL_WARPS) {  // a warp copies whole rows: no index division, 512 contiguous bytes per request
+      __nv_bfloat16* drow = sA + (size_t)r * p.a_pitch;
+      if (m0 + r < p.M) {
+        const __nv_bfloat16* srow = p.A + (long long)(m0 + r) * p.lda + kbase;
+        for (int c = lane; c < vec_per_row; c += 32) cp_async_cg_16(smem_u32(drow + c * 8), srow + c * 8);
+      } else {
+        for (int c = lane; c < vec_per_row; c += 32) *reinterpret_cast<uint4*>(drow + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     cp_async_wait_all();
   }
   // the KV-cache append position: one L2 read here instead of one per stored element after the multiply
   const long long pos_off = p.pos != nullptr ? (long long)__ldcg(p.pos) * p.pos_stride : 0ll;
   __syncthreads();
-  if (!LN && p.ksplit > 1) cluster_wait_all();
+  if (p.ksplit > 1) cluster_wait_all();
 
-  constexpr int NV = (MT * 16 * 8 + DL_THREADS - 1) / DL_THREADS;  // output elements per thread and tile
-  for (int tile = tile_first; tile < tile_end; ++tile) {
-    load_w(tile + 1, wn);  // next tile's weights stream in while this one is multiplied (zeros past the last tile)
+  constexpr int NV = (GE + DL_THREADS - 1) / DL_THREADS;  // output elements per thread and pass
+  for (int tile = tile_first; tile < tile_end; tile += NT) {
+    if constexpr (NT == 1) load_w(tile + 1, wn);  // next tile's weights stream in while this one is multiplied (zeros past the last tile)
     // bias and residual of the elements this thread stores: requested now, needed after the cross-warp / cluster sums
     float ebias[NV], eres[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int e = threadIdx.x + j * DL_THREADS;
-      const int row = m0 + (e >> 3), n = tile * 8 + (e & 7);
+      const int tj = e / TE, et = e - tj * TE;
+      const int row = m0 + (et >> 3), n = (tile + tj) * 8 + (et & 7);
       ebias[j] = eres[j] = 0.f;
-      if (krank == 0 && e < MT * 16 * 8 && row < p.M && n < p.N) {
+      if (krank == 0 && e < GE && tile + tj < tile_end && row < p.M && n < p.N) {
         if (p.bias != nullptr) ebias[j] = __ldg(p.bias + n);
         if (p.epilogue == DICOW_EPI_RESIDUAL_F32) eres[j] = __ldcg(p.resid + (long long)row * p.ldr + n);
       }
     }
-    float acc[MT][4];
+    float acc[NT][MT][4];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[j][m][0] = acc[j][m][1] = acc[j][m][2] = acc[j][m][3] = 0.f;
 #pragma unroll
     for (int i = 0; i < DL_KBW; ++i) {
       const int kb = warp + i * DL_WARPS;
@@ -352,17 +388,22 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
           const __nv_bfloat16* a0 = sA + (size_t)(m * 16 + g) * p.a_pitch + kb * 32 + t * 8;
           const uint4 lo = *reinterpret_cast<const uint4*>(a0);
           const uint4 hi = *reinterpret_cast<const uint4*>(a0 + 8 * (size_t)p.a_pitch);
-          mma_bf16_16816(acc[m], lo.x, hi.x, lo.y, hi.y, wv[i].x, wv[i].y);
-          mma_bf16_16816(acc[m], lo.z, hi.z, lo.w, hi.w, wv[i].z, wv[i].w);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            mma_bf16_16816(acc[j][m], lo.x, hi.x, lo.y, hi.y, wv[j][i].x, wv[j][i].y);
+            mma_bf16_16816(acc[j][m], lo.z, hi.z, lo.w, hi.w, wv[j][i].z, wv[j][i].w);
+          }
         }
       }
     }
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      float* r0 = red + ((size_t)warp * MT * 16 + m * 16 + g) * 8 + 2 * t;
-      r0[0] = acc[m][0], r0[1] = acc[m][1];
-      r0[64] = acc[m][2], r0[65] = acc[m][3];  // row g + 8
-    }
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float* r0 = red + (size_t)warp * GE + j * TE + (m * 16 + g) * 8 + 2 * t;
+        r0[0] = acc[j][m][0], r0[1] = acc[j][m][1];
+        r0[64] = acc[j][m][2], r0[65] = acc[j][m][3];  // row g + 8
+      }
     __syncthreads();
     // cross-warp sums; with split K the partial sums of ranks 1.. meet in rank 0's shared memory and are added in rank order
     float v[NV];
@@ -370,26 +411,33 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(const DecLinP
     for (int j = 0; j < NV; ++j) {
       const int e = threadIdx.x + j * DL_THREADS;
       v[j] = 0.f;
-      if (e < MT * 16 * 8) {
+      if (e < GE) {
 #pragma unroll
-        for (int w = 0; w < DL_WARPS; ++w) v[j] += red[(size_t)w * MT * 16 * 8 + e];
-        if (krank != 0) st_cluster_f32(map_to_cta(smem_u32(cpart + (size_t)(krank - 1) * MT * 16 * 8 + e), 0), v[j]);
+        for (int w = 0; w < DL_WARPS; ++w) v[j] += red[(size_t)w * GE + e];
+        // split K: the partial sum travels to rank 0's shared memory as an asynchronous store that reports its bytes to
+        // rank 0's mbarrier -- no cluster barrier (and none of its memory fences) after the multiply; ranks > 0 are done
+        if (krank != 0)
+          st_async_b32(map_to_cta(smem_u32(cpart + (size_t)(krank - 1) * GE + e), 0), __float_as_uint(v[j]),
+                       map_to_cta(smem_u32(&split_bar), 0));
       }
     }
-    if (p.ksplit > 1) cluster_sync_all();
+    if (p.ksplit > 1 && krank == 0) mbar_wait(&split_bar, 0);  // (split K is single-pass: one phase)
     if (krank == 0) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int e = threadIdx.x + j * DL_THREADS;
-        if (e < MT * 16 * 8) {
-          for (int r = 1; r < p.ksplit; ++r) v[j] += cpart[(size_t)(r - 1) * MT * 16 * 8 + e];
-          dl_store(p, m0 + (e >> 3), tile * 8 + (e & 7), v[j], ebias[j], eres[j], pos_off);
+        const int tj = e / TE, et = e - tj * TE;
+        if (e < GE && tile + tj < tile_end) {
+          for (int r = 1; r < p.ksplit; ++r) v[j] += cpart[(size_t)(r - 1) * GE + e];
+          dl_store(p, m0 + (et >> 3), (tile + tj) * 8 + (et & 7), v[j], ebias[j], eres[j], pos_off);
         }
       }
     }
-    __syncthreads();  // red is rewritten by the next tile
+    if constexpr (NT == 1) {
+      __syncthreads();  // red is rewritten by the next tile
 #pragma unroll
-    for (int k = 0; k < DL_KBW; ++k) wv[k] = wn[k];
+      for (int k = 0; k < DL_KBW; ++k) wv[0][k] = wn[k];
+    }
   }
 }
 
@@ -1087,11 +1135,11 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
   // split K over a cluster until a CTA's slice fits the per-warp register slab (<= 1280), then once more while the grid
   // would leave half of the SMs idle; slices stay multiples of 32.  The two-output form keeps K whole (fused q|k,v: N = 3d).
   int ksplit = 1;
-  while ((a->K / ksplit > DL_WARPS * DL_KBW * 32 || (a->K % ksplit) != 0 || ((a->K / ksplit) % 32) != 0) && ksplit < DL_MAX_KSPLIT) ++ksplit;
-  DICOW_REQUIRE(ctx, a->K / ksplit <= DL_WARPS * DL_KBW * 32 && (a->K % ksplit) == 0 && ((a->K / ksplit) % 32) == 0,
+  while ((a->K / ksplit > DL_MAX_KS || (a->K % ksplit) != 0 || ((a->K / ksplit) % 32) != 0) && ksplit < DL_MAX_KSPLIT) ++ksplit;
+  DICOW_REQUIRE(ctx, a->K / ksplit <= DL_MAX_KS && (a->K % ksplit) == 0 && ((a->K / ksplit) % 32) == 0,
                 "dicow_decode_linear: K = %d cannot be split into <= 8 slices of <= 1280 (multiples of 32)", a->K);
   if (a->out2 != nullptr) DICOW_REQUIRE(ctx, ksplit == 1, "dicow_decode_linear: two outputs need K <= 1280");
-  if (!ln && a->out2 == nullptr && tiles * ksplit < 2 * ctx->num_sms && 2 * ksplit <= DL_MAX_KSPLIT && a->K / ksplit >= 640 &&
+  if (a->out2 == nullptr && tiles * ksplit < 2 * ctx->num_sms && 2 * ksplit <= DL_MAX_KSPLIT && a->K / ksplit >= 640 &&
       ((a->K / (2 * ksplit)) % 32) == 0)
     ksplit *= 2;
   DecLinParams p{};
@@ -1102,7 +1150,24 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
   p.resid = a->resid, p.ldr = a->ldr;
   p.n_split = a->out2 != nullptr ? a->n_split : a->N, p.out2 = a->out2, p.ldo2 = a->ldo2, p.pos = a->pos, p.pos_stride = a->pos_stride;
   p.ksplit = ksplit, p.Ks = a->K / ksplit, p.a_pitch = p.Ks + 32;
-  const size_t smem = (size_t)MT * 16 * p.a_pitch * 2 + (size_t)(DL_WARPS + ksplit - 1) * MT * 16 * 8 * sizeof(float);
+  // tiles per pass: as many (<= 4) as still leave about one CTA per SM, for the layers' linears of a greedy / small-beam
+  // step (no LayerNorm prologue, M <= 32); DICOW_DL_NT=1 restores one tile per pass
+  static const int nt_cap = [] {
+    const char* e = getenv("DICOW_DL_NT");
+    return e != nullptr && e[0] >= '1' && e[0] <= '4' ? e[0] - '0' : 3;
+  }();
+  int NT = 1;
+  if (msplit == 1)
+    for (int c = nt_cap; c >= 2; --c)
+      if (ceil_div(tiles, c) * ksplit * 10 >= ctx->num_sms * 9 && ceil_div(tiles, c) * ksplit <= 2 * ctx->num_sms) {
+        NT = c;
+        break;
+      }
+  // 8 warps.  16 (3 k-blocks per warp instead of 5) measured slower for every single-pass shape: fc1 7.4 -> 9.3 us, the
+  // fused q|k,v projection 6.1 -> 8.1 us, the decode step 0.318 -> 0.344 ms (gpurun_out/s3_decode_nt.json).
+  constexpr int NW = 8;
+  const size_t smem = (size_t)MT * 16 * p.a_pitch * 2 + (size_t)(NW + ksplit - 1) * NT * MT * 16 * 8 * sizeof(float) +
+                      (ln ? 2 * (size_t)a->K * sizeof(float) : 0);
   DICOW_REQUIRE(ctx, smem <= (size_t)ctx->max_smem_optin, "dicow_decode_linear: %zu bytes of shared memory needed", smem);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   auto go = [&](auto kern) -> int {
@@ -1112,28 +1177,34 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
     // loads in flight more than it needs residency)
     // one wave: a CTA takes as many consecutive tiles as it needs for the grid to fit the resident CTA slots
     int per_sm = 1;
-    DICOW_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DL_THREADS, smem));
+    DICOW_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    p.tiles_per_cta = ksplit > 1 ? 1 : ceil_div(tiles * msplit, per_sm * ctx->num_sms);
-    int grid = ceil_div(tiles, p.tiles_per_cta) * ksplit;
-    unsigned cluster = (unsigned)ksplit;
-    if (ln) {  // clusters of DL_LN_CLUSTER CTAs share the LayerNorm; surplus CTAs of the last cluster own no tile
-      cluster = DL_LN_CLUSTER;
-      grid = ceil_div(grid, DL_LN_CLUSTER) * DL_LN_CLUSTER;
-    }
-    DICOW_CUDA_OK(ctx, launch_step_kernel(kern, dim3(grid, msplit), dim3(DL_THREADS), smem, stream, cluster, p));
+    p.tiles_per_cta = NT > 1 ? NT : ksplit > 1 ? 1 : ceil_div(tiles * msplit, per_sm * ctx->num_sms);
+    const int grid = ceil_div(tiles, p.tiles_per_cta) * ksplit;
+    const unsigned cluster = (unsigned)ksplit;
+    DICOW_CUDA_OK(ctx, launch_step_kernel(kern, dim3(grid, msplit), dim3(NW * 32), smem, stream, cluster, p));
     return DICOW_OK;
   };
-  switch (MT * 2 + (ln ? 1 : 0)) {
-    case 2: return go(decode_linear_kernel<1, false>);
-    case 3: return go(decode_linear_kernel<1, true>);
-    case 4: return go(decode_linear_kernel<2, false>);
-    case 5: return go(decode_linear_kernel<2, true>);
-    case 6: return go(decode_linear_kernel<3, false>);
-    case 7: return go(decode_linear_kernel<3, true>);
-    case 8: return go(decode_linear_kernel<4, false>);
-    default: return go(decode_linear_kernel<4, true>);
+  switch (NT * 16 + MT * 2 + (ln ? 1 : 0)) {
+    case 16 + 2: return go(decode_linear_kernel<1, false, 1, NW>);
+    case 16 + 3: return go(decode_linear_kernel<1, true, 1, NW>);
+    case 16 + 4: return go(decode_linear_kernel<2, false, 1, NW>);
+    case 16 + 5: return go(decode_linear_kernel<2, true, 1, NW>);
+    case 32 + 2: return go(decode_linear_kernel<1, false, 2, NW>);
+    case 32 + 3: return go(decode_linear_kernel<1, true, 2, NW>);
+    case 32 + 4: return go(decode_linear_kernel<2, false, 2, NW>);
+    case 32 + 5: return go(decode_linear_kernel<2, true, 2, NW>);
+    case 48 + 2: return go(decode_linear_kernel<1, false, 3, NW>);
+    case 48 + 3: return go(decode_linear_kernel<1, true, 3, NW>);
+    case 48 + 4: return go(decode_linear_kernel<2, false, 3, NW>);
+    case 48 + 5: return go(decode_linear_kernel<2, true, 3, NW>);
+    case 64 + 2: return go(decode_linear_kernel<1, false, 4, NW>);
+    case 64 + 3: return go(decode_linear_kernel<1, true, 4, NW>);
+    case 64 + 4: return go(decode_linear_kernel<2, false, 4, NW>);
+    case 64 + 5: return go(decode_linear_kernel<2, true, 4, NW>);
+    default: DICOW_REQUIRE(ctx, false, "dicow_decode_linear: no kernel for MT=%d NT=%d NW=%d ln=%d", MT, NT, NW, (int)ln);
   }
+  return DICOW_OK;
 }
 
 extern "C" int dicow_decode_attention_bf16(dicow_handle_t h, const dicow_decode_attention_args_t* a, void* stream_) {

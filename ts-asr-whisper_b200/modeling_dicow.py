@@ -412,7 +412,7 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
     # step graphs are captured once per batch size; set False to launch the step kernels eagerly (debugging)
     use_cuda_graphs = True
     # True: fused q|k,v projection, cluster split-K linear layers, few-rows LayerNorm kernel; "ln_prologue": LayerNorm as
-    # the prologue of the linear kernel instead; False: one kernel per operation (_decode_step_unfused), the baseline
+    # the prologue of the linear kernel instead (measured slower); False: one kernel per operation (_decode_step_unfused)
     fused_decode_step = True
     # EXPERIMENTAL, off by default: greedy steps of <= 16 rows run the decoder layers as ONE persistent kernel with grid
     # barriers between the phases (csrc/decode_mega.cu; DICOW_DECODE_MEGA=1 or decode_megakernel = True).  Token-parity green,
@@ -718,11 +718,14 @@ class DiCoWForConditionalGeneration(PreTrainedModel):
             if st.beams > 1:
                 raise NotImplementedError("beam search runs on the fused decode step (d_model % 32 == 0)")
             return self._decode_step_unfused(st, w, sample, gen)
-        ln_prologue = self.fused_decode_step == "ln_prologue" and d <= 1280  # the prologue holds a row in registers
+        # LayerNorm: the few-rows LayerNorm kernel in front of the linear kernel (default), or ("ln_prologue") as the
+        # prologue of the linear kernel, every CTA normalising the <= 32 rows itself (a row is held in registers: d <= 1280).
+        # The prologue is measured slower in both of its forms -- shared over a cluster of 8 through DSMEM (round 1: 15-17 us
+        # per layer linear) and per CTA (round 2: 10.9-14.4 us against 2.1 + 4.0-6.3 us) -- ~160 CTAs re-reading the same
+        # 80 KB of fp32 rows from L2 cost more than the LayerNorm launch they replace
+        ln_prologue = self.fused_decode_step == "ln_prologue" and d <= 1280 and B <= 32
 
         def ln_linear(W, out, g, b, **kw):
-            """LayerNorm(x) -> Linear: LayerNorm as the prologue of the linear kernel, or (default: measured faster,
-            DESIGN.md section 4.2) the few-rows LayerNorm kernel followed by the linear kernel on its bf16 output"""
             if ln_prologue:
                 return ops.decode_linear(W, out, x=st.x, gamma=g, beta=b, **kw)
             ops.fddt_layernorm(st.x, gamma=g, beta=b, ln_out_bf16=st.ln)
