@@ -125,7 +125,9 @@ DL_CASES = [(16, 3840, 1280, 0, True), (16, 1280, 1280, 2, False), (16, 1280, 51
             (5, 1280, 1280, 0, True), (48, 384, 1536, 2, False), (2, 128, 128, 1, True), (16, 640, 8192, 3, False),
             # LayerNorm prologue with K split over a cluster pair and several tiles per pass (the cross-attention q
             # projection of the step), 17..32 rows with the prologue, a ragged last tile group
-            (16, 1280, 1280, 2, True), (20, 2560, 1280, 0, True), (32, 5120, 1280, 1, True), (16, 3000, 640, 3, True)]
+            (16, 1280, 1280, 2, True), (20, 2560, 1280, 0, True), (32, 5120, 1280, 1, True), (16, 3000, 640, 3, True),
+            # the beam-search step at 60 hypotheses: two 32-row CTAs per tile group, several tiles per pass, K split 1 / 2 / 4
+            (60, 5120, 1280, 1, False), (60, 1280, 5120, 2, False), (60, 1280, 1280, 2, False), (60, 3840, 1280, 0, True)]
 
 
 @pytest.mark.parametrize("M,N,K,epi,ln", DL_CASES)

@@ -1150,19 +1150,22 @@ extern "C" int dicow_decode_linear(dicow_handle_t h, const dicow_decode_linear_a
   p.resid = a->resid, p.ldr = a->ldr;
   p.n_split = a->out2 != nullptr ? a->n_split : a->N, p.out2 = a->out2, p.ldo2 = a->ldo2, p.pos = a->pos, p.pos_stride = a->pos_stride;
   p.ksplit = ksplit, p.Ks = a->K / ksplit, p.a_pitch = p.Ks + 32;
-  // tiles per pass: as many (<= 4) as still leave about one CTA per SM, for the layers' linears of a greedy / small-beam
-  // step (no LayerNorm prologue, M <= 32); DICOW_DL_NT=1 restores one tile per pass
+  // tiles per pass: as many (<= 3; DICOW_DL_NT=1..4 overrides the cap) as still leave about one CTA per SM -- the layers'
+  // linears of a step; proj_out (thousands of tiles) keeps one tile per pass and loops
   static const int nt_cap = [] {
     const char* e = getenv("DICOW_DL_NT");
     return e != nullptr && e[0] >= '1' && e[0] <= '4' ? e[0] - '0' : 3;
   }();
+  // (beam search, M > 32: two 32-row CTAs per tile group.  One tile per pass staged an 84 KB slab per 20 KB of weights --
+  // 1 280 CTAs for fc1 at 60 hypotheses, 107 MB of L2 -> SM traffic for 13 MB of weights)
   int NT = 1;
-  if (msplit == 1)
-    for (int c = nt_cap; c >= 2; --c)
-      if (ceil_div(tiles, c) * ksplit * 10 >= ctx->num_sms * 9 && ceil_div(tiles, c) * ksplit <= 2 * ctx->num_sms) {
-        NT = c;
-        break;
-      }
+  for (int c = nt_cap; c >= 2; --c) {
+    const int ctas = ceil_div(tiles, c) * ksplit * msplit;
+    if (ctas * 10 >= ctx->num_sms * 9 && ctas <= (msplit > 1 ? 3 : 2) * ctx->num_sms) {
+      NT = c;
+      break;
+    }
+  }
   // 8 warps.  16 (3 k-blocks per warp instead of 5) measured slower for every single-pass shape: fc1 7.4 -> 9.3 us, the
   // fused q|k,v projection 6.1 -> 8.1 us, the decode step 0.318 -> 0.344 ms (gpurun_out/s3_decode_nt.json).
   constexpr int NW = 8;
