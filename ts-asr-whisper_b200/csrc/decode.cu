@@ -242,7 +242,6 @@ __global__ void __launch_bounds__(NW * 32) decode_linear_kernel(const DecLinPara
   if (p.ksplit > 1) {
     if (krank == 0 && threadIdx.x == 0) {
       mbar_init(&split_bar, 1);
-      mbar_arrive_expect_tx(&split_bar, (uint32_t)((p.ksplit - 1) * GE * sizeof(float)));
       fence_barrier_init();
     }
     cluster_arrive_relaxed();  // (a release here is a MEMBAR.ALL.GPU: 10 % of the kernel's stall samples)
@@ -356,7 +355,12 @@ __global__ void __launch_bounds__(NW * 32) decode_linear_kernel(const DecLinPara
   // the KV-cache append position: one L2 read here instead of one per stored element after the multiply
   const long long pos_off = p.pos != nullptr ? (long long)__ldcg(p.pos) * p.pos_stride : 0ll;
   __syncthreads();
-  if (p.ksplit > 1) cluster_wait_all();
+  if (p.ksplit > 1) {
+    // the one arrival of the phase, with the byte count of the peers' partial sums (bytes that land before this are
+    // counted against it: the transaction count may run negative)
+    if (krank == 0 && threadIdx.x == 0) mbar_arrive_expect_tx(&split_bar, (uint32_t)((p.ksplit - 1) * GE * sizeof(float)));
+    cluster_wait_all();
+  }
 
   constexpr int NV = (GE + DL_THREADS - 1) / DL_THREADS;  // output elements per thread and pass
   for (int tile = tile_first; tile < tile_end; tile += NT) {
@@ -926,6 +930,7 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   const int b = (int)blockIdx.x / csplit;
   const int rank = csplit > 1 ? (int)cluster_ctarank() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  if (csplit > 1) cluster_arrive_relaxed();  // "this CTA runs": waited for before the first store into rank 0's shared memory
   griddep_launch();
   griddep_wait();
   const int len = p.pos != nullptr ? (__ldcg(p.pos) + 1) : p.cur_len;  // tokens in the sequence so far
@@ -1009,6 +1014,8 @@ __global__ void __launch_bounds__(512) logits_rules_argmax_kernel(const RulesPar
   }
   if (lane == 0) s_text[warp] = bt, s_ts[warp] = bs, s_max[warp] = tmax, s_sum[warp] = tsum;
   __syncthreads();
+  if (csplit > 1) cluster_wait_all();  // every CTA of the cluster has started (compute-sanitizer: a store into the shared
+                                       // memory of a CTA that "might not have entered yet" otherwise)
   if (tid == 0) {
     for (int w = 1; w < nw; ++w) {
       bt = best_of(bt, s_text[w]);
